@@ -1,0 +1,115 @@
+/* psb.h -- C ABI of the B200 batch engine for PS signatures / EL PASSO (libpsb.so).
+ *
+ * The reference (Zhiyi-Zhang/PS-Signature-and-EL-PASSO) has no plugin or FFI mechanism: its hot
+ * path is reached through three C++ classes that call mcl directly.  This header is
+ * the boundary a maintainer binds instead of those mcl calls for BATCHED work; each entry point
+ * cites the reference interface it replaces.  Conventions are modelled on mcl's own C API
+ * (third-parties/mcl/include/mcl/bn.h:78-110): PODs are arrays of uint64_t holding little-endian
+ * limbs in MONTGOMERY form exactly as mcl keeps them in memory, so `std::vector<G1>::data()` etc.
+ * can be passed without conversion:
+ *     Fp  6 x u64   Fr  4 x u64   G1 18 x u64 (Jacobian x,y,z)   G2 36 x u64   GT 72 x u64
+ * z == 0 is the point at infinity.  int returns: 0 = ok, < 0 = error (psb_last_error()).
+ * Per-lane cryptographic failure is DATA (verdict byte 0), never an error.
+ * There is no CPU fallback: every entry fails with PSB_ERR_CUDA when no usable GPU is present.
+ */
+#ifndef PSB_H_
+#define PSB_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSB_CURVE_BLS12_381 5 /* = MCL_BLS12_381 (mcl/include/mcl/curve_type.h:91) */
+
+#define PSB_OK 0
+#define PSB_ERR_ARG (-1)
+#define PSB_ERR_CUDA (-2)
+#define PSB_ERR_NOT_INIT (-3)
+#define PSB_ERR_UNSUPPORTED (-4)
+#define PSB_ERR_NOMEM (-5)
+
+typedef struct psb_key psb_key;
+
+/* Replaces mcl::bn::initPairing(mcl::BLS12_381) (mcl/include/mcl/bn.hpp:2208) for the batch path.
+ * devices = CUDA ordinals to shard over (NULL/0 -> device 0 only).  One host worker thread and
+ * one stream per device; no inter-device communication. */
+int psb_init(int curve, const int* devices, int ndev);
+void psb_shutdown(void);
+int psb_num_devices(void);
+const char* psb_last_error(void);
+/* number of kernels this library has launched since psb_init (for the bench's gpu_launches) */
+uint64_t psb_launch_count(void);
+
+/* Public key of the batch = PSPubKey (src/ps-encoding.h:111-133): g, gg, XX, Y[n], YY[n]; all
+ * points may have any z (they are normalised once here).  X_secret = g^x, the PSSigner secret
+ * m_sk_X (src/ps-signer.h), or NULL for verify-only keys.  Builds the fixed-base window tables
+ * (idea: mcl/include/mcl/window_method.hpp:68-108) in HBM on every device.
+ * window_bits: 0 = default (16), else 4..16. */
+psb_key* psb_key_create(const uint64_t* g, const uint64_t* gg, const uint64_t* XX, const uint64_t* Y,
+                        const uint64_t* YY, size_t n, const uint64_t* X_secret, int window_bits);
+void psb_key_destroy(psb_key* key);
+size_t psb_key_num_attributes(const psb_key* key);
+size_t psb_key_table_bytes(const psb_key* key);
+
+/* Batched PSVerifier::verify (src/ps-verifier.cc:13-35) == PSRequester::verify
+ * (src/ps-requester.cc:115-137).  Lane j: sig1[j], sig2[j] and n attributes given either as
+ * strings (attr_blob + attr_off[N*n+1], attribute i of lane j = blob[off[j*n+i] .. off[j*n+i+1]))
+ * hashed on the device like Fr::setHashOf, or as precomputed scalars m (N*n Fr, Montgomery; used
+ * when attr_blob == NULL).  verdict[j] = 1 iff sig1 != 0 and e(sig1, XX + sum m_i YY_i) == e(sig2, gg).
+ * gt (optional, N x 72 u64) receives e(sig1,K) * e(sig2,gg)^-1 = lhs * unitaryInv(rhs). */
+int psb_verify(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* sig2,
+               const uint8_t* attr_blob, const uint64_t* attr_off, const uint64_t* m,
+               uint8_t* verdict, uint64_t* gt);
+
+/* Same computation with every buffer already resident in the memory of device `dev_index`
+ * (index into the psb_init list); launches on `stream` (a cudaStream_t, NULL = the library's own
+ * stream) and does not synchronise.  `ws` = device scratch of psb_verify_ws_bytes(key, N) bytes. */
+size_t psb_verify_ws_bytes(const psb_key* key, size_t N);
+int psb_verify_dev(psb_key* key, int dev_index, size_t N, const uint64_t* d_sig1, const uint64_t* d_sig2,
+                   const uint8_t* d_attr_blob, const uint64_t* d_attr_off, const uint64_t* d_m,
+                   uint8_t* d_verdict, uint64_t* d_gt, void* d_ws, void* stream);
+
+/* Batched PSRequester::randomize_credential (src/ps-requester.cc:139-148) with host-supplied
+ * scalars t (N Fr, Montgomery): out = (t*sig1, t*sig2), NORMALISED (z = 1; infinity = all zero).
+ * ser (optional, N x 96 bytes) = mcl serialisation of out1 || out2 (ec.hpp:849-896). */
+int psb_randomize(size_t N, const uint64_t* sig1, const uint64_t* sig2, const uint64_t* t,
+                  uint64_t* out1, uint64_t* out2, uint8_t* ser);
+
+/* Batched PSSigner::el_passo_provide_id (src/ps-signer.cc:63-146): NIZK check of the request
+ * (A, c, rs[rs_per_lane], attributes with "" = hidden, associated data), then
+ * sig = (u*g, u*(X + A + sum_plain H(attr_i) Y_i)) with host-supplied u (N Fr, Montgomery).
+ * verdict[j] = NIZK result; sig1/sig2 normalised (all-zero when the NIZK fails); ser optional. */
+int psb_provide_id(psb_key* key, size_t N, const uint64_t* A, const uint64_t* c, const uint64_t* rs,
+                   size_t rs_per_lane, const uint8_t* attr_blob, const uint64_t* attr_off,
+                   const uint8_t* ad_blob, const uint64_t* ad_off, const uint64_t* u,
+                   uint8_t* verdict, uint64_t* sig1, uint64_t* sig2, uint8_t* ser);
+
+/* Batched PSVerifier::el_passo_verify_id (src/ps-verifier.cc:37-138; with_id = 1) and
+ * el_passo_verify_id_without_id_retrieval (:140-212; with_id = 0, E1/E2/y/g/h ignored).
+ * service_pt = hashAndMapToG1(service_name), one value per batch computed by the host. */
+int psb_verify_id(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* sig2, const uint64_t* k,
+                  const uint64_t* phi, const uint64_t* E1, const uint64_t* E2, const uint64_t* c,
+                  const uint64_t* rs, size_t rs_per_lane, const uint8_t* attr_blob,
+                  const uint64_t* attr_off, const uint8_t* ad_blob, const uint64_t* ad_off,
+                  const uint64_t* service_pt, const uint64_t* y, const uint64_t* g, const uint64_t* h,
+                  int with_id, uint8_t* verdict);
+
+/* Batched mcl::bn::pairing (bn.hpp:1711-1715): out[j] = e(P[j], Q[j]), N x 72 u64. */
+int psb_pairing(size_t N, const uint64_t* P, const uint64_t* Q, uint64_t* out);
+
+/* Element-wise arithmetic probe for parity tests (ops in csrc/testops.cuh); one GPU thread per
+ * element.  a/b/c/out are host arrays of u32 words with the shapes psb_test_op_shape reports. */
+int psb_test_op_shape(int op, int shape[4]);
+int psb_test_op(int op, size_t n, const uint32_t* a, const uint32_t* b, const uint32_t* c, uint32_t* out);
+
+/* Micro-benchmarks (device-timed, CUDA events): returns milliseconds for `iters` dependent
+ * operations per thread over blocks x threads; kind: 0 = Fp mul, 1 = Fp sqr, 2 = Fp2 mul,
+ * 3 = Fp12 mul, 4 = raw mad.lo/mad.hi issue-rate probe, 5 = mad.wide probe. */
+double psb_microbench(int kind, int blocks, int threads, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSB_H_ */

@@ -1,0 +1,190 @@
+// curve.cuh -- G1 = E(Fp): y^2 = x^3 + 4 and G2 = E'(Fp2): y^2 = x^3 + 4(1+i), Jacobian coordinates.
+//
+// Replaces for the batched path mcl's EcT (reference: third-parties/mcl/include/mcl/ec.hpp:138-284
+// dblJacobi/addJacobi, :77-88 normalizeJacobi, :799 isZero <=> z == 0) and its scalar
+// multiplications (ec.hpp:1124-1139 mulArray, :1466-1523 GLV1; bn.hpp:765-860 GLV2).  Raw layout
+// = mcl's: (x, y, z) Montgomery limbs, z == 0 is the point at infinity, z == 1 after normalisation.
+// Internal formulas and schedules are our own; outputs are compared in canonical (normalised or
+// serialised) form only.
+#pragma once
+#include "tower.cuh"
+
+namespace psb {
+
+// ---- uniform field interface (overloads on Fp / Fp2) -------------------------------------------
+PSB_HD PSB_INL void f_add(Fp& r, const Fp& a, const Fp& b) { fp_add(r, a, b); }
+PSB_HD PSB_INL void f_sub(Fp& r, const Fp& a, const Fp& b) { fp_sub(r, a, b); }
+PSB_HD PSB_INL void f_dbl(Fp& r, const Fp& a) { fp_dbl(r, a); }
+PSB_HD PSB_INL void f_neg(Fp& r, const Fp& a) { fp_neg(r, a); }
+PSB_HD PSB_INL void f_mul(Fp& r, const Fp& a, const Fp& b) { fp_mul(r, a, b); }
+PSB_HD PSB_INL void f_sqr(Fp& r, const Fp& a) { fp_sqr(r, a); }
+PSB_HD PSB_INL void f_inv(Fp& r, const Fp& a) { fp_inv(r, a); }
+PSB_HD PSB_INL bool f_is_zero(const Fp& a) { return fp_is_zero(a); }
+PSB_HD PSB_INL bool f_eq(const Fp& a, const Fp& b) { return fp_eq(a, b); }
+PSB_HD PSB_INL void f_set_zero(Fp& r) { fp_set_zero(r); }
+PSB_HD PSB_INL void f_set_one(Fp& r) { fp_set_one(r); }
+PSB_HD PSB_INL void f_cmov(Fp& r, const Fp& a, bool c) { fp_cmov(r, a, c); }
+
+PSB_HD PSB_INL void f_add(Fp2& r, const Fp2& a, const Fp2& b) { fp2_add(r, a, b); }
+PSB_HD PSB_INL void f_sub(Fp2& r, const Fp2& a, const Fp2& b) { fp2_sub(r, a, b); }
+PSB_HD PSB_INL void f_dbl(Fp2& r, const Fp2& a) { fp2_dbl(r, a); }
+PSB_HD PSB_INL void f_neg(Fp2& r, const Fp2& a) { fp2_neg(r, a); }
+PSB_HD PSB_INL void f_mul(Fp2& r, const Fp2& a, const Fp2& b) { fp2_mul(r, a, b); }
+PSB_HD PSB_INL void f_sqr(Fp2& r, const Fp2& a) { fp2_sqr(r, a); }
+PSB_HD PSB_INL void f_inv(Fp2& r, const Fp2& a) { fp2_inv(r, a); }
+PSB_HD PSB_INL bool f_is_zero(const Fp2& a) { return fp2_is_zero(a); }
+PSB_HD PSB_INL bool f_eq(const Fp2& a, const Fp2& b) { return fp2_eq(a, b); }
+PSB_HD PSB_INL void f_set_zero(Fp2& r) { fp2_set_zero(r); }
+PSB_HD PSB_INL void f_set_one(Fp2& r) { fp2_set_one(r); }
+PSB_HD PSB_INL void f_cmov(Fp2& r, const Fp2& a, bool c) { fp2_cmov(r, a, c); }
+
+template <class F> struct Jac { F x, y, z; };   // mcl G1 / G2 object layout
+template <class F> struct Aff { F x, y; };      // table entry / normalised input (never infinity)
+typedef Jac<Fp> G1J;
+typedef Jac<Fp2> G2J;
+typedef Aff<Fp> G1A;
+typedef Aff<Fp2> G2A;
+
+template <class F> PSB_HD PSB_INL bool pt_is_zero(const Jac<F>& P) { return f_is_zero(P.z); }
+template <class F> PSB_HD PSB_INL void pt_set_zero(Jac<F>& P) { f_set_zero(P.x); f_set_zero(P.y); f_set_zero(P.z); }
+template <class F> PSB_HD PSB_INL void pt_neg(Jac<F>& R, const Jac<F>& P) { R.x = P.x; f_neg(R.y, P.y); R.z = P.z; }
+template <class F> PSB_HD PSB_INL void pt_from_aff(Jac<F>& R, const Aff<F>& P) { R.x = P.x; R.y = P.y; f_set_one(R.z); }
+
+// 2P, a = 0 (dbl-2009-l: 2M + 5S)
+template <class F>
+PSB_HD PSB_NOINL void pt_dbl(Jac<F>& R, const Jac<F>& P) {
+  F A, B, C, D, E, t;
+  f_sqr(A, P.x);
+  f_sqr(B, P.y);
+  f_sqr(C, B);
+  f_add(t, P.x, B); f_sqr(t, t); f_sub(t, t, A); f_sub(t, t, C); f_dbl(D, t);   // D = 2((X+B)^2 - A - C)
+  f_dbl(E, A); f_add(E, E, A);                                                   // E = 3A
+  f_mul(t, P.y, P.z); f_dbl(R.z, t);                                             // Z3 = 2YZ (0 stays 0)
+  f_sqr(t, E); f_sub(t, t, D); f_sub(R.x, t, D);                                 // X3 = E^2 - 2D
+  f_sub(t, D, R.x); f_mul(t, t, E);
+  f_dbl(C, C); f_dbl(C, C); f_dbl(C, C);                                         // 8C
+  f_sub(R.y, t, C);
+}
+
+// P + Q, both Jacobian (add-2007-bl with the exceptional cases of mcl addJacobi, ec.hpp:210-284)
+template <class F>
+PSB_HD PSB_NOINL void pt_add(Jac<F>& R, const Jac<F>& P, const Jac<F>& Q) {
+  if (pt_is_zero(P)) { R = Q; return; }
+  if (pt_is_zero(Q)) { R = P; return; }
+  F Z1Z1, Z2Z2, U1, U2, S1, S2, H, I, J, r, V, t;
+  f_sqr(Z1Z1, P.z);
+  f_sqr(Z2Z2, Q.z);
+  f_mul(U1, P.x, Z2Z2);
+  f_mul(U2, Q.x, Z1Z1);
+  f_mul(S1, P.y, Q.z); f_mul(S1, S1, Z2Z2);
+  f_mul(S2, Q.y, P.z); f_mul(S2, S2, Z1Z1);
+  f_sub(H, U2, U1);
+  f_sub(r, S2, S1);
+  if (f_is_zero(H)) {
+    if (f_is_zero(r)) { pt_dbl(R, P); } else { pt_set_zero(R); }
+    return;
+  }
+  f_dbl(r, r);
+  f_dbl(I, H); f_sqr(I, I);
+  f_mul(J, H, I);
+  f_mul(V, U1, I);
+  f_add(t, P.z, Q.z); f_sqr(t, t); f_sub(t, t, Z1Z1); f_sub(t, t, Z2Z2); f_mul(R.z, t, H);
+  f_sqr(t, r); f_sub(t, t, J); f_sub(t, t, V); f_sub(R.x, t, V);
+  f_sub(t, V, R.x); f_mul(t, t, r);
+  f_mul(S1, S1, J); f_dbl(S1, S1);
+  f_sub(R.y, t, S1);
+}
+
+// P + Q, Q affine and never infinity (madd-2007-bl: 7M + 4S)
+template <class F>
+PSB_HD PSB_NOINL void pt_madd(Jac<F>& R, const Jac<F>& P, const Aff<F>& Q) {
+  if (pt_is_zero(P)) { pt_from_aff(R, Q); return; }
+  F Z1Z1, U2, S2, H, HH, I, J, r, V, t;
+  f_sqr(Z1Z1, P.z);
+  f_mul(U2, Q.x, Z1Z1);
+  f_mul(S2, Q.y, P.z); f_mul(S2, S2, Z1Z1);
+  f_sub(H, U2, P.x);
+  f_sub(r, S2, P.y);
+  if (f_is_zero(H)) {
+    if (f_is_zero(r)) { pt_dbl(R, P); } else { pt_set_zero(R); }
+    return;
+  }
+  f_dbl(r, r);
+  f_sqr(HH, H);
+  f_dbl(I, HH); f_dbl(I, I);
+  f_mul(J, H, I);
+  f_mul(V, P.x, I);
+  f_add(t, P.z, H); f_sqr(t, t); f_sub(t, t, Z1Z1);
+  F y1 = P.y;
+  f_sub(R.z, t, HH);
+  f_sqr(t, r); f_sub(t, t, J); f_sub(t, t, V); f_sub(R.x, t, V);
+  f_sub(t, V, R.x); f_mul(t, t, r);
+  f_mul(J, y1, J); f_dbl(J, J);
+  f_sub(R.y, t, J);
+}
+
+// (x/z^2, y/z^3, 1); infinity -> all-zero (canonical zero, what mcl's clear() holds)
+template <class F>
+PSB_HD PSB_NOINL void pt_normalize(Jac<F>& R, const Jac<F>& P) {
+  if (pt_is_zero(P)) { pt_set_zero(R); return; }
+  F zi, zi2;
+  f_inv(zi, P.z);
+  f_sqr(zi2, zi);
+  f_mul(R.x, P.x, zi2);
+  f_mul(zi2, zi2, zi);
+  f_mul(R.y, P.y, zi2);
+  f_set_one(R.z);
+}
+
+// k*P, variable base: fixed 4-bit windows over the 256-bit normal-form scalar (MSB first).
+// k = 8 limbs, normal form (NOT Montgomery), k < 2^256.
+template <class F>
+PSB_HD PSB_NOINL void pt_mul(Jac<F>& R, const Jac<F>& P, const uint32_t* k) {
+  Jac<F> tbl[16];
+  pt_set_zero(tbl[0]);
+  tbl[1] = P;
+  pt_dbl(tbl[2], P);
+  for (int i = 3; i < 16; i++) pt_add(tbl[i], tbl[i - 1], P);
+  Jac<F> acc;
+  pt_set_zero(acc);
+  for (int i = 63; i >= 0; i--) {
+    pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc);
+    const uint32_t d = (k[i >> 3] >> ((i & 7) * 4)) & 0xF;
+    if (d) pt_add(acc, acc, tbl[d]);
+  }
+  R = acc;
+}
+
+// ---- fixed-base windows --------------------------------------------------------------------------
+// Signed w-bit recoding of a 256-bit normal-form scalar (< 2^255): digits in [-2^(w-1), 2^(w-1)],
+// nwin = ceil(256 / w).  dig[j] receives the signed digit of window j.
+PSB_HD PSB_INL int fixed_nwin(int w) { return (256 + w - 1) / w; }
+PSB_HD PSB_INL uint32_t scalar_bits(const uint32_t* k, int pos, int w) {
+  // w <= 16 bits starting at bit `pos` (may straddle a limb; bits >= 256 read as zero)
+  const int limb = pos >> 5, sh = pos & 31;
+  uint64_t v = (limb < 8) ? k[limb] : 0u;
+  if (limb + 1 < 8) v |= (uint64_t)k[limb + 1] << 32;
+  return (uint32_t)(v >> sh) & ((1u << w) - 1u);
+}
+
+// acc += k * B using the table of base `b`: entry (win, d) = d * 2^(w*win) * B, d = 1..2^(w-1), affine.
+// tbl points at the first entry of this base: index = win * 2^(w-1) + (d - 1).
+template <class F>
+PSB_HD PSB_INL void pt_fixed_mul_acc(Jac<F>& acc, const Aff<F>* tbl, const uint32_t* k, int w) {
+  const int nwin = fixed_nwin(w);
+  const uint32_t half = 1u << (w - 1);
+  uint32_t carry = 0;
+  for (int j = 0; j < nwin; j++) {
+    uint32_t d = scalar_bits(k, j * w, w) + carry;
+    carry = 0;
+    bool neg = false;
+    if (d > half) { d = (1u << w) - d; neg = true; carry = 1; }
+    if (d != 0) {
+      Aff<F> e = tbl[(size_t)j * half + (d - 1)];
+      if (neg) f_neg(e.y, e.y);
+      pt_madd(acc, acc, e);
+    }
+  }
+}
+
+}  // namespace psb

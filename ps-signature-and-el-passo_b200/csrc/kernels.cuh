@@ -1,0 +1,256 @@
+// kernels.cuh -- __global__ kernels of the batch engine: one GPU thread per batch lane.
+//
+// Lanes are independent, so every kernel is a plain 1-D grid over lanes; the big
+// per-lane state (an Fp12 is 576 B, a G2 point 288 B) lives in thread-local memory that the
+// hardware interleaves per warp (coalesced, L1/L2 resident), while the limb arithmetic runs in
+// registers.  Work is split into phase kernels (scalars -> fixed-base MSM -> Miller loop -> final
+// exponentiation) so that each phase gets its own register allocation; the hand-over state goes
+// through HBM once per phase (< 1 KB per lane against millions of integer MACs: negligible).
+#pragma once
+#include "testops.cuh"
+
+namespace psb {
+
+constexpr int kBlock = 128;
+
+// ---- parity probe ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_test_op(int op, size_t n, int s0, int s1, int s2, int s3,
+                                                    const uint32_t* a, const uint32_t* b, const uint32_t* c,
+                                                    uint32_t* out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  test_op_run(op, a + i * s0, b ? b + i * s1 : nullptr, c ? c + i * s2 : nullptr, out + i * s3);
+}
+
+// ---- micro-benchmarks -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bench_fp(int kind, int iters, const uint32_t* seed, uint32_t* sink) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (kind == 0 || kind == 1) {
+    Fp x, y;
+    for (int j = 0; j < 12; j++) { x.v[j] = seed[j] ^ (uint32_t)i; y.v[j] = seed[12 + j]; }
+    x.v[11] &= 0x0fffffffu; y.v[11] &= 0x0fffffffu;
+    for (int it = 0; it < iters; it++) {
+      if (kind == 0) fp_mul_inl(x, x, y); else fp_sqr_inl(x, x);
+    }
+    if (x.v[0] == 0xdeadbeefu) sink[0] = x.v[1];
+  } else if (kind == 2) {
+    Fp2 x, y;
+    uint32_t* px = (uint32_t*)&x; uint32_t* py = (uint32_t*)&y;
+    for (int j = 0; j < 24; j++) { px[j] = seed[j % 12] ^ (uint32_t)i; py[j] = seed[12 + (j % 12)]; }
+    x.a.v[11] &= 0x0fffffffu; x.b.v[11] &= 0x0fffffffu; y.a.v[11] &= 0x0fffffffu; y.b.v[11] &= 0x0fffffffu;
+    for (int it = 0; it < iters; it++) fp2_mul(x, x, y);
+    if (x.a.v[0] == 0xdeadbeefu) sink[0] = x.a.v[1];
+  } else if (kind == 3) {
+    Fp12 x, y;
+    uint32_t* px = (uint32_t*)&x; uint32_t* py = (uint32_t*)&y;
+    for (int j = 0; j < 144; j++) { px[j] = seed[j % 12] ^ (uint32_t)i; py[j] = seed[12 + (j % 12)]; }
+    for (int j = 11; j < 144; j += 12) { px[j] &= 0x0fffffffu; py[j] &= 0x0fffffffu; }
+    for (int it = 0; it < iters; it++) fp12_mul(x, x, y);
+    if (x.a.a.a.v[0] == 0xdeadbeefu) sink[0] = x.a.a.a.v[1];
+  }
+}
+
+// raw integer-multiply issue-rate probes: 8 independent accumulator pairs per thread
+__global__ void __launch_bounds__(256) k_bench_mad(int kind, int iters, const uint32_t* seed, uint32_t* sink) {
+  const uint32_t t = threadIdx.x + blockIdx.x * blockDim.x;
+  uint32_t a = seed[0] ^ t, b = seed[1] + t;
+  if (kind == 4) {
+    uint32_t lo[8], hi[8];
+    for (int j = 0; j < 8; j++) { lo[j] = seed[j] + t; hi[j] = seed[8 + j] ^ t; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(lo[j]), "+r"(hi[j]) : "r"(a), "r"(b));
+      }
+      a += lo[0];
+    }
+    uint32_t s = 0;
+    for (int j = 0; j < 8; j++) s ^= lo[j] ^ hi[j];
+    if (s == 0xdeadbeefu) sink[0] = s;
+  } else if (kind == 5) {
+    unsigned long long acc[8];
+    for (int j = 0; j < 8; j++) acc[j] = ((unsigned long long)seed[j] << 32) | (seed[8 + j] ^ t);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a), "r"(b));
+      }
+      a += (uint32_t)acc[0];
+    }
+    unsigned long long s = 0;
+    for (int j = 0; j < 8; j++) s ^= acc[j];
+    if (s == 0xdeadbeefull) sink[0] = (uint32_t)s;
+  } else {
+    // plain 32-bit IMAD (lo only), 16 independent chains
+    uint32_t lo[16];
+    for (int j = 0; j < 16; j++) lo[j] = seed[j] + t;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int j = 0; j < 16; j++) lo[j] = lo[j] * a + b;
+      a += lo[0];
+    }
+    uint32_t s = 0;
+    for (int j = 0; j < 16; j++) s ^= lo[j];
+    if (s == 0xdeadbeefu) sink[0] = s;
+  }
+}
+
+// ---- key setup --------------------------------------------------------------------------------------
+// normalise `count` points in place (any z -> z = 1)
+template <class F>
+__global__ void k_normalize_points(Jac<F>* pts, int count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  Jac<F> p = pts[i], r;
+  pt_normalize(r, p);
+  pts[i] = r;
+}
+
+// window bases: wb[b * nwin + j] = 2^(w j) * base[b]  (affine).  One thread per base.
+template <class F>
+__global__ void k_window_bases(const Jac<F>* bases /*normalised*/, int nbases, int w, Aff<F>* wb) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbases) return;
+  const int nwin = fixed_nwin(w);
+  Jac<F> cur = bases[b];
+  for (int j = 0; j < nwin; j++) {
+    Jac<F> nrm;
+    pt_normalize(nrm, cur);
+    wb[(size_t)b * nwin + j].x = nrm.x;
+    wb[(size_t)b * nwin + j].y = nrm.y;
+    for (int t = 0; t < w; t++) pt_dbl(cur, cur);
+  }
+}
+
+// table entries: tbl[(b * nwin + j) * half + (d-1)] = d * wb[b * nwin + j], d = 1..half, affine.
+// One thread per chunk of kTblChunk consecutive d; chunk-local Montgomery batch inversion.
+constexpr int kTblChunk = 16;
+template <class F>
+__global__ void __launch_bounds__(kBlock) k_build_table(const Aff<F>* wb, int nbases, int w, Aff<F>* tbl) {
+  const int nwin = fixed_nwin(w);
+  const uint32_t half = 1u << (w - 1);
+  const uint32_t chunks_per_win = (half + kTblChunk - 1) / kTblChunk;
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)nbases * nwin * chunks_per_win;
+  if (gid >= total) return;
+  const size_t bw = gid / chunks_per_win;       // b * nwin + j
+  const uint32_t ch = (uint32_t)(gid % chunks_per_win);
+  const uint32_t d0 = ch * kTblChunk;           // entries d0+1 .. d0+kTblChunk
+  const Aff<F> B = wb[bw];
+  // S = d0 * B by double-and-add over 16 bits
+  Jac<F> S;
+  pt_set_zero(S);
+  for (int bit = 15; bit >= 0; bit--) {
+    pt_dbl(S, S);
+    if ((d0 >> bit) & 1u) pt_madd(S, S, B);
+  }
+  Jac<F> J[kTblChunk];
+  F pre[kTblChunk];
+  for (int t = 0; t < kTblChunk; t++) {
+    pt_madd(S, S, B);
+    J[t] = S;
+    if (t == 0) pre[0] = S.z; else f_mul(pre[t], pre[t - 1], S.z);
+  }
+  F inv;
+  f_inv(inv, pre[kTblChunk - 1]);
+  for (int t = kTblChunk - 1; t >= 0; t--) {
+    F zi, zi2;
+    if (t == 0) zi = inv; else f_mul(zi, inv, pre[t - 1]);
+    f_mul(inv, inv, J[t].z);
+    const uint32_t d = d0 + t + 1;
+    if (d <= half) {
+      Aff<F> e;
+      f_sqr(zi2, zi);
+      f_mul(e.x, J[t].x, zi2);
+      f_mul(zi2, zi2, zi);
+      f_mul(e.y, J[t].y, zi2);
+      tbl[bw * half + (d - 1)] = e;
+    }
+  }
+}
+
+__global__ void k_fixed_lines(const G2J* gg /*normalised*/, FixedLine* lines) {
+  if (blockIdx.x * blockDim.x + threadIdx.x != 0) return;
+  G2A q;
+  q.x = gg->x; q.y = gg->y;
+  precompute_fixed_lines(lines, q);
+}
+
+// ---- PS verification pipeline -------------------------------------------------------------------------
+// phase 1: scalars m_i (SHA-256 of the attribute strings, or the caller's Fr) and
+//          K = XX + sum_i m_i YY_i from the per-key window tables.
+__global__ void __launch_bounds__(kBlock) k_verify_msm(size_t N, int n, int w, const uint8_t* blob, const uint64_t* off,
+                                                        const Fr* m_mont, const G2J* XX, const G2A* tbl, G2J* Kout) {
+  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= N) return;
+  const size_t per_base = (size_t)fixed_nwin(w) << (w - 1);
+  G2J acc = *XX;
+  for (int i = 0; i < n; i++) {
+    uint32_t k[8];
+    if (blob) {
+      const uint64_t b = off[lane * n + i], e = off[lane * n + i + 1];
+      fr_set_hash_of(k, blob + b, (size_t)(e - b));
+    } else {
+      Fr t, tn;
+      t = m_mont[lane * n + i];
+      fr_from_mont(tn, t);
+      for (int j = 0; j < 8; j++) k[j] = tn.v[j];
+    }
+    pt_fixed_mul_acc(acc, tbl + (size_t)i * per_base, k, w);
+  }
+  Kout[lane] = acc;
+}
+
+// phase 2: f = ML(sig1, K) * ML(-sig2, gg)  (one multi-Miller loop per lane)
+__global__ void __launch_bounds__(kBlock) k_verify_miller(size_t N, const G1J* sig1, const G1J* sig2, const G2J* K,
+                                                           const FixedLine* lines, Fp12* fout) {
+  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= N) return;
+  Fp x1, y1, x2, y2;
+  {
+    G1J p = sig1[lane];
+    g1_affine_for_pairing(x1, y1, p);
+    p = sig2[lane];
+    g1_affine_for_pairing(x2, y2, p);
+    fp_neg(y2, y2);
+  }
+  G2J q = K[lane];
+  Fp12 f;
+  miller_loop2(f, x1, y1, q, x2, y2, lines, true);
+  fout[lane] = f;
+}
+
+// phase 3: final exponentiation, verdict = (sig1 != 0) && (f^e == 1), optional GT
+__global__ void __launch_bounds__(kBlock) k_verify_final(size_t N, const G1J* sig1, const Fp12* fin, uint8_t* verdict,
+                                                          Fp12* gt) {
+  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= N) return;
+  Fp12 f = fin[lane], e;
+  final_exp(e, f);
+  const bool s1zero = fp_is_zero(sig1[lane].z);
+  verdict[lane] = (!s1zero && fp12_is_one(e)) ? 1 : 0;
+  if (gt) gt[lane] = e;
+}
+
+// plain pairing e(P, Q) per lane (no fixed argument)
+__global__ void __launch_bounds__(kBlock) k_pairing_miller(size_t N, const G1J* P, const G2J* Q, Fp12* fout) {
+  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= N) return;
+  Fp x1, y1, zero;
+  fp_set_zero(zero);
+  G1J p = P[lane];
+  g1_affine_for_pairing(x1, y1, p);
+  G2J q = Q[lane];
+  Fp12 f;
+  miller_loop2(f, x1, y1, q, zero, zero, nullptr, false);
+  fout[lane] = f;
+}
+__global__ void __launch_bounds__(kBlock) k_final_exp(size_t N, const Fp12* fin, Fp12* out) {
+  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= N) return;
+  Fp12 f = fin[lane], e;
+  final_exp(e, f);
+  out[lane] = e;
+}
+
+}  // namespace psb

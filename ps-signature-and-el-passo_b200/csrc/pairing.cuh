@@ -1,0 +1,203 @@
+// pairing.cuh -- optimal-ate pairing on BLS12-381: a two-pairing ("multi") Miller loop and mcl's
+// final exponentiation.
+//
+// Reference semantics (third-parties/mcl/include/mcl/bn.hpp): millerLoop :1660-1710,
+// precomputeG2 :1719-1758, precomputedMillerLoop2mixed :1827-1897, finalExp :1643-1659 =
+// mapToCyclotomic :1494-1502 + expHardPartBLS12 :1508-1555 (exponent 3(p^4-p^2+1)/r: SURVEY F3),
+// pow_z :1150-1176, cyclotomic squaring :1075-1144.
+//
+// Only the final-exponentiation OUTPUT is canonical; the Miller value differs from mcl's by
+// factors in proper subfields (our line functions are scaled differently: homogeneous projective
+// coordinates after Costello-Lange-Naehrig instead of mcl's Jacobian), which the final
+// exponentiation erases.  GT bytes therefore match mcl bit for bit.
+#pragma once
+#include "curve.cuh"
+
+namespace psb {
+
+// one precomputed line of the fixed G2 argument (affine slope form):
+//   l(P) = c0 + (nl * xP) w^2 + yP w^3,   nl = -lambda,  c0 = lambda*xT - yT
+struct FixedLine { Fp2 nl, c0; };
+constexpr int kMillerSteps = 63 + 5;  // doublings + additions for |z| = 0xd201000000010000
+
+struct G2H { Fp2 x, y, z; };  // homogeneous projective: (X/Z, Y/Z)
+
+PSB_HD PSB_INL bool z_bit(int i) { return (PSB_Z_ABS >> i) & 1ull; }
+
+// (4 xi) * 3 * c = 12 xi c   (3 b' C with b' = 4 xi)
+PSB_HD PSB_INL void fp2_mul_12xi(Fp2& r, const Fp2& c) {
+  Fp2 t, u;
+  fp2_mul_xi(t, c);
+  fp2_dbl(t, t); fp2_dbl(t, t);      // 4 xi c
+  fp2_dbl(u, t); fp2_add(r, u, t);   // 12 xi c
+}
+
+// T <- 2T and the tangent line at T evaluated at P = (xP, yP):
+//   line = (E - B) + (3 X^2 xP) w^2 + (-2YZ yP) w^3     (scaled by -2YZ in Fp2)
+PSB_HD PSB_NOINL void ml_dbl_step(G2H& T, Fp2& c0, Fp2& c2, Fp2& c3, const Fp& xP, const Fp& yP) {
+  Fp2 A, B, C, E, F, H, J, t, u;
+  fp2_mul(A, T.x, T.y);                 // XY
+  fp2_sqr(B, T.y);
+  fp2_sqr(C, T.z);
+  fp2_sqr(J, T.x);
+  fp2_add(H, T.y, T.z); fp2_sqr(H, H); fp2_sub(H, H, B); fp2_sub(H, H, C);   // 2YZ
+  fp2_mul_12xi(E, C);                   // 3 b' Z^2
+  fp2_dbl(F, E); fp2_add(F, F, E);      // 3E
+  // line
+  fp2_sub(c0, E, B);
+  fp2_dbl(t, J); fp2_add(t, t, J); fp2_mul_fp(c2, t, xP);
+  fp2_mul_fp(t, H, yP); fp2_neg(c3, t);
+  // point (scaled by 4): X3 = 2 XY (B - F), Y3 = (B + F)^2 - 12 E^2, Z3 = 4 B H
+  fp2_sub(t, B, F); fp2_mul(t, A, t); fp2_dbl(T.x, t);
+  fp2_add(t, B, F); fp2_sqr(t, t);
+  fp2_dbl(u, E); fp2_sqr(u, u);         // 4 E^2
+  fp2_sub(t, t, u); fp2_sub(t, t, u); fp2_sub(T.y, t, u);
+  fp2_mul(t, B, H); fp2_dbl(t, t); fp2_dbl(T.z, t);
+}
+
+// T <- T + Q (Q homogeneous projective, Q != +-T, neither infinity) and the chord through them at P:
+//   theta = Y1 Z2 - Y2 Z1, lam = X1 Z2 - X2 Z1
+//   line = (theta X2 - lam Y2) + (-theta Z2 xP) w^2 + (lam Z2 yP) w^3   (scaled by lam Z2)
+PSB_HD PSB_NOINL void ml_add_step(G2H& T, Fp2& c0, Fp2& c2, Fp2& c3, const G2H& Q, const Fp& xP, const Fp& yP) {
+  Fp2 A, Y1Z2, th, lm, W, l2, l3, N, t, u;
+  fp2_mul(A, T.x, Q.z);
+  fp2_mul(t, Q.x, T.z); fp2_sub(lm, A, t);
+  fp2_mul(Y1Z2, T.y, Q.z);
+  fp2_mul(t, Q.y, T.z); fp2_sub(th, Y1Z2, t);
+  // line
+  fp2_mul(t, th, Q.x); fp2_mul(u, lm, Q.y); fp2_sub(c0, t, u);
+  fp2_mul(t, th, Q.z); fp2_mul_fp(t, t, xP); fp2_neg(c2, t);
+  fp2_mul(t, lm, Q.z); fp2_mul_fp(c3, t, yP);
+  // point
+  fp2_mul(W, T.z, Q.z);
+  fp2_sqr(l2, lm);
+  fp2_mul(l3, l2, lm);
+  fp2_mul(l2, l2, A);                    // lam^2 A
+  fp2_sqr(t, th); fp2_mul(t, t, W);      // theta^2 W
+  fp2_sub(N, t, l2); fp2_sub(N, N, l2); fp2_add(N, N, l3);
+  fp2_mul(T.x, lm, N);
+  fp2_sub(t, l2, N); fp2_mul(t, th, t);
+  fp2_mul(u, l3, Y1Z2);
+  fp2_sub(T.y, t, u);
+  fp2_mul(T.z, l3, W);
+}
+
+// f = ML(P1, Q1) * ML(P2, Q2_fixed), conjugated for z < 0.
+//   P1 = (x1, y1), P2 = (x2, y2): affine Fp coordinates; an infinite P is passed as (0, 0) (its
+//   lines fall into Fp2 and die in the final exponentiation, like mcl: bls12_test.cpp:288-296).
+//   Q1: G2 Jacobian (any z); q1_zero => that pairing contributes 1 (bn.hpp:1666-1669).
+//   lines2: kMillerSteps precomputed lines of the fixed Q2 (per key); use2 = false skips them.
+PSB_HD PSB_NOINL void miller_loop2(Fp12& f, const Fp& x1, const Fp& y1, const G2J& Q1, const Fp& x2, const Fp& y2,
+                                   const FixedLine* lines2, bool use2) {
+  const bool use1 = !pt_is_zero(Q1);
+  G2H Q, T;
+  // Jacobian (X, Y, Z) -> homogeneous (X Z, Y, Z^3)
+  fp2_mul(Q.x, Q1.x, Q1.z);
+  Q.y = Q1.y;
+  fp2_sqr(Q.z, Q1.z); fp2_mul(Q.z, Q.z, Q1.z);
+  T = Q;
+  fp12_set_one(f);
+  Fp2 c0, c2, c3;
+  int li = 0;
+  for (int i = 62; i >= 0; i--) {
+    if (i != 62) fp12_sqr(f, f);
+    if (use1) {
+      ml_dbl_step(T, c0, c2, c3, x1, y1);
+      fp12_mul_line(f, c0, c2, c3);
+    }
+    if (use2) {
+      const FixedLine L = lines2[li];
+      fp2_mul_fp(c2, L.nl, x2);
+      c3.a = y2; fp_set_zero(c3.b);
+      fp12_mul_line(f, L.c0, c2, c3);
+    }
+    li++;
+    if (z_bit(i)) {
+      if (use1) {
+        ml_add_step(T, c0, c2, c3, Q, x1, y1);
+        fp12_mul_line(f, c0, c2, c3);
+      }
+      if (use2) {
+        const FixedLine L = lines2[li];
+        fp2_mul_fp(c2, L.nl, x2);
+        c3.a = y2; fp_set_zero(c3.b);
+        fp12_mul_line(f, L.c0, c2, c3);
+      }
+      li++;
+    }
+  }
+  fp6_neg(f.b, f.b);  // z < 0  (bn.hpp:1695-1697)
+}
+
+// precompute the kMillerSteps affine lines of a fixed Q (affine, not infinity).  One thread, once per key.
+PSB_HD PSB_NOINL void precompute_fixed_lines(FixedLine* out, const G2A& Q) {
+  Fp2 x = Q.x, y = Q.y, lam, t, u, x3;
+  int li = 0;
+  for (int i = 62; i >= 0; i--) {
+    // tangent: lam = 3x^2 / 2y
+    fp2_sqr(t, x); fp2_dbl(u, t); fp2_add(t, t, u);
+    fp2_dbl(u, y); fp2_inv(u, u); fp2_mul(lam, t, u);
+    fp2_neg(out[li].nl, lam);
+    fp2_mul(t, lam, x); fp2_sub(out[li].c0, t, y);
+    li++;
+    fp2_sqr(x3, lam); fp2_sub(x3, x3, x); fp2_sub(x3, x3, x);
+    fp2_sub(t, x, x3); fp2_mul(t, lam, t); fp2_sub(y, t, y);
+    x = x3;
+    if (z_bit(i)) {
+      // chord through T and Q: lam = (yQ - y)/(xQ - x)
+      fp2_sub(t, Q.y, y); fp2_sub(u, Q.x, x); fp2_inv(u, u); fp2_mul(lam, t, u);
+      fp2_neg(out[li].nl, lam);
+      fp2_mul(t, lam, Q.x); fp2_sub(out[li].c0, t, Q.y);
+      li++;
+      fp2_sqr(x3, lam); fp2_sub(x3, x3, x); fp2_sub(x3, x3, Q.x);
+      fp2_sub(t, x, x3); fp2_mul(t, lam, t); fp2_sub(y, t, y);
+      x = x3;
+    }
+  }
+}
+
+// y = x^z (z < 0): x^|z| by square-and-multiply with cyclotomic squarings, then conjugate
+PSB_HD PSB_NOINL void pow_z(Fp12& y, const Fp12& x) {
+  Fp12 acc = x;
+  for (int i = 62; i >= 0; i--) {
+    fp12_cyclo_sqr(acc, acc);
+    if (z_bit(i)) fp12_mul(acc, acc, x);
+  }
+  fp12_conj(y, acc);
+}
+
+// y = x^((p^12-1)/r * 3), structured as mcl's finalExp (bn.hpp:1643-1659)
+PSB_HD PSB_NOINL void final_exp(Fp12& y, const Fp12& x) {
+  Fp12 a0, a1, a2, a3, a4, a5, a7, t;
+  // easy part: t = x^((p^6-1)(p^2+1))   (mapToCyclotomic, bn.hpp:1494-1502)
+  fp12_frobenius(a0, x, 2);
+  fp12_mul(a0, a0, x);          // x^(p^2+1)
+  fp12_inv(a1, a0);
+  fp12_conj(a0, a0);            // ^(p^6)
+  fp12_mul(t, a1, a0);
+  // hard part (expHardPartBLS12, bn.hpp:1508-1555)
+  fp12_conj(a0, t);             // t^-1
+  fp12_cyclo_sqr(a1, a0);       // t^-2
+  pow_z(a2, t);                 // t^z
+  fp12_cyclo_sqr(a3, a2);       // t^2z
+  fp12_mul(a1, a1, a2);         // t^(z-2)
+  pow_z(a7, a1);                // t^(z^2-2z)
+  pow_z(a4, a7);                // t^(z^3-2z^2)
+  pow_z(a5, a4);                // t^(z^4-2z^3)
+  fp12_mul(a3, a3, a5);         // t^(z^4-2z^3+2z)
+  pow_z(a5, a3);                // t^(z^5-2z^4+2z^2)   (mcl's a6)
+  fp12_conj(a1, a1);            // t^(2-z)
+  fp12_mul(a1, a1, a5);
+  fp12_mul(a1, a1, t);          // t^c0,  c0 = z^5-2z^4+2z^2-z+3
+  fp12_mul(a3, a3, a0);         // t^c1,  c1 = z^4-2z^3+2z-1
+  fp12_frobenius(a3, a3, 1);
+  fp12_mul(a1, a1, a3);
+  fp12_mul(a4, a4, a2);         // t^c2,  c2 = z^3-2z^2+z
+  fp12_frobenius(a4, a4, 2);
+  fp12_mul(a1, a1, a4);
+  fp12_mul(a7, a7, t);          // t^c3,  c3 = z^2-2z+1
+  fp12_frobenius(a7, a7, 3);
+  fp12_mul(y, a7, a1);
+}
+
+}  // namespace psb

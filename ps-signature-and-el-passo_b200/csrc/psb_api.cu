@@ -1,0 +1,393 @@
+// psb_api.cu -- the extern "C" layer of libpsb.so (declared in include/psb.h).
+//
+// Host side of the batch engine: device list, per-key tables in HBM, lane sharding over the GPUs of
+// one box (one host worker thread + one stream per device, no inter-device communication, verdict
+// bytes written into disjoint slices of the caller's array -- SURVEY.md 8e), and kernel launches.
+// There is deliberately NO CPU implementation behind these entry points.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/psb.h"
+#include "kernels.cuh"
+
+using namespace psb;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+struct Dev {
+  int ordinal = 0;
+  cudaStream_t stream = nullptr;
+  DevBuf in[8];   // staging for host-pointer entry points
+  DevBuf ws;      // phase hand-over scratch
+  std::mutex mu;  // one batch at a time per device
+};
+
+std::vector<Dev*> g_devs;
+bool g_init = false;
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+  char buf[512];
+  if (e != cudaSuccess) snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+  else snprintf(buf, sizeof(buf), "%s", what);
+  g_err = buf;
+  return code;
+}
+#define CK(call)                                                        \
+  do {                                                                  \
+    cudaError_t e_ = (call);                                            \
+    if (e_ != cudaSuccess) return fail(PSB_ERR_CUDA, #call, e_);        \
+  } while (0)
+#define LAUNCHED() g_launches.fetch_add(1, std::memory_order_relaxed)
+
+inline unsigned nblocks(size_t n, int block = kBlock) { return (unsigned)((n + block - 1) / block); }
+
+int ensure(DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return PSB_OK;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr; b.cap = 0;
+  size_t cap = bytes + (bytes >> 3) + 256;
+  cudaError_t e = cudaMalloc(&b.p, cap);
+  if (e != cudaSuccess) return fail(PSB_ERR_NOMEM, "cudaMalloc", e);
+  b.cap = cap;
+  return PSB_OK;
+}
+
+struct KeyDev {
+  G1J* g1pts = nullptr;   // [0] g, [1] X (or zero), [2..2+n) Y_i         (normalised)
+  G2J* g2pts = nullptr;   // [0] gg, [1] XX, [2..2+n) YY_i                (normalised)
+  G2A* wbYY = nullptr;    // n * nwin window bases
+  G2A* tblYY = nullptr;   // n * nwin * 2^(w-1) affine entries
+  FixedLine* lines = nullptr;
+};
+
+}  // namespace
+
+struct psb_key {
+  size_t n = 0;
+  int w = 16;
+  bool hasX = false;
+  size_t table_bytes = 0;
+  std::vector<KeyDev> d;
+};
+
+namespace {
+
+// run f(dev_index, lane_begin, lane_end) on every device over a contiguous split of [0, N)
+template <class Fn>
+int shard(size_t N, Fn fn) {
+  const int G = (int)g_devs.size();
+  if (G == 1 || N < 2 * (size_t)G) return fn(0, (size_t)0, N);
+  std::vector<int> rc(G, 0);
+  std::vector<std::string> errs(G);
+  std::vector<std::thread> th;
+  for (int k = 0; k < G; k++) {
+    const size_t b = N * k / G, e = N * (k + 1) / G;
+    th.emplace_back([&, k, b, e]() { rc[k] = fn(k, b, e); if (rc[k]) errs[k] = g_err; });
+  }
+  for (auto& t : th) t.join();
+  for (int k = 0; k < G; k++) if (rc[k]) { g_err = errs[k]; return rc[k]; }
+  return PSB_OK;
+}
+
+int verify_launch(const psb_key* key, int di, size_t N, const G1J* d_sig1, const G1J* d_sig2, const uint8_t* d_blob,
+                  const uint64_t* d_off, const Fr* d_m, uint8_t* d_verdict, Fp12* d_gt, void* d_ws, cudaStream_t st) {
+  if (N == 0) return PSB_OK;
+  const KeyDev& kd = key->d[di];
+  G2J* dK = (G2J*)d_ws;
+  Fp12* dF = (Fp12*)((char*)d_ws + N * sizeof(G2J));
+  k_verify_msm<<<nblocks(N), kBlock, 0, st>>>(N, (int)key->n, key->w, d_blob, d_off, d_m, kd.g2pts + 1, kd.tblYY, dK);
+  LAUNCHED();
+  k_verify_miller<<<nblocks(N), kBlock, 0, st>>>(N, d_sig1, d_sig2, dK, kd.lines, dF);
+  LAUNCHED();
+  k_verify_final<<<nblocks(N), kBlock, 0, st>>>(N, d_sig1, dF, d_verdict, d_gt);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  return PSB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* psb_last_error(void) { return g_err.c_str(); }
+uint64_t psb_launch_count(void) { return g_launches.load(); }
+int psb_num_devices(void) { return g_init ? (int)g_devs.size() : 0; }
+
+int psb_init(int curve, const int* devices, int ndev) {
+  if (curve != PSB_CURVE_BLS12_381) return fail(PSB_ERR_UNSUPPORTED, "only BLS12-381 (curve 5) is built");
+  if (g_init) psb_shutdown();
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) return fail(PSB_ERR_CUDA, "no CUDA device (this library has no CPU path)", e);
+  std::vector<int> ords;
+  if (devices && ndev > 0) ords.assign(devices, devices + ndev); else ords.push_back(0);
+  for (int o : ords) {
+    if (o < 0 || o >= count) return fail(PSB_ERR_ARG, "device ordinal out of range");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, o));
+    if (prop.major < 10) return fail(PSB_ERR_UNSUPPORTED, "kernels are built for sm_100a only");
+    Dev* d = new Dev();
+    d->ordinal = o;
+    CK(cudaSetDevice(o));
+    CK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    // thread-local state (Fp12 temporaries, window tables of points) lives in local memory:
+    // prefer L1 over shared memory, and give deep call chains enough stack
+    cudaDeviceSetLimit(cudaLimitStackSize, 32 * 1024);
+    g_devs.push_back(d);
+  }
+  g_init = true;
+  return PSB_OK;
+}
+
+void psb_shutdown(void) {
+  for (Dev* d : g_devs) {
+    cudaSetDevice(d->ordinal);
+    for (auto& b : d->in) if (b.p) cudaFree(b.p);
+    if (d->ws.p) cudaFree(d->ws.p);
+    if (d->stream) cudaStreamDestroy(d->stream);
+    delete d;
+  }
+  g_devs.clear();
+  g_init = false;
+}
+
+size_t psb_key_num_attributes(const psb_key* key) { return key ? key->n : 0; }
+size_t psb_key_table_bytes(const psb_key* key) { return key ? key->table_bytes : 0; }
+
+void psb_key_destroy(psb_key* key) {
+  if (!key) return;
+  for (size_t i = 0; i < key->d.size(); i++) {
+    cudaSetDevice(g_devs[i]->ordinal);
+    KeyDev& k = key->d[i];
+    cudaFree(k.g1pts); cudaFree(k.g2pts); cudaFree(k.wbYY); cudaFree(k.tblYY); cudaFree(k.lines);
+  }
+  delete key;
+}
+
+psb_key* psb_key_create(const uint64_t* g, const uint64_t* gg, const uint64_t* XX, const uint64_t* Y,
+                        const uint64_t* YY, size_t n, const uint64_t* X_secret, int window_bits) {
+  if (!g_init) { fail(PSB_ERR_NOT_INIT, "psb_init not called"); return nullptr; }
+  if (!g || !gg || !XX || (n && (!Y || !YY))) { fail(PSB_ERR_ARG, "null key component"); return nullptr; }
+  int w = window_bits == 0 ? 16 : window_bits;
+  if (w < 4 || w > 16) { fail(PSB_ERR_ARG, "window_bits must be 4..16"); return nullptr; }
+  psb_key* key = new psb_key();
+  key->n = n; key->w = w; key->hasX = X_secret != nullptr;
+  key->d.resize(g_devs.size());
+  const int nwin = fixed_nwin(w);
+  const size_t half = (size_t)1 << (w - 1);
+  const size_t entries = n * nwin * half;
+  key->table_bytes = entries * sizeof(G2A);
+  std::vector<G1J> h1(2 + n);
+  std::vector<G2J> h2(2 + n);
+  memcpy(&h1[0], g, sizeof(G1J));
+  if (X_secret) memcpy(&h1[1], X_secret, sizeof(G1J)); else memset(&h1[1], 0, sizeof(G1J));
+  if (n) memcpy(&h1[2], Y, n * sizeof(G1J));
+  memcpy(&h2[0], gg, sizeof(G2J));
+  memcpy(&h2[1], XX, sizeof(G2J));
+  if (n) memcpy(&h2[2], YY, n * sizeof(G2J));
+  for (size_t di = 0; di < g_devs.size(); di++) {
+    Dev* dv = g_devs[di];
+    KeyDev& k = key->d[di];
+    cudaStream_t st = dv->stream;
+    bool ok = cudaSetDevice(dv->ordinal) == cudaSuccess;
+    ok = ok && cudaMalloc(&k.g1pts, h1.size() * sizeof(G1J)) == cudaSuccess;
+    ok = ok && cudaMalloc(&k.g2pts, h2.size() * sizeof(G2J)) == cudaSuccess;
+    ok = ok && cudaMalloc(&k.wbYY, (n * nwin + 1) * sizeof(G2A)) == cudaSuccess;
+    ok = ok && cudaMalloc(&k.tblYY, (entries + 1) * sizeof(G2A)) == cudaSuccess;
+    ok = ok && cudaMalloc(&k.lines, kMillerSteps * sizeof(FixedLine)) == cudaSuccess;
+    if (!ok) { fail(PSB_ERR_NOMEM, "key allocation", cudaGetLastError()); psb_key_destroy(key); return nullptr; }
+    cudaMemcpyAsync(k.g1pts, h1.data(), h1.size() * sizeof(G1J), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(k.g2pts, h2.data(), h2.size() * sizeof(G2J), cudaMemcpyHostToDevice, st);
+    k_normalize_points<Fp><<<nblocks(h1.size(), 32), 32, 0, st>>>(k.g1pts, (int)h1.size()); LAUNCHED();
+    k_normalize_points<Fp2><<<nblocks(h2.size(), 32), 32, 0, st>>>(k.g2pts, (int)h2.size()); LAUNCHED();
+    if (n) {
+      k_window_bases<Fp2><<<nblocks(n, 32), 32, 0, st>>>(k.g2pts + 2, (int)n, w, k.wbYY); LAUNCHED();
+      const size_t chunks = n * nwin * ((half + kTblChunk - 1) / kTblChunk);
+      k_build_table<Fp2><<<nblocks(chunks), kBlock, 0, st>>>(k.wbYY, (int)n, w, k.tblYY); LAUNCHED();
+    }
+    k_fixed_lines<<<1, 32, 0, st>>>(k.g2pts, k.lines); LAUNCHED();
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { fail(PSB_ERR_CUDA, "key setup kernels", e); psb_key_destroy(key); return nullptr; }
+  }
+  return key;
+}
+
+size_t psb_verify_ws_bytes(const psb_key* key, size_t N) {
+  (void)key;
+  return N * (sizeof(G2J) + sizeof(Fp12)) + 256;
+}
+
+int psb_verify_dev(psb_key* key, int dev_index, size_t N, const uint64_t* d_sig1, const uint64_t* d_sig2,
+                   const uint8_t* d_attr_blob, const uint64_t* d_attr_off, const uint64_t* d_m,
+                   uint8_t* d_verdict, uint64_t* d_gt, void* d_ws, void* stream) {
+  if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
+  if (!key || dev_index < 0 || dev_index >= (int)g_devs.size()) return fail(PSB_ERR_ARG, "bad key/device");
+  if (!d_sig1 || !d_sig2 || !d_verdict || !d_ws || (!d_attr_blob && !d_m && key->n)) return fail(PSB_ERR_ARG, "null buffer");
+  if (d_attr_blob && !d_attr_off) return fail(PSB_ERR_ARG, "attr_off missing");
+  CK(cudaSetDevice(g_devs[dev_index]->ordinal));
+  cudaStream_t st = stream ? (cudaStream_t)stream : g_devs[dev_index]->stream;
+  return verify_launch(key, dev_index, N, (const G1J*)d_sig1, (const G1J*)d_sig2, d_attr_blob, d_attr_off,
+                       (const Fr*)d_m, d_verdict, (Fp12*)d_gt, d_ws, st);
+}
+
+int psb_verify(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* sig2, const uint8_t* attr_blob,
+               const uint64_t* attr_off, const uint64_t* m, uint8_t* verdict, uint64_t* gt) {
+  if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
+  if (!key || !sig1 || !sig2 || !verdict) return fail(PSB_ERR_ARG, "null argument");
+  if (key->n && !attr_blob && !m) return fail(PSB_ERR_ARG, "need attributes or scalars");
+  if (attr_blob && !attr_off) return fail(PSB_ERR_ARG, "attr_off missing");
+  const size_t n = key->n;
+  return shard(N, [&](int di, size_t b, size_t e) -> int {
+    Dev* dv = g_devs[di];
+    std::lock_guard<std::mutex> lk(dv->mu);
+    const size_t L = e - b;
+    if (L == 0) return PSB_OK;
+    CK(cudaSetDevice(dv->ordinal));
+    cudaStream_t st = dv->stream;
+    int rc;
+    if ((rc = ensure(dv->in[0], L * sizeof(G1J)))) return rc;
+    if ((rc = ensure(dv->in[1], L * sizeof(G1J)))) return rc;
+    if ((rc = ensure(dv->in[4], L + 16))) return rc;
+    if ((rc = ensure(dv->ws, psb_verify_ws_bytes(key, L)))) return rc;
+    if (gt && (rc = ensure(dv->in[5], L * sizeof(Fp12)))) return rc;
+    CK(cudaMemcpyAsync(dv->in[0].p, sig1 + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dv->in[1].p, sig2 + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    const uint8_t* d_blob = nullptr; const uint64_t* d_off = nullptr; const Fr* d_m = nullptr;
+    if (attr_blob) {
+      const uint64_t o0 = attr_off[b * n], o1 = attr_off[e * n];
+      if ((rc = ensure(dv->in[2], (size_t)(o1 - o0) + 16))) return rc;
+      if ((rc = ensure(dv->in[3], (L * n + 1) * sizeof(uint64_t)))) return rc;
+      if (o1 > o0) CK(cudaMemcpyAsync(dv->in[2].p, attr_blob + o0, (size_t)(o1 - o0), cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(dv->in[3].p, attr_off + b * n, (L * n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+      d_blob = (const uint8_t*)dv->in[2].p - o0;  // offsets stay absolute
+      d_off = (const uint64_t*)dv->in[3].p;
+    } else if (n) {
+      if ((rc = ensure(dv->in[2], L * n * sizeof(Fr)))) return rc;
+      CK(cudaMemcpyAsync(dv->in[2].p, m + b * n * 4, L * n * sizeof(Fr), cudaMemcpyHostToDevice, st));
+      d_m = (const Fr*)dv->in[2].p;
+    }
+    rc = verify_launch(key, di, L, (const G1J*)dv->in[0].p, (const G1J*)dv->in[1].p, d_blob, d_off, d_m,
+                       (uint8_t*)dv->in[4].p, gt ? (Fp12*)dv->in[5].p : nullptr, dv->ws.p, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(verdict + b, dv->in[4].p, L, cudaMemcpyDeviceToHost, st));
+    if (gt) CK(cudaMemcpyAsync(gt + b * 72, dv->in[5].p, L * sizeof(Fp12), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PSB_OK;
+  });
+}
+
+int psb_pairing(size_t N, const uint64_t* P, const uint64_t* Q, uint64_t* out) {
+  if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
+  if (!P || !Q || !out) return fail(PSB_ERR_ARG, "null argument");
+  return shard(N, [&](int di, size_t b, size_t e) -> int {
+    Dev* dv = g_devs[di];
+    std::lock_guard<std::mutex> lk(dv->mu);
+    const size_t L = e - b;
+    if (L == 0) return PSB_OK;
+    CK(cudaSetDevice(dv->ordinal));
+    cudaStream_t st = dv->stream;
+    int rc;
+    if ((rc = ensure(dv->in[0], L * sizeof(G1J)))) return rc;
+    if ((rc = ensure(dv->in[1], L * sizeof(G2J)))) return rc;
+    if ((rc = ensure(dv->in[5], L * sizeof(Fp12)))) return rc;
+    if ((rc = ensure(dv->ws, L * sizeof(Fp12)))) return rc;
+    CK(cudaMemcpyAsync(dv->in[0].p, P + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dv->in[1].p, Q + b * 36, L * sizeof(G2J), cudaMemcpyHostToDevice, st));
+    k_pairing_miller<<<nblocks(L), kBlock, 0, st>>>(L, (const G1J*)dv->in[0].p, (const G2J*)dv->in[1].p, (Fp12*)dv->ws.p);
+    LAUNCHED();
+    k_final_exp<<<nblocks(L), kBlock, 0, st>>>(L, (const Fp12*)dv->ws.p, (Fp12*)dv->in[5].p);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out + b * 72, dv->in[5].p, L * sizeof(Fp12), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PSB_OK;
+  });
+}
+
+int psb_test_op_shape(int op, int shape[4]) { return test_op_shape(op, shape) ? PSB_OK : PSB_ERR_ARG; }
+
+int psb_test_op(int op, size_t n, const uint32_t* a, const uint32_t* b, const uint32_t* c, uint32_t* out) {
+  if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
+  int s[4];
+  if (!test_op_shape(op, s)) return fail(PSB_ERR_ARG, "unknown test op");
+  if (!a || !out || (s[1] && !b) || (s[2] && !c)) return fail(PSB_ERR_ARG, "null operand");
+  if (n == 0) return PSB_OK;
+  Dev* dv = g_devs[0];
+  std::lock_guard<std::mutex> lk(dv->mu);
+  CK(cudaSetDevice(dv->ordinal));
+  cudaStream_t st = dv->stream;
+  int rc;
+  const uint32_t* hp[3] = {a, b, c};
+  for (int i = 0; i < 3; i++) {
+    if (!s[i]) continue;
+    if ((rc = ensure(dv->in[i], n * s[i] * 4))) return rc;
+    CK(cudaMemcpyAsync(dv->in[i].p, hp[i], n * s[i] * 4, cudaMemcpyHostToDevice, st));
+  }
+  if ((rc = ensure(dv->in[3], n * s[3] * 4))) return rc;
+  k_test_op<<<nblocks(n), kBlock, 0, st>>>(op, n, s[0], s[1], s[2], s[3], (const uint32_t*)dv->in[0].p,
+                                           s[1] ? (const uint32_t*)dv->in[1].p : nullptr,
+                                           s[2] ? (const uint32_t*)dv->in[2].p : nullptr, (uint32_t*)dv->in[3].p);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, dv->in[3].p, n * s[3] * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return PSB_OK;
+}
+
+double psb_microbench(int kind, int blocks, int threads, int iters) {
+  if (!g_init) { fail(PSB_ERR_NOT_INIT, "psb_init not called"); return -1.0; }
+  Dev* dv = g_devs[0];
+  std::lock_guard<std::mutex> lk(dv->mu);
+  if (cudaSetDevice(dv->ordinal) != cudaSuccess) return -1.0;
+  cudaStream_t st = dv->stream;
+  if (ensure(dv->in[0], 64 * 4) || ensure(dv->in[1], 64)) return -1.0;
+  uint32_t seed[32];
+  for (int i = 0; i < 32; i++) seed[i] = 0x9e3779b9u * (i + 1) + 0x7f4a7c15u;
+  cudaMemcpyAsync(dv->in[0].p, seed, sizeof(seed), cudaMemcpyHostToDevice, st);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float ms = -1.f;
+  for (int rep = 0; rep < 2; rep++) {  // first pass = warm-up
+    cudaEventRecord(e0, st);
+    if (kind <= 3) k_bench_fp<<<blocks, threads, 0, st>>>(kind, iters, (const uint32_t*)dv->in[0].p, (uint32_t*)dv->in[1].p);
+    else k_bench_mad<<<blocks, threads, 0, st>>>(kind, iters, (const uint32_t*)dv->in[0].p, (uint32_t*)dv->in[1].p);
+    LAUNCHED();
+    cudaEventRecord(e1, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { ms = -1.f; break; }
+    cudaEventElapsedTime(&ms, e0, e1);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return (double)ms;
+}
+
+// ---- entry points still to be built this round (declared in psb.h) ---------------------------------
+int psb_randomize(size_t, const uint64_t*, const uint64_t*, const uint64_t*, uint64_t*, uint64_t*, uint8_t*) {
+  return fail(PSB_ERR_UNSUPPORTED, "psb_randomize: not built yet");
+}
+int psb_provide_id(psb_key*, size_t, const uint64_t*, const uint64_t*, const uint64_t*, size_t, const uint8_t*,
+                   const uint64_t*, const uint8_t*, const uint64_t*, const uint64_t*, uint8_t*, uint64_t*, uint64_t*,
+                   uint8_t*) {
+  return fail(PSB_ERR_UNSUPPORTED, "psb_provide_id: not built yet");
+}
+int psb_verify_id(psb_key*, size_t, const uint64_t*, const uint64_t*, const uint64_t*, const uint64_t*, const uint64_t*,
+                  const uint64_t*, const uint64_t*, const uint64_t*, size_t, const uint8_t*, const uint64_t*,
+                  const uint8_t*, const uint64_t*, const uint64_t*, const uint64_t*, const uint64_t*, const uint64_t*,
+                  int, uint8_t*) {
+  return fail(PSB_ERR_UNSUPPORTED, "psb_verify_id: not built yet");
+}
+
+}  // extern "C"

@@ -1,0 +1,305 @@
+"""engine.py -- ctypes binding of libpsb.so (include/psb.h) and a Python mirror of the reference's
+role classes for the batched path.
+
+Class and method names follow the reference (src/ps-verifier.h, src/ps-requester.h, src/ps-signer.h):
+PSVerifier.verify / el_passo_verify_id, PSRequester.verify / randomize_credential,
+PSSigner.el_passo_provide_id -- each taking a BATCH (numpy arrays in mcl's in-memory layout, see
+include/psb.h) instead of one object.  The real drop-in for C++ callers is host/ps_batch.hpp; this
+mirror exists so tests and bench.py read like the reference's own tests.
+
+There is no CPU fallback: loading fails loudly if libpsb.so is missing, and every call fails if no
+GPU is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpsb.so")
+
+FP, FR, G1, G2, GT = 6, 4, 18, 36, 72  # u64 words
+CURVE_BLS12_381 = 5
+
+_lib = None
+_inited = False
+
+
+class PsbError(RuntimeError):
+    pass
+
+
+def lib():
+    """dlopen libpsb.so (never builds, never falls back)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PsbError(f"{LIB_PATH} missing: run `python __graft_entry__.py build` (nvcc) first; "
+                           "there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.psb_last_error.restype = C.c_char_p
+        L.psb_launch_count.restype = C.c_uint64
+        L.psb_key_create.restype = C.c_void_p
+        L.psb_key_num_attributes.restype = C.c_size_t
+        L.psb_key_table_bytes.restype = C.c_size_t
+        L.psb_verify_ws_bytes.restype = C.c_size_t
+        L.psb_microbench.restype = C.c_double
+        L.psb_key_destroy.argtypes = [C.c_void_p]
+        L.psb_key_num_attributes.argtypes = [C.c_void_p]
+        L.psb_key_table_bytes.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+EXPORTS = ["psb_init", "psb_shutdown", "psb_num_devices", "psb_last_error", "psb_launch_count",
+           "psb_key_create", "psb_key_destroy", "psb_key_num_attributes", "psb_key_table_bytes",
+           "psb_verify", "psb_verify_ws_bytes", "psb_verify_dev", "psb_randomize", "psb_provide_id",
+           "psb_verify_id", "psb_pairing", "psb_test_op_shape", "psb_test_op", "psb_microbench"]
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise PsbError(f"{what} failed ({rc}): {lib().psb_last_error().decode()}")
+
+
+def init(devices: Optional[Sequence[int]] = None) -> None:
+    """psb_init: replaces initPairing(mcl::BLS12_381) for the batch path."""
+    global _inited
+    L = lib()
+    if devices is None:
+        rc = L.psb_init(CURVE_BLS12_381, None, 0)
+    else:
+        arr = (C.c_int * len(devices))(*devices)
+        rc = L.psb_init(CURVE_BLS12_381, arr, len(devices))
+    _check(rc, "psb_init")
+    _inited = True
+
+
+def ensure_init():
+    if not _inited:
+        init()
+
+
+def launch_count() -> int:
+    return int(lib().psb_launch_count())
+
+
+def _p(a):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"], "array must be C-contiguous"
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _u64(a, width):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    return a.reshape(-1, width)
+
+
+def pack_strings(strs: Sequence[bytes]):
+    """list of bytes -> (blob uint8, offsets uint64[len+1])"""
+    off = np.zeros(len(strs) + 1, dtype=np.uint64)
+    if len(strs):
+        off[1:] = np.cumsum([len(s) for s in strs], dtype=np.uint64)
+    blob = np.frombuffer(b"".join(strs) + b"\0" * 8, dtype=np.uint8).copy()
+    return blob, off
+
+
+def pack_attrs(attrs: Sequence[Sequence[bytes]]):
+    return pack_strings([a for lane in attrs for a in lane])
+
+
+class PSPubKey:
+    """PSPubKey (src/ps-encoding.h:111-133) + optional signer secret X = g^x, resident on the GPUs
+    together with its fixed-base window tables."""
+
+    def __init__(self, g, gg, XX, Yi, YYi, X_secret=None, window_bits: int = 0):
+        ensure_init()
+        self.g = _u64(g, G1).copy()
+        self.gg = _u64(gg, G2).copy()
+        self.XX = _u64(XX, G2).copy()
+        self.Yi = _u64(Yi, G1).copy()
+        self.YYi = _u64(YYi, G2).copy()
+        self.n = self.Yi.shape[0]
+        if self.YYi.shape[0] != self.n:
+            raise ValueError("attribute size does not match")
+        self.X = None if X_secret is None else _u64(X_secret, G1).copy()
+        h = lib().psb_key_create(_p(self.g), _p(self.gg), _p(self.XX), _p(self.Yi), _p(self.YYi),
+                                 C.c_size_t(self.n), _p(self.X), C.c_int(window_bits))
+        if not h:
+            raise PsbError("psb_key_create failed: " + lib().psb_last_error().decode())
+        self.handle = C.c_void_p(h)
+
+    @property
+    def table_bytes(self) -> int:
+        return int(lib().psb_key_table_bytes(self.handle))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().psb_key_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _attr_args(pk: PSPubKey, N: int, attributes, scalars):
+    if attributes is not None:
+        if isinstance(attributes, tuple):  # pre-packed (blob, off)
+            blob, off = attributes
+        else:
+            for lane in attributes:
+                if len(lane) != pk.n:
+                    raise ValueError("attribute size does not match")
+            blob, off = pack_attrs(attributes)
+        if off.shape[0] != N * pk.n + 1:
+            raise ValueError("attribute size does not match")
+        return blob, off, None
+    m = _u64(scalars, FR)
+    if m.shape[0] != N * pk.n:
+        raise ValueError("attribute size does not match")
+    return None, None, m
+
+
+class PSVerifier:
+    """batched PSVerifier (src/ps-verifier.h:11-71)."""
+
+    def __init__(self, pk: PSPubKey):
+        self.m_pk = pk
+
+    def verify(self, sig1, sig2, all_attributes=None, scalars=None, want_gt: bool = False):
+        """batched PSVerifier::verify (src/ps-verifier.cc:13-35).  sig1/sig2: (N,18) u64;
+        all_attributes: N lists of n byte strings (or a packed (blob, off) pair), or scalars (N*n,4).
+        Returns verdict uint8[N] (and GT (N,72) if want_gt)."""
+        s1 = _u64(sig1, G1)
+        s2 = _u64(sig2, G1)
+        N = s1.shape[0]
+        if s2.shape[0] != N:
+            raise ValueError("sig1/sig2 length mismatch")
+        blob, off, m = _attr_args(self.m_pk, N, all_attributes, scalars)
+        verdict = np.zeros(N, dtype=np.uint8)
+        gt = np.zeros((N, GT), dtype=np.uint64) if want_gt else None
+        _check(lib().psb_verify(self.m_pk.handle, C.c_size_t(N), _p(s1), _p(s2), _p(blob), _p(off), _p(m),
+                                _p(verdict), _p(gt)), "psb_verify")
+        return (verdict, gt) if want_gt else verdict
+
+    def el_passo_verify_id(self, proof: dict, attributes, associated_data: Sequence[bytes], service_pt,
+                           authority_pk=None, g=None, h=None, with_id: bool = True):
+        """batched el_passo_verify_id (src/ps-verifier.cc:37-138) / _without_id_retrieval (:140-212).
+        proof: dict of arrays sig1, sig2, k, phi, E1, E2, c, rs (N, per, 4); attributes: per lane the
+        proof's attribute list (b"" = hidden)."""
+        s1 = _u64(proof["sig1"], G1)
+        N = s1.shape[0]
+        rs = np.ascontiguousarray(proof["rs"], dtype=np.uint64).reshape(N, -1, FR)
+        blob, off = pack_attrs(attributes)
+        ad_blob, ad_off = pack_strings(list(associated_data))
+        verdict = np.zeros(N, dtype=np.uint8)
+        z1 = np.zeros((1, G1), dtype=np.uint64)
+        _check(lib().psb_verify_id(
+            self.m_pk.handle, C.c_size_t(N), _p(s1), _p(_u64(proof["sig2"], G1)), _p(_u64(proof["k"], G2)),
+            _p(_u64(proof["phi"], G1)), _p(_u64(proof["E1"], G1)) if with_id else None,
+            _p(_u64(proof["E2"], G1)) if with_id else None, _p(_u64(proof["c"], FR)), _p(rs),
+            C.c_size_t(rs.shape[1]), _p(blob), _p(off), _p(ad_blob), _p(ad_off), _p(_u64(service_pt, G1)),
+            _p(_u64(authority_pk, G1)) if with_id else _p(z1), _p(_u64(g, G1)) if with_id else _p(z1),
+            _p(_u64(h, G1)) if with_id else _p(z1), C.c_int(int(with_id)), _p(verdict)), "psb_verify_id")
+        return verdict
+
+
+class PSRequester:
+    """batched PSRequester (src/ps-requester.h:11-128): verify and randomize_credential."""
+
+    def __init__(self, pk: PSPubKey):
+        self.m_pk = pk
+
+    def verify(self, sig1, sig2, all_attributes=None, scalars=None, want_gt: bool = False):
+        return PSVerifier(self.m_pk).verify(sig1, sig2, all_attributes, scalars, want_gt)
+
+    @staticmethod
+    def randomize_credential(sig1, sig2, t, want_serialized: bool = False):
+        """batched randomize_credential (src/ps-requester.cc:139-148) with host-supplied t (N,4)."""
+        ensure_init()
+        s1 = _u64(sig1, G1)
+        s2 = _u64(sig2, G1)
+        tt = _u64(t, FR)
+        N = s1.shape[0]
+        o1 = np.zeros((N, G1), dtype=np.uint64)
+        o2 = np.zeros((N, G1), dtype=np.uint64)
+        ser = np.zeros((N, 96), dtype=np.uint8) if want_serialized else None
+        _check(lib().psb_randomize(C.c_size_t(N), _p(s1), _p(s2), _p(tt), _p(o1), _p(o2), _p(ser)),
+               "psb_randomize")
+        return (o1, o2, ser) if want_serialized else (o1, o2)
+
+
+class PSSigner:
+    """batched PSSigner (src/ps-signer.h:11-96): el_passo_provide_id with host-supplied u."""
+
+    def __init__(self, pk: PSPubKey):
+        if pk.X is None:
+            raise ValueError("signer key needs X_secret")
+        self.m_pk = pk
+
+    def el_passo_provide_id(self, A, c, rs, attributes, associated_data, u):
+        A = _u64(A, G1)
+        N = A.shape[0]
+        rs = np.ascontiguousarray(rs, dtype=np.uint64).reshape(N, -1, FR)
+        blob, off = pack_attrs(attributes)
+        ad_blob, ad_off = pack_strings(list(associated_data))
+        verdict = np.zeros(N, dtype=np.uint8)
+        s1 = np.zeros((N, G1), dtype=np.uint64)
+        s2 = np.zeros((N, G1), dtype=np.uint64)
+        ser = np.zeros((N, 96), dtype=np.uint8)
+        _check(lib().psb_provide_id(self.m_pk.handle, C.c_size_t(N), _p(A), _p(_u64(c, FR)), _p(rs),
+                                    C.c_size_t(rs.shape[1]), _p(blob), _p(off), _p(ad_blob), _p(ad_off),
+                                    _p(_u64(u, FR)), _p(verdict), _p(s1), _p(s2), _p(ser)), "psb_provide_id")
+        return verdict, s1, s2, ser
+
+
+def pairing(P, Q):
+    """batched mcl::bn::pairing (bn.hpp:1711-1715)."""
+    ensure_init()
+    P = _u64(P, G1)
+    Q = _u64(Q, G2)
+    out = np.zeros((P.shape[0], GT), dtype=np.uint64)
+    _check(lib().psb_pairing(C.c_size_t(P.shape[0]), _p(P), _p(Q), _p(out)), "psb_pairing")
+    return out
+
+
+def test_op(op: int, a, b=None, c=None):
+    """element-wise arithmetic probe (csrc/testops.cuh) -- parity tests only."""
+    ensure_init()
+    s = (C.c_int * 4)()
+    _check(lib().psb_test_op_shape(op, s), "psb_test_op_shape")
+    a32 = np.ascontiguousarray(a).view(np.uint32).reshape(-1, s[0])
+    n = a32.shape[0]
+    b32 = None if b is None or s[1] == 0 else np.ascontiguousarray(b).view(np.uint32).reshape(n, s[1])
+    c32 = None if c is None or s[2] == 0 else np.ascontiguousarray(c).view(np.uint32).reshape(n, s[2])
+    out = np.zeros((n, s[3]), dtype=np.uint32)
+    _check(lib().psb_test_op(op, C.c_size_t(n), _p(a32), _p(b32), _p(c32), _p(out)), "psb_test_op")
+    return out.view(np.uint64)
+
+
+def microbench(kind: int, blocks: int, threads: int, iters: int) -> float:
+    ensure_init()
+    ms = float(lib().psb_microbench(kind, blocks, threads, iters))
+    if ms < 0:
+        raise PsbError("psb_microbench failed: " + lib().psb_last_error().decode())
+    return ms
+
+
+def verify_ws_bytes(pk: PSPubKey, N: int) -> int:
+    return int(lib().psb_verify_ws_bytes(pk.handle, C.c_size_t(N)))
+
+
+def verify_dev(pk: PSPubKey, dev_index: int, N: int, d_sig1: int, d_sig2: int, d_blob: int, d_off: int,
+               d_m: int, d_verdict: int, d_gt: int, d_ws: int, stream: int = 0) -> None:
+    """psb_verify_dev with raw device pointers (e.g. torch tensors' data_ptr())."""
+    vp = lambda x: C.c_void_p(x) if x else None  # noqa: E731
+    _check(lib().psb_verify_dev(pk.handle, C.c_int(dev_index), C.c_size_t(N), vp(d_sig1), vp(d_sig2), vp(d_blob),
+                                vp(d_off), vp(d_m), vp(d_verdict), vp(d_gt), vp(d_ws), vp(stream)),
+           "psb_verify_dev")

@@ -1,0 +1,140 @@
+"""GPU parity, layer by layer: every arithmetic op of the engine (one GPU thread per element,
+through the C ABI's psb_test_op) against the reference compiled in oracle/_ref (mcl), bit-exact on
+raw Montgomery limbs / serialized points."""
+import numpy as np
+import pytest
+
+from tests.conftest import rand_fp_raw
+
+pytestmark = pytest.mark.gpu
+
+N = 257  # ragged on purpose (not a multiple of the block size)
+
+
+@pytest.fixture(scope="module")
+def rng():
+    return np.random.default_rng(20261017)
+
+
+def edge_fp(ref, a, b):
+    from oracle import ps_oracle as O
+    a[0] = 0
+    b[1] = 0
+    a[2] = ref.fp_from_ints([O.P - 1])[0]
+    b[2] = a[2]
+    a[3] = ref.fp_from_ints([1])[0]
+    return a, b
+
+
+@pytest.mark.parametrize("op,name", [(0, "add"), (1, "sub"), (2, "mul"), (3, "sqr"), (4, "neg"), (5, "inv")])
+def test_fp(gpu_pkg, ref, rng, op, name):
+    a, b = edge_fp(ref, rand_fp_raw(ref, rng, N), rand_fp_raw(ref, rng, N))
+    if op == 5:
+        a[0] = a[5]  # mcl's inv(0) traps
+    exp = ref.fp_op(op, a, b)
+    got = gpu_pkg.test_op(op, a, b if op < 3 else None)
+    assert np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize("op", range(6))
+def test_fp2(gpu_pkg, ref, rng, op):
+    a, b = rand_fp_raw(ref, rng, N, 2), rand_fp_raw(ref, rng, N, 2)
+    a[0] = 0 if op != 5 else a[1]
+    b[1] = 0
+    assert np.array_equal(gpu_pkg.test_op(10 + op, a, b if op < 3 else None), ref.fp2_op(op, a, b))
+
+
+def test_fp6(gpu_pkg, ref, rng):
+    a, b = rand_fp_raw(ref, rng, 65, 6), rand_fp_raw(ref, rng, 65, 6)
+    assert np.array_equal(gpu_pkg.test_op(20, a, b), ref.fp6_op(ref.OP_MUL, a, b))
+    assert np.array_equal(gpu_pkg.test_op(21, a), ref.fp6_op(ref.OP_INV, a))
+
+
+def test_fp12(gpu_pkg, ref, rng):
+    a, b = rand_fp_raw(ref, rng, 65, 12), rand_fp_raw(ref, rng, 65, 12)
+    assert np.array_equal(gpu_pkg.test_op(30, a, b), ref.fp12_op(ref.OP_MUL, a, b))
+    assert np.array_equal(gpu_pkg.test_op(31, a), ref.fp12_op(ref.OP_SQR, a))
+    assert np.array_equal(gpu_pkg.test_op(32, a), ref.fp12_op(ref.OP_INV, a))
+    for k in (1, 2, 3):
+        assert np.array_equal(gpu_pkg.test_op(32 + k, a), ref.fp12_frobenius(k, a))
+
+
+@pytest.fixture(scope="module")
+def points(ref):
+    ref.seed(99)
+    g, gg = ref.hash_to_g1(b"abc"), ref.hash_to_g2(b"edf")
+    n = 33
+    k1, k2 = ref.fr_rand(n), ref.fr_rand(n)
+    return dict(P=ref.g1_mul(g, k1), P2=ref.g1_mul(g, k2), Q=ref.g2_mul(gg, k1), Q2=ref.g2_mul(gg, k2),
+                k=ref.fr_rand(n), n=n)
+
+
+def test_g1(gpu_pkg, ref, points):
+    P, P2, k = points["P"], points["P2"], points["k"]
+    s = ref.g1_serialize
+    assert np.array_equal(s(gpu_pkg.test_op(40, P, P2)), s(ref.g1_op(ref.G_ADD, P, P2)))
+    assert np.array_equal(s(gpu_pkg.test_op(41, P)), s(ref.g1_op(ref.G_DBL, P)))
+    assert np.array_equal(gpu_pkg.test_op(42, P), ref.g1_op(ref.G_NORM, P))  # raw limbs, z = 1
+    assert np.array_equal(s(gpu_pkg.test_op(40, P, P)), s(ref.g1_op(ref.G_DBL, P)))  # P + P
+    neg = ref.g1_op(ref.G_NEG, P)
+    assert not gpu_pkg.test_op(40, P, neg).any()  # P + (-P) = canonical zero
+    zero = np.zeros_like(P)
+    assert np.array_equal(s(gpu_pkg.test_op(40, zero, P2)), s(P2))
+    assert np.array_equal(s(gpu_pkg.test_op(43, P, k)), s(ref.g1_mul(P, k)))
+    assert np.array_equal(s(gpu_pkg.test_op(44, P, ref.g1_op(ref.G_NORM, P2))), s(ref.g1_op(ref.G_ADD, P, P2)))
+
+
+def test_g2(gpu_pkg, ref, points):
+    Q, Q2, k = points["Q"], points["Q2"], points["k"]
+    s = ref.g2_serialize
+    assert np.array_equal(s(gpu_pkg.test_op(50, Q, Q2)), s(ref.g2_op(ref.G_ADD, Q, Q2)))
+    assert np.array_equal(s(gpu_pkg.test_op(51, Q)), s(ref.g2_op(ref.G_DBL, Q)))
+    assert np.array_equal(gpu_pkg.test_op(52, Q), ref.g2_op(ref.G_NORM, Q))
+    assert np.array_equal(s(gpu_pkg.test_op(50, Q, Q)), s(ref.g2_op(ref.G_DBL, Q)))
+    assert np.array_equal(s(gpu_pkg.test_op(53, Q, k)), s(ref.g2_mul(Q, k)))
+    assert np.array_equal(s(gpu_pkg.test_op(54, Q, ref.g2_op(ref.G_NORM, Q2))), s(ref.g2_op(ref.G_ADD, Q, Q2)))
+
+
+def test_scalar_edge_cases(gpu_pkg, ref, points):
+    """scalars 0, 1, 2, r-1 (mcl's small-int fast path, ec.hpp:1140-1260, must give the same point)."""
+    from oracle import ps_oracle as O
+    P = points["P"][:4]
+    k = ref.fr_from_ints([0, 1, 2, O.R - 1])
+    assert np.array_equal(ref.g1_serialize(gpu_pkg.test_op(43, P, k)), ref.g1_serialize(ref.g1_mul(P, k)))
+
+
+def test_pairing(gpu_pkg, ref, points):
+    P, Q = points["P"][:9], points["Q"][:9]
+    exp = ref.pairing(P, Q)
+    assert np.array_equal(gpu_pkg.test_op(60, P, Q), exp)       # probe path
+    assert np.array_equal(gpu_pkg.pairing(P, Q), exp)           # psb_pairing entry
+    f = ref.miller_loop(P, Q)
+    assert np.array_equal(gpu_pkg.test_op(61, f), ref.final_exp(f))  # final exponentiation on mcl's Miller value
+    cyc = exp
+    assert np.array_equal(gpu_pkg.test_op(36, cyc), ref.fp12_op(ref.OP_SQR, cyc))  # cyclotomic squaring
+
+
+def test_pairing_zero_points(gpu_pkg, ref, points):
+    """e(0, Q) = e(P, 0) = 1 (mcl: bn.hpp:1666-1669; bls12_test.cpp:288-296)."""
+    P, Q = points["P"][:2].copy(), points["Q"][:2].copy()
+    P[0] = 0
+    Q[1] = 0
+    assert np.array_equal(gpu_pkg.pairing(P, Q), ref.pairing(P, Q))
+
+
+def test_pairing_ratio_fixed_lines(gpu_pkg, ref, points):
+    P, Q, P2 = points["P"][:5], points["Q"][:5], points["P2"][:5]
+    Q2 = ref.g2_op(ref.G_NORM, points["Q2"][:5])
+    c = np.concatenate([P2, Q2], axis=1)
+    assert np.array_equal(gpu_pkg.test_op(62, P, Q, c), ref.pairing_ratio(P, Q, P2, Q2))
+
+
+def test_fr(gpu_pkg, ref):
+    ref.seed(5)
+    a, b = ref.fr_rand(64), ref.fr_rand(64)
+    assert np.array_equal(gpu_pkg.test_op(71, a, b), ref.fr_op(ref.OP_MUL, a, b))
+    assert np.array_equal(gpu_pkg.test_op(72, a, b), ref.fr_op(ref.OP_SUB, a, b))
+    assert np.array_equal(gpu_pkg.test_op(73, a, b), ref.fr_op(ref.OP_ADD, a, b))
+    ints = ref.fr_to_ints(a)
+    got = gpu_pkg.test_op(70, a)
+    assert [int.from_bytes(got[i].tobytes(), "little") for i in range(64)] == ints

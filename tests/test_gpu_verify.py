@@ -1,0 +1,73 @@
+"""GPU parity of the batched PS verification (psb_verify through the C ABI) against the reference's
+own PSVerifier::verify (oracle/_ref), incl. tampered lanes, edge cases, both attribute input forms,
+and the fused-lane GT bytes."""
+import numpy as np
+import pytest
+
+from tests import workload
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n_attrs,lanes,w", [(5, 130, 8), (5, 64, 16), (1, 33, 4), (3, 40, 11), (0, 8, 8)])
+def test_verify_matches_reference(gpu_pkg, ref, n_attrs, lanes, w):
+    wl = workload.make_verify_workload(n_attrs=n_attrs, lanes=lanes, seed=11, tamper_every=5)
+    pk = gpu_pkg.PSPubKey(wl.key.g, wl.key.gg, wl.key.XX, wl.key.Y, wl.key.YY, window_bits=w)
+    exp_v, exp_gt = workload.expected_verify(wl, want_gt=True)
+    got_v, got_gt = gpu_pkg.PSVerifier(pk).verify(wl.sig1, wl.sig2, wl.attrs, want_gt=True)
+    assert np.array_equal(got_v, exp_v)
+    assert exp_v.sum() == lanes - len(wl.tampered)  # honest lanes accept, tampered lanes reject
+    live = wl.sig1[:, 12:].any(axis=1)  # reference returns before pairing when sig1 == 0
+    assert np.array_equal(got_gt[live], exp_gt[live])
+    # same lanes, scalars supplied by the host instead of attribute strings
+    if n_attrs:
+        m = ref.fr_set_hash_of_batch([a for lane in wl.attrs for a in lane])
+        assert np.array_equal(gpu_pkg.PSVerifier(pk).verify(wl.sig1, wl.sig2, scalars=m), exp_v)
+    pk.close()
+
+
+def test_verify_unnormalized_inputs(gpu_pkg, ref):
+    """credentials and key points with arbitrary Jacobian z (straight out of G1::mul) verify the same."""
+    wl = workload.make_verify_workload(n_attrs=2, lanes=16, seed=3)
+    ref.seed(77)
+    t = ref.fr_rand(16)
+    s1, s2, _ = ref.randomize(wl.sig1, wl.sig2, t)  # raw Jacobian outputs of mcl, z != 1
+    assert (s1[:, 12:] != wl.sig1[:, 12:]).any()
+    pk = gpu_pkg.PSPubKey(wl.key.g, wl.key.gg, wl.key.XX, wl.key.Y, wl.key.YY, window_bits=8)
+    exp = ref.ps_verify(wl.key, s1, s2, wl.attrs)
+    assert exp.all()
+    assert np.array_equal(gpu_pkg.PSVerifier(pk).verify(s1, s2, wl.attrs), exp)
+
+
+def test_verify_edge_lanes(gpu_pkg, ref):
+    """sigma1 = 0 rejects; sigma2 = 0 with valid sigma1 rejects; empty attribute strings hash fine;
+    N = 0 and N = 1 work."""
+    wl = workload.make_verify_workload(n_attrs=2, lanes=6, seed=4)
+    pk = gpu_pkg.PSPubKey(wl.key.g, wl.key.gg, wl.key.XX, wl.key.Y, wl.key.YY, window_bits=8)
+    v = gpu_pkg.PSVerifier(pk)
+    wl.sig1[0] = 0
+    wl.sig2[1] = 0
+    wl.attrs[2][1] = b""
+    wl.attrs[3][0] = b"x" * 200  # multi-block SHA-256
+    exp = ref.ps_verify(wl.key, wl.sig1, wl.sig2, wl.attrs)
+    assert np.array_equal(v.verify(wl.sig1, wl.sig2, wl.attrs), exp)
+    assert list(exp) == [0, 0, 0, 0, 1, 1]
+    assert v.verify(wl.sig1[:0], wl.sig2[:0], []).shape == (0,)
+    assert np.array_equal(v.verify(wl.sig1[4:5], wl.sig2[4:5], wl.attrs[4:5]), exp[4:5])
+    with pytest.raises(ValueError):
+        v.verify(wl.sig1, wl.sig2, [a[:1] for a in wl.attrs])  # attribute size does not match
+
+
+def test_verify_large_batch_properties(gpu_pkg, ref):
+    """2^13 lanes: every honest lane accepts, every tampered lane rejects, and a sampled subset agrees
+    with the reference lane by lane (full-size property check)."""
+    lanes = 1 << 13
+    wl = workload.make_verify_workload(n_attrs=5, lanes=lanes, seed=21, tamper_every=64)
+    pk = gpu_pkg.PSPubKey(wl.key.g, wl.key.gg, wl.key.XX, wl.key.Y, wl.key.YY)
+    got = gpu_pkg.PSVerifier(pk).verify(wl.sig1, wl.sig2, (wl.blob, wl.off))
+    mask = np.ones(lanes, dtype=bool)
+    mask[wl.tampered] = False
+    assert got[mask].all() and not got[~mask].any()
+    idx = np.concatenate([np.arange(0, lanes, 37), wl.tampered])
+    sub = ref.ps_verify(wl.key, wl.sig1[idx], wl.sig2[idx], [wl.attrs[i] for i in idx], nthreads=ref.hw_threads())
+    assert np.array_equal(got[idx], sub)

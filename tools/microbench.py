@@ -1,0 +1,33 @@
+#!/usr/bin/env python3
+"""tools/microbench.py -- device-timed micro-benchmarks (run under gpurun): the integer-multiply
+issue rate of this B200 (the roofline denominator for every kernel here) and the
+throughput of the engine's Fp / Fp2 / Fp12 multiplications at several occupancies.
+Writes one JSON object to stdout (and to gpurun_out/microbench.json when that directory exists)."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+pkg = ge.load_package()
+pkg.init([0])
+SM = 148
+res = {"mad": [], "field": []}
+for kind, name, per_iter in [(6, "imad32 (mul.lo+add)", 16), (4, "mad.lo.cc+madc.hi (MAC32)", 8), (5, "mad.wide.u32 (MAC32)", 8)]:
+    for bps, thr in [(1, 256), (2, 256), (4, 256), (8, 256), (4, 128), (2, 1024)]:
+        iters = 20000
+        ms = pkg.microbench(kind, SM * bps, thr, iters)
+        ops = SM * bps * thr * iters * per_iter
+        res["mad"].append({"probe": name, "blocks_per_sm": bps, "threads": thr, "ms": ms,
+                           "Tops_per_s": ops / ms / 1e9, "ops_per_clk_per_sm_at_1965MHz": ops / (ms * 1e-3) / SM / 1.965e9})
+for kind, name, iters in [(0, "fp_mul", 2000), (1, "fp_sqr", 2000), (2, "fp2_mul", 1000), (3, "fp12_mul", 50)]:
+    for bps, thr in [(1, 128), (1, 256), (2, 128), (2, 256), (3, 128), (4, 128), (4, 256), (8, 128)]:
+        ms = pkg.microbench(kind, SM * bps, thr, iters)
+        ops = SM * bps * thr * iters
+        res["field"].append({"op": name, "blocks_per_sm": bps, "threads": thr, "ms": ms, "Gops_per_s": ops / ms / 1e6})
+out = json.dumps(res, indent=1)
+print(out)
+if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+    open(os.path.join(ROOT, "gpurun_out", "microbench.json"), "w").write(out)
