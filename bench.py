@@ -1,0 +1,347 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark: batched PS signature verification, 5 attributes, 2^20 signatures
+per B200 (BASELINE.json configs[1]); one JSON line on stdout.
+
+  python bench.py --gpus N --steps K --warmup W            # our CUDA engine (torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...   # the reference's own mcl CPU path
+
+A "step" is one pass of PSVerifier::verify over the whole synthetic batch.  `value` = verifications
+per second with inputs resident in HBM (psb_verify_dev, CUDA events on the launching stream, max over
+ranks); `e2e` = the same through the host-buffer C-ABI call (psb_verify: H2D copies of signatures,
+attribute strings and offsets + D2H of the verdict bytes inside the timed region).  Lanes shard over
+ranks with no data-path collective (weak scaling: 2^20 lanes per GPU).
+
+Synthetic data: key material from tests/golden/keys.json (seeded reference keygen with known
+exponents), 2^14 distinct honest signatures built with the engine's own G1 kernels, expanded to the
+full batch by per-lane randomisation (psb_randomize); every 1024-th lane tampered.  The oracle is
+used only as the checker of a lane sample and for the cpu_baseline / --impl reference legs.
+"""
+from __future__ import annotations
+
+import argparse
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+R_ORDER = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+N_ATTRS = 5
+# algorithmic work per verification in 32x32->64 multiply-accumulates:
+FPMUL_MAC32 = 300
+A_MILLER2 = 7673      # two-pairing Miller loop, FpMul-eq
+A_FINALEXP = 6100 + 480
+A_MSM_PER_ADD = 29    # one mixed Jacobian+affine G2 addition
+
+
+def a_verify_fpmul(n_attrs: int, window_bits: int) -> float:
+    nwin = (256 + window_bits - 1) // window_bits
+    return A_MILLER2 + A_FINALEXP + n_attrs * nwin * A_MSM_PER_ADD
+
+
+def fr_hash(msg: bytes) -> int:
+    """Fr::setHashOf rule (host-side scalar bookkeeping of the workload generator)."""
+    x = int.from_bytes(hashlib.sha256(msg).digest(), "little") & ((1 << 255) - 1)
+    if x >= R_ORDER:
+        x &= (1 << 254) - 1
+    return x
+
+
+def fr_mont(vals) -> np.ndarray:
+    out = np.empty((len(vals), 4), dtype=np.uint64)
+    for i, v in enumerate(vals):
+        out[i] = np.frombuffer(((v << 256) % R_ORDER).to_bytes(32, "little"), dtype=np.uint64)
+    return out
+
+
+def load_key(n: int):
+    with open(os.path.join(ROOT, "tests", "golden", "keys.json")) as f:
+        k = json.load(f)["keys"][str(n)]
+    arr = lambda h, w: np.frombuffer(bytes.fromhex(h), dtype=np.uint64).reshape(-1, w).copy()  # noqa: E731
+    return dict(g=arr(k["g"], 18), gg=arr(k["gg"], 36), XX=arr(k["XX"], 36), Y=arr(k["Y"], 18), YY=arr(k["YY"], 36),
+                X=arr(k["X"], 18), x=int(k["x"], 16), y=[int(v, 16) for v in k["y"]])
+
+
+def make_batch(pkg, key, lanes: int, rank: int, base: int = 1 << 14):
+    """(sig1, sig2, blob, off, expected verdict) for `lanes` lanes."""
+    base = min(base, lanes)
+    rng = np.random.default_rng(1000 + rank)
+    attrs = [[b"a%d:%d" % (i, j) for i in range(N_ATTRS)] for j in range(base)]
+    s = [(key["x"] + sum(key["y"][i] * fr_hash(a[i]) for i in range(N_ATTRS))) % R_ORDER for a in attrs]
+    u = [int.from_bytes(rng.bytes(32), "little") % R_ORDER for _ in range(base)]
+    b1 = pkg.g1_mul(key["g"], fr_mont(u))                                  # sigma1 = u g
+    b2 = pkg.g1_mul(key["g"], fr_mont([a * b % R_ORDER for a, b in zip(u, s)]))  # sigma2 = s sigma1
+    reps = (lanes + base - 1) // base
+    sig1 = np.tile(b1, (reps, 1))[:lanes].copy()
+    sig2 = np.tile(b2, (reps, 1))[:lanes].copy()
+    if reps > 1:  # make every lane distinct: (t sigma1, t sigma2) with a per-lane t
+        t = np.frombuffer(rng.bytes(32 * lanes), dtype=np.uint64).reshape(lanes, 4).copy()
+        t[:, 3] &= np.uint64(0x0FFFFFFFFFFFFFFF)  # < r; raw limbs are simply interpreted as Montgomery form
+        sig1, sig2 = pkg.PSRequester.randomize_credential(sig1, sig2, t)
+    lane_attrs = [attrs[j % base] for j in range(lanes)]
+    expected = np.ones(lanes, dtype=np.uint8)
+    for n_t, j in enumerate(range(1023, lanes, 1024)):
+        kind = n_t % 3
+        if kind == 0:
+            sig1[j], sig2[j] = sig2[j].copy(), sig1[j].copy()
+        elif kind == 1:
+            sig1[j] = 0
+        else:
+            a = list(lane_attrs[j]); a[0] = b"b" + a[0][1:]; lane_attrs[j] = a
+        expected[j] = 0
+    blob, off = pkg.pack_attrs(lane_attrs)
+    return sig1, sig2, blob, off, expected, lane_attrs
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "power_w_max": max(float(r[2]) for r in self.rows if len(r) >= 7), "samples": len(sm)}
+
+
+def cpu_reference_verify(key_n: int, sig1, sig2, lane_attrs, budget_s: float):
+    """the reference's own PSVerifier::verify (mcl) on all host threads over a bounded lane sample."""
+    from oracle import ref
+    km = ref.KeyMaterial(key_n, seed_=1)
+    threads = ref.hw_threads()
+    n = min(len(lane_attrs), 64 * threads)
+    blob, off = ref.pack_attrs(lane_attrs[:n])
+    v, t = ref.ps_verify_packed(km, sig1[:n].copy(), sig2[:n].copy(), blob, off, nthreads=threads, timed=True)
+    rate = n / t
+    n2 = int(min(len(lane_attrs), max(n, rate * budget_s)))
+    if n2 > n:
+        blob, off = ref.pack_attrs(lane_attrs[:n2])
+        v, t = ref.ps_verify_packed(km, sig1[:n2].copy(), sig2[:n2].copy(), blob, off, nthreads=threads, timed=True)
+        n = n2
+    pair_iters = 200
+    tp = ref.time_pairing(pair_iters, threads)
+    return dict(verdict=v, lanes=n, seconds=t, threads=threads, rate=n / t, pairings_per_s=pair_iters * threads / tp,
+                jit=ref.jit_enabled())
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--lanes", type=int, default=1 << 20, help="lanes per GPU (the named config is 2^20)")
+    ap.add_argument("--window-bits", type=int, default=16)
+    ap.add_argument("--cpu-budget-s", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = f"ps_verify n_attrs={N_ATTRS} lanes_per_gpu={args.lanes} BLS12-381"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        import __graft_entry__ as ge
+        key = load_key(N_ATTRS)
+        from oracle import ref
+        from tests import workload as wlmod
+        km = ref.KeyMaterial(N_ATTRS, seed_=1)
+        threads = ref.hw_threads()
+        sample = 256 * threads
+        attrs = wlmod.attr_strings(N_ATTRS, sample)
+        sig1, sig2 = wlmod.sign_lanes(km, attrs, seed=2, nthreads=threads)
+        blob, off = ref.pack_attrs(attrs)
+        times = []
+        for it in range(args.warmup + args.steps):
+            v, t = ref.ps_verify_packed(km, sig1, sig2, blob, off, nthreads=threads, timed=True)
+            assert v.all()
+            if it >= args.warmup:
+                times.append(t)
+        val = sample * len(times) / sum(times)
+        line = {"impl": "reference", "metric": "ps_verifications_per_sec", "value": val, "unit": "verifications/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u64-limbs (mcl, Xbyak JIT=%d)" % int(ref.jit_enabled()), "data": "synthetic",
+                "config": {"workload": workload, "reference": "PSVerifier::verify via mcl (oracle/_ref/libpsref.so)"},
+                "cpu_baseline": {"value": val, "unit": "verifications/s", "cores": threads, "kind": "reference",
+                                 "sample": f"{sample} lanes per step"},
+                "e2e": {"value": val, "unit": "verifications/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pkg.init([local_rank])
+    dev = torch.device("cuda", local_rank)
+
+    key = load_key(N_ATTRS)
+    pk = pkg.PSPubKey(key["g"], key["gg"], key["XX"], key["Y"], key["YY"], window_bits=args.window_bits)
+    N = args.lanes
+    sig1, sig2, blob, off, expected, lane_attrs = make_batch(pkg, key, N, rank)
+
+    # measured integer-MAC peak of this GPU (roofline denominator), a few hundred ms
+    peak_ms = min(pkg.microbench(5, 148 * 8, 256, 20000) for _ in range(2))
+    peak_mac = 148 * 8 * 256 * 20000 * 8 / (peak_ms * 1e-3)
+    peak_ms2 = min(pkg.microbench(4, 148 * 8, 256, 20000) for _ in range(2))
+    peak_mac = max(peak_mac, 148 * 8 * 256 * 20000 * 8 / (peak_ms2 * 1e-3))
+
+    # ---- device-resident arm -------------------------------------------------------------------
+    t_s1 = torch.from_numpy(sig1.view(np.int64)).to(dev)
+    t_s2 = torch.from_numpy(sig2.view(np.int64)).to(dev)
+    t_blob = torch.from_numpy(blob).to(dev)
+    t_off = torch.from_numpy(off.view(np.int64)).to(dev)
+    t_verdict = torch.zeros(N, dtype=torch.uint8, device=dev)
+    t_ws = torch.empty(pkg.verify_ws_bytes(pk, N), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step_dev():
+        pkg.verify_dev(pk, 0, N, t_s1.data_ptr(), t_s2.data_ptr(), t_blob.data_ptr(), t_off.data_ptr(), 0,
+                       t_verdict.data_ptr(), 0, t_ws.data_ptr(), stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step_dev()
+    torch.cuda.synchronize(dev)
+    got = t_verdict.cpu().numpy()
+    if not np.array_equal(got, expected):
+        raise SystemExit(f"verdict mismatch on {int((got != expected).sum())} lanes")
+
+    pkg.set_profiling(True)
+    phase = np.zeros(3)
+    launches0 = pkg.launch_count()
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step_dev()
+            phase += np.array(pkg.last_phase_ms(0))  # waits for this step (steps are serial anyway)
+        ev1.record(stream)
+        barrier()
+        ms_total = ev0.elapsed_time(ev1)
+    launches = pkg.launch_count() - launches0
+    pkg.set_profiling(False)
+    phase /= args.steps
+
+    # ---- end-to-end arm: host buffers through psb_verify ----------------------------------------------
+    ver = pkg.PSVerifier(pk)
+    ver.verify(sig1[:4096], sig2[:4096], (blob[:int(off[4096 * N_ATTRS]) + 8], off[:4096 * N_ATTRS + 1]))  # staging warm-up
+    e2e_steps = max(1, min(args.steps, 2))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        v_e2e = ver.verify(sig1, sig2, (blob, off))
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    if not np.array_equal(v_e2e, expected):
+        raise SystemExit("e2e verdict mismatch")
+    h2d = int(sig1.nbytes + sig2.nbytes + int(off[-1]) + off.nbytes)
+    d2h = int(N)
+
+    t_ms = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t_ms[0]), float(t_ms[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = world * N * args.steps / (ms_total * 1e-3)
+    e2e_val = world * N * e2e_steps / (e2e_ms * 1e-3)
+    names = ["k_verify_msm", "k_verify_miller", "k_verify_final"]
+    nwin = (256 + args.window_bits - 1) // args.window_bits
+    work = [N_ATTRS * nwin * A_MSM_PER_ADD, A_MILLER2, A_FINALEXP]
+    dom = int(np.argmax(phase))
+    achieved = work[dom] * FPMUL_MAC32 * N / (phase[dom] * 1e-3)
+    whole = a_verify_fpmul(N_ATTRS, args.window_bits) * FPMUL_MAC32 * value / world
+    line = {
+        "metric": "ps_verifications_per_sec", "value": value, "unit": "verifications/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32-limbs (381-bit Montgomery, int32 MAC)", "data": "synthetic",
+        "config": {"workload": workload, "window_bits": args.window_bits, "table_bytes": pk.table_bytes,
+                   "l2": "inputs + phase state (%.0f MB) exceed the 126 MB L2" % ((sig1.nbytes * 2 + len(t_ws)) / 1e6),
+                   "parallelism": f"lanes sharded over {world} GPU(s), no collective"},
+        "e2e": {"value": e2e_val, "unit": "verifications/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "roofline": {"bound": "int32-mac", "kernel": names[dom], "achieved": achieved / 1e12, "peak": peak_mac / 1e12,
+                     "unit": "TMAC32/s", "frac": achieved / peak_mac, "traffic": None,
+                     "peak_source": "measured live (mad.wide / mad.lo+hi probe, all SMs)",
+                     "whole_step_frac": whole / peak_mac,
+                     "phase_ms": dict(zip(names, [float(x) for x in phase])),
+                     "hbm": {"algorithmic_bytes_per_lane": h2d / N + 1 + 864 * 2,
+                             "achieved_GBps": (h2d / N + 1 + 864 * 2) * value / world / 1e9}},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cb = cpu_reference_verify(N_ATTRS, sig1, sig2, lane_attrs, args.cpu_budget_s)
+            agree = bool(np.array_equal(cb["verdict"], got[:cb["lanes"]]))
+            line["cpu_baseline"] = {"value": cb["rate"], "unit": "verifications/s", "cores": cb["threads"], "kind": "reference",
+                                    "sample": f"first {cb['lanes']} lanes of the same batch, PSVerifier::verify via mcl "
+                                              f"(JIT={int(cb['jit'])}), {cb['seconds']:.1f} s",
+                                    "pairings_per_s": cb["pairings_per_s"], "verdicts_agree_with_gpu": agree}
+            if not agree:
+                raise SystemExit("GPU verdicts disagree with the reference on the CPU sample")
+        except OSError as e:  # libpsref.so absent
+            line["cpu_baseline"] = {"value": None, "unit": "verifications/s", "cores": 0, "kind": "reference",
+                                    "sample": f"unavailable: {e}"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

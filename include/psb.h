@@ -71,11 +71,22 @@ int psb_verify_dev(psb_key* key, int dev_index, size_t N, const uint64_t* d_sig1
                    const uint8_t* d_attr_blob, const uint64_t* d_attr_off, const uint64_t* d_m,
                    uint8_t* d_verdict, uint64_t* d_gt, void* d_ws, void* stream);
 
+/* Per-phase device timing of psb_verify / psb_verify_dev: when profiling is on, CUDA events are
+ * recorded on the launching stream around the three phase kernels (fixed-base MSM, multi-Miller
+ * loop, final exponentiation); psb_last_phase_ms waits for the last profiled batch on that device
+ * and returns the three durations in milliseconds. */
+int psb_set_profiling(int on);
+int psb_last_phase_ms(int dev_index, float ms[3]);
+
 /* Batched PSRequester::randomize_credential (src/ps-requester.cc:139-148) with host-supplied
  * scalars t (N Fr, Montgomery): out = (t*sig1, t*sig2), NORMALISED (z = 1; infinity = all zero).
  * ser (optional, N x 96 bytes) = mcl serialisation of out1 || out2 (ec.hpp:849-896). */
 int psb_randomize(size_t N, const uint64_t* sig1, const uint64_t* sig2, const uint64_t* t,
                   uint64_t* out1, uint64_t* out2, uint8_t* ser);
+
+/* Batched G1::mul (mcl/include/mcl/ec.hpp:1124-1139): out[j] = k[j] * P[j] (p_stride = 1) or k[j] * P[0]
+ * (p_stride = 0), normalised.  k: N Fr, Montgomery. */
+int psb_g1_mul(size_t N, const uint64_t* P, int p_stride, const uint64_t* k, uint64_t* out);
 
 /* Batched PSSigner::el_passo_provide_id (src/ps-signer.cc:63-146): NIZK check of the request
  * (A, c, rs[rs_per_lane], attributes with "" = hidden, associated data), then

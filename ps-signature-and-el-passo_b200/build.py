@@ -33,8 +33,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          [os.path.join(CSRC, "psb_api.cu"), "-o", LIB]
+    extra = os.environ.get("PSB_EXTRA_FLAGS", "").split()
+    out = os.environ.get("PSB_LIB_OUT", LIB)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
+          [os.path.join(CSRC, "psb_api.cu"), "-o", out]
     subprocess.check_call(cmd, cwd=CSRC)
     return LIB
 

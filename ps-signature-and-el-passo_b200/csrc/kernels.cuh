@@ -253,4 +253,85 @@ __global__ void __launch_bounds__(kBlock) k_final_exp(size_t N, const Fp12* fin,
   out[lane] = e;
 }
 
+
+// ---- serialisation (mcl compressed little-endian form, ec.hpp:849-896, non-ETH mode) -----------------
+// G1: x as 48 LE bytes of the NORMAL form, bit 7 of the last byte = y odd; infinity = 48 zero bytes.
+PSB_HD PSB_NOINL void g1_serialize_norm(uint8_t* out, const G1J& P /*normalised or zero*/) {
+  if (fp_is_zero(P.z)) { for (int i = 0; i < 48; i++) out[i] = 0; return; }
+  Fp x, y;
+  fp_from_mont(x, P.x);
+  fp_from_mont(y, P.y);
+  for (int i = 0; i < 12; i++) {
+    out[4 * i] = (uint8_t)x.v[i]; out[4 * i + 1] = (uint8_t)(x.v[i] >> 8);
+    out[4 * i + 2] = (uint8_t)(x.v[i] >> 16); out[4 * i + 3] = (uint8_t)(x.v[i] >> 24);
+  }
+  if (y.v[0] & 1u) out[47] |= 0x80;
+}
+// G2: x.a || x.b (96 bytes), parity of y.a (fp_tower.hpp:312) in bit 7 of the last byte.
+PSB_HD PSB_NOINL void g2_serialize_norm(uint8_t* out, const G2J& P) {
+  if (fp2_is_zero(P.z)) { for (int i = 0; i < 96; i++) out[i] = 0; return; }
+  Fp xa, xb, ya;
+  fp_from_mont(xa, P.x.a);
+  fp_from_mont(xb, P.x.b);
+  fp_from_mont(ya, P.y.a);
+  for (int i = 0; i < 12; i++) {
+    out[4 * i] = (uint8_t)xa.v[i]; out[4 * i + 1] = (uint8_t)(xa.v[i] >> 8);
+    out[4 * i + 2] = (uint8_t)(xa.v[i] >> 16); out[4 * i + 3] = (uint8_t)(xa.v[i] >> 24);
+    out[48 + 4 * i] = (uint8_t)xb.v[i]; out[48 + 4 * i + 1] = (uint8_t)(xb.v[i] >> 8);
+    out[48 + 4 * i + 2] = (uint8_t)(xb.v[i] >> 16); out[48 + 4 * i + 3] = (uint8_t)(xb.v[i] >> 24);
+  }
+  if (ya.v[0] & 1u) out[95] |= 0x80;
+}
+
+// normalise two G1 points with ONE field inversion (Montgomery's trick); zero points stay canonical zero
+PSB_HD PSB_NOINL void g1_normalize2(G1J& A, G1J& B) {
+  const bool za = fp_is_zero(A.z), zb = fp_is_zero(B.z);
+  Fp one; fp_set_one(one);
+  Fp a = za ? one : A.z, b = zb ? one : B.z, ab, inv, ia, ib, t;
+  fp_mul(ab, a, b);
+  fp_inv(inv, ab);
+  fp_mul(ia, inv, b);
+  fp_mul(ib, inv, a);
+  if (za) { pt_set_zero(A); } else {
+    fp_sqr(t, ia); fp_mul(A.x, A.x, t); fp_mul(t, t, ia); fp_mul(A.y, A.y, t); A.z = one;
+  }
+  if (zb) { pt_set_zero(B); } else {
+    fp_sqr(t, ib); fp_mul(B.x, B.x, t); fp_mul(t, t, ib); fp_mul(B.y, B.y, t); B.z = one;
+  }
+}
+
+// ---- PSRequester::randomize_credential (src/ps-requester.cc:139-148) -----------------------------------
+// out = (t sig1, t sig2) normalised; t host-supplied (Fr Montgomery)
+__global__ void __launch_bounds__(kBlock) k_randomize(size_t N, const G1J* sig1, const G1J* sig2, const Fr* t,
+                                                       G1J* out1, G1J* out2, uint8_t* ser) {
+  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= N) return;
+  Fr k, kn;
+  k = t[lane];
+  fr_from_mont(kn, k);
+  G1J a = sig1[lane], b = sig2[lane], ra, rb;
+  pt_mul(ra, a, kn.v);
+  pt_mul(rb, b, kn.v);
+  g1_normalize2(ra, rb);
+  out1[lane] = ra;
+  out2[lane] = rb;
+  if (ser) {
+    g1_serialize_norm(ser + lane * 96, ra);
+    g1_serialize_norm(ser + lane * 96 + 48, rb);
+  }
+}
+
+// out[j] = k[j] * P[j or 0], normalised (generic batched G1::mul, used to synthesise workloads)
+__global__ void __launch_bounds__(kBlock) k_g1_mul(size_t N, const G1J* P, int p_stride, const Fr* k, G1J* out) {
+  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= N) return;
+  Fr kk, kn;
+  kk = k[lane];
+  fr_from_mont(kn, kk);
+  G1J a = P[p_stride ? lane : 0], r, n;
+  pt_mul(r, a, kn.v);
+  pt_normalize(n, r);
+  out[lane] = n;
+}
+
 }  // namespace psb

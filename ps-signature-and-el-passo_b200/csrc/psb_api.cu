@@ -30,6 +30,7 @@ struct Dev {
   cudaStream_t stream = nullptr;
   DevBuf in[8];   // staging for host-pointer entry points
   DevBuf ws;      // phase hand-over scratch
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // phase boundaries of the last verify (profiling)
   std::mutex mu;  // one batch at a time per device
 };
 
@@ -37,6 +38,7 @@ std::vector<Dev*> g_devs;
 bool g_init = false;
 thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
+bool g_profile = false;
 
 int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
   char buf[512];
@@ -108,12 +110,21 @@ int verify_launch(const psb_key* key, int di, size_t N, const G1J* d_sig1, const
   const KeyDev& kd = key->d[di];
   G2J* dK = (G2J*)d_ws;
   Fp12* dF = (Fp12*)((char*)d_ws + N * sizeof(G2J));
+  Dev* dv = g_devs[di];
+  const bool prof = g_profile;
+  if (prof) {
+    for (auto& e : dv->ev) if (!e) CK(cudaEventCreate(&e));
+    CK(cudaEventRecord(dv->ev[0], st));
+  }
   k_verify_msm<<<nblocks(N), kBlock, 0, st>>>(N, (int)key->n, key->w, d_blob, d_off, d_m, kd.g2pts + 1, kd.tblYY, dK);
   LAUNCHED();
+  if (prof) CK(cudaEventRecord(dv->ev[1], st));
   k_verify_miller<<<nblocks(N), kBlock, 0, st>>>(N, d_sig1, d_sig2, dK, kd.lines, dF);
   LAUNCHED();
+  if (prof) CK(cudaEventRecord(dv->ev[2], st));
   k_verify_final<<<nblocks(N), kBlock, 0, st>>>(N, d_sig1, dF, d_verdict, d_gt);
   LAUNCHED();
+  if (prof) CK(cudaEventRecord(dv->ev[3], st));
   CK(cudaGetLastError());
   return PSB_OK;
 }
@@ -125,6 +136,16 @@ extern "C" {
 const char* psb_last_error(void) { return g_err.c_str(); }
 uint64_t psb_launch_count(void) { return g_launches.load(); }
 int psb_num_devices(void) { return g_init ? (int)g_devs.size() : 0; }
+int psb_set_profiling(int on) { g_profile = on != 0; return PSB_OK; }
+int psb_last_phase_ms(int dev_index, float* ms) {
+  if (!g_init || dev_index < 0 || dev_index >= (int)g_devs.size() || !ms) return fail(PSB_ERR_ARG, "bad argument");
+  Dev* dv = g_devs[dev_index];
+  if (!dv->ev[3]) return fail(PSB_ERR_ARG, "no profiled verify yet");
+  CK(cudaSetDevice(dv->ordinal));
+  CK(cudaEventSynchronize(dv->ev[3]));
+  for (int i = 0; i < 3; i++) CK(cudaEventElapsedTime(&ms[i], dv->ev[i], dv->ev[i + 1]));
+  return PSB_OK;
+}
 
 int psb_init(int curve, const int* devices, int ndev) {
   if (curve != PSB_CURVE_BLS12_381) return fail(PSB_ERR_UNSUPPORTED, "only BLS12-381 (curve 5) is built");
@@ -157,6 +178,7 @@ void psb_shutdown(void) {
     cudaSetDevice(d->ordinal);
     for (auto& b : d->in) if (b.p) cudaFree(b.p);
     if (d->ws.p) cudaFree(d->ws.p);
+    for (auto& e : d->ev) if (e) cudaEventDestroy(e);
     if (d->stream) cudaStreamDestroy(d->stream);
     delete d;
   }
@@ -375,9 +397,63 @@ double psb_microbench(int kind, int blocks, int threads, int iters) {
 }
 
 // ---- entry points still to be built this round (declared in psb.h) ---------------------------------
-int psb_randomize(size_t, const uint64_t*, const uint64_t*, const uint64_t*, uint64_t*, uint64_t*, uint8_t*) {
-  return fail(PSB_ERR_UNSUPPORTED, "psb_randomize: not built yet");
+int psb_randomize(size_t N, const uint64_t* sig1, const uint64_t* sig2, const uint64_t* t, uint64_t* out1,
+                  uint64_t* out2, uint8_t* ser) {
+  if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
+  if (!sig1 || !sig2 || !t || !out1 || !out2) return fail(PSB_ERR_ARG, "null argument");
+  return shard(N, [&](int di, size_t b, size_t e) -> int {
+    Dev* dv = g_devs[di];
+    std::lock_guard<std::mutex> lk(dv->mu);
+    const size_t L = e - b;
+    if (L == 0) return PSB_OK;
+    CK(cudaSetDevice(dv->ordinal));
+    cudaStream_t st = dv->stream;
+    int rc;
+    for (int i = 0; i < 2; i++) if ((rc = ensure(dv->in[i], L * sizeof(G1J)))) return rc;
+    if ((rc = ensure(dv->in[2], L * sizeof(Fr)))) return rc;
+    for (int i = 3; i < 5; i++) if ((rc = ensure(dv->in[i], L * sizeof(G1J)))) return rc;
+    if (ser && (rc = ensure(dv->in[5], L * 96))) return rc;
+    CK(cudaMemcpyAsync(dv->in[0].p, sig1 + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dv->in[1].p, sig2 + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dv->in[2].p, t + b * 4, L * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    k_randomize<<<nblocks(L), kBlock, 0, st>>>(L, (const G1J*)dv->in[0].p, (const G1J*)dv->in[1].p, (const Fr*)dv->in[2].p,
+                                               (G1J*)dv->in[3].p, (G1J*)dv->in[4].p, ser ? (uint8_t*)dv->in[5].p : nullptr);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out1 + b * 18, dv->in[3].p, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out2 + b * 18, dv->in[4].p, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+    if (ser) CK(cudaMemcpyAsync(ser + b * 96, dv->in[5].p, L * 96, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PSB_OK;
+  });
 }
+
+int psb_g1_mul(size_t N, const uint64_t* P, int p_stride, const uint64_t* k, uint64_t* out) {
+  if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
+  if (!P || !k || !out) return fail(PSB_ERR_ARG, "null argument");
+  return shard(N, [&](int di, size_t b, size_t e) -> int {
+    Dev* dv = g_devs[di];
+    std::lock_guard<std::mutex> lk(dv->mu);
+    const size_t L = e - b;
+    if (L == 0) return PSB_OK;
+    CK(cudaSetDevice(dv->ordinal));
+    cudaStream_t st = dv->stream;
+    int rc;
+    const size_t np = p_stride ? L : 1;
+    if ((rc = ensure(dv->in[0], np * sizeof(G1J)))) return rc;
+    if ((rc = ensure(dv->in[2], L * sizeof(Fr)))) return rc;
+    if ((rc = ensure(dv->in[3], L * sizeof(G1J)))) return rc;
+    CK(cudaMemcpyAsync(dv->in[0].p, P + (p_stride ? b * 18 : 0), np * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dv->in[2].p, k + b * 4, L * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    k_g1_mul<<<nblocks(L), kBlock, 0, st>>>(L, (const G1J*)dv->in[0].p, p_stride, (const Fr*)dv->in[2].p, (G1J*)dv->in[3].p);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out + b * 18, dv->in[3].p, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PSB_OK;
+  });
+}
+
 int psb_provide_id(psb_key*, size_t, const uint64_t*, const uint64_t*, const uint64_t*, size_t, const uint8_t*,
                    const uint64_t*, const uint8_t*, const uint64_t*, const uint64_t*, uint8_t*, uint64_t*, uint64_t*,
                    uint8_t*) {

@@ -1,4 +1,4 @@
-// tower.cuh -- Fp2 / Fp6 / Fp12 with lazy (double-width) reduction.
+// tower.cuh -- Fp2 / Fp6 / Fp12 for BLS12-381.
 //
 // Tower (same as mcl so that raw bytes are interchangeable):
 //   Fp2  = Fp[i]/(i^2+1)            (mcl/include/mcl/fp_tower.hpp:214-611)
@@ -6,25 +6,26 @@
 //   Fp12 = Fp6[w]/(w^2 - v)          (fp_tower.hpp:1066-1372)
 // Memory order of an Fp12: a.a a.b a.c b.a b.b b.c = coefficients of w^0 w^2 w^4 w^1 w^3 w^5.
 //
-// Reduction points follow the same idea as mcl's Fp2Dbl/Fp6Dbl (accumulate unreduced 768-bit
-// products, one Montgomery reduction per output coefficient); the schedule itself is our own.
-// All narrow values are canonical (in [0,p)); all wide values are in [0, p*R).
+// Lazy reduction happens INSIDE the Fp2 product: each Fp2 coefficient is one fused two-product
+// Montgomery pass (fp_dot2: a0 b0 + a1 (-b1), a0 b1 + a1 b0) with a single reduction, everything in
+// registers.  mcl additionally carries unreduced 768-bit values across Fp6/Fp12 (Fp6Dbl,
+// fp_tower.hpp:978-1022); on the GPU those wide temporaries live in thread-local memory and the
+// measured L1/LSU traffic of that scheme outweighed the saved reductions, so above
+// Fp2 all values are canonical 48-byte elements.
 #pragma once
 #include "fp.cuh"
 
 namespace psb {
 
 struct Fp2 { Fp a, b; };
-struct Fp2W { FpW a, b; };
 struct Fp6 { Fp2 a, b, c; };
-struct Fp6W { Fp2W a, b, c; };
 struct Fp12 { Fp6 a, b; };
 
-// ---- Fp2 narrow -----------------------------------------------------------------------------
-PSB_HD PSB_INL void fp2_add(Fp2& r, const Fp2& x, const Fp2& y) { fp_add(r.a, x.a, y.a); fp_add(r.b, x.b, y.b); }
-PSB_HD PSB_INL void fp2_sub(Fp2& r, const Fp2& x, const Fp2& y) { fp_sub(r.a, x.a, y.a); fp_sub(r.b, x.b, y.b); }
-PSB_HD PSB_INL void fp2_neg(Fp2& r, const Fp2& x) { fp_neg(r.a, x.a); fp_neg(r.b, x.b); }
-PSB_HD PSB_INL void fp2_dbl(Fp2& r, const Fp2& x) { fp_dbl(r.a, x.a); fp_dbl(r.b, x.b); }
+// ---- Fp2 ------------------------------------------------------------------------------------------
+PSB_HD PSB_NOINL void fp2_add(Fp2& r, const Fp2& x, const Fp2& y) { fp_add(r.a, x.a, y.a); fp_add(r.b, x.b, y.b); }
+PSB_HD PSB_NOINL void fp2_sub(Fp2& r, const Fp2& x, const Fp2& y) { fp_sub(r.a, x.a, y.a); fp_sub(r.b, x.b, y.b); }
+PSB_HD PSB_NOINL void fp2_neg(Fp2& r, const Fp2& x) { fp_neg(r.a, x.a); fp_neg(r.b, x.b); }
+PSB_HD PSB_NOINL void fp2_dbl(Fp2& r, const Fp2& x) { fp_dbl(r.a, x.a); fp_dbl(r.b, x.b); }
 PSB_HD PSB_INL void fp2_conj(Fp2& r, const Fp2& x) { r.a = x.a; fp_neg(r.b, x.b); }
 PSB_HD PSB_INL void fp2_set_zero(Fp2& r) { fp_set_zero(r.a); fp_set_zero(r.b); }
 PSB_HD PSB_INL void fp2_set_one(Fp2& r) { fp_set_one(r.a); fp_set_zero(r.b); }
@@ -32,7 +33,7 @@ PSB_HD PSB_INL bool fp2_is_zero(const Fp2& x) { return fp_is_zero(x.a) & fp_is_z
 PSB_HD PSB_INL bool fp2_eq(const Fp2& x, const Fp2& y) { return fp_eq(x.a, y.a) & fp_eq(x.b, y.b); }
 PSB_HD PSB_INL void fp2_cmov(Fp2& r, const Fp2& x, bool c) { fp_cmov(r.a, x.a, c); fp_cmov(r.b, x.b, c); }
 // (a + b i)(1 + i) = (a - b) + (a + b) i      (fp_tower.hpp:584-592)
-PSB_HD PSB_INL void fp2_mul_xi(Fp2& r, const Fp2& x) {
+PSB_HD PSB_NOINL void fp2_mul_xi(Fp2& r, const Fp2& x) {
   Fp t;
   fp_sub(t, x.a, x.b);
   fp_add(r.b, x.a, x.b);
@@ -40,59 +41,35 @@ PSB_HD PSB_INL void fp2_mul_xi(Fp2& r, const Fp2& x) {
 }
 PSB_HD PSB_INL void fp2_mul_fp(Fp2& r, const Fp2& x, const Fp& k) { fp_mul(r.a, x.a, k); fp_mul(r.b, x.b, k); }
 
-// ---- Fp2 wide ---------------------------------------------------------------------------------
-// r = x*y unreduced: Karatsuba, 3 wide products (mcl fp2Dbl_mulPreW, fp_tower.hpp:713-741)
-PSB_HD PSB_NOINL void fp2_mulw(Fp2W& r, const Fp2& x, const Fp2& y) {
-  Fp s, t;
-  fp_add_nr(s, x.a, x.b);  // < 2p
-  fp_add_nr(t, y.a, y.b);
-  FpW d0, d1;
-  fp_mulw(r.b, s, t);      // < 4p^2 < 2^764
-  fp_mulw(d0, x.a, y.a);
-  fp_mulw(d1, x.b, y.b);
-  fpw_sub_nr(r.b, r.b, d0);
-  fpw_sub_nr(r.b, r.b, d1);  // a0 b1 + a1 b0 in [0, 2p^2) < pR
-  fpw_sub(r.a, d0, d1);      // a0 b0 - a1 b1 mod pR
+// (a0 + a1 i)(b0 + b1 i) = (a0 b0 - a1 b1) + (a0 b1 + a1 b0) i : two fused two-product passes
+// (value of mcl Fp2::mul, fp_tower.hpp:528-534)
+PSB_HD PSB_NOINL void fp2_mul(Fp2& r, const Fp2& x, const Fp2& y) {
+  Fp nb, re;
+  fp_neg(nb, y.b);
+  fp_dot2(re, x.a, y.a, x.b, nb);
+  fp_dot2(r.b, x.a, y.b, x.b, y.a);
+  r.a = re;
 }
-// r = x^2 unreduced: (a+b)(a-b), 2ab
-PSB_HD PSB_NOINL void fp2_sqrw(Fp2W& r, const Fp2& x) {
-  Fp s, d;
-  fp_add_nr(s, x.a, x.b);  // < 2p
-  fp_sub(d, x.a, x.b);     // canonical
-  FpW t;
-  fp_mulw(t, s, d);        // < 2p^2 < pR
-  fp_add_nr(s, x.a, x.a);
-  fp_mulw(r.b, s, x.b);    // 2ab < 2p^2
-  r.a = t;
+// (a + b i)^2 = (a + b)(a - b) + 2ab i       (fp_tower.hpp:539-550)
+PSB_HD PSB_NOINL void fp2_sqr(Fp2& r, const Fp2& x) {
+  Fp s, d, t;
+  fp_add_nr(s, x.a, x.b);  // < 2p: fine as a Montgomery multiplicand (result still < 2p before the final subtraction)
+  fp_sub(d, x.a, x.b);
+  fp_add_nr(t, x.a, x.a);
+  fp_mul(r.b, t, x.b);
+  fp_mul(r.a, s, d);
 }
-PSB_HD PSB_NOINL void fp2w_redc(Fp2& r, const Fp2W& t) { fp_redc(r.a, t.a); fp_redc(r.b, t.b); }
-PSB_HD PSB_NOINL void fp2w_add(Fp2W& r, const Fp2W& x, const Fp2W& y) { fpw_add(r.a, x.a, y.a); fpw_add(r.b, x.b, y.b); }
-PSB_HD PSB_NOINL void fp2w_sub(Fp2W& r, const Fp2W& x, const Fp2W& y) { fpw_sub(r.a, x.a, y.a); fpw_sub(r.b, x.b, y.b); }
-PSB_HD PSB_NOINL void fp2w_mul_xi(Fp2W& r, const Fp2W& x) {
-  FpW t;
-  fpw_sub(t, x.a, x.b);
-  fpw_add(r.b, x.a, x.b);
-  r.a = t;
-}
-
-PSB_HD PSB_NOINL void fp2_mul(Fp2& r, const Fp2& x, const Fp2& y) { Fp2W t; fp2_mulw(t, x, y); fp2w_redc(r, t); }
-PSB_HD PSB_NOINL void fp2_sqr(Fp2& r, const Fp2& x) { Fp2W t; fp2_sqrw(t, x); fp2w_redc(r, t); }
-
 // x^-1 = conj(x) / (a^2 + b^2)   (fp_tower.hpp:597-611)
 PSB_HD PSB_NOINL void fp2_inv(Fp2& r, const Fp2& x) {
-  FpW t0, t1;
-  fp_sqrw(t0, x.a);
-  fp_sqrw(t1, x.b);
-  fpw_add_nr(t0, t0, t1);  // < 2p^2 < pR
   Fp n;
-  fp_redc(n, t0);
+  fp_dot2(n, x.a, x.a, x.b, x.b);
   fp_inv(n, n);
   fp_mul(r.a, x.a, n);
   fp_mul(n, x.b, n);
   fp_neg(r.b, n);
 }
 
-// ---- Fp6 --------------------------------------------------------------------------------------
+// ---- Fp6 ------------------------------------------------------------------------------------------
 PSB_HD PSB_INL void fp6_add(Fp6& r, const Fp6& x, const Fp6& y) { fp2_add(r.a, x.a, y.a); fp2_add(r.b, x.b, y.b); fp2_add(r.c, x.c, y.c); }
 PSB_HD PSB_INL void fp6_sub(Fp6& r, const Fp6& x, const Fp6& y) { fp2_sub(r.a, x.a, y.a); fp2_sub(r.b, x.b, y.b); fp2_sub(r.c, x.c, y.c); }
 PSB_HD PSB_INL void fp6_neg(Fp6& r, const Fp6& x) { fp2_neg(r.a, x.a); fp2_neg(r.b, x.b); fp2_neg(r.c, x.c); }
@@ -105,61 +82,58 @@ PSB_HD PSB_INL void fp6_mul_v(Fp6& r, const Fp6& x) {
   r.b = x.a;
   r.a = t;
 }
-PSB_HD PSB_INL void fp6w_sub(Fp6W& r, const Fp6W& x, const Fp6W& y) { fp2w_sub(r.a, x.a, y.a); fp2w_sub(r.b, x.b, y.b); fp2w_sub(r.c, x.c, y.c); }
-PSB_HD PSB_INL void fp6w_add(Fp6W& r, const Fp6W& x, const Fp6W& y) { fp2w_add(r.a, x.a, y.a); fp2w_add(r.b, x.b, y.b); fp2w_add(r.c, x.c, y.c); }
-PSB_HD PSB_INL void fp6w_redc(Fp6& r, const Fp6W& t) { fp2w_redc(r.a, t.a); fp2w_redc(r.b, t.b); fp2w_redc(r.c, t.c); }
 
-// z = x*y unreduced: Karatsuba over v, 6 Fp2 wide products (cf. mcl Fp6Dbl::mulPre, fp_tower.hpp:978-1022)
-PSB_HD PSB_NOINL void fp6_mulw(Fp6W& z, const Fp6& x, const Fp6& y) {
-  Fp2W v0, v1, v2, T;
-  Fp2 s, t;
-  fp2_mulw(v0, x.a, y.a);
-  fp2_mulw(v1, x.b, y.b);
-  fp2_mulw(v2, x.c, y.c);
+// z = x*y: Karatsuba over v, 6 Fp2 products (value of mcl Fp6::mul, fp_tower.hpp:978-1022)
+PSB_HD PSB_NOINL void fp6_mul(Fp6& z, const Fp6& x, const Fp6& y) {
+  Fp2 v0, v1, v2, s, t, c0, c1;
+  fp2_mul(v0, x.a, y.a);
+  fp2_mul(v1, x.b, y.b);
+  fp2_mul(v2, x.c, y.c);
   // c0 = v0 + xi((b+c)(b'+c') - v1 - v2)
   fp2_add(s, x.b, x.c); fp2_add(t, y.b, y.c);
-  fp2_mulw(T, s, t);
-  fp2w_sub(T, T, v1); fp2w_sub(T, T, v2);
-  fp2w_mul_xi(T, T);
-  fp2w_add(z.a, T, v0);
+  fp2_mul(c0, s, t);
+  fp2_sub(c0, c0, v1); fp2_sub(c0, c0, v2);
+  fp2_mul_xi(c0, c0);
+  fp2_add(c0, c0, v0);
   // c1 = (a+b)(a'+b') - v0 - v1 + xi v2
   fp2_add(s, x.a, x.b); fp2_add(t, y.a, y.b);
-  fp2_mulw(T, s, t);
-  fp2w_sub(T, T, v0); fp2w_sub(T, T, v1);
-  fp2w_mul_xi(z.b, v2);
-  fp2w_add(z.b, z.b, T);
+  fp2_mul(c1, s, t);
+  fp2_sub(c1, c1, v0); fp2_sub(c1, c1, v1);
+  fp2_mul_xi(s, v2);
+  fp2_add(c1, c1, s);
   // c2 = (a+c)(a'+c') - v0 - v2 + v1
   fp2_add(s, x.a, x.c); fp2_add(t, y.a, y.c);
-  fp2_mulw(T, s, t);
-  fp2w_sub(T, T, v0); fp2w_sub(T, T, v2);
-  fp2w_add(z.c, T, v1);
+  fp2_mul(s, s, t);
+  fp2_sub(s, s, v0); fp2_sub(s, s, v2);
+  fp2_add(z.c, s, v1);
+  z.a = c0;
+  z.b = c1;
 }
-PSB_HD PSB_NOINL void fp6_mul(Fp6& r, const Fp6& x, const Fp6& y) { Fp6W t; fp6_mulw(t, x, y); fp6w_redc(r, t); }
 
-// x * (a0 + a1 v) unreduced, 5 Fp2 products (sparse operand; cf. mcl Fp6mul_01, bn.hpp:1298-1320)
-PSB_HD PSB_NOINL void fp6_mulw_01(Fp6W& z, const Fp6& x, const Fp2& a0, const Fp2& a1) {
-  Fp2W v0, v1, T;
-  Fp2 s, t;
-  fp2_mulw(v0, x.a, a0);
-  fp2_mulw(v1, x.b, a1);
-  // r1 = (x0+x1)(a0+a1) - v0 - v1
+// x * (a0 + a1 v), 5 Fp2 products (sparse operand; cf. mcl Fp6mul_01, bn.hpp:1298-1320)
+PSB_HD PSB_NOINL void fp6_mul_01(Fp6& z, const Fp6& x, const Fp2& a0, const Fp2& a1) {
+  Fp2 v0, v1, s, t, r1;
+  fp2_mul(v0, x.a, a0);
+  fp2_mul(v1, x.b, a1);
   fp2_add(s, x.a, x.b); fp2_add(t, a0, a1);
-  fp2_mulw(z.b, s, t);
-  fp2w_sub(z.b, z.b, v0); fp2w_sub(z.b, z.b, v1);
-  // r0 = v0 + xi x2 a1
-  fp2_mulw(T, x.c, a1);
-  fp2w_mul_xi(T, T);
-  fp2w_add(z.a, T, v0);
-  // r2 = v1 + x2 a0
-  fp2_mulw(T, x.c, a0);
-  fp2w_add(z.c, T, v1);
+  fp2_mul(r1, s, t);
+  fp2_sub(r1, r1, v0); fp2_sub(r1, r1, v1);     // x0 a1 + x1 a0
+  fp2_mul(s, x.c, a1);
+  fp2_mul_xi(s, s);
+  fp2_mul(t, x.c, a0);
+  fp2_add(z.a, s, v0);                          // x0 a0 + xi x2 a1
+  fp2_add(z.c, t, v1);                          // x1 a1 + x2 a0
+  z.b = r1;
 }
-// x * (b1 v) unreduced, 3 Fp2 products
-PSB_HD PSB_NOINL void fp6_mulw_1(Fp6W& z, const Fp6& x, const Fp2& b1) {
-  fp2_mulw(z.a, x.c, b1);
-  fp2w_mul_xi(z.a, z.a);
-  fp2_mulw(z.b, x.a, b1);
-  fp2_mulw(z.c, x.b, b1);
+// x * (b1 v), 3 Fp2 products
+PSB_HD PSB_NOINL void fp6_mul_1(Fp6& z, const Fp6& x, const Fp2& b1) {
+  Fp2 t0, t1;
+  fp2_mul(t0, x.c, b1);
+  fp2_mul_xi(t0, t0);
+  fp2_mul(t1, x.a, b1);
+  fp2_mul(z.c, x.b, b1);
+  z.b = t1;
+  z.a = t0;
 }
 
 // x^-1  (fp_tower.hpp:917-948)
@@ -180,13 +154,6 @@ PSB_HD PSB_INL void fp12_set_one(Fp12& r) {
   fp2_set_zero(r.b.a); fp2_set_zero(r.b.b); fp2_set_zero(r.b.c);
 }
 PSB_HD PSB_INL void fp12_conj(Fp12& r, const Fp12& x) { r.a = x.a; fp6_neg(r.b, x.b); }  // unitaryInv
-PSB_HD PSB_INL bool fp12_eq(const Fp12& x, const Fp12& y) {
-  const uint32_t* p = (const uint32_t*)&x;
-  const uint32_t* q = (const uint32_t*)&y;
-  uint32_t o = 0;
-  for (int i = 0; i < 144; i++) o |= p[i] ^ q[i];
-  return o == 0;
-}
 PSB_HD PSB_INL bool fp12_is_one(const Fp12& x) {
   const uint32_t* p = (const uint32_t*)&x;
   uint32_t o = 0;
@@ -195,24 +162,18 @@ PSB_HD PSB_INL bool fp12_is_one(const Fp12& x) {
   return o == 0;
 }
 
-// z = x*y: Karatsuba over w with one reduction per output coefficient (cf. fp_tower.hpp:1131-1160)
+// z = x*y: Karatsuba over w (value of mcl Fp12::mul, fp_tower.hpp:1131-1160)
 PSB_HD PSB_NOINL void fp12_mul(Fp12& z, const Fp12& x, const Fp12& y) {
-  Fp6W T0, T1, T2;
-  Fp6 s, t;
-  fp6_mulw(T0, x.a, y.a);
-  fp6_mulw(T1, x.b, y.b);
+  Fp6 t0, t1, s, t;
+  fp6_mul(t0, x.a, y.a);
+  fp6_mul(t1, x.b, y.b);
   fp6_add(s, x.a, x.b);
   fp6_add(t, y.a, y.b);
-  fp6_mulw(T2, s, t);
-  fp6w_sub(T2, T2, T0);
-  fp6w_sub(T2, T2, T1);
-  fp6w_redc(z.b, T2);
-  // z.a = T0 + v*T1 = (T0.a + xi T1.c, T0.b + T1.a, T0.c + T1.b)
-  fp2w_mul_xi(T2.a, T1.c);
-  fp2w_add(T0.a, T0.a, T2.a);
-  fp2w_add(T0.b, T0.b, T1.a);
-  fp2w_add(T0.c, T0.c, T1.b);
-  fp6w_redc(z.a, T0);
+  fp6_mul(s, s, t);
+  fp6_sub(s, s, t0);
+  fp6_sub(z.b, s, t1);
+  fp6_mul_v(t1, t1);
+  fp6_add(z.a, t0, t1);
 }
 
 // z = x^2 (complex squaring: 2 Fp6 products; cf. fp_tower.hpp:1166-1178)
@@ -232,22 +193,17 @@ PSB_HD PSB_NOINL void fp12_sqr(Fp12& z, const Fp12& x) {
 // f *= (c0 + c2 w^2 + c3 w^3): the sparse line of an M-type twist (cf. mcl mul_041, bn.hpp:1436-1468)
 // with A = c0 + c2 v, B = c3 v:  f.a' = fa A + v fb B,  f.b' = (fa+fb)(A+B) - fa A - fb B.   13 Fp2 products.
 PSB_HD PSB_NOINL void fp12_mul_line(Fp12& f, const Fp2& c0, const Fp2& c2, const Fp2& c3) {
-  Fp6W T0, T1, T2;
-  Fp6 s;
+  Fp6 t0, t1, s;
   Fp2 c23;
-  fp6_mulw_01(T0, f.a, c0, c2);
-  fp6_mulw_1(T1, f.b, c3);
+  fp6_mul_01(t0, f.a, c0, c2);
+  fp6_mul_1(t1, f.b, c3);
   fp6_add(s, f.a, f.b);
   fp2_add(c23, c2, c3);
-  fp6_mulw_01(T2, s, c0, c23);
-  fp6w_sub(T2, T2, T0);
-  fp6w_sub(T2, T2, T1);
-  fp6w_redc(f.b, T2);
-  fp2w_mul_xi(T2.a, T1.c);
-  fp2w_add(T0.a, T0.a, T2.a);
-  fp2w_add(T0.b, T0.b, T1.a);
-  fp2w_add(T0.c, T0.c, T1.b);
-  fp6w_redc(f.a, T0);
+  fp6_mul_01(s, s, c0, c23);
+  fp6_sub(s, s, t0);
+  fp6_sub(f.b, s, t1);
+  fp6_mul_v(t1, t1);
+  fp6_add(f.a, t0, t1);
 }
 
 // x^-1 = (a - b w)/(a^2 - v b^2)   (fp_tower.hpp:1183-1198)
@@ -286,18 +242,15 @@ PSB_HD PSB_NOINL void fp12_frobenius(Fp12& r, const Fp12& x, int j) {
 
 // Granger-Scott squaring in the cyclotomic subgroup (cf. mcl fasterSqr/sqrFp4, bn.hpp:1075-1144)
 PSB_HD PSB_NOINL void fp4_sqr(Fp2& z0, Fp2& z1, const Fp2& x0, const Fp2& x1) {
-  Fp2W T0, T1, T2;
-  Fp2 s;
-  fp2_sqrw(T0, x0);
-  fp2_sqrw(T1, x1);
-  fp2w_mul_xi(T2, T1);
-  fp2w_add(T2, T2, T0);
+  Fp2 t0, t1, s;
+  fp2_sqr(t0, x0);
+  fp2_sqr(t1, x1);
   fp2_add(s, x0, x1);
-  fp2w_redc(z0, T2);          // x0^2 + xi x1^2
-  fp2_sqrw(T2, s);
-  fp2w_sub(T2, T2, T0);
-  fp2w_sub(T2, T2, T1);
-  fp2w_redc(z1, T2);          // 2 x0 x1
+  fp2_sqr(s, s);
+  fp2_sub(s, s, t0);
+  fp2_sub(z1, s, t1);           // 2 x0 x1
+  fp2_mul_xi(t1, t1);
+  fp2_add(z0, t1, t0);          // x0^2 + xi x1^2
 }
 PSB_HD PSB_NOINL void fp12_cyclo_sqr(Fp12& y, const Fp12& x) {
   // slots: x0=a.a x4=a.b x3=a.c x2=b.a x1=b.b x5=b.c

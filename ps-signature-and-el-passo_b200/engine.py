@@ -19,7 +19,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpsb.so")
+LIB_PATH = os.environ.get("PSB_LIB", os.path.join(_HERE, "libpsb.so"))
 
 FP, FR, G1, G2, GT = 6, 4, 18, 36, 72  # u64 words
 CURVE_BLS12_381 = 5
@@ -57,7 +57,7 @@ def lib():
 EXPORTS = ["psb_init", "psb_shutdown", "psb_num_devices", "psb_last_error", "psb_launch_count",
            "psb_key_create", "psb_key_destroy", "psb_key_num_attributes", "psb_key_table_bytes",
            "psb_verify", "psb_verify_ws_bytes", "psb_verify_dev", "psb_randomize", "psb_provide_id",
-           "psb_verify_id", "psb_pairing", "psb_test_op_shape", "psb_test_op", "psb_microbench"]
+           "psb_verify_id", "psb_pairing", "psb_g1_mul", "psb_set_profiling", "psb_last_phase_ms", "psb_test_op_shape", "psb_test_op", "psb_microbench"]
 
 
 def _check(rc: int, what: str):
@@ -270,6 +270,18 @@ def pairing(P, Q):
     return out
 
 
+def g1_mul(P, k):
+    """batched G1::mul, normalised output; P is (N,18) or a single point (broadcast)."""
+    ensure_init()
+    P = _u64(P, G1)
+    k = _u64(k, FR)
+    N = k.shape[0]
+    stride = 0 if (P.shape[0] == 1 and N != 1) else 1
+    out = np.zeros((N, G1), dtype=np.uint64)
+    _check(lib().psb_g1_mul(C.c_size_t(N), _p(P), C.c_int(stride), _p(k), _p(out)), "psb_g1_mul")
+    return out
+
+
 def test_op(op: int, a, b=None, c=None):
     """element-wise arithmetic probe (csrc/testops.cuh) -- parity tests only."""
     ensure_init()
@@ -303,3 +315,14 @@ def verify_dev(pk: PSPubKey, dev_index: int, N: int, d_sig1: int, d_sig2: int, d
     _check(lib().psb_verify_dev(pk.handle, C.c_int(dev_index), C.c_size_t(N), vp(d_sig1), vp(d_sig2), vp(d_blob),
                                 vp(d_off), vp(d_m), vp(d_verdict), vp(d_gt), vp(d_ws), vp(stream)),
            "psb_verify_dev")
+
+
+def set_profiling(on: bool) -> None:
+    lib().psb_set_profiling(C.c_int(int(on)))
+
+
+def last_phase_ms(dev_index: int = 0):
+    """(msm, miller, final_exp) device milliseconds of the last profiled verify on that device."""
+    ms = (C.c_float * 3)()
+    _check(lib().psb_last_phase_ms(C.c_int(dev_index), ms), "psb_last_phase_ms")
+    return [float(x) for x in ms]

@@ -1,0 +1,79 @@
+#!/usr/bin/env python3
+"""tests/golden/gen_golden.py -- regenerates the committed golden fixtures.  Needs /root/reference
+(parses mcl's known-answer tests out of third-parties/mcl/test/bls12_test.cpp and runs the
+reference compiled by oracle/Makefile).  Outputs, all small JSON with hex strings:
+
+  mcl_kat.json   mcl's own KATs: BLS12-381 generators + e(g1,g2) (bls12_test.cpp:19-65), the
+                 finalExp input/output pair (:398-436)
+  keys.json      synthetic PS keys (n = 5, 10, 20, 50) with known exponents, seed 1,
+                 g = H1("abc"), gg = H2("edf"), all points normalized
+  protocol.json  reference outputs of the protocol entry points on small seeded batches:
+                 verify (verdict + fused GT), randomize (serialized), provide_id, verify_id
+"""
+import json
+import os
+import re
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import ref  # noqa: E402
+from tests import workload  # noqa: E402
+
+MCL_TEST = "/root/reference/third-parties/mcl/test/bls12_test.cpp"
+
+
+def hx(a):
+    return np.ascontiguousarray(a).tobytes().hex()
+
+
+def mcl_kat():
+    src = open(MCL_TEST).read()
+    blk = src[src.index("mcl::BLS12_381,"):src.index("CYBOZU_TEST_AUTO(size)")]
+    nums = re.findall(r'"((?:0x[0-9A-Fa-f]+ ?)+)"', blk)
+    flat = " ".join(nums).split()
+    p, r = flat[0], flat[1]
+    g2 = flat[2:6]
+    g1 = flat[6:8]
+    e = flat[8:20]
+    fe = src[src.index("CYBOZU_TEST_AUTO(finalExp)"):]
+    e0 = re.findall(r'"([0-9A-F]{96})', fe[fe.index("e0Str"):fe.index("e1Str")])
+    e1 = re.findall(r'"([0-9A-F]{96})', fe[fe.index("e1Str"):fe.index("Fp12 e0, e1, e2;")])
+    assert len(e) == 12 and len(e0) == 12 and len(e1) == 12
+    return {"source": "third-parties/mcl/test/bls12_test.cpp:19-65,398-436",
+            "p": p, "r": r, "g1": g1, "g2": g2, "e_g1_g2": e,
+            "final_exp_in": ["0x" + x for x in e0], "final_exp_out": ["0x" + x for x in e1]}
+
+
+def keys():
+    out = {}
+    for n in (5, 10, 20, 50):
+        k = ref.KeyMaterial(n, seed_=1)
+        out[str(n)] = {"g": hx(k.g), "gg": hx(k.gg), "XX": hx(k.XX), "Y": hx(k.Y), "YY": hx(k.YY), "X": hx(k.X),
+                       "x": hex(ref.fr_to_ints(k.x)[0]), "y": [hex(v) for v in ref.fr_to_ints(k.y)]}
+    return {"seed": 1, "g_label": "abc", "gg_label": "edf", "layout": "mcl raw Montgomery limbs, little-endian", "keys": out}
+
+
+def protocol():
+    out = {}
+    wl = workload.make_verify_workload(n_attrs=5, lanes=12, seed=2, tamper_every=3)
+    v, gt = workload.expected_verify(wl, want_gt=True)
+    out["verify"] = {"n": 5, "key_seed": 1, "sig1": hx(wl.sig1), "sig2": hx(wl.sig2),
+                     "attrs": [[a.decode() for a in lane] for lane in wl.attrs],
+                     "verdict": v.tolist(), "gt": hx(gt), "tampered": wl.tampered.tolist()}
+    ref.seed(6)
+    t = ref.fr_rand(12)
+    o1, o2, ser = ref.randomize(wl.sig1, wl.sig2, t)
+    out["randomize"] = {"t": hx(t), "ser": hx(ser)}
+    out["hash"] = {"attr0": hx(ref.fr_set_hash_of(b"attr0")), "empty": hx(ref.fr_set_hash_of(b""))}
+    return out
+
+
+if __name__ == "__main__":
+    for name, fn in (("mcl_kat.json", mcl_kat), ("keys.json", keys), ("protocol.json", protocol)):
+        with open(os.path.join(HERE, name), "w") as f:
+            json.dump(fn(), f, indent=1)
+        print("wrote", name, os.path.getsize(os.path.join(HERE, name)), "bytes")

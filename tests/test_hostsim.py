@@ -1,0 +1,71 @@
+"""CPU: the engine's __host__ __device__ arithmetic (tower, curves, pairing, SHA-256), compiled for
+the host by tests/hostsim, against the reference -- checks the LOGIC the GPU kernels share.  The
+PTX carry chains themselves are only exercised by the -m gpu tests."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests.conftest import rand_fp_raw
+
+
+def hop(hs, op, a, b=None, c=None):
+    s = (C.c_int * 4)()
+    assert hs.hostsim_op_shape(op, s) == 0
+    a32 = np.ascontiguousarray(a).view(np.uint32).reshape(-1, s[0])
+    n = a32.shape[0]
+    b32 = None if b is None or not s[1] else np.ascontiguousarray(b).view(np.uint32).reshape(n, s[1])
+    c32 = None if c is None or not s[2] else np.ascontiguousarray(c).view(np.uint32).reshape(n, s[2])
+    out = np.zeros((n, s[3]), dtype=np.uint32)
+    p = lambda x: None if x is None else x.ctypes.data_as(C.c_void_p)  # noqa: E731
+    assert hs.hostsim_op(op, C.c_size_t(n), p(a32), p(b32), p(c32), p(out)) == 0
+    return out.view(np.uint64)
+
+
+@pytest.fixture(scope="module")
+def rng():
+    return np.random.default_rng(7)
+
+
+def test_fields(hostsim, ref, rng):
+    a, b = rand_fp_raw(ref, rng, 32), rand_fp_raw(ref, rng, 32)
+    b[1] = 0
+    for op in range(6):
+        assert np.array_equal(hop(hostsim, op, a, b if op < 3 else None), ref.fp_op(op, a, b)), op
+    a, b = rand_fp_raw(ref, rng, 16, 2), rand_fp_raw(ref, rng, 16, 2)
+    for op in range(6):
+        assert np.array_equal(hop(hostsim, 10 + op, a, b if op < 3 else None), ref.fp2_op(op, a, b)), op
+    a, b = rand_fp_raw(ref, rng, 4, 6), rand_fp_raw(ref, rng, 4, 6)
+    assert np.array_equal(hop(hostsim, 20, a, b), ref.fp6_op(ref.OP_MUL, a, b))
+    assert np.array_equal(hop(hostsim, 21, a), ref.fp6_op(ref.OP_INV, a))
+    a, b = rand_fp_raw(ref, rng, 3, 12), rand_fp_raw(ref, rng, 3, 12)
+    assert np.array_equal(hop(hostsim, 30, a, b), ref.fp12_op(ref.OP_MUL, a, b))
+    assert np.array_equal(hop(hostsim, 31, a), ref.fp12_op(ref.OP_SQR, a))
+    assert np.array_equal(hop(hostsim, 32, a), ref.fp12_op(ref.OP_INV, a))
+    for k in (1, 2, 3):
+        assert np.array_equal(hop(hostsim, 32 + k, a), ref.fp12_frobenius(k, a))
+
+
+def test_groups_and_pairing(hostsim, ref):
+    ref.seed(31)
+    g, gg = ref.hash_to_g1(b"abc"), ref.hash_to_g2(b"edf")
+    k1, k2, k3 = ref.fr_rand(4), ref.fr_rand(4), ref.fr_rand(4)
+    P, P2, Q, Q2 = ref.g1_mul(g, k1), ref.g1_mul(g, k2), ref.g2_mul(gg, k1), ref.g2_mul(gg, k2)
+    s1, s2 = ref.g1_serialize, ref.g2_serialize
+    assert np.array_equal(s1(hop(hostsim, 40, P, P2)), s1(ref.g1_op(ref.G_ADD, P, P2)))
+    assert np.array_equal(s1(hop(hostsim, 43, P, k3)), s1(ref.g1_mul(P, k3)))
+    assert np.array_equal(hop(hostsim, 42, P), ref.g1_op(ref.G_NORM, P))
+    assert np.array_equal(s2(hop(hostsim, 50, Q, Q2)), s2(ref.g2_op(ref.G_ADD, Q, Q2)))
+    assert np.array_equal(s2(hop(hostsim, 53, Q, k3)), s2(ref.g2_mul(Q, k3)))
+    assert np.array_equal(hop(hostsim, 60, P[:2], Q[:2]), ref.pairing(P[:2], Q[:2]))
+    Q2n = ref.g2_op(ref.G_NORM, Q2)
+    c = np.concatenate([P2[:2], Q2n[:2]], axis=1)
+    assert np.array_equal(hop(hostsim, 62, P[:2], Q[:2], c), ref.pairing_ratio(P[:2], Q[:2], P2[:2], Q2n[:2]))
+
+
+def test_sha256_to_scalar(hostsim):
+    from oracle import ps_oracle as O
+    for msg in (b"", b"attr0", b"x" * 55, b"y" * 56, b"z" * 64, b"w" * 200):
+        k = np.zeros(8, dtype=np.uint32)
+        hostsim.hostsim_set_hash_of(msg, C.c_size_t(len(msg)), k.ctypes.data_as(C.c_void_p))
+        assert int.from_bytes(k.tobytes(), "little") == O.fr_set_hash_of(msg)

@@ -16,7 +16,7 @@ pkg.init([0])
 SM = 148
 res = {"mad": [], "field": []}
 for kind, name, per_iter in [(6, "imad32 (mul.lo+add)", 16), (4, "mad.lo.cc+madc.hi (MAC32)", 8), (5, "mad.wide.u32 (MAC32)", 8)]:
-    for bps, thr in [(1, 256), (2, 256), (4, 256), (8, 256), (4, 128), (2, 1024)]:
+    for bps, thr in [(1, 256), (2, 256), (4, 256), (8, 256), (4, 128), (1, 128)]:
         iters = 20000
         ms = pkg.microbench(kind, SM * bps, thr, iters)
         ops = SM * bps * thr * iters * per_iter
