@@ -390,10 +390,10 @@ PSB_HD PSB_INL void fpw_sub_nr(FpW& r, const FpW& a, const FpW& b) { sub_n<24>(r
 // iteration in a rolled loop to keep the instruction footprint small (I-cache).
 #ifdef __CUDA_ARCH__
 #include "fp_cios.cuh"
-#ifdef PSB_CIOS_UNROLLED
-#define PSB_CIOS_LOOP _Pragma("unroll")
-#else
+#ifdef PSB_CIOS_ROLLED
 #define PSB_CIOS_LOOP _Pragma("unroll 1")
+#else
+#define PSB_CIOS_LOOP _Pragma("unroll")  // measured: 646k vs 578k verif/s rolled (r1)
 #endif
 __device__ PSB_NOINL void fp_mul(Fp& r, const Fp& a_, const Fp& b_) {
   uint32_t a0 = a_.v[0], a1 = a_.v[1], a2 = a_.v[2], a3 = a_.v[3], a4 = a_.v[4], a5 = a_.v[5], a6 = a_.v[6], a7 = a_.v[7], a8 = a_.v[8], a9 = a_.v[9], a10 = a_.v[10], a11 = a_.v[11];
