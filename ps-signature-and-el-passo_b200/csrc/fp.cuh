@@ -330,10 +330,31 @@ struct alignas(16) Fp { uint32_t v[12]; };    // canonical, Montgomery (mcl Fp: 
 struct alignas(16) FpW { uint32_t v[24]; };   // unreduced double width, value in [0, p*R) (mcl FpDbl, fp_tower.hpp:13-178)
 struct alignas(16) Fr { uint32_t v[8]; };
 
-PSB_HD PSB_INL void fp_add(Fp& r, const Fp& a, const Fp& b) { mod_add<FpT>(r.v, a.v, b.v); }
-PSB_HD PSB_INL void fp_sub(Fp& r, const Fp& a, const Fp& b) { mod_sub<FpT>(r.v, a.v, b.v); }
-PSB_HD PSB_INL void fp_neg(Fp& r, const Fp& a) { mod_neg<FpT>(r.v, a.v); }
-PSB_HD PSB_INL void fp_dbl(Fp& r, const Fp& a) { mod_add<FpT>(r.v, a.v, a.v); }
+// 128-bit limb moves between an Fp in memory (16-byte aligned) and a register array
+PSB_HD PSB_INL void fp_ld(uint32_t* d, const Fp& s) {
+#ifdef __CUDA_ARCH__
+  const uint4* q = reinterpret_cast<const uint4*>(s.v);
+  const uint4 v0 = q[0], v1 = q[1], v2 = q[2];
+  d[0] = v0.x; d[1] = v0.y; d[2] = v0.z; d[3] = v0.w; d[4] = v1.x; d[5] = v1.y; d[6] = v1.z; d[7] = v1.w;
+  d[8] = v2.x; d[9] = v2.y; d[10] = v2.z; d[11] = v2.w;
+#else
+  for (int i = 0; i < 12; i++) d[i] = s.v[i];
+#endif
+}
+PSB_HD PSB_INL void fp_st(Fp& d, const uint32_t* t) {
+#ifdef __CUDA_ARCH__
+  uint4* q = reinterpret_cast<uint4*>(d.v);
+  q[0] = make_uint4(t[0], t[1], t[2], t[3]);
+  q[1] = make_uint4(t[4], t[5], t[6], t[7]);
+  q[2] = make_uint4(t[8], t[9], t[10], t[11]);
+#else
+  for (int i = 0; i < 12; i++) d.v[i] = t[i];
+#endif
+}
+PSB_HD PSB_INL void fp_add(Fp& r, const Fp& a, const Fp& b) { uint32_t x[12], y[12]; fp_ld(x, a); fp_ld(y, b); mod_add<FpT>(x, x, y); fp_st(r, x); }
+PSB_HD PSB_INL void fp_sub(Fp& r, const Fp& a, const Fp& b) { uint32_t x[12], y[12]; fp_ld(x, a); fp_ld(y, b); mod_sub<FpT>(x, x, y); fp_st(r, x); }
+PSB_HD PSB_INL void fp_neg(Fp& r, const Fp& a) { uint32_t x[12]; fp_ld(x, a); mod_neg<FpT>(x, x); fp_st(r, x); }
+PSB_HD PSB_INL void fp_dbl(Fp& r, const Fp& a) { uint32_t x[12]; fp_ld(x, a); mod_add<FpT>(x, x, x); fp_st(r, x); }
 // a + b without reduction (< 2p < 2^384): only as an operand of mulw (mcl Fp::addPre)
 PSB_HD PSB_INL void fp_add_nr(Fp& r, const Fp& a, const Fp& b) { add_n<12>(r.v, a.v, b.v); }
 PSB_HD PSB_INL void fp_mulw(FpW& r, const Fp& a, const Fp& b) { mulw_n<12>(r.v, a.v, b.v); }
@@ -379,87 +400,16 @@ PSB_HD PSB_INL void fpw_sub(FpW& r, const FpW& a, const FpW& b) {
 PSB_HD PSB_INL void fpw_add_nr(FpW& r, const FpW& a, const FpW& b) { add_n<24>(r.v, a.v, b.v); }
 PSB_HD PSB_INL void fpw_sub_nr(FpW& r, const FpW& a, const FpW& b) { sub_n<24>(r.v, a.v, b.v); }
 
-// Montgomery product (mcl Fp::mul / Fp::sqr; cf. mcl/src/low_func.hpp:554-652, fp_generator.hpp:827-868).
-//
-// Device: operand-scanning CIOS with the running sum split into an EVEN and an ODD accumulator
-// array (T = E + 2^32 O).  A 32x32->64 product of an even limb lands on an aligned limb pair of E,
-// of an odd limb on an aligned pair of O, so each row is two carry chains of six wide MACs
-// (mad.lo.cc + madc.hi.cc, fused by ptxas into IMAD.WIDE.U32.X) with no separate carry adds; the
-// per-row shift by one limb is folded into the MAC chain of the odd array (destination limb j,
-// addend limb j+2) and the two arrays swap roles every row.  Rows are processed two per loop
-// iteration in a rolled loop to keep the instruction footprint small (I-cache).
+// Montgomery product / square (mcl Fp::mul / Fp::sqr).  Device: even/odd CIOS kernels (cios.cuh).
+}  // namespace psb
 #ifdef __CUDA_ARCH__
-#include "fp_cios.cuh"
-#ifdef PSB_CIOS_ROLLED
-#define PSB_CIOS_LOOP _Pragma("unroll 1")
-#else
-#define PSB_CIOS_LOOP _Pragma("unroll")  // measured: 646k vs 578k verif/s rolled (r1)
+#include "cios.cuh"
 #endif
-__device__ PSB_NOINL void fp_mul(Fp& r, const Fp& a_, const Fp& b_) {
-  uint32_t a0 = a_.v[0], a1 = a_.v[1], a2 = a_.v[2], a3 = a_.v[3], a4 = a_.v[4], a5 = a_.v[5], a6 = a_.v[6], a7 = a_.v[7], a8 = a_.v[8], a9 = a_.v[9], a10 = a_.v[10], a11 = a_.v[11];
-  const uint32_t* bp = b_.v;
-  uint32_t x0, x1, x2, x3, x4, x5, x6, x7, x8, x9, x10, x11, y0, y1, y2, y3, y4, y5, y6, y7, y8, y9, y10, y11, m;
-  uint32_t b = bp[0];
-  PSB_ROW_FIRST_EVEN(x0, x1, x2, x3, x4, x5, x6, x7, x8, x9, x10, x11, a0, a2, a4, a6, a8, a10, b); PSB_ROW_FIRST_ODD(y0, y1, y2, y3, y4, y5, y6, y7, y8, y9, y10, y11, a1, a3, a5, a7, a9, a11, b);
-  m = x0 * PSB_FP_N0; PSB_RED_ODD(y0, y1, y2, y3, y4, y5, y6, y7, y8, y9, y10, y11, m); PSB_RED_EVEN(x0, x1, x2, x3, x4, x5, x6, x7, x8, x9, x10, x11, y11, m);
-  b = bp[1];
-  PSB_ROW_ODD_RSHIFT(y0, x0, x1, x2, x3, x4, x5, x6, x7, x8, x9, x10, x11, a1, a3, a5, a7, a9, a11, b); PSB_ROW_EVEN(y0, y1, y2, y3, y4, y5, y6, y7, y8, y9, y10, y11, x11, a0, a2, a4, a6, a8, a10, b);
-  m = y0 * PSB_FP_N0; PSB_RED_ODD(x0, x1, x2, x3, x4, x5, x6, x7, x8, x9, x10, x11, m); PSB_RED_EVEN(y0, y1, y2, y3, y4, y5, y6, y7, y8, y9, y10, y11, x11, m);
-PSB_CIOS_LOOP
-  for (int i = 2; i < 12; i += 2) {
-    const uint32_t b0 = bp[i], b1 = bp[i + 1];
-    PSB_ROW_ODD_RSHIFT(x0, y0, y1, y2, y3, y4, y5, y6, y7, y8, y9, y10, y11, a1, a3, a5, a7, a9, a11, b0); PSB_ROW_EVEN(x0, x1, x2, x3, x4, x5, x6, x7, x8, x9, x10, x11, y11, a0, a2, a4, a6, a8, a10, b0);
-    m = x0 * PSB_FP_N0; PSB_RED_ODD(y0, y1, y2, y3, y4, y5, y6, y7, y8, y9, y10, y11, m); PSB_RED_EVEN(x0, x1, x2, x3, x4, x5, x6, x7, x8, x9, x10, x11, y11, m);
-    PSB_ROW_ODD_RSHIFT(y0, x0, x1, x2, x3, x4, x5, x6, x7, x8, x9, x10, x11, a1, a3, a5, a7, a9, a11, b1); PSB_ROW_EVEN(y0, y1, y2, y3, y4, y5, y6, y7, y8, y9, y10, y11, x11, a0, a2, a4, a6, a8, a10, b1);
-    m = y0 * PSB_FP_N0; PSB_RED_ODD(x0, x1, x2, x3, x4, x5, x6, x7, x8, x9, x10, x11, m); PSB_RED_EVEN(y0, y1, y2, y3, y4, y5, y6, y7, y8, y9, y10, y11, x11, m);
-  }
-  // last row had even = Y (y0 == 0), odd = X:  T = (Y >> 32) + X
-  uint32_t t[12];
-  t[0] = ptx::add_cc(y1, x0); t[1] = ptx::addc_cc(y2, x1); t[2] = ptx::addc_cc(y3, x2); t[3] = ptx::addc_cc(y4, x3);
-  t[4] = ptx::addc_cc(y5, x4); t[5] = ptx::addc_cc(y6, x5); t[6] = ptx::addc_cc(y7, x6); t[7] = ptx::addc_cc(y8, x7);
-  t[8] = ptx::addc_cc(y9, x8); t[9] = ptx::addc_cc(y10, x9); t[10] = ptx::addc_cc(y11, x10); t[11] = ptx::addc(0, x11);
-  cond_sub_mod<FpT>(t);
-  PSB_UNROLL
-  for (int i = 0; i < 12; i++) r.v[i] = t[i];
-}
-
-// r = (a b + c d) / R mod p with ONE reduction per row ("dot2"); a b + c d < 2 p^2 keeps the result < 2p.
-__device__ PSB_NOINL void fp_dot2(Fp& r, const Fp& a_, const Fp& b_, const Fp& c_, const Fp& d_) {
-  uint32_t a0 = a_.v[0], a1 = a_.v[1], a2 = a_.v[2], a3 = a_.v[3], a4 = a_.v[4], a5 = a_.v[5], a6 = a_.v[6], a7 = a_.v[7], a8 = a_.v[8], a9 = a_.v[9], a10 = a_.v[10], a11 = a_.v[11];
-  uint32_t c0 = c_.v[0], c1 = c_.v[1], c2 = c_.v[2], c3 = c_.v[3], c4 = c_.v[4], c5 = c_.v[5], c6 = c_.v[6], c7 = c_.v[7], c8 = c_.v[8], c9 = c_.v[9], c10 = c_.v[10], c11 = c_.v[11];
-  const uint32_t* bp = b_.v;
-  const uint32_t* dp = d_.v;
-  uint32_t x0, x1, x2, x3, x4, x5, x6, x7, x8, x9, x10, x11, y0, y1, y2, y3, y4, y5, y6, y7, y8, y9, y10, y11, m;
-  uint32_t b = bp[0], d = dp[0];
-  PSB_ROW_FIRST_EVEN(x0, x1, x2, x3, x4, x5, x6, x7, x8, x9, x10, x11, a0, a2, a4, a6, a8, a10, b); PSB_ROW_FIRST_ODD(y0, y1, y2, y3, y4, y5, y6, y7, y8, y9, y10, y11, a1, a3, a5, a7, a9, a11, b);
-  PSB_ROW_ODD(y0, y1, y2, y3, y4, y5, y6, y7, y8, y9, y10, y11, c1, c3, c5, c7, c9, c11, d); PSB_ROW_EVEN(x0, x1, x2, x3, x4, x5, x6, x7, x8, x9, x10, x11, y11, c0, c2, c4, c6, c8, c10, d);
-  m = x0 * PSB_FP_N0; PSB_RED_ODD(y0, y1, y2, y3, y4, y5, y6, y7, y8, y9, y10, y11, m); PSB_RED_EVEN(x0, x1, x2, x3, x4, x5, x6, x7, x8, x9, x10, x11, y11, m);
-  b = bp[1]; d = dp[1];
-  PSB_ROW_ODD_RSHIFT(y0, x0, x1, x2, x3, x4, x5, x6, x7, x8, x9, x10, x11, a1, a3, a5, a7, a9, a11, b); PSB_ROW_EVEN(y0, y1, y2, y3, y4, y5, y6, y7, y8, y9, y10, y11, x11, a0, a2, a4, a6, a8, a10, b);
-  PSB_ROW_ODD(x0, x1, x2, x3, x4, x5, x6, x7, x8, x9, x10, x11, c1, c3, c5, c7, c9, c11, d); PSB_ROW_EVEN(y0, y1, y2, y3, y4, y5, y6, y7, y8, y9, y10, y11, x11, c0, c2, c4, c6, c8, c10, d);
-  m = y0 * PSB_FP_N0; PSB_RED_ODD(x0, x1, x2, x3, x4, x5, x6, x7, x8, x9, x10, x11, m); PSB_RED_EVEN(y0, y1, y2, y3, y4, y5, y6, y7, y8, y9, y10, y11, x11, m);
-PSB_CIOS_LOOP
-  for (int i = 2; i < 12; i += 2) {
-    const uint32_t b0 = bp[i], b1 = bp[i + 1], d0 = dp[i], d1 = dp[i + 1];
-    PSB_ROW_ODD_RSHIFT(x0, y0, y1, y2, y3, y4, y5, y6, y7, y8, y9, y10, y11, a1, a3, a5, a7, a9, a11, b0); PSB_ROW_EVEN(x0, x1, x2, x3, x4, x5, x6, x7, x8, x9, x10, x11, y11, a0, a2, a4, a6, a8, a10, b0);
-    PSB_ROW_ODD(y0, y1, y2, y3, y4, y5, y6, y7, y8, y9, y10, y11, c1, c3, c5, c7, c9, c11, d0); PSB_ROW_EVEN(x0, x1, x2, x3, x4, x5, x6, x7, x8, x9, x10, x11, y11, c0, c2, c4, c6, c8, c10, d0);
-    m = x0 * PSB_FP_N0; PSB_RED_ODD(y0, y1, y2, y3, y4, y5, y6, y7, y8, y9, y10, y11, m); PSB_RED_EVEN(x0, x1, x2, x3, x4, x5, x6, x7, x8, x9, x10, x11, y11, m);
-    PSB_ROW_ODD_RSHIFT(y0, x0, x1, x2, x3, x4, x5, x6, x7, x8, x9, x10, x11, a1, a3, a5, a7, a9, a11, b1); PSB_ROW_EVEN(y0, y1, y2, y3, y4, y5, y6, y7, y8, y9, y10, y11, x11, a0, a2, a4, a6, a8, a10, b1);
-    PSB_ROW_ODD(x0, x1, x2, x3, x4, x5, x6, x7, x8, x9, x10, x11, c1, c3, c5, c7, c9, c11, d1); PSB_ROW_EVEN(y0, y1, y2, y3, y4, y5, y6, y7, y8, y9, y10, y11, x11, c0, c2, c4, c6, c8, c10, d1);
-    m = y0 * PSB_FP_N0; PSB_RED_ODD(x0, x1, x2, x3, x4, x5, x6, x7, x8, x9, x10, x11, m); PSB_RED_EVEN(y0, y1, y2, y3, y4, y5, y6, y7, y8, y9, y10, y11, x11, m);
-  }
-  // last row had even = Y (y0 == 0), odd = X:  T = (Y >> 32) + X
-  uint32_t t[12];
-  t[0] = ptx::add_cc(y1, x0); t[1] = ptx::addc_cc(y2, x1); t[2] = ptx::addc_cc(y3, x2); t[3] = ptx::addc_cc(y4, x3);
-  t[4] = ptx::addc_cc(y5, x4); t[5] = ptx::addc_cc(y6, x5); t[6] = ptx::addc_cc(y7, x6); t[7] = ptx::addc_cc(y8, x7);
-  t[8] = ptx::addc_cc(y9, x8); t[9] = ptx::addc_cc(y10, x9); t[10] = ptx::addc_cc(y11, x10); t[11] = ptx::addc(0, x11);
-  cond_sub_mod<FpT>(t);
-  PSB_UNROLL
-  for (int i = 0; i < 12; i++) r.v[i] = t[i];
-}
-__device__ PSB_INL void fp_sqr(Fp& r, const Fp& a) { fp_mul(r, a, a); }
-__device__ PSB_INL void fp_mul_inl(Fp& r, const Fp& a, const Fp& b) { fp_mul(r, a, b); }
-__device__ PSB_INL void fp_sqr_inl(Fp& r, const Fp& a) { fp_mul(r, a, a); }
+namespace psb {
+#ifdef __CUDA_ARCH__
+__device__ PSB_INL void fp_mul(Fp& r, const Fp& a, const Fp& b) { cios::mul(r.v, a.v, b.v); }
+__device__ PSB_INL void fp_sqr(Fp& r, const Fp& a) { cios::mul(r.v, a.v, a.v); }
+__device__ PSB_INL void fp_dot2(Fp& r, const Fp& a, const Fp& b, const Fp& c, const Fp& d) { cios::dot2(r.v, a.v, b.v, c.v, d.v); }
 #else
 // host build (tests/hostsim only): same values through the generic product-scanning code
 PSB_HD inline void fp_mul(Fp& r, const Fp& a, const Fp& b) { FpW t; fp_mulw(t, a, b); fp_redc(r, t); }
@@ -467,9 +417,9 @@ PSB_HD inline void fp_sqr(Fp& r, const Fp& a) { FpW t; fp_sqrw(t, a); fp_redc(r,
 PSB_HD inline void fp_dot2(Fp& r, const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
   FpW t, u; fp_mulw(t, a, b); fp_mulw(u, c, d); fpw_add_nr(t, t, u); fp_redc(r, t);
 }
-PSB_HD inline void fp_mul_inl(Fp& r, const Fp& a, const Fp& b) { fp_mul(r, a, b); }
-PSB_HD inline void fp_sqr_inl(Fp& r, const Fp& a) { fp_sqr(r, a); }
 #endif
+PSB_HD PSB_INL void fp_mul_inl(Fp& r, const Fp& a, const Fp& b) { fp_mul(r, a, b); }
+PSB_HD PSB_INL void fp_sqr_inl(Fp& r, const Fp& a) { fp_sqr(r, a); }
 
 // a^-1 = a^(p-2) (Fermat; mcl Fp::inv gives the same canonical value, mcl/src/fp.cpp:215-246).
 // Fixed 4-bit windows: constant schedule, no divergence.  inv(0) = 0 like mcl's.

@@ -12,6 +12,12 @@
 namespace psb {
 
 constexpr int kBlock = 128;
+// resident blocks per SM the verify kernels are compiled for: 4 x 128 threads = 128 registers/thread.
+// Measured on B200 (r1): the kernels run at the 1000 W power cap, and higher occupancy (5/6/8 blocks)
+// only lowered the SM clock (1942 -> 1837 -> 1762 -> 1702 MHz) and the throughput.
+#ifndef PSB_MINB
+#define PSB_MINB 4
+#endif
 
 // ---- parity probe ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_test_op(int op, size_t n, int s0, int s1, int s2, int s3,
@@ -179,7 +185,7 @@ __global__ void k_fixed_lines(const G2J* gg /*normalised*/, FixedLine* lines) {
 // ---- PS verification pipeline -------------------------------------------------------------------------
 // phase 1: scalars m_i (SHA-256 of the attribute strings, or the caller's Fr) and
 //          K = XX + sum_i m_i YY_i from the per-key window tables.
-__global__ void __launch_bounds__(kBlock) k_verify_msm(size_t N, int n, int w, const uint8_t* blob, const uint64_t* off,
+__global__ void __launch_bounds__(kBlock, PSB_MINB) k_verify_msm(size_t N, int n, int w, const uint8_t* blob, const uint64_t* off,
                                                         const Fr* m_mont, const G2J* XX, const G2A* tbl, G2J* Kout) {
   const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (lane >= N) return;
@@ -202,7 +208,7 @@ __global__ void __launch_bounds__(kBlock) k_verify_msm(size_t N, int n, int w, c
 }
 
 // phase 2: f = ML(sig1, K) * ML(-sig2, gg)  (one multi-Miller loop per lane)
-__global__ void __launch_bounds__(kBlock) k_verify_miller(size_t N, const G1J* sig1, const G1J* sig2, const G2J* K,
+__global__ void __launch_bounds__(kBlock, PSB_MINB) k_verify_miller(size_t N, const G1J* sig1, const G1J* sig2, const G2J* K,
                                                            const FixedLine* lines, Fp12* fout) {
   const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (lane >= N) return;
@@ -221,7 +227,7 @@ __global__ void __launch_bounds__(kBlock) k_verify_miller(size_t N, const G1J* s
 }
 
 // phase 3: final exponentiation, verdict = (sig1 != 0) && (f^e == 1), optional GT
-__global__ void __launch_bounds__(kBlock) k_verify_final(size_t N, const G1J* sig1, const Fp12* fin, uint8_t* verdict,
+__global__ void __launch_bounds__(kBlock, PSB_MINB) k_verify_final(size_t N, const G1J* sig1, const Fp12* fin, uint8_t* verdict,
                                                           Fp12* gt) {
   const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (lane >= N) return;

@@ -39,10 +39,22 @@ PSB_HD PSB_NOINL void fp2_mul_xi(Fp2& r, const Fp2& x) {
   fp_add(r.b, x.a, x.b);
   r.a = t;
 }
-PSB_HD PSB_INL void fp2_mul_fp(Fp2& r, const Fp2& x, const Fp& k) { fp_mul(r.a, x.a, k); fp_mul(r.b, x.b, k); }
+PSB_HD PSB_INL void fp2_mul_fp(Fp2& r, const Fp2& x, const Fp& k) {
+#if defined(__CUDA_ARCH__) && defined(PSB_FP2_FUSED)
+  cios::fp2_mul_fp(r.a.v, x.a.v, k.v);   // Fp2 is two contiguous Fp: 24 limbs
+#else
+  fp_mul(r.a, x.a, k); fp_mul(r.b, x.b, k);
+#endif
+}
 
 // (a0 + a1 i)(b0 + b1 i) = (a0 b0 - a1 b1) + (a0 b1 + a1 b0) i : two fused two-product passes
 // (value of mcl Fp2::mul, fp_tower.hpp:528-534)
+#if defined(__CUDA_ARCH__) && defined(PSB_FP2_FUSED)
+// two accumulator pairs side by side: more ILP but ~160 registers -> lower occupancy; measured
+// slower on B200 (750k vs 832k verif/s, r1), kept for experiments only
+__device__ PSB_INL void fp2_mul(Fp2& r, const Fp2& x, const Fp2& y) { cios::fp2_mul(r.a.v, x.a.v, y.a.v); }
+__device__ PSB_INL void fp2_sqr(Fp2& r, const Fp2& x) { cios::fp2_sqr(r.a.v, x.a.v); }
+#else
 PSB_HD PSB_NOINL void fp2_mul(Fp2& r, const Fp2& x, const Fp2& y) {
   Fp nb, re;
   fp_neg(nb, y.b);
@@ -59,6 +71,7 @@ PSB_HD PSB_NOINL void fp2_sqr(Fp2& r, const Fp2& x) {
   fp_mul(r.b, t, x.b);
   fp_mul(r.a, s, d);
 }
+#endif
 // x^-1 = conj(x) / (a^2 + b^2)   (fp_tower.hpp:597-611)
 PSB_HD PSB_NOINL void fp2_inv(Fp2& r, const Fp2& x) {
   Fp n;
