@@ -8,6 +8,7 @@
 // through HBM once per phase (< 1 KB per lane against millions of integer MACs: negligible).
 #pragma once
 #include "testops.cuh"
+#include "protocol.cuh"
 
 namespace psb {
 
@@ -227,14 +228,17 @@ __global__ void __launch_bounds__(kBlock, PSB_MINB) k_verify_miller(size_t N, co
 }
 
 // phase 3: final exponentiation, verdict = (sig1 != 0) && (f^e == 1), optional GT
+//          reject_zero_sig1: PSVerifier::verify rejects sig1 == 0 (ps-verifier.cc:16-18), el_passo_verify_id does not;
+//          pre (optional): per-lane verdict of an earlier step (the NIZK check) that is ANDed in.
 __global__ void __launch_bounds__(kBlock, PSB_MINB) k_verify_final(size_t N, const G1J* sig1, const Fp12* fin, uint8_t* verdict,
-                                                          Fp12* gt) {
+                                                          Fp12* gt, const uint8_t* pre, int reject_zero_sig1) {
   const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (lane >= N) return;
   Fp12 f = fin[lane], e;
   final_exp(e, f);
-  const bool s1zero = fp_is_zero(sig1[lane].z);
-  verdict[lane] = (!s1zero && fp12_is_one(e)) ? 1 : 0;
+  const bool s1zero = reject_zero_sig1 && fp_is_zero(sig1[lane].z);
+  const bool pre_ok = pre ? pre[lane] != 0 : true;
+  verdict[lane] = (pre_ok && !s1zero && fp12_is_one(e)) ? 1 : 0;
   if (gt) gt[lane] = e;
 }
 
@@ -259,52 +263,6 @@ __global__ void __launch_bounds__(kBlock) k_final_exp(size_t N, const Fp12* fin,
   out[lane] = e;
 }
 
-
-// ---- serialisation (mcl compressed little-endian form, ec.hpp:849-896, non-ETH mode) -----------------
-// G1: x as 48 LE bytes of the NORMAL form, bit 7 of the last byte = y odd; infinity = 48 zero bytes.
-PSB_HD PSB_NOINL void g1_serialize_norm(uint8_t* out, const G1J& P /*normalised or zero*/) {
-  if (fp_is_zero(P.z)) { for (int i = 0; i < 48; i++) out[i] = 0; return; }
-  Fp x, y;
-  fp_from_mont(x, P.x);
-  fp_from_mont(y, P.y);
-  for (int i = 0; i < 12; i++) {
-    out[4 * i] = (uint8_t)x.v[i]; out[4 * i + 1] = (uint8_t)(x.v[i] >> 8);
-    out[4 * i + 2] = (uint8_t)(x.v[i] >> 16); out[4 * i + 3] = (uint8_t)(x.v[i] >> 24);
-  }
-  if (y.v[0] & 1u) out[47] |= 0x80;
-}
-// G2: x.a || x.b (96 bytes), parity of y.a (fp_tower.hpp:312) in bit 7 of the last byte.
-PSB_HD PSB_NOINL void g2_serialize_norm(uint8_t* out, const G2J& P) {
-  if (fp2_is_zero(P.z)) { for (int i = 0; i < 96; i++) out[i] = 0; return; }
-  Fp xa, xb, ya;
-  fp_from_mont(xa, P.x.a);
-  fp_from_mont(xb, P.x.b);
-  fp_from_mont(ya, P.y.a);
-  for (int i = 0; i < 12; i++) {
-    out[4 * i] = (uint8_t)xa.v[i]; out[4 * i + 1] = (uint8_t)(xa.v[i] >> 8);
-    out[4 * i + 2] = (uint8_t)(xa.v[i] >> 16); out[4 * i + 3] = (uint8_t)(xa.v[i] >> 24);
-    out[48 + 4 * i] = (uint8_t)xb.v[i]; out[48 + 4 * i + 1] = (uint8_t)(xb.v[i] >> 8);
-    out[48 + 4 * i + 2] = (uint8_t)(xb.v[i] >> 16); out[48 + 4 * i + 3] = (uint8_t)(xb.v[i] >> 24);
-  }
-  if (ya.v[0] & 1u) out[95] |= 0x80;
-}
-
-// normalise two G1 points with ONE field inversion (Montgomery's trick); zero points stay canonical zero
-PSB_HD PSB_NOINL void g1_normalize2(G1J& A, G1J& B) {
-  const bool za = fp_is_zero(A.z), zb = fp_is_zero(B.z);
-  Fp one; fp_set_one(one);
-  Fp a = za ? one : A.z, b = zb ? one : B.z, ab, inv, ia, ib, t;
-  fp_mul(ab, a, b);
-  fp_inv(inv, ab);
-  fp_mul(ia, inv, b);
-  fp_mul(ib, inv, a);
-  if (za) { pt_set_zero(A); } else {
-    fp_sqr(t, ia); fp_mul(A.x, A.x, t); fp_mul(t, t, ia); fp_mul(A.y, A.y, t); A.z = one;
-  }
-  if (zb) { pt_set_zero(B); } else {
-    fp_sqr(t, ib); fp_mul(B.x, B.x, t); fp_mul(t, t, ib); fp_mul(B.y, B.y, t); B.z = one;
-  }
-}
 
 // ---- PSRequester::randomize_credential (src/ps-requester.cc:139-148) -----------------------------------
 // out = (t sig1, t sig2) normalised; t host-supplied (Fr Montgomery)
@@ -338,6 +296,65 @@ __global__ void __launch_bounds__(kBlock) k_g1_mul(size_t N, const G1J* P, int p
   pt_mul(r, a, kn.v);
   pt_normalize(n, r);
   out[lane] = n;
+}
+
+// ---- PSSigner::el_passo_provide_id (src/ps-signer.cc:63-146) -------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_provide_id(size_t N, int n, int w, const G1A* tblG1, const G1J* g1pts,
+                                                        const G1J* A, const Fr* c, const Fr* rs, int per,
+                                                        const uint8_t* blob, const uint64_t* off, const uint8_t* ad_blob,
+                                                        const uint64_t* ad_off, const Fr* u, uint8_t* verdict, G1J* sig1,
+                                                        G1J* sig2, uint8_t* ser) {
+  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= N) return;
+  G1J s1, s2;
+  const TblGeom tg{w};
+  const bool ok = provide_id_lane(n, tg, tblG1, g1pts[1], A[lane], c + lane, rs + lane * per, per, blob, off + lane * n,
+                                  ad_blob + ad_off[lane], (size_t)(ad_off[lane + 1] - ad_off[lane]), u + lane, s1, s2);
+  verdict[lane] = ok ? 1 : 0;
+  sig1[lane] = s1;
+  sig2[lane] = s2;
+  if (ser) {
+    g1_serialize_norm(ser + lane * 96, s1);
+    g1_serialize_norm(ser + lane * 96 + 48, s2);
+  }
+}
+
+// ---- PSVerifier::el_passo_verify_id (src/ps-verifier.cc:37-212): NIZK steps; the pairing check reuses
+//      k_verify_miller / k_verify_final with K from step 1 ------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_vid_g2(size_t N, int n, int w, const G2A* tblYY, const G2A* tblAux, const G2J* k,
+                                                    const Fr* c, const Fr* rs, int per, int with_id, const uint8_t* blob,
+                                                    const uint64_t* off, G2J* Vk, G2J* K, uint8_t* ok) {
+  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= N) return;
+  G2J vk, kk;
+  const TblGeom tg{w};
+  const bool r = verify_id_g2_lane(n, tg, tblYY, tblAux, k[lane], c + lane, rs + lane * per, per, with_id, blob,
+                                   off + lane * n, vk, kk);
+  Vk[lane] = vk;
+  K[lane] = kk;
+  ok[lane] = r ? 1 : 0;
+}
+__global__ void __launch_bounds__(kBlock) k_vid_g1(size_t N, int wb, const G1A* tblB, const G1J* phi, const G1J* E1,
+                                                    const G1J* E2, const Fr* c, const Fr* rs, int per, int with_id,
+                                                    G1J* V /*3 per lane*/) {
+  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= N) return;
+  G1J a, b, d;
+  const TblGeom tb{wb};
+  verify_id_g1_lane(tb, tblB, phi[lane], with_id ? E1 + lane : nullptr, with_id ? E2 + lane : nullptr, c + lane,
+                    rs + lane * per, per, with_id, a, b, d);
+  V[3 * lane] = a; V[3 * lane + 1] = b; V[3 * lane + 2] = d;
+}
+__global__ void __launch_bounds__(kBlock) k_vid_hash(size_t N, const G2J* k, const G1J* phi, const G1J* E1, const G1J* E2,
+                                                      const G2J* Vk, const G1J* V, int with_id, const Fr* c,
+                                                      const uint8_t* ad_blob, const uint64_t* ad_off, uint8_t* ok) {
+  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= N) return;
+  if (!ok[lane]) return;
+  const bool r = verify_id_hash_lane(k[lane], phi[lane], with_id ? E1 + lane : nullptr, with_id ? E2 + lane : nullptr,
+                                     Vk[lane], V[3 * lane], V[3 * lane + 1], V[3 * lane + 2], with_id, c + lane,
+                                     ad_blob + ad_off[lane], (size_t)(ad_off[lane + 1] - ad_off[lane]));
+  ok[lane] = r ? 1 : 0;
 }
 
 }  // namespace psb

@@ -6,7 +6,9 @@
 // There is deliberately NO CPU implementation behind these entry points.
 #include <cuda_runtime.h>
 
+#include <array>
 #include <atomic>
+#include <memory>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -30,6 +32,7 @@ struct Dev {
   cudaStream_t stream = nullptr;
   DevBuf in[8];   // staging for host-pointer entry points
   DevBuf ws;      // phase hand-over scratch
+  DevBuf arena;   // staging + scratch of the EL PASSO entry points (carved by Arena)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // phase boundaries of the last verify (profiling)
   std::mutex mu;  // one batch at a time per device
 };
@@ -70,9 +73,23 @@ int ensure(DevBuf& b, size_t bytes) {
 struct KeyDev {
   G1J* g1pts = nullptr;   // [0] g, [1] X (or zero), [2..2+n) Y_i         (normalised)
   G2J* g2pts = nullptr;   // [0] gg, [1] XX, [2..2+n) YY_i                (normalised)
-  G2A* wbYY = nullptr;    // n * nwin window bases
   G2A* tblYY = nullptr;   // n * nwin * 2^(w-1) affine entries
+  G2A* tblAux = nullptr;  // [gg, XX] tables (el_passo_verify_id; built on first use)
+  G1A* tblG1 = nullptr;   // [g, Y_0 .. Y_{n-1}] tables (el_passo_provide_id; built on first use)
   FixedLine* lines = nullptr;
+};
+
+// window tables of the per-batch G1 bases of el_passo_verify_id: H(service), g, y, h (one value per
+// batch).  Cached per key by the points' bytes so that a relying party's steady stream of batches builds them once.
+constexpr int kBatchW = 12;
+struct BatchTbl {
+  std::array<uint64_t, 4 * 18> id{};
+  int nbases = 0;
+  std::vector<int> ordinals;
+  std::vector<G1A*> tbl;   // per device
+  ~BatchTbl() {
+    for (size_t i = 0; i < tbl.size(); i++) if (tbl[i]) { cudaSetDevice(ordinals[i]); cudaFree(tbl[i]); }
+  }
 };
 
 }  // namespace
@@ -83,6 +100,9 @@ struct psb_key {
   bool hasX = false;
   size_t table_bytes = 0;
   std::vector<KeyDev> d;
+  std::mutex mu;                                   // lazy tables + batch-table cache
+  bool haveG1 = false, haveAux = false;
+  std::vector<std::shared_ptr<BatchTbl>> batch;    // FIFO, at most kBatchCache entries
 };
 
 namespace {
@@ -104,6 +124,48 @@ int shard(size_t N, Fn fn) {
   return PSB_OK;
 }
 
+constexpr size_t kBatchCache = 8;
+
+// fixed-base window tables of `nbases` NORMALISED device points: tbl[(b * nwin + j) * 2^(w-1) + d - 1] = d 2^(w j) B_b
+template <class F>
+int build_tables(cudaStream_t st, const Jac<F>* d_pts, int nbases, int w, Aff<F>** out) {
+  const int nwin = fixed_nwin(w);
+  const size_t half = (size_t)1 << (w - 1);
+  const size_t entries = (size_t)nbases * nwin * half;
+  Aff<F>* wb = nullptr;
+  Aff<F>* tbl = nullptr;
+  cudaError_t e = cudaMalloc(&wb, ((size_t)nbases * nwin + 1) * sizeof(Aff<F>));
+  if (e == cudaSuccess) e = cudaMalloc(&tbl, (entries + 1) * sizeof(Aff<F>));
+  if (e != cudaSuccess) { cudaFree(wb); return fail(PSB_ERR_NOMEM, "table allocation", e); }
+  k_window_bases<F><<<nblocks(nbases, 32), 32, 0, st>>>(d_pts, nbases, w, wb); LAUNCHED();
+  const size_t chunks = (size_t)nbases * nwin * ((half + kTblChunk - 1) / kTblChunk);
+  k_build_table<F><<<nblocks(chunks), kBlock, 0, st>>>(wb, nbases, w, tbl); LAUNCHED();
+  e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  cudaFree(wb);
+  if (e != cudaSuccess) { cudaFree(tbl); return fail(PSB_ERR_CUDA, "table build kernels", e); }
+  *out = tbl;
+  return PSB_OK;
+}
+
+// bump allocator over one device buffer: sizes are summed first (measure pass), then carved
+struct Arena {
+  char* base = nullptr;
+  size_t used = 0;
+  template <class T> T* take(size_t count) {
+    const size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+    T* p = base ? (T*)(base + used) : nullptr;
+    used += bytes;
+    return p;
+  }
+};
+
+bool is_zero_words(const uint64_t* p, size_t n) {
+  uint64_t o = 0;
+  for (size_t i = 0; i < n; i++) o |= p[i];
+  return o == 0;
+}
+
 int verify_launch(const psb_key* key, int di, size_t N, const G1J* d_sig1, const G1J* d_sig2, const uint8_t* d_blob,
                   const uint64_t* d_off, const Fr* d_m, uint8_t* d_verdict, Fp12* d_gt, void* d_ws, cudaStream_t st) {
   if (N == 0) return PSB_OK;
@@ -122,7 +184,7 @@ int verify_launch(const psb_key* key, int di, size_t N, const G1J* d_sig1, const
   k_verify_miller<<<nblocks(N), kBlock, 0, st>>>(N, d_sig1, d_sig2, dK, kd.lines, dF);
   LAUNCHED();
   if (prof) CK(cudaEventRecord(dv->ev[2], st));
-  k_verify_final<<<nblocks(N), kBlock, 0, st>>>(N, d_sig1, dF, d_verdict, d_gt);
+  k_verify_final<<<nblocks(N), kBlock, 0, st>>>(N, d_sig1, dF, d_verdict, d_gt, nullptr, 1);
   LAUNCHED();
   if (prof) CK(cudaEventRecord(dv->ev[3], st));
   CK(cudaGetLastError());
@@ -178,6 +240,7 @@ void psb_shutdown(void) {
     cudaSetDevice(d->ordinal);
     for (auto& b : d->in) if (b.p) cudaFree(b.p);
     if (d->ws.p) cudaFree(d->ws.p);
+    if (d->arena.p) cudaFree(d->arena.p);
     for (auto& e : d->ev) if (e) cudaEventDestroy(e);
     if (d->stream) cudaStreamDestroy(d->stream);
     delete d;
@@ -194,7 +257,8 @@ void psb_key_destroy(psb_key* key) {
   for (size_t i = 0; i < key->d.size(); i++) {
     cudaSetDevice(g_devs[i]->ordinal);
     KeyDev& k = key->d[i];
-    cudaFree(k.g1pts); cudaFree(k.g2pts); cudaFree(k.wbYY); cudaFree(k.tblYY); cudaFree(k.lines);
+    cudaFree(k.g1pts); cudaFree(k.g2pts); cudaFree(k.tblYY); cudaFree(k.tblAux); cudaFree(k.tblG1);
+    cudaFree(k.lines);
   }
   delete key;
 }
@@ -205,13 +269,16 @@ psb_key* psb_key_create(const uint64_t* g, const uint64_t* gg, const uint64_t* X
   if (!g || !gg || !XX || (n && (!Y || !YY))) { fail(PSB_ERR_ARG, "null key component"); return nullptr; }
   int w = window_bits == 0 ? 16 : window_bits;
   if (w < 4 || w > 16) { fail(PSB_ERR_ARG, "window_bits must be 4..16"); return nullptr; }
+  // fixed bases must be finite points: their window tables hold affine entries (z == 0 <=> infinity)
+  bool inf = is_zero_words(g + 12, 6) || is_zero_words(gg + 24, 12) || is_zero_words(XX + 24, 12);
+  for (size_t i = 0; i < n; i++) inf = inf || is_zero_words(Y + 18 * i + 12, 6) || is_zero_words(YY + 36 * i + 24, 12);
+  if (inf) { fail(PSB_ERR_ARG, "key component is the point at infinity"); return nullptr; }
   psb_key* key = new psb_key();
   key->n = n; key->w = w; key->hasX = X_secret != nullptr;
   key->d.resize(g_devs.size());
   const int nwin = fixed_nwin(w);
   const size_t half = (size_t)1 << (w - 1);
-  const size_t entries = n * nwin * half;
-  key->table_bytes = entries * sizeof(G2A);
+  key->table_bytes = n * nwin * half * sizeof(G2A);
   std::vector<G1J> h1(2 + n);
   std::vector<G2J> h2(2 + n);
   memcpy(&h1[0], g, sizeof(G1J));
@@ -227,20 +294,14 @@ psb_key* psb_key_create(const uint64_t* g, const uint64_t* gg, const uint64_t* X
     bool ok = cudaSetDevice(dv->ordinal) == cudaSuccess;
     ok = ok && cudaMalloc(&k.g1pts, h1.size() * sizeof(G1J)) == cudaSuccess;
     ok = ok && cudaMalloc(&k.g2pts, h2.size() * sizeof(G2J)) == cudaSuccess;
-    ok = ok && cudaMalloc(&k.wbYY, (n * nwin + 1) * sizeof(G2A)) == cudaSuccess;
-    ok = ok && cudaMalloc(&k.tblYY, (entries + 1) * sizeof(G2A)) == cudaSuccess;
     ok = ok && cudaMalloc(&k.lines, kMillerSteps * sizeof(FixedLine)) == cudaSuccess;
     if (!ok) { fail(PSB_ERR_NOMEM, "key allocation", cudaGetLastError()); psb_key_destroy(key); return nullptr; }
     cudaMemcpyAsync(k.g1pts, h1.data(), h1.size() * sizeof(G1J), cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(k.g2pts, h2.data(), h2.size() * sizeof(G2J), cudaMemcpyHostToDevice, st);
     k_normalize_points<Fp><<<nblocks(h1.size(), 32), 32, 0, st>>>(k.g1pts, (int)h1.size()); LAUNCHED();
     k_normalize_points<Fp2><<<nblocks(h2.size(), 32), 32, 0, st>>>(k.g2pts, (int)h2.size()); LAUNCHED();
-    if (n) {
-      k_window_bases<Fp2><<<nblocks(n, 32), 32, 0, st>>>(k.g2pts + 2, (int)n, w, k.wbYY); LAUNCHED();
-      const size_t chunks = n * nwin * ((half + kTblChunk - 1) / kTblChunk);
-      k_build_table<Fp2><<<nblocks(chunks), kBlock, 0, st>>>(k.wbYY, (int)n, w, k.tblYY); LAUNCHED();
-    }
     k_fixed_lines<<<1, 32, 0, st>>>(k.g2pts, k.lines); LAUNCHED();
+    if (n && build_tables<Fp2>(st, k.g2pts + 2, (int)n, w, &k.tblYY) != PSB_OK) { psb_key_destroy(key); return nullptr; }
     cudaError_t e = cudaStreamSynchronize(st);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { fail(PSB_ERR_CUDA, "key setup kernels", e); psb_key_destroy(key); return nullptr; }
@@ -396,7 +457,6 @@ double psb_microbench(int kind, int blocks, int threads, int iters) {
   return (double)ms;
 }
 
-// ---- entry points still to be built this round (declared in psb.h) ---------------------------------
 int psb_randomize(size_t N, const uint64_t* sig1, const uint64_t* sig2, const uint64_t* t, uint64_t* out1,
                   uint64_t* out2, uint8_t* ser) {
   if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
@@ -454,16 +514,193 @@ int psb_g1_mul(size_t N, const uint64_t* P, int p_stride, const uint64_t* k, uin
   });
 }
 
-int psb_provide_id(psb_key*, size_t, const uint64_t*, const uint64_t*, const uint64_t*, size_t, const uint8_t*,
-                   const uint64_t*, const uint8_t*, const uint64_t*, const uint64_t*, uint8_t*, uint64_t*, uint64_t*,
-                   uint8_t*) {
-  return fail(PSB_ERR_UNSUPPORTED, "psb_provide_id: not built yet");
+// lazily built per-key tables (under key->mu): G1 [g, Y_i] for issuance, G2 [gg, XX] for sign-on verification
+static int ensure_issuer_tables(psb_key* key) {
+  std::lock_guard<std::mutex> lk(key->mu);
+  if (key->haveG1) return PSB_OK;
+  for (size_t di = 0; di < g_devs.size(); di++) {
+    Dev* dv = g_devs[di];
+    std::lock_guard<std::mutex> dl(dv->mu);
+    CK(cudaSetDevice(dv->ordinal));
+    KeyDev& k = key->d[di];
+    // bases [g, Y_0..] are not contiguous in g1pts ([g, X, Y..]): gather them
+    G1J* tmp = nullptr;
+    CK(cudaMalloc(&tmp, (1 + key->n) * sizeof(G1J)));
+    cudaMemcpyAsync(tmp, k.g1pts, sizeof(G1J), cudaMemcpyDeviceToDevice, dv->stream);
+    if (key->n) cudaMemcpyAsync(tmp + 1, k.g1pts + 2, key->n * sizeof(G1J), cudaMemcpyDeviceToDevice, dv->stream);
+    const int rc = build_tables<Fp>(dv->stream, tmp, (int)(1 + key->n), key->w, &k.tblG1);
+    cudaFree(tmp);
+    if (rc) return rc;
+  }
+  key->haveG1 = true;
+  return PSB_OK;
 }
-int psb_verify_id(psb_key*, size_t, const uint64_t*, const uint64_t*, const uint64_t*, const uint64_t*, const uint64_t*,
-                  const uint64_t*, const uint64_t*, const uint64_t*, size_t, const uint8_t*, const uint64_t*,
-                  const uint8_t*, const uint64_t*, const uint64_t*, const uint64_t*, const uint64_t*, const uint64_t*,
-                  int, uint8_t*) {
-  return fail(PSB_ERR_UNSUPPORTED, "psb_verify_id: not built yet");
+static int ensure_verifier_tables(psb_key* key) {
+  std::lock_guard<std::mutex> lk(key->mu);
+  if (key->haveAux) return PSB_OK;
+  for (size_t di = 0; di < g_devs.size(); di++) {
+    Dev* dv = g_devs[di];
+    std::lock_guard<std::mutex> dl(dv->mu);
+    CK(cudaSetDevice(dv->ordinal));
+    const int rc = build_tables<Fp2>(dv->stream, key->d[di].g2pts, 2, key->w, &key->d[di].tblAux);
+    if (rc) return rc;
+  }
+  key->haveAux = true;
+  return PSB_OK;
+}
+// per-batch G1 bases [H(service), g, y, h] (nb = 1 without id retrieval) -> cached window tables
+static int get_batch_tables(psb_key* key, const uint64_t* const pts[4], int nb, std::shared_ptr<BatchTbl>& out) {
+  std::array<uint64_t, 4 * 18> id{};
+  for (int i = 0; i < nb; i++) {
+    if (is_zero_words(pts[i] + 12, 6)) return fail(PSB_ERR_ARG, "service/authority point is the point at infinity");
+    memcpy(&id[18 * i], pts[i], 18 * sizeof(uint64_t));
+  }
+  std::lock_guard<std::mutex> lk(key->mu);
+  for (auto& b : key->batch) if (b->nbases == nb && b->id == id) { out = b; return PSB_OK; }
+  auto bt = std::make_shared<BatchTbl>();
+  bt->id = id; bt->nbases = nb;
+  for (size_t di = 0; di < g_devs.size(); di++) {
+    Dev* dv = g_devs[di];
+    std::lock_guard<std::mutex> dl(dv->mu);
+    CK(cudaSetDevice(dv->ordinal));
+    G1J* tmp = nullptr;
+    CK(cudaMalloc(&tmp, nb * sizeof(G1J)));
+    cudaMemcpyAsync(tmp, id.data(), nb * sizeof(G1J), cudaMemcpyHostToDevice, dv->stream);
+    k_normalize_points<Fp><<<1, 32, 0, dv->stream>>>(tmp, nb); LAUNCHED();
+    G1A* t = nullptr;
+    const int rc = build_tables<Fp>(dv->stream, tmp, nb, kBatchW, &t);
+    cudaFree(tmp);
+    bt->ordinals.push_back(dv->ordinal);
+    bt->tbl.push_back(t);
+    if (rc) return rc;
+  }
+  if (key->batch.size() >= kBatchCache) key->batch.erase(key->batch.begin());
+  key->batch.push_back(bt);
+  out = bt;
+  return PSB_OK;
+}
+
+int psb_provide_id(psb_key* key, size_t N, const uint64_t* A, const uint64_t* c, const uint64_t* rs, size_t per,
+                   const uint8_t* attr_blob, const uint64_t* attr_off, const uint8_t* ad_blob, const uint64_t* ad_off,
+                   const uint64_t* u, uint8_t* verdict, uint64_t* sig1, uint64_t* sig2, uint8_t* ser) {
+  if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
+  if (!key || !A || !c || (per && !rs) || !attr_blob || !attr_off || !ad_blob || !ad_off || !u || !verdict || !sig1 || !sig2)
+    return fail(PSB_ERR_ARG, "null argument");
+  if (!key->hasX) return fail(PSB_ERR_ARG, "key was created without the signer secret X");
+  int rc = ensure_issuer_tables(key);
+  if (rc) return rc;
+  const size_t n = key->n;
+  return shard(N, [&](int di, size_t b, size_t e) -> int {
+    Dev* dv = g_devs[di];
+    std::lock_guard<std::mutex> lk(dv->mu);
+    const size_t L = e - b;
+    if (L == 0) return PSB_OK;
+    CK(cudaSetDevice(dv->ordinal));
+    cudaStream_t st = dv->stream;
+    const uint64_t o0 = attr_off[b * n], o1 = attr_off[e * n], a0 = ad_off[b], a1 = ad_off[e];
+    Arena ar;
+    G1J *dA = nullptr, *dS1 = nullptr, *dS2 = nullptr; Fr *dc = nullptr, *drs = nullptr, *du = nullptr;
+    uint8_t *dblob = nullptr, *dad = nullptr, *dver = nullptr, *dser = nullptr; uint64_t *doff = nullptr, *dadoff = nullptr;
+    for (int pass = 0; pass < 2; pass++) {
+      ar.used = 0;
+      dA = ar.take<G1J>(L); dc = ar.take<Fr>(L); drs = ar.take<Fr>(L * per + 1); du = ar.take<Fr>(L);
+      dblob = ar.take<uint8_t>((size_t)(o1 - o0) + 16); doff = ar.take<uint64_t>(L * n + 1);
+      dad = ar.take<uint8_t>((size_t)(a1 - a0) + 16); dadoff = ar.take<uint64_t>(L + 1);
+      dver = ar.take<uint8_t>(L); dS1 = ar.take<G1J>(L); dS2 = ar.take<G1J>(L); dser = ar.take<uint8_t>(L * 96);
+      if (pass == 0) { int r = ensure(dv->arena, ar.used); if (r) return r; ar.base = (char*)dv->arena.p; }
+    }
+    CK(cudaMemcpyAsync(dA, A + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dc, c + b * 4, L * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    if (per) CK(cudaMemcpyAsync(drs, rs + b * per * 4, L * per * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(du, u + b * 4, L * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    if (o1 > o0) CK(cudaMemcpyAsync(dblob, attr_blob + o0, (size_t)(o1 - o0), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(doff, attr_off + b * n, (L * n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    if (a1 > a0) CK(cudaMemcpyAsync(dad, ad_blob + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dadoff, ad_off + b, (L + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    const KeyDev& kd = key->d[di];
+    k_provide_id<<<nblocks(L), kBlock, 0, st>>>(L, (int)n, key->w, kd.tblG1, kd.g1pts, dA, dc, drs, (int)per, dblob - o0, doff,
+                                                dad - a0, dadoff, du, dver, dS1, dS2, ser ? dser : nullptr);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(verdict + b, dver, L, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(sig1 + b * 18, dS1, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(sig2 + b * 18, dS2, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+    if (ser) CK(cudaMemcpyAsync(ser + b * 96, dser, L * 96, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PSB_OK;
+  });
+}
+
+int psb_verify_id(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* sig2, const uint64_t* k,
+                  const uint64_t* phi, const uint64_t* E1, const uint64_t* E2, const uint64_t* c, const uint64_t* rs,
+                  size_t per, const uint8_t* attr_blob, const uint64_t* attr_off, const uint8_t* ad_blob,
+                  const uint64_t* ad_off, const uint64_t* service_pt, const uint64_t* y, const uint64_t* g,
+                  const uint64_t* h, int with_id, uint8_t* verdict) {
+  if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
+  if (!key || !sig1 || !sig2 || !k || !phi || !c || (per && !rs) || !attr_blob || !attr_off || !ad_blob || !ad_off ||
+      !service_pt || !verdict)
+    return fail(PSB_ERR_ARG, "null argument");
+  if (with_id && (!E1 || !E2 || !y || !g || !h)) return fail(PSB_ERR_ARG, "E1/E2/y/g/h are required with id retrieval");
+  int rc = ensure_verifier_tables(key);
+  if (rc) return rc;
+  std::shared_ptr<BatchTbl> bt;
+  const uint64_t* const pts[4] = {service_pt, g, y, h};
+  if ((rc = get_batch_tables(key, pts, with_id ? 4 : 1, bt))) return rc;
+  const size_t n = key->n;
+  return shard(N, [&](int di, size_t b, size_t e) -> int {
+    Dev* dv = g_devs[di];
+    std::lock_guard<std::mutex> lk(dv->mu);
+    const size_t L = e - b;
+    if (L == 0) return PSB_OK;
+    CK(cudaSetDevice(dv->ordinal));
+    cudaStream_t st = dv->stream;
+    const uint64_t o0 = attr_off[b * n], o1 = attr_off[e * n], a0 = ad_off[b], a1 = ad_off[e];
+    Arena ar;
+    G1J *dS1 = nullptr, *dS2 = nullptr, *dphi = nullptr, *dE1 = nullptr, *dE2 = nullptr, *dV = nullptr;
+    G2J *dk = nullptr, *dVk = nullptr, *dK = nullptr; Fr *dc = nullptr, *drs = nullptr; Fp12* dF = nullptr;
+    uint8_t *dblob = nullptr, *dad = nullptr, *dver = nullptr, *dok = nullptr; uint64_t *doff = nullptr, *dadoff = nullptr;
+    for (int pass = 0; pass < 2; pass++) {
+      ar.used = 0;
+      dS1 = ar.take<G1J>(L); dS2 = ar.take<G1J>(L); dk = ar.take<G2J>(L); dphi = ar.take<G1J>(L);
+      dE1 = ar.take<G1J>(with_id ? L : 1); dE2 = ar.take<G1J>(with_id ? L : 1);
+      dc = ar.take<Fr>(L); drs = ar.take<Fr>(L * per + 1);
+      dblob = ar.take<uint8_t>((size_t)(o1 - o0) + 16); doff = ar.take<uint64_t>(L * n + 1);
+      dad = ar.take<uint8_t>((size_t)(a1 - a0) + 16); dadoff = ar.take<uint64_t>(L + 1);
+      dVk = ar.take<G2J>(L); dK = ar.take<G2J>(L); dV = ar.take<G1J>(3 * L); dF = ar.take<Fp12>(L);
+      dok = ar.take<uint8_t>(L); dver = ar.take<uint8_t>(L);
+      if (pass == 0) { int r = ensure(dv->arena, ar.used); if (r) return r; ar.base = (char*)dv->arena.p; }
+    }
+    CK(cudaMemcpyAsync(dS1, sig1 + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dS2, sig2 + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dk, k + b * 36, L * sizeof(G2J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dphi, phi + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    if (with_id) {
+      CK(cudaMemcpyAsync(dE1, E1 + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(dE2, E2 + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemcpyAsync(dc, c + b * 4, L * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    if (per) CK(cudaMemcpyAsync(drs, rs + b * per * 4, L * per * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    if (o1 > o0) CK(cudaMemcpyAsync(dblob, attr_blob + o0, (size_t)(o1 - o0), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(doff, attr_off + b * n, (L * n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    if (a1 > a0) CK(cudaMemcpyAsync(dad, ad_blob + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dadoff, ad_off + b, (L + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    const KeyDev& kd = key->d[di];
+    k_vid_g2<<<nblocks(L), kBlock, 0, st>>>(L, (int)n, key->w, kd.tblYY, kd.tblAux, dk, dc, drs, (int)per, with_id, dblob - o0, doff,
+                                            dVk, dK, dok);
+    LAUNCHED();
+    k_vid_g1<<<nblocks(L), kBlock, 0, st>>>(L, kBatchW, bt->tbl[di], dphi, dE1, dE2, dc, drs, (int)per, with_id, dV);
+    LAUNCHED();
+    k_vid_hash<<<nblocks(L), kBlock, 0, st>>>(L, dk, dphi, dE1, dE2, dVk, dV, with_id, dc, dad - a0, dadoff, dok);
+    LAUNCHED();
+    k_verify_miller<<<nblocks(L), kBlock, 0, st>>>(L, dS1, dS2, dK, kd.lines, dF);
+    LAUNCHED();
+    k_verify_final<<<nblocks(L), kBlock, 0, st>>>(L, dS1, dF, dver, nullptr, dok, 0);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(verdict + b, dver, L, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PSB_OK;
+  });
 }
 
 }  // extern "C"

@@ -8,7 +8,9 @@ reference compiled by oracle/Makefile).  Outputs, all small JSON with hex string
   keys.json      synthetic PS keys (n = 5, 10, 20, 50) with known exponents, seed 1,
                  g = H1("abc"), gg = H2("edf"), all points normalized
   protocol.json  reference outputs of the protocol entry points on small seeded batches:
-                 verify (verdict + fused GT), randomize (serialized), provide_id, verify_id
+                 verify (verdict + fused GT), randomize (serialized)
+  elpasso.json   reference outputs of el_passo_provide_id (serialized credentials) and
+                 el_passo_verify_id / _without_id_retrieval (verdicts) on small seeded batches
 """
 import json
 import os
@@ -72,8 +74,30 @@ def protocol():
     return out
 
 
+def elpasso():
+    """reference outputs of el_passo_provide_id / el_passo_verify_id[_without_id_retrieval] (key seed 1, n = 5,
+    attributes 0 and 1 hidden), incl. tampered lanes."""
+    out = {}
+    wl = workload.make_issuance_workload(5, 8, 2, seed=4, tamper_every=3)
+    v, s1, s2, ser = workload.expected_provide_id(wl)
+    ser[~v.astype(bool)] = 0
+    out["provide_id"] = {"n": 5, "key_seed": 1, "A": hx(wl.A), "c": hx(wl.c), "rs": hx(wl.rs), "u": hx(wl.u),
+                         "attrs": [[a.decode() for a in lane] for lane in wl.req_attrs],
+                         "ads": [a.decode() for a in wl.ads], "verdict": v.tolist(), "ser": hx(ser),
+                         "tampered": wl.tampered.tolist()}
+    for name, with_id in (("verify_id", True), ("verify_id_without_id_retrieval", False)):
+        sw = workload.make_signon_workload(5, 8, 2, seed=3, with_id=with_id, tamper_every=2)
+        ev = workload.expected_verify_id(sw)
+        d = {k: hx(sw.proof[k]) for k in ("sig1", "sig2", "k", "phi", "E1", "E2", "c", "rs")}
+        d.update({"attrs": [[a.decode() for a in lane] for lane in sw.proof_attrs], "ads": [a.decode() for a in sw.ads],
+                  "service": sw.service.decode(), "service_pt": hx(sw.service_pt), "y": hx(sw.y), "g": hx(sw.g),
+                  "h": hx(sw.h), "verdict": ev.tolist(), "tampered": sw.tampered.tolist()})
+        out[name] = d
+    return out
+
+
 if __name__ == "__main__":
-    for name, fn in (("mcl_kat.json", mcl_kat), ("keys.json", keys), ("protocol.json", protocol)):
+    for name, fn in (("mcl_kat.json", mcl_kat), ("keys.json", keys), ("protocol.json", protocol), ("elpasso.json", elpasso)):
         with open(os.path.join(HERE, name), "w") as f:
             json.dump(fn(), f, indent=1)
         print("wrote", name, os.path.getsize(os.path.join(HERE, name)), "bytes")

@@ -17,3 +17,99 @@ int hostsim_op(int op, size_t n, const uint32_t* a, const uint32_t* b, const uin
 }
 void hostsim_set_hash_of(const uint8_t* msg, size_t len, uint32_t* k) { psb::fr_set_hash_of(k, msg, len); }
 }
+
+// ---- protocol lane functions (csrc/protocol.cuh) on the host: table building + one lane at a time ------
+#include <vector>
+#include "../../ps-signature-and-el-passo_b200/csrc/protocol.cuh"
+namespace {
+using namespace psb;
+// same table geometry as k_window_bases / k_build_table: entry (win, d) = d * 2^(w win) * B, affine
+template <class F>
+void host_table(std::vector<Aff<F>>& out, const Jac<F>& base, int w) {
+  const int nwin = fixed_nwin(w);
+  const uint32_t half = 1u << (w - 1);
+  Jac<F> cur = base;
+  for (int j = 0; j < nwin; j++) {
+    Jac<F> acc, nrm;
+    pt_set_zero(acc);
+    for (uint32_t d = 1; d <= half; d++) {
+      pt_add(acc, acc, cur);
+      pt_normalize(nrm, acc);
+      Aff<F> e; e.x = nrm.x; e.y = nrm.y;
+      out.push_back(e);
+    }
+    for (int t = 0; t < w; t++) pt_dbl(cur, cur);
+  }
+}
+}  // namespace
+
+extern "C" {
+// fixed-base multiplication probe: out = acc0 + k * B via a host-built table (k: Fr Montgomery)
+void hostsim_fixed_mul_g1(int w, const uint32_t* B, const uint32_t* k_mont, uint32_t* out) {
+  G1J b; ld(b, B);
+  std::vector<G1A> t; host_table(t, b, w);
+  uint32_t k[8]; Fr km; ld(km, k_mont); fr_load_normal(k, &km);
+  G1J acc; pt_set_zero(acc);
+  pt_fixed_mul_acc(acc, t.data(), k, w);
+  G1J n; pt_normalize(n, acc); st(out, n);
+}
+
+void hostsim_provide_id(int n, int w, const uint32_t* g, const uint32_t* X, const uint32_t* Y, size_t N,
+                        const uint32_t* A, const uint32_t* c, const uint32_t* rs, int per, const uint8_t* blob,
+                        const uint64_t* off, const uint8_t* ad_blob, const uint64_t* ad_off, const uint32_t* u,
+                        uint8_t* verdict, uint32_t* sig1, uint32_t* sig2) {
+  std::vector<G1A> tbl;
+  G1J b; ld(b, g); host_table(tbl, b, w);
+  for (int i = 0; i < n; i++) { ld(b, Y + 36 * i); host_table(tbl, b, w); }
+  G1J Xs; ld(Xs, X);
+  for (size_t j = 0; j < N; j++) {
+    G1J a, s1, s2; ld(a, A + 36 * j);
+    bool ok = provide_id_lane(n, TblGeom{w}, tbl.data(), Xs, a, (const Fr*)(c + 8 * j), (const Fr*)(rs + 8 * per * j), per,
+                              blob, off + j * n, ad_blob + ad_off[j], (size_t)(ad_off[j + 1] - ad_off[j]),
+                              (const Fr*)(u + 8 * j), s1, s2);
+    verdict[j] = ok;
+    st(sig1 + 36 * j, s1); st(sig2 + 36 * j, s2);
+  }
+}
+
+void hostsim_verify_id(int n, int w, const uint32_t* gg, const uint32_t* XX, const uint32_t* YY, size_t N,
+                       const uint32_t* sig1, const uint32_t* sig2, const uint32_t* k, const uint32_t* phi,
+                       const uint32_t* E1, const uint32_t* E2, const uint32_t* c, const uint32_t* rs, int per,
+                       const uint8_t* blob, const uint64_t* off, const uint8_t* ad_blob, const uint64_t* ad_off,
+                       const uint32_t* service_pt, const uint32_t* y, const uint32_t* g, const uint32_t* h, int with_id,
+                       uint8_t* nizk, uint8_t* verdict) {
+  std::vector<G2A> tYY, tAux;
+  std::vector<G1A> tB;
+  G2J b2; G1J b1;
+  for (int i = 0; i < n; i++) { ld(b2, YY + 72 * i); host_table(tYY, b2, w); }
+  G2J ggj; ld(ggj, gg); host_table(tAux, ggj, w);
+  ld(b2, XX); host_table(tAux, b2, w);
+  ld(b1, service_pt); host_table(tB, b1, w);
+  if (with_id) { ld(b1, g); host_table(tB, b1, w); ld(b1, y); host_table(tB, b1, w); ld(b1, h); host_table(tB, b1, w); }
+  std::vector<FixedLine> lines(kMillerSteps);
+  G2A q; q.x = ggj.x; q.y = ggj.y;
+  precompute_fixed_lines(lines.data(), q);
+  for (size_t j = 0; j < N; j++) {
+    G2J kj, Vk, K; ld(kj, k + 72 * j);
+    G1J ph, e1, e2, Vphi, VE1, VE2, s1, s2;
+    ld(ph, phi + 36 * j);
+    if (with_id) { ld(e1, E1 + 36 * j); ld(e2, E2 + 36 * j); }
+    const Fr* cj = (const Fr*)(c + 8 * j);
+    const Fr* rj = (const Fr*)(rs + 8 * per * j);
+    bool ok = verify_id_g2_lane(n, TblGeom{w}, tYY.data(), tAux.data(), kj, cj, rj, per, with_id, blob, off + j * n, Vk, K);
+    verify_id_g1_lane(TblGeom{w}, tB.data(), ph, &e1, &e2, cj, rj, per, with_id, Vphi, VE1, VE2);
+    ok = ok && verify_id_hash_lane(kj, ph, &e1, &e2, Vk, Vphi, VE1, VE2, with_id, cj, ad_blob + ad_off[j],
+                                   (size_t)(ad_off[j + 1] - ad_off[j]));
+    nizk[j] = ok;
+    ld(s1, sig1 + 36 * j); ld(s2, sig2 + 36 * j);
+    Fp x1, y1, x2, y2;
+    g1_affine_for_pairing(x1, y1, s1);
+    g1_affine_for_pairing(x2, y2, s2);
+    fp_neg(y2, y2);
+    Fp12 f, e;
+    miller_loop2(f, x1, y1, K, x2, y2, lines.data(), true);
+    final_exp(e, f);
+    verdict[j] = ok && fp12_is_one(e);
+  }
+}
+}

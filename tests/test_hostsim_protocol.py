@@ -1,0 +1,65 @@
+"""CPU: the EL PASSO lane functions of csrc/protocol.cuh (issuance, sign-on verification), compiled for the
+host by tests/hostsim, against the reference's own PSSigner::el_passo_provide_id and
+PSVerifier::el_passo_verify_id -- the same code the GPU kernels wrap, minus the PTX carry chains."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests import workload
+
+
+def _p(a):
+    return None if a is None else np.ascontiguousarray(a).ctypes.data_as(C.c_void_p)
+
+
+def test_fixed_base_table_mul(hostsim, ref):
+    ref.seed(21)
+    k = ref.fr_rand(3)
+    k[2] = ref.fr_from_ints([0])[0]
+    g = ref.hash_to_g1(b"abc")
+    for w in (4, 5):
+        for i in range(3):
+            out = np.zeros(18, dtype=np.uint64)
+            hostsim.hostsim_fixed_mul_g1(C.c_int(w), _p(g), _p(k[i]), _p(out))
+            assert np.array_equal(out, ref.g1_op(ref.G_NORM, ref.g1_mul(g, k[i:i + 1]))[0]), (w, i)
+
+
+@pytest.mark.parametrize("n_attrs,n_hidden", [(5, 2), (1, 1), (1, 0), (3, 3)])
+def test_provide_id_lanes(hostsim, ref, n_attrs, n_hidden):
+    lanes = 6
+    wl = workload.make_issuance_workload(n_attrs, lanes, n_hidden, seed=4, tamper_every=2)
+    ev, e1, e2, _ = workload.expected_provide_id(wl)
+    blob, off = ref.pack_attrs(wl.req_attrs)
+    ad_blob, ad_off = ref.pack_strings(wl.ads)
+    verdict = np.zeros(lanes, dtype=np.uint8)
+    s1 = np.zeros((lanes, 18), dtype=np.uint64)
+    s2 = np.zeros((lanes, 18), dtype=np.uint64)
+    hostsim.hostsim_provide_id(C.c_int(n_attrs), C.c_int(4), _p(wl.key.g), _p(wl.key.X), _p(wl.key.Y), C.c_size_t(lanes),
+                               _p(wl.A), _p(wl.c), _p(wl.rs), C.c_int(wl.rs.shape[1]), _p(blob), _p(off), _p(ad_blob),
+                               _p(ad_off), _p(wl.u), _p(verdict), _p(s1), _p(s2))
+    assert verdict.tolist() == ev.tolist()
+    assert ev.sum() == lanes - len(wl.tampered)
+    ok = ev.astype(bool)
+    assert np.array_equal(s1[ok], ref.g1_op(ref.G_NORM, e1[ok]))
+    assert np.array_equal(s2[ok], ref.g1_op(ref.G_NORM, e2[ok]))
+    assert not s1[~ok].any() and not s2[~ok].any()
+
+
+@pytest.mark.parametrize("n_attrs,n_hidden,with_id", [(5, 2, True), (4, 2, False), (2, 2, True)])
+def test_verify_id_lanes(hostsim, ref, n_attrs, n_hidden, with_id):
+    lanes = 7
+    wl = workload.make_signon_workload(n_attrs, lanes, n_hidden, seed=3, with_id=with_id, tamper_every=1 if n_attrs == 5 else 3)
+    ev = workload.expected_verify_id(wl)
+    p = wl.proof
+    blob, off = ref.pack_attrs(wl.proof_attrs)
+    ad_blob, ad_off = ref.pack_strings(wl.ads)
+    nizk = np.zeros(lanes, dtype=np.uint8)
+    verdict = np.zeros(lanes, dtype=np.uint8)
+    hostsim.hostsim_verify_id(C.c_int(n_attrs), C.c_int(4), _p(wl.key.gg), _p(wl.key.XX), _p(wl.key.YY), C.c_size_t(lanes),
+                              _p(p["sig1"]), _p(p["sig2"]), _p(p["k"]), _p(p["phi"]), _p(p["E1"]), _p(p["E2"]), _p(p["c"]),
+                              _p(p["rs"]), C.c_int(p["rs"].shape[1]), _p(blob), _p(off), _p(ad_blob), _p(ad_off),
+                              _p(wl.service_pt), _p(wl.y), _p(wl.g), _p(wl.h), C.c_int(int(with_id)), _p(nizk), _p(verdict))
+    assert verdict.tolist() == ev.tolist(), (nizk.tolist(), wl.tampered.tolist())
+    if n_attrs != 5:
+        assert ev.sum() == lanes - len(wl.tampered)

@@ -110,6 +110,38 @@ def test_randomize_golden():
         assert O.g1_serialize(r1) + O.g1_serialize(r2) == ser[96 * j:96 * (j + 1)]
 
 
+def test_elpasso_golden():
+    """oracle restatement of el_passo_provide_id / el_passo_verify_id[_without_id_retrieval] against the reference's
+    committed outputs (tests/golden/elpasso.json): serialized credentials and verdicts incl. tampered lanes."""
+    pk, k = _key(5)
+    X = O.g1_from_raw(bytes.fromhex(k["X"]))
+    e = load("elpasso.json")
+    q = e["provide_id"]
+    A, c, rs, u, ser = (bytes.fromhex(q[x]) for x in ("A", "c", "rs", "u", "ser"))
+    N = len(q["verdict"])
+    per = len(rs) // 32 // N
+    for j in range(0, N, 2):   # every other lane keeps the pure-Python run short; covers accepted + tampered lanes
+        rj = [O.fr_from_raw(rs[32 * (j * per + i):32 * (j * per + i + 1)]) for i in range(per)]
+        ok, s1, s2 = O.provide_id(pk, X, O.g1_from_raw(A[144 * j:144 * (j + 1)]), O.fr_from_raw(c[32 * j:32 * (j + 1)]), rj,
+                                  [a.encode() for a in q["attrs"][j]], q["ads"][j].encode(), O.fr_from_raw(u[32 * j:32 * (j + 1)]))
+        assert int(ok) == q["verdict"][j]
+        if ok:
+            assert O.g1_serialize(s1) + O.g1_serialize(s2) == ser[96 * j:96 * (j + 1)]
+    for name, with_id, lanes in (("verify_id", True, (0, 1, 3)), ("verify_id_without_id_retrieval", False, (0, 5))):
+        q = e[name]
+        N = len(q["verdict"])
+        raw = {x: bytes.fromhex(q[x]) for x in ("sig1", "sig2", "k", "phi", "E1", "E2", "c", "rs", "service_pt", "y", "g", "h")}
+        per = len(raw["rs"]) // 32 // N
+        g1 = lambda x, j: O.g1_from_raw(raw[x][144 * j:144 * (j + 1)])  # noqa: E731
+        for j in lanes:
+            rj = [O.fr_from_raw(raw["rs"][32 * (j * per + i):32 * (j * per + i + 1)]) for i in range(per)]
+            got = O.verify_id(pk, g1("sig1", j), g1("sig2", j), O.g2_from_raw(raw["k"][288 * j:288 * (j + 1)]), g1("phi", j),
+                              g1("E1", j) if with_id else None, g1("E2", j) if with_id else None,
+                              O.fr_from_raw(raw["c"][32 * j:32 * (j + 1)]), rj, [a.encode() for a in q["attrs"][j]],
+                              q["ads"][j].encode(), g1("service_pt", 0), g1("y", 0), g1("g", 0), g1("h", 0), with_id)
+            assert int(got) == q["verdict"][j], (name, j)
+
+
 def test_oracle_vs_live_reference(ref):
     """seeded random inputs through the compiled reference, byte for byte."""
     ref.seed(123)

@@ -82,3 +82,115 @@ def expected_verify(wl: VerifyWorkload, want_gt: bool = False, nthreads: int = 0
     """the reference's own PSVerifier::verify on every lane (+ lhs * unitaryInv(rhs) as GT)."""
     nthreads = nthreads or ref.hw_threads()
     return ref.ps_verify(wl.key, wl.sig1, wl.sig2, wl.attrs, want_gt=want_gt, nthreads=nthreads)
+
+
+# ---- EL PASSO issuance (SURVEY 8d config 4) and sign-on (config 3) workloads ---------------------------
+@dataclass
+class IssuanceWorkload:
+    key: "ref.KeyMaterial"
+    A: np.ndarray            # (N, 18)
+    c: np.ndarray            # (N, 4)
+    rs: np.ndarray           # (N, h+1, 4)
+    req_attrs: List[List[bytes]]   # the REQUEST's attribute lists: b"" for hidden
+    ads: List[bytes]
+    u: np.ndarray            # (N, 4) host-supplied issuance scalars
+    tampered: np.ndarray
+
+
+def _hidden_mask(n_attrs: int, n_hidden: int) -> np.ndarray:
+    hidden = np.zeros(n_attrs, dtype=np.uint8)
+    hidden[:n_hidden] = 1
+    return hidden
+
+
+def make_issuance_workload(n_attrs: int = 5, lanes: int = 16, n_hidden: int = 2, seed: int = 4,
+                           tamper_every: int = 0, key_seed: int = 1, nthreads: int = 0) -> IssuanceWorkload:
+    """requests from the reference's own PSRequester::el_passo_request_id under per-lane seeds."""
+    nthreads = nthreads or ref.hw_threads()
+    key = ref.KeyMaterial(n_attrs, seed_=key_seed)
+    attrs = attr_strings(n_attrs, lanes)
+    hidden = _hidden_mask(n_attrs, n_hidden)
+    ads = [b"sess%d" % j for j in range(lanes)]
+    A, c, rs = ref.request_id(key, attrs, hidden, ads, seed * 1000003, nthreads)
+    req_attrs = [[b"" if hidden[i] else lane[i] for i in range(n_attrs)] for lane in attrs]
+    ref.seed(seed + 1)
+    u = ref.fr_rand(lanes)
+    tampered = []
+    if tamper_every:
+        one = ref.fr_from_ints([1])
+        for t, j in enumerate(range(tamper_every - 1, lanes, tamper_every)):
+            kind = t % 4
+            if kind == 0:      # challenge off by one
+                c[j] = ref.fr_op(ref.OP_ADD, c[j:j + 1], one)[0]
+            elif kind == 1:    # a response off by one
+                rs[j, -1] = ref.fr_op(ref.OP_ADD, rs[j, -1:].copy(), one)[0]
+            elif kind == 2:    # associated data changed
+                ads[j] = ads[j] + b"!"
+            else:              # commitment replaced
+                A[j] = ref.g1_op(ref.G_ADD, A[j:j + 1], key.g.reshape(1, -1))[0]
+            tampered.append(j)
+    return IssuanceWorkload(key, A, c, rs, req_attrs, ads, u, np.array(tampered, dtype=np.int64))
+
+
+def expected_provide_id(wl: IssuanceWorkload, nthreads: int = 0):
+    """the reference's own PSSigner::el_passo_provide_id with the RandGen primed to yield u_j."""
+    return ref.provide_id(wl.key, wl.A, wl.c, wl.rs, wl.req_attrs, wl.ads, wl.u, nthreads or ref.hw_threads())
+
+
+@dataclass
+class SignonWorkload:
+    key: "ref.KeyMaterial"
+    proof: dict              # sig1 sig2 k phi E1 E2 c rs
+    proof_attrs: List[List[bytes]]
+    ads: List[bytes]
+    service: bytes
+    service_pt: np.ndarray
+    y: np.ndarray
+    g: np.ndarray
+    h: np.ndarray
+    with_id: bool
+    tampered: np.ndarray
+
+
+def make_signon_workload(n_attrs: int = 5, lanes: int = 16, n_hidden: int = 2, seed: int = 3, with_id: bool = True,
+                         tamper_every: int = 0, key_seed: int = 1, nthreads: int = 0) -> SignonWorkload:
+    """proofs from the reference's own PSRequester::el_passo_prove_id (test/ps-tests.cc:106-111 shape)."""
+    nthreads = nthreads or ref.hw_threads()
+    key = ref.KeyMaterial(n_attrs, seed_=key_seed)
+    attrs = attr_strings(n_attrs, lanes)
+    hidden = _hidden_mask(n_attrs, n_hidden)
+    sig1, sig2 = sign_lanes(key, attrs, seed + 7, nthreads)
+    ads = [b"sess%d" % j for j in range(lanes)]
+    service = b"rp.example"
+    y, g, h = ref.hash_to_g1(b"ghi"), ref.hash_to_g1(b"abc"), ref.hash_to_g1(b"jkl")
+    proof = ref.prove_id(key, sig1, sig2, attrs, hidden, ads, service, y, g, h, seed * 1000003, with_id, nthreads)
+    proof_attrs = [[b"" if hidden[i] else lane[i] for i in range(n_attrs)] for lane in attrs]
+    tampered = []
+    if tamper_every:
+        one = ref.fr_from_ints([1])
+        for t, j in enumerate(range(tamper_every - 1, lanes, tamper_every)):
+            kind = t % 6
+            if kind == 0:
+                proof["c"][j] = ref.fr_op(ref.OP_ADD, proof["c"][j:j + 1], one)[0]
+            elif kind == 1:
+                proof["rs"][j, 0] = ref.fr_op(ref.OP_ADD, proof["rs"][j, :1].copy(), one)[0]
+            elif kind == 2:
+                proof["k"][j] = ref.g2_op(ref.G_ADD, proof["k"][j:j + 1], key.gg.reshape(1, -1))[0]
+            elif kind == 3:    # NIZK still fine, pairing check fails
+                proof["sig2"][j] = ref.g1_op(ref.G_ADD, proof["sig2"][j:j + 1], key.g.reshape(1, -1))[0]
+            elif kind == 4:    # sigma = (0, 0): el_passo_verify_id has no zero check (SURVEY F9)
+                proof["sig1"][j] = 0
+                proof["sig2"][j] = 0
+            else:              # plaintext attribute changed: NIZK fine, K differs
+                if n_hidden < n_attrs:
+                    proof_attrs[j][n_attrs - 1] = proof_attrs[j][n_attrs - 1] + b"x"
+                else:
+                    ads[j] = ads[j] + b"!"
+            tampered.append(j)
+    return SignonWorkload(key, proof, proof_attrs, ads, service, ref.hash_to_g1(service), y, g, h, with_id,
+                          np.array(tampered, dtype=np.int64))
+
+
+def expected_verify_id(wl: SignonWorkload, nthreads: int = 0):
+    return ref.verify_id(wl.key, wl.proof, wl.proof_attrs, wl.ads, wl.service, wl.y, wl.g, wl.h, wl.with_id,
+                         nthreads or ref.hw_threads())
