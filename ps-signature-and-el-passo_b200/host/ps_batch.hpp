@@ -1,0 +1,284 @@
+// ps_batch.hpp -- C++ host side of the B200 batch engine: the reference's three role classes with
+// BATCHED overloads that marshal into flat arrays and call the extern "C" layer (include/psb.h).
+//
+// Drop-in use: include this header instead of ps-signer.h / ps-requester.h / ps-verifier.h and write
+// `psb::PSVerifier` (or `using psb::PSVerifier;`).  The classes derive from the reference's own
+// (src/ps-verifier.h:11-71, src/ps-requester.h:11-128, src/ps-signer.h:11-96), so every scalar method
+// keeps its signature and keeps running on the host through mcl; the overloads below add the same
+// methods over std::vector batches and run on the GPUs:
+//
+//   psb::PSVerifier::verify(sigs, all_attributes)                       -> psb_verify
+//   psb::PSVerifier::el_passo_verify_id(proofs, ads, service, y, g, h)  -> psb_verify_id
+//   psb::PSVerifier::el_passo_verify_id_without_id_retrieval(...)       -> psb_verify_id (with_id = 0)
+//   psb::PSRequester::verify(sigs, all_attributes)                      -> psb_verify
+//   psb::PSRequester::randomize_credential(sigs, t)                     -> psb_randomize   (t host-supplied)
+//   psb::PSSigner::el_passo_provide_id(requests, ads, u, sigs)          -> psb_provide_id  (u host-supplied)
+//
+// mcl objects are passed WITHOUT conversion: G1/G2/Fr in memory are Montgomery limb arrays in exactly
+// the layout psb.h takes.  Requires mcl::bn::initPairing(mcl::BLS12_381) -- the engine
+// implements the 381-bit curve only (the reference's tests default to BN254) -- and
+// psb::init() once per process.  Errors: std::runtime_error("attribute size does not match") as in
+// src/ps-requester.cc:31-33 for size mismatches; psb::Error for engine failures (no GPU, CUDA error).
+// There is no CPU fallback for the batched overloads.
+#ifndef PSB_HOST_PS_BATCH_HPP_
+#define PSB_HOST_PS_BATCH_HPP_
+
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "ps-requester.h"
+#include "ps-signer.h"
+#include "ps-verifier.h"
+#include "psb.h"
+
+namespace psb {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& what) : std::runtime_error(what + ": " + psb_last_error()), code(c) {}
+};
+inline void check(int rc, const char* what) { if (rc != PSB_OK) throw Error(rc, what); }
+
+// once per process, after mcl::bn::initPairing(mcl::BLS12_381); devices = CUDA ordinals (empty = device 0)
+inline void init(const std::vector<int>& devices = {}) {
+  static_assert(sizeof(mcl::bls12::G1) == 18 * 8 && sizeof(mcl::bls12::G2) == 36 * 8 && sizeof(mcl::bls12::Fr) == 4 * 8 &&
+                sizeof(mcl::bls12::GT) == 72 * 8, "include <mcl/bls12_381.hpp> (384-bit Fp, 256-bit Fr storage)");
+  if (mcl::bls12::Fp::getOp().N != 6 || !mcl::bls12::Fp::getOp().isMont)
+    throw std::runtime_error("psb: call mcl::bn::initPairing(mcl::BLS12_381) first (381-bit Montgomery field)");
+  check(psb_init(PSB_CURVE_BLS12_381, devices.empty() ? nullptr : devices.data(), (int)devices.size()), "psb_init");
+}
+
+namespace detail {
+inline const uint64_t* u64(const void* p) { return reinterpret_cast<const uint64_t*>(p); }
+inline uint64_t* u64(void* p) { return reinterpret_cast<uint64_t*>(p); }
+
+// flat string arrays: blob + offsets[count + 1]
+struct Strings {
+  std::vector<uint8_t> blob;
+  std::vector<uint64_t> off{0};
+  void add(const std::string& s) {
+    blob.insert(blob.end(), s.begin(), s.end());
+    off.push_back(blob.size());
+  }
+  const uint8_t* data() { if (blob.empty()) blob.push_back(0); return blob.data(); }
+};
+
+struct KeyDeleter { void operator()(psb_key* k) const { psb_key_destroy(k); } };
+using KeyHandle = std::shared_ptr<psb_key>;
+
+inline KeyHandle make_key(const PSPubKey& pk, const mcl::bls12::G1* X_secret, int window_bits) {
+  if (pk.Yi.size() != pk.YYi.size()) throw std::runtime_error("attribute size does not match");
+  psb_key* k = psb_key_create(u64(&pk.g), u64(&pk.gg), u64(&pk.XX), u64(pk.Yi.data()), u64(pk.YYi.data()), pk.Yi.size(),
+                              X_secret ? u64(X_secret) : nullptr, window_bits);
+  if (!k) throw Error(PSB_ERR_ARG, "psb_key_create");
+  return KeyHandle(k, KeyDeleter());
+}
+
+inline std::vector<uint8_t> verify_batch(psb_key* key, size_t n, const std::vector<PSCredential>& sigs,
+                                         const std::vector<std::vector<std::string>>& all_attributes) {
+  const size_t N = sigs.size();
+  if (all_attributes.size() != N) throw std::runtime_error("attribute size does not match");
+  std::vector<mcl::bls12::G1> s1(N), s2(N);
+  Strings at;
+  for (size_t j = 0; j < N; j++) {
+    if (all_attributes[j].size() != n) throw std::runtime_error("attribute size does not match");
+    s1[j] = sigs[j].sig1; s2[j] = sigs[j].sig2;
+    for (const auto& a : all_attributes[j]) at.add(a);
+  }
+  std::vector<uint8_t> verdict(N);
+  if (N == 0) return verdict;
+  check(psb_verify(key, N, u64(s1.data()), u64(s2.data()), at.data(), at.off.data(), nullptr, verdict.data(), nullptr),
+        "psb_verify");
+  return verdict;
+}
+}  // namespace detail
+
+// ---- PSVerifier ----------------------------------------------------------------------------------------
+class PSVerifier : public ::PSVerifier {
+public:
+  explicit PSVerifier(const PSPubKey& pk, int window_bits = 0)
+      : ::PSVerifier(pk), m_n(pk.Yi.size()), m_key(detail::make_key(pk, nullptr, window_bits)) {}
+
+  using ::PSVerifier::verify;
+  using ::PSVerifier::el_passo_verify_id;
+  using ::PSVerifier::el_passo_verify_id_without_id_retrieval;
+
+  // batched PSVerifier::verify (src/ps-verifier.cc:13-35): verdict[j] = verify(sigs[j], all_attributes[j])
+  std::vector<uint8_t> verify(const std::vector<PSCredential>& sigs,
+                              const std::vector<std::vector<std::string>>& all_attributes) const {
+    return detail::verify_batch(m_key.get(), m_n, sigs, all_attributes);
+  }
+
+  // batched el_passo_verify_id (src/ps-verifier.cc:37-138); one associated_data per proof
+  std::vector<uint8_t> el_passo_verify_id(const std::vector<IdProof>& proofs, const std::vector<std::string>& associated_data,
+                                          const std::string& service_name, const mcl::bls12::G1& authority_pk,
+                                          const mcl::bls12::G1& g, const mcl::bls12::G1& h) const {
+    return verify_id_batch(proofs, associated_data, service_name, &authority_pk, &g, &h);
+  }
+  // batched el_passo_verify_id_without_id_retrieval (src/ps-verifier.cc:140-212)
+  std::vector<uint8_t> el_passo_verify_id_without_id_retrieval(const std::vector<IdProof>& proofs,
+                                                               const std::vector<std::string>& associated_data,
+                                                               const std::string& service_name) const {
+    return verify_id_batch(proofs, associated_data, service_name, nullptr, nullptr, nullptr);
+  }
+
+private:
+  std::vector<uint8_t> verify_id_batch(const std::vector<IdProof>& proofs, const std::vector<std::string>& ads,
+                                       const std::string& service_name, const mcl::bls12::G1* y, const mcl::bls12::G1* g,
+                                       const mcl::bls12::G1* h) const {
+    using namespace mcl::bls12;
+    const size_t N = proofs.size();
+    const bool with_id = y != nullptr;
+    if (ads.size() != N) throw std::runtime_error("associated data size does not match");
+    std::vector<uint8_t> verdict(N);
+    if (N == 0) return verdict;
+    const size_t per = proofs[0].rs.size();
+    std::vector<G1> s1(N), s2(N), phi(N), E1(with_id ? N : 0), E2(with_id ? N : 0);
+    std::vector<G2> k(N);
+    std::vector<Fr> c(N), rs(N * per + 1);
+    std::vector<uint8_t> missing(N, 0);
+    detail::Strings at, ad;
+    for (size_t j = 0; j < N; j++) {
+      const IdProof& p = proofs[j];
+      if (p.attributes.size() != m_n) throw std::runtime_error("attribute size does not match");
+      if (p.rs.size() != per) throw std::runtime_error("psb: proofs of one batch must carry the same number of responses");
+      s1[j] = p.sig1; s2[j] = p.sig2; k[j] = p.k; phi[j] = p.phi; c[j] = p.c;
+      for (size_t i = 0; i < per; i++) rs[j * per + i] = p.rs[i];
+      if (with_id) {
+        if (p.E1.has_value() && p.E2.has_value()) { E1[j] = *p.E1; E2[j] = *p.E2; }
+        else { E1[j].clear(); E2[j].clear(); missing[j] = 1; }   // reference returns false (ps-verifier.cc:68-70)
+      }
+      for (const auto& a : p.attributes) at.add(a);
+      ad.add(ads[j]);
+    }
+    G1 svc;
+    hashAndMapToG1(svc, service_name);   // one value per batch, on the host
+    check(psb_verify_id(m_key.get(), N, detail::u64(s1.data()), detail::u64(s2.data()), detail::u64(k.data()),
+                                detail::u64(phi.data()), with_id ? detail::u64(E1.data()) : nullptr,
+                                with_id ? detail::u64(E2.data()) : nullptr, detail::u64(c.data()), detail::u64(rs.data()), per,
+                                at.data(), at.off.data(), ad.data(), ad.off.data(), detail::u64(&svc),
+                                with_id ? detail::u64(y) : nullptr, with_id ? detail::u64(g) : nullptr,
+                                with_id ? detail::u64(h) : nullptr, with_id ? 1 : 0, verdict.data()),
+                  "psb_verify_id");
+    for (size_t j = 0; j < N; j++) if (missing[j]) verdict[j] = 0;
+    return verdict;
+  }
+
+  size_t m_n;
+  detail::KeyHandle m_key;
+};
+
+// ---- PSRequester ---------------------------------------------------------------------------------------
+class PSRequester : public ::PSRequester {
+public:
+  explicit PSRequester(const PSPubKey& pk, int window_bits = 0)
+      : ::PSRequester(pk), m_n(pk.Yi.size()), m_key(detail::make_key(pk, nullptr, window_bits)) {}
+
+  using ::PSRequester::verify;
+  using ::PSRequester::randomize_credential;
+
+  // batched PSRequester::verify (src/ps-requester.cc:115-137)
+  std::vector<uint8_t> verify(const std::vector<PSCredential>& sigs,
+                              const std::vector<std::vector<std::string>>& all_attributes) const {
+    return detail::verify_batch(m_key.get(), m_n, sigs, all_attributes);
+  }
+
+  // batched randomize_credential (src/ps-requester.cc:139-148): out[j] = (t[j] sig1, t[j] sig2) with the
+  // randomisers t supplied by the caller (draw them with Fr::setByCSPRNG exactly as the reference does)
+  std::vector<PSCredential> randomize_credential(const std::vector<PSCredential>& sigs,
+                                                 const std::vector<mcl::bls12::Fr>& t) const {
+    using namespace mcl::bls12;
+    const size_t N = sigs.size();
+    if (t.size() != N) throw std::runtime_error("psb: one randomiser per credential");
+    std::vector<PSCredential> out(N);
+    if (N == 0) return out;
+    std::vector<G1> s1(N), s2(N), o1(N), o2(N);
+    for (size_t j = 0; j < N; j++) { s1[j] = sigs[j].sig1; s2[j] = sigs[j].sig2; }
+    check(psb_randomize(N, detail::u64(s1.data()), detail::u64(s2.data()), detail::u64(t.data()),
+                                detail::u64(o1.data()), detail::u64(o2.data()), nullptr), "psb_randomize");
+    for (size_t j = 0; j < N; j++) { out[j].sig1 = o1[j]; out[j].sig2 = o2[j]; }
+    return out;
+  }
+
+private:
+  size_t m_n;
+  detail::KeyHandle m_key;
+};
+
+// ---- PSSigner ------------------------------------------------------------------------------------------
+// The reference keeps X = g^x private (src/ps-signer.h:92) and drops the exponents.  The
+// batch path needs X on the device; key_gen() below recovers it through the PUBLIC API only: with the
+// process RandGen momentarily yielding u = 1, sign_commitment(g) returns (g, X + g) (ps-signer.cc:132-146).
+// A maintainer applying INTEGRATION.md's in-class patch reads m_sk_X directly instead.
+class PSSigner : public ::PSSigner {
+public:
+  explicit PSSigner(size_t attribute_num, int window_bits = 0) : ::PSSigner(attribute_num), m_w(window_bits) {}
+  PSSigner(size_t attribute_num, const mcl::bls12::G1& g, const mcl::bls12::G2& gg, int window_bits = 0)
+      : ::PSSigner(attribute_num, g, gg), m_w(window_bits) {}
+
+  using ::PSSigner::el_passo_provide_id;
+
+  PSPubKey key_gen() {   // hides ::PSSigner::key_gen (not virtual there); same return value
+    using namespace mcl::bls12;
+    PSPubKey pk = ::PSSigner::key_gen();
+    mcl::fp::RandGen saved = mcl::fp::RandGen::get();
+    mcl::fp::RandGen::setRandFunc(nullptr, read_one);
+    PSCredential s = ::PSSigner::sign_commitment(pk.g);
+    mcl::fp::RandGen::setRandGen(saved);
+    G1 X;
+    G1::sub(X, s.sig2, pk.g);
+    if (s.sig1 != pk.g) throw std::runtime_error("psb: could not recover the signer secret through sign_commitment");
+    m_n = pk.Yi.size();
+    m_key = detail::make_key(pk, &X, m_w);
+    return pk;
+  }
+
+  // batched el_passo_provide_id (src/ps-signer.cc:63-72): returns the NIZK verdicts; sigs[j] is assigned for
+  // accepted requests (normalised points, equal as group elements and byte-identical once serialised to the
+  // reference's with the same u[j]); u[j] are the issuance scalars the reference draws with Fr::setByCSPRNG.
+  std::vector<uint8_t> el_passo_provide_id(const std::vector<PSCredRequest>& requests,
+                                           const std::vector<std::string>& associated_data,
+                                           const std::vector<mcl::bls12::Fr>& u, std::vector<PSCredential>& sigs) const {
+    using namespace mcl::bls12;
+    if (!m_key) throw std::runtime_error("psb: call key_gen() first");
+    const size_t N = requests.size();
+    if (associated_data.size() != N || u.size() != N) throw std::runtime_error("psb: one associated_data and one u per request");
+    std::vector<uint8_t> verdict(N);
+    sigs.resize(N);
+    if (N == 0) return verdict;
+    const size_t per = requests[0].rs.size();
+    std::vector<G1> A(N), o1(N), o2(N);
+    std::vector<Fr> c(N), rs(N * per + 1);
+    detail::Strings at, ad;
+    for (size_t j = 0; j < N; j++) {
+      const PSCredRequest& r = requests[j];
+      if (r.attributes.size() != m_n) throw std::runtime_error("attribute size does not match");
+      if (r.rs.size() != per) throw std::runtime_error("psb: requests of one batch must carry the same number of responses");
+      A[j] = r.A; c[j] = r.c;
+      for (size_t i = 0; i < per; i++) rs[j * per + i] = r.rs[i];
+      for (const auto& a : r.attributes) at.add(a);
+      ad.add(associated_data[j]);
+    }
+    check(psb_provide_id(m_key.get(), N, detail::u64(A.data()), detail::u64(c.data()), detail::u64(rs.data()), per,
+                                 at.data(), at.off.data(), ad.data(), ad.off.data(), detail::u64(u.data()), verdict.data(),
+                                 detail::u64(o1.data()), detail::u64(o2.data()), nullptr), "psb_provide_id");
+    for (size_t j = 0; j < N; j++) if (verdict[j]) { sigs[j].sig1 = o1[j]; sigs[j].sig2 = o2[j]; }
+    return verdict;
+  }
+
+private:
+  static uint32_t read_one(void*, void* buf, uint32_t n) {   // little-endian integer 1
+    std::memset(buf, 0, n);
+    if (n) static_cast<uint8_t*>(buf)[0] = 1;
+    return n;
+  }
+  int m_w;
+  size_t m_n = 0;
+  detail::KeyHandle m_key;
+};
+
+}  // namespace psb
+#endif  // PSB_HOST_PS_BATCH_HPP_

@@ -1,0 +1,131 @@
+// tests/host/test_ps_batch.cc -- TEST of the C++ drop-in (host/ps_batch.hpp): the reference's own EL PASSO
+// flow (test/ps-tests.cc:53-137), with every RP / IdP / randomize step ALSO run through the batched
+// overloads on the GPU and compared lane by lane with the reference's scalar methods (mcl, host).
+// Linked against the UNMODIFIED reference objects (oracle/_ref/*.o) and libpsb.so.  Exit 0 = all equal.
+// Without a usable GPU psb::init throws: exit code 3 (there is no CPU fallback).
+#include <cstdio>
+#include <iostream>
+#include <tuple>
+
+#include "ps_batch.hpp"
+
+using namespace mcl::bls12;
+
+static int fails = 0;
+#define EXPECT(cond)                                                          \
+  do {                                                                        \
+    if (!(cond)) { std::printf("FAIL %s:%d %s\n", __FILE__, __LINE__, #cond); fails++; } \
+  } while (0)
+
+static std::string ser(const G1& p) { return p.serializeToHexStr(); }
+
+int main(int argc, char** argv) {
+  const size_t N = argc > 1 ? std::stoul(argv[1]) : 24;   // lanes
+  const size_t n = 5;                                      // attributes, first two hidden
+  initPairing(mcl::BLS12_381);
+  try {
+    psb::init();
+  } catch (const std::exception& e) {
+    std::printf("psb::init failed (no CPU fallback): %s\n", e.what());
+    return 3;
+  }
+  G1 g, authority_pk, h;
+  G2 gg;
+  hashAndMapToG1(g, "abc");
+  hashAndMapToG2(gg, "edf");
+  hashAndMapToG1(authority_pk, "ghi");
+  hashAndMapToG1(h, "jkl");
+
+  psb::PSSigner idp(n, g, gg, 8);
+  PSPubKey pk = idp.key_gen();
+  psb::PSVerifier rp(pk, 8);
+  psb::PSRequester wallet(pk, 8);
+
+  // users: one reference PSRequester per lane (it keeps the blinding factor between request and unblind)
+  std::vector<::PSRequester> users(N, ::PSRequester(pk));
+  std::vector<std::vector<std::tuple<std::string, bool>>> attrs(N);
+  std::vector<std::vector<std::string>> plain(N);
+  std::vector<PSCredRequest> requests;
+  std::vector<std::string> ads;
+  for (size_t j = 0; j < N; j++) {
+    for (size_t i = 0; i < n; i++) {
+      attrs[j].push_back(std::make_tuple("a" + std::to_string(i) + ":" + std::to_string(j), i < 2));
+      plain[j].push_back(std::get<0>(attrs[j][i]));
+    }
+    ads.push_back("sess" + std::to_string(j));
+    requests.push_back(users[j].el_passo_request_id(attrs[j], ads[j]));
+  }
+  if (N > 3) requests[3].c += 1;   // tampered request: must be rejected by both paths
+
+  // IdP-ProvideID, batched on the GPU with host-supplied u
+  std::vector<Fr> u(N);
+  for (auto& x : u) x.setByCSPRNG();
+  std::vector<PSCredential> issued;
+  std::vector<uint8_t> ok = idp.el_passo_provide_id(requests, ads, u, issued);
+  std::vector<PSCredential> creds(N);
+  for (size_t j = 0; j < N; j++) {
+    PSCredential scalar_sig;
+    const bool scalar_ok = idp.el_passo_provide_id(requests[j], ads[j], scalar_sig);   // reference, own random u
+    EXPECT(scalar_ok == (ok[j] != 0));
+    if (!ok[j]) { creds[j] = scalar_sig; continue; }
+    // same u => same credential: sigma1 = u g, sigma2 / sigma1 relation checked through unblind + verify
+    G1 ug; G1::mul(ug, pk.g, u[j]);
+    EXPECT(ser(issued[j].sig1) == ser(ug));
+    creds[j] = users[j].unblind_credential(issued[j]);
+    EXPECT(users[j].verify(creds[j], plain[j]));      // reference verifies the GPU-issued credential
+  }
+  if (N > 3) {   // lane 3's request was tampered: give it a valid credential for the later steps
+    PSCredRequest r = users[3].el_passo_request_id(attrs[3], ads[3]);
+    PSCredential s; EXPECT(idp.el_passo_provide_id(r, ads[3], s));
+    creds[3] = users[3].unblind_credential(s);
+  }
+
+  // batched verify (requester and verifier side) vs the reference, incl. tampered lanes
+  std::vector<PSCredential> vc = creds;
+  if (N > 5) { vc[5].sig2 += pk.g; vc[1].sig1.clear(); }
+  std::vector<uint8_t> v1 = rp.verify(vc, plain), v2 = wallet.verify(vc, plain);
+  for (size_t j = 0; j < N; j++) {
+    const bool want = static_cast<const ::PSVerifier&>(rp).verify(vc[j], plain[j]);
+    EXPECT(want == (v1[j] != 0) && want == (v2[j] != 0));
+  }
+
+  // batched randomize_credential with host-supplied t vs t * sigma on the host
+  std::vector<Fr> t(N);
+  for (auto& x : t) x.setByCSPRNG();
+  std::vector<PSCredential> rnd = wallet.randomize_credential(creds, t);
+  for (size_t j = 0; j < N; j++) {
+    G1 a, b;
+    G1::mul(a, creds[j].sig1, t[j]);
+    G1::mul(b, creds[j].sig2, t[j]);
+    EXPECT(ser(rnd[j].sig1) == ser(a) && ser(rnd[j].sig2) == ser(b));
+  }
+
+  // User-ProveID on the host (reference), RP-VerifyID batched on the GPU vs the reference
+  std::vector<IdProof> proofs, proofs2;
+  for (size_t j = 0; j < N; j++) {
+    proofs.push_back(users[j].el_passo_prove_id(creds[j], attrs[j], ads[j], "service", authority_pk, g, h));
+    proofs2.push_back(users[j].el_passo_prove_id_without_id_retrieval(creds[j], attrs[j], ads[j], "service"));
+  }
+  if (N > 6) {
+    proofs[2].c += 1; proofs[4].rs[1] += 1; proofs[6].sig2 += pk.g; proofs2[2].k += pk.gg; proofs2[4].attributes[4] += "x";
+    proofs[0].E1.reset();
+  }
+  std::vector<uint8_t> w1 = rp.el_passo_verify_id(proofs, ads, "service", authority_pk, g, h);
+  std::vector<uint8_t> w2 = rp.el_passo_verify_id_without_id_retrieval(proofs2, ads, "service");
+  size_t accepted = 0;
+  for (size_t j = 0; j < N; j++) {
+    const ::PSVerifier& ref = rp;
+    EXPECT(ref.el_passo_verify_id(proofs[j], ads[j], "service", authority_pk, g, h) == (w1[j] != 0));
+    EXPECT(ref.el_passo_verify_id_without_id_retrieval(proofs2[j], ads[j], "service") == (w2[j] != 0));
+    accepted += w1[j];
+  }
+  EXPECT(accepted > 0 && accepted < N);
+
+  // size mismatch raises like the reference's requester (src/ps-requester.cc:31-33)
+  bool threw = false;
+  try { plain[0].pop_back(); rp.verify(vc, plain); } catch (const std::runtime_error&) { threw = true; }
+  EXPECT(threw);
+
+  std::printf("test_ps_batch: %zu lanes, %llu kernel launches, %d failures\n", N, (unsigned long long)psb_launch_count(), fails);
+  return fails ? 1 : 0;
+}
