@@ -161,6 +161,23 @@ def cpu_reference_verify(key_n: int, sig1, sig2, lane_attrs, budget_s: float):
                 jit=ref.jit_enabled())
 
 
+def max_over_ranks(values, world: int, device=None):
+    """MAX over ranks of a list of floats (device times): the whole job is as slow as its slowest GPU.
+    Works on any torch.distributed backend (NCCL on the GPU box, gloo in the CPU tests)."""
+    if world <= 1:
+        return [float(v) for v in values]
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(values, dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+def job_throughput(lanes_per_rank: int, world: int, steps: int, ms_max: float) -> float:
+    """whole-job units per second: every rank processed lanes_per_rank * steps lanes in ms_max (weak scaling)."""
+    return world * lanes_per_rank * steps / (ms_max * 1e-3)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -289,17 +306,14 @@ def main():
     h2d = int(sig1.nbytes + sig2.nbytes + int(off[-1]) + off.nbytes)
     d2h = int(N)
 
-    t_ms = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(t_ms[0]), float(t_ms[1])
+    ms_total, e2e_ms = max_over_ranks([ms_total, e2e_s * 1e3], world, dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    value = world * N * args.steps / (ms_total * 1e-3)
-    e2e_val = world * N * e2e_steps / (e2e_ms * 1e-3)
+    value = job_throughput(N, world, args.steps, ms_total)
+    e2e_val = job_throughput(N, world, e2e_steps, e2e_ms)
     names = ["k_verify_msm", "k_verify_miller", "k_verify_final"]
     nwin = (256 + args.window_bits - 1) // args.window_bits
     work = [N_ATTRS * nwin * A_MSM_PER_ADD, A_MILLER2, A_FINALEXP]

@@ -39,6 +39,9 @@ int psb_init(int curve, const int* devices, int ndev);
 void psb_shutdown(void);
 int psb_num_devices(void);
 const char* psb_last_error(void);
+/* lane range [begin, end) that device k of ndev processes in every batched call (contiguous split):
+ * the host-side "gather" is each device writing its slice of the caller's output arrays.  Pure host arithmetic. */
+int psb_shard_range(size_t N, int ndev, int k, size_t* begin, size_t* end);
 /* number of kernels this library has launched since psb_init (for the bench's gpu_launches) */
 uint64_t psb_launch_count(void);
 

@@ -116,7 +116,8 @@ int shard(size_t N, Fn fn) {
   std::vector<std::string> errs(G);
   std::vector<std::thread> th;
   for (int k = 0; k < G; k++) {
-    const size_t b = N * k / G, e = N * (k + 1) / G;
+    size_t b, e;
+    psb_shard_range(N, G, k, &b, &e);
     th.emplace_back([&, k, b, e]() { rc[k] = fn(k, b, e); if (rc[k]) errs[k] = g_err; });
   }
   for (auto& t : th) t.join();
@@ -198,6 +199,13 @@ extern "C" {
 const char* psb_last_error(void) { return g_err.c_str(); }
 uint64_t psb_launch_count(void) { return g_launches.load(); }
 int psb_num_devices(void) { return g_init ? (int)g_devs.size() : 0; }
+int psb_shard_range(size_t N, int ndev, int k, size_t* begin, size_t* end) {
+  if (ndev <= 0 || k < 0 || k >= ndev || !begin || !end) return fail(PSB_ERR_ARG, "bad shard index");
+  // contiguous, balanced to within one lane, covers [0, N) exactly; 128-bit product: N can be 2^24 * ndev
+  *begin = (size_t)((unsigned __int128)N * (unsigned)k / (unsigned)ndev);
+  *end = (size_t)((unsigned __int128)N * (unsigned)(k + 1) / (unsigned)ndev);
+  return PSB_OK;
+}
 int psb_set_profiling(int on) { g_profile = on != 0; return PSB_OK; }
 int psb_last_phase_ms(int dev_index, float* ms) {
   if (!g_init || dev_index < 0 || dev_index >= (int)g_devs.size() || !ms) return fail(PSB_ERR_ARG, "bad argument");

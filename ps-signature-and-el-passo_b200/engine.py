@@ -54,7 +54,7 @@ def lib():
     return _lib
 
 
-EXPORTS = ["psb_init", "psb_shutdown", "psb_num_devices", "psb_last_error", "psb_launch_count",
+EXPORTS = ["psb_init", "psb_shutdown", "psb_num_devices", "psb_last_error", "psb_shard_range", "psb_launch_count",
            "psb_key_create", "psb_key_destroy", "psb_key_num_attributes", "psb_key_table_bytes",
            "psb_verify", "psb_verify_ws_bytes", "psb_verify_dev", "psb_randomize", "psb_provide_id",
            "psb_verify_id", "psb_pairing", "psb_g1_mul", "psb_set_profiling", "psb_last_phase_ms", "psb_test_op_shape", "psb_test_op", "psb_microbench"]
@@ -81,6 +81,13 @@ def init(devices: Optional[Sequence[int]] = None) -> None:
 def ensure_init():
     if not _inited:
         init()
+
+
+def shard_range(N: int, ndev: int, k: int):
+    """lane range [b, e) of device k (pure host arithmetic, no GPU needed)."""
+    b, e = C.c_size_t(), C.c_size_t()
+    _check(lib().psb_shard_range(C.c_size_t(N), C.c_int(ndev), C.c_int(k), C.byref(b), C.byref(e)), "psb_shard_range")
+    return int(b.value), int(e.value)
 
 
 def launch_count() -> int:
@@ -110,6 +117,13 @@ def pack_strings(strs: Sequence[bytes]):
 
 def pack_attrs(attrs: Sequence[Sequence[bytes]]):
     return pack_strings([a for lane in attrs for a in lane])
+
+
+def _packed(x, flat: bool):
+    """accept pre-packed (blob, off) pairs wherever string lists are taken (keeps python out of timed regions)."""
+    if isinstance(x, tuple):
+        return x
+    return pack_strings(list(x)) if flat else pack_attrs(x)
 
 
 class PSPubKey:
@@ -197,8 +211,10 @@ class PSVerifier:
         s1 = _u64(proof["sig1"], G1)
         N = s1.shape[0]
         rs = np.ascontiguousarray(proof["rs"], dtype=np.uint64).reshape(N, -1, FR)
-        blob, off = pack_attrs(attributes)
-        ad_blob, ad_off = pack_strings(list(associated_data))
+        blob, off = _packed(attributes, False)
+        ad_blob, ad_off = _packed(associated_data, True)
+        if off.shape[0] != N * self.m_pk.n + 1 or ad_off.shape[0] != N + 1:
+            raise ValueError("attribute size does not match")
         verdict = np.zeros(N, dtype=np.uint8)
         z1 = np.zeros((1, G1), dtype=np.uint64)
         _check(lib().psb_verify_id(
@@ -248,8 +264,10 @@ class PSSigner:
         A = _u64(A, G1)
         N = A.shape[0]
         rs = np.ascontiguousarray(rs, dtype=np.uint64).reshape(N, -1, FR)
-        blob, off = pack_attrs(attributes)
-        ad_blob, ad_off = pack_strings(list(associated_data))
+        blob, off = _packed(attributes, False)
+        ad_blob, ad_off = _packed(associated_data, True)
+        if off.shape[0] != N * self.m_pk.n + 1 or ad_off.shape[0] != N + 1:
+            raise ValueError("attribute size does not match")
         verdict = np.zeros(N, dtype=np.uint8)
         s1 = np.zeros((N, G1), dtype=np.uint64)
         s2 = np.zeros((N, G1), dtype=np.uint64)

@@ -1,0 +1,159 @@
+#!/usr/bin/env python3
+"""tests/bench_configs.py -- MEASUREMENT of the secondary BASELINE.json configs (run under gpurun; not the
+headline bench, which is bench.py):
+
+  cfg3  EL PASSO RP sign-on verification  el_passo_verify_id, 10 attributes (2 hidden), 2^18 requests
+  cfg4  EL PASSO blind issuance           el_passo_provide_id, 20 attributes (2 hidden), 2^18 requests
+        + requester randomize_credential  2^18 credentials
+  cfg5  PS verification, 50 attributes    lanes per GPU as given (the named 2^24 is sharded over 8 GPUs)
+
+Inputs come from the reference's own prover/requester code (tests/workload.py, oracle = test infrastructure):
+`--distinct` proofs/requests are generated and tiled to the full batch.  Every config is timed end to
+end through the public batched call with HOST buffers (H2D + kernels + D2H, wall clock around a blocking call, best of
+`--reps`), verdicts are compared with the reference on the distinct lanes, and the reference's own method is timed on
+all host threads over the same distinct lanes.  One JSON line per config on stdout and in gpurun_out/configs.jsonl.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+from oracle import ref  # noqa: E402
+from tests import workload  # noqa: E402
+
+
+def tile(a, reps):
+    return np.ascontiguousarray(np.tile(a, (reps,) + (1,) * (a.ndim - 1)))
+
+
+def timed(fn, reps):
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        out = fn()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return out, best
+
+
+def emit(rec, fh):
+    line = json.dumps(rec)
+    print(line, flush=True)
+    fh.write(line + "\n")
+    fh.flush()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--lanes", type=int, default=1 << 18)
+    ap.add_argument("--lanes50", type=int, default=1 << 18)
+    ap.add_argument("--distinct", type=int, default=1 << 12)
+    ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--configs", default="3,4,5")
+    ap.add_argument("--window-bits", type=int, default=16)
+    args = ap.parse_args()
+    pkg = ge.load_package()
+    pkg.init([0])
+    threads = ref.hw_threads()
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    fh = open(os.path.join(ROOT, "gpurun_out", "configs.jsonl"), "a")
+    D, N = args.distinct, args.lanes
+    reps_tile = N // D
+    cfgs = args.configs.split(",")
+
+    if "3" in cfgs:
+        for with_id in (True, False):
+            sw = workload.make_signon_workload(10, D, 2, seed=3, with_id=with_id, tamper_every=64)
+            t0 = time.perf_counter()
+            ev = workload.expected_verify_id(sw, nthreads=threads)
+            cpu_s = time.perf_counter() - t0
+            pk = pkg.PSPubKey(sw.key.g, sw.key.gg, sw.key.XX, sw.key.Y, sw.key.YY, window_bits=args.window_bits)
+            proof = {k: tile(v, reps_tile) for k, v in sw.proof.items()}
+            attrs = pkg.pack_attrs(sw.proof_attrs * reps_tile)   # packed outside the timed region
+            ads = pkg.pack_strings(sw.ads * reps_tile)
+            ver = pkg.PSVerifier(pk)
+            ver.el_passo_verify_id({k: v[:D] for k, v in proof.items()}, sw.proof_attrs, sw.ads, sw.service_pt, sw.y, sw.g, sw.h,
+                                   with_id=with_id)  # tables + staging warm-up
+            l0 = pkg.launch_count()
+            got, dt = timed(lambda: ver.el_passo_verify_id(proof, attrs, ads, sw.service_pt, sw.y, sw.g, sw.h, with_id=with_id),
+                            args.reps)
+            assert np.array_equal(got, np.tile(ev, reps_tile)), "verify_id verdict mismatch vs reference"
+            emit({"config": "cfg3 el_passo_verify_id" + ("" if with_id else "_without_id_retrieval"), "n_attrs": 10, "hidden": 2,
+                  "lanes": N, "distinct": D, "metric": "signon_verifications_per_sec", "e2e_value": N / dt, "seconds": dt,
+                  "includes": "H2D + kernels + D2H through psb_verify_id (host buffers)", "gpu_launches": pkg.launch_count() - l0,
+                  "accepted": int(got.sum()), "cpu_reference": {"value": D / cpu_s, "cores": threads, "sample": f"{D} lanes"},
+                  "parity": "verdicts identical to PSVerifier::el_passo_verify_id on all distinct lanes"}, fh)
+            pk.close()
+
+    if "4" in cfgs:
+        iw = workload.make_issuance_workload(20, D, 2, seed=4, tamper_every=64)
+        t0 = time.perf_counter()
+        ev, e1, e2, eser = workload.expected_provide_id(iw, nthreads=threads)
+        cpu_s = time.perf_counter() - t0
+        pk = pkg.PSPubKey(iw.key.g, iw.key.gg, iw.key.XX, iw.key.Y, iw.key.YY, X_secret=iw.key.X, window_bits=args.window_bits)
+        A, c, rs, u = tile(iw.A, reps_tile), tile(iw.c, reps_tile), tile(iw.rs, reps_tile), tile(iw.u, reps_tile)
+        attrs, ads = pkg.pack_attrs(iw.req_attrs * reps_tile), pkg.pack_strings(iw.ads * reps_tile)
+        sg = pkg.PSSigner(pk)
+        sg.el_passo_provide_id(A[:D], c[:D], rs[:D], iw.req_attrs, iw.ads, u[:D])
+        l0 = pkg.launch_count()
+        (v, s1, s2, ser), dt = timed(lambda: sg.el_passo_provide_id(A, c, rs, attrs, ads, u), args.reps)
+        ok = ev.astype(bool)
+        assert np.array_equal(v, np.tile(ev, reps_tile)), "provide_id verdict mismatch vs reference"
+        assert np.array_equal(ser[:D][ok], eser[ok]) and np.array_equal(ser[-D:][ok], eser[ok]), "credential bytes mismatch"
+        emit({"config": "cfg4 el_passo_provide_id", "n_attrs": 20, "hidden": 2, "lanes": N, "distinct": D,
+              "metric": "credentials_issued_per_sec", "e2e_value": N / dt, "seconds": dt, "gpu_launches": pkg.launch_count() - l0,
+              "accepted": int(v.sum()), "cpu_reference": {"value": D / cpu_s, "cores": threads, "sample": f"{D} lanes"},
+              "parity": "verdicts + serialized credentials byte-identical to PSSigner::el_passo_provide_id (same u)"}, fh)
+        # randomize the issued credentials
+        ref.seed(6)
+        t = tile(ref.fr_rand(D), reps_tile)
+        t0 = time.perf_counter()
+        r1, r2, rser = ref.randomize(s1[:D], s2[:D], t[:D], nthreads=threads)
+        cpu_s = time.perf_counter() - t0
+        pkg.PSRequester.randomize_credential(s1[:D], s2[:D], t[:D])
+        l0 = pkg.launch_count()
+        (o1, o2, oser), dt = timed(lambda: pkg.PSRequester.randomize_credential(s1, s2, t, want_serialized=True), args.reps)
+        assert np.array_equal(oser[:D], rser), "randomize bytes mismatch"
+        emit({"config": "cfg4 randomize_credential", "lanes": N, "distinct": D, "metric": "credentials_randomized_per_sec",
+              "e2e_value": N / dt, "seconds": dt, "gpu_launches": pkg.launch_count() - l0,
+              "cpu_reference": {"value": D / cpu_s, "cores": threads, "sample": f"{D} lanes"},
+              "parity": "serialized credentials byte-identical to t*sigma via mcl"}, fh)
+        pk.close()
+
+    if "5" in cfgs:
+        N5 = args.lanes50
+        D5 = min(D, N5)
+        wl = workload.make_verify_workload(n_attrs=50, lanes=D5, seed=2, tamper_every=64)
+        t0 = time.perf_counter()
+        ev = workload.expected_verify(wl, nthreads=threads)
+        cpu_s = time.perf_counter() - t0
+        pk = pkg.PSPubKey(wl.key.g, wl.key.gg, wl.key.XX, wl.key.Y, wl.key.YY, window_bits=args.window_bits)
+        r5 = N5 // D5
+        s1, s2 = tile(wl.sig1, r5), tile(wl.sig2, r5)
+        blob = np.concatenate([wl.blob[:int(wl.off[-1])]] * r5 + [np.zeros(8, dtype=np.uint8)])
+        base = np.arange(r5, dtype=np.uint64).repeat(D5 * 50) * np.uint64(int(wl.off[-1]))
+        off = np.concatenate([np.tile(wl.off[:-1], r5) + base, np.array([int(wl.off[-1]) * r5], dtype=np.uint64)])
+        ver = pkg.PSVerifier(pk)
+        ver.verify(wl.sig1, wl.sig2, (wl.blob, wl.off))
+        pkg.set_profiling(True)
+        l0 = pkg.launch_count()
+        got, dt = timed(lambda: ver.verify(s1, s2, (blob, off)), args.reps)
+        phase = pkg.last_phase_ms(0)
+        pkg.set_profiling(False)
+        assert np.array_equal(got, np.tile(ev, r5)), "verify(50) verdict mismatch vs reference"
+        emit({"config": "cfg5 ps_verify n_attrs=50", "lanes": N5, "distinct": D5, "metric": "ps_verifications_per_sec",
+              "e2e_value": N5 / dt, "seconds": dt, "phase_ms": dict(zip(["msm", "miller", "final_exp"], phase)),
+              "table_bytes": pk.table_bytes, "gpu_launches": pkg.launch_count() - l0,
+              "cpu_reference": {"value": D5 / cpu_s, "cores": threads, "sample": f"{D5} lanes"},
+              "parity": "verdicts identical to PSVerifier::verify on all distinct lanes"}, fh)
+        pk.close()
+
+
+if __name__ == "__main__":
+    main()
