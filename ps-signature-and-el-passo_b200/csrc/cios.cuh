@@ -52,14 +52,17 @@ __device__ PSB_INL void reduce(L12& E, L12& O) {
   PSB_X(PSB_RED_ODD, PSB_ALL(O), m);
   PSB_X(PSB_RED_EVEN, PSB_ALL(E), O[11], m);
 }
-// after the last row (even = E with E[0] == 0, odd = O): T = (E >> 32) + O, canonicalise, store
-__device__ PSB_INL void finish(uint32_t* r, const L12& E, const L12& O) {
-  uint32_t t[12];
+// after the last row (even = E with E[0] == 0, odd = O): T = (E >> 32) + O, canonicalised into registers
+__device__ PSB_INL void finish_rr(uint32_t* t, const L12& E, const L12& O) {
   t[0] = ptx::add_cc(E[1], O[0]);
   PSB_UNROLL
   for (int i = 1; i < 11; i++) t[i] = ptx::addc_cc(E[i + 1], O[i]);
   t[11] = ptx::addc(0, O[11]);
   cond_sub_mod<FpT>(t);
+}
+__device__ PSB_INL void finish(uint32_t* r, const L12& E, const L12& O) {
+  uint32_t t[12];
+  finish_rr(t, E, O);
   uint4* q = reinterpret_cast<uint4*>(r);   // every Fp is 16-byte aligned: three 128-bit stores
   q[0] = make_uint4(t[0], t[1], t[2], t[3]);
   q[1] = make_uint4(t[4], t[5], t[6], t[7]);
@@ -73,11 +76,10 @@ __device__ PSB_INL void load12(L12& d, const uint32_t* s) {
   d[8] = v2.x; d[9] = v2.y; d[10] = v2.z; d[11] = v2.w;
 }
 
-// r = a * b / R mod p
-__device__ PSB_NOINL void mul(uint32_t* r, const uint32_t* a_, const uint32_t* b_) {
-  L12 a, b, X, Y;
-  load12(a, a_);
-  load12(b, b_);
+// register-level cores: operands and result are register arrays (no memory operands), fully inlined into the
+// fused tower functions (tower.cuh) so that sums / differences feed the multiplier without a stack round trip
+__device__ PSB_INL void mul_rr(uint32_t* r, const L12& a, const L12& b) {
+  L12 X, Y;
   first(X, Y, a, b[0]);
   reduce(X, Y);
   PSB_UNROLL
@@ -89,16 +91,11 @@ __device__ PSB_NOINL void mul(uint32_t* r, const uint32_t* a_, const uint32_t* b
       reduce(X, Y);
     }
   }
-  finish(r, Y, X);
+  finish_rr(r, Y, X);
 }
-
 // r = (a b + c d) / R mod p, one reduction per row
-__device__ PSB_NOINL void dot2(uint32_t* r, const uint32_t* a_, const uint32_t* b_, const uint32_t* c_, const uint32_t* d_) {
-  L12 a, b, c, d, X, Y;
-  load12(a, a_);
-  load12(c, c_);
-  load12(b, b_);
-  load12(d, d_);
+__device__ PSB_INL void dot2_rr(uint32_t* r, const L12& a, const L12& b, const L12& c, const L12& d) {
+  L12 X, Y;
   first(X, Y, a, b[0]);
   mac(X, Y, c, d[0]);
   reduce(X, Y);
@@ -113,82 +110,98 @@ __device__ PSB_NOINL void dot2(uint32_t* r, const uint32_t* a_, const uint32_t* 
       reduce(X, Y);
     }
   }
-  finish(r, Y, X);
+  finish_rr(r, Y, X);
 }
 
-// Fp2 product: r = x * y,  x = a + c i,  y = y0 + y1 i
-//   re = a y0 + (p - c) y1,   im = a y1 + c y0       (two accumulator pairs, 4 + 2 chains per row)
-__device__ PSB_NOINL void fp2_mul(uint32_t* r, const uint32_t* x, const uint32_t* y) {
-  L12 a, c, nc, X1, Y1, X2, Y2;
-  load12(a, x);
-  load12(c, x + 12);
-  nc[0] = ptx::sub_cc(FpT::p(0), c[0]);
+// ---- rolled cores (EXPERIMENT, not on the product path) ------------------------------------------------
+// Rolled loops keep the multiplicands in registers and stream the multiplier limbs from memory, two rows per
+// iteration.  Measured (r1f): the per-row shift of the accumulator arrays is free register renaming in unrolled code
+// but costs ~24 IMAD.MOV per array per iteration at the loop back edge (+45 % instructions) -> kept for reference only.
+__device__ PSB_INL void zero12(L12& x) {
   PSB_UNROLL
-  for (int i = 1; i < 11; i++) nc[i] = ptx::subc_cc(FpT::p(i), c[i]);
-  nc[11] = ptx::subc(FpT::p(11), c[11]);   // p - c in (0, p]: fine as a multiplicand
-  {
-    const uint32_t y0 = y[0], y1 = y[12];
-    first(X1, Y1, a, y0); mac(X1, Y1, nc, y1); reduce(X1, Y1);
-    first(X2, Y2, a, y1); mac(X2, Y2, c, y0); reduce(X2, Y2);
+  for (int i = 0; i < 12; i++) x[i] = 0;
+}
+__device__ PSB_INL uint2 ld2(const uint32_t* p) { return *reinterpret_cast<const uint2*>(p); }   // limb pairs are 8-byte aligned
+
+// two independent products side by side:  r1 = a1 * b1,  r2 = a2 * b2   (b1, b2 in memory)
+__device__ PSB_INL void mul2_loop(uint32_t* r1, uint32_t* r2, const L12& a1, const uint32_t* b1, const L12& a2, const uint32_t* b2) {
+  L12 X1, Y1, X2, Y2;
+  zero12(X1); zero12(Y1); zero12(X2); zero12(Y2);
+#pragma unroll 1
+  for (int i = 0; i < 12; i += 2) {
+    const uint2 p = ld2(b1 + i), q = ld2(b2 + i);
+    mac_shift(X1, Y1, a1, p.x); reduce(X1, Y1);
+    mac_shift(X2, Y2, a2, q.x); reduce(X2, Y2);
+    mac_shift(Y1, X1, a1, p.y); reduce(Y1, X1);
+    mac_shift(Y2, X2, a2, q.y); reduce(Y2, X2);
   }
-  PSB_UNROLL
-  for (int i = 1; i < 12; i += 2) {
-    {
-      const uint32_t y0 = y[i], y1 = y[12 + i];
-      mac_shift(Y1, X1, a, y0); mac(Y1, X1, nc, y1); reduce(Y1, X1);
-      mac_shift(Y2, X2, a, y1); mac(Y2, X2, c, y0); reduce(Y2, X2);
-    }
-    if (i + 1 < 12) {
-      const uint32_t y0 = y[i + 1], y1 = y[13 + i];
-      mac_shift(X1, Y1, a, y0); mac(X1, Y1, nc, y1); reduce(X1, Y1);
-      mac_shift(X2, Y2, a, y1); mac(X2, Y2, c, y0); reduce(X2, Y2);
-    }
+  finish_rr(r1, Y1, X1);
+  finish_rr(r2, Y2, X2);
+}
+// Fp2 product with multiplicands xa, xb, nxb = -xb (mod p, any representative < 2p) in registers and the
+// multiplier y = (ya, yb) in memory:  re = xa ya + nxb yb,  im = xa yb + xb ya   (four carry chains per row)
+__device__ PSB_INL void fp2mul_loop(uint32_t* re, uint32_t* im, const L12& xa, const L12& xb, const L12& nxb,
+                                    const uint32_t* ya, const uint32_t* yb) {
+  L12 X1, Y1, X2, Y2;
+  zero12(X1); zero12(Y1); zero12(X2); zero12(Y2);
+#pragma unroll 1
+  for (int i = 0; i < 12; i += 2) {
+    const uint2 p = ld2(ya + i), q = ld2(yb + i);
+    mac_shift(X1, Y1, xa, p.x); mac(X1, Y1, nxb, q.x); reduce(X1, Y1);
+    mac_shift(X2, Y2, xa, q.x); mac(X2, Y2, xb, p.x); reduce(X2, Y2);
+    mac_shift(Y1, X1, xa, p.y); mac(Y1, X1, nxb, q.y); reduce(Y1, X1);
+    mac_shift(Y2, X2, xa, q.y); mac(Y2, X2, xb, p.y); reduce(Y2, X2);
   }
-  finish(r, Y1, X1);
-  finish(r + 12, Y2, X2);
+  finish_rr(re, Y1, X1);
+  finish_rr(im, Y2, X2);
+}
+// single product / two-product dot with streamed multipliers
+__device__ PSB_INL void mul_loop(uint32_t* r, const L12& a, const uint32_t* b) {
+  L12 X, Y;
+  zero12(X); zero12(Y);
+#pragma unroll 1
+  for (int i = 0; i < 12; i += 2) {
+    const uint2 p = ld2(b + i);
+    mac_shift(X, Y, a, p.x); reduce(X, Y);
+    mac_shift(Y, X, a, p.y); reduce(Y, X);
+  }
+  finish_rr(r, Y, X);
+}
+__device__ PSB_INL void dot2_loop(uint32_t* r, const L12& a, const uint32_t* b, const L12& c, const uint32_t* d) {
+  L12 X, Y;
+  zero12(X); zero12(Y);
+#pragma unroll 1
+  for (int i = 0; i < 12; i += 2) {
+    const uint2 p = ld2(b + i), q = ld2(d + i);
+    mac_shift(X, Y, a, p.x); mac(X, Y, c, q.x); reduce(X, Y);
+    mac_shift(Y, X, a, p.y); mac(Y, X, c, q.y); reduce(Y, X);
+  }
+  finish_rr(r, Y, X);
 }
 
-// Fp2 square: (a + b i)^2 = (a + b)(a - b) + (2a) b i    (multiplicands a+b, 2a are unreduced, < 2p)
-__device__ PSB_NOINL void fp2_sqr(uint32_t* r, const uint32_t* x) {
-  L12 a, b, s, t, d, X1, Y1, X2, Y2;
-  load12(a, x);
-  load12(b, x + 12);
-  add_n<12>(s, a, b);
-  add_n<12>(t, a, a);
-  mod_sub<FpT>(d, a, b);
-  first(X1, Y1, s, d[0]); reduce(X1, Y1);
-  first(X2, Y2, t, b[0]); reduce(X2, Y2);
-  PSB_UNROLL
-  for (int i = 1; i < 12; i += 2) {
-    mac_shift(Y1, X1, s, d[i]); reduce(Y1, X1);
-    mac_shift(Y2, X2, t, b[i]); reduce(Y2, X2);
-    if (i + 1 < 12) {
-      mac_shift(X1, Y1, s, d[i + 1]); reduce(X1, Y1);
-      mac_shift(X2, Y2, t, b[i + 1]); reduce(X2, Y2);
-    }
-  }
-  finish(r, Y1, X1);
-  finish(r + 12, Y2, X2);
+__device__ PSB_INL void store12(uint32_t* r, const L12& t) {
+  uint4* q = reinterpret_cast<uint4*>(r);   // every Fp is 16-byte aligned: three 128-bit stores
+  q[0] = make_uint4(t[0], t[1], t[2], t[3]);
+  q[1] = make_uint4(t[4], t[5], t[6], t[7]);
+  q[2] = make_uint4(t[8], t[9], t[10], t[11]);
 }
-
-// Fp2 * Fp: (a + c i) k
-__device__ PSB_NOINL void fp2_mul_fp(uint32_t* r, const uint32_t* x, const uint32_t* k) {
-  L12 a, c, X1, Y1, X2, Y2;
-  load12(a, x);
-  load12(c, x + 12);
-  first(X1, Y1, a, k[0]); reduce(X1, Y1);
-  first(X2, Y2, c, k[0]); reduce(X2, Y2);
-  PSB_UNROLL
-  for (int i = 1; i < 12; i += 2) {
-    mac_shift(Y1, X1, a, k[i]); reduce(Y1, X1);
-    mac_shift(Y2, X2, c, k[i]); reduce(Y2, X2);
-    if (i + 1 < 12) {
-      mac_shift(X1, Y1, a, k[i + 1]); reduce(X1, Y1);
-      mac_shift(X2, Y2, c, k[i + 1]); reduce(X2, Y2);
-    }
-  }
-  finish(r, Y1, X1);
-  finish(r + 12, Y2, X2);
+// r = a * b / R mod p  (memory operands; r may alias a or b)
+__device__ PSB_NOINL void mul(uint32_t* r, const uint32_t* a_, const uint32_t* b_) {
+  L12 a, b, t;
+  load12(a, a_);
+  load12(b, b_);
+  mul_rr(t, a, b);
+  store12(r, t);
+}
+// r = (a b + c d) / R mod p  (memory operands)
+__device__ PSB_NOINL void dot2(uint32_t* r, const uint32_t* a_, const uint32_t* b_, const uint32_t* c_, const uint32_t* d_) {
+  L12 a, b, c, d, t;
+  load12(a, a_);
+  load12(c, c_);
+  load12(b, b_);
+  load12(d, d_);
+  dot2_rr(t, a, b, c, d);
+  store12(r, t);
 }
 
 }  // namespace cios

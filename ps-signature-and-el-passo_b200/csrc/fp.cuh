@@ -418,6 +418,35 @@ PSB_HD inline void fp_dot2(Fp& r, const Fp& a, const Fp& b, const Fp& c, const F
   FpW t, u; fp_mulw(t, a, b); fp_mulw(u, c, d); fpw_add_nr(t, t, u); fp_redc(r, t);
 }
 #endif
+// register-resident variants for the fused tower functions: operands are LOCAL Fp values that never touch memory
+// (loaded once with fp_ld, stored once with fp_st); everything inlines.
+#ifdef __CUDA_ARCH__
+__device__ PSB_INL void fp_mul_rr(Fp& r, const Fp& a, const Fp& b) { cios::mul_rr(r.v, a.v, b.v); }
+__device__ PSB_INL void fp_dot2_rr(Fp& r, const Fp& a, const Fp& b, const Fp& c, const Fp& d) { cios::dot2_rr(r.v, a.v, b.v, c.v, d.v); }
+#else
+PSB_HD PSB_INL void fp_mul_rr(Fp& r, const Fp& a, const Fp& b) { FpW t; mulw_n<12>(t.v, a.v, b.v); redc_n<FpT>(r.v, t.v); }
+PSB_HD PSB_INL void fp_dot2_rr(Fp& r, const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+  FpW t, u; mulw_n<12>(t.v, a.v, b.v); mulw_n<12>(u.v, c.v, d.v); add_n<24>(t.v, t.v, u.v); redc_n<FpT>(r.v, t.v);
+}
+#endif
+PSB_HD PSB_INL void fp_add_rr(Fp& r, const Fp& a, const Fp& b) { mod_add<FpT>(r.v, a.v, b.v); }
+PSB_HD PSB_INL void fp_sub_rr(Fp& r, const Fp& a, const Fp& b) { mod_sub<FpT>(r.v, a.v, b.v); }
+PSB_HD PSB_INL void fp_dbl_rr(Fp& r, const Fp& a) { mod_add<FpT>(r.v, a.v, a.v); }
+PSB_HD PSB_INL void fp_addnr_rr(Fp& r, const Fp& a, const Fp& b) { add_n<12>(r.v, a.v, b.v); }   // < 2p: multiplicand only
+// p - a for a in [0, p]: in (0, p] (NOT canonical for a = 0) -- multiplicand only
+PSB_HD PSB_INL void fp_pminus_rr(Fp& r, const Fp& a) {
+#ifdef __CUDA_ARCH__
+  r.v[0] = ptx::sub_cc(FpT::p(0), a.v[0]);
+  PSB_UNROLL
+  for (int i = 1; i < 11; i++) r.v[i] = ptx::subc_cc(FpT::p(i), a.v[i]);
+  r.v[11] = ptx::subc(FpT::p(11), a.v[11]);
+#else
+  int64_t c = 0;
+  for (int i = 0; i < 12; i++) { c += (int64_t)FpT::p(i) - a.v[i]; r.v[i] = (uint32_t)c; c >>= 32; }
+#endif
+}
+PSB_HD PSB_INL void fp_get(Fp& d, const Fp& mem) { fp_ld(d.v, mem); }
+PSB_HD PSB_INL void fp_put(Fp& mem, const Fp& s) { fp_st(mem, s.v); }
 PSB_HD PSB_INL void fp_mul_inl(Fp& r, const Fp& a, const Fp& b) { fp_mul(r, a, b); }
 PSB_HD PSB_INL void fp_sqr_inl(Fp& r, const Fp& a) { fp_sqr(r, a); }
 

@@ -22,10 +22,50 @@ struct Fp6 { Fp2 a, b, c; };
 struct Fp12 { Fp6 a, b; };
 
 // ---- Fp2 ------------------------------------------------------------------------------------------
-PSB_HD PSB_NOINL void fp2_add(Fp2& r, const Fp2& x, const Fp2& y) { fp_add(r.a, x.a, y.a); fp_add(r.b, x.b, y.b); }
-PSB_HD PSB_NOINL void fp2_sub(Fp2& r, const Fp2& x, const Fp2& y) { fp_sub(r.a, x.a, y.a); fp_sub(r.b, x.b, y.b); }
-PSB_HD PSB_NOINL void fp2_neg(Fp2& r, const Fp2& x) { fp_neg(r.a, x.a); fp_neg(r.b, x.b); }
-PSB_HD PSB_NOINL void fp2_dbl(Fp2& r, const Fp2& x) { fp_dbl(r.a, x.a); fp_dbl(r.b, x.b); }
+// additive ops over `cnt` consecutive Fp components (2 = Fp2, 6 = Fp6, 12 = Fp12): ONE rolled loop each, so an
+// Fp6 addition is one call and a few dozen instructions of code (instruction-cache budget, see the fused kernels below)
+PSB_HD PSB_NOINL void fpn_add(Fp* r, const Fp* x, const Fp* y, int cnt) {
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+  for (int k = 0; k < cnt; k++) fp_add(r[k], x[k], y[k]);
+}
+PSB_HD PSB_NOINL void fpn_sub(Fp* r, const Fp* x, const Fp* y, int cnt) {
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+  for (int k = 0; k < cnt; k++) fp_sub(r[k], x[k], y[k]);
+}
+PSB_HD PSB_NOINL void fpn_neg(Fp* r, const Fp* x, int cnt) {
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+  for (int k = 0; k < cnt; k++) fp_neg(r[k], x[k]);
+}
+PSB_HD PSB_NOINL void fpn_dbl(Fp* r, const Fp* x, int cnt) {
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+  for (int k = 0; k < cnt; k++) fp_dbl(r[k], x[k]);
+}
+// r = a - b - c over cnt components
+PSB_HD PSB_NOINL void fpn_sub2(Fp* r, const Fp* a, const Fp* b, const Fp* c, int cnt) {
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+  for (int k = 0; k < cnt; k++) {
+    uint32_t x[12], y[12];
+    fp_ld(x, a[k]); fp_ld(y, b[k]);
+    mod_sub<FpT>(x, x, y);
+    fp_ld(y, c[k]);
+    mod_sub<FpT>(x, x, y);
+    fp_st(r[k], x);
+  }
+}
+PSB_HD PSB_INL void fp2_add(Fp2& r, const Fp2& x, const Fp2& y) { fpn_add(&r.a, &x.a, &y.a, 2); }
+PSB_HD PSB_INL void fp2_sub(Fp2& r, const Fp2& x, const Fp2& y) { fpn_sub(&r.a, &x.a, &y.a, 2); }
+PSB_HD PSB_INL void fp2_neg(Fp2& r, const Fp2& x) { fpn_neg(&r.a, &x.a, 2); }
+PSB_HD PSB_INL void fp2_dbl(Fp2& r, const Fp2& x) { fpn_dbl(&r.a, &x.a, 2); }
 PSB_HD PSB_INL void fp2_conj(Fp2& r, const Fp2& x) { r.a = x.a; fp_neg(r.b, x.b); }
 PSB_HD PSB_INL void fp2_set_zero(Fp2& r) { fp_set_zero(r.a); fp_set_zero(r.b); }
 PSB_HD PSB_INL void fp2_set_one(Fp2& r) { fp_set_one(r.a); fp_set_zero(r.b); }
@@ -39,39 +79,147 @@ PSB_HD PSB_NOINL void fp2_mul_xi(Fp2& r, const Fp2& x) {
   fp_add(r.b, x.a, x.b);
   r.a = t;
 }
-PSB_HD PSB_INL void fp2_mul_fp(Fp2& r, const Fp2& x, const Fp& k) {
-#if defined(__CUDA_ARCH__) && defined(PSB_FP2_FUSED)
-  cios::fp2_mul_fp(r.a.v, x.a.v, k.v);   // Fp2 is two contiguous Fp: 24 limbs
+// ---- fused Fp2 kernels ---------------------------------------------------------------------------------
+// Two constraints shape these (both measured, profiles/r1d, r1e):
+//  * the additive glue of the tower as separate calls (each a stack round trip) took ~30 % of the instructions but
+//    ~58 % of the stall samples of the final exponentiation -> sums / differences are formed in registers next to
+//    the multiplier, and multi-term combinations are single functions;
+//  * fully unrolled fused functions (13-20 KB of code each) overflow the SM's instruction caches (50 % of the stall
+//    samples became instruction-fetch) -> multipliers are ROLLED loops that keep the multiplicands in registers and
+//    stream the multiplier limbs from memory (cios.cuh), and component-wise combinations loop over the components.
+#ifdef __CUDA_ARCH__
+#define PSB_ROLL _Pragma("unroll 1")
 #else
-  fp_mul(r.a, x.a, k); fp_mul(r.b, x.b, k);
+#define PSB_ROLL
 #endif
+PSB_HD PSB_INL Fp* fp2_comp(Fp2& x, int k) { return &x.a + k; }
+PSB_HD PSB_INL const Fp* fp2_comp(const Fp2& x, int k) { return &x.a + k; }
+
+// 2p - a for a in [0, 2p): a representative of -a in (0, 2p] (multiplicand only)
+PSB_HD PSB_INL void fp_2pminus_rr(Fp& r, const Fp& a) {
+  Fp t;
+  fp_pminus_rr(t, a);                 // p - a in (-p, p], two's complement when negative
+  Fp pp;
+  PSB_UNROLL
+  for (int i = 0; i < 12; i++) pp.v[i] = FpT::p(i);
+  add_n<12>(r.v, t.v, pp.v);          // + p (carry out cancels the wrap)
 }
 
-// (a0 + a1 i)(b0 + b1 i) = (a0 b0 - a1 b1) + (a0 b1 + a1 b0) i : two fused two-product passes
-// (value of mcl Fp2::mul, fp_tower.hpp:528-534)
-#if defined(__CUDA_ARCH__) && defined(PSB_FP2_FUSED)
-// two accumulator pairs side by side: more ILP but ~160 registers -> lower occupancy; measured
-// slower on B200 (750k vs 832k verif/s, r1), kept for experiments only
-__device__ PSB_INL void fp2_mul(Fp2& r, const Fp2& x, const Fp2& y) { cios::fp2_mul(r.a.v, x.a.v, y.a.v); }
-__device__ PSB_INL void fp2_sqr(Fp2& r, const Fp2& x) { cios::fp2_sqr(r.a.v, x.a.v); }
+#ifdef __CUDA_ARCH__
+// Two multiplier ENGINES carry every Fp2 product of the tower (instruction-cache budget: each engine is one fully
+// unrolled register-resident body; the variants differ only in a short operand-preparation prologue selected by
+// warp-uniform null-pointer tests):
+//   engine A  (re, im) = (xa ya + xb (p - yb), xa yb + xb ya)   x = x1 [+ x2],  y = y1 [+ y2]      fp2_mul, fp2_mul_sum
+//   engine B  (re, im) = (m1 n1, m2 n2)                         squares (x = x1 [+ x2]) and Fp2 * Fp  fp2_sqr, fp2_sqr_sum, fp2_mul_fp
+__device__ PSB_NOINL void fp2_engine_a(Fp2& r, const Fp2* x1, const Fp2* x2, const Fp2* y1, const Fp2* y2) {
+  Fp xa, xb, ya, yb, u, nb, re, im;
+  fp_get(xa, x1->a); fp_get(xb, x1->b); fp_get(ya, y1->a); fp_get(yb, y1->b);
+  if (x2) {
+    fp_get(u, x2->a); fp_addnr_rr(xa, xa, u);     // multiplicand side: unreduced (< 2p)
+    fp_get(u, x2->b); fp_addnr_rr(xb, xb, u);
+    fp_get(u, y2->a); fp_add_rr(ya, ya, u);       // multiplier side: canonical
+    fp_get(u, y2->b); fp_add_rr(yb, yb, u);
+  }
+  fp_pminus_rr(nb, yb);
+  fp_dot2_rr(re, xa, ya, xb, nb);
+  fp_dot2_rr(im, xa, yb, xb, ya);
+  fp_put(r.a, re); fp_put(r.b, im);
+}
+__device__ PSB_NOINL void fp2_engine_b(Fp2& r, const Fp2* x1, const Fp2* x2, const Fp* k) {
+  Fp m1, n1, m2, n2, u, re, im;
+  fp_get(m1, x1->a); fp_get(m2, x1->b);
+  if (k) {                                         // (a + b i) k
+    fp_get(n1, *k);
+    n2 = n1;
+  } else {                                         // (a + b i)^2 = (a + b)(a - b) + (2a) b i
+    if (x2) {
+      fp_get(u, x2->a); fp_add_rr(m1, m1, u);
+      fp_get(u, x2->b); fp_add_rr(m2, m2, u);
+    }
+    n2 = m2;                                       // b
+    fp_sub_rr(n1, m1, m2);                         // a - b
+    fp_addnr_rr(m2, m1, m1);                       // 2a   (< 2p: multiplicand only)
+    fp_addnr_rr(m1, m1, n2);                       // a + b
+  }
+  fp_mul_rr(re, m1, n1);
+  fp_mul_rr(im, m2, n2);
+  fp_put(r.a, re); fp_put(r.b, im);
+}
+__device__ PSB_INL void fp2_mul(Fp2& r, const Fp2& x, const Fp2& y) { fp2_engine_a(r, &x, nullptr, &y, nullptr); }
+__device__ PSB_INL void fp2_mul_sum(Fp2& r, const Fp2& x1, const Fp2& x2, const Fp2& y1, const Fp2& y2) { fp2_engine_a(r, &x1, &x2, &y1, &y2); }
+__device__ PSB_INL void fp2_sqr(Fp2& r, const Fp2& x) { fp2_engine_b(r, &x, nullptr, nullptr); }
+__device__ PSB_INL void fp2_sqr_sum(Fp2& r, const Fp2& x1, const Fp2& x2) { fp2_engine_b(r, &x1, &x2, nullptr); }
+__device__ PSB_INL void fp2_mul_fp(Fp2& r, const Fp2& x, const Fp& k) { fp2_engine_b(r, &x, nullptr, &k); }
 #else
-PSB_HD PSB_NOINL void fp2_mul(Fp2& r, const Fp2& x, const Fp2& y) {
+// host build (tests/hostsim): same values through the generic code
+PSB_HD inline void fp2_mul(Fp2& r, const Fp2& x, const Fp2& y) {
   Fp nb, re;
   fp_neg(nb, y.b);
   fp_dot2(re, x.a, y.a, x.b, nb);
   fp_dot2(r.b, x.a, y.b, x.b, y.a);
   r.a = re;
 }
-// (a + b i)^2 = (a + b)(a - b) + 2ab i       (fp_tower.hpp:539-550)
-PSB_HD PSB_NOINL void fp2_sqr(Fp2& r, const Fp2& x) {
+PSB_HD inline void fp2_sqr(Fp2& r, const Fp2& x) {
   Fp s, d, t;
-  fp_add_nr(s, x.a, x.b);  // < 2p: fine as a Montgomery multiplicand (result still < 2p before the final subtraction)
+  fp_add_nr(s, x.a, x.b);
   fp_sub(d, x.a, x.b);
   fp_add_nr(t, x.a, x.a);
   fp_mul(r.b, t, x.b);
   fp_mul(r.a, s, d);
 }
+PSB_HD inline void fp2_mul_sum(Fp2& r, const Fp2& x1, const Fp2& x2, const Fp2& y1, const Fp2& y2) {
+  Fp2 s, t;
+  fp2_add(s, x1, x2); fp2_add(t, y1, y2);
+  fp2_mul(r, s, t);
+}
+PSB_HD inline void fp2_sqr_sum(Fp2& r, const Fp2& x1, const Fp2& x2) {
+  Fp2 s;
+  fp2_add(s, x1, x2);
+  fp2_sqr(r, s);
+}
+PSB_HD inline void fp2_mul_fp(Fp2& r, const Fp2& x, const Fp& k) { fp_mul(r.a, x.a, k); fp_mul(r.b, x.b, k); }
 #endif
+
+// component-wise combinations: one call, a rolled loop over the two components
+PSB_HD PSB_INL void fp2_sub2(Fp2& r, const Fp2& a, const Fp2& b, const Fp2& c) { fpn_sub2(&r.a, &a.a, &b.a, &c.a, 2); }   // a - b - c
+// r = a - b - c + d
+PSB_HD PSB_NOINL void fp2_sub2_add(Fp2& r, const Fp2& a, const Fp2& b, const Fp2& c, const Fp2& d) {
+  PSB_ROLL
+  for (int k = 0; k < 2; k++) {
+    Fp x, y;
+    fp_get(x, *fp2_comp(a, k)); fp_get(y, *fp2_comp(b, k));
+    fp_sub_rr(x, x, y);
+    fp_get(y, *fp2_comp(c, k));
+    fp_sub_rr(x, x, y);
+    fp_get(y, *fp2_comp(d, k));
+    fp_add_rr(x, x, y);
+    fp_put(*fp2_comp(r, k), x);
+  }
+}
+// r = 3a - 2b (minus = true) or 3a + 2b: the output combination of the Granger-Scott squaring
+PSB_HD PSB_NOINL void fp2_3a2b(Fp2& r, const Fp2& a, const Fp2& b, bool minus) {
+  PSB_ROLL
+  for (int k = 0; k < 2; k++) {
+    Fp x, y, u;
+    fp_get(x, *fp2_comp(a, k)); fp_get(y, *fp2_comp(b, k));
+    if (minus) fp_sub_rr(u, x, y); else fp_add_rr(u, x, y);
+    fp_dbl_rr(u, u);
+    fp_add_rr(u, u, x);
+    fp_put(*fp2_comp(r, k), u);
+  }
+}
+// r = b + xi a (minus = false) or b - xi a;   xi a = (a.a - a.b) + (a.a + a.b) i
+PSB_HD PSB_NOINL void fp2_xi_addsub(Fp2& r, const Fp2& a, const Fp2& b, bool minus) {
+  Fp x, y, w0, w1;
+  fp_get(x, a.a); fp_get(y, a.b);
+  fp_sub_rr(w0, x, y);
+  fp_add_rr(w1, x, y);
+  fp_get(x, b.a); fp_get(y, b.b);
+  if (minus) { fp_sub_rr(x, x, w0); fp_sub_rr(y, y, w1); } else { fp_add_rr(x, x, w0); fp_add_rr(y, y, w1); }
+  fp_put(r.a, x); fp_put(r.b, y);
+}
+PSB_HD PSB_INL void fp2_xi_add(Fp2& r, const Fp2& a, const Fp2& b) { fp2_xi_addsub(r, a, b, false); }   // xi a + b
+
 // x^-1 = conj(x) / (a^2 + b^2)   (fp_tower.hpp:597-611)
 PSB_HD PSB_NOINL void fp2_inv(Fp2& r, const Fp2& x) {
   Fp n;
@@ -83,10 +231,10 @@ PSB_HD PSB_NOINL void fp2_inv(Fp2& r, const Fp2& x) {
 }
 
 // ---- Fp6 ------------------------------------------------------------------------------------------
-PSB_HD PSB_INL void fp6_add(Fp6& r, const Fp6& x, const Fp6& y) { fp2_add(r.a, x.a, y.a); fp2_add(r.b, x.b, y.b); fp2_add(r.c, x.c, y.c); }
-PSB_HD PSB_INL void fp6_sub(Fp6& r, const Fp6& x, const Fp6& y) { fp2_sub(r.a, x.a, y.a); fp2_sub(r.b, x.b, y.b); fp2_sub(r.c, x.c, y.c); }
-PSB_HD PSB_INL void fp6_neg(Fp6& r, const Fp6& x) { fp2_neg(r.a, x.a); fp2_neg(r.b, x.b); fp2_neg(r.c, x.c); }
-PSB_HD PSB_INL void fp6_dbl(Fp6& r, const Fp6& x) { fp2_dbl(r.a, x.a); fp2_dbl(r.b, x.b); fp2_dbl(r.c, x.c); }
+PSB_HD PSB_INL void fp6_add(Fp6& r, const Fp6& x, const Fp6& y) { fpn_add(&r.a.a, &x.a.a, &y.a.a, 6); }
+PSB_HD PSB_INL void fp6_sub(Fp6& r, const Fp6& x, const Fp6& y) { fpn_sub(&r.a.a, &x.a.a, &y.a.a, 6); }
+PSB_HD PSB_INL void fp6_neg(Fp6& r, const Fp6& x) { fpn_neg(&r.a.a, &x.a.a, 6); }
+PSB_HD PSB_INL void fp6_dbl(Fp6& r, const Fp6& x) { fpn_dbl(&r.a.a, &x.a.a, 6); }
 // (a + b v + c v^2) v = xi c + a v + b v^2
 PSB_HD PSB_INL void fp6_mul_v(Fp6& r, const Fp6& x) {
   Fp2 t;
@@ -98,45 +246,31 @@ PSB_HD PSB_INL void fp6_mul_v(Fp6& r, const Fp6& x) {
 
 // z = x*y: Karatsuba over v, 6 Fp2 products (value of mcl Fp6::mul, fp_tower.hpp:978-1022)
 PSB_HD PSB_NOINL void fp6_mul(Fp6& z, const Fp6& x, const Fp6& y) {
-  Fp2 v0, v1, v2, s, t, c0, c1;
+  Fp2 v0, v1, v2, m0, m1, m2;
   fp2_mul(v0, x.a, y.a);
   fp2_mul(v1, x.b, y.b);
   fp2_mul(v2, x.c, y.c);
-  // c0 = v0 + xi((b+c)(b'+c') - v1 - v2)
-  fp2_add(s, x.b, x.c); fp2_add(t, y.b, y.c);
-  fp2_mul(c0, s, t);
-  fp2_sub(c0, c0, v1); fp2_sub(c0, c0, v2);
-  fp2_mul_xi(c0, c0);
-  fp2_add(c0, c0, v0);
-  // c1 = (a+b)(a'+b') - v0 - v1 + xi v2
-  fp2_add(s, x.a, x.b); fp2_add(t, y.a, y.b);
-  fp2_mul(c1, s, t);
-  fp2_sub(c1, c1, v0); fp2_sub(c1, c1, v1);
-  fp2_mul_xi(s, v2);
-  fp2_add(c1, c1, s);
-  // c2 = (a+c)(a'+c') - v0 - v2 + v1
-  fp2_add(s, x.a, x.c); fp2_add(t, y.a, y.c);
-  fp2_mul(s, s, t);
-  fp2_sub(s, s, v0); fp2_sub(s, s, v2);
-  fp2_add(z.c, s, v1);
-  z.a = c0;
-  z.b = c1;
+  fp2_mul_sum(m0, x.b, x.c, y.b, y.c);
+  fp2_mul_sum(m1, x.a, x.b, y.a, y.b);
+  fp2_mul_sum(m2, x.a, x.c, y.a, y.c);
+  fp2_sub2(m0, m0, v1, v2);
+  fp2_xi_add(z.a, m0, v0);                // v0 + xi((b+c)(b'+c') - v1 - v2)
+  fp2_sub2(m1, m1, v0, v1);
+  fp2_xi_add(z.b, v2, m1);                // (a+b)(a'+b') - v0 - v1 + xi v2
+  fp2_sub2_add(z.c, m2, v0, v2, v1);      // (a+c)(a'+c') - v0 - v2 + v1
 }
 
 // x * (a0 + a1 v), 5 Fp2 products (sparse operand; cf. mcl Fp6mul_01, bn.hpp:1298-1320)
 PSB_HD PSB_NOINL void fp6_mul_01(Fp6& z, const Fp6& x, const Fp2& a0, const Fp2& a1) {
-  Fp2 v0, v1, s, t, r1;
+  Fp2 v0, v1, m, s, t;
   fp2_mul(v0, x.a, a0);
   fp2_mul(v1, x.b, a1);
-  fp2_add(s, x.a, x.b); fp2_add(t, a0, a1);
-  fp2_mul(r1, s, t);
-  fp2_sub(r1, r1, v0); fp2_sub(r1, r1, v1);     // x0 a1 + x1 a0
+  fp2_mul_sum(m, x.a, x.b, a0, a1);
   fp2_mul(s, x.c, a1);
-  fp2_mul_xi(s, s);
   fp2_mul(t, x.c, a0);
-  fp2_add(z.a, s, v0);                          // x0 a0 + xi x2 a1
+  fp2_xi_add(z.a, s, v0);                       // x0 a0 + xi x2 a1
   fp2_add(z.c, t, v1);                          // x1 a1 + x2 a0
-  z.b = r1;
+  fp2_sub2(z.b, m, v0, v1);                     // x0 a1 + x1 a0
 }
 // x * (b1 v), 3 Fp2 products
 PSB_HD PSB_NOINL void fp6_mul_1(Fp6& z, const Fp6& x, const Fp2& b1) {
@@ -175,6 +309,17 @@ PSB_HD PSB_INL bool fp12_is_one(const Fp12& x) {
   return o == 0;
 }
 
+// r = a + v b  (Fp6)
+PSB_HD PSB_INL void fp6_add_mulv(Fp6& r, const Fp6& a, const Fp6& b) {
+  Fp2 t;
+  fp2_xi_add(t, b.c, a.a);
+  fp2_add(r.c, a.c, b.b);
+  fp2_add(r.b, a.b, b.a);
+  r.a = t;
+}
+// r = a - b - c  (Fp6)
+PSB_HD PSB_INL void fp6_sub2(Fp6& r, const Fp6& a, const Fp6& b, const Fp6& c) { fpn_sub2(&r.a.a, &a.a.a, &b.a.a, &c.a.a, 6); }
+
 // z = x*y: Karatsuba over w (value of mcl Fp12::mul, fp_tower.hpp:1131-1160)
 PSB_HD PSB_NOINL void fp12_mul(Fp12& z, const Fp12& x, const Fp12& y) {
   Fp6 t0, t1, s, t;
@@ -183,23 +328,22 @@ PSB_HD PSB_NOINL void fp12_mul(Fp12& z, const Fp12& x, const Fp12& y) {
   fp6_add(s, x.a, x.b);
   fp6_add(t, y.a, y.b);
   fp6_mul(s, s, t);
-  fp6_sub(s, s, t0);
-  fp6_sub(z.b, s, t1);
-  fp6_mul_v(t1, t1);
-  fp6_add(z.a, t0, t1);
+  fp6_sub2(z.b, s, t0, t1);
+  fp6_add_mulv(z.a, t0, t1);
 }
 
 // z = x^2 (complex squaring: 2 Fp6 products; cf. fp_tower.hpp:1166-1178)
 PSB_HD PSB_NOINL void fp12_sqr(Fp12& z, const Fp12& x) {
   Fp6 t0, t1, t2;
   fp6_add(t0, x.a, x.b);
-  fp6_mul_v(t1, x.b);
-  fp6_add(t1, t1, x.a);
+  fp6_add_mulv(t1, x.a, x.b);
   fp6_mul(t2, x.a, x.b);   // ab
   fp6_mul(t0, t0, t1);     // (a+b)(a+vb) = a^2 + v b^2 + ab + v ab
-  fp6_sub(t0, t0, t2);
-  fp6_mul_v(t1, t2);
-  fp6_sub(z.a, t0, t1);
+  // z.a = t0 - t2 - v t2
+  fp2_sub(t0.a, t0.a, t2.a);
+  fp2_xi_addsub(z.a.a, t2.c, t0.a, true);
+  fp2_sub2(z.a.b, t0.b, t2.b, t2.a);
+  fp2_sub2(z.a.c, t0.c, t2.c, t2.b);
   fp6_dbl(z.b, t2);
 }
 
@@ -213,10 +357,8 @@ PSB_HD PSB_NOINL void fp12_mul_line(Fp12& f, const Fp2& c0, const Fp2& c2, const
   fp6_add(s, f.a, f.b);
   fp2_add(c23, c2, c3);
   fp6_mul_01(s, s, c0, c23);
-  fp6_sub(s, s, t0);
-  fp6_sub(f.b, s, t1);
-  fp6_mul_v(t1, t1);
-  fp6_add(f.a, t0, t1);
+  fp6_sub2(f.b, s, t0, t1);
+  fp6_add_mulv(f.a, t0, t1);
 }
 
 // x^-1 = (a - b w)/(a^2 - v b^2)   (fp_tower.hpp:1183-1198)
@@ -253,32 +395,32 @@ PSB_HD PSB_NOINL void fp12_frobenius(Fp12& r, const Fp12& x, int j) {
   }
 }
 
-// Granger-Scott squaring in the cyclotomic subgroup (cf. mcl fasterSqr/sqrFp4, bn.hpp:1075-1144)
-PSB_HD PSB_NOINL void fp4_sqr(Fp2& z0, Fp2& z1, const Fp2& x0, const Fp2& x1) {
-  Fp2 t0, t1, s;
-  fp2_sqr(t0, x0);
-  fp2_sqr(t1, x1);
-  fp2_add(s, x0, x1);
-  fp2_sqr(s, s);
-  fp2_sub(s, s, t0);
-  fp2_sub(z1, s, t1);           // 2 x0 x1
-  fp2_mul_xi(t1, t1);
-  fp2_add(z0, t1, t0);          // x0^2 + xi x1^2
-}
+// Granger-Scott squaring in the cyclotomic subgroup (cf. mcl fasterSqr/sqrFp4, bn.hpp:1075-1144).
+// Per Fp4 pair (xe, xo): t0 = xe^2, t1 = xo^2, s = (xe + xo)^2;  z0 = t0 + xi t1,  z1 = s - t0 - t1 = 2 xe xo;
+// outputs 3 z -+ 2 x are formed by the fused fp2_gs_* kernels (no intermediate z is stored).
 PSB_HD PSB_NOINL void fp12_cyclo_sqr(Fp12& y, const Fp12& x) {
   // slots: x0=a.a x4=a.b x3=a.c x2=b.a x1=b.b x5=b.c
-  Fp2 t0, t1, t2, t3, u;
-  const Fp2 x0 = x.a.a, x4 = x.a.b, x3 = x.a.c, x2 = x.b.a, x1 = x.b.b, x5 = x.b.c;
-  fp4_sqr(t0, t1, x0, x1);
-  fp2_sub(u, t0, x0); fp2_dbl(u, u); fp2_add(y.a.a, u, t0);     // y0 = 3 t0 - 2 x0
-  fp2_add(u, t1, x1); fp2_dbl(u, u); fp2_add(y.b.b, u, t1);     // y1 = 3 t1 + 2 x1
-  fp4_sqr(t0, t1, x2, x3);
-  fp4_sqr(t2, t3, x4, x5);
-  fp2_sub(u, t0, x4); fp2_dbl(u, u); fp2_add(y.a.b, u, t0);     // y4 = 3 t0 - 2 x4
-  fp2_add(u, t1, x5); fp2_dbl(u, u); fp2_add(y.b.c, u, t1);     // y5 = 3 t1 + 2 x5
-  fp2_mul_xi(t0, t3);
-  fp2_add(u, t0, x2); fp2_dbl(u, u); fp2_add(y.b.a, u, t0);     // y2 = 3 xi t3 + 2 x2
-  fp2_sub(u, t2, x3); fp2_dbl(u, u); fp2_add(y.a.c, u, t2);     // y3 = 3 t2 - 2 x3
+  Fp2 t0, t1, s, u0, u1, v2, v3;
+  // pair (x0, x1) -> y0, y1
+  fp2_sqr(t0, x.a.a); fp2_sqr(t1, x.b.b); fp2_sqr_sum(s, x.a.a, x.b.b);
+  fp2_sub2(s, s, t0, t1);                       // z1 = 2 x0 x1
+  fp2_xi_add(t0, t1, t0);                       // z0 = x0^2 + xi x1^2
+  fp2_3a2b(u0, t0, x.a.a, true);                // y0 = 3 z0 - 2 x0
+  fp2_3a2b(u1, s, x.b.b, false);                // y1 = 3 z1 + 2 x1
+  // pair (x4, x5) -> y2 (needs x2), y3 (needs x3): before the x4 / x5 slots are overwritten
+  fp2_sqr(t0, x.a.b); fp2_sqr(t1, x.b.c); fp2_sqr_sum(s, x.a.b, x.b.c);
+  fp2_sub2(s, s, t0, t1);
+  fp2_mul_xi(s, s);
+  fp2_xi_add(t0, t1, t0);
+  fp2_3a2b(v2, s, x.b.a, false);                // y2 = 3 xi z1 + 2 x2
+  fp2_3a2b(v3, t0, x.a.c, true);                // y3 = 3 z0 - 2 x3
+  // pair (x2, x3) -> y4 (needs x4), y5 (needs x5)
+  fp2_sqr(t0, x.b.a); fp2_sqr(t1, x.a.c); fp2_sqr_sum(s, x.b.a, x.a.c);
+  fp2_sub2(s, s, t0, t1);
+  fp2_xi_add(t0, t1, t0);
+  fp2_3a2b(y.a.b, t0, x.a.b, true);             // y4 = 3 z0 - 2 x4
+  fp2_3a2b(y.b.c, s, x.b.c, false);             // y5 = 3 z1 + 2 x5
+  y.a.a = u0; y.b.b = u1; y.b.a = v2; y.a.c = v3;
 }
 
 }  // namespace psb
