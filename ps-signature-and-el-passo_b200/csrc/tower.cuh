@@ -112,7 +112,7 @@ PSB_HD PSB_INL void fp_2pminus_rr(Fp& r, const Fp& a) {
 //   engine A  (re, im) = (xa ya + xb (p - yb), xa yb + xb ya)   x = x1 [+ x2],  y = y1 [+ y2]      fp2_mul, fp2_mul_sum
 //   engine B  (re, im) = (m1 n1, m2 n2)                         squares (x = x1 [+ x2]) and Fp2 * Fp  fp2_sqr, fp2_sqr_sum, fp2_mul_fp
 __device__ PSB_NOINL void fp2_engine_a(Fp2& r, const Fp2* x1, const Fp2* x2, const Fp2* y1, const Fp2* y2) {
-  Fp xa, xb, ya, yb, u, nb, re, im;
+  Fp xa, xb, ya, yb, u, nb, re;
   fp_get(xa, x1->a); fp_get(xb, x1->b); fp_get(ya, y1->a); fp_get(yb, y1->b);
   if (x2) {
     fp_get(u, x2->a); fp_addnr_rr(xa, xa, u);     // multiplicand side: unreduced (< 2p)
@@ -121,12 +121,18 @@ __device__ PSB_NOINL void fp2_engine_a(Fp2& r, const Fp2* x1, const Fp2* x2, con
     fp_get(u, y2->b); fp_add_rr(yb, yb, u);
   }
   fp_pminus_rr(nb, yb);
-  fp_dot2_rr(re, xa, ya, xb, nb);
-  fp_dot2_rr(im, xa, yb, xb, ya);
-  fp_put(r.a, re); fp_put(r.b, im);
+  // one multiplier body, executed twice (real, imaginary): half the code of two unrolled copies -- a 20 KB
+  // straight-line engine still stalled ~25 % of its samples on instruction fetch (r1g)
+  PSB_ROLL
+  for (int k = 0; k < 2; k++) {
+    Fp q, t;
+    if (k == 0) { q = ya; t = nb; } else { q = yb; t = ya; }
+    fp_dot2_rr(re, xa, q, xb, t);
+    fp_put(*fp2_comp(r, k), re);
+  }
 }
 __device__ PSB_NOINL void fp2_engine_b(Fp2& r, const Fp2* x1, const Fp2* x2, const Fp* k) {
-  Fp m1, n1, m2, n2, u, re, im;
+  Fp m1, n1, m2, n2, u, re;
   fp_get(m1, x1->a); fp_get(m2, x1->b);
   if (k) {                                         // (a + b i) k
     fp_get(n1, *k);
@@ -141,9 +147,13 @@ __device__ PSB_NOINL void fp2_engine_b(Fp2& r, const Fp2* x1, const Fp2* x2, con
     fp_addnr_rr(m2, m1, m1);                       // 2a   (< 2p: multiplicand only)
     fp_addnr_rr(m1, m1, n2);                       // a + b
   }
-  fp_mul_rr(re, m1, n1);
-  fp_mul_rr(im, m2, n2);
-  fp_put(r.a, re); fp_put(r.b, im);
+  PSB_ROLL
+  for (int k = 0; k < 2; k++) {
+    Fp m, n;
+    if (k == 0) { m = m1; n = n1; } else { m = m2; n = n2; }
+    fp_mul_rr(re, m, n);
+    fp_put(*fp2_comp(r, k), re);
+  }
 }
 __device__ PSB_INL void fp2_mul(Fp2& r, const Fp2& x, const Fp2& y) { fp2_engine_a(r, &x, nullptr, &y, nullptr); }
 __device__ PSB_INL void fp2_mul_sum(Fp2& r, const Fp2& x1, const Fp2& x2, const Fp2& y1, const Fp2& y2) { fp2_engine_a(r, &x1, &x2, &y1, &y2); }
