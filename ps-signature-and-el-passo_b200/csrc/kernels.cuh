@@ -87,6 +87,22 @@ __global__ void __launch_bounds__(256) k_bench_mad(int kind, int iters, const ui
     unsigned long long s = 0;
     for (int j = 0; j < 8; j++) s ^= acc[j];
     if (s == 0xdeadbeefull) sink[0] = (uint32_t)s;
+  } else if (kind == 7) {
+#ifdef __CUDA_ARCH__
+    // the multiplier's own instruction form: carry-chained wide MACs (IMAD.WIDE.U32.X rows of six, as in cios.cuh),
+    // three independent accumulator pairs = six independent carry chains per thread.  72 MAC32 per iteration.
+    cios::L12 E1, O1, E2, O2, E3, O3, av;
+    for (int j = 0; j < 12; j++) { E1[j] = seed[j] + t; O1[j] = seed[12 + j] ^ t; E2[j] = E1[j] + 1; O2[j] = O1[j] + 2; E3[j] = E1[j] ^ 5; O3[j] = O1[j] ^ 9; av[j] = seed[j] * (t | 1); }
+    for (int it = 0; it < iters; it++) {
+      cios::mac(E1, O1, av, b);
+      cios::mac(E2, O2, av, a);
+      cios::mac(E3, O3, av, b ^ a);
+      a += E1[0];
+    }
+    uint32_t s = 0;
+    for (int j = 0; j < 12; j++) s ^= E1[j] ^ O1[j] ^ E2[j] ^ O2[j] ^ E3[j] ^ O3[j];
+    if (s == 0xdeadbeefu) sink[0] = s;
+#endif
   } else {
     // plain 32-bit IMAD (lo only), 16 independent chains
     uint32_t lo[16];

@@ -187,7 +187,7 @@ class PSVerifier:
     def __init__(self, pk: PSPubKey):
         self.m_pk = pk
 
-    def verify(self, sig1, sig2, all_attributes=None, scalars=None, want_gt: bool = False):
+    def verify(self, sig1, sig2, all_attributes=None, scalars=None, want_gt: bool = False, out=None):
         """batched PSVerifier::verify (src/ps-verifier.cc:13-35).  sig1/sig2: (N,18) u64;
         all_attributes: N lists of n byte strings (or a packed (blob, off) pair), or scalars (N*n,4).
         Returns verdict uint8[N] (and GT (N,72) if want_gt)."""
@@ -197,7 +197,9 @@ class PSVerifier:
         if s2.shape[0] != N:
             raise ValueError("sig1/sig2 length mismatch")
         blob, off, m = _attr_args(self.m_pk, N, all_attributes, scalars)
-        verdict = np.zeros(N, dtype=np.uint8)
+        verdict = np.zeros(N, dtype=np.uint8) if out is None else out
+        if verdict.shape != (N,) or verdict.dtype != np.uint8:
+            raise ValueError("out must be uint8[N]")
         gt = np.zeros((N, GT), dtype=np.uint64) if want_gt else None
         _check(lib().psb_verify(self.m_pk.handle, C.c_size_t(N), _p(s1), _p(s2), _p(blob), _p(off), _p(m),
                                 _p(verdict), _p(gt)), "psb_verify")

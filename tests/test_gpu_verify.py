@@ -71,3 +71,49 @@ def test_verify_large_batch_properties(gpu_pkg, ref):
     idx = np.concatenate([np.arange(0, lanes, 37), wl.tampered])
     sub = ref.ps_verify(wl.key, wl.sig1[idx], wl.sig2[idx], [wl.attrs[i] for i in idx], nthreads=ref.hw_threads())
     assert np.array_equal(got[idx], sub)
+
+
+def test_attribute_hash_padding_boundaries(gpu_pkg, ref):
+    """device SHA-256 -> Fr (Fr::setHashOf rule) at every padding boundary: attribute lengths around 55/56, 63/64/65,
+    119/120 bytes, and lanes whose digest exceeds r after the 255-bit mask (second mask to 254 bits)."""
+    lens = [0, 1, 54, 55, 56, 57, 63, 64, 65, 118, 119, 120, 121, 128, 191, 192, 300]
+    key = ref.KeyMaterial(2, seed_=1)
+    attrs = [[bytes([65 + (i % 26)]) * L, b"tail%d" % i] for i, L in enumerate(lens)]
+    # hunt a few strings whose masked digest is >= r (probability ~ 1/10 each): exercises the 254-bit remask
+    import hashlib
+    R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+    j = 0
+    while sum(1 for a in attrs if a[1].startswith(b"big")) < 3:
+        s = b"big%d" % j
+        j += 1
+        if int.from_bytes(hashlib.sha256(s).digest(), "little") & ((1 << 255) - 1) >= R:
+            attrs.append([b"x", s])
+    sig1, sig2 = workload.sign_lanes(key, attrs, seed=31)
+    pk = gpu_pkg.PSPubKey(key.g, key.gg, key.XX, key.Y, key.YY, window_bits=8)
+    exp = ref.ps_verify(key, sig1, sig2, attrs)
+    assert exp.all()
+    assert np.array_equal(gpu_pkg.PSVerifier(pk).verify(sig1, sig2, attrs), exp)
+    # and the same signatures against attribute strings one byte longer must all fail
+    bad = [[a[0] + b"!", a[1]] for a in attrs]
+    assert not gpu_pkg.PSVerifier(pk).verify(sig1, sig2, bad).any()
+    pk.close()
+
+
+def test_randomize_verify_round_trip_large(gpu_pkg, ref):
+    """size-independent property at 2^14 lanes: verify(randomize(sigma, t)) == verify(sigma) for every lane
+    (honest and tampered), with per-lane random t; t = 0 sends a credential to (0, 0), which verify rejects."""
+    lanes = 1 << 14
+    wl = workload.make_verify_workload(n_attrs=3, lanes=lanes, seed=23, tamper_every=97)
+    pk = gpu_pkg.PSPubKey(wl.key.g, wl.key.gg, wl.key.XX, wl.key.Y, wl.key.YY, window_bits=12)
+    ver = gpu_pkg.PSVerifier(pk)
+    base = ver.verify(wl.sig1, wl.sig2, (wl.blob, wl.off))
+    ref.seed(99)
+    t = ref.fr_rand(lanes)
+    t[5] = 0
+    r1, r2 = gpu_pkg.PSRequester.randomize_credential(wl.sig1, wl.sig2, t)
+    again = ver.verify(r1, r2, (wl.blob, wl.off))
+    exp = base.copy()
+    exp[5] = 0
+    assert np.array_equal(again, exp)
+    assert not r1[5].any() and not r2[5].any()
+    pk.close()
