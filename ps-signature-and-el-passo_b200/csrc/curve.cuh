@@ -136,10 +136,10 @@ PSB_HD PSB_NOINL void pt_normalize(Jac<F>& R, const Jac<F>& P) {
   f_set_one(R.z);
 }
 
-// k*P, variable base: fixed 4-bit windows over the 256-bit normal-form scalar (MSB first).
-// k = 8 limbs, normal form (NOT Montgomery), k < 2^256.
+// k*P, variable base, no endomorphism: fixed 4-bit windows over the 256-bit normal-form scalar (MSB first).
+// k = 8 limbs, normal form (NOT Montgomery), k < 2^256.  Kept as the plain reference path of the GLV/GLS versions.
 template <class F>
-PSB_HD PSB_NOINL void pt_mul(Jac<F>& R, const Jac<F>& P, const uint32_t* k) {
+PSB_HD PSB_NOINL void pt_mul_window(Jac<F>& R, const Jac<F>& P, const uint32_t* k) {
   Jac<F> tbl[16];
   pt_set_zero(tbl[0]);
   tbl[1] = P;
@@ -154,6 +154,159 @@ PSB_HD PSB_NOINL void pt_mul(Jac<F>& R, const Jac<F>& P, const uint32_t* k) {
   }
   R = acc;
 }
+
+// ---- GLV (G1) and GLS (G2) variable-base multiplication -----------------------------------------------------
+// Same group element as mcl's G1::mul / G2::mul (which use the same endomorphisms with w-NAF: ec.hpp:1457-1523
+// GLV1, bn.hpp:765-860 GLV2); only the schedule is ours: fixed 4-bit joint windows, one shared table of multiples
+// of P, endomorphic images of table entries formed on the fly.
+//   G1: phi(X, Y, Z) = (beta X, Y, Z) = [lambda] P, lambda = z^2 - 1;  k = k1 + k2 lambda with k1, k2 < 2^128
+//       (r = lambda^2 + lambda + 1, so k2 = floor(k / lambda) <= lambda + 1).  128 doublings instead of 256.
+//   G2: psi(X, Y, Z) = (conj(X) cx, conj(Y) cy, conj(Z)) = [z] Q (z < 0);  k = sum d_i |z|^i, d_i < 2^64, so
+//       k Q = d0 Q - d1 psi(Q) + d2 psi^2(Q) - d3 psi^3(Q).  64 doublings instead of 256.
+
+// q = floor(k / lambda), rem = k mod lambda for k < r  (Barrett with mu = floor(2^256 / lambda), deficit <= 2)
+PSB_HD PSB_INL void glv1_split(uint32_t k1[4], uint32_t k2[4], const uint32_t* k) {
+  const uint32_t* mu = PSB_K(GLV_MU);
+  const uint32_t* lam = PSB_K(GLV_LAMBDA);
+  // top 5 limbs of k * mu (13 limbs): only columns >= 6 can influence limbs 8..12 through carries of 2 limbs;
+  // compute the full product column by column with a 3-word accumulator
+  uint32_t q[5];
+  {
+    uint64_t lo = 0, hi = 0;
+    for (int col = 0; col < 13; col++) {
+      for (int i = 0; i < 8; i++) {
+        const int j = col - i;
+        if (j < 0 || j > 4) continue;
+        const uint64_t pr = (uint64_t)k[i] * mu[j];
+        const uint64_t nl = lo + pr;
+        hi += nl < lo;
+        lo = nl;
+      }
+      if (col >= 8) q[col - 8] = (uint32_t)lo;
+      lo = (lo >> 32) | (hi << 32);
+      hi = 0;
+    }
+  }
+  // rem = k - q * lambda  (mod 2^160: rem < 3 lambda < 2^130)
+  uint32_t rem[5];
+  {
+    uint32_t ql[5];
+    uint64_t lo = 0, hi = 0;
+    for (int col = 0; col < 5; col++) {
+      for (int i = 0; i <= col; i++) {
+        const int j = col - i;
+        if (i > 4 || j > 3) continue;
+        const uint64_t pr = (uint64_t)q[i] * lam[j];
+        const uint64_t nl = lo + pr;
+        hi += nl < lo;
+        lo = nl;
+      }
+      ql[col] = (uint32_t)lo;
+      lo = (lo >> 32) | (hi << 32);
+      hi = 0;
+    }
+    int64_t c = 0;
+    for (int i = 0; i < 5; i++) { c += (int64_t)k[i] - ql[i]; rem[i] = (uint32_t)c; c >>= 32; }
+  }
+  for (int it = 0; it < 3; it++) {   // at most two corrections
+    uint32_t t[5];
+    int64_t c = 0;
+    for (int i = 0; i < 5; i++) { c += (int64_t)rem[i] - (i < 4 ? lam[i] : 0u); t[i] = (uint32_t)c; c >>= 32; }
+    if (c < 0) break;                // rem < lambda
+    for (int i = 0; i < 5; i++) rem[i] = t[i];
+    uint64_t cc = 1;
+    for (int i = 0; i < 5; i++) { cc += q[i]; q[i] = (uint32_t)cc; cc >>= 32; }
+  }
+  for (int i = 0; i < 4; i++) { k1[i] = rem[i]; k2[i] = q[i]; }
+}
+
+PSB_HD PSB_NOINL void g1_mul_glv(G1J& R, const G1J& P, const uint32_t* k) {
+  uint32_t k1[4], k2[4];
+  glv1_split(k1, k2, k);
+  G1J tbl[16];
+  pt_set_zero(tbl[0]);
+  tbl[1] = P;
+  pt_dbl(tbl[2], P);
+  for (int i = 3; i < 16; i++) pt_add(tbl[i], tbl[i - 1], P);
+  Fp beta;
+  for (int i = 0; i < 12; i++) beta.v[i] = PSB_K(GLV_BETA)[i];
+  G1J acc, T;
+  pt_set_zero(acc);
+  for (int i = 31; i >= 0; i--) {
+    pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc);
+    const uint32_t d1 = (k1[i >> 3] >> ((i & 7) * 4)) & 0xF, d2 = (k2[i >> 3] >> ((i & 7) * 4)) & 0xF;
+    if (d1) pt_add(acc, acc, tbl[d1]);
+    if (d2) {
+      T = tbl[d2];
+      fp_mul(T.x, T.x, beta);          // phi(d2 P)
+      pt_add(acc, acc, T);
+    }
+  }
+  R = acc;
+}
+
+// d_i = base-|z| digits of k (k < 2^256 -> four digits below 2^64 for k < r)
+PSB_HD PSB_INL void gls_split(uint64_t d[4], const uint32_t* k) {
+  uint32_t q[8];
+  for (int i = 0; i < 8; i++) q[i] = k[i];
+  for (int j = 0; j < 3; j++) {
+    unsigned __int128 rem = 0;
+    for (int i = 7; i >= 0; i--) {
+      const unsigned __int128 cur = (rem << 32) | q[i];
+      q[i] = (uint32_t)(cur / PSB_Z_ABS);
+      rem = cur % PSB_Z_ABS;
+    }
+    d[j] = (uint64_t)rem;
+  }
+  d[3] = ((uint64_t)q[1] << 32) | q[0];
+}
+
+// (-1)^j psi^j(T) for a Jacobian point, j = 1..3 (constants from tools/gen_constants.py)
+PSB_HD PSB_NOINL void g2_psi_signed(G2J& T, int j) {
+  if (j == 2) {
+    Fp n;
+    for (int i = 0; i < 12; i++) n.v[i] = PSB_K(PSI_NCX)[i];
+    fp2_mul_fp(T.x, T.x, n);
+    fp2_neg(T.y, T.y);                 // psi^2(x, y) = (x N(cx), -y); sign +
+    return;
+  }
+  Fp2 c;
+  const uint32_t* cxp = (j == 1) ? PSB_K(PSI_CX) : PSB_K(PSI_CX3);
+  for (int i = 0; i < 12; i++) { c.a.v[i] = cxp[i]; c.b.v[i] = cxp[12 + i]; }
+  fp2_conj(T.x, T.x); fp2_conj(T.y, T.y); fp2_conj(T.z, T.z);
+  fp2_mul(T.x, T.x, c);
+  for (int i = 0; i < 12; i++) { c.a.v[i] = PSB_K(PSI_CY)[i]; c.b.v[i] = PSB_K(PSI_CY)[12 + i]; }
+  fp2_mul(T.y, T.y, c);
+  if (j == 1) fp2_neg(T.y, T.y);       // -psi(T);  -psi^3(T) = (conj(x) cx3, +conj(y) cy)
+}
+
+PSB_HD PSB_NOINL void g2_mul_gls(G2J& R, const G2J& P, const uint32_t* k) {
+  uint64_t d[4];
+  gls_split(d, k);
+  G2J tbl[16];
+  pt_set_zero(tbl[0]);
+  tbl[1] = P;
+  pt_dbl(tbl[2], P);
+  for (int i = 3; i < 16; i++) pt_add(tbl[i], tbl[i - 1], P);
+  G2J acc, T;
+  pt_set_zero(acc);
+  for (int i = 15; i >= 0; i--) {
+    pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc);
+    for (int j = 0; j < 4; j++) {
+      const uint32_t dj = (uint32_t)(d[j] >> (4 * i)) & 0xF;
+      if (!dj) continue;
+      if (j == 0) { pt_add(acc, acc, tbl[dj]); continue; }
+      T = tbl[dj];
+      g2_psi_signed(T, j);
+      pt_add(acc, acc, T);
+    }
+  }
+  R = acc;
+}
+
+// variable-base multiplication used by the protocol kernels
+PSB_HD PSB_INL void pt_mul(G1J& R, const G1J& P, const uint32_t* k) { g1_mul_glv(R, P, k); }
+PSB_HD PSB_INL void pt_mul(G2J& R, const G2J& P, const uint32_t* k) { g2_mul_gls(R, P, k); }
 
 // ---- fixed-base windows --------------------------------------------------------------------------
 // Signed w-bit recoding of a 256-bit normal-form scalar (< 2^255): digits in [-2^(w-1), 2^(w-1)],

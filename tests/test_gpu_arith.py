@@ -138,3 +138,20 @@ def test_fr(gpu_pkg, ref):
     ints = ref.fr_to_ints(a)
     got = gpu_pkg.test_op(70, a)
     assert [int.from_bytes(got[i].tobytes(), "little") for i in range(64)] == ints
+
+
+def test_glv_gls_scalar_edges(gpu_pkg, ref):
+    """GLV (G1) / GLS (G2) variable-base multiplication on the GPU at the decomposition boundaries."""
+    from oracle import ps_oracle as O
+    Z = 0xd201000000010000
+    lam = Z * Z - 1
+    ks = [0, 1, 2, 15, 16, lam - 1, lam, lam + 1, 2 * lam, lam * lam, lam * (lam + 1), Z - 1, Z, Z + 1, Z * Z, Z ** 3, Z ** 3 - 1,
+          (1 << 64) - 1, 1 << 64, (1 << 128) - 1, 1 << 128, O.R - 1, O.R - 2]
+    rng = np.random.default_rng(5)
+    ks += [int.from_bytes(rng.bytes(32), "little") % O.R for _ in range(105)]
+    k = ref.fr_from_ints(ks)
+    g, gg = ref.hash_to_g1(b"abc"), ref.hash_to_g2(b"edf")
+    P = ref.g1_op(ref.G_DBL, np.repeat(g.reshape(1, -1), len(ks), axis=0))   # z != 1
+    Q = ref.g2_op(ref.G_DBL, np.repeat(gg.reshape(1, -1), len(ks), axis=0))
+    assert np.array_equal(ref.g1_serialize(gpu_pkg.test_op(43, P, k)), ref.g1_serialize(ref.g1_mul(P, k)))
+    assert np.array_equal(ref.g2_serialize(gpu_pkg.test_op(53, Q, k)), ref.g2_serialize(ref.g2_mul(Q, k)))

@@ -69,3 +69,28 @@ def test_sha256_to_scalar(hostsim):
         k = np.zeros(8, dtype=np.uint32)
         hostsim.hostsim_set_hash_of(msg, C.c_size_t(len(msg)), k.ctypes.data_as(C.c_void_p))
         assert int.from_bytes(k.tobytes(), "little") == O.fr_set_hash_of(msg)
+
+
+def test_glv_gls_scalar_edges(hostsim, ref):
+    """GLV (G1) / GLS (G2) variable-base multiplication at the decomposition boundaries: 0, 1, lambda-1, lambda,
+    lambda+1, multiples of |z|, r-1, and random scalars -- against mcl's G1::mul / G2::mul (normalised)."""
+    from oracle import ps_oracle as O
+    Z = 0xd201000000010000
+    lam = Z * Z - 1
+    ks = [0, 1, 2, 15, 16, lam - 1, lam, lam + 1, 2 * lam, lam * lam, lam * (lam + 1), Z - 1, Z, Z + 1, Z * Z, Z ** 3, Z ** 3 - 1,
+          (1 << 64) - 1, 1 << 64, (1 << 128) - 1, 1 << 128, O.R - 1, O.R - 2]
+    rng = np.random.default_rng(5)
+    ks += [int.from_bytes(rng.bytes(32), "little") % O.R for _ in range(9)]
+    k = ref.fr_from_ints(ks)
+    g, gg = ref.hash_to_g1(b"abc"), ref.hash_to_g2(b"edf")
+    P = np.repeat(g.reshape(1, -1), len(ks), axis=0)
+    Q = np.repeat(gg.reshape(1, -1), len(ks), axis=0)
+    norm1 = lambda a: hop(hostsim, 42, a)  # noqa: E731  T_G1_NORM
+    norm2 = lambda a: hop(hostsim, 52, a)  # noqa: E731  T_G2_NORM
+    assert np.array_equal(norm1(hop(hostsim, 43, P, k)), ref.g1_op(ref.G_NORM, ref.g1_mul(g, k)))
+    assert np.array_equal(norm2(hop(hostsim, 53, Q, k)), ref.g2_op(ref.G_NORM, ref.g2_mul(gg, k)))
+    # un-normalised input points (z != 1)
+    P2 = ref.g1_op(ref.G_DBL, P)
+    Q2 = ref.g2_op(ref.G_DBL, Q)
+    assert np.array_equal(norm1(hop(hostsim, 43, P2, k)), ref.g1_op(ref.G_NORM, ref.g1_mul(P2, k)))
+    assert np.array_equal(norm2(hop(hostsim, 53, Q2, k)), ref.g2_op(ref.G_NORM, ref.g2_mul(Q2, k)))
