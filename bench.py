@@ -313,7 +313,19 @@ def main():
     h2d = int(sig1.nbytes + sig2.nbytes + int(off[-1]) + off.nbytes)
     d2h = int(N)
 
-    ms_total, e2e_ms = max_over_ranks([ms_total, e2e_s * 1e3], world, dev)
+    # ---- pairings/s (BASELINE.json: "pairings/sec vs mcl CPU"): batched mcl::bn::pairing through psb_pairing ------
+    NP = min(N, 1 << 17)
+    rng = np.random.default_rng(77 + rank)
+    kk = np.frombuffer(rng.bytes(32 * NP), dtype=np.uint64).reshape(NP, 4).copy()
+    kk[:, 3] &= np.uint64(0x0FFFFFFFFFFFFFFF)
+    Pp = pkg.g1_mul(key["g"], kk)                       # NP distinct G1 points
+    Qq = np.ascontiguousarray(np.tile(key["YY"], (NP // N_ATTRS + 1, 1))[:NP])   # G2 points of the key, cycled
+    pkg.pairing(Pp[:4096], Qq[:4096])
+    barrier()
+    t0 = time.perf_counter()
+    gt_pair = pkg.pairing(Pp, Qq)
+    pair_s = time.perf_counter() - t0
+    ms_total, e2e_ms, pair_ms = max_over_ranks([ms_total, e2e_s * 1e3, pair_s * 1e3], world, dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -343,6 +355,8 @@ def main():
                    "parallelism": f"lanes sharded over {world} GPU(s), no collective"},
         "e2e": {"value": e2e_val, "unit": "verifications/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps},
+        "pairings": {"value": job_throughput(NP, world, 1, pair_ms), "unit": "pairings/s", "lanes_per_gpu": NP,
+                     "how": "psb_pairing end to end (H2D of G1/G2 points, Miller loop + final exponentiation, D2H of 576-byte GT)"},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "roofline": {"bound": "int32-mac", "kernel": names[dom], "achieved": achieved / 1e12, "peak": peak_mac / 1e12,
@@ -359,6 +373,12 @@ def main():
         try:
             cb = cpu_reference_verify(N_ATTRS, sig1, sig2, lane_attrs, args.cpu_budget_s)
             agree = bool(np.array_equal(cb["verdict"], got[:cb["lanes"]]))
+            from oracle import ref as _ref   # checker: GT bytes of a pairing sample against mcl::bn::pairing
+            pair_ok = bool(np.array_equal(gt_pair[:64], _ref.pairing(Pp[:64], Qq[:64])))
+            line["pairings"]["cpu_reference_pairings_per_s"] = cb["pairings_per_s"]
+            line["pairings"]["gt_bytes_agree_with_reference"] = pair_ok
+            if not pair_ok:
+                raise SystemExit("GPU pairing GT bytes disagree with the reference")
             line["cpu_baseline"] = {"value": cb["rate"], "unit": "verifications/s", "cores": cb["threads"], "kind": "reference",
                                     "sample": f"first {cb['lanes']} lanes of the same batch, PSVerifier::verify via mcl "
                                               f"(JIT={int(cb['jit'])}), {cb['seconds']:.1f} s",

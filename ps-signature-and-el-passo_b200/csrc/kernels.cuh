@@ -160,10 +160,10 @@ __global__ void __launch_bounds__(kBlock) k_build_table(const Aff<F>* wb, int nb
   const uint32_t ch = (uint32_t)(gid % chunks_per_win);
   const uint32_t d0 = ch * kTblChunk;           // entries d0+1 .. d0+kTblChunk
   const Aff<F> B = wb[bw];
-  // S = d0 * B by double-and-add over 16 bits
+  // S = d0 * B by double-and-add (d0 < 2^19 for w <= 20)
   Jac<F> S;
   pt_set_zero(S);
-  for (int bit = 15; bit >= 0; bit--) {
+  for (int bit = 19; bit >= 0; bit--) {
     pt_dbl(S, S);
     if ((d0 >> bit) & 1u) pt_madd(S, S, B);
   }
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(kBlock, PSB_MINB) k_verify_final(size_t N, con
 }
 
 // plain pairing e(P, Q) per lane (no fixed argument)
-__global__ void __launch_bounds__(kBlock) k_pairing_miller(size_t N, const G1J* P, const G2J* Q, Fp12* fout) {
+__global__ void __launch_bounds__(kBlock, PSB_MINB) k_pairing_miller(size_t N, const G1J* P, const G2J* Q, Fp12* fout) {
   const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (lane >= N) return;
   Fp x1, y1, zero;
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(kBlock) k_pairing_miller(size_t N, const G1J* 
   miller_loop2(f, x1, y1, q, zero, zero, nullptr, false);
   fout[lane] = f;
 }
-__global__ void __launch_bounds__(kBlock) k_final_exp(size_t N, const Fp12* fin, Fp12* out) {
+__global__ void __launch_bounds__(kBlock, PSB_MINB) k_final_exp(size_t N, const Fp12* fin, Fp12* out) {
   const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (lane >= N) return;
   Fp12 f = fin[lane], e;

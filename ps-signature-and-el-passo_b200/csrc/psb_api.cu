@@ -276,7 +276,7 @@ psb_key* psb_key_create(const uint64_t* g, const uint64_t* gg, const uint64_t* X
   if (!g_init) { fail(PSB_ERR_NOT_INIT, "psb_init not called"); return nullptr; }
   if (!g || !gg || !XX || (n && (!Y || !YY))) { fail(PSB_ERR_ARG, "null key component"); return nullptr; }
   int w = window_bits == 0 ? 16 : window_bits;
-  if (w < 4 || w > 16) { fail(PSB_ERR_ARG, "window_bits must be 4..16"); return nullptr; }
+  if (w < 4 || w > 20) { fail(PSB_ERR_ARG, "window_bits must be 4..20"); return nullptr; }
   // fixed bases must be finite points: their window tables hold affine entries (z == 0 <=> infinity)
   bool inf = is_zero_words(g + 12, 6) || is_zero_words(gg + 24, 12) || is_zero_words(XX + 24, 12);
   for (size_t i = 0; i < n; i++) inf = inf || is_zero_words(Y + 18 * i + 12, 6) || is_zero_words(YY + 36 * i + 24, 12);
