@@ -66,6 +66,21 @@ int psb_verify(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* sig
                const uint8_t* attr_blob, const uint64_t* attr_off, const uint64_t* m,
                uint8_t* verdict, uint64_t* gt);
 
+/* Batched G1::deserialize / G2::deserialize = point decompression (mcl/include/mcl/ec.hpp:924-1057, IoSerialize,
+ * mcl's default little-endian mode): element j is the 48 (G1) / 96 (G2) bytes at ser + j * stride.  out[j] = the
+ * point with z = 1 (all-zero for the infinity encoding); ok[j] = 1 iff mcl's deserialize would succeed (x < p and
+ * x^3 + b a square).  SURVEY.md 8f rank 1: wire-format ingest on the device. */
+int psb_g1_deserialize(size_t N, const uint8_t* ser, size_t stride, uint64_t* out, uint8_t* ok);
+int psb_g2_deserialize(size_t N, const uint8_t* ser, size_t stride, uint64_t* out, uint8_t* ok);
+
+/* psb_verify on SERIALIZED credentials: lane j reads sigma1 at cred + j * stride + off1 and sigma2 at + off2
+ * (48 bytes each).  PSCredential::toBufferString (src/ps-encoding.cc:384-391) is two TLVs of 1 + 1 + 48 bytes:
+ * stride = 100, off1 = 2, off2 = 52; a bare 96-byte sigma1 || sigma2 is stride = 96, off1 = 0, off2 = 48.
+ * Points are decompressed on the device; a lane whose encoding mcl would reject gets verdict 0 and decoded[j] = 0
+ * (decoded is optional).  Attributes as strings only. */
+int psb_verify_ser(psb_key* key, size_t N, const uint8_t* cred, size_t stride, size_t off1, size_t off2,
+                   const uint8_t* attr_blob, const uint64_t* attr_off, uint8_t* verdict, uint8_t* decoded);
+
 /* Same computation with every buffer already resident in the memory of device `dev_index`
  * (index into the psb_init list); launches on `stream` (a cudaStream_t, NULL = the library's own
  * stream) and does not synchronise.  `ws` = device scratch of psb_verify_ws_bytes(key, N) bytes. */

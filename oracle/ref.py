@@ -222,6 +222,28 @@ def g2_deserialize(b):
     return out, bool(ok)
 
 
+def cred_encode(sig1, sig2):
+    """PSCredential::toBufferString of every lane -> uint8 (N, 100)."""
+    sig1 = _u64(sig1).reshape(-1, G1)
+    sig2 = _u64(sig2).reshape(-1, G1)
+    N = sig1.shape[0]
+    out = np.zeros(N * 100, dtype=np.uint8)
+    lib().ref_cred_encode.restype = C.c_size_t
+    used = lib().ref_cred_encode(C.c_size_t(N), _p(sig1), _p(sig2), _p(out), C.c_size_t(out.size))
+    assert used == N * 100, used
+    return out.reshape(N, 100)
+
+
+def cred_decode(buf):
+    """PSCredential::fromBufferString of every lane (uint8 (N, 100)) -> sig1, sig2."""
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    N, stride = buf.shape
+    s1 = np.zeros((N, G1), dtype=np.uint64)
+    s2 = np.zeros((N, G1), dtype=np.uint64)
+    lib().ref_cred_decode(C.c_size_t(N), _p(buf), C.c_size_t(stride), _p(s1), _p(s2))
+    return s1, s2
+
+
 def hash_to_g1(msg: bytes):
     out = np.empty(G1, dtype=np.uint64)
     lib().ref_hash_to_g1(C.c_char_p(msg), C.c_size_t(len(msg)), _p(out))

@@ -271,6 +271,27 @@ size_t ref_key_encode(void* key, uint8_t* out, size_t cap) {
   return b.size();
 }
 
+// credentials through the reference's own TLV codec (PSCredential::toBufferString / fromBufferString,
+// src/ps-encoding.cc:384-401): n credentials -> n * 100 bytes; and back (decode returns the parsed points)
+size_t ref_cred_encode(size_t n, const G1* sig1, const G1* sig2, uint8_t* out, size_t cap) {
+  size_t used = 0;
+  for (size_t i = 0; i < n; i++) {
+    PSCredential c; c.sig1 = sig1[i]; c.sig2 = sig2[i];
+    PSBuffer b = c.toBufferString();
+    if (used + b.size() > cap) return 0;
+    memcpy(out + used, b.data(), b.size());
+    used += b.size();
+  }
+  return used;
+}
+void ref_cred_decode(size_t n, const uint8_t* in, size_t stride, G1* sig1, G1* sig2) {
+  for (size_t i = 0; i < n; i++) {
+    PSBuffer b; b.assign(in + i * stride, in + (i + 1) * stride);
+    PSCredential c = PSCredential::fromBufferString(b);
+    sig1[i] = c.sig1; sig2[i] = c.sig2;
+  }
+}
+
 static inline std::vector<std::string> lane_attrs(const uint8_t* blob, const u64* off, size_t lane,
                                                   size_t n) {
   std::vector<std::string> v; v.reserve(n);

@@ -314,6 +314,27 @@ __global__ void __launch_bounds__(kBlock) k_g1_mul(size_t N, const G1J* P, int p
   out[lane] = n;
 }
 
+// ---- batched G1::deserialize / G2::deserialize (point decompression) ----------------------
+// element j is read at ser + j * stride (+ offset applied by the caller); ok[j] &= / = decode success
+__global__ void __launch_bounds__(kBlock) k_g1_deserialize(size_t N, const uint8_t* ser, size_t stride, G1J* out, uint8_t* ok,
+                                                            int accumulate) {
+  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= N) return;
+  G1J P;
+  const bool r = g1_deserialize(P, ser + lane * stride);
+  out[lane] = P;
+  ok[lane] = (uint8_t)((accumulate ? ok[lane] : 1) & (r ? 1 : 0));
+}
+__global__ void __launch_bounds__(kBlock) k_g2_deserialize(size_t N, const uint8_t* ser, size_t stride, G2J* out, uint8_t* ok,
+                                                            int accumulate) {
+  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= N) return;
+  G2J P;
+  const bool r = g2_deserialize(P, ser + lane * stride);
+  out[lane] = P;
+  ok[lane] = (uint8_t)((accumulate ? ok[lane] : 1) & (r ? 1 : 0));
+}
+
 // ---- PSSigner::el_passo_provide_id (src/ps-signer.cc:63-146) -------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_provide_id(size_t N, int n, int w, const G1A* tblG1, const G1J* g1pts,
                                                         const G1J* A, const Fr* c, const Fr* rs, int per,

@@ -47,6 +47,107 @@ PSB_HD PSB_NOINL void g2_serialize_norm(uint8_t* out, const G2J& P) {
   if (ya.v[0] & 1u) out[95] |= 0x80;
 }
 
+// ---- deserialisation = point decompression (mcl EcT::load, ec.hpp:924-1057, IoSerialize, non-ETH mode) ---------------
+// relying parties receive compressed points (48 / 96 bytes), and decompressing them with mcl on
+// the host (a square root each) would cap a GPU box long before the pairing kernels do.
+// 48 little-endian bytes -> canonical Montgomery Fp; false if the value is >= p (Fp::setArray, NoMask: fp.hpp:342-345)
+PSB_HD PSB_INL bool fp_from_le_bytes(Fp& r, const uint8_t* b, uint8_t last_mask) {
+  Fp n;
+  for (int i = 0; i < 12; i++)
+    n.v[i] = (uint32_t)b[4 * i] | ((uint32_t)b[4 * i + 1] << 8) | ((uint32_t)b[4 * i + 2] << 16) |
+             ((uint32_t)(i == 11 ? (b[47] & last_mask) : b[4 * i + 3]) << 24);
+  uint32_t t[12];
+  if (sub_mod_n<FpT>(t, n.v) == 0) return false;   // n >= p
+  fp_to_mont(r, n);
+  return true;
+}
+// mcl Fp::squareRoot for p = 3 mod 4 (gmp_util.hpp:880-897): a = 0 -> 0; non-residue -> false; else a^((p+1)/4)
+PSB_HD PSB_NOINL bool fp_sqrt(Fp& y, const Fp& a) {
+  if (fp_is_zero(a)) { fp_set_zero(y); return true; }
+  Fp r, t;
+  fp_pow_nib(r, a, PSB_K(FP_PP1D4_NIB));
+  fp_sqr(t, r);
+  if (!fp_eq(t, a)) return false;
+  y = r;
+  return true;
+}
+PSB_HD PSB_INL bool fp_is_odd(const Fp& a) {       // parity of the NORMAL form (Fp::isOdd)
+  Fp n;
+  fp_from_mont(n, a);
+  return (n.v[0] & 1u) != 0;
+}
+PSB_HD PSB_INL void fp_div2(Fp& r, const Fp& a) {   // Fp::divBy2 (works on the Montgomery representative)
+  uint32_t t[13];
+  for (int i = 0; i < 12; i++) t[i] = a.v[i];
+  t[12] = 0;
+  if (a.v[0] & 1u) {
+    uint64_t c = 0;
+    for (int i = 0; i < 12; i++) { c += (uint64_t)t[i] + FpT::p(i); t[i] = (uint32_t)c; c >>= 32; }
+    t[12] = (uint32_t)c;
+  }
+  for (int i = 0; i < 12; i++) r.v[i] = (t[i] >> 1) | (t[i + 1] << 31);
+}
+// mcl Fp2::squareRoot (fp_tower.hpp:320-352), same root selection
+PSB_HD PSB_NOINL bool fp2_sqrt(Fp2& y, const Fp2& x) {
+  Fp t1, t2;
+  if (fp_is_zero(x.b)) {
+    if (fp_sqrt(t1, x.a)) { y.a = t1; fp_set_zero(y.b); }
+    else { fp_neg(t2, x.a); fp_sqrt(t1, t2); fp_set_zero(y.a); y.b = t1; }
+    return true;
+  }
+  fp_dot2(t1, x.a, x.a, x.b, x.b);             // c^2 + d^2
+  if (!fp_sqrt(t1, t1)) return false;
+  Fp u;
+  fp_add(u, x.a, t1);
+  fp_div2(u, u);
+  if (!fp_sqrt(t2, u)) {
+    fp_sub(u, x.a, t1);
+    fp_div2(u, u);
+    fp_sqrt(t2, u);
+  }
+  y.a = t2;
+  fp_dbl(t2, t2);
+  fp_inv(t2, t2);
+  fp_mul(y.b, x.b, t2);
+  return true;
+}
+// G1::deserialize: all-zero = infinity; bit 7 of the last byte = y odd; x >= p or x^3 + 4 a non-residue -> false
+PSB_HD PSB_NOINL bool g1_deserialize(G1J& P, const uint8_t* b) {
+  uint8_t o = 0;
+  for (int i = 0; i < 48; i++) o |= b[i];
+  pt_set_zero(P);
+  if (o == 0) return true;
+  const bool y_odd = (b[47] >> 7) != 0;
+  Fp x, y, t, four;
+  if (!fp_from_le_bytes(x, b, 0x7f)) return false;
+  fp_sqr(t, x); fp_mul(t, t, x);
+  fp_set_one(four); fp_dbl(four, four); fp_dbl(four, four);
+  fp_add(t, t, four);
+  if (!fp_sqrt(y, t)) return false;
+  if (fp_is_odd(y) != y_odd) fp_neg(y, y);
+  P.x = x; P.y = y; fp_set_one(P.z);
+  return true;
+}
+// G2::deserialize: x.a || x.b (96 bytes), flag in the last byte, parity of y.a (Fp2::isOdd, fp_tower.hpp:312)
+PSB_HD PSB_NOINL bool g2_deserialize(G2J& P, const uint8_t* b) {
+  uint8_t o = 0;
+  for (int i = 0; i < 96; i++) o |= b[i];
+  pt_set_zero(P);
+  if (o == 0) return true;
+  const bool y_odd = (b[95] >> 7) != 0;
+  Fp2 x, y, t, bb;
+  if (!fp_from_le_bytes(x.a, b, 0xff)) return false;
+  if (!fp_from_le_bytes(x.b, b + 48, 0x7f)) return false;
+  fp2_sqr(t, x); fp2_mul(t, t, x);
+  fp_set_one(bb.a); fp_dbl(bb.a, bb.a); fp_dbl(bb.a, bb.a);    // b' = 4 xi = 4 + 4i
+  bb.b = bb.a;
+  fp2_add(t, t, bb);
+  if (!fp2_sqrt(y, t)) return false;
+  if (fp_is_odd(y.a) != y_odd) fp2_neg(y, y);
+  P.x = x; P.y = y; fp2_set_one(P.z);
+  return true;
+}
+
 // simultaneous inversion (Montgomery's trick): z[i] <- z[i]^-1 for the non-zero entries, ONE fp_inv.
 // Zero entries stay zero.  cnt <= 8.
 PSB_HD PSB_NOINL void fp_batch_inv(Fp* z, int cnt) {

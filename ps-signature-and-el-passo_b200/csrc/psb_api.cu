@@ -168,7 +168,8 @@ bool is_zero_words(const uint64_t* p, size_t n) {
 }
 
 int verify_launch(const psb_key* key, int di, size_t N, const G1J* d_sig1, const G1J* d_sig2, const uint8_t* d_blob,
-                  const uint64_t* d_off, const Fr* d_m, uint8_t* d_verdict, Fp12* d_gt, void* d_ws, cudaStream_t st) {
+                  const uint64_t* d_off, const Fr* d_m, uint8_t* d_verdict, Fp12* d_gt, void* d_ws, cudaStream_t st,
+                  const uint8_t* d_pre = nullptr) {
   if (N == 0) return PSB_OK;
   const KeyDev& kd = key->d[di];
   G2J* dK = (G2J*)d_ws;
@@ -185,7 +186,7 @@ int verify_launch(const psb_key* key, int di, size_t N, const G1J* d_sig1, const
   k_verify_miller<<<nblocks(N), kBlock, 0, st>>>(N, d_sig1, d_sig2, dK, kd.lines, dF);
   LAUNCHED();
   if (prof) CK(cudaEventRecord(dv->ev[2], st));
-  k_verify_final<<<nblocks(N), kBlock, 0, st>>>(N, d_sig1, dF, d_verdict, d_gt, nullptr, 1);
+  k_verify_final<<<nblocks(N), kBlock, 0, st>>>(N, d_sig1, dF, d_verdict, d_gt, d_pre, 1);
   LAUNCHED();
   if (prof) CK(cudaEventRecord(dv->ev[3], st));
   CK(cudaGetLastError());
@@ -376,6 +377,81 @@ int psb_verify(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* sig
     if (rc) return rc;
     CK(cudaMemcpyAsync(verdict + b, dv->in[4].p, L, cudaMemcpyDeviceToHost, st));
     if (gt) CK(cudaMemcpyAsync(gt + b * 72, dv->in[5].p, L * sizeof(Fp12), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PSB_OK;
+  });
+}
+
+static int deserialize_impl(bool g2, size_t N, const uint8_t* ser, size_t stride, uint64_t* out, uint8_t* ok) {
+  if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
+  const size_t esz = g2 ? 96 : 48, words = g2 ? 36 : 18;
+  if (!ser || !out || !ok || stride < esz) return fail(PSB_ERR_ARG, "bad argument");
+  return shard(N, [&](int di, size_t b, size_t e) -> int {
+    Dev* dv = g_devs[di];
+    std::lock_guard<std::mutex> lk(dv->mu);
+    const size_t L = e - b;
+    if (L == 0) return PSB_OK;
+    CK(cudaSetDevice(dv->ordinal));
+    cudaStream_t st = dv->stream;
+    const size_t span = (L - 1) * stride + esz;
+    Arena ar;
+    uint8_t *dser = nullptr, *dok = nullptr; uint64_t* dout = nullptr;
+    for (int pass = 0; pass < 2; pass++) {
+      ar.used = 0;
+      dser = ar.take<uint8_t>(span); dok = ar.take<uint8_t>(L); dout = ar.take<uint64_t>(L * words);
+      if (pass == 0) { int r = ensure(dv->arena, ar.used); if (r) return r; ar.base = (char*)dv->arena.p; }
+    }
+    CK(cudaMemcpyAsync(dser, ser + b * stride, span, cudaMemcpyHostToDevice, st));
+    if (g2) k_g2_deserialize<<<nblocks(L), kBlock, 0, st>>>(L, dser, stride, (G2J*)dout, dok, 0);
+    else k_g1_deserialize<<<nblocks(L), kBlock, 0, st>>>(L, dser, stride, (G1J*)dout, dok, 0);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out + b * words, dout, L * words * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ok + b, dok, L, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PSB_OK;
+  });
+}
+int psb_g1_deserialize(size_t N, const uint8_t* ser, size_t stride, uint64_t* out, uint8_t* ok) {
+  return deserialize_impl(false, N, ser, stride, out, ok);
+}
+int psb_g2_deserialize(size_t N, const uint8_t* ser, size_t stride, uint64_t* out, uint8_t* ok) {
+  return deserialize_impl(true, N, ser, stride, out, ok);
+}
+
+int psb_verify_ser(psb_key* key, size_t N, const uint8_t* cred, size_t stride, size_t off1, size_t off2,
+                   const uint8_t* attr_blob, const uint64_t* attr_off, uint8_t* verdict, uint8_t* decoded) {
+  if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
+  if (!key || !cred || !verdict || (key->n && (!attr_blob || !attr_off))) return fail(PSB_ERR_ARG, "null argument");
+  if (off1 + 48 > stride || off2 + 48 > stride) return fail(PSB_ERR_ARG, "offsets exceed the stride");
+  const size_t n = key->n;
+  return shard(N, [&](int di, size_t b, size_t e) -> int {
+    Dev* dv = g_devs[di];
+    std::lock_guard<std::mutex> lk(dv->mu);
+    const size_t L = e - b;
+    if (L == 0) return PSB_OK;
+    CK(cudaSetDevice(dv->ordinal));
+    cudaStream_t st = dv->stream;
+    const uint64_t o0 = n ? attr_off[b * n] : 0, o1 = n ? attr_off[e * n] : 0;
+    Arena ar;
+    uint8_t *dcred = nullptr, *dblob = nullptr, *dok = nullptr, *dver = nullptr; uint64_t* doff = nullptr;
+    G1J *dS1 = nullptr, *dS2 = nullptr; char* dws = nullptr;
+    for (int pass = 0; pass < 2; pass++) {
+      ar.used = 0;
+      dcred = ar.take<uint8_t>(L * stride); dS1 = ar.take<G1J>(L); dS2 = ar.take<G1J>(L);
+      dblob = ar.take<uint8_t>((size_t)(o1 - o0) + 16); doff = ar.take<uint64_t>(L * n + 1);
+      dok = ar.take<uint8_t>(L); dver = ar.take<uint8_t>(L); dws = ar.take<char>(psb_verify_ws_bytes(key, L));
+      if (pass == 0) { int r = ensure(dv->arena, ar.used); if (r) return r; ar.base = (char*)dv->arena.p; }
+    }
+    CK(cudaMemcpyAsync(dcred, cred + b * stride, L * stride, cudaMemcpyHostToDevice, st));
+    if (o1 > o0) CK(cudaMemcpyAsync(dblob, attr_blob + o0, (size_t)(o1 - o0), cudaMemcpyHostToDevice, st));
+    if (n) CK(cudaMemcpyAsync(doff, attr_off + b * n, (L * n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    k_g1_deserialize<<<nblocks(L), kBlock, 0, st>>>(L, dcred + off1, stride, dS1, dok, 0); LAUNCHED();
+    k_g1_deserialize<<<nblocks(L), kBlock, 0, st>>>(L, dcred + off2, stride, dS2, dok, 1); LAUNCHED();
+    int rc = verify_launch(key, di, L, dS1, dS2, dblob - o0, doff, nullptr, dver, nullptr, dws, st, dok);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(verdict + b, dver, L, cudaMemcpyDeviceToHost, st));
+    if (decoded) CK(cudaMemcpyAsync(decoded + b, dok, L, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return PSB_OK;
   });

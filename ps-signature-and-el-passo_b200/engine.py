@@ -56,7 +56,7 @@ def lib():
 
 EXPORTS = ["psb_init", "psb_shutdown", "psb_num_devices", "psb_last_error", "psb_shard_range", "psb_launch_count",
            "psb_key_create", "psb_key_destroy", "psb_key_num_attributes", "psb_key_table_bytes",
-           "psb_verify", "psb_verify_ws_bytes", "psb_verify_dev", "psb_randomize", "psb_provide_id",
+           "psb_verify", "psb_verify_ser", "psb_g1_deserialize", "psb_g2_deserialize", "psb_verify_ws_bytes", "psb_verify_dev", "psb_randomize", "psb_provide_id",
            "psb_verify_id", "psb_pairing", "psb_g1_mul", "psb_set_profiling", "psb_last_phase_ms", "psb_test_op_shape", "psb_test_op", "psb_microbench"]
 
 
@@ -205,6 +205,20 @@ class PSVerifier:
                                 _p(verdict), _p(gt)), "psb_verify")
         return (verdict, gt) if want_gt else verdict
 
+    def verify_serialized(self, cred, all_attributes, stride: int = 100, off1: int = 2, off2: int = 52):
+        """batched verify of SERIALIZED credentials (psb_verify_ser): cred = uint8 (N, stride); defaults are the
+        layout of PSCredential::toBufferString (src/ps-encoding.cc:384-391).  Returns (verdict, decoded)."""
+        cred = np.ascontiguousarray(cred, dtype=np.uint8).reshape(-1, stride)
+        N = cred.shape[0]
+        blob, off = _packed(all_attributes, False)
+        if off.shape[0] != N * self.m_pk.n + 1:
+            raise ValueError("attribute size does not match")
+        verdict = np.zeros(N, dtype=np.uint8)
+        decoded = np.zeros(N, dtype=np.uint8)
+        _check(lib().psb_verify_ser(self.m_pk.handle, C.c_size_t(N), _p(cred), C.c_size_t(stride), C.c_size_t(off1),
+                                    C.c_size_t(off2), _p(blob), _p(off), _p(verdict), _p(decoded)), "psb_verify_ser")
+        return verdict, decoded
+
     def el_passo_verify_id(self, proof: dict, attributes, associated_data: Sequence[bytes], service_pt,
                            authority_pk=None, g=None, h=None, with_id: bool = True):
         """batched el_passo_verify_id (src/ps-verifier.cc:37-138) / _without_id_retrieval (:140-212).
@@ -288,6 +302,27 @@ def pairing(P, Q):
     out = np.zeros((P.shape[0], GT), dtype=np.uint64)
     _check(lib().psb_pairing(C.c_size_t(P.shape[0]), _p(P), _p(Q), _p(out)), "psb_pairing")
     return out
+
+
+def g1_deserialize(ser, stride: int = 48):
+    """batched G1::deserialize (point decompression): ser uint8 (N, stride) -> (points (N,18), ok uint8[N])."""
+    ensure_init()
+    ser = np.ascontiguousarray(ser, dtype=np.uint8).reshape(-1, stride)
+    N = ser.shape[0]
+    out = np.zeros((N, G1), dtype=np.uint64)
+    ok = np.zeros(N, dtype=np.uint8)
+    _check(lib().psb_g1_deserialize(C.c_size_t(N), _p(ser), C.c_size_t(stride), _p(out), _p(ok)), "psb_g1_deserialize")
+    return out, ok
+
+
+def g2_deserialize(ser, stride: int = 96):
+    ensure_init()
+    ser = np.ascontiguousarray(ser, dtype=np.uint8).reshape(-1, stride)
+    N = ser.shape[0]
+    out = np.zeros((N, G2), dtype=np.uint64)
+    ok = np.zeros(N, dtype=np.uint8)
+    _check(lib().psb_g2_deserialize(C.c_size_t(N), _p(ser), C.c_size_t(stride), _p(out), _p(ok)), "psb_g2_deserialize")
+    return out, ok
 
 
 def g1_mul(P, k):

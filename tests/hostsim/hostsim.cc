@@ -112,4 +112,8 @@ void hostsim_verify_id(int n, int w, const uint32_t* gg, const uint32_t* XX, con
     verdict[j] = ok && fp12_is_one(e);
   }
 }
+
+// point decompression probes (csrc/protocol.cuh): returns 1 on success
+int hostsim_g1_deserialize(const uint8_t* b, uint32_t* out) { G1J P; const bool r = g1_deserialize(P, b); st(out, P); return r; }
+int hostsim_g2_deserialize(const uint8_t* b, uint32_t* out) { G2J P; const bool r = g2_deserialize(P, b); st(out, P); return r; }
 }

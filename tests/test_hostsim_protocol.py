@@ -63,3 +63,16 @@ def test_verify_id_lanes(hostsim, ref, n_attrs, n_hidden, with_id):
     assert verdict.tolist() == ev.tolist(), (nizk.tolist(), wl.tampered.tolist())
     if n_attrs != 5:
         assert ev.sum() == lanes - len(wl.tampered)
+
+
+@pytest.mark.parametrize("g2", [False, True])
+def test_point_decompression_lanes(hostsim, ref, g2):
+    enc, want, okv = workload.deserialize_cases(g2)
+    assert 0 < okv.sum() < len(okv)
+    fn = hostsim.hostsim_g2_deserialize if g2 else hostsim.hostsim_g1_deserialize
+    for j in range(len(okv)):
+        out = np.zeros(36 if g2 else 18, dtype=np.uint64)
+        r = fn(_p(enc[j]), _p(out))
+        assert r == okv[j], j
+        if okv[j]:
+            assert np.array_equal(out, want[j]), j
