@@ -112,6 +112,36 @@ public:
     return detail::verify_batch(m_key.get(), m_n, sigs, all_attributes);
   }
 
+  // batched verify straight from the WIRE form: credentials[j] = PSCredential::toBufferString() bytes (two G1 TLVs,
+  // src/ps-encoding.cc:384-401).  Points are decompressed on the GPU (psb_verify_ser); buffers that are not the
+  // canonical 100-byte layout go through the reference's own parser on the host first.  An undecodable point gives
+  // verdict 0 (the reference's parser ignores deserialize failures).
+  std::vector<uint8_t> verify(const std::vector<PSBuffer>& credentials,
+                              const std::vector<std::vector<std::string>>& all_attributes) const {
+    using namespace mcl::bls12;
+    const size_t N = credentials.size();
+    if (all_attributes.size() != N) throw std::runtime_error("attribute size does not match");
+    std::vector<uint8_t> flat(N * 96 + 1), verdict(N);
+    detail::Strings at;
+    for (size_t j = 0; j < N; j++) {
+      if (all_attributes[j].size() != m_n) throw std::runtime_error("attribute size does not match");
+      const PSBuffer& b = credentials[j];
+      if (b.size() == 100 && b[0] == 1 && b[1] == 48 && b[50] == 1 && b[51] == 48) {
+        std::memcpy(&flat[96 * j], &b[2], 48);
+        std::memcpy(&flat[96 * j + 48], &b[52], 48);
+      } else {
+        PSCredential c = PSCredential::fromBufferString(b);
+        c.sig1.serialize(&flat[96 * j], 48);
+        c.sig2.serialize(&flat[96 * j + 48], 48);
+      }
+      for (const auto& a : all_attributes[j]) at.add(a);
+    }
+    if (N == 0) return verdict;
+    check(psb_verify_ser(m_key.get(), N, flat.data(), 96, 0, 48, at.data(), at.off.data(), verdict.data(), nullptr),
+          "psb_verify_ser");
+    return verdict;
+  }
+
   // batched el_passo_verify_id (src/ps-verifier.cc:37-138); one associated_data per proof
   std::vector<uint8_t> el_passo_verify_id(const std::vector<IdProof>& proofs, const std::vector<std::string>& associated_data,
                                           const std::string& service_name, const mcl::bls12::G1& authority_pk,

@@ -55,7 +55,7 @@ def main():
     ap.add_argument("--lanes50", type=int, default=1 << 18)
     ap.add_argument("--distinct", type=int, default=1 << 12)
     ap.add_argument("--reps", type=int, default=2)
-    ap.add_argument("--configs", default="3,4,5")
+    ap.add_argument("--configs", default="3,4,5,w")
     ap.add_argument("--window-bits", type=int, default=16)
     args = ap.parse_args()
     pkg = ge.load_package()
@@ -124,6 +124,31 @@ def main():
               "e2e_value": N / dt, "seconds": dt, "gpu_launches": pkg.launch_count() - l0,
               "cpu_reference": {"value": D / cpu_s, "cores": threads, "sample": f"{D} lanes"},
               "parity": "serialized credentials byte-identical to t*sigma via mcl"}, fh)
+        pk.close()
+
+    if "w" in cfgs:   # cfg2 from the wire: serialized credentials (100-byte TLV), decompressed on the device
+        D2 = min(1 << 14, N)
+        wl = workload.make_verify_workload(n_attrs=5, lanes=D2, seed=2, tamper_every=64)
+        buf = ref.cred_encode(wl.sig1, wl.sig2)
+        t0 = time.perf_counter()
+        s1, s2 = ref.cred_decode(buf)          # the reference's parser: 2 x G1::deserialize per credential, one thread
+        dec_s = time.perf_counter() - t0
+        ev = workload.expected_verify(wl, nthreads=threads)
+        pk = pkg.PSPubKey(wl.key.g, wl.key.gg, wl.key.XX, wl.key.Y, wl.key.YY, window_bits=args.window_bits)
+        r2 = N // D2
+        big = np.ascontiguousarray(np.tile(buf, (r2, 1)))
+        battrs = pkg.pack_attrs(wl.attrs * r2)
+        ver = pkg.PSVerifier(pk)
+        ver.verify_serialized(big, battrs)
+        l0 = pkg.launch_count()
+        (got, dec), dt = timed(lambda: ver.verify_serialized(big, battrs), args.reps)
+        assert dec.all() and np.array_equal(got, np.tile(ev, r2)), "verify_serialized verdict mismatch vs reference"
+        emit({"config": "cfg2-wire ps_verify from serialized credentials", "n_attrs": 5, "lanes": N, "distinct": D2,
+              "metric": "ps_verifications_per_sec", "e2e_value": N / dt, "seconds": dt, "h2d_bytes_per_lane": 100,
+              "gpu_launches": pkg.launch_count() - l0,
+              "cpu_reference": {"deserialize_credentials_per_sec_one_thread": D2 / dec_s,
+                                "note": "PSCredential::fromBufferString = 2 G1::deserialize (mcl, host)"},
+              "parity": "verdicts identical to fromBufferString + PSVerifier::verify on all distinct lanes"}, fh)
         pk.close()
 
     if "5" in cfgs:

@@ -89,6 +89,14 @@ int main(int argc, char** argv) {
     EXPECT(want == (v1[j] != 0) && want == (v2[j] != 0));
   }
 
+  // the same credentials in wire form (PSCredential::toBufferString), decompressed on the GPU
+  {
+    std::vector<PSBuffer> wire;
+    for (auto& c : vc) wire.push_back(c.toBufferString());
+    std::vector<uint8_t> v3 = rp.verify(wire, plain);
+    for (size_t j = 0; j < N; j++) EXPECT(v3[j] == v1[j]);
+  }
+
   // batched randomize_credential with host-supplied t vs t * sigma on the host
   std::vector<Fr> t(N);
   for (auto& x : t) x.setByCSPRNG();
