@@ -125,6 +125,31 @@ int psb_verify_id(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* 
                   const uint64_t* service_pt, const uint64_t* y, const uint64_t* g, const uint64_t* h,
                   int with_id, uint8_t* verdict);
 
+/* ---- prover side.  The reference draws its blinding / commitment scalars from mcl's CSPRNG;
+ * the batch entries take them from the host, per lane, IN THE REFERENCE'S DRAW ORDER, so the same scalars reproduce the
+ * reference's requests and proofs byte for byte.  hide = n flags shared by the batch (1 = attribute hidden), h = their
+ * sum.  All attribute strings (hidden ones included) are given: the prover knows them.  Outputs are normalised. ---- */
+
+/* Batched PSRequester::el_passo_request_id (src/ps-requester.cc:19-97).  rnd: N x (h + 2) Fr = t1 (the blinding the
+ * requester keeps for psb_unblind), the commitment randomness of g, one per hidden attribute.
+ * Out: A (N G1), c (N Fr), rs (N x (h + 1) Fr); the request's attribute list is the input with hidden entries emptied. */
+int psb_request_id(psb_key* key, size_t N, const uint8_t* attr_blob, const uint64_t* attr_off, const uint8_t* hide,
+                   const uint8_t* ad_blob, const uint64_t* ad_off, const uint64_t* rnd, uint64_t* A, uint64_t* c,
+                   uint64_t* rs);
+
+/* Batched PSRequester::unblind_credential (src/ps-requester.cc:99-113): out2 = sig2 - t1 * sig1 (sig1 is unchanged). */
+int psb_unblind(size_t N, const uint64_t* sig1, const uint64_t* sig2, const uint64_t* t1, uint64_t* out2);
+
+/* Batched PSRequester::el_passo_prove_id (src/ps-requester.cc:150-310; with_id = 1) and
+ * el_passo_prove_id_without_id_retrieval (:312-432; with_id = 0, y/g/h/E1/E2 ignored).
+ * rnd per lane: with_id: t, r, epsilon, hid_0..hid_{h-1}, random2, random3 (h + 5); else t, r, hid.., random2 (h + 3).
+ * Out: the IdProof fields sig1, sig2, k (G2), phi, E1, E2, c, rs (N x (h + 2) or (h + 1) Fr). */
+int psb_prove_id(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* sig2, const uint8_t* attr_blob,
+                 const uint64_t* attr_off, const uint8_t* hide, const uint8_t* ad_blob, const uint64_t* ad_off,
+                 const uint64_t* service_pt, const uint64_t* y, const uint64_t* g, const uint64_t* h, int with_id,
+                 const uint64_t* rnd, uint64_t* o_sig1, uint64_t* o_sig2, uint64_t* o_k, uint64_t* o_phi, uint64_t* o_E1,
+                 uint64_t* o_E2, uint64_t* o_c, uint64_t* o_rs);
+
 /* Batched mcl::bn::pairing (bn.hpp:1711-1715): out[j] = e(P[j], Q[j]), N x 72 u64. */
 int psb_pairing(size_t N, const uint64_t* P, const uint64_t* Q, uint64_t* out);
 

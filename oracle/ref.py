@@ -394,6 +394,30 @@ def request_id(key, attrs, hidden, ads, seed_, nthreads=1):
     return A, c, rs
 
 
+def lane_draws(seed_, lanes, count):
+    """the first `count` Fr::setByCSPRNG draws of each lane's stream (seed_ + lane): exactly the scalars the
+    reference's prover methods consume under ref_seed(seed_ + lane), in draw order -> (lanes, count, 4)."""
+    out = np.empty((lanes, count, FR), dtype=np.uint64)
+    for j in range(lanes):
+        seed(seed_ + j)
+        out[j] = fr_rand(count)
+    return out
+
+
+def unblind(key, attrs, hidden, ads, seed_, sig1, sig2, nthreads=1):
+    """replays el_passo_request_id under (seed_ + lane) to set m_t1, then the real unblind_credential."""
+    N = len(attrs)
+    blob, off = pack_attrs(attrs)
+    ad_blob, ad_off = pack_strings(ads)
+    hidden = np.ascontiguousarray(hidden, dtype=np.uint8)
+    o1 = np.empty((N, G1), dtype=np.uint64)
+    o2 = np.empty((N, G1), dtype=np.uint64)
+    lib().ref_unblind(key.handle, C.c_size_t(N), C.c_size_t(key.n), _p(blob), _p(off), _p(hidden), _p(ad_blob),
+                      _p(ad_off), C.c_uint64(seed_), _p(_u64(sig1)), _p(_u64(sig2)), _p(o1), _p(o2),
+                      C.c_int(nthreads))
+    return o1, o2
+
+
 def provide_id(key, A, c, rs, attrs, ads, u, nthreads=1):
     """attrs here are the REQUEST's attribute lists (b"" for hidden)."""
     N = A.shape[0]

@@ -398,6 +398,27 @@ void ref_request_id(void* key, size_t N, size_t n, const uint8_t* blob, const u6
   });
 }
 
+// PSRequester::unblind_credential (src/ps-requester.cc:99-113) uses the private blinding m_t1 that
+// el_passo_request_id drew: the request is replayed under the same per-lane seed on the same
+// PSRequester object, then the real unblind_credential is called on (sig1, sig2).
+void ref_unblind(void* key, size_t N, size_t n, const uint8_t* blob, const u64* off, const uint8_t* hidden,
+                 const uint8_t* ad_blob, const u64* ad_off, u64 seed, const G1* sig1, const G1* sig2,
+                 G1* o_sig1, G1* o_sig2, int nthreads) {
+  RefKey* k = (RefKey*)key;
+  par_for(N, nthreads, [&](size_t i, int) {
+    PSRequester u(k->pk);
+    std::vector<std::string> a = lane_attrs(blob, off, i, n);
+    std::vector<std::tuple<std::string, bool>> attrs;
+    for (size_t j = 0; j < n; j++) attrs.push_back(std::make_tuple(a[j], hidden[j] != 0));
+    std::string ad((const char*)ad_blob + ad_off[i], (size_t)(ad_off[i + 1] - ad_off[i]));
+    ref_seed(seed + i);
+    (void)u.el_passo_request_id(attrs, ad);
+    PSCredential c; c.sig1 = sig1[i]; c.sig2 = sig2[i];
+    PSCredential r = u.unblind_credential(c);
+    o_sig1[i] = r.sig1; o_sig2[i] = r.sig2;
+  });
+}
+
 // el_passo_provide_id on every lane with the u_i the caller supplies: the RandGen stream is
 // primed so that the reference's `u.setByCSPRNG()` (src/ps-signer.cc:135-136) yields exactly u_i.
 // setByCSPRNG reads 32 raw bytes and applies the SmallMask rule; feeding the little-endian bytes

@@ -9,6 +9,7 @@
 #pragma once
 #include "testops.cuh"
 #include "protocol.cuh"
+#include "prover.cuh"
 
 namespace psb {
 
@@ -392,6 +393,69 @@ __global__ void __launch_bounds__(kBlock) k_vid_hash(size_t N, const G2J* k, con
                                      Vk[lane], V[3 * lane], V[3 * lane + 1], V[3 * lane + 2], with_id, c + lane,
                                      ad_blob + ad_off[lane], (size_t)(ad_off[lane + 1] - ad_off[lane]));
   ok[lane] = r ? 1 : 0;
+}
+
+// ---- prover side: PSRequester::el_passo_request_id / unblind_credential / el_passo_prove_id ----
+// hide: n flags shared by the batch; rnd: `per` host-supplied scalars per lane in the reference's draw order (prover.cuh)
+__global__ void __launch_bounds__(kBlock) k_request_id(size_t N, int n, int w, const G1A* tblG1, const uint8_t* hide, int h,
+                                                        const uint8_t* blob, const uint64_t* off, const uint8_t* ad_blob,
+                                                        const uint64_t* ad_off, const Fr* rnd, G1J* A, Fr* c, Fr* rs) {
+  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= N) return;
+  G1J a;
+  Fr cc;
+  request_id_lane(n, TblGeom{w}, tblG1, hide, blob, off + lane * n, ad_blob + ad_off[lane],
+                  (size_t)(ad_off[lane + 1] - ad_off[lane]), rnd + lane * (h + 2), a, cc, rs + lane * (h + 1));
+  A[lane] = a;
+  c[lane] = cc;
+}
+__global__ void __launch_bounds__(kBlock) k_unblind(size_t N, const G1J* sig1, const G1J* sig2, const Fr* t1, G1J* out2) {
+  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= N) return;
+  G1J r;
+  unblind_lane(r, sig1[lane], sig2[lane], t1 + lane);
+  out2[lane] = r;
+}
+__global__ void __launch_bounds__(kBlock) k_pid_g2(size_t N, int n, int w, const G2A* tblYY, const G2A* tblAux, const G2J* XX,
+                                                    const uint8_t* hide, int h, int with_id, const uint8_t* blob,
+                                                    const uint64_t* off, const Fr* rnd, G2J* k, G2J* Vk) {
+  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= N) return;
+  G2J a, b;
+  prove_id_g2_lane(n, TblGeom{w}, tblYY, tblAux, *XX, hide, blob, off + lane * n, rnd + lane * prove_rnd_per_lane(h, with_id), h,
+                   with_id, a, b);
+  k[lane] = a;
+  Vk[lane] = b;
+}
+__global__ void __launch_bounds__(kBlock) k_pid_g1(size_t N, int n, int wb, const G1A* tblB, const G1J* sig1, const G1J* sig2,
+                                                    const uint8_t* blob, const uint64_t* off, const Fr* rnd, int h, int with_id,
+                                                    G1J* o_sig1, G1J* o_sig2, G1J* W /*6 per lane*/) {
+  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= N) return;
+  G1J s1, s2, w6[6];
+  prove_id_g1_lane(TblGeom{wb}, tblB, sig1[lane], sig2[lane], blob, off + lane * n, rnd + lane * prove_rnd_per_lane(h, with_id), h,
+                   with_id, s1, s2, w6);
+  o_sig1[lane] = s1;
+  o_sig2[lane] = s2;
+  for (int i = 0; i < 6; i++) W[6 * lane + i] = w6[i];
+}
+__global__ void __launch_bounds__(kBlock) k_pid_hash(size_t N, int n, const uint8_t* hide, int h, int with_id, const uint8_t* blob,
+                                                      const uint64_t* off, const uint8_t* ad_blob, const uint64_t* ad_off,
+                                                      const Fr* rnd, G2J* k, const G2J* Vk, const G1J* W, G1J* phi, G1J* E1,
+                                                      G1J* E2, Fr* c, Fr* rs) {
+  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= N) return;
+  G2J kk = k[lane];
+  G1J w6[6];
+  for (int i = 0; i < 6; i++) w6[i] = W[6 * lane + i];
+  Fr cc;
+  const int per = h + (with_id ? 2 : 1);
+  prove_id_hash_lane(n, hide, blob, off + lane * n, ad_blob + ad_off[lane], (size_t)(ad_off[lane + 1] - ad_off[lane]),
+                     rnd + lane * prove_rnd_per_lane(h, with_id), h, with_id, kk, Vk[lane], w6, cc, rs + lane * per);
+  k[lane] = kk;
+  phi[lane] = w6[0];
+  if (with_id) { E1[lane] = w6[2]; E2[lane] = w6[3]; }
+  c[lane] = cc;
 }
 
 }  // namespace psb

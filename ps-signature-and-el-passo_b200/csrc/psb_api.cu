@@ -787,4 +787,158 @@ int psb_verify_id(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* 
   });
 }
 
+// ---- prover side -----------------------------------------------------------------------------
+static size_t count_hidden(const uint8_t* hide, size_t n) {
+  size_t h = 0;
+  for (size_t i = 0; i < n; i++) h += hide[i] ? 1 : 0;
+  return h;
+}
+
+int psb_request_id(psb_key* key, size_t N, const uint8_t* attr_blob, const uint64_t* attr_off, const uint8_t* hide,
+                   const uint8_t* ad_blob, const uint64_t* ad_off, const uint64_t* rnd, uint64_t* A, uint64_t* c,
+                   uint64_t* rs) {
+  if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
+  if (!key || !attr_blob || !attr_off || (key->n && !hide) || !ad_blob || !ad_off || !rnd || !A || !c || !rs)
+    return fail(PSB_ERR_ARG, "null argument");
+  int rc = ensure_issuer_tables(key);
+  if (rc) return rc;
+  const size_t n = key->n, h = count_hidden(hide, n);
+  return shard(N, [&](int di, size_t b, size_t e) -> int {
+    Dev* dv = g_devs[di];
+    std::lock_guard<std::mutex> lk(dv->mu);
+    const size_t L = e - b;
+    if (L == 0) return PSB_OK;
+    CK(cudaSetDevice(dv->ordinal));
+    cudaStream_t st = dv->stream;
+    const uint64_t o0 = attr_off[b * n], o1 = attr_off[e * n], a0 = ad_off[b], a1 = ad_off[e];
+    Arena ar;
+    G1J* dA = nullptr; Fr *dc = nullptr, *drs = nullptr, *drnd = nullptr;
+    uint8_t *dblob = nullptr, *dad = nullptr, *dhide = nullptr; uint64_t *doff = nullptr, *dadoff = nullptr;
+    for (int pass = 0; pass < 2; pass++) {
+      ar.used = 0;
+      dA = ar.take<G1J>(L); dc = ar.take<Fr>(L); drs = ar.take<Fr>(L * (h + 1)); drnd = ar.take<Fr>(L * (h + 2));
+      dblob = ar.take<uint8_t>((size_t)(o1 - o0) + 16); doff = ar.take<uint64_t>(L * n + 1);
+      dad = ar.take<uint8_t>((size_t)(a1 - a0) + 16); dadoff = ar.take<uint64_t>(L + 1); dhide = ar.take<uint8_t>(n + 16);
+      if (pass == 0) { int r = ensure(dv->arena, ar.used); if (r) return r; ar.base = (char*)dv->arena.p; }
+    }
+    CK(cudaMemcpyAsync(drnd, rnd + b * (h + 2) * 4, L * (h + 2) * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    if (o1 > o0) CK(cudaMemcpyAsync(dblob, attr_blob + o0, (size_t)(o1 - o0), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(doff, attr_off + b * n, (L * n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    if (a1 > a0) CK(cudaMemcpyAsync(dad, ad_blob + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dadoff, ad_off + b, (L + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    if (n) CK(cudaMemcpyAsync(dhide, hide, n, cudaMemcpyHostToDevice, st));
+    const KeyDev& kd = key->d[di];
+    k_request_id<<<nblocks(L), kBlock, 0, st>>>(L, (int)n, key->w, kd.tblG1, dhide, (int)h, dblob - o0, doff, dad - a0, dadoff,
+                                                drnd, dA, dc, drs);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(A + b * 18, dA, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(c + b * 4, dc, L * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(rs + b * (h + 1) * 4, drs, L * (h + 1) * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PSB_OK;
+  });
+}
+
+int psb_unblind(size_t N, const uint64_t* sig1, const uint64_t* sig2, const uint64_t* t1, uint64_t* out2) {
+  if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
+  if (!sig1 || !sig2 || !t1 || !out2) return fail(PSB_ERR_ARG, "null argument");
+  return shard(N, [&](int di, size_t b, size_t e) -> int {
+    Dev* dv = g_devs[di];
+    std::lock_guard<std::mutex> lk(dv->mu);
+    const size_t L = e - b;
+    if (L == 0) return PSB_OK;
+    CK(cudaSetDevice(dv->ordinal));
+    cudaStream_t st = dv->stream;
+    int rc;
+    for (int i = 0; i < 2; i++) if ((rc = ensure(dv->in[i], L * sizeof(G1J)))) return rc;
+    if ((rc = ensure(dv->in[2], L * sizeof(Fr)))) return rc;
+    if ((rc = ensure(dv->in[3], L * sizeof(G1J)))) return rc;
+    CK(cudaMemcpyAsync(dv->in[0].p, sig1 + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dv->in[1].p, sig2 + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dv->in[2].p, t1 + b * 4, L * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    k_unblind<<<nblocks(L), kBlock, 0, st>>>(L, (const G1J*)dv->in[0].p, (const G1J*)dv->in[1].p, (const Fr*)dv->in[2].p,
+                                             (G1J*)dv->in[3].p);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out2 + b * 18, dv->in[3].p, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PSB_OK;
+  });
+}
+
+int psb_prove_id(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* sig2, const uint8_t* attr_blob,
+                 const uint64_t* attr_off, const uint8_t* hide, const uint8_t* ad_blob, const uint64_t* ad_off,
+                 const uint64_t* service_pt, const uint64_t* y, const uint64_t* g, const uint64_t* h_pt, int with_id,
+                 const uint64_t* rnd, uint64_t* o_sig1, uint64_t* o_sig2, uint64_t* o_k, uint64_t* o_phi, uint64_t* o_E1,
+                 uint64_t* o_E2, uint64_t* o_c, uint64_t* o_rs) {
+  if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
+  if (!key || !sig1 || !sig2 || !attr_blob || !attr_off || !hide || !ad_blob || !ad_off || !service_pt || !rnd || !o_sig1 ||
+      !o_sig2 || !o_k || !o_phi || !o_c || !o_rs)
+    return fail(PSB_ERR_ARG, "null argument");
+  if (with_id && (!y || !g || !h_pt || !o_E1 || !o_E2)) return fail(PSB_ERR_ARG, "y/g/h/E1/E2 are required with id retrieval");
+  // the reference reads attributes[0] (and attributes[1] with id retrieval) unconditionally: ps-requester.cc:173,185
+  if (key->n < (with_id ? 2u : 1u)) return fail(PSB_ERR_ARG, "the proof needs attribute 0 (and attribute 1 with id retrieval)");
+  int rc = ensure_verifier_tables(key);
+  if (rc) return rc;
+  std::shared_ptr<BatchTbl> bt;
+  const uint64_t* const pts[4] = {service_pt, g, y, h_pt};
+  if ((rc = get_batch_tables(key, pts, with_id ? 4 : 1, bt))) return rc;
+  const size_t n = key->n, h = count_hidden(hide, n);
+  const size_t rper = h + (with_id ? 5 : 3), per = h + (with_id ? 2 : 1);
+  return shard(N, [&](int di, size_t b, size_t e) -> int {
+    Dev* dv = g_devs[di];
+    std::lock_guard<std::mutex> lk(dv->mu);
+    const size_t L = e - b;
+    if (L == 0) return PSB_OK;
+    CK(cudaSetDevice(dv->ordinal));
+    cudaStream_t st = dv->stream;
+    const uint64_t o0 = attr_off[b * n], o1 = attr_off[e * n], a0 = ad_off[b], a1 = ad_off[e];
+    Arena ar;
+    G1J *dS1 = nullptr, *dS2 = nullptr, *dO1 = nullptr, *dO2 = nullptr, *dW = nullptr, *dphi = nullptr, *dE1 = nullptr, *dE2 = nullptr;
+    G2J *dk = nullptr, *dVk = nullptr; Fr *dc = nullptr, *drs = nullptr, *drnd = nullptr;
+    uint8_t *dblob = nullptr, *dad = nullptr, *dhide = nullptr; uint64_t *doff = nullptr, *dadoff = nullptr;
+    for (int pass = 0; pass < 2; pass++) {
+      ar.used = 0;
+      dS1 = ar.take<G1J>(L); dS2 = ar.take<G1J>(L); dO1 = ar.take<G1J>(L); dO2 = ar.take<G1J>(L); dW = ar.take<G1J>(6 * L);
+      dphi = ar.take<G1J>(L); dE1 = ar.take<G1J>(L); dE2 = ar.take<G1J>(L); dk = ar.take<G2J>(L); dVk = ar.take<G2J>(L);
+      dc = ar.take<Fr>(L); drs = ar.take<Fr>(L * per); drnd = ar.take<Fr>(L * rper);
+      dblob = ar.take<uint8_t>((size_t)(o1 - o0) + 16); doff = ar.take<uint64_t>(L * n + 1);
+      dad = ar.take<uint8_t>((size_t)(a1 - a0) + 16); dadoff = ar.take<uint64_t>(L + 1); dhide = ar.take<uint8_t>(n + 16);
+      if (pass == 0) { int r = ensure(dv->arena, ar.used); if (r) return r; ar.base = (char*)dv->arena.p; }
+    }
+    CK(cudaMemcpyAsync(dS1, sig1 + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dS2, sig2 + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(drnd, rnd + b * rper * 4, L * rper * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    if (o1 > o0) CK(cudaMemcpyAsync(dblob, attr_blob + o0, (size_t)(o1 - o0), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(doff, attr_off + b * n, (L * n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    if (a1 > a0) CK(cudaMemcpyAsync(dad, ad_blob + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dadoff, ad_off + b, (L + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dhide, hide, n, cudaMemcpyHostToDevice, st));
+    const KeyDev& kd = key->d[di];
+    k_pid_g2<<<nblocks(L), kBlock, 0, st>>>(L, (int)n, key->w, kd.tblYY, kd.tblAux, kd.g2pts + 1, dhide, (int)h, with_id, dblob - o0,
+                                            doff, drnd, dk, dVk);
+    LAUNCHED();
+    k_pid_g1<<<nblocks(L), kBlock, 0, st>>>(L, (int)n, kBatchW, bt->tbl[di], dS1, dS2, dblob - o0, doff, drnd, (int)h, with_id, dO1,
+                                            dO2, dW);
+    LAUNCHED();
+    k_pid_hash<<<nblocks(L), kBlock, 0, st>>>(L, (int)n, dhide, (int)h, with_id, dblob - o0, doff, dad - a0, dadoff, drnd, dk, dVk,
+                                              dW, dphi, dE1, dE2, dc, drs);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(o_sig1 + b * 18, dO1, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(o_sig2 + b * 18, dO2, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(o_k + b * 36, dk, L * sizeof(G2J), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(o_phi + b * 18, dphi, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+    if (with_id) {
+      CK(cudaMemcpyAsync(o_E1 + b * 18, dE1, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(o_E2 + b * 18, dE2, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaMemcpyAsync(o_c + b * 4, dc, L * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(o_rs + b * per * 4, drs, L * per * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PSB_OK;
+  });
+}
+
 }  // extern "C"

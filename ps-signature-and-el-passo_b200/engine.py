@@ -57,7 +57,7 @@ def lib():
 EXPORTS = ["psb_init", "psb_shutdown", "psb_num_devices", "psb_last_error", "psb_shard_range", "psb_launch_count",
            "psb_key_create", "psb_key_destroy", "psb_key_num_attributes", "psb_key_table_bytes",
            "psb_verify", "psb_verify_ser", "psb_g1_deserialize", "psb_g2_deserialize", "psb_verify_ws_bytes", "psb_verify_dev", "psb_randomize", "psb_provide_id",
-           "psb_verify_id", "psb_pairing", "psb_g1_mul", "psb_set_profiling", "psb_last_phase_ms", "psb_test_op_shape", "psb_test_op", "psb_microbench"]
+           "psb_verify_id", "psb_request_id", "psb_unblind", "psb_prove_id", "psb_pairing", "psb_g1_mul", "psb_set_profiling", "psb_last_phase_ms", "psb_test_op_shape", "psb_test_op", "psb_microbench"]
 
 
 def _check(rc: int, what: str):
@@ -244,7 +244,8 @@ class PSVerifier:
 
 
 class PSRequester:
-    """batched PSRequester (src/ps-requester.h:11-128): verify and randomize_credential."""
+    """batched PSRequester (src/ps-requester.h:11-128): verify, randomize_credential and the prover side
+    (el_passo_request_id, unblind_credential, el_passo_prove_id) with host-supplied scalars."""
 
     def __init__(self, pk: PSPubKey):
         self.m_pk = pk
@@ -266,6 +267,66 @@ class PSRequester:
         _check(lib().psb_randomize(C.c_size_t(N), _p(s1), _p(s2), _p(tt), _p(o1), _p(o2), _p(ser)),
                "psb_randomize")
         return (o1, o2, ser) if want_serialized else (o1, o2)
+
+    def el_passo_request_id(self, attributes, hidden, associated_data, rnd):
+        """batched el_passo_request_id (src/ps-requester.cc:19-97).  attributes: per lane ALL n values; hidden: n flags
+        shared by the batch; rnd (N, h+2, 4) = t1, r0, one per hidden attribute (the reference's draw order).
+        Returns A (N,18) normalised, c (N,4), rs (N,h+1,4)."""
+        pk = self.m_pk
+        hidden = np.ascontiguousarray(hidden, dtype=np.uint8)
+        if hidden.shape != (pk.n,):
+            raise ValueError("attribute size does not match")
+        h = int((hidden != 0).sum())
+        blob, off = _packed(attributes, False)
+        ad_blob, ad_off = _packed(associated_data, True)
+        N = ad_off.shape[0] - 1
+        if off.shape[0] != N * pk.n + 1:
+            raise ValueError("attribute size does not match")
+        rnd = np.ascontiguousarray(rnd, dtype=np.uint64).reshape(N, h + 2, FR)
+        A = np.zeros((N, G1), dtype=np.uint64)
+        c = np.zeros((N, FR), dtype=np.uint64)
+        rs = np.zeros((N, h + 1, FR), dtype=np.uint64)
+        _check(lib().psb_request_id(pk.handle, C.c_size_t(N), _p(blob), _p(off), _p(hidden), _p(ad_blob), _p(ad_off),
+                                    _p(rnd), _p(A), _p(c), _p(rs)), "psb_request_id")
+        return A, c, rs
+
+    @staticmethod
+    def unblind_credential(sig1, sig2, t1):
+        """batched unblind_credential (src/ps-requester.cc:99-113): (sig1, sig2 - t1 sig1); sig2 normalised."""
+        ensure_init()
+        s1 = _u64(sig1, G1)
+        s2 = _u64(sig2, G1)
+        N = s1.shape[0]
+        o2 = np.zeros((N, G1), dtype=np.uint64)
+        _check(lib().psb_unblind(C.c_size_t(N), _p(s1), _p(s2), _p(_u64(t1, FR)), _p(o2)), "psb_unblind")
+        return s1, o2
+
+    def el_passo_prove_id(self, sig1, sig2, attributes, hidden, associated_data, service_pt, authority_pk=None, g=None,
+                          h=None, rnd=None, with_id: bool = True):
+        """batched el_passo_prove_id (src/ps-requester.cc:150-310) / _without_id_retrieval (:312-432).
+        rnd (N, h+5 | h+3, 4) in the reference's draw order (include/psb.h).  Returns the IdProof fields as a dict."""
+        pk = self.m_pk
+        hidden = np.ascontiguousarray(hidden, dtype=np.uint8)
+        if hidden.shape != (pk.n,):
+            raise ValueError("attribute size does not match")
+        hh = int((hidden != 0).sum())
+        s1 = _u64(sig1, G1)
+        N = s1.shape[0]
+        blob, off = _packed(attributes, False)
+        ad_blob, ad_off = _packed(associated_data, True)
+        if off.shape[0] != N * pk.n + 1 or ad_off.shape[0] != N + 1:
+            raise ValueError("attribute size does not match")
+        rnd = np.ascontiguousarray(rnd, dtype=np.uint64).reshape(N, hh + (5 if with_id else 3), FR)
+        per = hh + (2 if with_id else 1)
+        o = dict(sig1=np.zeros((N, G1), np.uint64), sig2=np.zeros((N, G1), np.uint64), k=np.zeros((N, G2), np.uint64),
+                 phi=np.zeros((N, G1), np.uint64), E1=np.zeros((N, G1), np.uint64), E2=np.zeros((N, G1), np.uint64),
+                 c=np.zeros((N, FR), np.uint64), rs=np.zeros((N, per, FR), np.uint64))
+        _check(lib().psb_prove_id(
+            pk.handle, C.c_size_t(N), _p(s1), _p(_u64(sig2, G1)), _p(blob), _p(off), _p(hidden), _p(ad_blob), _p(ad_off),
+            _p(_u64(service_pt, G1)), _p(_u64(authority_pk, G1)) if with_id else None, _p(_u64(g, G1)) if with_id else None,
+            _p(_u64(h, G1)) if with_id else None, C.c_int(int(with_id)), _p(rnd), _p(o["sig1"]), _p(o["sig2"]), _p(o["k"]),
+            _p(o["phi"]), _p(o["E1"]), _p(o["E2"]), _p(o["c"]), _p(o["rs"])), "psb_prove_id")
+        return o
 
 
 class PSSigner:

@@ -20,7 +20,7 @@ void hostsim_set_hash_of(const uint8_t* msg, size_t len, uint32_t* k) { psb::fr_
 
 // ---- protocol lane functions (csrc/protocol.cuh) on the host: table building + one lane at a time ------
 #include <vector>
-#include "../../ps-signature-and-el-passo_b200/csrc/protocol.cuh"
+#include "../../ps-signature-and-el-passo_b200/csrc/prover.cuh"
 namespace {
 using namespace psb;
 // same table geometry as k_window_bases / k_build_table: entry (win, d) = d * 2^(w win) * B, affine
@@ -116,4 +116,53 @@ void hostsim_verify_id(int n, int w, const uint32_t* gg, const uint32_t* XX, con
 // point decompression probes (csrc/protocol.cuh): returns 1 on success
 int hostsim_g1_deserialize(const uint8_t* b, uint32_t* out) { G1J P; const bool r = g1_deserialize(P, b); st(out, P); return r; }
 int hostsim_g2_deserialize(const uint8_t* b, uint32_t* out) { G2J P; const bool r = g2_deserialize(P, b); st(out, P); return r; }
+// ---- prover side (csrc/prover.cuh) ------------------------------------------------------------------------
+void hostsim_request_id(int n, int w, const uint32_t* g, const uint32_t* Y, size_t N, const uint8_t* hide, const uint8_t* blob,
+                        const uint64_t* off, const uint8_t* ad_blob, const uint64_t* ad_off, const uint32_t* rnd, uint32_t* A,
+                        uint32_t* c, uint32_t* rs) {
+  std::vector<G1A> tbl;
+  G1J b; ld(b, g); host_table(tbl, b, w);
+  for (int i = 0; i < n; i++) { ld(b, Y + 36 * i); host_table(tbl, b, w); }
+  int h = 0; for (int i = 0; i < n; i++) h += hide[i] ? 1 : 0;
+  for (size_t j = 0; j < N; j++) {
+    G1J a; Fr cc;
+    request_id_lane(n, TblGeom{w}, tbl.data(), hide, blob, off + j * n, ad_blob + ad_off[j], (size_t)(ad_off[j + 1] - ad_off[j]),
+                    (const Fr*)(rnd + 8 * (h + 2) * j), a, cc, (Fr*)(rs + 8 * (h + 1) * j));
+    st(A + 36 * j, a); st(c + 8 * j, cc);
+  }
+}
+void hostsim_unblind(size_t N, const uint32_t* sig1, const uint32_t* sig2, const uint32_t* t1, uint32_t* out2) {
+  for (size_t j = 0; j < N; j++) {
+    G1J a, b, r; ld(a, sig1 + 36 * j); ld(b, sig2 + 36 * j);
+    unblind_lane(r, a, b, (const Fr*)(t1 + 8 * j));
+    st(out2 + 36 * j, r);
+  }
+}
+void hostsim_prove_id(int n, int w, const uint32_t* gg, const uint32_t* XX, const uint32_t* YY, size_t N, const uint32_t* sig1,
+                      const uint32_t* sig2, const uint8_t* hide, const uint8_t* blob, const uint64_t* off, const uint8_t* ad_blob,
+                      const uint64_t* ad_off, const uint32_t* service_pt, const uint32_t* y, const uint32_t* g, const uint32_t* h_pt,
+                      int with_id, const uint32_t* rnd, uint32_t* o_sig1, uint32_t* o_sig2, uint32_t* o_k, uint32_t* o_phi,
+                      uint32_t* o_E1, uint32_t* o_E2, uint32_t* o_c, uint32_t* o_rs) {
+  std::vector<G2A> tYY, tAux;
+  std::vector<G1A> tB;
+  G2J b2, XXj; G1J b1;
+  for (int i = 0; i < n; i++) { ld(b2, YY + 72 * i); host_table(tYY, b2, w); }
+  ld(b2, gg); host_table(tAux, b2, w);
+  ld(XXj, XX); host_table(tAux, XXj, w);
+  ld(b1, service_pt); host_table(tB, b1, w);
+  if (with_id) { ld(b1, g); host_table(tB, b1, w); ld(b1, y); host_table(tB, b1, w); ld(b1, h_pt); host_table(tB, b1, w); }
+  int h = 0; for (int i = 0; i < n; i++) h += hide[i] ? 1 : 0;
+  const int rper = prove_rnd_per_lane(h, with_id), per = h + (with_id ? 2 : 1);
+  for (size_t j = 0; j < N; j++) {
+    const Fr* rj = (const Fr*)(rnd + 8 * rper * j);
+    G2J k, Vk; G1J s1, s2, o1, o2, W[6]; Fr cc;
+    ld(s1, sig1 + 36 * j); ld(s2, sig2 + 36 * j);
+    prove_id_g2_lane(n, TblGeom{w}, tYY.data(), tAux.data(), XXj, hide, blob, off + j * n, rj, h, with_id, k, Vk);
+    prove_id_g1_lane(TblGeom{w}, tB.data(), s1, s2, blob, off + j * n, rj, h, with_id, o1, o2, W);
+    prove_id_hash_lane(n, hide, blob, off + j * n, ad_blob + ad_off[j], (size_t)(ad_off[j + 1] - ad_off[j]), rj, h, with_id, k, Vk,
+                       W, cc, (Fr*)(o_rs + 8 * per * j));
+    st(o_sig1 + 36 * j, o1); st(o_sig2 + 36 * j, o2); st(o_k + 72 * j, k); st(o_phi + 36 * j, W[0]); st(o_c + 8 * j, cc);
+    if (with_id) { st(o_E1 + 36 * j, W[2]); st(o_E2 + 36 * j, W[3]); }
+  }
+}
 }

@@ -196,6 +196,83 @@ def expected_verify_id(wl: SignonWorkload, nthreads: int = 0):
                          nthreads or ref.hw_threads())
 
 
+# ---- prover side: the reference's own requester methods under per-lane seeds, plus the scalars
+#      those methods drew (replayed from the same streams) ------------------------------------------------------------
+@dataclass
+class ProverRequestWorkload:
+    key: "ref.KeyMaterial"
+    attrs: List[List[bytes]]   # ALL attribute values (the requester knows the hidden ones)
+    hidden: np.ndarray
+    ads: List[bytes]
+    rnd: np.ndarray            # (N, h+2, 4): t1, r0, one per hidden attribute
+    exp_A: np.ndarray          # reference outputs (A is raw Jacobian)
+    exp_c: np.ndarray
+    exp_rs: np.ndarray
+    blind_sig1: np.ndarray     # a blinded credential for the request (issued by the reference signer)
+    blind_sig2: np.ndarray
+    exp_unblind2: np.ndarray
+
+
+def make_prover_request_workload(n_attrs=5, lanes=8, n_hidden=2, seed=6, key_seed=1, nthreads=0) -> ProverRequestWorkload:
+    nthreads = nthreads or ref.hw_threads()
+    key = ref.KeyMaterial(n_attrs, seed_=key_seed)
+    attrs = attr_strings(n_attrs, lanes)
+    hidden = _hidden_mask(n_attrs, n_hidden)
+    ads = [b"sess%d" % j for j in range(lanes)]
+    s = seed * 1000003
+    A, c, rs = ref.request_id(key, attrs, hidden, ads, s, nthreads)
+    rnd = ref.lane_draws(s, lanes, n_hidden + 2)
+    req_attrs = [[b"" if hidden[i] else lane[i] for i in range(n_attrs)] for lane in attrs]
+    ref.seed(seed + 1)
+    u = ref.fr_rand(lanes)
+    v, b1, b2, _ = ref.provide_id(key, A, c, rs, req_attrs, ads, u, nthreads)
+    assert v.all()
+    _, un2 = ref.unblind(key, attrs, hidden, ads, s, b1, b2, nthreads)
+    return ProverRequestWorkload(key, attrs, hidden, ads, rnd, A, c, rs, b1, b2, un2)
+
+
+@dataclass
+class ProverSignonWorkload:
+    key: "ref.KeyMaterial"
+    sig1: np.ndarray
+    sig2: np.ndarray
+    attrs: List[List[bytes]]
+    hidden: np.ndarray
+    ads: List[bytes]
+    service: bytes
+    service_pt: np.ndarray
+    y: np.ndarray
+    g: np.ndarray
+    h: np.ndarray
+    with_id: bool
+    rnd: np.ndarray            # (N, h+5 | h+3, 4) in the reference's draw order
+    exp: dict                  # the reference's IdProof fields (raw Jacobian points)
+
+
+def make_prover_signon_workload(n_attrs=5, lanes=8, n_hidden=2, seed=8, with_id=True, key_seed=1, nthreads=0):
+    nthreads = nthreads or ref.hw_threads()
+    key = ref.KeyMaterial(n_attrs, seed_=key_seed)
+    attrs = attr_strings(n_attrs, lanes)
+    hidden = _hidden_mask(n_attrs, n_hidden)
+    sig1, sig2 = sign_lanes(key, attrs, seed + 7, nthreads)
+    ads = [b"sess%d" % j for j in range(lanes)]
+    service = b"rp.example"
+    y, g, h = ref.hash_to_g1(b"ghi"), ref.hash_to_g1(b"abc"), ref.hash_to_g1(b"jkl")
+    s = seed * 1000003
+    exp = ref.prove_id(key, sig1, sig2, attrs, hidden, ads, service, y, g, h, s, with_id, nthreads)
+    rnd = ref.lane_draws(s, lanes, n_hidden + (5 if with_id else 3))
+    return ProverSignonWorkload(key, sig1, sig2, attrs, hidden, ads, service, ref.hash_to_g1(service), y, g, h, with_id, rnd, exp)
+
+
+def assert_proof_equal(got: dict, exp: dict, with_id: bool):
+    """our (normalised) proof against the reference's raw-Jacobian IdProof: points after mcl's normalize, scalars raw."""
+    for name in ("sig1", "sig2", "phi") + (("E1", "E2") if with_id else ()):
+        assert np.array_equal(got[name], ref.g1_op(ref.G_NORM, exp[name])), name
+    assert np.array_equal(got["k"], ref.g2_op(ref.G_NORM, exp["k"])), "k"
+    assert np.array_equal(got["c"], exp["c"]), "c"
+    assert np.array_equal(np.asarray(got["rs"]).reshape(exp["rs"].shape), exp["rs"]), "rs"
+
+
 # ---- wire-format ingest (SURVEY 8f rank 1) ------------------------------------------------------------------
 def deserialize_cases(g2: bool, count=24):
     """serialized points (valid, infinity, flag flipped, x >= p, non-residue x) + mcl's verdict and result."""
