@@ -12,6 +12,9 @@
 //   psb::PSVerifier::el_passo_verify_id_without_id_retrieval(...)       -> psb_verify_id (with_id = 0)
 //   psb::PSRequester::verify(sigs, all_attributes)                      -> psb_verify
 //   psb::PSRequester::randomize_credential(sigs, t)                     -> psb_randomize   (t host-supplied)
+//   psb::PSRequester::el_passo_request_id(attributes, ads, rnd)         -> psb_request_id  (rnd host-supplied, draw order)
+//   psb::PSRequester::unblind_credential(sigs, t1)                      -> psb_unblind     (t1 = rnd[j][0] of the request)
+//   psb::PSRequester::el_passo_prove_id[_without_id_retrieval](...)     -> psb_prove_id    (rnd host-supplied, draw order)
 //   psb::PSSigner::el_passo_provide_id(requests, ads, u, sigs)          -> psb_provide_id  (u host-supplied)
 //
 // mcl objects are passed WITHOUT conversion: G1/G2/Fr in memory are Montgomery limb arrays in exactly
@@ -27,6 +30,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "ps-requester.h"
@@ -209,6 +213,11 @@ public:
 
   using ::PSRequester::verify;
   using ::PSRequester::randomize_credential;
+  using ::PSRequester::el_passo_request_id;
+  using ::PSRequester::unblind_credential;
+  using ::PSRequester::el_passo_prove_id;
+  using ::PSRequester::el_passo_prove_id_without_id_retrieval;
+  typedef std::vector<std::tuple<std::string, bool>> AttrList;   // (value, hide) as in src/ps-requester.h:39
 
   // batched PSRequester::verify (src/ps-requester.cc:115-137)
   std::vector<uint8_t> verify(const std::vector<PSCredential>& sigs,
@@ -233,7 +242,124 @@ public:
     return out;
   }
 
+  // batched el_passo_request_id (src/ps-requester.cc:19-97).  All lanes share one hide pattern.  rnd[j] = the h + 2
+  // scalars the reference would draw with Fr::setByCSPRNG, in its draw order: t1 (the blinding -- keep it for
+  // unblind_credential; the scalar method stores it in m_t1), the randomness of g, one per hidden attribute.
+  std::vector<PSCredRequest> el_passo_request_id(const std::vector<AttrList>& attributes,
+                                                 const std::vector<std::string>& associated_data,
+                                                 const std::vector<std::vector<mcl::bls12::Fr>>& rnd) const {
+    using namespace mcl::bls12;
+    const size_t N = attributes.size();
+    if (associated_data.size() != N || rnd.size() != N) throw std::runtime_error("psb: one associated_data and one rnd per lane");
+    std::vector<PSCredRequest> out(N);
+    if (N == 0) return out;
+    std::vector<uint8_t> hide;
+    detail::Strings at, ad;
+    const size_t h = flatten(attributes, associated_data, hide, at, ad);
+    std::vector<Fr> r(N * (h + 2)), c(N), rs(N * (h + 1));
+    std::vector<G1> A(N);
+    for (size_t j = 0; j < N; j++) {
+      if (rnd[j].size() != h + 2) throw std::runtime_error("psb: el_passo_request_id needs h + 2 scalars per lane");
+      for (size_t i = 0; i < h + 2; i++) r[j * (h + 2) + i] = rnd[j][i];
+    }
+    check(psb_request_id(m_key.get(), N, at.data(), at.off.data(), hide.data(), ad.data(), ad.off.data(), detail::u64(r.data()),
+                         detail::u64(A.data()), detail::u64(c.data()), detail::u64(rs.data())), "psb_request_id");
+    for (size_t j = 0; j < N; j++) {
+      out[j].A = A[j]; out[j].c = c[j];
+      out[j].rs.assign(rs.begin() + j * (h + 1), rs.begin() + (j + 1) * (h + 1));
+      for (const auto& a : attributes[j]) out[j].attributes.push_back(std::get<1>(a) ? std::string() : std::get<0>(a));
+    }
+    return out;
+  }
+
+  // batched unblind_credential (src/ps-requester.cc:99-113): (sig1, sig2 - t1[j] sig1)
+  std::vector<PSCredential> unblind_credential(const std::vector<PSCredential>& sigs, const std::vector<mcl::bls12::Fr>& t1) const {
+    using namespace mcl::bls12;
+    const size_t N = sigs.size();
+    if (t1.size() != N) throw std::runtime_error("psb: one blinding factor per credential");
+    std::vector<PSCredential> out(N);
+    if (N == 0) return out;
+    std::vector<G1> s1(N), s2(N), o2(N);
+    for (size_t j = 0; j < N; j++) { s1[j] = sigs[j].sig1; s2[j] = sigs[j].sig2; }
+    check(psb_unblind(N, detail::u64(s1.data()), detail::u64(s2.data()), detail::u64(t1.data()), detail::u64(o2.data())), "psb_unblind");
+    for (size_t j = 0; j < N; j++) { out[j].sig1 = s1[j]; out[j].sig2 = o2[j]; }
+    return out;
+  }
+
+  // batched el_passo_prove_id (src/ps-requester.cc:150-310); rnd[j] = t, r, epsilon, one per hidden attribute, random2, random3
+  std::vector<IdProof> el_passo_prove_id(const std::vector<PSCredential>& sigs, const std::vector<AttrList>& attributes,
+                                         const std::vector<std::string>& associated_data, const std::string& service_name,
+                                         const mcl::bls12::G1& authority_pk, const mcl::bls12::G1& g, const mcl::bls12::G1& h,
+                                         const std::vector<std::vector<mcl::bls12::Fr>>& rnd) const {
+    return prove_batch(sigs, attributes, associated_data, service_name, &authority_pk, &g, &h, rnd);
+  }
+  // batched el_passo_prove_id_without_id_retrieval (:312-432); rnd[j] = t, r, one per hidden attribute, random2
+  std::vector<IdProof> el_passo_prove_id_without_id_retrieval(const std::vector<PSCredential>& sigs,
+                                                              const std::vector<AttrList>& attributes,
+                                                              const std::vector<std::string>& associated_data,
+                                                              const std::string& service_name,
+                                                              const std::vector<std::vector<mcl::bls12::Fr>>& rnd) const {
+    return prove_batch(sigs, attributes, associated_data, service_name, nullptr, nullptr, nullptr, rnd);
+  }
+
 private:
+  // (value, hide) lists -> flat strings + the batch's hide pattern; returns the number of hidden attributes
+  size_t flatten(const std::vector<AttrList>& attributes, const std::vector<std::string>& ads, std::vector<uint8_t>& hide,
+                 detail::Strings& at, detail::Strings& ad) const {
+    hide.assign(m_n + 1, 0);
+    for (size_t j = 0; j < attributes.size(); j++) {
+      if (attributes[j].size() != m_n) throw std::runtime_error("attribute size does not match");   // ps-requester.cc:31-33
+      for (size_t i = 0; i < m_n; i++) {
+        const uint8_t hd = std::get<1>(attributes[j][i]) ? 1 : 0;
+        if (j == 0) hide[i] = hd;
+        else if (hide[i] != hd) throw std::runtime_error("psb: all lanes of a batch must hide the same attributes");
+        at.add(std::get<0>(attributes[j][i]));
+      }
+      ad.add(ads[j]);
+    }
+    size_t h = 0;
+    for (size_t i = 0; i < m_n; i++) h += hide[i];
+    return h;
+  }
+  std::vector<IdProof> prove_batch(const std::vector<PSCredential>& sigs, const std::vector<AttrList>& attributes,
+                                   const std::vector<std::string>& ads, const std::string& service_name, const mcl::bls12::G1* y,
+                                   const mcl::bls12::G1* g, const mcl::bls12::G1* hp,
+                                   const std::vector<std::vector<mcl::bls12::Fr>>& rnd) const {
+    using namespace mcl::bls12;
+    const size_t N = sigs.size();
+    const bool with_id = y != nullptr;
+    if (attributes.size() != N || ads.size() != N || rnd.size() != N) throw std::runtime_error("psb: one attribute list, associated_data and rnd per lane");
+    std::vector<IdProof> out(N);
+    if (N == 0) return out;
+    std::vector<uint8_t> hide;
+    detail::Strings at, ad;
+    const size_t h = flatten(attributes, ads, hide, at, ad);
+    const size_t rper = h + (with_id ? 5 : 3), per = h + (with_id ? 2 : 1);
+    std::vector<Fr> r(N * rper), c(N), rs(N * per);
+    std::vector<G1> s1(N), s2(N), o1(N), o2(N), phi(N), E1(N), E2(N);
+    std::vector<G2> k(N);
+    for (size_t j = 0; j < N; j++) {
+      if (rnd[j].size() != rper) throw std::runtime_error("psb: el_passo_prove_id needs h + 5 (h + 3 without id retrieval) scalars per lane");
+      for (size_t i = 0; i < rper; i++) r[j * rper + i] = rnd[j][i];
+      s1[j] = sigs[j].sig1; s2[j] = sigs[j].sig2;
+    }
+    G1 svc;
+    hashAndMapToG1(svc, service_name);   // one value per batch, on the host
+    check(psb_prove_id(m_key.get(), N, detail::u64(s1.data()), detail::u64(s2.data()), at.data(), at.off.data(), hide.data(), ad.data(),
+                       ad.off.data(), detail::u64(&svc), with_id ? detail::u64(y) : nullptr, with_id ? detail::u64(g) : nullptr,
+                       with_id ? detail::u64(hp) : nullptr, with_id ? 1 : 0, detail::u64(r.data()), detail::u64(o1.data()),
+                       detail::u64(o2.data()), detail::u64(k.data()), detail::u64(phi.data()), detail::u64(E1.data()),
+                       detail::u64(E2.data()), detail::u64(c.data()), detail::u64(rs.data())), "psb_prove_id");
+    for (size_t j = 0; j < N; j++) {
+      IdProof& p = out[j];
+      p.sig1 = o1[j]; p.sig2 = o2[j]; p.k = k[j]; p.phi = phi[j]; p.c = c[j];
+      if (with_id) { p.E1 = E1[j]; p.E2 = E2[j]; }
+      p.rs.assign(rs.begin() + j * per, rs.begin() + (j + 1) * per);
+      for (const auto& a : attributes[j]) p.attributes.push_back(std::get<1>(a) ? std::string() : std::get<0>(a));
+    }
+    return out;
+  }
+
   size_t m_n;
   detail::KeyHandle m_key;
 };

@@ -6,6 +6,7 @@ headline bench, which is bench.py):
   cfg4  EL PASSO blind issuance           el_passo_provide_id, 20 attributes (2 hidden), 2^18 requests
         + requester randomize_credential  2^18 credentials
   cfg5  PS verification, 50 attributes    lanes per GPU as given (the named 2^24 is sharded over 8 GPUs)
+  p     prover side         el_passo_request_id (20 attrs), unblind_credential, el_passo_prove_id (10 attrs)
 
 Inputs come from the reference's own prover/requester code (tests/workload.py, oracle = test infrastructure):
 `--distinct` proofs/requests are generated and tiled to the full batch.  Every config is timed end to
@@ -55,7 +56,7 @@ def main():
     ap.add_argument("--lanes50", type=int, default=1 << 18)
     ap.add_argument("--distinct", type=int, default=1 << 12)
     ap.add_argument("--reps", type=int, default=2)
-    ap.add_argument("--configs", default="3,4,5,w")
+    ap.add_argument("--configs", default="3,4,5,w,p")
     ap.add_argument("--window-bits", type=int, default=16)
     args = ap.parse_args()
     pkg = ge.load_package()
@@ -150,6 +151,57 @@ def main():
                                 "note": "PSCredential::fromBufferString = 2 G1::deserialize (mcl, host)"},
               "parity": "verdicts identical to fromBufferString + PSVerifier::verify on all distinct lanes"}, fh)
         pk.close()
+
+    if "p" in cfgs:   # prover side: what generates cfg3 / cfg4 inputs at scale
+        pw = workload.make_prover_request_workload(20, D, 2, seed=6, nthreads=threads)
+        t0 = time.perf_counter()
+        ref.request_id(pw.key, pw.attrs, pw.hidden, pw.ads, 6 * 1000003, threads)
+        cpu_s = time.perf_counter() - t0
+        pk = pkg.PSPubKey(pw.key.g, pw.key.gg, pw.key.XX, pw.key.Y, pw.key.YY, window_bits=args.window_bits)
+        rq = pkg.PSRequester(pk)
+        attrs, ads, rnd = pkg.pack_attrs(pw.attrs * reps_tile), pkg.pack_strings(pw.ads * reps_tile), tile(pw.rnd, reps_tile)
+        rq.el_passo_request_id(pw.attrs, pw.hidden, pw.ads, pw.rnd)
+        l0 = pkg.launch_count()
+        (A, c, rs), dt = timed(lambda: rq.el_passo_request_id(attrs, pw.hidden, ads, rnd), args.reps)
+        assert np.array_equal(A[-D:], ref.g1_op(ref.G_NORM, pw.exp_A)) and np.array_equal(c[:D], pw.exp_c) and \
+            np.array_equal(rs[-D:], pw.exp_rs), "request_id mismatch vs reference"
+        emit({"config": "prover el_passo_request_id", "n_attrs": 20, "hidden": 2, "lanes": N, "distinct": D,
+              "metric": "requests_per_sec", "e2e_value": N / dt, "seconds": dt, "gpu_launches": pkg.launch_count() - l0,
+              "cpu_reference": {"value": D / cpu_s, "cores": threads, "sample": f"{D} lanes"},
+              "parity": "A, c, rs identical to PSRequester::el_passo_request_id under the same scalars"}, fh)
+        b1, b2, t1 = tile(pw.blind_sig1, reps_tile), tile(pw.blind_sig2, reps_tile), tile(pw.rnd[:, 0].copy(), reps_tile)
+        t0 = time.perf_counter()
+        ref.unblind(pw.key, pw.attrs, pw.hidden, pw.ads, 6 * 1000003, pw.blind_sig1, pw.blind_sig2, threads)
+        cpu_s = time.perf_counter() - t0
+        rq.unblind_credential(b1[:D], b2[:D], t1[:D])
+        l0 = pkg.launch_count()
+        (_, un2), dt = timed(lambda: rq.unblind_credential(b1, b2, t1), args.reps)
+        assert np.array_equal(un2[-D:], ref.g1_op(ref.G_NORM, pw.exp_unblind2)), "unblind mismatch vs reference"
+        emit({"config": "prover unblind_credential", "lanes": N, "distinct": D, "metric": "credentials_unblinded_per_sec",
+              "e2e_value": N / dt, "seconds": dt, "gpu_launches": pkg.launch_count() - l0,
+              "cpu_reference": {"value": D / cpu_s, "cores": threads, "sample": f"{D} lanes (includes replaying the request to set m_t1)"},
+              "parity": "sig2 - t1 sig1 identical to PSRequester::unblind_credential"}, fh)
+        pk.close()
+        for with_id in (True, False):
+            sw = workload.make_prover_signon_workload(10, D, 2, seed=8, with_id=with_id, nthreads=threads)
+            t0 = time.perf_counter()
+            ref.prove_id(sw.key, sw.sig1, sw.sig2, sw.attrs, sw.hidden, sw.ads, sw.service, sw.y, sw.g, sw.h, 8 * 1000003, with_id, threads)
+            cpu_s = time.perf_counter() - t0
+            pk = pkg.PSPubKey(sw.key.g, sw.key.gg, sw.key.XX, sw.key.Y, sw.key.YY, window_bits=args.window_bits)
+            rq = pkg.PSRequester(pk)
+            s1, s2, rnd = tile(sw.sig1, reps_tile), tile(sw.sig2, reps_tile), tile(sw.rnd, reps_tile)
+            attrs, ads = pkg.pack_attrs(sw.attrs * reps_tile), pkg.pack_strings(sw.ads * reps_tile)
+            rq.el_passo_prove_id(sw.sig1, sw.sig2, sw.attrs, sw.hidden, sw.ads, sw.service_pt, sw.y, sw.g, sw.h, rnd=sw.rnd, with_id=with_id)
+            l0 = pkg.launch_count()
+            got, dt = timed(lambda: rq.el_passo_prove_id(s1, s2, attrs, sw.hidden, ads, sw.service_pt, sw.y, sw.g, sw.h, rnd=rnd,
+                                                         with_id=with_id), args.reps)
+            workload.assert_proof_equal({k: v[-D:] for k, v in got.items()}, sw.exp, with_id)
+            emit({"config": "prover el_passo_prove_id" + ("" if with_id else "_without_id_retrieval"), "n_attrs": 10, "hidden": 2,
+                  "lanes": N, "distinct": D, "metric": "proofs_per_sec", "e2e_value": N / dt, "seconds": dt,
+                  "gpu_launches": pkg.launch_count() - l0,
+                  "cpu_reference": {"value": D / cpu_s, "cores": threads, "sample": f"{D} lanes"},
+                  "parity": "every IdProof field identical to PSRequester::el_passo_prove_id under the same scalars"}, fh)
+            pk.close()
 
     if "5" in cfgs:
         N5 = args.lanes50

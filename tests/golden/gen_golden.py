@@ -11,6 +11,8 @@ reference compiled by oracle/Makefile).  Outputs, all small JSON with hex string
                  verify (verdict + fused GT), randomize (serialized)
   elpasso.json   reference outputs of el_passo_provide_id (serialized credentials) and
                  el_passo_verify_id / _without_id_retrieval (verdicts) on small seeded batches
+  prover.json    reference outputs of el_passo_request_id, unblind_credential and el_passo_prove_id
+                 [_without_id_retrieval] under per-lane seeded streams, with the scalars those methods drew
 """
 import json
 import os
@@ -96,8 +98,29 @@ def elpasso():
     return out
 
 
+def prover():
+    """reference prover outputs (key seed 1, n = 5, attributes 0 and 1 hidden) + the scalars drawn, in draw order."""
+    out = {}
+    pw = workload.make_prover_request_workload(5, 6, 2, seed=6)
+    out["request_id"] = {"n": 5, "key_seed": 1, "hidden": pw.hidden.tolist(), "attrs": [[a.decode() for a in lane] for lane in pw.attrs],
+                         "ads": [a.decode() for a in pw.ads], "rnd": hx(pw.rnd), "A": hx(ref.g1_op(ref.G_NORM, pw.exp_A)),
+                         "c": hx(pw.exp_c), "rs": hx(pw.exp_rs), "blind_sig1": hx(pw.blind_sig1), "blind_sig2": hx(pw.blind_sig2),
+                         "unblind_sig2": hx(ref.g1_op(ref.G_NORM, pw.exp_unblind2))}
+    for name, with_id in (("prove_id", True), ("prove_id_without_id_retrieval", False)):
+        sw = workload.make_prover_signon_workload(5, 6, 2, seed=8, with_id=with_id)
+        d = {k: hx(ref.g1_op(ref.G_NORM, sw.exp[k])) for k in ("sig1", "sig2", "phi")}
+        if with_id:
+            d.update({k: hx(ref.g1_op(ref.G_NORM, sw.exp[k])) for k in ("E1", "E2")})
+        d.update({"k": hx(ref.g2_op(ref.G_NORM, sw.exp["k"])), "c": hx(sw.exp["c"]), "rs": hx(sw.exp["rs"]),
+                  "in_sig1": hx(sw.sig1), "in_sig2": hx(sw.sig2), "rnd": hx(sw.rnd), "hidden": sw.hidden.tolist(),
+                  "attrs": [[a.decode() for a in lane] for lane in sw.attrs], "ads": [a.decode() for a in sw.ads],
+                  "service": sw.service.decode(), "service_pt": hx(sw.service_pt), "y": hx(sw.y), "g": hx(sw.g), "h": hx(sw.h)})
+        out[name] = d
+    return out
+
+
 if __name__ == "__main__":
-    for name, fn in (("mcl_kat.json", mcl_kat), ("keys.json", keys), ("protocol.json", protocol), ("elpasso.json", elpasso)):
+    for name, fn in (("mcl_kat.json", mcl_kat), ("keys.json", keys), ("protocol.json", protocol), ("elpasso.json", elpasso), ("prover.json", prover)):
         with open(os.path.join(HERE, name), "w") as f:
             json.dump(fn(), f, indent=1)
         print("wrote", name, os.path.getsize(os.path.join(HERE, name)), "bytes")

@@ -129,6 +129,59 @@ int main(int argc, char** argv) {
   }
   EXPECT(accepted > 0 && accepted < N);
 
+  // ---- prover side on the GPU: the reference's methods under a replayed CSPRNG stream vs the batched
+  //      overloads fed the same scalars; requests / proofs compared field by field in serialized form -------------
+  {
+    struct Replay {
+      static std::vector<uint8_t>& buf() { static std::vector<uint8_t> b; return b; }
+      static size_t& pos() { static size_t p = 0; return p; }
+      static uint32_t read(void*, void* out, uint32_t n) {
+        for (uint32_t i = 0; i < n; i++) static_cast<uint8_t*>(out)[i] = buf()[(pos()++) % buf().size()];
+        return n;
+      }
+    };
+    const size_t hcount = 2;
+    std::vector<std::vector<Fr>> rq_rnd(N), pv_rnd(N), pv2_rnd(N);
+    std::vector<PSCredRequest> ref_req;
+    std::vector<IdProof> ref_pv, ref_pv2;
+    std::vector<::PSRequester> u2(N, ::PSRequester(pk));
+    mcl::fp::RandGen saved = mcl::fp::RandGen::get();
+    for (size_t j = 0; j < N; j++) {
+      // a per-lane byte stream; the scalars are what setByCSPRNG makes of consecutive 32-byte reads
+      Replay::buf().resize(32 * 16);
+      for (size_t i = 0; i < Replay::buf().size(); i++) Replay::buf()[i] = (uint8_t)(i * 131 + j * 17 + 7);
+      auto draws = [&](size_t cnt) { std::vector<Fr> v(cnt); Replay::pos() = 0; for (auto& x : v) x.setByCSPRNG(); Replay::pos() = 0; return v; };
+      mcl::fp::RandGen::setRandFunc(nullptr, Replay::read);
+      rq_rnd[j] = draws(hcount + 2);
+      ref_req.push_back(u2[j].el_passo_request_id(attrs[j], ads[j]));
+      pv_rnd[j] = draws(hcount + 5);
+      ref_pv.push_back(u2[j].el_passo_prove_id(creds[j], attrs[j], ads[j], "service", authority_pk, g, h));
+      pv2_rnd[j] = draws(hcount + 3);
+      ref_pv2.push_back(u2[j].el_passo_prove_id_without_id_retrieval(creds[j], attrs[j], ads[j], "service"));
+      mcl::fp::RandGen::setRandGen(saved);
+    }
+    std::vector<PSCredRequest> got_req = wallet.el_passo_request_id(attrs, ads, rq_rnd);
+    std::vector<IdProof> got_pv = wallet.el_passo_prove_id(creds, attrs, ads, "service", authority_pk, g, h, pv_rnd);
+    std::vector<IdProof> got_pv2 = wallet.el_passo_prove_id_without_id_retrieval(creds, attrs, ads, "service", pv2_rnd);
+    std::vector<Fr> t1(N);
+    for (size_t j = 0; j < N; j++) {
+      EXPECT(got_req[j].toBufferString() == ref_req[j].toBufferString());     // the wire form of the request, byte for byte
+      EXPECT(got_pv[j].toBufferString() == ref_pv[j].toBufferString());
+      EXPECT(got_pv2[j].toBufferString() == ref_pv2[j].toBufferString());
+      t1[j] = rq_rnd[j][0];
+    }
+    // issue on the GPU for the GPU-made requests, unblind on the GPU, verify with the reference
+    std::vector<PSCredential> iss2;
+    std::vector<uint8_t> ok2 = idp.el_passo_provide_id(got_req, ads, u, iss2);
+    std::vector<PSCredential> un2 = wallet.unblind_credential(iss2, t1);
+    for (size_t j = 0; j < N; j++) {
+      EXPECT(ok2[j]);
+      PSCredential r = u2[j].unblind_credential(iss2[j]);                      // m_t1 of u2[j] is the replayed t1
+      EXPECT(ser(un2[j].sig1) == ser(r.sig1) && ser(un2[j].sig2) == ser(r.sig2));
+      EXPECT(static_cast<const ::PSVerifier&>(rp).verify(un2[j], plain[j]));
+    }
+  }
+
   // size mismatch raises like the reference's requester (src/ps-requester.cc:31-33)
   bool threw = false;
   try { plain[0].pop_back(); rp.verify(vc, plain); } catch (const std::runtime_error&) { threw = true; }

@@ -64,3 +64,35 @@ def test_prove_id_argument_checks(gpu_pkg, ref):
     with pytest.raises(ValueError):
         gpu_pkg.PSRequester(pk).el_passo_request_id(pw.attrs, np.zeros(3, np.uint8), pw.ads, pw.rnd)
     pk.close()
+
+
+def test_prover_golden_fixtures_on_gpu(gpu_pkg):
+    """committed reference outputs (tests/golden/prover.json): requests, unblinded credentials, proofs."""
+    import json
+    import os
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    keys = json.load(open(os.path.join(G, "keys.json")))["keys"]["5"]
+    p = json.load(open(os.path.join(G, "prover.json")))
+    arr = lambda h, w: np.frombuffer(bytes.fromhex(h), dtype=np.uint64).reshape(-1, w).copy()  # noqa: E731
+    pk = gpu_pkg.PSPubKey(arr(keys["g"], 18), arr(keys["gg"], 36), arr(keys["XX"], 36), arr(keys["Y"], 18), arr(keys["YY"], 36),
+                          window_bits=8)
+    rq = gpu_pkg.PSRequester(pk)
+    q = p["request_id"]
+    N = len(q["ads"])
+    hidden = np.array(q["hidden"], dtype=np.uint8)
+    attrs = [[a.encode() for a in lane] for lane in q["attrs"]]
+    rnd = arr(q["rnd"], 4).reshape(N, -1, 4)
+    A, c, rs = rq.el_passo_request_id(attrs, hidden, [a.encode() for a in q["ads"]], rnd)
+    assert A.tobytes().hex() == q["A"] and c.tobytes().hex() == q["c"] and rs.tobytes().hex() == q["rs"]
+    _, un2 = rq.unblind_credential(arr(q["blind_sig1"], 18), arr(q["blind_sig2"], 18), rnd[:, 0])
+    assert un2.tobytes().hex() == q["unblind_sig2"]
+    for name, with_id in (("prove_id", True), ("prove_id_without_id_retrieval", False)):
+        q = p[name]
+        N = len(q["ads"])
+        attrs = [[a.encode() for a in lane] for lane in q["attrs"]]
+        got = rq.el_passo_prove_id(arr(q["in_sig1"], 18), arr(q["in_sig2"], 18), attrs, hidden, [a.encode() for a in q["ads"]],
+                                   arr(q["service_pt"], 18), arr(q["y"], 18), arr(q["g"], 18), arr(q["h"], 18),
+                                   rnd=arr(q["rnd"], 4).reshape(N, -1, 4), with_id=with_id)
+        for f in ("sig1", "sig2", "k", "phi", "c", "rs") + (("E1", "E2") if with_id else ()):
+            assert got[f].tobytes().hex() == q[f], (name, f)
+    pk.close()
