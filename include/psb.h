@@ -150,6 +150,12 @@ int psb_prove_id(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* s
                  const uint64_t* rnd, uint64_t* o_sig1, uint64_t* o_sig2, uint64_t* o_k, uint64_t* o_phi, uint64_t* o_E1,
                  uint64_t* o_E2, uint64_t* o_c, uint64_t* o_rs);
 
+/* Batched mcl::bn::hashAndMapToG1 (bn.hpp:2088-2097): message j = blob[off[j] .. off[j+1]);
+ * out[j] = the NORMALISED point mcl returns as a group element (SHA-512 -> Fp, Shallue-van de Woestijne map, cofactor
+ * (z-1)^2/3); ok[j] = 0 only for the exceptional hash values mcl asserts against.  For relying parties whose batches
+ * mix many service names; with one service name per batch the host computes it once (psb_verify_id's service_pt). */
+int psb_hash_to_g1(size_t N, const uint8_t* msg_blob, const uint64_t* msg_off, uint64_t* out, uint8_t* ok);
+
 /* Batched mcl::bn::pairing (bn.hpp:1711-1715): out[j] = e(P[j], Q[j]), N x 72 u64. */
 int psb_pairing(size_t N, const uint64_t* P, const uint64_t* Q, uint64_t* out);
 

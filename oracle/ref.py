@@ -250,6 +250,19 @@ def hash_to_g1(msg: bytes):
     return out
 
 
+def map_to_g1(t):
+    """mcl mapToG1 (calcBN + cofactor clearing) of one Fp (6 u64) -> (point, ok)."""
+    out = np.zeros(G1, dtype=np.uint64)
+    ok = lib().ref_map_to_g1(_p(_u64(t)), _p(out))
+    return out, int(ok)
+
+
+def fp_set_hash_of(msg: bytes):
+    out = np.empty(FP, dtype=np.uint64)
+    lib().ref_fp_set_hash_of(C.c_char_p(msg), C.c_size_t(len(msg)), _p(out))
+    return out
+
+
 def hash_to_g2(msg: bytes):
     out = np.empty(G2, dtype=np.uint64)
     lib().ref_hash_to_g2(C.c_char_p(msg), C.c_size_t(len(msg)), _p(out))

@@ -204,6 +204,9 @@ int ref_g2_deserialize(size_t n, const uint8_t* in, G2* P) {
   return ok;
 }
 void ref_hash_to_g1(const uint8_t* msg, size_t len, G1* out) { hashAndMapToG1(*out, msg, len); }
+// mapToG1 on a given field element (calcBN + cofactor); returns 0 for mcl's exceptional inputs (t = 0, ...)
+int ref_map_to_g1(const Fp* t, G1* out) { bool b; mapToG1(&b, *out, *t); if (!b) out->clear(); return b ? 1 : 0; }
+void ref_fp_set_hash_of(const uint8_t* msg, size_t len, Fp* out) { out->setHashOf(msg, len); }
 void ref_hash_to_g2(const uint8_t* msg, size_t len, G2* out) { hashAndMapToG2(*out, msg, len); }
 
 // ---- pairing ----------------------------------------------------------------------------------

@@ -10,6 +10,7 @@
 #include "testops.cuh"
 #include "protocol.cuh"
 #include "prover.cuh"
+#include "hash_to_curve.cuh"
 
 namespace psb {
 
@@ -456,6 +457,16 @@ __global__ void __launch_bounds__(kBlock) k_pid_hash(size_t N, int n, const uint
   phi[lane] = w6[0];
   if (with_id) { E1[lane] = w6[2]; E2[lane] = w6[3]; }
   c[lane] = cc;
+}
+
+// ---- batched hashAndMapToG1 (mcl bn.hpp:2088-2097) ---------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_hash_to_g1(size_t N, const uint8_t* blob, const uint64_t* off, G1J* out, uint8_t* ok) {
+  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= N) return;
+  G1J P;
+  const bool r = hash_and_map_to_g1(P, blob + off[lane], (size_t)(off[lane + 1] - off[lane]));
+  out[lane] = P;
+  ok[lane] = r ? 1 : 0;
 }
 
 }  // namespace psb

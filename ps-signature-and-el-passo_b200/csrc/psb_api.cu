@@ -941,4 +941,34 @@ int psb_prove_id(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* s
   });
 }
 
+int psb_hash_to_g1(size_t N, const uint8_t* msg_blob, const uint64_t* msg_off, uint64_t* out, uint8_t* ok) {
+  if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
+  if (!msg_blob || !msg_off || !out || !ok) return fail(PSB_ERR_ARG, "null argument");
+  return shard(N, [&](int di, size_t b, size_t e) -> int {
+    Dev* dv = g_devs[di];
+    std::lock_guard<std::mutex> lk(dv->mu);
+    const size_t L = e - b;
+    if (L == 0) return PSB_OK;
+    CK(cudaSetDevice(dv->ordinal));
+    cudaStream_t st = dv->stream;
+    const uint64_t o0 = msg_off[b], o1 = msg_off[e];
+    Arena ar;
+    uint8_t *dblob = nullptr, *dok = nullptr; uint64_t* doff = nullptr; G1J* dout = nullptr;
+    for (int pass = 0; pass < 2; pass++) {
+      ar.used = 0;
+      dblob = ar.take<uint8_t>((size_t)(o1 - o0) + 16); doff = ar.take<uint64_t>(L + 1); dout = ar.take<G1J>(L); dok = ar.take<uint8_t>(L);
+      if (pass == 0) { int r = ensure(dv->arena, ar.used); if (r) return r; ar.base = (char*)dv->arena.p; }
+    }
+    if (o1 > o0) CK(cudaMemcpyAsync(dblob, msg_blob + o0, (size_t)(o1 - o0), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(doff, msg_off + b, (L + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    k_hash_to_g1<<<nblocks(L), kBlock, 0, st>>>(L, dblob - o0, doff, dout, dok);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out + b * 18, dout, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ok + b, dok, L, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PSB_OK;
+  });
+}
+
 }  // extern "C"

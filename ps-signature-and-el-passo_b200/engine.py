@@ -57,7 +57,7 @@ def lib():
 EXPORTS = ["psb_init", "psb_shutdown", "psb_num_devices", "psb_last_error", "psb_shard_range", "psb_launch_count",
            "psb_key_create", "psb_key_destroy", "psb_key_num_attributes", "psb_key_table_bytes",
            "psb_verify", "psb_verify_ser", "psb_g1_deserialize", "psb_g2_deserialize", "psb_verify_ws_bytes", "psb_verify_dev", "psb_randomize", "psb_provide_id",
-           "psb_verify_id", "psb_request_id", "psb_unblind", "psb_prove_id", "psb_pairing", "psb_g1_mul", "psb_set_profiling", "psb_last_phase_ms", "psb_test_op_shape", "psb_test_op", "psb_microbench"]
+           "psb_verify_id", "psb_request_id", "psb_unblind", "psb_prove_id", "psb_hash_to_g1", "psb_pairing", "psb_g1_mul", "psb_set_profiling", "psb_last_phase_ms", "psb_test_op_shape", "psb_test_op", "psb_microbench"]
 
 
 def _check(rc: int, what: str):
@@ -363,6 +363,17 @@ def pairing(P, Q):
     out = np.zeros((P.shape[0], GT), dtype=np.uint64)
     _check(lib().psb_pairing(C.c_size_t(P.shape[0]), _p(P), _p(Q), _p(out)), "psb_pairing")
     return out
+
+
+def hash_and_map_to_g1(msgs):
+    """batched mcl::bn::hashAndMapToG1: list of byte strings (or packed (blob, off)) -> (points (N,18) normalised, ok)."""
+    ensure_init()
+    blob, off = _packed(msgs, True)
+    N = off.shape[0] - 1
+    out = np.zeros((N, G1), dtype=np.uint64)
+    ok = np.zeros(N, dtype=np.uint8)
+    _check(lib().psb_hash_to_g1(C.c_size_t(N), _p(blob), _p(off), _p(out), _p(ok)), "psb_hash_to_g1")
+    return out, ok
 
 
 def g1_deserialize(ser, stride: int = 48):

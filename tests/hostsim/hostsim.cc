@@ -21,6 +21,7 @@ void hostsim_set_hash_of(const uint8_t* msg, size_t len, uint32_t* k) { psb::fr_
 // ---- protocol lane functions (csrc/protocol.cuh) on the host: table building + one lane at a time ------
 #include <vector>
 #include "../../ps-signature-and-el-passo_b200/csrc/prover.cuh"
+#include "../../ps-signature-and-el-passo_b200/csrc/hash_to_curve.cuh"
 namespace {
 using namespace psb;
 // same table geometry as k_window_bases / k_build_table: entry (win, d) = d * 2^(w win) * B, affine
@@ -165,4 +166,11 @@ void hostsim_prove_id(int n, int w, const uint32_t* gg, const uint32_t* XX, cons
     if (with_id) { st(o_E1 + 36 * j, W[2]); st(o_E2 + 36 * j, W[3]); }
   }
 }
+// hashAndMapToG1 probes (csrc/hash_to_curve.cuh)
+void hostsim_sha512(const uint8_t* msg, size_t len, uint8_t* out64) {
+  uint64_t h[8]; sha512(h, msg, len);
+  for (int i = 0; i < 64; i++) out64[i] = (uint8_t)(h[i >> 3] >> (56 - 8 * (i & 7)));
+}
+int hostsim_hash_to_g1(const uint8_t* msg, size_t len, uint32_t* out) { G1J P; const bool r = hash_and_map_to_g1(P, msg, len); st(out, P); return r; }
+int hostsim_map_to_g1(const uint32_t* t, uint32_t* out) { Fp tt; ld(tt, t); G1J P, Q; const bool r = map_to_g1(P, tt); if (r) g1_clear_cofactor(Q, P); else pt_set_zero(Q); st(out, Q); return r; }
 }
