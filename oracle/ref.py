@@ -13,10 +13,19 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_ref", "libpsref.so")
 REF_ROOT = "/root/reference"
 
-FP, FR, G1, G2, GT, FP2, FP6 = 6, 4, 18, 36, 72, 12, 36
+# One curve per process (mcl keeps the curve in static state): PSB_CURVE=bn254 selects the BN254 build of the
+# reference (oracle/Makefile target `bn254`, packed 256-bit objects), anything else BLS12-381.
+CURVE = os.environ.get("PSB_CURVE", "bls12_381").lower()
+assert CURVE in ("bls12_381", "bn254"), CURVE
+BN254 = CURVE == "bn254"
+LIB_PATH = os.path.join(_HERE, "_ref", "libpsref_bn254.so" if BN254 else "libpsref.so")
+MCL_CURVE = 0 if BN254 else 5            # mcl/include/mcl/curve_type.h
+FP = 4 if BN254 else 6                   # u64 words of an Fp
+FR, G1, G2, GT, FP2, FP6 = 4, 3 * FP, 6 * FP, 12 * FP, 2 * FP, 6 * FP
+SZ1, SZ2 = 8 * FP, 16 * FP               # serialized Fp / compressed G1, compressed G2 (bytes)
+CRED = 2 * (2 + SZ1)                     # PSCredential::toBufferString: two TLV-framed G1 (100 / 68 bytes)
 OP_ADD, OP_SUB, OP_MUL, OP_SQR, OP_NEG, OP_INV = range(6)
 G_ADD, G_SUB, G_DBL, G_NEG, G_NORM = range(5)
 
@@ -29,7 +38,7 @@ def build(force: bool = False) -> bool:
         return True
     if not os.path.isdir(REF_ROOT):
         return False
-    subprocess.check_call(["make", "-C", _HERE, "-j8", "all"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", _HERE, "-j8", "all"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     return os.path.exists(LIB_PATH)
 
 
@@ -49,8 +58,8 @@ def lib():
         _lib.ref_key_create.restype = C.c_void_p
         _lib.ref_signer_create.restype = C.c_void_p
         _lib.ref_key_encode.restype = C.c_size_t
-        if _lib.ref_init(5) != 0:
-            raise RuntimeError("ref_init(BLS12_381) failed")
+        if _lib.ref_init(MCL_CURVE) != 0:
+            raise RuntimeError(f"ref_init({CURVE}) failed")
     return _lib
 
 
@@ -113,7 +122,7 @@ def fp12_frobenius(k, a):
 
 
 def fp_from_ints(vals):
-    buf = np.frombuffer(b"".join(int(v).to_bytes(48, "little") for v in vals), dtype=np.uint8).copy()
+    buf = np.frombuffer(b"".join(int(v).to_bytes(SZ1, "little") for v in vals), dtype=np.uint8).copy()
     out = np.empty((len(vals), FP), dtype=np.uint64)
     lib().ref_fp_from_bytes(C.c_size_t(len(vals)), _p(buf), _p(out))
     return out
@@ -196,27 +205,27 @@ def g2_mul(P, k, nthreads=1):
 
 def g1_serialize(P):
     P = _u64(P).reshape(-1, G1)
-    out = np.empty((P.shape[0], 48), dtype=np.uint8)
+    out = np.empty((P.shape[0], SZ1), dtype=np.uint8)
     lib().ref_g1_serialize(C.c_size_t(P.shape[0]), _p(P), _p(out))
     return out
 
 
 def g2_serialize(P):
     P = _u64(P).reshape(-1, G2)
-    out = np.empty((P.shape[0], 96), dtype=np.uint8)
+    out = np.empty((P.shape[0], SZ2), dtype=np.uint8)
     lib().ref_g2_serialize(C.c_size_t(P.shape[0]), _p(P), _p(out))
     return out
 
 
 def g1_deserialize(b):
-    b = np.ascontiguousarray(b, dtype=np.uint8).reshape(-1, 48)
+    b = np.ascontiguousarray(b, dtype=np.uint8).reshape(-1, SZ1)
     out = np.empty((b.shape[0], G1), dtype=np.uint64)
     ok = lib().ref_g1_deserialize(C.c_size_t(b.shape[0]), _p(b), _p(out))
     return out, bool(ok)
 
 
 def g2_deserialize(b):
-    b = np.ascontiguousarray(b, dtype=np.uint8).reshape(-1, 96)
+    b = np.ascontiguousarray(b, dtype=np.uint8).reshape(-1, SZ2)
     out = np.empty((b.shape[0], G2), dtype=np.uint64)
     ok = lib().ref_g2_deserialize(C.c_size_t(b.shape[0]), _p(b), _p(out))
     return out, bool(ok)
@@ -227,11 +236,11 @@ def cred_encode(sig1, sig2):
     sig1 = _u64(sig1).reshape(-1, G1)
     sig2 = _u64(sig2).reshape(-1, G1)
     N = sig1.shape[0]
-    out = np.zeros(N * 100, dtype=np.uint8)
+    out = np.zeros(N * CRED, dtype=np.uint8)
     lib().ref_cred_encode.restype = C.c_size_t
     used = lib().ref_cred_encode(C.c_size_t(N), _p(sig1), _p(sig2), _p(out), C.c_size_t(out.size))
-    assert used == N * 100, used
-    return out.reshape(N, 100)
+    assert used == N * CRED, used
+    return out.reshape(N, CRED)
 
 
 def cred_decode(buf):
@@ -377,7 +386,7 @@ def randomize(sig1, sig2, t, nthreads=1):
     N = sig1.shape[0]
     o1 = np.empty_like(sig1)
     o2 = np.empty_like(sig2)
-    ser = np.empty((N, 96), dtype=np.uint8)
+    ser = np.empty((N, SZ2), dtype=np.uint8)
     lib().ref_randomize(C.c_size_t(N), _p(sig1), _p(sig2), _p(t), _p(o1), _p(o2), _p(ser),
                         C.c_int(nthreads))
     return o1, o2, ser
@@ -441,7 +450,7 @@ def provide_id(key, A, c, rs, attrs, ads, u, nthreads=1):
     verdict = np.empty(N, dtype=np.uint8)
     s1 = np.empty((N, G1), dtype=np.uint64)
     s2 = np.empty((N, G1), dtype=np.uint64)
-    ser = np.empty((N, 96), dtype=np.uint8)
+    ser = np.empty((N, SZ2), dtype=np.uint8)
     lib().ref_provide_id(key.signer(), C.c_size_t(N), C.c_size_t(key.n), _p(_u64(A)), _p(_u64(c)),
                          _p(rs), C.c_size_t(per), _p(blob), _p(off), _p(ad_blob), _p(ad_off),
                          _p(_u64(u)), _p(verdict), _p(s1), _p(s2), _p(ser), C.c_int(nthreads))

@@ -25,6 +25,13 @@
 
 using namespace mcl::bls12;
 typedef uint64_t u64;
+// serialized sizes: Fp / compressed G1 = 48 bytes for BLS12-381, 32 for the BN254 build (oracle/Makefile target bn254)
+#ifdef PSREF_BN254
+static const size_t SZ1 = 32;
+#else
+static const size_t SZ1 = 48;
+#endif
+static const size_t SZ2 = 2 * SZ1;
 
 // ---------------------------------------------------------------------------------------------
 // deterministic, thread-local byte stream installed as mcl's RandGen (SURVEY.md 8c "DetRng")
@@ -129,10 +136,10 @@ void ref_fp12_frobenius(int k, size_t n, const Fp12* a, Fp12* out) {
 
 // integers <-> Montgomery: little-endian byte strings (48 / 32 bytes), value must be < modulus
 void ref_fp_from_bytes(size_t n, const uint8_t* in, Fp* out) {
-  for (size_t i = 0; i < n; i++) out[i].setArray(in + 48 * i, 48);
+  for (size_t i = 0; i < n; i++) out[i].setArray(in + SZ1 * i, SZ1);
 }
 void ref_fp_to_bytes(size_t n, const Fp* in, uint8_t* out) {
-  for (size_t i = 0; i < n; i++) in[i].serialize(out + 48 * i, 48);
+  for (size_t i = 0; i < n; i++) in[i].serialize(out + SZ1 * i, SZ1);
 }
 void ref_fr_from_bytes(size_t n, const uint8_t* in, Fr* out) {
   for (size_t i = 0; i < n; i++) out[i].setArray(in + 32 * i, 32);
@@ -188,19 +195,19 @@ int ref_g2_eq(const G2* a, const G2* b) { return *a == *b; }
 
 // mcl compressed little-endian serialization (48 / 96 bytes) and its lowercase-hex form
 void ref_g1_serialize(size_t n, const G1* P, uint8_t* out) {
-  for (size_t i = 0; i < n; i++) P[i].serialize(out + 48 * i, 48);
+  for (size_t i = 0; i < n; i++) P[i].serialize(out + SZ1 * i, SZ1);
 }
 void ref_g2_serialize(size_t n, const G2* P, uint8_t* out) {
-  for (size_t i = 0; i < n; i++) P[i].serialize(out + 96 * i, 96);
+  for (size_t i = 0; i < n; i++) P[i].serialize(out + SZ2 * i, SZ2);
 }
 int ref_g1_deserialize(size_t n, const uint8_t* in, G1* P) {
   int ok = 1;
-  for (size_t i = 0; i < n; i++) ok &= (P[i].deserialize(in + 48 * i, 48) == 48);
+  for (size_t i = 0; i < n; i++) ok &= (P[i].deserialize(in + SZ1 * i, SZ1) == SZ1);
   return ok;
 }
 int ref_g2_deserialize(size_t n, const uint8_t* in, G2* P) {
   int ok = 1;
-  for (size_t i = 0; i < n; i++) ok &= (P[i].deserialize(in + 96 * i, 96) == 96);
+  for (size_t i = 0; i < n; i++) ok &= (P[i].deserialize(in + SZ2 * i, SZ2) == SZ2);
   return ok;
 }
 void ref_hash_to_g1(const uint8_t* msg, size_t len, G1* out) { hashAndMapToG1(*out, msg, len); }
@@ -338,8 +345,8 @@ void ref_randomize(size_t N, const G1* sig1, const G1* sig2, const Fr* t, G1* ou
     G1::mul(out1[i], sig1[i], t[i]);
     G1::mul(out2[i], sig2[i], t[i]);
     if (ser_or_null) {
-      out1[i].serialize(ser_or_null + 96 * i, 48);
-      out2[i].serialize(ser_or_null + 96 * i + 48, 48);
+      out1[i].serialize(ser_or_null + SZ2 * i, SZ1);
+      out2[i].serialize(ser_or_null + SZ2 * i + SZ1, SZ1);
     }
   });
 }
@@ -451,8 +458,8 @@ void ref_provide_id(void* signer, size_t N, size_t n, const G1* A, const Fr* c, 
     verdict[i] = ok ? 1 : 0;
     sig1[i] = out.sig1; sig2[i] = out.sig2;
     if (ser_or_null) {
-      out.sig1.serialize(ser_or_null + 96 * i, 48);
-      out.sig2.serialize(ser_or_null + 96 * i + 48, 48);
+      out.sig1.serialize(ser_or_null + SZ2 * i, SZ1);
+      out.sig2.serialize(ser_or_null + SZ2 * i + SZ1, SZ1);
     }
   });
   mcl::fp::RandGen::setRandFunc(nullptr, det_read);

@@ -20,15 +20,26 @@
 // Bounds: inputs < 2p (multiplicands of squarings are unreduced sums), sum of products < 4 p^2
 // => T < 2p at every row and the final value < 2p: one conditional subtraction canonicalises.
 #pragma once
+#ifdef PSB_CURVE_BN254
+#include "fp_cios_bn254.cuh"
+#else
 #include "fp_cios.cuh"
+#endif
 
 namespace psb {
 namespace cios {
 
-typedef uint32_t L12[12];
+typedef uint32_t L12[PSB_NL];   // one field element in registers (12 limbs for BLS12-381, 8 for BN254)
+#if PSB_NL == 12
 #define PSB_EV(v) v[0], v[2], v[4], v[6], v[8], v[10]
 #define PSB_OD(v) v[1], v[3], v[5], v[7], v[9], v[11]
 #define PSB_ALL(v) v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]
+#else
+#define PSB_EV(v) v[0], v[2], v[4], v[6]
+#define PSB_OD(v) v[1], v[3], v[5], v[7]
+#define PSB_ALL(v) v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]
+#endif
+#define PSB_TOP (PSB_NL - 1)
 #define PSB_X(m, ...) m(__VA_ARGS__)  // expand the limb lists before the row macro counts its arguments
 
 // first row of an accumulator pair: E = a_even * b, O = a_odd * b
@@ -39,41 +50,46 @@ __device__ PSB_INL void first(L12& E, L12& O, const L12& a, uint32_t b) {
 // first product of a later row: merge the stray limb, shift the odd array, accumulate a * b
 __device__ PSB_INL void mac_shift(L12& E, L12& O, const L12& a, uint32_t b) {
   PSB_X(PSB_ROW_ODD_RSHIFT, E[0], PSB_ALL(O), PSB_OD(a), b);
-  PSB_X(PSB_ROW_EVEN, PSB_ALL(E), O[11], PSB_EV(a), b);
+  PSB_X(PSB_ROW_EVEN, PSB_ALL(E), O[PSB_TOP], PSB_EV(a), b);
 }
 // further product of the same row, in place
 __device__ PSB_INL void mac(L12& E, L12& O, const L12& a, uint32_t b) {
   PSB_X(PSB_ROW_ODD, PSB_ALL(O), PSB_OD(a), b);
-  PSB_X(PSB_ROW_EVEN, PSB_ALL(E), O[11], PSB_EV(a), b);
+  PSB_X(PSB_ROW_EVEN, PSB_ALL(E), O[PSB_TOP], PSB_EV(a), b);
 }
 // Montgomery step of the row: m = T mod 2^32 * (-p^-1), T += m p  (low limb of E becomes 0)
 __device__ PSB_INL void reduce(L12& E, L12& O) {
   const uint32_t m = E[0] * PSB_FP_N0;
   PSB_X(PSB_RED_ODD, PSB_ALL(O), m);
-  PSB_X(PSB_RED_EVEN, PSB_ALL(E), O[11], m);
+  PSB_X(PSB_RED_EVEN, PSB_ALL(E), O[PSB_TOP], m);
 }
 // after the last row (even = E with E[0] == 0, odd = O): T = (E >> 32) + O, canonicalised into registers
 __device__ PSB_INL void finish_rr(uint32_t* t, const L12& E, const L12& O) {
   t[0] = ptx::add_cc(E[1], O[0]);
   PSB_UNROLL
-  for (int i = 1; i < 11; i++) t[i] = ptx::addc_cc(E[i + 1], O[i]);
-  t[11] = ptx::addc(0, O[11]);
+  for (int i = 1; i < PSB_TOP; i++) t[i] = ptx::addc_cc(E[i + 1], O[i]);
+  t[PSB_TOP] = ptx::addc(0, O[PSB_TOP]);
   cond_sub_mod<FpT>(t);
 }
 __device__ PSB_INL void finish(uint32_t* r, const L12& E, const L12& O) {
-  uint32_t t[12];
+  uint32_t t[PSB_NL];
   finish_rr(t, E, O);
   uint4* q = reinterpret_cast<uint4*>(r);   // every Fp is 16-byte aligned: three 128-bit stores
   q[0] = make_uint4(t[0], t[1], t[2], t[3]);
   q[1] = make_uint4(t[4], t[5], t[6], t[7]);
+#if PSB_NL == 12
   q[2] = make_uint4(t[8], t[9], t[10], t[11]);
+#endif
 }
 __device__ PSB_INL void load12(L12& d, const uint32_t* s) {
   const uint4* q = reinterpret_cast<const uint4*>(s);   // three 128-bit loads
-  const uint4 v0 = q[0], v1 = q[1], v2 = q[2];
+  const uint4 v0 = q[0], v1 = q[1];
   d[0] = v0.x; d[1] = v0.y; d[2] = v0.z; d[3] = v0.w;
   d[4] = v1.x; d[5] = v1.y; d[6] = v1.z; d[7] = v1.w;
+#if PSB_NL == 12
+  const uint4 v2 = q[2];
   d[8] = v2.x; d[9] = v2.y; d[10] = v2.z; d[11] = v2.w;
+#endif
 }
 
 // register-level cores: operands and result are register arrays (no memory operands), fully inlined into the
@@ -83,10 +99,10 @@ __device__ PSB_INL void mul_rr(uint32_t* r, const L12& a, const L12& b) {
   first(X, Y, a, b[0]);
   reduce(X, Y);
   PSB_UNROLL
-  for (int i = 1; i < 12; i += 2) {
+  for (int i = 1; i < PSB_NL; i += 2) {
     mac_shift(Y, X, a, b[i]);
     reduce(Y, X);
-    if (i + 1 < 12) {
+    if (i + 1 < PSB_NL) {
       mac_shift(X, Y, a, b[i + 1]);
       reduce(X, Y);
     }
@@ -100,11 +116,11 @@ __device__ PSB_INL void dot2_rr(uint32_t* r, const L12& a, const L12& b, const L
   mac(X, Y, c, d[0]);
   reduce(X, Y);
   PSB_UNROLL
-  for (int i = 1; i < 12; i += 2) {
+  for (int i = 1; i < PSB_NL; i += 2) {
     mac_shift(Y, X, a, b[i]);
     mac(Y, X, c, d[i]);
     reduce(Y, X);
-    if (i + 1 < 12) {
+    if (i + 1 < PSB_NL) {
       mac_shift(X, Y, a, b[i + 1]);
       mac(X, Y, c, d[i + 1]);
       reduce(X, Y);
@@ -119,7 +135,7 @@ __device__ PSB_INL void dot2_rr(uint32_t* r, const L12& a, const L12& b, const L
 // but costs ~24 IMAD.MOV per array per iteration at the loop back edge (+45 % instructions) -> kept for reference only.
 __device__ PSB_INL void zero12(L12& x) {
   PSB_UNROLL
-  for (int i = 0; i < 12; i++) x[i] = 0;
+  for (int i = 0; i < PSB_NL; i++) x[i] = 0;
 }
 __device__ PSB_INL uint2 ld2(const uint32_t* p) { return *reinterpret_cast<const uint2*>(p); }   // limb pairs are 8-byte aligned
 
@@ -128,7 +144,7 @@ __device__ PSB_INL void mul2_loop(uint32_t* r1, uint32_t* r2, const L12& a1, con
   L12 X1, Y1, X2, Y2;
   zero12(X1); zero12(Y1); zero12(X2); zero12(Y2);
 #pragma unroll 1
-  for (int i = 0; i < 12; i += 2) {
+  for (int i = 0; i < PSB_NL; i += 2) {
     const uint2 p = ld2(b1 + i), q = ld2(b2 + i);
     mac_shift(X1, Y1, a1, p.x); reduce(X1, Y1);
     mac_shift(X2, Y2, a2, q.x); reduce(X2, Y2);
@@ -145,7 +161,7 @@ __device__ PSB_INL void fp2mul_loop(uint32_t* re, uint32_t* im, const L12& xa, c
   L12 X1, Y1, X2, Y2;
   zero12(X1); zero12(Y1); zero12(X2); zero12(Y2);
 #pragma unroll 1
-  for (int i = 0; i < 12; i += 2) {
+  for (int i = 0; i < PSB_NL; i += 2) {
     const uint2 p = ld2(ya + i), q = ld2(yb + i);
     mac_shift(X1, Y1, xa, p.x); mac(X1, Y1, nxb, q.x); reduce(X1, Y1);
     mac_shift(X2, Y2, xa, q.x); mac(X2, Y2, xb, p.x); reduce(X2, Y2);
@@ -160,7 +176,7 @@ __device__ PSB_INL void mul_loop(uint32_t* r, const L12& a, const uint32_t* b) {
   L12 X, Y;
   zero12(X); zero12(Y);
 #pragma unroll 1
-  for (int i = 0; i < 12; i += 2) {
+  for (int i = 0; i < PSB_NL; i += 2) {
     const uint2 p = ld2(b + i);
     mac_shift(X, Y, a, p.x); reduce(X, Y);
     mac_shift(Y, X, a, p.y); reduce(Y, X);
@@ -171,7 +187,7 @@ __device__ PSB_INL void dot2_loop(uint32_t* r, const L12& a, const uint32_t* b, 
   L12 X, Y;
   zero12(X); zero12(Y);
 #pragma unroll 1
-  for (int i = 0; i < 12; i += 2) {
+  for (int i = 0; i < PSB_NL; i += 2) {
     const uint2 p = ld2(b + i), q = ld2(d + i);
     mac_shift(X, Y, a, p.x); mac(X, Y, c, q.x); reduce(X, Y);
     mac_shift(Y, X, a, p.y); mac(Y, X, c, q.y); reduce(Y, X);
@@ -183,7 +199,9 @@ __device__ PSB_INL void store12(uint32_t* r, const L12& t) {
   uint4* q = reinterpret_cast<uint4*>(r);   // every Fp is 16-byte aligned: three 128-bit stores
   q[0] = make_uint4(t[0], t[1], t[2], t[3]);
   q[1] = make_uint4(t[4], t[5], t[6], t[7]);
+#if PSB_NL == 12
   q[2] = make_uint4(t[8], t[9], t[10], t[11]);
+#endif
 }
 // r = a * b / R mod p  (memory operands; r may alias a or b)
 __device__ PSB_NOINL void mul(uint32_t* r, const uint32_t* a_, const uint32_t* b_) {

@@ -1,4 +1,5 @@
-// curve.cuh -- G1 = E(Fp): y^2 = x^3 + 4 and G2 = E'(Fp2): y^2 = x^3 + 4(1+i), Jacobian coordinates.
+// curve.cuh -- G1 = E(Fp): y^2 = x^3 + b and G2 = E'(Fp2): y^2 = x^3 + b', Jacobian coordinates
+// (BLS12-381: b = 4, b' = 4(1+i); BN254: b = 2, b' = 2/(1+i) = 1 - i).
 //
 // Replaces for the batched path mcl's EcT (reference: third-parties/mcl/include/mcl/ec.hpp:138-284
 // dblJacobi/addJacobi, :77-88 normalizeJacobi, :799 isZero <=> z == 0) and its scalar
@@ -164,6 +165,7 @@ PSB_HD PSB_NOINL void pt_mul_window(Jac<F>& R, const Jac<F>& P, const uint32_t* 
 //   G2: psi(X, Y, Z) = (conj(X) cx, conj(Y) cy, conj(Z)) = [z] Q (z < 0);  k = sum d_i |z|^i, d_i < 2^64, so
 //       k Q = d0 Q - d1 psi(Q) + d2 psi^2(Q) - d3 psi^3(Q).  64 doublings instead of 256.
 
+#if !PSB_IS_BN
 // q = floor(k / lambda), rem = k mod lambda for k < r  (Barrett with mu = floor(2^256 / lambda), deficit <= 2)
 PSB_HD PSB_INL void glv1_split(uint32_t k1[4], uint32_t k2[4], const uint32_t* k) {
   const uint32_t* mu = PSB_K(GLV_MU);
@@ -307,6 +309,11 @@ PSB_HD PSB_NOINL void g2_mul_gls(G2J& R, const G2J& P, const uint32_t* k) {
 // variable-base multiplication used by the protocol kernels
 PSB_HD PSB_INL void pt_mul(G1J& R, const G1J& P, const uint32_t* k) { g1_mul_glv(R, P, k); }
 PSB_HD PSB_INL void pt_mul(G2J& R, const G2J& P, const uint32_t* k) { g2_mul_gls(R, P, k); }
+#else
+// BN254: plain fixed-window multiplication (the GLV / GLS lattices of BN curves are not built; same group element)
+PSB_HD PSB_INL void pt_mul(G1J& R, const G1J& P, const uint32_t* k) { pt_mul_window(R, P, k); }
+PSB_HD PSB_INL void pt_mul(G2J& R, const G2J& P, const uint32_t* k) { pt_mul_window(R, P, k); }
+#endif
 
 // ---- fixed-base windows --------------------------------------------------------------------------
 // Signed w-bit recoding of a 256-bit normal-form scalar (< 2^255): digits in [-2^(w-1), 2^(w-1)],

@@ -33,7 +33,11 @@
 #define PSB_UNROLL
 #endif
 
+#ifdef PSB_CURVE_BN254
+#include "constants_bn254.cuh"
+#else
 #include "constants.cuh"
+#endif
 
 namespace psb {
 
@@ -41,13 +45,17 @@ namespace psb {
 // modulus traits: limbs as compile-time immediates (switch folds after unrolling)
 // ------------------------------------------------------------------------------------------------
 struct FpT {
-  static constexpr int N = 12;
+  static constexpr int N = PSB_NL;
   static constexpr uint32_t N0 = PSB_FP_N0;
   PSB_HD static PSB_INL uint32_t p(int i) {
     switch (i) {
       case 0: return PSB_P0; case 1: return PSB_P1; case 2: return PSB_P2; case 3: return PSB_P3;
+#if PSB_NL == 12
       case 4: return PSB_P4; case 5: return PSB_P5; case 6: return PSB_P6; case 7: return PSB_P7;
       case 8: return PSB_P8; case 9: return PSB_P9; case 10: return PSB_P10; default: return PSB_P11;
+#else
+      case 4: return PSB_P4; case 5: return PSB_P5; case 6: return PSB_P6; default: return PSB_P7;
+#endif
     }
   }
 };
@@ -326,19 +334,22 @@ PSB_HD PSB_INL void redc_n(uint32_t* r, const uint32_t* t) {
 // ------------------------------------------------------------------------------------------------
 // typed wrappers
 // ------------------------------------------------------------------------------------------------
-struct alignas(16) Fp { uint32_t v[12]; };    // canonical, Montgomery (mcl Fp: mcl/include/mcl/fp.hpp:76-106)
-struct alignas(16) FpW { uint32_t v[24]; };   // unreduced double width, value in [0, p*R) (mcl FpDbl, fp_tower.hpp:13-178)
+struct alignas(16) Fp { uint32_t v[PSB_NL]; };    // canonical, Montgomery (mcl Fp: mcl/include/mcl/fp.hpp:76-106)
+struct alignas(16) FpW { uint32_t v[2 * PSB_NL]; };   // unreduced double width, value in [0, p*R) (mcl FpDbl, fp_tower.hpp:13-178)
 struct alignas(16) Fr { uint32_t v[8]; };
 
 // 128-bit limb moves between an Fp in memory (16-byte aligned) and a register array
 PSB_HD PSB_INL void fp_ld(uint32_t* d, const Fp& s) {
 #ifdef __CUDA_ARCH__
   const uint4* q = reinterpret_cast<const uint4*>(s.v);
-  const uint4 v0 = q[0], v1 = q[1], v2 = q[2];
+  const uint4 v0 = q[0], v1 = q[1];
   d[0] = v0.x; d[1] = v0.y; d[2] = v0.z; d[3] = v0.w; d[4] = v1.x; d[5] = v1.y; d[6] = v1.z; d[7] = v1.w;
+#if PSB_NL == 12
+  const uint4 v2 = q[2];
   d[8] = v2.x; d[9] = v2.y; d[10] = v2.z; d[11] = v2.w;
+#endif
 #else
-  for (int i = 0; i < 12; i++) d[i] = s.v[i];
+  for (int i = 0; i < PSB_NL; i++) d[i] = s.v[i];
 #endif
 }
 PSB_HD PSB_INL void fp_st(Fp& d, const uint32_t* t) {
@@ -346,59 +357,61 @@ PSB_HD PSB_INL void fp_st(Fp& d, const uint32_t* t) {
   uint4* q = reinterpret_cast<uint4*>(d.v);
   q[0] = make_uint4(t[0], t[1], t[2], t[3]);
   q[1] = make_uint4(t[4], t[5], t[6], t[7]);
+#if PSB_NL == 12
   q[2] = make_uint4(t[8], t[9], t[10], t[11]);
+#endif
 #else
-  for (int i = 0; i < 12; i++) d.v[i] = t[i];
+  for (int i = 0; i < PSB_NL; i++) d.v[i] = t[i];
 #endif
 }
-PSB_HD PSB_INL void fp_add(Fp& r, const Fp& a, const Fp& b) { uint32_t x[12], y[12]; fp_ld(x, a); fp_ld(y, b); mod_add<FpT>(x, x, y); fp_st(r, x); }
-PSB_HD PSB_INL void fp_sub(Fp& r, const Fp& a, const Fp& b) { uint32_t x[12], y[12]; fp_ld(x, a); fp_ld(y, b); mod_sub<FpT>(x, x, y); fp_st(r, x); }
-PSB_HD PSB_INL void fp_neg(Fp& r, const Fp& a) { uint32_t x[12]; fp_ld(x, a); mod_neg<FpT>(x, x); fp_st(r, x); }
-PSB_HD PSB_INL void fp_dbl(Fp& r, const Fp& a) { uint32_t x[12]; fp_ld(x, a); mod_add<FpT>(x, x, x); fp_st(r, x); }
+PSB_HD PSB_INL void fp_add(Fp& r, const Fp& a, const Fp& b) { uint32_t x[PSB_NL], y[PSB_NL]; fp_ld(x, a); fp_ld(y, b); mod_add<FpT>(x, x, y); fp_st(r, x); }
+PSB_HD PSB_INL void fp_sub(Fp& r, const Fp& a, const Fp& b) { uint32_t x[PSB_NL], y[PSB_NL]; fp_ld(x, a); fp_ld(y, b); mod_sub<FpT>(x, x, y); fp_st(r, x); }
+PSB_HD PSB_INL void fp_neg(Fp& r, const Fp& a) { uint32_t x[PSB_NL]; fp_ld(x, a); mod_neg<FpT>(x, x); fp_st(r, x); }
+PSB_HD PSB_INL void fp_dbl(Fp& r, const Fp& a) { uint32_t x[PSB_NL]; fp_ld(x, a); mod_add<FpT>(x, x, x); fp_st(r, x); }
 // a + b without reduction (< 2p < 2^384): only as an operand of mulw (mcl Fp::addPre)
-PSB_HD PSB_INL void fp_add_nr(Fp& r, const Fp& a, const Fp& b) { add_n<12>(r.v, a.v, b.v); }
-PSB_HD PSB_INL void fp_mulw(FpW& r, const Fp& a, const Fp& b) { mulw_n<12>(r.v, a.v, b.v); }
-PSB_HD PSB_INL void fp_sqrw(FpW& r, const Fp& a) { sqrw_n<12>(r.v, a.v); }
+PSB_HD PSB_INL void fp_add_nr(Fp& r, const Fp& a, const Fp& b) { add_n<PSB_NL>(r.v, a.v, b.v); }
+PSB_HD PSB_INL void fp_mulw(FpW& r, const Fp& a, const Fp& b) { mulw_n<PSB_NL>(r.v, a.v, b.v); }
+PSB_HD PSB_INL void fp_sqrw(FpW& r, const Fp& a) { sqrw_n<PSB_NL>(r.v, a.v); }
 PSB_HD PSB_INL void fp_redc(Fp& r, const FpW& t) { redc_n<FpT>(r.v, t.v); }
 PSB_HD PSB_INL bool fp_is_zero(const Fp& a) { return is_zero_n<FpT>(a.v); }
 PSB_HD PSB_INL bool fp_eq(const Fp& a, const Fp& b) {
   uint32_t o = 0;
   PSB_UNROLL
-  for (int i = 0; i < 12; i++) o |= a.v[i] ^ b.v[i];
+  for (int i = 0; i < PSB_NL; i++) o |= a.v[i] ^ b.v[i];
   return o == 0;
 }
 PSB_HD PSB_INL void fp_set_zero(Fp& r) {
   PSB_UNROLL
-  for (int i = 0; i < 12; i++) r.v[i] = 0;
+  for (int i = 0; i < PSB_NL; i++) r.v[i] = 0;
 }
 PSB_HD PSB_INL void fp_set_one(Fp& r) {
   PSB_UNROLL
-  for (int i = 0; i < 12; i++) r.v[i] = PSB_K(FP_ONE)[i];
+  for (int i = 0; i < PSB_NL; i++) r.v[i] = PSB_K(FP_ONE)[i];
 }
 PSB_HD PSB_INL void fp_cmov(Fp& r, const Fp& a, bool c) {
   PSB_UNROLL
-  for (int i = 0; i < 12; i++) r.v[i] = c ? a.v[i] : r.v[i];
+  for (int i = 0; i < PSB_NL; i++) r.v[i] = c ? a.v[i] : r.v[i];
 }
 
 // double-width add/sub modulo p*R (mcl FpDbl::add / ::sub, fp_tower.hpp:60-100): only the high
 // half needs the correction because p*R has a zero low half.
 PSB_HD PSB_INL void fpw_add(FpW& r, const FpW& a, const FpW& b) {
-  uint32_t s[24];
-  add_n<24>(s, a.v, b.v);  // < 2 p R < 2^768
-  cond_sub_mod<FpT>(s + 12);
+  uint32_t s[2 * PSB_NL];
+  add_n<2 * PSB_NL>(s, a.v, b.v);  // < 2 p R < 2^768
+  cond_sub_mod<FpT>(s + PSB_NL);
   PSB_UNROLL
-  for (int i = 0; i < 24; i++) r.v[i] = s[i];
+  for (int i = 0; i < 2 * PSB_NL; i++) r.v[i] = s[i];
 }
 PSB_HD PSB_INL void fpw_sub(FpW& r, const FpW& a, const FpW& b) {
-  uint32_t s[24];
-  uint32_t borrow = sub_n<24>(s, a.v, b.v);
+  uint32_t s[2 * PSB_NL];
+  uint32_t borrow = sub_n<2 * PSB_NL>(s, a.v, b.v);
   PSB_UNROLL
-  for (int i = 0; i < 12; i++) r.v[i] = s[i];
-  add_mod_masked_n<FpT>(r.v + 12, s + 12, 0u - borrow);
+  for (int i = 0; i < PSB_NL; i++) r.v[i] = s[i];
+  add_mod_masked_n<FpT>(r.v + PSB_NL, s + PSB_NL, 0u - borrow);
 }
 // no-correction variants (caller guarantees 0 <= result < p*R)
-PSB_HD PSB_INL void fpw_add_nr(FpW& r, const FpW& a, const FpW& b) { add_n<24>(r.v, a.v, b.v); }
-PSB_HD PSB_INL void fpw_sub_nr(FpW& r, const FpW& a, const FpW& b) { sub_n<24>(r.v, a.v, b.v); }
+PSB_HD PSB_INL void fpw_add_nr(FpW& r, const FpW& a, const FpW& b) { add_n<2 * PSB_NL>(r.v, a.v, b.v); }
+PSB_HD PSB_INL void fpw_sub_nr(FpW& r, const FpW& a, const FpW& b) { sub_n<2 * PSB_NL>(r.v, a.v, b.v); }
 
 // Montgomery product / square (mcl Fp::mul / Fp::sqr).  Device: even/odd CIOS kernels (cios.cuh).
 }  // namespace psb
@@ -424,25 +437,25 @@ PSB_HD inline void fp_dot2(Fp& r, const Fp& a, const Fp& b, const Fp& c, const F
 __device__ PSB_INL void fp_mul_rr(Fp& r, const Fp& a, const Fp& b) { cios::mul_rr(r.v, a.v, b.v); }
 __device__ PSB_INL void fp_dot2_rr(Fp& r, const Fp& a, const Fp& b, const Fp& c, const Fp& d) { cios::dot2_rr(r.v, a.v, b.v, c.v, d.v); }
 #else
-PSB_HD PSB_INL void fp_mul_rr(Fp& r, const Fp& a, const Fp& b) { FpW t; mulw_n<12>(t.v, a.v, b.v); redc_n<FpT>(r.v, t.v); }
+PSB_HD PSB_INL void fp_mul_rr(Fp& r, const Fp& a, const Fp& b) { FpW t; mulw_n<PSB_NL>(t.v, a.v, b.v); redc_n<FpT>(r.v, t.v); }
 PSB_HD PSB_INL void fp_dot2_rr(Fp& r, const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
-  FpW t, u; mulw_n<12>(t.v, a.v, b.v); mulw_n<12>(u.v, c.v, d.v); add_n<24>(t.v, t.v, u.v); redc_n<FpT>(r.v, t.v);
+  FpW t, u; mulw_n<PSB_NL>(t.v, a.v, b.v); mulw_n<PSB_NL>(u.v, c.v, d.v); add_n<2 * PSB_NL>(t.v, t.v, u.v); redc_n<FpT>(r.v, t.v);
 }
 #endif
 PSB_HD PSB_INL void fp_add_rr(Fp& r, const Fp& a, const Fp& b) { mod_add<FpT>(r.v, a.v, b.v); }
 PSB_HD PSB_INL void fp_sub_rr(Fp& r, const Fp& a, const Fp& b) { mod_sub<FpT>(r.v, a.v, b.v); }
 PSB_HD PSB_INL void fp_dbl_rr(Fp& r, const Fp& a) { mod_add<FpT>(r.v, a.v, a.v); }
-PSB_HD PSB_INL void fp_addnr_rr(Fp& r, const Fp& a, const Fp& b) { add_n<12>(r.v, a.v, b.v); }   // < 2p: multiplicand only
+PSB_HD PSB_INL void fp_addnr_rr(Fp& r, const Fp& a, const Fp& b) { add_n<PSB_NL>(r.v, a.v, b.v); }   // < 2p: multiplicand only
 // p - a for a in [0, p]: in (0, p] (NOT canonical for a = 0) -- multiplicand only
 PSB_HD PSB_INL void fp_pminus_rr(Fp& r, const Fp& a) {
 #ifdef __CUDA_ARCH__
   r.v[0] = ptx::sub_cc(FpT::p(0), a.v[0]);
   PSB_UNROLL
-  for (int i = 1; i < 11; i++) r.v[i] = ptx::subc_cc(FpT::p(i), a.v[i]);
-  r.v[11] = ptx::subc(FpT::p(11), a.v[11]);
+  for (int i = 1; i < PSB_NL - 1; i++) r.v[i] = ptx::subc_cc(FpT::p(i), a.v[i]);
+  r.v[PSB_NL - 1] = ptx::subc(FpT::p(PSB_NL - 1), a.v[PSB_NL - 1]);
 #else
   int64_t c = 0;
-  for (int i = 0; i < 12; i++) { c += (int64_t)FpT::p(i) - a.v[i]; r.v[i] = (uint32_t)c; c >>= 32; }
+  for (int i = 0; i < PSB_NL; i++) { c += (int64_t)FpT::p(i) - a.v[i]; r.v[i] = (uint32_t)c; c >>= 32; }
 #endif
 }
 PSB_HD PSB_INL void fp_get(Fp& d, const Fp& mem) { fp_ld(d.v, mem); }
@@ -452,13 +465,13 @@ PSB_HD PSB_INL void fp_sqr_inl(Fp& r, const Fp& a) { fp_sqr(r, a); }
 
 // a^-1 = a^(p-2) (Fermat; mcl Fp::inv gives the same canonical value, mcl/src/fp.cpp:215-246).
 // Fixed 4-bit windows: constant schedule, no divergence.  inv(0) = 0 like mcl's.
-PSB_HD PSB_NOINL void fp_pow_nib(Fp& r, const Fp& a, const uint32_t* nib /*96 LE nibbles*/) {
+PSB_HD PSB_NOINL void fp_pow_nib(Fp& r, const Fp& a, const uint32_t* nib /*8 * PSB_NL LE nibbles*/) {
   Fp tbl[16];
   fp_set_one(tbl[0]);
   tbl[1] = a;
   for (int i = 2; i < 16; i++) fp_mul(tbl[i], tbl[i - 1], a);
-  Fp acc = tbl[nib[95]];
-  for (int i = 94; i >= 0; i--) {
+  Fp acc = tbl[nib[8 * PSB_NL - 1]];
+  for (int i = 8 * PSB_NL - 2; i >= 0; i--) {
     fp_sqr(acc, acc); fp_sqr(acc, acc); fp_sqr(acc, acc); fp_sqr(acc, acc);
     const uint32_t d = nib[i];
     if (d) fp_mul(acc, acc, tbl[d]);  // nib is a per-kernel constant: uniform branch
@@ -471,13 +484,13 @@ PSB_HD PSB_INL void fp_inv(Fp& r, const Fp& a) { fp_pow_nib(r, a, PSB_K(FP_PM2_N
 PSB_HD PSB_INL void fp_from_mont(Fp& r, const Fp& a) {
   FpW t;
   PSB_UNROLL
-  for (int i = 0; i < 12; i++) { t.v[i] = a.v[i]; t.v[i + 12] = 0; }
+  for (int i = 0; i < PSB_NL; i++) { t.v[i] = a.v[i]; t.v[i + PSB_NL] = 0; }
   fp_redc(r, t);
 }
 PSB_HD PSB_INL void fp_to_mont(Fp& r, const Fp& a) {
   Fp r2;
   PSB_UNROLL
-  for (int i = 0; i < 12; i++) r2.v[i] = PSB_K(FP_R2)[i];
+  for (int i = 0; i < PSB_NL; i++) r2.v[i] = PSB_K(FP_R2)[i];
   fp_mul(r, a, r2);
 }
 

@@ -88,11 +88,12 @@ PSB_HD PSB_NOINL void sha512(uint64_t h[8], const uint8_t* msg, size_t len) {
 
 // Fp::setHashOf(msg): canonical Montgomery element
 PSB_HD PSB_NOINL void fp_set_hash_of(Fp& t, const uint8_t* msg, size_t len) {
+  Fp n;
+#if PSB_FP_BITS > 256
   uint64_t h[8];
   sha512(h, msg, len);
-  Fp n;
   // the first 48 digest BYTES as a little-endian integer: digest byte j = byte (7 - j%8) of word j/8
-  for (int i = 0; i < 12; i++) {
+  for (int i = 0; i < PSB_NL; i++) {
     uint32_t v = 0;
     for (int b = 0; b < 4; b++) {
       const int j = 4 * i + b;
@@ -101,9 +102,19 @@ PSB_HD PSB_NOINL void fp_set_hash_of(Fp& t, const uint8_t* msg, size_t len) {
     }
     n.v[i] = v;
   }
-  n.v[11] &= (1u << 29) - 1u;                       // 381 bits
-  uint32_t tmp[12];
-  if (sub_mod_n<FpT>(tmp, n.v) == 0) n.v[11] &= (1u << 28) - 1u;   // >= p: 380 bits
+#else
+  // fields of at most 256 bits hash with SHA-256 (mcl/src/fp.cpp:552-556): 32 digest bytes, little-endian
+  Sha256 s;
+  sha256_init(s);
+  sha256_update(s, msg, len);
+  uint32_t d[8];
+  sha256_final(s, d);
+  for (int i = 0; i < PSB_NL; i++) n.v[i] = bswap32(d[i]);
+#endif
+  constexpr int top = PSB_FP_BITS - 32 * (PSB_NL - 1);              // bits of p in the top limb
+  n.v[PSB_NL - 1] &= (1u << top) - 1u;                              // bitSize(p) bits
+  uint32_t tmp[PSB_NL];
+  if (sub_mod_n<FpT>(tmp, n.v) == 0) n.v[PSB_NL - 1] &= (1u << (top - 1)) - 1u;   // >= p: one bit less
   fp_to_mont(t, n);
 }
 
@@ -116,7 +127,7 @@ PSB_HD PSB_NOINL int fp_legendre(const Fp& a) {
   return fp_eq(r, one) ? 1 : -1;
 }
 
-// MapTo::calcBN for G1 (b = 4).  false for the exceptional inputs (t = 0, t^2 + 5 = 0), like mcl.
+// MapTo::calcBN for G1.  false for the exceptional inputs (t = 0, t^2 + b + 1 = 0), like mcl.
 PSB_HD PSB_NOINL bool map_to_g1(G1J& P, const Fp& t) {
   pt_set_zero(P);
   const int leg = fp_legendre(t);
@@ -124,8 +135,8 @@ PSB_HD PSB_NOINL bool map_to_g1(G1J& P, const Fp& t) {
   const bool negative = leg < 0;
   Fp one, four, c1, c2, w, x, y, u;
   fp_set_one(one);
-  fp_dbl(four, one); fp_dbl(four, four);
-  for (int i = 0; i < 12; i++) { c1.v[i] = PSB_K(MAPTO_C1)[i]; c2.v[i] = PSB_K(MAPTO_C2)[i]; }
+  fp_set_curve_b(four);                   // the curve constant b (4 for BLS12-381, 2 for BN254)
+  for (int i = 0; i < PSB_NL; i++) { c1.v[i] = PSB_K(MAPTO_C1)[i]; c2.v[i] = PSB_K(MAPTO_C2)[i]; }
   fp_sqr(w, t);
   fp_add(w, w, four);
   fp_add(w, w, one);                      // t^2 + b + 1
@@ -137,7 +148,7 @@ PSB_HD PSB_NOINL bool map_to_g1(G1J& P, const Fp& t) {
     if (i == 0) { fp_mul(x, t, w); fp_neg(x, x); fp_add(x, x, c2); }
     else if (i == 1) { fp_neg(x, x); fp_sub(x, x, one); }
     else { fp_sqr(x, w); fp_inv(x, x); fp_add(x, x, one); }
-    fp_sqr(u, x); fp_mul(u, u, x); fp_add(u, u, four);     // x^3 + 4
+    fp_sqr(u, x); fp_mul(u, u, x); fp_add(u, u, four);     // x^3 + b
     if (fp_sqrt(y, u)) {
       if (negative) fp_neg(y, y);
       P.x = x; P.y = y; fp_set_one(P.z);
@@ -149,9 +160,13 @@ PSB_HD PSB_NOINL bool map_to_g1(G1J& P, const Fp& t) {
 
 // P <- [(z-1)^2 / 3] P, plain windowed multiplication (valid for any curve point), normalised
 PSB_HD PSB_NOINL void g1_clear_cofactor(G1J& R, const G1J& P) {
+#if PSB_IS_BN
+  R = P;                                  // BN curves: E(Fp) has prime order, the map output is already in G1 with z = 1
+#else
   G1J T;
   pt_mul_window(T, P, PSB_K(G1_COFACTOR));
   pt_normalize(R, T);
+#endif
 }
 
 // hashAndMapToG1(msg): normalised point; returns false only for the exceptional hash values mcl asserts against

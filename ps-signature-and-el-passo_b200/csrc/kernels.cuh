@@ -32,12 +32,14 @@ __global__ void __launch_bounds__(kBlock) k_test_op(int op, size_t n, int s0, in
 }
 
 // ---- micro-benchmarks -----------------------------------------------------------------------------
+// keeps random limb patterns below p (top limb of p: 0x1a0111ea for BLS12-381, 0x25236482 for BN254)
+constexpr uint32_t kTopMask = 0x0fffffffu;
 __global__ void __launch_bounds__(256) k_bench_fp(int kind, int iters, const uint32_t* seed, uint32_t* sink) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (kind == 0 || kind == 1) {
     Fp x, y;
-    for (int j = 0; j < 12; j++) { x.v[j] = seed[j] ^ (uint32_t)i; y.v[j] = seed[12 + j]; }
-    x.v[11] &= 0x0fffffffu; y.v[11] &= 0x0fffffffu;
+    for (int j = 0; j < PSB_NL; j++) { x.v[j] = seed[j] ^ (uint32_t)i; y.v[j] = seed[PSB_NL + j]; }
+    x.v[PSB_NL - 1] &= kTopMask; y.v[PSB_NL - 1] &= kTopMask;
     for (int it = 0; it < iters; it++) {
       if (kind == 0) fp_mul_inl(x, x, y); else fp_sqr_inl(x, x);
     }
@@ -45,15 +47,15 @@ __global__ void __launch_bounds__(256) k_bench_fp(int kind, int iters, const uin
   } else if (kind == 2) {
     Fp2 x, y;
     uint32_t* px = (uint32_t*)&x; uint32_t* py = (uint32_t*)&y;
-    for (int j = 0; j < 24; j++) { px[j] = seed[j % 12] ^ (uint32_t)i; py[j] = seed[12 + (j % 12)]; }
-    x.a.v[11] &= 0x0fffffffu; x.b.v[11] &= 0x0fffffffu; y.a.v[11] &= 0x0fffffffu; y.b.v[11] &= 0x0fffffffu;
+    for (int j = 0; j < 2 * PSB_NL; j++) { px[j] = seed[j % PSB_NL] ^ (uint32_t)i; py[j] = seed[PSB_NL + (j % PSB_NL)]; }
+    x.a.v[PSB_NL - 1] &= kTopMask; x.b.v[PSB_NL - 1] &= kTopMask; y.a.v[PSB_NL - 1] &= kTopMask; y.b.v[PSB_NL - 1] &= kTopMask;
     for (int it = 0; it < iters; it++) fp2_mul(x, x, y);
     if (x.a.v[0] == 0xdeadbeefu) sink[0] = x.a.v[1];
   } else if (kind == 3) {
     Fp12 x, y;
     uint32_t* px = (uint32_t*)&x; uint32_t* py = (uint32_t*)&y;
-    for (int j = 0; j < 144; j++) { px[j] = seed[j % 12] ^ (uint32_t)i; py[j] = seed[12 + (j % 12)]; }
-    for (int j = 11; j < 144; j += 12) { px[j] &= 0x0fffffffu; py[j] &= 0x0fffffffu; }
+    for (int j = 0; j < 12 * PSB_NL; j++) { px[j] = seed[j % PSB_NL] ^ (uint32_t)i; py[j] = seed[PSB_NL + (j % PSB_NL)]; }
+    for (int j = PSB_NL - 1; j < 12 * PSB_NL; j += PSB_NL) { px[j] &= kTopMask; py[j] &= kTopMask; }
     for (int it = 0; it < iters; it++) fp12_mul(x, x, y);
     if (x.a.a.a.v[0] == 0xdeadbeefu) sink[0] = x.a.a.a.v[1];
   }
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(256) k_bench_mad(int kind, int iters, const ui
     // the multiplier's own instruction form: carry-chained wide MACs (IMAD.WIDE.U32.X rows of six, as in cios.cuh),
     // three independent accumulator pairs = six independent carry chains per thread.  72 MAC32 per iteration.
     cios::L12 E1, O1, E2, O2, E3, O3, av;
-    for (int j = 0; j < 12; j++) { E1[j] = seed[j] + t; O1[j] = seed[12 + j] ^ t; E2[j] = E1[j] + 1; O2[j] = O1[j] + 2; E3[j] = E1[j] ^ 5; O3[j] = O1[j] ^ 9; av[j] = seed[j] * (t | 1); }
+    for (int j = 0; j < PSB_NL; j++) { E1[j] = seed[j] + t; O1[j] = seed[PSB_NL + j] ^ t; E2[j] = E1[j] + 1; O2[j] = O1[j] + 2; E3[j] = E1[j] ^ 5; O3[j] = O1[j] ^ 9; av[j] = seed[j] * (t | 1); }
     for (int it = 0; it < iters; it++) {
       cios::mac(E1, O1, av, b);
       cios::mac(E2, O2, av, a);
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(256) k_bench_mad(int kind, int iters, const ui
       a += E1[0];
     }
     uint32_t s = 0;
-    for (int j = 0; j < 12; j++) s ^= E1[j] ^ O1[j] ^ E2[j] ^ O2[j] ^ E3[j] ^ O3[j];
+    for (int j = 0; j < PSB_NL; j++) s ^= E1[j] ^ O1[j] ^ E2[j] ^ O2[j] ^ E3[j] ^ O3[j];
     if (s == 0xdeadbeefu) sink[0] = s;
 #endif
   } else {
@@ -298,8 +300,8 @@ __global__ void __launch_bounds__(kBlock) k_randomize(size_t N, const G1J* sig1,
   out1[lane] = ra;
   out2[lane] = rb;
   if (ser) {
-    g1_serialize_norm(ser + lane * 96, ra);
-    g1_serialize_norm(ser + lane * 96 + 48, rb);
+    g1_serialize_norm(ser + lane * 2 * kFpBytes, ra);
+    g1_serialize_norm(ser + lane * 2 * kFpBytes + kFpBytes, rb);
   }
 }
 
@@ -353,8 +355,8 @@ __global__ void __launch_bounds__(kBlock) k_provide_id(size_t N, int n, int w, c
   sig1[lane] = s1;
   sig2[lane] = s2;
   if (ser) {
-    g1_serialize_norm(ser + lane * 96, s1);
-    g1_serialize_norm(ser + lane * 96 + 48, s2);
+    g1_serialize_norm(ser + lane * 2 * kFpBytes, s1);
+    g1_serialize_norm(ser + lane * 2 * kFpBytes + kFpBytes, s2);
   }
 }
 

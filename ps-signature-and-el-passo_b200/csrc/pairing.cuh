@@ -1,5 +1,5 @@
-// pairing.cuh -- optimal-ate pairing on BLS12-381: a two-pairing ("multi") Miller loop and mcl's
-// final exponentiation.
+// pairing.cuh -- optimal-ate pairing on BLS12-381 (M-type twist, loop over |z|) and BN254 (D-type twist, loop over
+// |6z+2| plus the two Frobenius additions): a two-pairing ("multi") Miller loop and mcl's final exponentiation.
 //
 // Reference semantics (third-parties/mcl/include/mcl/bn.hpp): millerLoop :1660-1710,
 // precomputeG2 :1719-1758, precomputedMillerLoop2mixed :1827-1897, finalExp :1643-1659 =
@@ -18,18 +18,44 @@ namespace psb {
 // one precomputed line of the fixed G2 argument (affine slope form):
 //   l(P) = c0 + (nl * xP) w^2 + yP w^3,   nl = -lambda,  c0 = lambda*xT - yT
 struct FixedLine { Fp2 nl, c0; };
-constexpr int kMillerSteps = 63 + 5;  // doublings + additions for |z| = 0xd201000000010000
+// doublings + additions of the loop parameter (BLS12-381: |z| = 0xd201000000010000 -> 63 + 5; BN254: |6z+2| =
+// 0x18300000000000004 -> 64 + 4, plus the two closing additions of pi(Q) and -pi^2(Q), bn.hpp:1698-1709)
+constexpr int kMillerSteps = PSB_ML_NBITS + PSB_ML_ADDS + (PSB_IS_BN ? 2 : 0);
 
 struct G2H { Fp2 x, y, z; };  // homogeneous projective: (X/Z, Y/Z)
 
 PSB_HD PSB_INL bool z_bit(int i) { return (PSB_Z_ABS >> i) & 1ull; }
+// bit i of the Miller loop parameter (65 bits for BN254)
+PSB_HD PSB_INL bool ml_bit(int i) { return i >= 64 ? ((PSB_ML_HI >> (i - 64)) & 1ull) : ((PSB_ML_LO >> i) & 1ull); }
 
-// (4 xi) * 3 * c = 12 xi c   (3 b' C with b' = 4 xi)
-PSB_HD PSB_INL void fp2_mul_12xi(Fp2& r, const Fp2& c) {
+// 3 b' c with b' the constant of the twist E'
+#if PSB_TWIST_MTYPE
+// b' = 4 xi:  (4 xi) * 3 * c = 12 xi c
+PSB_HD PSB_INL void fp2_mul_3bt(Fp2& r, const Fp2& c) {
   Fp2 t, u;
   fp2_mul_xi(t, c);
   fp2_dbl(t, t); fp2_dbl(t, t);      // 4 xi c
   fp2_dbl(u, t); fp2_add(r, u, t);   // 12 xi c
+}
+#else
+// b' = 2 / xi = 1 - i (mcl twist_b shortcut, bn.hpp:950-953):  (a + b i)(1 - i) = (a + b) + (b - a) i
+PSB_HD PSB_INL void fp2_mul_3bt(Fp2& r, const Fp2& c) {
+  Fp2 t, u;
+  fp_add(t.a, c.a, c.b);
+  fp_sub(t.b, c.b, c.a);
+  fp2_dbl(u, t); fp2_add(r, u, t);
+}
+#endif
+
+// f *= line, the line given as the three Fp2 values the step functions produce: c0 (constant term), c2 (the xP term),
+// c3 (the yP term).  M-type twist: c0 + c2 w^2 + c3 w^3.  D-type twist: the untwist multiplies instead of dividing,
+// l(P) = yP - lambda xP w + (lambda xT - yT) w^3, i.e. the same three values sit at w^3, w^1 and w^0.
+PSB_HD PSB_INL void ml_mul_line(Fp12& f, const Fp2& c0, const Fp2& c2, const Fp2& c3) {
+#if PSB_TWIST_MTYPE
+  fp12_mul_line(f, c0, c2, c3);
+#else
+  fp12_mul_line_d(f, c3, c2, c0);
+#endif
 }
 
 // T <- 2T and the tangent line at T evaluated at P = (xP, yP):
@@ -41,7 +67,7 @@ PSB_HD PSB_NOINL void ml_dbl_step(G2H& T, Fp2& c0, Fp2& c2, Fp2& c3, const Fp& x
   fp2_sqr(C, T.z);
   fp2_sqr(J, T.x);
   fp2_add(H, T.y, T.z); fp2_sqr(H, H); fp2_sub(H, H, B); fp2_sub(H, H, C);   // 2YZ
-  fp2_mul_12xi(E, C);                   // 3 b' Z^2
+  fp2_mul_3bt(E, C);                    // 3 b' Z^2
   fp2_dbl(F, E); fp2_add(F, F, E);      // 3E
   // line
   fp2_sub(c0, E, B);
@@ -82,6 +108,19 @@ PSB_HD PSB_NOINL void ml_add_step(G2H& T, Fp2& c0, Fp2& c2, Fp2& c3, const G2H& 
   fp2_mul(T.z, l3, W);
 }
 
+#if PSB_IS_BN
+// pi on the twist (mcl Frobenius(G2), bn.hpp:2155-2162): (x, y) -> (conj(x) cx, conj(y) cy); homogeneous: conj(Z)
+PSB_HD PSB_INL void fp2_load_const(Fp2& c, const uint32_t* w) {
+  for (int i = 0; i < PSB_NL; i++) { c.a.v[i] = w[i]; c.b.v[i] = w[PSB_NL + i]; }
+}
+PSB_HD PSB_NOINL void g2h_frobenius(G2H& Q) {
+  Fp2 c;
+  fp2_conj(Q.x, Q.x); fp2_conj(Q.y, Q.y); fp2_conj(Q.z, Q.z);
+  fp2_load_const(c, PSB_K(PSI_CX)); fp2_mul(Q.x, Q.x, c);
+  fp2_load_const(c, PSB_K(PSI_CY)); fp2_mul(Q.y, Q.y, c);
+}
+#endif
+
 // f = ML(P1, Q1) * ML(P2, Q2_fixed), conjugated for z < 0.
 //   P1 = (x1, y1), P2 = (x2, y2): affine Fp coordinates; an infinite P is passed as (0, 0) (its
 //   lines fall into Fp2 and die in the final exponentiation, like mcl: bls12_test.cpp:288-296).
@@ -99,41 +138,62 @@ PSB_HD PSB_NOINL void miller_loop2(Fp12& f, const Fp& x1, const Fp& y1, const G2
   fp12_set_one(f);
   Fp2 c0, c2, c3;
   int li = 0;
-  for (int i = 62; i >= 0; i--) {
-    if (i != 62) fp12_sqr(f, f);
+  for (int i = PSB_ML_NBITS - 1; i >= 0; i--) {
+    if (i != PSB_ML_NBITS - 1) fp12_sqr(f, f);
     if (use1) {
       ml_dbl_step(T, c0, c2, c3, x1, y1);
-      fp12_mul_line(f, c0, c2, c3);
+      ml_mul_line(f, c0, c2, c3);
     }
     if (use2) {
       const FixedLine L = lines2[li];
       fp2_mul_fp(c2, L.nl, x2);
       c3.a = y2; fp_set_zero(c3.b);
-      fp12_mul_line(f, L.c0, c2, c3);
+      ml_mul_line(f, L.c0, c2, c3);
     }
     li++;
-    if (z_bit(i)) {
+    if (ml_bit(i)) {
       if (use1) {
         ml_add_step(T, c0, c2, c3, Q, x1, y1);
-        fp12_mul_line(f, c0, c2, c3);
+        ml_mul_line(f, c0, c2, c3);
       }
       if (use2) {
         const FixedLine L = lines2[li];
         fp2_mul_fp(c2, L.nl, x2);
         c3.a = y2; fp_set_zero(c3.b);
-        fp12_mul_line(f, L.c0, c2, c3);
+        ml_mul_line(f, L.c0, c2, c3);
       }
       li++;
     }
   }
   fp6_neg(f.b, f.b);  // z < 0  (bn.hpp:1695-1697)
+#if PSB_IS_BN
+  // BN tail (bn.hpp:1698-1709): T <- -T (z < 0), then the chords through pi(Q) and -pi^2(Q)
+  if (use1) {
+    fp2_neg(T.y, T.y);
+    g2h_frobenius(Q);
+    ml_add_step(T, c0, c2, c3, Q, x1, y1);
+    ml_mul_line(f, c0, c2, c3);
+    g2h_frobenius(Q);
+    fp2_neg(Q.y, Q.y);
+    ml_add_step(T, c0, c2, c3, Q, x1, y1);
+    ml_mul_line(f, c0, c2, c3);
+  }
+  if (use2) {
+    for (int t = 0; t < 2; t++) {
+      const FixedLine L = lines2[li++];
+      fp2_mul_fp(c2, L.nl, x2);
+      c3.a = y2; fp_set_zero(c3.b);
+      ml_mul_line(f, L.c0, c2, c3);
+    }
+  }
+#endif
 }
 
 // precompute the kMillerSteps affine lines of a fixed Q (affine, not infinity).  One thread, once per key.
 PSB_HD PSB_NOINL void precompute_fixed_lines(FixedLine* out, const G2A& Q) {
   Fp2 x = Q.x, y = Q.y, lam, t, u, x3;
   int li = 0;
-  for (int i = 62; i >= 0; i--) {
+  for (int i = PSB_ML_NBITS - 1; i >= 0; i--) {
     // tangent: lam = 3x^2 / 2y
     fp2_sqr(t, x); fp2_dbl(u, t); fp2_add(t, t, u);
     fp2_dbl(u, y); fp2_inv(u, u); fp2_mul(lam, t, u);
@@ -143,7 +203,7 @@ PSB_HD PSB_NOINL void precompute_fixed_lines(FixedLine* out, const G2A& Q) {
     fp2_sqr(x3, lam); fp2_sub(x3, x3, x); fp2_sub(x3, x3, x);
     fp2_sub(t, x, x3); fp2_mul(t, lam, t); fp2_sub(y, t, y);
     x = x3;
-    if (z_bit(i)) {
+    if (ml_bit(i)) {
       // chord through T and Q: lam = (yQ - y)/(xQ - x)
       fp2_sub(t, Q.y, y); fp2_sub(u, Q.x, x); fp2_inv(u, u); fp2_mul(lam, t, u);
       fp2_neg(out[li].nl, lam);
@@ -154,12 +214,29 @@ PSB_HD PSB_NOINL void precompute_fixed_lines(FixedLine* out, const G2A& Q) {
       x = x3;
     }
   }
+#if PSB_IS_BN
+  fp2_neg(y, y);                                        // T <- -T
+  Fp2 qx = Q.x, qy = Q.y, c;
+  for (int k = 0; k < 2; k++) {
+    fp2_conj(qx, qx); fp2_conj(qy, qy);
+    fp2_load_const(c, PSB_K(PSI_CX)); fp2_mul(qx, qx, c);
+    fp2_load_const(c, PSB_K(PSI_CY)); fp2_mul(qy, qy, c);
+    if (k == 1) fp2_neg(qy, qy);                        // pi(Q), then -pi^2(Q)
+    fp2_sub(t, qy, y); fp2_sub(u, qx, x); fp2_inv(u, u); fp2_mul(lam, t, u);
+    fp2_neg(out[li].nl, lam);
+    fp2_mul(t, lam, qx); fp2_sub(out[li].c0, t, qy);
+    li++;
+    fp2_sqr(x3, lam); fp2_sub(x3, x3, x); fp2_sub(x3, x3, qx);
+    fp2_sub(t, x, x3); fp2_mul(t, lam, t); fp2_sub(y, t, y);
+    x = x3;
+  }
+#endif
 }
 
 // y = x^z (z < 0): x^|z| by square-and-multiply with cyclotomic squarings, then conjugate
 PSB_HD PSB_NOINL void pow_z(Fp12& y, const Fp12& x) {
   Fp12 acc = x;
-  for (int i = 62; i >= 0; i--) {
+  for (int i = PSB_Z_NBITS - 1; i >= 0; i--) {
     fp12_cyclo_sqr(acc, acc);
     if (z_bit(i)) fp12_mul(acc, acc, x);
   }
@@ -175,6 +252,32 @@ PSB_HD PSB_NOINL void final_exp(Fp12& y, const Fp12& x) {
   fp12_inv(a1, a0);
   fp12_conj(a0, a0);            // ^(p^6)
   fp12_mul(t, a1, a0);
+#if PSB_IS_BN
+  // hard part (expHardPartBN, bn.hpp:1576-1621): t^(d 2z(6z^2+3z+1)), d = (p^4 - p^2 + 1)/r  (Fuentes-Castaneda et al.)
+  Fp12 a, b;
+  pow_z(b, t);                  // t^z
+  fp12_cyclo_sqr(b, b);         // t^2z
+  fp12_cyclo_sqr(a, b);         // t^4z
+  fp12_mul(a, a, b);            // t^6z
+  pow_z(a2, a);                 // t^(6z^2)
+  fp12_mul(a, a, a2);
+  fp12_cyclo_sqr(a3, a2);       // t^(12z^2)
+  pow_z(a3, a3);                // t^(12z^3)
+  fp12_mul(a, a, a3);
+  fp12_conj(b, b);
+  fp12_mul(b, b, a);
+  fp12_mul(a2, a2, a);
+  fp12_frobenius(a, a, 2);
+  fp12_mul(a, a, a2);
+  fp12_mul(a, a, t);
+  fp12_conj(a4, t);
+  fp12_mul(a4, a4, b);
+  fp12_frobenius(b, b, 1);
+  fp12_mul(a, a, b);
+  fp12_frobenius(a4, a4, 3);
+  fp12_mul(y, a4, a);
+  (void)a5; (void)a7;
+#else
   // hard part (expHardPartBLS12, bn.hpp:1508-1555)
   fp12_conj(a0, t);             // t^-1
   fp12_cyclo_sqr(a1, a0);       // t^-2
@@ -198,6 +301,7 @@ PSB_HD PSB_NOINL void final_exp(Fp12& y, const Fp12& x) {
   fp12_mul(a7, a7, t);          // t^c3,  c3 = z^2-2z+1
   fp12_frobenius(a7, a7, 3);
   fp12_mul(y, a7, a1);
+#endif
 }
 
 }  // namespace psb

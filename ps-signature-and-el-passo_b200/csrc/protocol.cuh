@@ -19,32 +19,34 @@
 namespace psb {
 
 // ---- serialisation (mcl compressed little-endian form, ec.hpp:849-896, non-ETH mode) -----------------
-// G1: x as 48 LE bytes of the NORMAL form, bit 7 of the last byte = y odd; infinity = 48 zero bytes.
+// kFpBytes = 48 (BLS12-381) or 32 (BN254).
+// G1: x as kFpBytes LE bytes of the NORMAL form, bit 7 of the last byte = y odd; infinity = all-zero bytes.
+constexpr int kFpBytes = 4 * PSB_NL;
 PSB_HD PSB_NOINL void g1_serialize_norm(uint8_t* out, const G1J& P /*normalised or zero*/) {
-  if (fp_is_zero(P.z)) { for (int i = 0; i < 48; i++) out[i] = 0; return; }
+  if (fp_is_zero(P.z)) { for (int i = 0; i < kFpBytes; i++) out[i] = 0; return; }
   Fp x, y;
   fp_from_mont(x, P.x);
   fp_from_mont(y, P.y);
-  for (int i = 0; i < 12; i++) {
+  for (int i = 0; i < PSB_NL; i++) {
     out[4 * i] = (uint8_t)x.v[i]; out[4 * i + 1] = (uint8_t)(x.v[i] >> 8);
     out[4 * i + 2] = (uint8_t)(x.v[i] >> 16); out[4 * i + 3] = (uint8_t)(x.v[i] >> 24);
   }
-  if (y.v[0] & 1u) out[47] |= 0x80;
+  if (y.v[0] & 1u) out[kFpBytes - 1] |= 0x80;
 }
 // G2: x.a || x.b (96 bytes), parity of y.a (fp_tower.hpp:312) in bit 7 of the last byte.
 PSB_HD PSB_NOINL void g2_serialize_norm(uint8_t* out, const G2J& P) {
-  if (fp2_is_zero(P.z)) { for (int i = 0; i < 96; i++) out[i] = 0; return; }
+  if (fp2_is_zero(P.z)) { for (int i = 0; i < 2 * kFpBytes; i++) out[i] = 0; return; }
   Fp xa, xb, ya;
   fp_from_mont(xa, P.x.a);
   fp_from_mont(xb, P.x.b);
   fp_from_mont(ya, P.y.a);
-  for (int i = 0; i < 12; i++) {
+  for (int i = 0; i < PSB_NL; i++) {
     out[4 * i] = (uint8_t)xa.v[i]; out[4 * i + 1] = (uint8_t)(xa.v[i] >> 8);
     out[4 * i + 2] = (uint8_t)(xa.v[i] >> 16); out[4 * i + 3] = (uint8_t)(xa.v[i] >> 24);
-    out[48 + 4 * i] = (uint8_t)xb.v[i]; out[48 + 4 * i + 1] = (uint8_t)(xb.v[i] >> 8);
-    out[48 + 4 * i + 2] = (uint8_t)(xb.v[i] >> 16); out[48 + 4 * i + 3] = (uint8_t)(xb.v[i] >> 24);
+    out[kFpBytes + 4 * i] = (uint8_t)xb.v[i]; out[kFpBytes + 4 * i + 1] = (uint8_t)(xb.v[i] >> 8);
+    out[kFpBytes + 4 * i + 2] = (uint8_t)(xb.v[i] >> 16); out[kFpBytes + 4 * i + 3] = (uint8_t)(xb.v[i] >> 24);
   }
-  if (ya.v[0] & 1u) out[95] |= 0x80;
+  if (ya.v[0] & 1u) out[2 * kFpBytes - 1] |= 0x80;
 }
 
 // ---- deserialisation = point decompression (mcl EcT::load, ec.hpp:924-1057, IoSerialize, non-ETH mode) ---------------
@@ -53,10 +55,10 @@ PSB_HD PSB_NOINL void g2_serialize_norm(uint8_t* out, const G2J& P) {
 // 48 little-endian bytes -> canonical Montgomery Fp; false if the value is >= p (Fp::setArray, NoMask: fp.hpp:342-345)
 PSB_HD PSB_INL bool fp_from_le_bytes(Fp& r, const uint8_t* b, uint8_t last_mask) {
   Fp n;
-  for (int i = 0; i < 12; i++)
+  for (int i = 0; i < PSB_NL; i++)
     n.v[i] = (uint32_t)b[4 * i] | ((uint32_t)b[4 * i + 1] << 8) | ((uint32_t)b[4 * i + 2] << 16) |
-             ((uint32_t)(i == 11 ? (b[47] & last_mask) : b[4 * i + 3]) << 24);
-  uint32_t t[12];
+             ((uint32_t)(i == PSB_NL - 1 ? (b[kFpBytes - 1] & last_mask) : b[4 * i + 3]) << 24);
+  uint32_t t[PSB_NL];
   if (sub_mod_n<FpT>(t, n.v) == 0) return false;   // n >= p
   fp_to_mont(r, n);
   return true;
@@ -77,15 +79,15 @@ PSB_HD PSB_INL bool fp_is_odd(const Fp& a) {       // parity of the NORMAL form 
   return (n.v[0] & 1u) != 0;
 }
 PSB_HD PSB_INL void fp_div2(Fp& r, const Fp& a) {   // Fp::divBy2 (works on the Montgomery representative)
-  uint32_t t[13];
-  for (int i = 0; i < 12; i++) t[i] = a.v[i];
-  t[12] = 0;
+  uint32_t t[PSB_NL + 1];
+  for (int i = 0; i < PSB_NL; i++) t[i] = a.v[i];
+  t[PSB_NL] = 0;
   if (a.v[0] & 1u) {
     uint64_t c = 0;
-    for (int i = 0; i < 12; i++) { c += (uint64_t)t[i] + FpT::p(i); t[i] = (uint32_t)c; c >>= 32; }
-    t[12] = (uint32_t)c;
+    for (int i = 0; i < PSB_NL; i++) { c += (uint64_t)t[i] + FpT::p(i); t[i] = (uint32_t)c; c >>= 32; }
+    t[PSB_NL] = (uint32_t)c;
   }
-  for (int i = 0; i < 12; i++) r.v[i] = (t[i] >> 1) | (t[i + 1] << 31);
+  for (int i = 0; i < PSB_NL; i++) r.v[i] = (t[i] >> 1) | (t[i + 1] << 31);
 }
 // mcl Fp2::squareRoot (fp_tower.hpp:320-352), same root selection
 PSB_HD PSB_NOINL bool fp2_sqrt(Fp2& y, const Fp2& x) {
@@ -111,18 +113,25 @@ PSB_HD PSB_NOINL bool fp2_sqrt(Fp2& y, const Fp2& x) {
   fp_mul(y.b, x.b, t2);
   return true;
 }
+// the curve constant b (4 or 2) as a Montgomery element
+PSB_HD PSB_INL void fp_set_curve_b(Fp& r) {
+  fp_set_one(r); fp_dbl(r, r);
+#if PSB_CURVE_B == 4
+  fp_dbl(r, r);
+#endif
+}
 // G1::deserialize: all-zero = infinity; bit 7 of the last byte = y odd; x >= p or x^3 + 4 a non-residue -> false
 PSB_HD PSB_NOINL bool g1_deserialize(G1J& P, const uint8_t* b) {
   uint8_t o = 0;
-  for (int i = 0; i < 48; i++) o |= b[i];
+  for (int i = 0; i < kFpBytes; i++) o |= b[i];
   pt_set_zero(P);
   if (o == 0) return true;
-  const bool y_odd = (b[47] >> 7) != 0;
-  Fp x, y, t, four;
+  const bool y_odd = (b[kFpBytes - 1] >> 7) != 0;
+  Fp x, y, t, cb;
   if (!fp_from_le_bytes(x, b, 0x7f)) return false;
   fp_sqr(t, x); fp_mul(t, t, x);
-  fp_set_one(four); fp_dbl(four, four); fp_dbl(four, four);
-  fp_add(t, t, four);
+  fp_set_curve_b(cb);
+  fp_add(t, t, cb);
   if (!fp_sqrt(y, t)) return false;
   if (fp_is_odd(y) != y_odd) fp_neg(y, y);
   P.x = x; P.y = y; fp_set_one(P.z);
@@ -131,16 +140,20 @@ PSB_HD PSB_NOINL bool g1_deserialize(G1J& P, const uint8_t* b) {
 // G2::deserialize: x.a || x.b (96 bytes), flag in the last byte, parity of y.a (Fp2::isOdd, fp_tower.hpp:312)
 PSB_HD PSB_NOINL bool g2_deserialize(G2J& P, const uint8_t* b) {
   uint8_t o = 0;
-  for (int i = 0; i < 96; i++) o |= b[i];
+  for (int i = 0; i < 2 * kFpBytes; i++) o |= b[i];
   pt_set_zero(P);
   if (o == 0) return true;
-  const bool y_odd = (b[95] >> 7) != 0;
+  const bool y_odd = (b[2 * kFpBytes - 1] >> 7) != 0;
   Fp2 x, y, t, bb;
   if (!fp_from_le_bytes(x.a, b, 0xff)) return false;
-  if (!fp_from_le_bytes(x.b, b + 48, 0x7f)) return false;
+  if (!fp_from_le_bytes(x.b, b + kFpBytes, 0x7f)) return false;
   fp2_sqr(t, x); fp2_mul(t, t, x);
-  fp_set_one(bb.a); fp_dbl(bb.a, bb.a); fp_dbl(bb.a, bb.a);    // b' = 4 xi = 4 + 4i
+#if PSB_TWIST_MTYPE
+  fp_set_curve_b(bb.a);                                          // b' = 4 xi = 4 + 4i
   bb.b = bb.a;
+#else
+  fp_set_one(bb.a); fp_neg(bb.b, bb.a);                          // b' = 2 / xi = 1 - i
+#endif
   fp2_add(t, t, bb);
   if (!fp2_sqrt(y, t)) return false;
   if (fp_is_odd(y.a) != y_odd) fp2_neg(y, y);
@@ -201,14 +214,14 @@ PSB_HD PSB_INL void sha_put_hex(Sha256& s, const uint8_t* bytes, int n) {
   }
 }
 PSB_HD PSB_NOINL void sha_put_g1_hex(Sha256& s, const G1J& P /*normalised*/) {
-  uint8_t b[48];
+  uint8_t b[kFpBytes];
   g1_serialize_norm(b, P);
-  sha_put_hex(s, b, 48);
+  sha_put_hex(s, b, kFpBytes);
 }
 PSB_HD PSB_NOINL void sha_put_g2_hex(Sha256& s, const G2J& P /*normalised*/) {
-  uint8_t b[96];
+  uint8_t b[2 * kFpBytes];
   g2_serialize_norm(b, P);
-  sha_put_hex(s, b, 96);
+  sha_put_hex(s, b, 2 * kFpBytes);
 }
 // c = Fr::setHashOf(digest_engine.digest(ad)): the 32 raw digest bytes are hashed AGAIN (double hash)
 PSB_HD PSB_NOINL void challenge_finish(uint32_t c[8], Sha256& s, const uint8_t* ad, size_t ad_len) {

@@ -23,6 +23,16 @@ using namespace psb;
 
 namespace {
 
+// sizes of mcl's objects in 64-bit words and of their serialisations in bytes (BLS12-381: 6/18/36/72 words, 48/96
+// bytes; BN254: 4/12/24/48 words, 32/64 bytes)
+constexpr size_t kFpW = PSB_NL / 2;       // Fp
+constexpr size_t kG1W = 3 * kFpW;         // G1 Jacobian
+constexpr size_t kG2W = 6 * kFpW;         // G2 Jacobian
+constexpr size_t kGtW = 12 * kFpW;        // GT
+constexpr size_t kG1Ser = 4 * PSB_NL;     // compressed G1
+constexpr size_t kG2Ser = 8 * PSB_NL;     // compressed G2
+constexpr size_t kCredSer = 2 * kG1Ser;   // sig1 || sig2
+
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
@@ -83,7 +93,7 @@ struct KeyDev {
 // batch).  Cached per key by the points' bytes so that a relying party's steady stream of batches builds them once.
 constexpr int kBatchW = 12;
 struct BatchTbl {
-  std::array<uint64_t, 4 * 18> id{};
+  std::array<uint64_t, 4 * kG1W> id{};
   int nbases = 0;
   std::vector<int> ordinals;
   std::vector<G1A*> tbl;   // per device
@@ -219,7 +229,11 @@ int psb_last_phase_ms(int dev_index, float* ms) {
 }
 
 int psb_init(int curve, const int* devices, int ndev) {
-  if (curve != PSB_CURVE_BLS12_381) return fail(PSB_ERR_UNSUPPORTED, "only BLS12-381 (curve 5) is built");
+#if PSB_IS_BN
+  if (curve != PSB_MCL_CURVE) return fail(PSB_ERR_UNSUPPORTED, "this library (libpsb_bn254.so) is built for BN254 (curve 0); BLS12-381 is libpsb.so");
+#else
+  if (curve != PSB_MCL_CURVE) return fail(PSB_ERR_UNSUPPORTED, "this library (libpsb.so) is built for BLS12-381 (curve 5); BN254 is libpsb_bn254.so");
+#endif
   if (g_init) psb_shutdown();
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
@@ -279,8 +293,8 @@ psb_key* psb_key_create(const uint64_t* g, const uint64_t* gg, const uint64_t* X
   int w = window_bits == 0 ? 16 : window_bits;
   if (w < 4 || w > 20) { fail(PSB_ERR_ARG, "window_bits must be 4..20"); return nullptr; }
   // fixed bases must be finite points: their window tables hold affine entries (z == 0 <=> infinity)
-  bool inf = is_zero_words(g + 12, 6) || is_zero_words(gg + 24, 12) || is_zero_words(XX + 24, 12);
-  for (size_t i = 0; i < n; i++) inf = inf || is_zero_words(Y + 18 * i + 12, 6) || is_zero_words(YY + 36 * i + 24, 12);
+  bool inf = is_zero_words(g + 2 * kFpW, kFpW) || is_zero_words(gg + 4 * kFpW, 2 * kFpW) || is_zero_words(XX + 4 * kFpW, 2 * kFpW);
+  for (size_t i = 0; i < n; i++) inf = inf || is_zero_words(Y + kG1W * i + 2 * kFpW, kFpW) || is_zero_words(YY + kG2W * i + 4 * kFpW, 2 * kFpW);
   if (inf) { fail(PSB_ERR_ARG, "key component is the point at infinity"); return nullptr; }
   psb_key* key = new psb_key();
   key->n = n; key->w = w; key->hasX = X_secret != nullptr;
@@ -356,8 +370,8 @@ int psb_verify(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* sig
     if ((rc = ensure(dv->in[4], L + 16))) return rc;
     if ((rc = ensure(dv->ws, psb_verify_ws_bytes(key, L)))) return rc;
     if (gt && (rc = ensure(dv->in[5], L * sizeof(Fp12)))) return rc;
-    CK(cudaMemcpyAsync(dv->in[0].p, sig1 + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(dv->in[1].p, sig2 + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dv->in[0].p, sig1 + b * kG1W, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dv->in[1].p, sig2 + b * kG1W, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
     const uint8_t* d_blob = nullptr; const uint64_t* d_off = nullptr; const Fr* d_m = nullptr;
     if (attr_blob) {
       const uint64_t o0 = attr_off[b * n], o1 = attr_off[e * n];
@@ -376,7 +390,7 @@ int psb_verify(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* sig
                        (uint8_t*)dv->in[4].p, gt ? (Fp12*)dv->in[5].p : nullptr, dv->ws.p, st);
     if (rc) return rc;
     CK(cudaMemcpyAsync(verdict + b, dv->in[4].p, L, cudaMemcpyDeviceToHost, st));
-    if (gt) CK(cudaMemcpyAsync(gt + b * 72, dv->in[5].p, L * sizeof(Fp12), cudaMemcpyDeviceToHost, st));
+    if (gt) CK(cudaMemcpyAsync(gt + b * kGtW, dv->in[5].p, L * sizeof(Fp12), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return PSB_OK;
   });
@@ -384,7 +398,7 @@ int psb_verify(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* sig
 
 static int deserialize_impl(bool g2, size_t N, const uint8_t* ser, size_t stride, uint64_t* out, uint8_t* ok) {
   if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
-  const size_t esz = g2 ? 96 : 48, words = g2 ? 36 : 18;
+  const size_t esz = g2 ? kG2Ser : kG1Ser, words = g2 ? kG2W : kG1W;
   if (!ser || !out || !ok || stride < esz) return fail(PSB_ERR_ARG, "bad argument");
   return shard(N, [&](int di, size_t b, size_t e) -> int {
     Dev* dv = g_devs[di];
@@ -423,7 +437,7 @@ int psb_verify_ser(psb_key* key, size_t N, const uint8_t* cred, size_t stride, s
                    const uint8_t* attr_blob, const uint64_t* attr_off, uint8_t* verdict, uint8_t* decoded) {
   if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
   if (!key || !cred || !verdict || (key->n && (!attr_blob || !attr_off))) return fail(PSB_ERR_ARG, "null argument");
-  if (off1 + 48 > stride || off2 + 48 > stride) return fail(PSB_ERR_ARG, "offsets exceed the stride");
+  if (off1 + kG1Ser > stride || off2 + kG1Ser > stride) return fail(PSB_ERR_ARG, "offsets exceed the stride");
   const size_t n = key->n;
   return shard(N, [&](int di, size_t b, size_t e) -> int {
     Dev* dv = g_devs[di];
@@ -472,14 +486,14 @@ int psb_pairing(size_t N, const uint64_t* P, const uint64_t* Q, uint64_t* out) {
     if ((rc = ensure(dv->in[1], L * sizeof(G2J)))) return rc;
     if ((rc = ensure(dv->in[5], L * sizeof(Fp12)))) return rc;
     if ((rc = ensure(dv->ws, L * sizeof(Fp12)))) return rc;
-    CK(cudaMemcpyAsync(dv->in[0].p, P + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(dv->in[1].p, Q + b * 36, L * sizeof(G2J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dv->in[0].p, P + b * kG1W, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dv->in[1].p, Q + b * kG2W, L * sizeof(G2J), cudaMemcpyHostToDevice, st));
     k_pairing_miller<<<nblocks(L), kBlock, 0, st>>>(L, (const G1J*)dv->in[0].p, (const G2J*)dv->in[1].p, (Fp12*)dv->ws.p);
     LAUNCHED();
     k_final_exp<<<nblocks(L), kBlock, 0, st>>>(L, (const Fp12*)dv->ws.p, (Fp12*)dv->in[5].p);
     LAUNCHED();
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(out + b * 72, dv->in[5].p, L * sizeof(Fp12), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out + b * kGtW, dv->in[5].p, L * sizeof(Fp12), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return PSB_OK;
   });
@@ -556,17 +570,17 @@ int psb_randomize(size_t N, const uint64_t* sig1, const uint64_t* sig2, const ui
     for (int i = 0; i < 2; i++) if ((rc = ensure(dv->in[i], L * sizeof(G1J)))) return rc;
     if ((rc = ensure(dv->in[2], L * sizeof(Fr)))) return rc;
     for (int i = 3; i < 5; i++) if ((rc = ensure(dv->in[i], L * sizeof(G1J)))) return rc;
-    if (ser && (rc = ensure(dv->in[5], L * 96))) return rc;
-    CK(cudaMemcpyAsync(dv->in[0].p, sig1 + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(dv->in[1].p, sig2 + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    if (ser && (rc = ensure(dv->in[5], L * kCredSer))) return rc;
+    CK(cudaMemcpyAsync(dv->in[0].p, sig1 + b * kG1W, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dv->in[1].p, sig2 + b * kG1W, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(dv->in[2].p, t + b * 4, L * sizeof(Fr), cudaMemcpyHostToDevice, st));
     k_randomize<<<nblocks(L), kBlock, 0, st>>>(L, (const G1J*)dv->in[0].p, (const G1J*)dv->in[1].p, (const Fr*)dv->in[2].p,
                                                (G1J*)dv->in[3].p, (G1J*)dv->in[4].p, ser ? (uint8_t*)dv->in[5].p : nullptr);
     LAUNCHED();
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(out1 + b * 18, dv->in[3].p, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(out2 + b * 18, dv->in[4].p, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
-    if (ser) CK(cudaMemcpyAsync(ser + b * 96, dv->in[5].p, L * 96, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out1 + b * kG1W, dv->in[3].p, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out2 + b * kG1W, dv->in[4].p, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+    if (ser) CK(cudaMemcpyAsync(ser + b * kCredSer, dv->in[5].p, L * kCredSer, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return PSB_OK;
   });
@@ -587,12 +601,12 @@ int psb_g1_mul(size_t N, const uint64_t* P, int p_stride, const uint64_t* k, uin
     if ((rc = ensure(dv->in[0], np * sizeof(G1J)))) return rc;
     if ((rc = ensure(dv->in[2], L * sizeof(Fr)))) return rc;
     if ((rc = ensure(dv->in[3], L * sizeof(G1J)))) return rc;
-    CK(cudaMemcpyAsync(dv->in[0].p, P + (p_stride ? b * 18 : 0), np * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dv->in[0].p, P + (p_stride ? b * kG1W : 0), np * sizeof(G1J), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(dv->in[2].p, k + b * 4, L * sizeof(Fr), cudaMemcpyHostToDevice, st));
     k_g1_mul<<<nblocks(L), kBlock, 0, st>>>(L, (const G1J*)dv->in[0].p, p_stride, (const Fr*)dv->in[2].p, (G1J*)dv->in[3].p);
     LAUNCHED();
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(out + b * 18, dv->in[3].p, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out + b * kG1W, dv->in[3].p, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return PSB_OK;
   });
@@ -634,10 +648,10 @@ static int ensure_verifier_tables(psb_key* key) {
 }
 // per-batch G1 bases [H(service), g, y, h] (nb = 1 without id retrieval) -> cached window tables
 static int get_batch_tables(psb_key* key, const uint64_t* const pts[4], int nb, std::shared_ptr<BatchTbl>& out) {
-  std::array<uint64_t, 4 * 18> id{};
+  std::array<uint64_t, 4 * kG1W> id{};
   for (int i = 0; i < nb; i++) {
-    if (is_zero_words(pts[i] + 12, 6)) return fail(PSB_ERR_ARG, "service/authority point is the point at infinity");
-    memcpy(&id[18 * i], pts[i], 18 * sizeof(uint64_t));
+    if (is_zero_words(pts[i] + 2 * kFpW, kFpW)) return fail(PSB_ERR_ARG, "service/authority point is the point at infinity");
+    memcpy(&id[kG1W * i], pts[i], kG1W * sizeof(uint64_t));
   }
   std::lock_guard<std::mutex> lk(key->mu);
   for (auto& b : key->batch) if (b->nbases == nb && b->id == id) { out = b; return PSB_OK; }
@@ -690,10 +704,10 @@ int psb_provide_id(psb_key* key, size_t N, const uint64_t* A, const uint64_t* c,
       dA = ar.take<G1J>(L); dc = ar.take<Fr>(L); drs = ar.take<Fr>(L * per + 1); du = ar.take<Fr>(L);
       dblob = ar.take<uint8_t>((size_t)(o1 - o0) + 16); doff = ar.take<uint64_t>(L * n + 1);
       dad = ar.take<uint8_t>((size_t)(a1 - a0) + 16); dadoff = ar.take<uint64_t>(L + 1);
-      dver = ar.take<uint8_t>(L); dS1 = ar.take<G1J>(L); dS2 = ar.take<G1J>(L); dser = ar.take<uint8_t>(L * 96);
+      dver = ar.take<uint8_t>(L); dS1 = ar.take<G1J>(L); dS2 = ar.take<G1J>(L); dser = ar.take<uint8_t>(L * kCredSer);
       if (pass == 0) { int r = ensure(dv->arena, ar.used); if (r) return r; ar.base = (char*)dv->arena.p; }
     }
-    CK(cudaMemcpyAsync(dA, A + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dA, A + b * kG1W, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(dc, c + b * 4, L * sizeof(Fr), cudaMemcpyHostToDevice, st));
     if (per) CK(cudaMemcpyAsync(drs, rs + b * per * 4, L * per * sizeof(Fr), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(du, u + b * 4, L * sizeof(Fr), cudaMemcpyHostToDevice, st));
@@ -707,9 +721,9 @@ int psb_provide_id(psb_key* key, size_t N, const uint64_t* A, const uint64_t* c,
     LAUNCHED();
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(verdict + b, dver, L, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(sig1 + b * 18, dS1, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(sig2 + b * 18, dS2, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
-    if (ser) CK(cudaMemcpyAsync(ser + b * 96, dser, L * 96, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(sig1 + b * kG1W, dS1, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(sig2 + b * kG1W, dS2, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+    if (ser) CK(cudaMemcpyAsync(ser + b * kCredSer, dser, L * kCredSer, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return PSB_OK;
   });
@@ -754,13 +768,13 @@ int psb_verify_id(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* 
       dok = ar.take<uint8_t>(L); dver = ar.take<uint8_t>(L);
       if (pass == 0) { int r = ensure(dv->arena, ar.used); if (r) return r; ar.base = (char*)dv->arena.p; }
     }
-    CK(cudaMemcpyAsync(dS1, sig1 + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(dS2, sig2 + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(dk, k + b * 36, L * sizeof(G2J), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(dphi, phi + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dS1, sig1 + b * kG1W, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dS2, sig2 + b * kG1W, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dk, k + b * kG2W, L * sizeof(G2J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dphi, phi + b * kG1W, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
     if (with_id) {
-      CK(cudaMemcpyAsync(dE1, E1 + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
-      CK(cudaMemcpyAsync(dE2, E2 + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(dE1, E1 + b * kG1W, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(dE2, E2 + b * kG1W, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
     }
     CK(cudaMemcpyAsync(dc, c + b * 4, L * sizeof(Fr), cudaMemcpyHostToDevice, st));
     if (per) CK(cudaMemcpyAsync(drs, rs + b * per * 4, L * per * sizeof(Fr), cudaMemcpyHostToDevice, st));
@@ -832,7 +846,7 @@ int psb_request_id(psb_key* key, size_t N, const uint8_t* attr_blob, const uint6
                                                 drnd, dA, dc, drs);
     LAUNCHED();
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(A + b * 18, dA, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(A + b * kG1W, dA, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(c + b * 4, dc, L * sizeof(Fr), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(rs + b * (h + 1) * 4, drs, L * (h + 1) * sizeof(Fr), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -854,14 +868,14 @@ int psb_unblind(size_t N, const uint64_t* sig1, const uint64_t* sig2, const uint
     for (int i = 0; i < 2; i++) if ((rc = ensure(dv->in[i], L * sizeof(G1J)))) return rc;
     if ((rc = ensure(dv->in[2], L * sizeof(Fr)))) return rc;
     if ((rc = ensure(dv->in[3], L * sizeof(G1J)))) return rc;
-    CK(cudaMemcpyAsync(dv->in[0].p, sig1 + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(dv->in[1].p, sig2 + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dv->in[0].p, sig1 + b * kG1W, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dv->in[1].p, sig2 + b * kG1W, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(dv->in[2].p, t1 + b * 4, L * sizeof(Fr), cudaMemcpyHostToDevice, st));
     k_unblind<<<nblocks(L), kBlock, 0, st>>>(L, (const G1J*)dv->in[0].p, (const G1J*)dv->in[1].p, (const Fr*)dv->in[2].p,
                                              (G1J*)dv->in[3].p);
     LAUNCHED();
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(out2 + b * 18, dv->in[3].p, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out2 + b * kG1W, dv->in[3].p, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return PSB_OK;
   });
@@ -907,8 +921,8 @@ int psb_prove_id(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* s
       dad = ar.take<uint8_t>((size_t)(a1 - a0) + 16); dadoff = ar.take<uint64_t>(L + 1); dhide = ar.take<uint8_t>(n + 16);
       if (pass == 0) { int r = ensure(dv->arena, ar.used); if (r) return r; ar.base = (char*)dv->arena.p; }
     }
-    CK(cudaMemcpyAsync(dS1, sig1 + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(dS2, sig2 + b * 18, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dS1, sig1 + b * kG1W, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dS2, sig2 + b * kG1W, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(drnd, rnd + b * rper * 4, L * rper * sizeof(Fr), cudaMemcpyHostToDevice, st));
     if (o1 > o0) CK(cudaMemcpyAsync(dblob, attr_blob + o0, (size_t)(o1 - o0), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(doff, attr_off + b * n, (L * n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
@@ -926,13 +940,13 @@ int psb_prove_id(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* s
                                               dW, dphi, dE1, dE2, dc, drs);
     LAUNCHED();
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(o_sig1 + b * 18, dO1, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(o_sig2 + b * 18, dO2, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(o_k + b * 36, dk, L * sizeof(G2J), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(o_phi + b * 18, dphi, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(o_sig1 + b * kG1W, dO1, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(o_sig2 + b * kG1W, dO2, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(o_k + b * kG2W, dk, L * sizeof(G2J), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(o_phi + b * kG1W, dphi, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
     if (with_id) {
-      CK(cudaMemcpyAsync(o_E1 + b * 18, dE1, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
-      CK(cudaMemcpyAsync(o_E2 + b * 18, dE2, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(o_E1 + b * kG1W, dE1, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(o_E2 + b * kG1W, dE2, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
     }
     CK(cudaMemcpyAsync(o_c + b * 4, dc, L * sizeof(Fr), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(o_rs + b * per * 4, drs, L * per * sizeof(Fr), cudaMemcpyDeviceToHost, st));
@@ -964,7 +978,7 @@ int psb_hash_to_g1(size_t N, const uint8_t* msg_blob, const uint64_t* msg_off, u
     k_hash_to_g1<<<nblocks(L), kBlock, 0, st>>>(L, dblob - o0, doff, dout, dok);
     LAUNCHED();
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(out + b * 18, dout, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out + b * kG1W, dout, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(ok + b, dok, L, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return PSB_OK;

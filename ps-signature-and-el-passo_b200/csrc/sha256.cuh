@@ -81,19 +81,21 @@ PSB_HD PSB_INL uint32_t bswap32(uint32_t x) {
   return (x >> 24) | ((x >> 8) & 0xff00u) | ((x << 8) & 0xff0000u) | (x << 24);
 }
 
-// SmallMask on the digest: little-endian integer of the 32 digest bytes, & (2^255-1), and
-// & (2^254-1) if still >= r.  Output is the NORMAL form scalar (8 LE limbs).
+// SmallMask on the digest (mcl fp.cpp:612-662): little-endian integer of the 32 digest bytes, masked to bitSize(r)
+// bits (255 for BLS12-381, 254 for BN254) and to one bit less if still >= r.  Output: NORMAL form scalar (8 LE limbs).
+constexpr uint32_t kFrMask1 = (1u << (PSB_FR_BITS - 224)) - 1u;
+constexpr uint32_t kFrMask2 = (1u << (PSB_FR_BITS - 225)) - 1u;
 PSB_HD PSB_INL void digest_to_fr_normal(uint32_t k[8], const uint32_t digest_words[8]) {
   for (int i = 0; i < 8; i++) k[i] = bswap32(digest_words[i]);
-  k[7] &= 0x7fffffffu;
-  if (fr_geq_modulus(k)) k[7] &= 0x3fffffffu;
+  k[7] &= kFrMask1;
+  if (fr_geq_modulus(k)) k[7] &= kFrMask2;
 }
 // 32 raw little-endian bytes (e.g. a CSPRNG draw, mcl Fr::setByCSPRNG fp.hpp:408-414) -> scalar
 PSB_HD PSB_INL void bytes_to_fr_normal(uint32_t k[8], const uint8_t* b) {
   for (int i = 0; i < 8; i++)
     k[i] = (uint32_t)b[4 * i] | ((uint32_t)b[4 * i + 1] << 8) | ((uint32_t)b[4 * i + 2] << 16) | ((uint32_t)b[4 * i + 3] << 24);
-  k[7] &= 0x7fffffffu;
-  if (fr_geq_modulus(k)) k[7] &= 0x3fffffffu;
+  k[7] &= kFrMask1;
+  if (fr_geq_modulus(k)) k[7] &= kFrMask2;
 }
 
 // Fr::setHashOf(msg) -> normal-form scalar

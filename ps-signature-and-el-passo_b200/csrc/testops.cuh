@@ -12,7 +12,7 @@ enum TestOp {
   T_FP2_ADD = 10, T_FP2_SUB, T_FP2_MUL, T_FP2_SQR, T_FP2_NEG, T_FP2_INV,
   T_FP6_MUL = 20, T_FP6_INV,
   T_FP12_MUL = 30, T_FP12_SQR, T_FP12_INV, T_FP12_FROB1, T_FP12_FROB2, T_FP12_FROB3, T_FP12_CYCLO_SQR,
-  T_FP12_MUL_LINE,  // a = Fp12, b = 3 Fp2 (c0, c2, c3)
+  T_FP12_MUL_LINE,  // a = Fp12, b = 3 Fp2: M-type twist c0 + c2 w^2 + c3 w^3, D-type twist c0 + c1 w + c3 w^3
   T_G1_ADD = 40, T_G1_DBL, T_G1_NORM, T_G1_MUL /* b = Fr Montgomery */, T_G1_MADD /* b = normalised G1 */,
   T_G2_ADD = 50, T_G2_DBL, T_G2_NORM, T_G2_MUL, T_G2_MADD,
   T_PAIRING = 60,      // a = G1, b = G2 -> GT = finalExp(millerLoop(a, b))
@@ -23,7 +23,7 @@ enum TestOp {
 
 // sizes in u32 words: {a, b, c, out}; 0 = unused
 PSB_HD inline bool test_op_shape(int op, int s[4]) {
-  const int FP = 12, FP2 = 24, FP6 = 72, FP12 = 144, G1 = 36, G2 = 72, FR = 8;
+  const int FP = PSB_NL, FP2 = 2 * FP, FP6 = 6 * FP, FP12 = 12 * FP, G1 = 3 * FP, G2 = 6 * FP, FR = 8;
   s[0] = s[1] = s[2] = s[3] = 0;
   switch (op) {
     case T_FP_ADD: case T_FP_SUB: case T_FP_MUL: s[0] = s[1] = s[3] = FP; return true;
@@ -103,7 +103,14 @@ PSB_HD inline void test_op_run(int op, const uint32_t* a, const uint32_t* b, con
       else if (op == T_FP12_FROB3) fp12_frobenius(r, x, 3);
       else if (op == T_FP12_CYCLO_SQR) fp12_cyclo_sqr(r, x);
       else if (op == T_MILLER_FE_ONLY) final_exp(r, x);
-      else { Fp2 c0, c2, c3; ld(c0, b); ld(c2, b + 24); ld(c3, b + 48); r = x; fp12_mul_line(r, c0, c2, c3); }
+      else {
+        Fp2 c0, c2, c3; ld(c0, b); ld(c2, b + 2 * PSB_NL); ld(c3, b + 4 * PSB_NL); r = x;
+#if PSB_TWIST_MTYPE
+        fp12_mul_line(r, c0, c2, c3);        // c0 + c2 w^2 + c3 w^3
+#else
+        fp12_mul_line_d(r, c0, c2, c3);      // c0 + c2 w + c3 w^3
+#endif
+      }
       st(out, r); break; }
     case T_G1_ADD: case T_G1_DBL: case T_G1_NORM: case T_G1_MUL: case T_G1_MADD: {
       G1J x, y, r; ld(x, a);
@@ -130,7 +137,7 @@ PSB_HD inline void test_op_run(int op, const uint32_t* a, const uint32_t* b, con
       final_exp(e, f);
       st(out, e); break; }
     case T_PAIRING_RATIO: {
-      G1J P1, P2; G2J Q1, Q2; ld(P1, a); ld(Q1, b); ld(P2, c); ld(Q2, c + 36);
+      G1J P1, P2; G2J Q1, Q2; ld(P1, a); ld(Q1, b); ld(P2, c); ld(Q2, c + 3 * PSB_NL);
       Fp x1, y1, x2, y2;
       g1_affine_for_pairing(x1, y1, P1);
       g1_affine_for_pairing(x2, y2, P2);

@@ -54,7 +54,7 @@ PSB_HD PSB_NOINL void fpn_sub2(Fp* r, const Fp* a, const Fp* b, const Fp* c, int
 #pragma unroll 1
 #endif
   for (int k = 0; k < cnt; k++) {
-    uint32_t x[12], y[12];
+    uint32_t x[PSB_NL], y[PSB_NL];
     fp_ld(x, a[k]); fp_ld(y, b[k]);
     mod_sub<FpT>(x, x, y);
     fp_ld(y, c[k]);
@@ -101,8 +101,8 @@ PSB_HD PSB_INL void fp_2pminus_rr(Fp& r, const Fp& a) {
   fp_pminus_rr(t, a);                 // p - a in (-p, p], two's complement when negative
   Fp pp;
   PSB_UNROLL
-  for (int i = 0; i < 12; i++) pp.v[i] = FpT::p(i);
-  add_n<12>(r.v, t.v, pp.v);          // + p (carry out cancels the wrap)
+  for (int i = 0; i < PSB_NL; i++) pp.v[i] = FpT::p(i);
+  add_n<PSB_NL>(r.v, t.v, pp.v);          // + p (carry out cancels the wrap)
 }
 
 #ifdef __CUDA_ARCH__
@@ -314,8 +314,8 @@ PSB_HD PSB_INL void fp12_conj(Fp12& r, const Fp12& x) { r.a = x.a; fp6_neg(r.b, 
 PSB_HD PSB_INL bool fp12_is_one(const Fp12& x) {
   const uint32_t* p = (const uint32_t*)&x;
   uint32_t o = 0;
-  for (int i = 0; i < 12; i++) o |= p[i] ^ PSB_K(FP_ONE)[i];
-  for (int i = 12; i < 144; i++) o |= p[i];
+  for (int i = 0; i < PSB_NL; i++) o |= p[i] ^ PSB_K(FP_ONE)[i];
+  for (int i = PSB_NL; i < 12 * PSB_NL; i++) o |= p[i];
   return o == 0;
 }
 
@@ -371,6 +371,26 @@ PSB_HD PSB_NOINL void fp12_mul_line(Fp12& f, const Fp2& c0, const Fp2& c2, const
   fp6_add_mulv(f.a, t0, t1);
 }
 
+// x * a0 with a0 in Fp2, 3 Fp2 products
+PSB_HD PSB_NOINL void fp6_mul_fp2(Fp6& z, const Fp6& x, const Fp2& a0) {
+  fp2_mul(z.a, x.a, a0);
+  fp2_mul(z.b, x.b, a0);
+  fp2_mul(z.c, x.c, a0);
+}
+// f *= (c0 + c1 w + c3 w^3): the sparse line of a D-type twist (cf. mcl mul_403, bn.hpp:1335-1419)
+// with A = c0, B = c1 + c3 v:  f.a' = fa A + v fb B,  f.b' = (fa+fb)(A+B) - fa A - fb B.   13 Fp2 products.
+PSB_HD PSB_NOINL void fp12_mul_line_d(Fp12& f, const Fp2& c0, const Fp2& c1, const Fp2& c3) {
+  Fp6 t0, t1, s;
+  Fp2 c01;
+  fp6_mul_fp2(t0, f.a, c0);
+  fp6_mul_01(t1, f.b, c1, c3);
+  fp6_add(s, f.a, f.b);
+  fp2_add(c01, c0, c1);
+  fp6_mul_01(s, s, c01, c3);
+  fp6_sub2(f.b, s, t0, t1);
+  fp6_add_mulv(f.a, t0, t1);
+}
+
 // x^-1 = (a - b w)/(a^2 - v b^2)   (fp_tower.hpp:1183-1198)
 PSB_HD PSB_NOINL void fp12_inv(Fp12& r, const Fp12& x) {
   Fp6 t0, t1;
@@ -398,7 +418,7 @@ PSB_HD PSB_NOINL void fp12_frobenius(Fp12& r, const Fp12& x, int j) {
     if (j & 1) fp_neg(c.b, c.b);
     if (k > 0) {
       Fp2 g;
-      for (int i = 0; i < 12; i++) { g.a.v[i] = tbl[(k - 1) * 24 + i]; g.b.v[i] = tbl[(k - 1) * 24 + 12 + i]; }
+      for (int i = 0; i < PSB_NL; i++) { g.a.v[i] = tbl[(k - 1) * 2 * PSB_NL + i]; g.b.v[i] = tbl[(k - 1) * 2 * PSB_NL + PSB_NL + i]; }
       fp2_mul(c, c, g);
     }
     *fp12_coeff(r, k) = c;

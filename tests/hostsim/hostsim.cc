@@ -24,6 +24,7 @@ void hostsim_set_hash_of(const uint8_t* msg, size_t len, uint32_t* k) { psb::fr_
 #include "../../ps-signature-and-el-passo_b200/csrc/hash_to_curve.cuh"
 namespace {
 using namespace psb;
+constexpr int kG1U = 3 * PSB_NL, kG2U = 6 * PSB_NL;   // u32 words of a Jacobian G1 / G2 point
 // same table geometry as k_window_bases / k_build_table: entry (win, d) = d * 2^(w win) * B, affine
 template <class F>
 void host_table(std::vector<Aff<F>>& out, const Jac<F>& base, int w) {
@@ -61,15 +62,15 @@ void hostsim_provide_id(int n, int w, const uint32_t* g, const uint32_t* X, cons
                         uint8_t* verdict, uint32_t* sig1, uint32_t* sig2) {
   std::vector<G1A> tbl;
   G1J b; ld(b, g); host_table(tbl, b, w);
-  for (int i = 0; i < n; i++) { ld(b, Y + 36 * i); host_table(tbl, b, w); }
+  for (int i = 0; i < n; i++) { ld(b, Y + kG1U * i); host_table(tbl, b, w); }
   G1J Xs; ld(Xs, X);
   for (size_t j = 0; j < N; j++) {
-    G1J a, s1, s2; ld(a, A + 36 * j);
+    G1J a, s1, s2; ld(a, A + kG1U * j);
     bool ok = provide_id_lane(n, TblGeom{w}, tbl.data(), Xs, a, (const Fr*)(c + 8 * j), (const Fr*)(rs + 8 * per * j), per,
                               blob, off + j * n, ad_blob + ad_off[j], (size_t)(ad_off[j + 1] - ad_off[j]),
                               (const Fr*)(u + 8 * j), s1, s2);
     verdict[j] = ok;
-    st(sig1 + 36 * j, s1); st(sig2 + 36 * j, s2);
+    st(sig1 + kG1U * j, s1); st(sig2 + kG1U * j, s2);
   }
 }
 
@@ -82,7 +83,7 @@ void hostsim_verify_id(int n, int w, const uint32_t* gg, const uint32_t* XX, con
   std::vector<G2A> tYY, tAux;
   std::vector<G1A> tB;
   G2J b2; G1J b1;
-  for (int i = 0; i < n; i++) { ld(b2, YY + 72 * i); host_table(tYY, b2, w); }
+  for (int i = 0; i < n; i++) { ld(b2, YY + kG2U * i); host_table(tYY, b2, w); }
   G2J ggj; ld(ggj, gg); host_table(tAux, ggj, w);
   ld(b2, XX); host_table(tAux, b2, w);
   ld(b1, service_pt); host_table(tB, b1, w);
@@ -91,10 +92,10 @@ void hostsim_verify_id(int n, int w, const uint32_t* gg, const uint32_t* XX, con
   G2A q; q.x = ggj.x; q.y = ggj.y;
   precompute_fixed_lines(lines.data(), q);
   for (size_t j = 0; j < N; j++) {
-    G2J kj, Vk, K; ld(kj, k + 72 * j);
+    G2J kj, Vk, K; ld(kj, k + kG2U * j);
     G1J ph, e1, e2, Vphi, VE1, VE2, s1, s2;
-    ld(ph, phi + 36 * j);
-    if (with_id) { ld(e1, E1 + 36 * j); ld(e2, E2 + 36 * j); }
+    ld(ph, phi + kG1U * j);
+    if (with_id) { ld(e1, E1 + kG1U * j); ld(e2, E2 + kG1U * j); }
     const Fr* cj = (const Fr*)(c + 8 * j);
     const Fr* rj = (const Fr*)(rs + 8 * per * j);
     bool ok = verify_id_g2_lane(n, TblGeom{w}, tYY.data(), tAux.data(), kj, cj, rj, per, with_id, blob, off + j * n, Vk, K);
@@ -102,7 +103,7 @@ void hostsim_verify_id(int n, int w, const uint32_t* gg, const uint32_t* XX, con
     ok = ok && verify_id_hash_lane(kj, ph, &e1, &e2, Vk, Vphi, VE1, VE2, with_id, cj, ad_blob + ad_off[j],
                                    (size_t)(ad_off[j + 1] - ad_off[j]));
     nizk[j] = ok;
-    ld(s1, sig1 + 36 * j); ld(s2, sig2 + 36 * j);
+    ld(s1, sig1 + kG1U * j); ld(s2, sig2 + kG1U * j);
     Fp x1, y1, x2, y2;
     g1_affine_for_pairing(x1, y1, s1);
     g1_affine_for_pairing(x2, y2, s2);
@@ -123,20 +124,20 @@ void hostsim_request_id(int n, int w, const uint32_t* g, const uint32_t* Y, size
                         uint32_t* c, uint32_t* rs) {
   std::vector<G1A> tbl;
   G1J b; ld(b, g); host_table(tbl, b, w);
-  for (int i = 0; i < n; i++) { ld(b, Y + 36 * i); host_table(tbl, b, w); }
+  for (int i = 0; i < n; i++) { ld(b, Y + kG1U * i); host_table(tbl, b, w); }
   int h = 0; for (int i = 0; i < n; i++) h += hide[i] ? 1 : 0;
   for (size_t j = 0; j < N; j++) {
     G1J a; Fr cc;
     request_id_lane(n, TblGeom{w}, tbl.data(), hide, blob, off + j * n, ad_blob + ad_off[j], (size_t)(ad_off[j + 1] - ad_off[j]),
                     (const Fr*)(rnd + 8 * (h + 2) * j), a, cc, (Fr*)(rs + 8 * (h + 1) * j));
-    st(A + 36 * j, a); st(c + 8 * j, cc);
+    st(A + kG1U * j, a); st(c + 8 * j, cc);
   }
 }
 void hostsim_unblind(size_t N, const uint32_t* sig1, const uint32_t* sig2, const uint32_t* t1, uint32_t* out2) {
   for (size_t j = 0; j < N; j++) {
-    G1J a, b, r; ld(a, sig1 + 36 * j); ld(b, sig2 + 36 * j);
+    G1J a, b, r; ld(a, sig1 + kG1U * j); ld(b, sig2 + kG1U * j);
     unblind_lane(r, a, b, (const Fr*)(t1 + 8 * j));
-    st(out2 + 36 * j, r);
+    st(out2 + kG1U * j, r);
   }
 }
 void hostsim_prove_id(int n, int w, const uint32_t* gg, const uint32_t* XX, const uint32_t* YY, size_t N, const uint32_t* sig1,
@@ -147,7 +148,7 @@ void hostsim_prove_id(int n, int w, const uint32_t* gg, const uint32_t* XX, cons
   std::vector<G2A> tYY, tAux;
   std::vector<G1A> tB;
   G2J b2, XXj; G1J b1;
-  for (int i = 0; i < n; i++) { ld(b2, YY + 72 * i); host_table(tYY, b2, w); }
+  for (int i = 0; i < n; i++) { ld(b2, YY + kG2U * i); host_table(tYY, b2, w); }
   ld(b2, gg); host_table(tAux, b2, w);
   ld(XXj, XX); host_table(tAux, XXj, w);
   ld(b1, service_pt); host_table(tB, b1, w);
@@ -157,13 +158,13 @@ void hostsim_prove_id(int n, int w, const uint32_t* gg, const uint32_t* XX, cons
   for (size_t j = 0; j < N; j++) {
     const Fr* rj = (const Fr*)(rnd + 8 * rper * j);
     G2J k, Vk; G1J s1, s2, o1, o2, W[6]; Fr cc;
-    ld(s1, sig1 + 36 * j); ld(s2, sig2 + 36 * j);
+    ld(s1, sig1 + kG1U * j); ld(s2, sig2 + kG1U * j);
     prove_id_g2_lane(n, TblGeom{w}, tYY.data(), tAux.data(), XXj, hide, blob, off + j * n, rj, h, with_id, k, Vk);
     prove_id_g1_lane(TblGeom{w}, tB.data(), s1, s2, blob, off + j * n, rj, h, with_id, o1, o2, W);
     prove_id_hash_lane(n, hide, blob, off + j * n, ad_blob + ad_off[j], (size_t)(ad_off[j + 1] - ad_off[j]), rj, h, with_id, k, Vk,
                        W, cc, (Fr*)(o_rs + 8 * per * j));
-    st(o_sig1 + 36 * j, o1); st(o_sig2 + 36 * j, o2); st(o_k + 72 * j, k); st(o_phi + 36 * j, W[0]); st(o_c + 8 * j, cc);
-    if (with_id) { st(o_E1 + 36 * j, W[2]); st(o_E2 + 36 * j, W[3]); }
+    st(o_sig1 + kG1U * j, o1); st(o_sig2 + kG1U * j, o2); st(o_k + kG2U * j, k); st(o_phi + kG1U * j, W[0]); st(o_c + 8 * j, cc);
+    if (with_id) { st(o_E1 + kG1U * j, W[2]); st(o_E2 + kG1U * j, W[3]); }
   }
 }
 // hashAndMapToG1 probes (csrc/hash_to_curve.cuh)
