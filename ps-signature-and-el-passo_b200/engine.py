@@ -19,10 +19,20 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("PSB_LIB", os.path.join(_HERE, "libpsb.so"))
+# One curve per library / per process, like mcl's own bn256 / bn384 builds: PSB_CURVE=bn254 selects
+# libpsb_bn254.so (what the reference's shipped tests get from initPairing()), anything else
+# libpsb.so (BLS12-381, the north star's curve).
+CURVE = os.environ.get("PSB_CURVE", "bls12_381").lower()
+assert CURVE in ("bls12_381", "bn254"), CURVE
+BN254 = CURVE == "bn254"
+LIB_PATH = os.environ.get("PSB_LIB", os.path.join(_HERE, "libpsb_bn254.so" if BN254 else "libpsb.so"))
 
-FP, FR, G1, G2, GT = 6, 4, 18, 36, 72  # u64 words
-CURVE_BLS12_381 = 5
+FP = 4 if BN254 else 6                              # u64 words of an Fp
+FR, G1, G2, GT = 4, 3 * FP, 6 * FP, 12 * FP         # u64 words
+G1_SER, G2_SER = 8 * FP, 16 * FP                    # compressed point bytes (mcl serialize)
+CRED_SER = 2 * G1_SER                               # bare serialized credential (sigma1 || sigma2)
+CURVE_BLS12_381, CURVE_BN254 = 5, 0                 # mcl/include/mcl/curve_type.h
+MCL_CURVE = CURVE_BN254 if BN254 else CURVE_BLS12_381
 
 _lib = None
 _inited = False
@@ -70,10 +80,10 @@ def init(devices: Optional[Sequence[int]] = None) -> None:
     global _inited
     L = lib()
     if devices is None:
-        rc = L.psb_init(CURVE_BLS12_381, None, 0)
+        rc = L.psb_init(MCL_CURVE, None, 0)
     else:
         arr = (C.c_int * len(devices))(*devices)
-        rc = L.psb_init(CURVE_BLS12_381, arr, len(devices))
+        rc = L.psb_init(MCL_CURVE, arr, len(devices))
     _check(rc, "psb_init")
     _inited = True
 
@@ -205,7 +215,7 @@ class PSVerifier:
                                 _p(verdict), _p(gt)), "psb_verify")
         return (verdict, gt) if want_gt else verdict
 
-    def verify_serialized(self, cred, all_attributes, stride: int = 100, off1: int = 2, off2: int = 52):
+    def verify_serialized(self, cred, all_attributes, stride: int = 2 * (2 + G1_SER), off1: int = 2, off2: int = 4 + G1_SER):
         """batched verify of SERIALIZED credentials (psb_verify_ser): cred = uint8 (N, stride); defaults are the
         layout of PSCredential::toBufferString (src/ps-encoding.cc:384-391).  Returns (verdict, decoded)."""
         cred = np.ascontiguousarray(cred, dtype=np.uint8).reshape(-1, stride)
@@ -263,7 +273,7 @@ class PSRequester:
         N = s1.shape[0]
         o1 = np.zeros((N, G1), dtype=np.uint64)
         o2 = np.zeros((N, G1), dtype=np.uint64)
-        ser = np.zeros((N, 96), dtype=np.uint8) if want_serialized else None
+        ser = np.zeros((N, CRED_SER), dtype=np.uint8) if want_serialized else None
         _check(lib().psb_randomize(C.c_size_t(N), _p(s1), _p(s2), _p(tt), _p(o1), _p(o2), _p(ser)),
                "psb_randomize")
         return (o1, o2, ser) if want_serialized else (o1, o2)
@@ -348,7 +358,7 @@ class PSSigner:
         verdict = np.zeros(N, dtype=np.uint8)
         s1 = np.zeros((N, G1), dtype=np.uint64)
         s2 = np.zeros((N, G1), dtype=np.uint64)
-        ser = np.zeros((N, 96), dtype=np.uint8)
+        ser = np.zeros((N, CRED_SER), dtype=np.uint8)
         _check(lib().psb_provide_id(self.m_pk.handle, C.c_size_t(N), _p(A), _p(_u64(c, FR)), _p(rs),
                                     C.c_size_t(rs.shape[1]), _p(blob), _p(off), _p(ad_blob), _p(ad_off),
                                     _p(_u64(u, FR)), _p(verdict), _p(s1), _p(s2), _p(ser)), "psb_provide_id")
@@ -376,7 +386,7 @@ def hash_and_map_to_g1(msgs):
     return out, ok
 
 
-def g1_deserialize(ser, stride: int = 48):
+def g1_deserialize(ser, stride: int = G1_SER):
     """batched G1::deserialize (point decompression): ser uint8 (N, stride) -> (points (N,18), ok uint8[N])."""
     ensure_init()
     ser = np.ascontiguousarray(ser, dtype=np.uint8).reshape(-1, stride)
@@ -387,7 +397,7 @@ def g1_deserialize(ser, stride: int = 48):
     return out, ok
 
 
-def g2_deserialize(ser, stride: int = 96):
+def g2_deserialize(ser, stride: int = G2_SER):
     ensure_init()
     ser = np.ascontiguousarray(ser, dtype=np.uint8).reshape(-1, stride)
     N = ser.shape[0]

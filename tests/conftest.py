@@ -28,6 +28,13 @@ else:
     FIELD_P = (_z - 1) ** 2 * GROUP_R // 3 + _z
 
 
+CURVE_Z = abs(_z)                                    # |z| of the curve family parameter
+FPW = 4 if BN254 else 6                              # u64 words: Fp, then G1 / G2 / GT Jacobian / tower objects
+G1W, G2W, GTW = 3 * FPW, 6 * FPW, 12 * FPW
+FP_BYTES = 8 * FPW                                   # serialized Fp = compressed G1
+G1_SER, G2_SER = FP_BYTES, 2 * FP_BYTES
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
@@ -64,5 +71,5 @@ def hostsim():
 
 def rand_fp_raw(ref, rng, n, k=1):
     """n x k random canonical Fp values as raw Montgomery limbs (n, FP * k) u64."""
-    vals = [int.from_bytes(rng.bytes(48), "little") % FIELD_P for _ in range(n * k)]
+    vals = [int.from_bytes(rng.bytes(FP_BYTES), "little") % FIELD_P for _ in range(n * k)]
     return ref.fp_from_ints(vals).reshape(n, k * ref.FP)

@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 
 from tests import workload
+from tests.conftest import bls_only
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -79,6 +80,7 @@ def test_verify_id_unnormalized_inputs(gpu_pkg, ref):
     pk.close()
 
 
+@bls_only
 def test_elpasso_golden_fixtures_on_gpu(gpu_pkg):
     """committed reference outputs (tests/golden/elpasso.json): issuance bytes + sign-on verdicts."""
     keys = json.load(open(os.path.join(G, "keys.json")))["keys"]["5"]

@@ -32,7 +32,7 @@ def test_verify_sharded_over_all_devices(tmp_path):
         v, gt = pkg.PSVerifier(pk).verify(wl.sig1, wl.sig2, wl.attrs, want_gt=True)
         ev, egt = workload.expected_verify(wl, want_gt=True)
         assert np.array_equal(v, ev)
-        live = wl.sig1[:, 12:].any(axis=1)
+        live = wl.sig1[:, 2 * pkg.FP:].any(axis=1)
         assert np.array_equal(gt[live], egt[live])
         sw = workload.make_signon_workload(5, 41, 2, seed=3, with_id=True, tamper_every=4)
         got = pkg.PSVerifier(pk).el_passo_verify_id(sw.proof, sw.proof_attrs, sw.ads, sw.service_pt, sw.y, sw.g, sw.h)

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from tests import workload
+from tests.conftest import G1_SER, bls_only
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -32,8 +33,8 @@ def test_randomize_seeded_reference_method(gpu_pkg, ref):
     wl = workload.make_verify_workload(n_attrs=1, lanes=2, seed=9)
     r1, r2, t = ref.randomize_seeded(wl.key, 4242, wl.sig1[0], wl.sig2[0])
     o1, o2, ser = gpu_pkg.PSRequester.randomize_credential(wl.sig1[:1], wl.sig2[:1], t.reshape(1, 4), want_serialized=True)
-    assert ser[0, :48].tobytes() == ref.g1_serialize(r1)[0].tobytes()
-    assert ser[0, 48:].tobytes() == ref.g1_serialize(r2)[0].tobytes()
+    assert ser[0, :G1_SER].tobytes() == ref.g1_serialize(r1)[0].tobytes()
+    assert ser[0, G1_SER:].tobytes() == ref.g1_serialize(r2)[0].tobytes()
 
 
 def test_g1_mul_batch(gpu_pkg, ref):
@@ -45,6 +46,7 @@ def test_g1_mul_batch(gpu_pkg, ref):
     assert np.array_equal(gpu_pkg.g1_mul(P, k), ref.g1_op(ref.G_NORM, ref.g1_mul(P, k)))
 
 
+@bls_only
 def test_golden_fixtures_on_gpu(gpu_pkg):
     """committed reference outputs (tests/golden/protocol.json): verify verdict + GT, randomize bytes."""
     keys = json.load(open(os.path.join(G, "keys.json")))["keys"]["5"]

@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from tests import workload
+from tests.conftest import bls_only
 
 pytestmark = pytest.mark.gpu
 
@@ -66,6 +67,7 @@ def test_prove_id_argument_checks(gpu_pkg, ref):
     pk.close()
 
 
+@bls_only
 def test_prover_golden_fixtures_on_gpu(gpu_pkg):
     """committed reference outputs (tests/golden/prover.json): requests, unblinded credentials, proofs."""
     import json

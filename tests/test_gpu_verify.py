@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 from tests import workload
+from tests.conftest import FPW
 
 pytestmark = pytest.mark.gpu
 
@@ -17,7 +18,7 @@ def test_verify_matches_reference(gpu_pkg, ref, n_attrs, lanes, w):
     got_v, got_gt = gpu_pkg.PSVerifier(pk).verify(wl.sig1, wl.sig2, wl.attrs, want_gt=True)
     assert np.array_equal(got_v, exp_v)
     assert exp_v.sum() == lanes - len(wl.tampered)  # honest lanes accept, tampered lanes reject
-    live = wl.sig1[:, 12:].any(axis=1)  # reference returns before pairing when sig1 == 0
+    live = wl.sig1[:, 2 * FPW:].any(axis=1)  # reference returns before pairing when sig1 == 0
     assert np.array_equal(got_gt[live], exp_gt[live])
     # same lanes, scalars supplied by the host instead of attribute strings
     if n_attrs:
@@ -32,7 +33,7 @@ def test_verify_unnormalized_inputs(gpu_pkg, ref):
     ref.seed(77)
     t = ref.fr_rand(16)
     s1, s2, _ = ref.randomize(wl.sig1, wl.sig2, t)  # raw Jacobian outputs of mcl, z != 1
-    assert (s1[:, 12:] != wl.sig1[:, 12:]).any()
+    assert (s1[:, 2 * FPW:] != wl.sig1[:, 2 * FPW:]).any()
     pk = gpu_pkg.PSPubKey(wl.key.g, wl.key.gg, wl.key.XX, wl.key.Y, wl.key.YY, window_bits=8)
     exp = ref.ps_verify(wl.key, s1, s2, wl.attrs)
     assert exp.all()

@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 from tests import workload
+from tests.conftest import G1_SER
 
 pytestmark = pytest.mark.gpu
 
@@ -37,7 +38,8 @@ def test_verify_serialized_credentials(gpu_pkg, ref):
     lanes = 200
     wl = workload.make_verify_workload(n_attrs=5, lanes=lanes, seed=29, tamper_every=9)
     buf = ref.cred_encode(wl.sig1, wl.sig2)
-    assert buf.shape == (lanes, 100) and buf[0, 0] == 1 and buf[0, 1] == 48 and buf[0, 50] == 1 and buf[0, 51] == 48
+    S, T = G1_SER, 2 + G1_SER                     # compressed G1 (48 / 32 bytes), one TLV-framed G1
+    assert buf.shape == (lanes, 2 * T) and buf[0, 0] == 1 and buf[0, 1] == S and buf[0, T] == 1 and buf[0, T + 1] == S
     pk = gpu_pkg.PSPubKey(wl.key.g, wl.key.gg, wl.key.XX, wl.key.Y, wl.key.YY, window_bits=8)
     ver = gpu_pkg.PSVerifier(pk)
     s1, s2 = ref.cred_decode(buf)
@@ -48,16 +50,16 @@ def test_verify_serialized_credentials(gpu_pkg, ref):
     # undecodable sigma2 on lane 0 (find an x with x^3 + 4 a non-residue), flipped y flag on lane 1
     bad = buf.copy()
     for v in range(1, 50):
-        bad[0, 52:100] = 0
-        bad[0, 52] = v
-        if not ref.g1_deserialize(bad[0:1, 52:100].copy())[1]:
+        bad[0, T + 2:2 * T] = 0
+        bad[0, T + 2] = v
+        if not ref.g1_deserialize(bad[0:1, T + 2:2 * T].copy())[1]:
             break
-    bad[1, 49] ^= 0x80
+    bad[1, T - 1] ^= 0x80
     got2, dec2 = ver.verify_serialized(bad, wl.attrs)
     assert dec2.tolist() == [0] + [1] * (lanes - 1)
     assert got2[0] == 0 and got2[1] == 0 and np.array_equal(got2[2:], exp[2:])
-    # bare 96-byte layout
-    raw = np.concatenate([buf[:, 2:50], buf[:, 52:100]], axis=1)
-    got3, _ = ver.verify_serialized(raw, wl.attrs, stride=96, off1=0, off2=48)
+    # bare layout: sigma1 || sigma2 (96 / 64 bytes)
+    raw = np.concatenate([buf[:, 2:T], buf[:, T + 2:2 * T]], axis=1)
+    got3, _ = ver.verify_serialized(raw, wl.attrs, stride=2 * S, off1=0, off2=S)
     assert np.array_equal(got3, exp)
     pk.close()

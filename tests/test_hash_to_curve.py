@@ -7,6 +7,8 @@ import hashlib
 import numpy as np
 import pytest
 
+from tests.conftest import FIELD_P, FP_BYTES, G1W
+
 MSGS = [b"", b"abc", b"rp.example", b"service", b"a" * 111, b"b" * 112, b"c" * 127, b"d" * 128, b"e" * 129, b"f" * 239, b"g" * 240,
         bytes(range(256)) * 3] + [b"svc%d.example.org" % i for i in range(40)]
 
@@ -24,7 +26,7 @@ def test_sha512_on_hostsim(hostsim):
 
 def test_hash_to_g1_lanes_match_mcl(hostsim, ref):
     for m in MSGS[:20]:
-        out = np.zeros(18, dtype=np.uint64)
+        out = np.zeros(G1W, dtype=np.uint64)
         assert hostsim.hostsim_hash_to_g1(C.c_char_p(m), C.c_size_t(len(m)), _p(out)) == 1
         want = ref.g1_op(ref.G_NORM, ref.hash_to_g1(m).reshape(1, -1))[0]
         assert np.array_equal(out, want), m[:16]
@@ -33,11 +35,10 @@ def test_hash_to_g1_lanes_match_mcl(hostsim, ref):
 def test_map_to_g1_exceptional_and_signs(hostsim, ref):
     """t = 0 is rejected like mcl; t and -t map to points with opposite y (Legendre sign rule); all three x-candidates occur."""
     rng = np.random.default_rng(5)
-    from oracle import ps_oracle as O
-    vals = [0, 1, 2, O.P - 1, O.P - 2] + [int.from_bytes(rng.bytes(48), "little") % O.P for _ in range(30)]
+    vals = [0, 1, 2, FIELD_P - 1, FIELD_P - 2] + [int.from_bytes(rng.bytes(FP_BYTES), "little") % FIELD_P for _ in range(30)]
     ts = ref.fp_from_ints(vals)
     for j, t in enumerate(ts):
-        out = np.zeros(18, dtype=np.uint64)
+        out = np.zeros(G1W, dtype=np.uint64)
         r = hostsim.hostsim_map_to_g1(_p(t), _p(out))
         want, ok = ref.map_to_g1(t)
         assert r == ok, vals[j]

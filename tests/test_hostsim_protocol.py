@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from tests import workload
+from tests.conftest import G1W, G2W
 
 
 def _p(a):
@@ -20,7 +21,7 @@ def test_fixed_base_table_mul(hostsim, ref):
     g = ref.hash_to_g1(b"abc")
     for w in (4, 5):
         for i in range(3):
-            out = np.zeros(18, dtype=np.uint64)
+            out = np.zeros(G1W, dtype=np.uint64)
             hostsim.hostsim_fixed_mul_g1(C.c_int(w), _p(g), _p(k[i]), _p(out))
             assert np.array_equal(out, ref.g1_op(ref.G_NORM, ref.g1_mul(g, k[i:i + 1]))[0]), (w, i)
 
@@ -33,8 +34,8 @@ def test_provide_id_lanes(hostsim, ref, n_attrs, n_hidden):
     blob, off = ref.pack_attrs(wl.req_attrs)
     ad_blob, ad_off = ref.pack_strings(wl.ads)
     verdict = np.zeros(lanes, dtype=np.uint8)
-    s1 = np.zeros((lanes, 18), dtype=np.uint64)
-    s2 = np.zeros((lanes, 18), dtype=np.uint64)
+    s1 = np.zeros((lanes, G1W), dtype=np.uint64)
+    s2 = np.zeros((lanes, G1W), dtype=np.uint64)
     hostsim.hostsim_provide_id(C.c_int(n_attrs), C.c_int(4), _p(wl.key.g), _p(wl.key.X), _p(wl.key.Y), C.c_size_t(lanes),
                                _p(wl.A), _p(wl.c), _p(wl.rs), C.c_int(wl.rs.shape[1]), _p(blob), _p(off), _p(ad_blob),
                                _p(ad_off), _p(wl.u), _p(verdict), _p(s1), _p(s2))
@@ -71,7 +72,7 @@ def test_point_decompression_lanes(hostsim, ref, g2):
     assert 0 < okv.sum() < len(okv)
     fn = hostsim.hostsim_g2_deserialize if g2 else hostsim.hostsim_g1_deserialize
     for j in range(len(okv)):
-        out = np.zeros(36 if g2 else 18, dtype=np.uint64)
+        out = np.zeros(G2W if g2 else G1W, dtype=np.uint64)
         r = fn(_p(enc[j]), _p(out))
         assert r == okv[j], j
         if okv[j]:

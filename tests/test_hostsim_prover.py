@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from tests import workload
+from tests.conftest import G1W, G2W, bls_only
 
 
 def _p(a):
@@ -19,7 +20,7 @@ def test_request_id_and_unblind_lanes(hostsim, ref, n_attrs, n_hidden):
     pw = workload.make_prover_request_workload(n_attrs, lanes, n_hidden, seed=6)
     blob, off = ref.pack_attrs(pw.attrs)
     ad_blob, ad_off = ref.pack_strings(pw.ads)
-    A = np.zeros((lanes, 18), dtype=np.uint64)
+    A = np.zeros((lanes, G1W), dtype=np.uint64)
     c = np.zeros((lanes, 4), dtype=np.uint64)
     rs = np.zeros((lanes, n_hidden + 1, 4), dtype=np.uint64)
     hostsim.hostsim_request_id(C.c_int(n_attrs), C.c_int(4), _p(pw.key.g), _p(pw.key.Y), C.c_size_t(lanes), _p(pw.hidden),
@@ -27,7 +28,7 @@ def test_request_id_and_unblind_lanes(hostsim, ref, n_attrs, n_hidden):
     assert np.array_equal(A, ref.g1_op(ref.G_NORM, pw.exp_A))
     assert np.array_equal(c, pw.exp_c)
     assert np.array_equal(rs, pw.exp_rs)
-    out2 = np.zeros((lanes, 18), dtype=np.uint64)
+    out2 = np.zeros((lanes, G1W), dtype=np.uint64)
     hostsim.hostsim_unblind(C.c_size_t(lanes), _p(pw.blind_sig1), _p(pw.blind_sig2), _p(pw.rnd[:, 0].copy()), _p(out2))
     assert np.array_equal(out2, ref.g1_op(ref.G_NORM, pw.exp_unblind2))
 
@@ -39,8 +40,8 @@ def test_prove_id_lanes(hostsim, ref, n_attrs, n_hidden, with_id):
     blob, off = ref.pack_attrs(pw.attrs)
     ad_blob, ad_off = ref.pack_strings(pw.ads)
     per = n_hidden + (2 if with_id else 1)
-    o = dict(sig1=np.zeros((lanes, 18), np.uint64), sig2=np.zeros((lanes, 18), np.uint64), k=np.zeros((lanes, 36), np.uint64),
-             phi=np.zeros((lanes, 18), np.uint64), E1=np.zeros((lanes, 18), np.uint64), E2=np.zeros((lanes, 18), np.uint64),
+    o = dict(sig1=np.zeros((lanes, G1W), np.uint64), sig2=np.zeros((lanes, G1W), np.uint64), k=np.zeros((lanes, G2W), np.uint64),
+             phi=np.zeros((lanes, G1W), np.uint64), E1=np.zeros((lanes, G1W), np.uint64), E2=np.zeros((lanes, G1W), np.uint64),
              c=np.zeros((lanes, 4), np.uint64), rs=np.zeros((lanes, per, 4), np.uint64))
     hostsim.hostsim_prove_id(C.c_int(n_attrs), C.c_int(4), _p(pw.key.gg), _p(pw.key.XX), _p(pw.key.YY), C.c_size_t(lanes),
                              _p(pw.sig1), _p(pw.sig2), _p(pw.hidden), _p(blob), _p(off), _p(ad_blob), _p(ad_off),
@@ -60,6 +61,7 @@ def _golden():
     return keys, p, arr
 
 
+@bls_only
 def test_prover_golden_fixtures_on_hostsim(hostsim):
     """committed reference outputs (tests/golden/prover.json), no live reference needed."""
     from oracle import ref as R

@@ -276,28 +276,29 @@ def assert_proof_equal(got: dict, exp: dict, with_id: bool):
 # ---- wire-format ingest ------------------------------------------------------------------
 def deserialize_cases(g2: bool, count=24):
     """serialized points (valid, infinity, flag flipped, x >= p, non-residue x) + mcl's verdict and result."""
-    from oracle import ps_oracle as O
+    from tests.conftest import FIELD_P
+    FB = 8 * ref.FP                              # bytes of a serialized Fp (48 / 32)
     rng = np.random.default_rng(11)
     base = ref.hash_to_g2(b"edf") if g2 else ref.hash_to_g1(b"abc")
     if g2:
-        mul, ser, deser, SZ = ref.g2_mul, ref.g2_serialize, ref.g2_deserialize, 96
+        mul, ser, deser, SZ = ref.g2_mul, ref.g2_serialize, ref.g2_deserialize, 2 * FB
     else:
-        mul, ser, deser, SZ = ref.g1_mul, ref.g1_serialize, ref.g1_deserialize, 48
+        mul, ser, deser, SZ = ref.g1_mul, ref.g1_serialize, ref.g1_deserialize, FB
     ref.seed(17)
     pts = mul(base, ref.fr_rand(count))
     enc = ser(pts).copy()
     enc[1] = 0                                   # infinity
     enc[2, SZ - 1] ^= 0x80                       # other root
     enc[3, :] = 0xff                             # x >= p (and flag set)
-    pbytes = np.frombuffer(O.P.to_bytes(48, "little"), dtype=np.uint8)
-    enc[4, SZ - 48:] = pbytes                    # x (or x.b) == p exactly
+    pbytes = np.frombuffer(FIELD_P.to_bytes(FB, "little"), dtype=np.uint8)
+    enc[4, SZ - FB:] = pbytes                    # x (or x.b) == p exactly
     for j in range(5, count):                    # random x: about half are non-residues
         if j % 2:
             enc[j, :SZ - 1] = np.frombuffer(rng.bytes(SZ - 1), dtype=np.uint8)
             enc[j, SZ - 1] &= 0x99               # keep x below p most of the time
     if g2:
         enc[5, :] = 0; enc[5, 0] = 3             # x = 3 (x.b = 0): exercises the x.b == 0 branch of Fp2::squareRoot
-        enc[7, :] = 0; enc[7, 0] = 2; enc[7, 95] = 0x80
+        enc[7, :] = 0; enc[7, 0] = 2; enc[7, SZ - 1] = 0x80
     want, okv = [], []
     for j in range(count):
         out, ok = deser(enc[j:j + 1])
