@@ -178,7 +178,22 @@ def job_throughput(lanes_per_rank: int, world: int, steps: int, ms_max: float) -
     return world * lanes_per_rank * steps / (ms_max * 1e-3)
 
 
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line: native libraries (NCCL prints its version banner on the first
+    collective) write to fd 1 directly, so fd 1 is pointed at stderr for the whole run and the result line goes to
+    the saved descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+def _emit(saved_fd: int, line: dict):
+    os.write(saved_fd, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    out_fd = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
@@ -223,7 +238,7 @@ def main():
                 "cpu_baseline": {"value": val, "unit": "verifications/s", "cores": threads, "kind": "reference",
                                  "sample": f"{sample} lanes per step"},
                 "e2e": {"value": val, "unit": "verifications/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        _emit(out_fd, line)
         return
 
     import torch
@@ -388,7 +403,7 @@ def main():
         except OSError as e:  # libpsref.so absent
             line["cpu_baseline"] = {"value": None, "unit": "verifications/s", "cores": 0, "kind": "reference",
                                     "sample": f"unavailable: {e}"}
-    print(json.dumps(line))
+    _emit(out_fd, line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -21,7 +21,8 @@
 extern "C" {
 #endif
 
-#define PSB_CURVE_BLS12_381 5 /* = MCL_BLS12_381 (mcl/include/mcl/curve_type.h:91) */
+#define PSB_CURVE_BLS12_381 5 /* = MCL_BLS12_381 (mcl/include/mcl/curve_type.h:91): libpsb.so */
+#define PSB_CURVE_BN254 0     /* = MCL_BN254 (curve_type.h:85), what initPairing() selects: libpsb_bn254.so */
 
 #define PSB_OK 0
 #define PSB_ERR_ARG (-1)

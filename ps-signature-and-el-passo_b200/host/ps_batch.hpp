@@ -18,9 +18,10 @@
 //   psb::PSSigner::el_passo_provide_id(requests, ads, u, sigs)          -> psb_provide_id  (u host-supplied)
 //
 // mcl objects are passed WITHOUT conversion: G1/G2/Fr in memory are Montgomery limb arrays in exactly
-// the layout psb.h takes.  Requires mcl::bn::initPairing(mcl::BLS12_381) -- the engine
-// implements the 381-bit curve only (the reference's tests default to BN254) -- and
-// psb::init() once per process.  Errors: std::runtime_error("attribute size does not match") as in
+// the layout psb.h takes.  One curve per build, like mcl's own bn256 / bn384 libraries: with
+// <mcl/bls12_381.hpp> objects (384-bit Fp, the reference's headers) call mcl::bn::initPairing(mcl::BLS12_381) and
+// link libpsb.so; with mcl's 256-bit configuration (<mcl/bn256.hpp> first, 4-word Fp) call initPairing() = BN254 --
+// what the reference's shipped tests select -- and link libpsb_bn254.so.  psb::init() once per process.  Errors: std::runtime_error("attribute size does not match") as in
 // src/ps-requester.cc:31-33 for size mismatches; psb::Error for engine failures (no GPU, CUDA error).
 // There is no CPU fallback for the batched overloads.
 #ifndef PSB_HOST_PS_BATCH_HPP_
@@ -46,13 +47,20 @@ struct Error : std::runtime_error {
 };
 inline void check(int rc, const char* what) { if (rc != PSB_OK) throw Error(rc, what); }
 
-// once per process, after mcl::bn::initPairing(mcl::BLS12_381); devices = CUDA ordinals (empty = device 0)
+constexpr size_t kFpWords = sizeof(mcl::bls12::Fp) / 8;   // 6: BLS12-381 objects (libpsb.so), 4: BN254 objects (libpsb_bn254.so)
+constexpr size_t kG1Ser = 8 * kFpWords;                   // compressed G1 on the wire: 48 / 32 bytes
+constexpr size_t kCredSer = 2 * (2 + kG1Ser);             // PSCredential::toBufferString: two TLV-framed G1 (100 / 68 bytes)
+
+// once per process, after mcl::bn::initPairing(...); devices = CUDA ordinals (empty = device 0)
 inline void init(const std::vector<int>& devices = {}) {
-  static_assert(sizeof(mcl::bls12::G1) == 18 * 8 && sizeof(mcl::bls12::G2) == 36 * 8 && sizeof(mcl::bls12::Fr) == 4 * 8 &&
-                sizeof(mcl::bls12::GT) == 72 * 8, "include <mcl/bls12_381.hpp> (384-bit Fp, 256-bit Fr storage)");
-  if (mcl::bls12::Fp::getOp().N != 6 || !mcl::bls12::Fp::getOp().isMont)
-    throw std::runtime_error("psb: call mcl::bn::initPairing(mcl::BLS12_381) first (381-bit Montgomery field)");
-  check(psb_init(PSB_CURVE_BLS12_381, devices.empty() ? nullptr : devices.data(), (int)devices.size()), "psb_init");
+  static_assert(kFpWords == 6 || kFpWords == 4, "mcl object size must be 384 bit (bls12_381.hpp) or 256 bit (bn256.hpp)");
+  static_assert(sizeof(mcl::bls12::G1) == 3 * kFpWords * 8 && sizeof(mcl::bls12::G2) == 6 * kFpWords * 8 &&
+                sizeof(mcl::bls12::Fr) == 4 * 8 && sizeof(mcl::bls12::GT) == 12 * kFpWords * 8, "unexpected mcl object layout");
+  if (mcl::bls12::Fp::getOp().N != kFpWords || !mcl::bls12::Fp::getOp().isMont)
+    throw std::runtime_error(kFpWords == 6 ? "psb: call mcl::bn::initPairing(mcl::BLS12_381) first (381-bit Montgomery field)"
+                                           : "psb: call mcl::bn::initPairing() (BN254) first (254-bit Montgomery field)");
+  check(psb_init(kFpWords == 6 ? PSB_CURVE_BLS12_381 : PSB_CURVE_BN254, devices.empty() ? nullptr : devices.data(),
+                 (int)devices.size()), "psb_init");
 }
 
 namespace detail {
@@ -118,30 +126,31 @@ public:
 
   // batched verify straight from the WIRE form: credentials[j] = PSCredential::toBufferString() bytes (two G1 TLVs,
   // src/ps-encoding.cc:384-401).  Points are decompressed on the GPU (psb_verify_ser); buffers that are not the
-  // canonical 100-byte layout go through the reference's own parser on the host first.  An undecodable point gives
+  // canonical 100-byte (BN254: 68-byte) layout go through the reference's own parser on the host first.  An undecodable point gives
   // verdict 0 (the reference's parser ignores deserialize failures).
   std::vector<uint8_t> verify(const std::vector<PSBuffer>& credentials,
                               const std::vector<std::vector<std::string>>& all_attributes) const {
     using namespace mcl::bls12;
     const size_t N = credentials.size();
     if (all_attributes.size() != N) throw std::runtime_error("attribute size does not match");
-    std::vector<uint8_t> flat(N * 96 + 1), verdict(N);
+    constexpr size_t S = kG1Ser, T = 2 + kG1Ser;   // compressed G1, one TLV-framed G1
+    std::vector<uint8_t> flat(N * 2 * S + 1), verdict(N);
     detail::Strings at;
     for (size_t j = 0; j < N; j++) {
       if (all_attributes[j].size() != m_n) throw std::runtime_error("attribute size does not match");
       const PSBuffer& b = credentials[j];
-      if (b.size() == 100 && b[0] == 1 && b[1] == 48 && b[50] == 1 && b[51] == 48) {
-        std::memcpy(&flat[96 * j], &b[2], 48);
-        std::memcpy(&flat[96 * j + 48], &b[52], 48);
+      if (b.size() == kCredSer && b[0] == 1 && b[1] == S && b[T] == 1 && b[T + 1] == S) {
+        std::memcpy(&flat[2 * S * j], &b[2], S);
+        std::memcpy(&flat[2 * S * j + S], &b[T + 2], S);
       } else {
         PSCredential c = PSCredential::fromBufferString(b);
-        c.sig1.serialize(&flat[96 * j], 48);
-        c.sig2.serialize(&flat[96 * j + 48], 48);
+        c.sig1.serialize(&flat[2 * S * j], S);
+        c.sig2.serialize(&flat[2 * S * j + S], S);
       }
       for (const auto& a : all_attributes[j]) at.add(a);
     }
     if (N == 0) return verdict;
-    check(psb_verify_ser(m_key.get(), N, flat.data(), 96, 0, 48, at.data(), at.off.data(), verdict.data(), nullptr),
+    check(psb_verify_ser(m_key.get(), N, flat.data(), 2 * S, 0, S, at.data(), at.off.data(), verdict.data(), nullptr),
           "psb_verify_ser");
     return verdict;
   }

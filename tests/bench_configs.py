@@ -44,6 +44,7 @@ def timed(fn, reps):
 
 
 def emit(rec, fh):
+    rec = dict(rec, curve=ref.CURVE)
     line = json.dumps(rec)
     print(line, flush=True)
     fh.write(line + "\n")
@@ -145,7 +146,7 @@ def main():
         (got, dec), dt = timed(lambda: ver.verify_serialized(big, battrs), args.reps)
         assert dec.all() and np.array_equal(got, np.tile(ev, r2)), "verify_serialized verdict mismatch vs reference"
         emit({"config": "cfg2-wire ps_verify from serialized credentials", "n_attrs": 5, "lanes": N, "distinct": D2,
-              "metric": "ps_verifications_per_sec", "e2e_value": N / dt, "seconds": dt, "h2d_bytes_per_lane": 100,
+              "metric": "ps_verifications_per_sec", "e2e_value": N / dt, "seconds": dt, "h2d_bytes_per_lane": int(buf.shape[1]),
               "gpu_launches": pkg.launch_count() - l0,
               "cpu_reference": {"deserialize_credentials_per_sec_one_thread": D2 / dec_s,
                                 "note": "PSCredential::fromBufferString = 2 G1::deserialize (mcl, host)"},

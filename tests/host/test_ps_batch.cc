@@ -22,7 +22,11 @@ static std::string ser(const G1& p) { return p.serializeToHexStr(); }
 int main(int argc, char** argv) {
   const size_t N = argc > 1 ? std::stoul(argv[1]) : 24;   // lanes
   const size_t n = 5;                                      // attributes, first two hidden
+#ifdef PSREF_BN254
+  initPairing();                 // BN254, as the reference's own tests do (test/ps-tests.cc:142)
+#else
   initPairing(mcl::BLS12_381);
+#endif
   try {
     psb::init();
   } catch (const std::exception& e) {

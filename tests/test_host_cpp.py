@@ -9,14 +9,16 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "oracle", "_ref", "test_ps_batch")
+BIN_BN254 = BIN + "_bn254"   # same source, mcl's 256-bit configuration + initPairing() = BN254, linked with libpsb_bn254.so
 
 
-def _bin():
-    if not os.path.exists(BIN):
+def _bin(path=BIN):
+    if not os.path.exists(path):
         if not os.path.isdir("/root/reference"):
             pytest.skip("oracle/_ref/test_ps_batch not built (needs /root/reference)")
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "hosttest"], stdout=subprocess.DEVNULL)
-    return BIN
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "hosttest"], stdout=subprocess.DEVNULL,
+                              stderr=subprocess.DEVNULL)
+    return path
 
 
 def test_cpp_dropin_fails_loudly_without_gpu():
@@ -24,13 +26,15 @@ def test_cpp_dropin_fails_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():
         pytest.skip("a GPU is present")
-    r = subprocess.run([_bin(), "4"], capture_output=True, text=True, timeout=120)
-    assert r.returncode == 3, r.stdout + r.stderr
-    assert "no CPU fallback" in r.stdout
+    for path in (BIN, BIN_BN254):
+        r = subprocess.run([_bin(path), "4"], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 3, r.stdout + r.stderr
+        assert "no CPU fallback" in r.stdout
 
 
 @pytest.mark.gpu
-def test_cpp_dropin_matches_reference_flow():
-    r = subprocess.run([_bin(), "24"], capture_output=True, text=True, timeout=600)
+@pytest.mark.parametrize("path", [BIN, BIN_BN254], ids=["bls12_381", "bn254"])
+def test_cpp_dropin_matches_reference_flow(path):
+    r = subprocess.run([_bin(path), "24"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "0 failures" in r.stdout
