@@ -1,5 +1,5 @@
 """build.py -- compiles the CUDA engine in-tree (sm_100a only): csrc/psb_api.cu -> libpsb.so (BLS12-381) and, with
--DPSB_CURVE_BN254, libpsb_bn254.so (BN254: same sources, 8-limb field, D-type twist, BN Miller loop / final
+-DPSB_BUILD_BN254, libpsb_bn254.so (BN254: same sources, 8-limb field, D-type twist, BN Miller loop / final
 exponentiation).  One curve per library, like mcl's own bn256 / bn384 builds; the C ABI (include/psb.h) is the same.
 
 nvcc cross-compiles without a GPU; the resulting .so travels with the repo snapshot to the GPU box.
@@ -46,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if force or stale(LIB):
         jobs.append(_compile(os.environ.get("PSB_LIB_OUT", LIB), [], verbose))
     if (force or stale(LIB_BN254)) and not os.environ.get("PSB_SKIP_BN254"):
-        jobs.append(_compile(LIB_BN254, ["-DPSB_CURVE_BN254"], verbose))
+        jobs.append(_compile(LIB_BN254, ["-DPSB_BUILD_BN254"], verbose))
     for j in jobs:
         if j.wait() != 0:
             raise subprocess.CalledProcessError(j.returncode, j.args)

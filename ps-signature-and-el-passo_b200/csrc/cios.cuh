@@ -20,7 +20,7 @@
 // Bounds: inputs < 2p (multiplicands of squarings are unreduced sums), sum of products < 4 p^2
 // => T < 2p at every row and the final value < 2p: one conditional subtraction canonicalises.
 #pragma once
-#ifdef PSB_CURVE_BN254
+#ifdef PSB_BUILD_BN254
 #include "fp_cios_bn254.cuh"
 #else
 #include "fp_cios.cuh"

@@ -33,7 +33,7 @@
 #define PSB_UNROLL
 #endif
 
-#ifdef PSB_CURVE_BN254
+#ifdef PSB_BUILD_BN254
 #include "constants_bn254.cuh"
 #else
 #include "constants.cuh"

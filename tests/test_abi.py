@@ -33,8 +33,12 @@ def test_no_cpu_fallback(pkg):
         has_gpu = False
     if has_gpu:
         pytest.skip("GPU present")
-    assert L.psb_init(5, None, 0) != 0  # no device -> error, never a silent CPU path
-    assert b"no CUDA device" in L.psb_last_error() or L.psb_last_error()
+    L.psb_last_error.restype = C.c_char_p
+    assert L.psb_init(pkg.MCL_CURVE, None, 0) != 0  # no device -> error, never a silent CPU path
+    assert b"no CUDA device" in L.psb_last_error()  # ... and the curve check passed: the library is built for ITS curve
+    other = 0 if pkg.MCL_CURVE == 5 else 5
+    assert L.psb_init(other, None, 0) == -4         # PSB_ERR_UNSUPPORTED: one curve per library
+    assert b"is built for" in L.psb_last_error()
     assert L.psb_test_op(0, C.c_size_t(1), None, None, None, None) != 0
 
 

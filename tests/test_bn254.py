@@ -1,7 +1,7 @@
 """BN254 instantiation: the curve `initPairing()` selects in the reference's shipped tests and WASM
 build.  One curve per process -- mcl and the engine keep the curve in static state, and each curve is its own
 library (libpsb_bn254.so / libhostsim_bn254.so / oracle/_ref/libpsref_bn254.so, all built from the same sources with
--DPSB_CURVE_BN254 resp. mcl's 256-bit configuration) -- so the curve-generic test modules are re-run in a child pytest
+-DPSB_BUILD_BN254 resp. mcl's 256-bit configuration) -- so the curve-generic test modules are re-run in a child pytest
 with PSB_CURVE=bn254.  Golden-fixture and Python-oracle tests are BLS12-381-only (`bls_only`) and skip themselves there.
 """
 import os
