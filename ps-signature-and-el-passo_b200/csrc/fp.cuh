@@ -478,7 +478,8 @@ PSB_HD PSB_NOINL void fp_pow_nib(Fp& r, const Fp& a, const uint32_t* nib /*8 * P
   }
   r = acc;
 }
-PSB_HD PSB_INL void fp_inv(Fp& r, const Fp& a) { fp_pow_nib(r, a, PSB_K(FP_PM2_NIB)); }
+// (kept as the cross-check of modinv.cuh and for A/B builds with -DPSB_INV_FERMAT; the product path uses fp_inv there)
+PSB_HD PSB_INL void fp_inv_fermat(Fp& r, const Fp& a) { fp_pow_nib(r, a, PSB_K(FP_PM2_NIB)); }
 
 // normal form <-> Montgomery
 PSB_HD PSB_INL void fp_from_mont(Fp& r, const Fp& a) {

@@ -21,6 +21,10 @@ struct FixedLine { Fp2 nl, c0; };
 // doublings + additions of the loop parameter (BLS12-381: |z| = 0xd201000000010000 -> 63 + 5; BN254: |6z+2| =
 // 0x18300000000000004 -> 64 + 4, plus the two closing additions of pi(Q) and -pi^2(Q), bn.hpp:1698-1709)
 constexpr int kMillerSteps = PSB_ML_NBITS + PSB_ML_ADDS + (PSB_IS_BN ? 2 : 0);
+// a fixed-line table holds one trailing slot whose first word says whether the lines were scaled to constant term 1
+// (precompute_fixed_lines): any factor in Fp2 dies in the final exponentiation, and a line 1 + c2 w^2 + c3 w^3 costs
+// 9 Fp2 products instead of 13
+constexpr int kFixedLineSlots = kMillerSteps + 1;
 
 struct G2H { Fp2 x, y, z; };  // homogeneous projective: (X/Z, Y/Z)
 
@@ -108,6 +112,22 @@ PSB_HD PSB_NOINL void ml_add_step(G2H& T, Fp2& c0, Fp2& c2, Fp2& c3, const G2H& 
   fp2_mul(T.z, l3, W);
 }
 
+// f *= the precomputed line L of the fixed argument, evaluated at P2 = (x2, y2)
+PSB_HD PSB_INL void ml_fixed_line(Fp12& f, const FixedLine& L, const Fp& x2, const Fp& y2, bool scaled) {
+  Fp2 c2, c3;
+  fp2_mul_fp(c2, L.nl, x2);
+#if PSB_TWIST_MTYPE
+  if (scaled) {                                   // L = (nl / c0, 1 / c0)
+    fp2_mul_fp(c3, L.c0, y2);
+    fp12_mul_line_1(f, c2, c3);
+    return;
+  }
+#endif
+  (void)scaled;
+  c3.a = y2; fp_set_zero(c3.b);
+  ml_mul_line(f, L.c0, c2, c3);
+}
+
 #if PSB_IS_BN
 // pi on the twist (mcl Frobenius(G2), bn.hpp:2155-2162): (x, y) -> (conj(x) cx, conj(y) cy); homogeneous: conj(Z)
 PSB_HD PSB_INL void fp2_load_const(Fp2& c, const uint32_t* w) {
@@ -129,6 +149,7 @@ PSB_HD PSB_NOINL void g2h_frobenius(G2H& Q) {
 PSB_HD PSB_NOINL void miller_loop2(Fp12& f, const Fp& x1, const Fp& y1, const G2J& Q1, const Fp& x2, const Fp& y2,
                                    const FixedLine* lines2, bool use2) {
   const bool use1 = !pt_is_zero(Q1);
+  const bool scaled2 = use2 && lines2[kMillerSteps].nl.a.v[0] != 0;
   G2H Q, T;
   // Jacobian (X, Y, Z) -> homogeneous (X Z, Y, Z^3)
   fp2_mul(Q.x, Q1.x, Q1.z);
@@ -146,9 +167,7 @@ PSB_HD PSB_NOINL void miller_loop2(Fp12& f, const Fp& x1, const Fp& y1, const G2
     }
     if (use2) {
       const FixedLine L = lines2[li];
-      fp2_mul_fp(c2, L.nl, x2);
-      c3.a = y2; fp_set_zero(c3.b);
-      ml_mul_line(f, L.c0, c2, c3);
+      ml_fixed_line(f, L, x2, y2, scaled2);
     }
     li++;
     if (ml_bit(i)) {
@@ -158,9 +177,7 @@ PSB_HD PSB_NOINL void miller_loop2(Fp12& f, const Fp& x1, const Fp& y1, const G2
       }
       if (use2) {
         const FixedLine L = lines2[li];
-        fp2_mul_fp(c2, L.nl, x2);
-        c3.a = y2; fp_set_zero(c3.b);
-        ml_mul_line(f, L.c0, c2, c3);
+        ml_fixed_line(f, L, x2, y2, scaled2);
       }
       li++;
     }
@@ -181,15 +198,13 @@ PSB_HD PSB_NOINL void miller_loop2(Fp12& f, const Fp& x1, const Fp& y1, const G2
   if (use2) {
     for (int t = 0; t < 2; t++) {
       const FixedLine L = lines2[li++];
-      fp2_mul_fp(c2, L.nl, x2);
-      c3.a = y2; fp_set_zero(c3.b);
-      ml_mul_line(f, L.c0, c2, c3);
+      ml_fixed_line(f, L, x2, y2, scaled2);
     }
   }
 #endif
 }
 
-// precompute the kMillerSteps affine lines of a fixed Q (affine, not infinity).  One thread, once per key.
+// precompute the kMillerSteps affine lines of a fixed Q (affine, not infinity) into out[kFixedLineSlots].  One thread, once per key.
 PSB_HD PSB_NOINL void precompute_fixed_lines(FixedLine* out, const G2A& Q) {
   Fp2 x = Q.x, y = Q.y, lam, t, u, x3;
   int li = 0;
@@ -231,16 +246,95 @@ PSB_HD PSB_NOINL void precompute_fixed_lines(FixedLine* out, const G2A& Q) {
     x = x3;
   }
 #endif
+  // scale every line to constant term 1 (M-type twist): (nl, c0) -> (nl / c0, 1 / c0); a zero c0 (a tangent or chord through
+  // x = 0, y = 0: probability ~1/p^2) leaves the table unscaled
+  fp2_set_zero(out[kMillerSteps].nl); fp2_set_zero(out[kMillerSteps].c0);
+#if PSB_TWIST_MTYPE && !defined(PSB_LINES_UNSCALED)
+  bool all = true;
+  for (int k = 0; k < kMillerSteps; k++) all = all && !fp2_is_zero(out[k].c0);
+  if (all) {
+    for (int k = 0; k < kMillerSteps; k++) {
+      Fp2 ic;
+      fp2_inv(ic, out[k].c0);
+      fp2_mul(out[k].nl, out[k].nl, ic);
+      out[k].c0 = ic;
+    }
+    out[kMillerSteps].nl.a.v[0] = 1;
+  }
+#endif
 }
 
-// y = x^z (z < 0): x^|z| by square-and-multiply with cyclotomic squarings, then conjugate
-PSB_HD PSB_NOINL void pow_z(Fp12& y, const Fp12& x) {
+// y = x^z (z < 0): x^|z| by square-and-multiply with cyclotomic squarings, then conjugate (mcl pow_z, bn.hpp:1150-1176)
+PSB_HD PSB_NOINL void pow_z_gs(Fp12& y, const Fp12& x) {
   Fp12 acc = x;
   for (int i = PSB_Z_NBITS - 1; i >= 0; i--) {
     fp12_cyclo_sqr(acc, acc);
     if (z_bit(i)) fp12_mul(acc, acc, x);
   }
   fp12_conj(y, acc);
+}
+
+// The same value through Karabina's compressed squarings: x^|z| = prod over the set bits i of x^(2^i).  ONE chain of
+// PSB_Z_NBITS compressed squarings (6 Fp2 squarings each instead of 9) passes through every x^(2^i); the compressed
+// values at the set bits are kept, their (g0, g1) coordinates are rebuilt with ONE shared inversion (Montgomery's trick
+// over the denominators 4 g2), and the full elements are multiplied together.  x must lie in the cyclotomic subgroup.
+// A zero denominator (x = 1, e.g. a lane whose Miller value is trivial; otherwise probability ~2^-760) falls back to
+// pow_z_gs, so the result is the same field element on every input.
+constexpr int kZSetBits = PSB_Z_SETBITS_HI;          // set bits of |z| above bit 0, including the leading one
+PSB_HD PSB_NOINL void pow_z(Fp12& y, const Fp12& x) {
+#ifdef PSB_POWZ_GS
+  pow_z_gs(y, x);
+#else
+  CycC keep[kZSetBits];
+  Fp2 pre[kZSetBits];
+  {
+    CycC c;
+    c.g2 = x.b.a; c.g3 = x.a.c; c.g4 = x.a.b; c.g5 = x.b.c;
+    int k = 0;
+    for (int i = 1; i <= PSB_Z_NBITS; i++) {
+      cyclo_csqr(c, c);
+      if (i == PSB_Z_NBITS || z_bit(i)) keep[k++] = c;
+    }
+  }
+  // prefix products of the denominators 4 g2
+  for (int k = 0; k < kZSetBits; k++) {
+    Fp2 d;
+    fp2_dbl(d, keep[k].g2); fp2_dbl(d, d);
+    if (k == 0) pre[0] = d; else fp2_mul(pre[k], pre[k - 1], d);
+  }
+  bool degenerate = fp2_is_zero(pre[kZSetBits - 1]);
+#ifdef __CUDA_ARCH__
+  // Both paths give the same field element, so the whole warp takes the fallback when any lane needs it: the call
+  // stays warp-uniform.  (A divergent call here let the callee's use of uniform registers clobber stack addresses the
+  // other lanes still held in uniform registers -- observed as an invalid local read on the BN254 build.)
+  degenerate = __any_sync(__activemask(), degenerate);
+#endif
+  if (degenerate) { pow_z_gs(y, x); return; }
+  Fp2 inv;
+  fp2_inv(inv, pre[kZSetBits - 1]);
+  Fp12 acc, t;
+  for (int k = kZSetBits - 1; k >= 0; k--) {
+    Fp2 dinv, num, g1;
+    if (k > 0) {
+      Fp2 d;
+      fp2_mul(dinv, inv, pre[k - 1]);            // 1 / den_k
+      fp2_dbl(d, keep[k].g2); fp2_dbl(d, d);
+      fp2_mul(inv, inv, d);                      // 1 / (den_0 ... den_{k-1})
+    } else {
+      dinv = inv;
+    }
+    cyclo_decompress_num(num, keep[k]);
+    fp2_mul(g1, num, dinv);
+    if (k == kZSetBits - 1) {
+      cyclo_decompress_fill(acc, keep[k], g1);
+    } else {
+      cyclo_decompress_fill(t, keep[k], g1);
+      fp12_mul(acc, acc, t);
+    }
+  }
+  if (z_bit(0)) fp12_mul(acc, acc, x);
+  fp12_conj(y, acc);
+#endif
 }
 
 // y = x^((p^12-1)/r * 3), structured as mcl's finalExp (bn.hpp:1643-1659)

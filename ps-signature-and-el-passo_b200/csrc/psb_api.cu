@@ -317,7 +317,7 @@ psb_key* psb_key_create(const uint64_t* g, const uint64_t* gg, const uint64_t* X
     bool ok = cudaSetDevice(dv->ordinal) == cudaSuccess;
     ok = ok && cudaMalloc(&k.g1pts, h1.size() * sizeof(G1J)) == cudaSuccess;
     ok = ok && cudaMalloc(&k.g2pts, h2.size() * sizeof(G2J)) == cudaSuccess;
-    ok = ok && cudaMalloc(&k.lines, kMillerSteps * sizeof(FixedLine)) == cudaSuccess;
+    ok = ok && cudaMalloc(&k.lines, kFixedLineSlots * sizeof(FixedLine)) == cudaSuccess;
     if (!ok) { fail(PSB_ERR_NOMEM, "key allocation", cudaGetLastError()); psb_key_destroy(key); return nullptr; }
     cudaMemcpyAsync(k.g1pts, h1.data(), h1.size() * sizeof(G1J), cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(k.g2pts, h2.data(), h2.size() * sizeof(G2J), cudaMemcpyHostToDevice, st);

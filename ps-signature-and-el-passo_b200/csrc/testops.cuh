@@ -142,7 +142,7 @@ PSB_HD inline void test_op_run(int op, const uint32_t* a, const uint32_t* b, con
       g1_affine_for_pairing(x1, y1, P1);
       g1_affine_for_pairing(x2, y2, P2);
       fp_neg(y2, y2);
-      FixedLine lines[kMillerSteps];
+      FixedLine lines[kFixedLineSlots];
       G2A q2; q2.x = Q2.x; q2.y = Q2.y;
       precompute_fixed_lines(lines, q2);
       Fp12 f, e;

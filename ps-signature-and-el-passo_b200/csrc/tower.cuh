@@ -14,6 +14,7 @@
 // Fp2 all values are canonical 48-byte elements.
 #pragma once
 #include "fp.cuh"
+#include "modinv.cuh"
 
 namespace psb {
 
@@ -371,6 +372,23 @@ PSB_HD PSB_NOINL void fp12_mul_line(Fp12& f, const Fp2& c0, const Fp2& c2, const
   fp6_add_mulv(f.a, t0, t1);
 }
 
+// f *= (1 + c2 w^2 + c3 w^3): a line whose constant term was scaled to 1 (fixed-argument lines, pairing.cuh).
+// With A = 1 + c2 v, B = c3 v:  fa A = fa + fa (c2 v),  (fa + fb)(A + B) = fa + fb + (fa + fb)((c2 + c3) v)
+//   f.a' = fa + fa (c2 v) + v fb (c3 v),   f.b' = fb + (fa + fb)((c2 + c3) v) - fa (c2 v) - fb (c3 v).    9 Fp2 products.
+PSB_HD PSB_NOINL void fp12_mul_line_1(Fp12& f, const Fp2& c2, const Fp2& c3) {
+  Fp6 t0, t1, s;
+  Fp2 c23;
+  fp6_mul_1(t0, f.a, c2);
+  fp6_mul_1(t1, f.b, c3);
+  fp6_add(s, f.a, f.b);
+  fp2_add(c23, c2, c3);
+  fp6_mul_1(s, s, c23);
+  fp6_sub2(s, s, t0, t1);
+  fp6_add(f.b, f.b, s);
+  fp6_add_mulv(t0, t0, t1);
+  fp6_add(f.a, f.a, t0);
+}
+
 // x * a0 with a0 in Fp2, 3 Fp2 products
 PSB_HD PSB_NOINL void fp6_mul_fp2(Fp6& z, const Fp6& x, const Fp2& a0) {
   fp2_mul(z.a, x.a, a0);
@@ -426,31 +444,76 @@ PSB_HD PSB_NOINL void fp12_frobenius(Fp12& r, const Fp12& x, int j) {
 }
 
 // Granger-Scott squaring in the cyclotomic subgroup (cf. mcl fasterSqr/sqrFp4, bn.hpp:1075-1144).
-// Per Fp4 pair (xe, xo): t0 = xe^2, t1 = xo^2, s = (xe + xo)^2;  z0 = t0 + xi t1,  z1 = s - t0 - t1 = 2 xe xo;
-// outputs 3 z -+ 2 x are formed by the fused fp2_gs_* kernels (no intermediate z is stored).
-PSB_HD PSB_NOINL void fp12_cyclo_sqr(Fp12& y, const Fp12& x) {
-  // slots: x0=a.a x4=a.b x3=a.c x2=b.a x1=b.b x5=b.c
-  Fp2 t0, t1, s, u0, u1, v2, v3;
-  // pair (x0, x1) -> y0, y1
-  fp2_sqr(t0, x.a.a); fp2_sqr(t1, x.b.b); fp2_sqr_sum(s, x.a.a, x.b.b);
-  fp2_sub2(s, s, t0, t1);                       // z1 = 2 x0 x1
-  fp2_xi_add(t0, t1, t0);                       // z0 = x0^2 + xi x1^2
-  fp2_3a2b(u0, t0, x.a.a, true);                // y0 = 3 z0 - 2 x0
-  fp2_3a2b(u1, s, x.b.b, false);                // y1 = 3 z1 + 2 x1
-  // pair (x4, x5) -> y2 (needs x2), y3 (needs x3): before the x4 / x5 slots are overwritten
-  fp2_sqr(t0, x.a.b); fp2_sqr(t1, x.b.c); fp2_sqr_sum(s, x.a.b, x.b.c);
+// With s = w^3 (s^2 = xi) an element is A + B w + C w^2 over Fp4 = Fp2[s]:  A = x0 + x1 s, B = x2 + x3 s, C = x4 + x5 s,
+// and x^2 = (3 A^2 - 2 conj A) + (3 s C^2 + 2 conj B) w + (3 B^2 - 2 conj C) w^2.
+// Per Fp4 square (xe + xo s)^2 = z0 + z1 s:  t0 = xe^2, t1 = xo^2, z0 = t0 + xi t1, z1 = (xe + xo)^2 - t0 - t1;
+// outputs 3 z -+ 2 x are formed by the fused fp2_3a2b kernel (no intermediate z is stored).
+//
+// The B and C coordinates of the square depend on B and C only: that is Karabina's compressed squaring ("Squaring in
+// cyclotomic subgroups", Math. Comp. 2013) -- 6 Fp2 squarings instead of 9 -- used by pow_z (pairing.cuh) for the
+// long runs of squarings; (x0, x1) are recovered afterwards by cyclo_decompress_*.
+struct CycC { Fp2 g2, g3, g4, g5; };   // (x2, x3, x4, x5) = slots b.a, a.c, a.b, b.c of an Fp12
+
+// (y2, y3, y4, y5) = compressed square of (x2, x3, x4, x5); outputs may alias the inputs slot by slot
+PSB_HD PSB_NOINL void cyclo_csqr4(Fp2& y2, Fp2& y3, Fp2& y4, Fp2& y5, const Fp2& x2, const Fp2& x3, const Fp2& x4, const Fp2& x5) {
+  Fp2 t0, t1, s, v2, v3;
+  // C^2 -> y2 = 3 xi z1 + 2 x2,  y3 = 3 z0 - 2 x3
+  fp2_sqr(t0, x4); fp2_sqr(t1, x5); fp2_sqr_sum(s, x4, x5);
   fp2_sub2(s, s, t0, t1);
   fp2_mul_xi(s, s);
   fp2_xi_add(t0, t1, t0);
-  fp2_3a2b(v2, s, x.b.a, false);                // y2 = 3 xi z1 + 2 x2
-  fp2_3a2b(v3, t0, x.a.c, true);                // y3 = 3 z0 - 2 x3
-  // pair (x2, x3) -> y4 (needs x4), y5 (needs x5)
-  fp2_sqr(t0, x.b.a); fp2_sqr(t1, x.a.c); fp2_sqr_sum(s, x.b.a, x.a.c);
+  fp2_3a2b(v2, s, x2, false);
+  fp2_3a2b(v3, t0, x3, true);
+  // B^2 -> y4 = 3 z0 - 2 x4,  y5 = 3 z1 + 2 x5
+  fp2_sqr(t0, x2); fp2_sqr(t1, x3); fp2_sqr_sum(s, x2, x3);
   fp2_sub2(s, s, t0, t1);
   fp2_xi_add(t0, t1, t0);
-  fp2_3a2b(y.a.b, t0, x.a.b, true);             // y4 = 3 z0 - 2 x4
-  fp2_3a2b(y.b.c, s, x.b.c, false);             // y5 = 3 z1 + 2 x5
-  y.a.a = u0; y.b.b = u1; y.b.a = v2; y.a.c = v3;
+  fp2_3a2b(y4, t0, x4, true);
+  fp2_3a2b(y5, s, x5, false);
+  y2 = v2; y3 = v3;
+}
+PSB_HD PSB_INL void cyclo_csqr(CycC& y, const CycC& x) { cyclo_csqr4(y.g2, y.g3, y.g4, y.g5, x.g2, x.g3, x.g4, x.g5); }
+
+PSB_HD PSB_NOINL void fp12_cyclo_sqr(Fp12& y, const Fp12& x) {
+  // slots: x0=a.a x4=a.b x3=a.c x2=b.a x1=b.b x5=b.c
+  Fp2 t0, t1, s, u0, u1;
+  // A^2 -> y0 = 3 z0 - 2 x0,  y1 = 3 z1 + 2 x1
+  fp2_sqr(t0, x.a.a); fp2_sqr(t1, x.b.b); fp2_sqr_sum(s, x.a.a, x.b.b);
+  fp2_sub2(s, s, t0, t1);                       // z1 = 2 x0 x1
+  fp2_xi_add(t0, t1, t0);                       // z0 = x0^2 + xi x1^2
+  fp2_3a2b(u0, t0, x.a.a, true);
+  fp2_3a2b(u1, s, x.b.b, false);
+  cyclo_csqr4(y.b.a, y.a.c, y.a.b, y.b.c, x.b.a, x.a.c, x.a.b, x.b.c);
+  y.a.a = u0; y.b.b = u1;
+}
+
+// Decompression (Karabina, Thm 3.2 in the basis above), split around the one inversion so that several elements share it:
+//   g1 = (xi g5^2 + 3 g4^2 - 2 g3) / (4 g2),   g0 = (2 g1^2 + g2 g5 - 3 g3 g4) xi + 1        (g2 != 0)
+PSB_HD PSB_NOINL void cyclo_decompress_num(Fp2& num, const CycC& c) {
+  Fp2 t0, t1;
+  fp2_sqr(t0, c.g5);
+  fp2_sqr(t1, c.g4);
+  fp2_xi_add(t0, t0, t1);            // xi g5^2 + g4^2
+  fp2_dbl(t1, t1);                   // 2 g4^2
+  fp2_add(t0, t0, t1);
+  fp2_dbl(t1, c.g3);
+  fp2_sub(num, t0, t1);
+}
+// x = the full element with (g0, g1) rebuilt from g1 = num / (4 g2)
+PSB_HD PSB_NOINL void cyclo_decompress_fill(Fp12& x, const CycC& c, const Fp2& g1) {
+  Fp2 t0, t1, t2;
+  fp2_sqr(t0, g1); fp2_dbl(t0, t0);             // 2 g1^2
+  fp2_mul(t1, c.g2, c.g5);
+  fp2_mul(t2, c.g3, c.g4);
+  fp2_add(t0, t0, t1);
+  fp2_dbl(t1, t2); fp2_add(t1, t1, t2);         // 3 g3 g4
+  fp2_sub(t0, t0, t1);
+  fp2_mul_xi(t0, t0);
+  Fp2 one;
+  fp2_set_one(one);
+  fp2_add(x.a.a, t0, one);
+  x.b.b = g1;
+  x.b.a = c.g2; x.a.c = c.g3; x.a.b = c.g4; x.b.c = c.g5;
 }
 
 }  // namespace psb

@@ -88,7 +88,7 @@ void hostsim_verify_id(int n, int w, const uint32_t* gg, const uint32_t* XX, con
   ld(b2, XX); host_table(tAux, b2, w);
   ld(b1, service_pt); host_table(tB, b1, w);
   if (with_id) { ld(b1, g); host_table(tB, b1, w); ld(b1, y); host_table(tB, b1, w); ld(b1, h); host_table(tB, b1, w); }
-  std::vector<FixedLine> lines(kMillerSteps);
+  std::vector<FixedLine> lines(kFixedLineSlots);
   G2A q; q.x = ggj.x; q.y = ggj.y;
   precompute_fixed_lines(lines.data(), q);
   for (size_t j = 0; j < N; j++) {

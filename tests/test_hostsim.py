@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from tests.conftest import BN254, CURVE_Z, GROUP_R, rand_fp_raw
+from tests.conftest import BN254, CURVE_Z, FIELD_P, FP_BYTES, GROUP_R, rand_fp_raw
 
 
 def hop(hs, op, a, b=None, c=None):
@@ -44,6 +44,36 @@ def test_fields(hostsim, ref, rng):
     assert np.array_equal(hop(hostsim, 32, a), ref.fp12_op(ref.OP_INV, a))
     for k in (1, 2, 3):
         assert np.array_equal(hop(hostsim, 32 + k, a), ref.fp12_frobenius(k, a))
+
+
+def test_fp_inv_divsteps_edges(hostsim, ref, rng):
+    """Fp::inv through the Bernstein-Yang divstep iteration (csrc/modinv.cuh) on raw limb patterns that stress the
+    iteration count and the sign handling: 0, 1, p-1, powers of two (long runs of even g), p - 2^k, all-ones limbs, and
+    random values -- against mcl's Fp::inv (ext-gcd), raw Montgomery limbs compared bit for bit."""
+    P = FIELD_P
+    bits = P.bit_length()
+    raw = [0, 1, 2, 3, P - 1, P - 2, (P - 1) // 2, (P + 1) // 2, (1 << (bits - 1)) - 1, 1 << (bits - 1)]
+    raw += [1 << k for k in range(1, bits - 1, 7)] + [P - (1 << k) for k in range(1, bits - 1, 11)]
+    raw += [((1 << bits) - 1) % P, (0x5555555555555555 * (1 << 320 | 1 << 256 | 1 << 192 | 1 << 128 | 1 << 64 | 1)) % P]
+    raw += [int.from_bytes(rng.bytes(FP_BYTES), "little") % P for _ in range(300)]
+    a = np.frombuffer(b"".join(v.to_bytes(FP_BYTES, "little") for v in raw), dtype=np.uint64).reshape(len(raw), -1).copy()
+    got = hop(hostsim, 5, a)
+    assert not got[0].any()          # inv(0) = 0 (the reference's Vint ext-gcd divides by zero on 0: not asked)
+    assert np.array_equal(got[1:], ref.fp_op(5, a[1:]))
+
+
+def test_final_exp_compressed_pow_z_and_fallback(hostsim, ref, rng):
+    """finalExp with pow_z on Karabina's compressed squarings (csrc/pairing.cuh): generic Fp12 inputs, and inputs whose
+    cyclotomic image is 1 (the value 1 itself, elements of Fp2 and Fp6: a zero denominator in the decompression, which
+    must take the Granger-Scott fallback) -- GT bytes against mcl's finalExp."""
+    a = rand_fp_raw(ref, rng, 6, 12)
+    one = ref.fp_from_ints([1]).reshape(-1)
+    fp = a.shape[1] // 12
+    a[0] = 0; a[0, :fp] = one                 # 1
+    a[1, 2 * fp:] = 0                         # an element of Fp2
+    a[2, 6 * fp:] = 0                         # an element of Fp6 (b = 0)
+    assert np.array_equal(hop(hostsim, 61, a), ref.final_exp(a))
+    assert np.array_equal(hop(hostsim, 61, a[:3]), np.repeat(a[0:1], 3, axis=0))
 
 
 def test_groups_and_pairing(hostsim, ref):
