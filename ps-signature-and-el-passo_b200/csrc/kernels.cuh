@@ -14,13 +14,22 @@
 
 namespace psb {
 
-constexpr int kBlock = 128;
-// resident blocks per SM the verify kernels are compiled for: 4 x 128 threads = 128 registers/thread.
-// Measured on B200 (r1): the kernels run at the 1000 W power cap, and higher occupancy (5/6/8 blocks)
-// only lowered the SM clock (1942 -> 1837 -> 1762 -> 1702 MHz) and the throughput.
-#ifndef PSB_MINB
-#define PSB_MINB 4
+#ifndef PSB_BLOCK
+#define PSB_BLOCK 128
 #endif
+constexpr int kBlock = PSB_BLOCK;
+// The pairing-pipeline kernels (MSM, Miller loop, final exponentiation) are compiled for 128 registers/thread
+// (__launch_bounds__(512, 1)) = 16 resident warps per SM, launched as ONE 512-thread block per SM for large batches and
+// as 256- or 128-thread blocks for small ones (pair_block() in psb_api.cu).  Measured on B200 (r1s, 2^20 lanes): the warps
+// of a block run the same straight-line schedule nearly in step and share instruction fetches -- the final
+// exponentiation, whose stall samples are 18 % instruction fetch, takes 363 / 345 / 337 ms with 128 / 256 / 512-thread
+// blocks at the same occupancy; the Miller loop and the MSM do not care.  More warps per SM (5/6/8 x 128 threads)
+// only lowered the SM clock at the 1000 W cap (1942 -> 1837 -> 1762 -> 1702 MHz) and the throughput (r1).
+#ifndef PSB_PAIR_BLOCK
+#define PSB_PAIR_BLOCK 512
+#endif
+constexpr int kPairBlock = PSB_PAIR_BLOCK;
+#define PSB_PAIR_BOUNDS __launch_bounds__(kPairBlock, 512 / kPairBlock)
 
 // ---- parity probe ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_test_op(int op, size_t n, int s0, int s1, int s2, int s3,
@@ -107,6 +116,33 @@ __global__ void __launch_bounds__(256) k_bench_mad(int kind, int iters, const ui
     for (int j = 0; j < PSB_NL; j++) s ^= E1[j] ^ O1[j] ^ E2[j] ^ O2[j] ^ E3[j] ^ O3[j];
     if (s == 0xdeadbeefu) sink[0] = s;
 #endif
+  } else if (kind == 8) {
+    // FP64 fused multiply-add (round toward zero, the form of the double-precision big-number multipliers): 8 chains.
+    // Orientation for a DFMA-based Montgomery multiplier: one DFMA carries a 52-bit x 52-bit partial product.
+    double acc[8], x = (double)(a | 1u), y = 1.0 + (double)(b & 0xffu) * 1e-9;
+    for (int j = 0; j < 8; j++) acc[j] = (double)(seed[j] ^ t);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[j] = __fma_rz(acc[j], y, x);
+    }
+    double s = 0;
+    for (int j = 0; j < 8; j++) s += acc[j];
+    if (s == 12345.678) sink[0] = 1;
+  } else if (kind == 9) {
+    // one row of a carry-free radix-2^30 multiplier: 13 independent 64-bit accumulators, 13 distinct multiplicand limbs
+    unsigned long long acc[13];
+    uint32_t av[13];
+    for (int j = 0; j < 13; j++) { acc[j] = ((unsigned long long)(seed[j] & 0xffff) << 32) | (seed[8 + j] ^ t); av[j] = (seed[j + 3] + t) & 0x3fffffffu; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int j = 0; j < 13; j++) {
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(av[j]), "r"(b));
+      }
+      b = (b + (uint32_t)acc[0]) & 0x3fffffffu;   // (sums wrap: a rate probe, not arithmetic)
+    }
+    unsigned long long s = 0;
+    for (int j = 0; j < 13; j++) s ^= acc[j];
+    if (s == 0xdeadbeefull) sink[0] = (uint32_t)s;
   } else {
     // plain 32-bit IMAD (lo only), 16 independent chains
     uint32_t lo[16];
@@ -206,7 +242,7 @@ __global__ void k_fixed_lines(const G2J* gg /*normalised*/, FixedLine* lines) {
 // ---- PS verification pipeline -------------------------------------------------------------------------
 // phase 1: scalars m_i (SHA-256 of the attribute strings, or the caller's Fr) and
 //          K = XX + sum_i m_i YY_i from the per-key window tables.
-__global__ void __launch_bounds__(kBlock, PSB_MINB) k_verify_msm(size_t N, int n, int w, const uint8_t* blob, const uint64_t* off,
+__global__ void PSB_PAIR_BOUNDS k_verify_msm(size_t N, int n, int w, const uint8_t* blob, const uint64_t* off,
                                                         const Fr* m_mont, const G2J* XX, const G2A* tbl, G2J* Kout) {
   const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (lane >= N) return;
@@ -229,7 +265,7 @@ __global__ void __launch_bounds__(kBlock, PSB_MINB) k_verify_msm(size_t N, int n
 }
 
 // phase 2: f = ML(sig1, K) * ML(-sig2, gg)  (one multi-Miller loop per lane)
-__global__ void __launch_bounds__(kBlock, PSB_MINB) k_verify_miller(size_t N, const G1J* sig1, const G1J* sig2, const G2J* K,
+__global__ void PSB_PAIR_BOUNDS k_verify_miller(size_t N, const G1J* sig1, const G1J* sig2, const G2J* K,
                                                            const FixedLine* lines, Fp12* fout) {
   const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (lane >= N) return;
@@ -250,7 +286,7 @@ __global__ void __launch_bounds__(kBlock, PSB_MINB) k_verify_miller(size_t N, co
 // phase 3: final exponentiation, verdict = (sig1 != 0) && (f^e == 1), optional GT
 //          reject_zero_sig1: PSVerifier::verify rejects sig1 == 0 (ps-verifier.cc:16-18), el_passo_verify_id does not;
 //          pre (optional): per-lane verdict of an earlier step (the NIZK check) that is ANDed in.
-__global__ void __launch_bounds__(kBlock, PSB_MINB) k_verify_final(size_t N, const G1J* sig1, const Fp12* fin, uint8_t* verdict,
+__global__ void PSB_PAIR_BOUNDS k_verify_final(size_t N, const G1J* sig1, const Fp12* fin, uint8_t* verdict,
                                                           Fp12* gt, const uint8_t* pre, int reject_zero_sig1) {
   const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (lane >= N) return;
@@ -263,7 +299,7 @@ __global__ void __launch_bounds__(kBlock, PSB_MINB) k_verify_final(size_t N, con
 }
 
 // plain pairing e(P, Q) per lane (no fixed argument)
-__global__ void __launch_bounds__(kBlock, PSB_MINB) k_pairing_miller(size_t N, const G1J* P, const G2J* Q, Fp12* fout) {
+__global__ void PSB_PAIR_BOUNDS k_pairing_miller(size_t N, const G1J* P, const G2J* Q, Fp12* fout) {
   const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (lane >= N) return;
   Fp x1, y1, zero;
@@ -275,7 +311,7 @@ __global__ void __launch_bounds__(kBlock, PSB_MINB) k_pairing_miller(size_t N, c
   miller_loop2(f, x1, y1, q, zero, zero, nullptr, false);
   fout[lane] = f;
 }
-__global__ void __launch_bounds__(kBlock, PSB_MINB) k_final_exp(size_t N, const Fp12* fin, Fp12* out) {
+__global__ void PSB_PAIR_BOUNDS k_final_exp(size_t N, const Fp12* fin, Fp12* out) {
   const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (lane >= N) return;
   Fp12 f = fin[lane], e;

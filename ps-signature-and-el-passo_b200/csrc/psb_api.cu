@@ -68,6 +68,14 @@ int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
 #define LAUNCHED() g_launches.fetch_add(1, std::memory_order_relaxed)
 
 inline unsigned nblocks(size_t n, int block = kBlock) { return (unsigned)((n + block - 1) / block); }
+// block size of the pairing-pipeline kernels: one 512-thread block per SM once the batch fills the GPU that way (shared
+// instruction fetches, kernels.cuh), smaller blocks for small batches so that they still spread over all SMs
+int g_sms = 148;   // SMs of device 0 (psb_init)
+inline int pair_block(size_t n) {
+  int b = kPairBlock;
+  while (b > 128 && n < (size_t)g_sms * b) b >>= 1;
+  return b;
+}
 
 int ensure(DevBuf& b, size_t bytes) {
   if (bytes <= b.cap) return PSB_OK;
@@ -190,13 +198,13 @@ int verify_launch(const psb_key* key, int di, size_t N, const G1J* d_sig1, const
     for (auto& e : dv->ev) if (!e) CK(cudaEventCreate(&e));
     CK(cudaEventRecord(dv->ev[0], st));
   }
-  k_verify_msm<<<nblocks(N), kBlock, 0, st>>>(N, (int)key->n, key->w, d_blob, d_off, d_m, kd.g2pts + 1, kd.tblYY, dK);
+  k_verify_msm<<<nblocks(N, pair_block(N)), pair_block(N), 0, st>>>(N, (int)key->n, key->w, d_blob, d_off, d_m, kd.g2pts + 1, kd.tblYY, dK);
   LAUNCHED();
   if (prof) CK(cudaEventRecord(dv->ev[1], st));
-  k_verify_miller<<<nblocks(N), kBlock, 0, st>>>(N, d_sig1, d_sig2, dK, kd.lines, dF);
+  k_verify_miller<<<nblocks(N, pair_block(N)), pair_block(N), 0, st>>>(N, d_sig1, d_sig2, dK, kd.lines, dF);
   LAUNCHED();
   if (prof) CK(cudaEventRecord(dv->ev[2], st));
-  k_verify_final<<<nblocks(N), kBlock, 0, st>>>(N, d_sig1, dF, d_verdict, d_gt, d_pre, 1);
+  k_verify_final<<<nblocks(N, pair_block(N)), pair_block(N), 0, st>>>(N, d_sig1, dF, d_verdict, d_gt, d_pre, 1);
   LAUNCHED();
   if (prof) CK(cudaEventRecord(dv->ev[3], st));
   CK(cudaGetLastError());
@@ -245,6 +253,7 @@ int psb_init(int curve, const int* devices, int ndev) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, o));
     if (prop.major < 10) return fail(PSB_ERR_UNSUPPORTED, "kernels are built for sm_100a only");
+    if (g_devs.empty()) g_sms = prop.multiProcessorCount;
     Dev* d = new Dev();
     d->ordinal = o;
     CK(cudaSetDevice(o));
@@ -488,9 +497,9 @@ int psb_pairing(size_t N, const uint64_t* P, const uint64_t* Q, uint64_t* out) {
     if ((rc = ensure(dv->ws, L * sizeof(Fp12)))) return rc;
     CK(cudaMemcpyAsync(dv->in[0].p, P + b * kG1W, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(dv->in[1].p, Q + b * kG2W, L * sizeof(G2J), cudaMemcpyHostToDevice, st));
-    k_pairing_miller<<<nblocks(L), kBlock, 0, st>>>(L, (const G1J*)dv->in[0].p, (const G2J*)dv->in[1].p, (Fp12*)dv->ws.p);
+    k_pairing_miller<<<nblocks(L, pair_block(L)), pair_block(L), 0, st>>>(L, (const G1J*)dv->in[0].p, (const G2J*)dv->in[1].p, (Fp12*)dv->ws.p);
     LAUNCHED();
-    k_final_exp<<<nblocks(L), kBlock, 0, st>>>(L, (const Fp12*)dv->ws.p, (Fp12*)dv->in[5].p);
+    k_final_exp<<<nblocks(L, pair_block(L)), pair_block(L), 0, st>>>(L, (const Fp12*)dv->ws.p, (Fp12*)dv->in[5].p);
     LAUNCHED();
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out + b * kGtW, dv->in[5].p, L * sizeof(Fp12), cudaMemcpyDeviceToHost, st));
@@ -790,9 +799,9 @@ int psb_verify_id(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* 
     LAUNCHED();
     k_vid_hash<<<nblocks(L), kBlock, 0, st>>>(L, dk, dphi, dE1, dE2, dVk, dV, with_id, dc, dad - a0, dadoff, dok);
     LAUNCHED();
-    k_verify_miller<<<nblocks(L), kBlock, 0, st>>>(L, dS1, dS2, dK, kd.lines, dF);
+    k_verify_miller<<<nblocks(L, pair_block(L)), pair_block(L), 0, st>>>(L, dS1, dS2, dK, kd.lines, dF);
     LAUNCHED();
-    k_verify_final<<<nblocks(L), kBlock, 0, st>>>(L, dS1, dF, dver, nullptr, dok, 0);
+    k_verify_final<<<nblocks(L, pair_block(L)), pair_block(L), 0, st>>>(L, dS1, dF, dver, nullptr, dok, 0);
     LAUNCHED();
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(verdict + b, dver, L, cudaMemcpyDeviceToHost, st));

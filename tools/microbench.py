@@ -16,7 +16,8 @@ pkg.init([0])
 SM = 148
 res = {"mad": [], "field": []}
 for kind, name, per_iter in [(6, "imad32 (mul.lo+add)", 16), (4, "mad.lo.cc+madc.hi (MAC32)", 8), (5, "mad.wide.u32 (MAC32)", 8),
-                             (7, "carry-chained IMAD.WIDE.U32.X rows (CIOS form, MAC32)", 36)]:
+                             (7, "carry-chained IMAD.WIDE.U32.X rows (CIOS form, MAC32)", 36),
+                             (8, "fma.rz.f64 (DFMA)", 8), (9, "mad.wide.u32 rows of 13 distinct limbs (radix-2^30 form, MAC)", 13)]:
     for bps, thr in [(1, 256), (2, 256), (4, 256), (8, 256), (4, 128), (1, 128)]:
         iters = 20000
         ms = pkg.microbench(kind, SM * bps, thr, iters)
