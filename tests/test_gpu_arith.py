@@ -153,3 +153,36 @@ def test_glv_gls_scalar_edges(gpu_pkg, ref):
     Q = ref.g2_op(ref.G_DBL, np.repeat(gg.reshape(1, -1), len(ks), axis=0))
     assert np.array_equal(ref.g1_serialize(gpu_pkg.test_op(43, P, k)), ref.g1_serialize(ref.g1_mul(P, k)))
     assert np.array_equal(ref.g2_serialize(gpu_pkg.test_op(53, Q, k)), ref.g2_serialize(ref.g2_mul(Q, k)))
+
+
+def test_fp_inv_divsteps_edges_gpu(gpu_pkg, ref):
+    """Bernstein-Yang Fp inversion (csrc/modinv.cuh) on the device: raw limb patterns 1, p-1, powers of two, p - 2^k,
+    random -- against mcl's Fp::inv; inv(0) = 0."""
+    from tests.conftest import FIELD_P, FP_BYTES
+    P, bits = FIELD_P, FIELD_P.bit_length()
+    rng = np.random.default_rng(11)
+    raw = [0, 1, 2, P - 1, P - 2, (P - 1) // 2, (1 << (bits - 1)) - 1, 1 << (bits - 1)]
+    raw += [1 << k for k in range(1, bits - 1, 13)] + [P - (1 << k) for k in range(1, bits - 1, 17)]
+    raw += [int.from_bytes(rng.bytes(FP_BYTES), "little") % P for _ in range(200)]
+    a = np.frombuffer(b"".join(v.to_bytes(FP_BYTES, "little") for v in raw), dtype=np.uint64).reshape(len(raw), -1).copy()
+    got = gpu_pkg.test_op(5, a)
+    assert not got[0].any()
+    assert np.array_equal(got[1:], ref.fp_op(5, a[1:]))
+
+
+def test_final_exp_compressed_pow_z_mixed_warp(gpu_pkg, ref):
+    """finalExp with pow_z on compressed squarings: lanes whose cyclotomic image is 1 (the value 1, elements of Fp2 /
+    Fp6: zero denominators -> the whole warp takes the Granger-Scott fallback) interleaved with generic lanes in the
+    same warps, plus warps with no such lane -- GT bytes against mcl's finalExp on every lane."""
+    from tests.conftest import rand_fp_raw
+    rng = np.random.default_rng(13)
+    n = 96                                     # three warps; degenerate lanes only in the first
+    a = rand_fp_raw(ref, rng, n, 12)
+    fp = a.shape[1] // 12
+    one = ref.fp_from_ints([1]).reshape(-1)
+    a[3] = 0; a[3, :fp] = one
+    a[7, 2 * fp:] = 0
+    a[20, 6 * fp:] = 0
+    want = ref.final_exp(a)
+    assert np.array_equal(gpu_pkg.test_op(61, a), want)
+    assert np.array_equal(want[3], a[3]) and np.array_equal(want[7], a[3]) and np.array_equal(want[20], a[3])
