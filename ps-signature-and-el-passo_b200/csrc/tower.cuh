@@ -219,17 +219,16 @@ PSB_HD PSB_NOINL void fp2_3a2b(Fp2& r, const Fp2& a, const Fp2& b, bool minus) {
     fp_put(*fp2_comp(r, k), u);
   }
 }
-// r = b + xi a (minus = false) or b - xi a;   xi a = (a.a - a.b) + (a.a + a.b) i
-PSB_HD PSB_NOINL void fp2_xi_addsub(Fp2& r, const Fp2& a, const Fp2& b, bool minus) {
+// r = b + xi a;   xi a = (a.a - a.b) + (a.a + a.b) i     (one variant only: instruction-cache budget)
+PSB_HD PSB_NOINL void fp2_xi_add(Fp2& r, const Fp2& a, const Fp2& b) {
   Fp x, y, w0, w1;
   fp_get(x, a.a); fp_get(y, a.b);
   fp_sub_rr(w0, x, y);
   fp_add_rr(w1, x, y);
   fp_get(x, b.a); fp_get(y, b.b);
-  if (minus) { fp_sub_rr(x, x, w0); fp_sub_rr(y, y, w1); } else { fp_add_rr(x, x, w0); fp_add_rr(y, y, w1); }
+  fp_add_rr(x, x, w0); fp_add_rr(y, y, w1);
   fp_put(r.a, x); fp_put(r.b, y);
 }
-PSB_HD PSB_INL void fp2_xi_add(Fp2& r, const Fp2& a, const Fp2& b) { fp2_xi_addsub(r, a, b, false); }   // xi a + b
 
 // x^-1 = conj(x) / (a^2 + b^2)   (fp_tower.hpp:597-611)
 PSB_HD PSB_NOINL void fp2_inv(Fp2& r, const Fp2& x) {
@@ -351,8 +350,8 @@ PSB_HD PSB_NOINL void fp12_sqr(Fp12& z, const Fp12& x) {
   fp6_mul(t2, x.a, x.b);   // ab
   fp6_mul(t0, t0, t1);     // (a+b)(a+vb) = a^2 + v b^2 + ab + v ab
   // z.a = t0 - t2 - v t2
-  fp2_sub(t0.a, t0.a, t2.a);
-  fp2_xi_addsub(z.a.a, t2.c, t0.a, true);
+  fp2_mul_xi(t1.a, t2.c);                 // (t1 is dead here)
+  fp2_sub2(z.a.a, t0.a, t2.a, t1.a);
   fp2_sub2(z.a.b, t0.b, t2.b, t2.a);
   fp2_sub2(z.a.c, t0.c, t2.c, t2.b);
   fp6_dbl(z.b, t2);
