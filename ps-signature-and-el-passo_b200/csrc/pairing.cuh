@@ -287,7 +287,7 @@ PSB_HD PSB_NOINL void pow_z(Fp12& y, const Fp12& x) {
   pow_z_gs(y, x);
 #else
   CycC keep[kZSetBits];
-  Fp2 pre[kZSetBits];
+  Fp2 pre[kZSetBits], den[kZSetBits];
   {
     CycC c;
     c.g2 = x.b.a; c.g3 = x.a.c; c.g4 = x.a.b; c.g5 = x.b.c;
@@ -297,30 +297,36 @@ PSB_HD PSB_NOINL void pow_z(Fp12& y, const Fp12& x) {
       if (i == PSB_Z_NBITS || z_bit(i)) keep[k++] = c;
     }
   }
-  // prefix products of the denominators 4 g2
+  // prefix products of the denominators 4 g2.  x = 1 (a lane whose Miller value lies in a proper subfield, e.g. a
+  // credential with sigma = 0) compresses to (0, 0, 0, 0): there the denominator is replaced by 1 -- the numerator is 0,
+  // so g1 = 0 and g0 = 1 come out right with no other code path (a tampered lane must not slow down its warp).
+  // g2 = 0 on any OTHER element (probability ~2^-380) takes the Granger-Scott path.
+  bool rare = false;
   for (int k = 0; k < kZSetBits; k++) {
-    Fp2 d;
-    fp2_dbl(d, keep[k].g2); fp2_dbl(d, d);
+    Fp2 d, one;
+    fp2_set_one(one);
+    fp2_dbl(d, keep[k].g2); fp2_dbl(d, d);      // (no call under a lane-dependent branch: see below)
+    const bool z2 = fp2_is_zero(keep[k].g2);
+    rare = rare || (z2 && !(fp2_is_zero(keep[k].g3) && fp2_is_zero(keep[k].g4) && fp2_is_zero(keep[k].g5)));
+    fp2_cmov(d, one, z2);
+    den[k] = d;
     if (k == 0) pre[0] = d; else fp2_mul(pre[k], pre[k - 1], d);
   }
-  bool degenerate = fp2_is_zero(pre[kZSetBits - 1]);
 #ifdef __CUDA_ARCH__
   // Both paths give the same field element, so the whole warp takes the fallback when any lane needs it: the call
   // stays warp-uniform.  (A divergent call here let the callee's use of uniform registers clobber stack addresses the
   // other lanes still held in uniform registers -- observed as an invalid local read on the BN254 build.)
-  degenerate = __any_sync(__activemask(), degenerate);
+  rare = __any_sync(__activemask(), rare);
 #endif
-  if (degenerate) { pow_z_gs(y, x); return; }
+  if (rare) { pow_z_gs(y, x); return; }
   Fp2 inv;
   fp2_inv(inv, pre[kZSetBits - 1]);
   Fp12 acc, t;
   for (int k = kZSetBits - 1; k >= 0; k--) {
     Fp2 dinv, num, g1;
     if (k > 0) {
-      Fp2 d;
       fp2_mul(dinv, inv, pre[k - 1]);            // 1 / den_k
-      fp2_dbl(d, keep[k].g2); fp2_dbl(d, d);
-      fp2_mul(inv, inv, d);                      // 1 / (den_0 ... den_{k-1})
+      fp2_mul(inv, inv, den[k]);                 // 1 / (den_0 ... den_{k-1})
     } else {
       dinv = inv;
     }
