@@ -163,6 +163,7 @@ PSB_HD PSB_NOINL void miller_loop2(Fp12& f, const Fp& x1, const Fp& y1, const G2
   fp12_set_one(f);
   Fp2 c0, c2, c3;
   int li = 0;
+  PSB_ROLL
   for (int i = PSB_ML_NBITS - 1; i >= 0; i--) {
     if (i != PSB_ML_NBITS - 1) fp12_sqr(f, f);
     if (use1) {
@@ -268,6 +269,7 @@ PSB_HD PSB_NOINL void precompute_fixed_lines(FixedLine* out, const G2A& Q) {
 // y = x^z (z < 0): x^|z| by square-and-multiply with cyclotomic squarings, then conjugate (mcl pow_z, bn.hpp:1150-1176)
 PSB_HD PSB_NOINL void pow_z_gs(Fp12& y, const Fp12& x) {
   Fp12 acc = x;
+  PSB_ROLL
   for (int i = PSB_Z_NBITS - 1; i >= 0; i--) {
     fp12_cyclo_sqr(acc, acc);
     if (z_bit(i)) fp12_mul(acc, acc, x);
@@ -287,11 +289,12 @@ PSB_HD PSB_NOINL void pow_z(Fp12& y, const Fp12& x) {
   pow_z_gs(y, x);
 #else
   CycC keep[kZSetBits];
-  Fp2 pre[kZSetBits], den[kZSetBits];
+  Fp2 pre[kZSetBits];
   {
     CycC c;
     c.g2 = x.b.a; c.g3 = x.a.c; c.g4 = x.a.b; c.g5 = x.b.c;
     int k = 0;
+    PSB_ROLL   // (left to itself the compiler unrolls all 63 trips: 40 KB of straight-line code through the instruction caches)
     for (int i = 1; i <= PSB_Z_NBITS; i++) {
       cyclo_csqr(c, c);
       if (i == PSB_Z_NBITS || z_bit(i)) keep[k++] = c;
@@ -302,6 +305,7 @@ PSB_HD PSB_NOINL void pow_z(Fp12& y, const Fp12& x) {
   // so g1 = 0 and g0 = 1 come out right with no other code path (a tampered lane must not slow down its warp).
   // g2 = 0 on any OTHER element (probability ~2^-380) takes the Granger-Scott path.
   bool rare = false;
+  PSB_ROLL
   for (int k = 0; k < kZSetBits; k++) {
     Fp2 d, one;
     fp2_set_one(one);
@@ -309,7 +313,6 @@ PSB_HD PSB_NOINL void pow_z(Fp12& y, const Fp12& x) {
     const bool z2 = fp2_is_zero(keep[k].g2);
     rare = rare || (z2 && !(fp2_is_zero(keep[k].g3) && fp2_is_zero(keep[k].g4) && fp2_is_zero(keep[k].g5)));
     fp2_cmov(d, one, z2);
-    den[k] = d;
     if (k == 0) pre[0] = d; else fp2_mul(pre[k], pre[k - 1], d);
   }
 #ifdef __CUDA_ARCH__
@@ -322,11 +325,16 @@ PSB_HD PSB_NOINL void pow_z(Fp12& y, const Fp12& x) {
   Fp2 inv;
   fp2_inv(inv, pre[kZSetBits - 1]);
   Fp12 acc, t;
+  PSB_ROLL
   for (int k = kZSetBits - 1; k >= 0; k--) {
     Fp2 dinv, num, g1;
     if (k > 0) {
+      Fp2 d, one;
       fp2_mul(dinv, inv, pre[k - 1]);            // 1 / den_k
-      fp2_mul(inv, inv, den[k]);                 // 1 / (den_0 ... den_{k-1})
+      fp2_set_one(one);
+      fp2_dbl(d, keep[k].g2); fp2_dbl(d, d);
+      fp2_cmov(d, one, fp2_is_zero(keep[k].g2));
+      fp2_mul(inv, inv, d);                      // 1 / (den_0 ... den_{k-1})
     } else {
       dinv = inv;
     }

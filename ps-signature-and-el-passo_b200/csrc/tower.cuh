@@ -430,6 +430,7 @@ PSB_HD PSB_INL Fp2* fp12_coeff(Fp12& x, int k) {  // k-th power of w -> slot
 PSB_HD PSB_NOINL void fp12_frobenius(Fp12& r, const Fp12& x, int j) {
   const uint32_t* tbl = (j == 1) ? PSB_K(FROB_G1) : (j == 2) ? PSB_K(FROB_G2) : PSB_K(FROB_G3);
   Fp12 in = x;
+  PSB_ROLL
   for (int k = 0; k < 6; k++) {
     Fp2 c = *fp12_coeff(in, k);
     if (j & 1) fp_neg(c.b, c.b);
