@@ -30,6 +30,12 @@ constexpr int kBlock = PSB_BLOCK;
 #endif
 constexpr int kPairBlock = PSB_PAIR_BLOCK;
 #define PSB_PAIR_BOUNDS __launch_bounds__(kPairBlock, 512 / kPairBlock)
+// protocol kernels (EL PASSO NIZK steps, issuance, prover side): 128-thread blocks
+#ifndef PSB_PROTO_MINB
+#define PSB_PROTO_BOUNDS __launch_bounds__(kBlock)
+#else
+#define PSB_PROTO_BOUNDS __launch_bounds__(kBlock, PSB_PROTO_MINB)
+#endif
 
 // ---- parity probe ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_test_op(int op, size_t n, int s0, int s1, int s2, int s3,
@@ -322,7 +328,7 @@ __global__ void PSB_PAIR_BOUNDS k_final_exp(size_t N, const Fp12* fin, Fp12* out
 
 // ---- PSRequester::randomize_credential (src/ps-requester.cc:139-148) -----------------------------------
 // out = (t sig1, t sig2) normalised; t host-supplied (Fr Montgomery)
-__global__ void __launch_bounds__(kBlock) k_randomize(size_t N, const G1J* sig1, const G1J* sig2, const Fr* t,
+__global__ void PSB_PROTO_BOUNDS k_randomize(size_t N, const G1J* sig1, const G1J* sig2, const Fr* t,
                                                        G1J* out1, G1J* out2, uint8_t* ser) {
   const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (lane >= N) return;
@@ -342,7 +348,7 @@ __global__ void __launch_bounds__(kBlock) k_randomize(size_t N, const G1J* sig1,
 }
 
 // out[j] = k[j] * P[j or 0], normalised (generic batched G1::mul, used to synthesise workloads)
-__global__ void __launch_bounds__(kBlock) k_g1_mul(size_t N, const G1J* P, int p_stride, const Fr* k, G1J* out) {
+__global__ void PSB_PROTO_BOUNDS k_g1_mul(size_t N, const G1J* P, int p_stride, const Fr* k, G1J* out) {
   const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (lane >= N) return;
   Fr kk, kn;
@@ -376,7 +382,7 @@ __global__ void __launch_bounds__(kBlock) k_g2_deserialize(size_t N, const uint8
 }
 
 // ---- PSSigner::el_passo_provide_id (src/ps-signer.cc:63-146) -------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_provide_id(size_t N, int n, int w, const G1A* tblG1, const G1J* g1pts,
+__global__ void PSB_PROTO_BOUNDS k_provide_id(size_t N, int n, int w, const G1A* tblG1, const G1J* g1pts,
                                                         const G1J* A, const Fr* c, const Fr* rs, int per,
                                                         const uint8_t* blob, const uint64_t* off, const uint8_t* ad_blob,
                                                         const uint64_t* ad_off, const Fr* u, uint8_t* verdict, G1J* sig1,
@@ -398,7 +404,7 @@ __global__ void __launch_bounds__(kBlock) k_provide_id(size_t N, int n, int w, c
 
 // ---- PSVerifier::el_passo_verify_id (src/ps-verifier.cc:37-212): NIZK steps; the pairing check reuses
 //      k_verify_miller / k_verify_final with K from step 1 ------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_vid_g2(size_t N, int n, int w, const G2A* tblYY, const G2A* tblAux, const G2J* k,
+__global__ void PSB_PROTO_BOUNDS k_vid_g2(size_t N, int n, int w, const G2A* tblYY, const G2A* tblAux, const G2J* k,
                                                     const Fr* c, const Fr* rs, int per, int with_id, const uint8_t* blob,
                                                     const uint64_t* off, G2J* Vk, G2J* K, uint8_t* ok) {
   const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -411,7 +417,7 @@ __global__ void __launch_bounds__(kBlock) k_vid_g2(size_t N, int n, int w, const
   K[lane] = kk;
   ok[lane] = r ? 1 : 0;
 }
-__global__ void __launch_bounds__(kBlock) k_vid_g1(size_t N, int wb, const G1A* tblB, const G1J* phi, const G1J* E1,
+__global__ void PSB_PROTO_BOUNDS k_vid_g1(size_t N, int wb, const G1A* tblB, const G1J* phi, const G1J* E1,
                                                     const G1J* E2, const Fr* c, const Fr* rs, int per, int with_id,
                                                     G1J* V /*3 per lane*/) {
   const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -422,7 +428,7 @@ __global__ void __launch_bounds__(kBlock) k_vid_g1(size_t N, int wb, const G1A* 
                     rs + lane * per, per, with_id, a, b, d);
   V[3 * lane] = a; V[3 * lane + 1] = b; V[3 * lane + 2] = d;
 }
-__global__ void __launch_bounds__(kBlock) k_vid_hash(size_t N, const G2J* k, const G1J* phi, const G1J* E1, const G1J* E2,
+__global__ void PSB_PROTO_BOUNDS k_vid_hash(size_t N, const G2J* k, const G1J* phi, const G1J* E1, const G1J* E2,
                                                       const G2J* Vk, const G1J* V, int with_id, const Fr* c,
                                                       const uint8_t* ad_blob, const uint64_t* ad_off, uint8_t* ok) {
   const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -436,7 +442,7 @@ __global__ void __launch_bounds__(kBlock) k_vid_hash(size_t N, const G2J* k, con
 
 // ---- prover side: PSRequester::el_passo_request_id / unblind_credential / el_passo_prove_id ----
 // hide: n flags shared by the batch; rnd: `per` host-supplied scalars per lane in the reference's draw order (prover.cuh)
-__global__ void __launch_bounds__(kBlock) k_request_id(size_t N, int n, int w, const G1A* tblG1, const uint8_t* hide, int h,
+__global__ void PSB_PROTO_BOUNDS k_request_id(size_t N, int n, int w, const G1A* tblG1, const uint8_t* hide, int h,
                                                         const uint8_t* blob, const uint64_t* off, const uint8_t* ad_blob,
                                                         const uint64_t* ad_off, const Fr* rnd, G1J* A, Fr* c, Fr* rs) {
   const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -448,14 +454,14 @@ __global__ void __launch_bounds__(kBlock) k_request_id(size_t N, int n, int w, c
   A[lane] = a;
   c[lane] = cc;
 }
-__global__ void __launch_bounds__(kBlock) k_unblind(size_t N, const G1J* sig1, const G1J* sig2, const Fr* t1, G1J* out2) {
+__global__ void PSB_PROTO_BOUNDS k_unblind(size_t N, const G1J* sig1, const G1J* sig2, const Fr* t1, G1J* out2) {
   const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (lane >= N) return;
   G1J r;
   unblind_lane(r, sig1[lane], sig2[lane], t1 + lane);
   out2[lane] = r;
 }
-__global__ void __launch_bounds__(kBlock) k_pid_g2(size_t N, int n, int w, const G2A* tblYY, const G2A* tblAux, const G2J* XX,
+__global__ void PSB_PROTO_BOUNDS k_pid_g2(size_t N, int n, int w, const G2A* tblYY, const G2A* tblAux, const G2J* XX,
                                                     const uint8_t* hide, int h, int with_id, const uint8_t* blob,
                                                     const uint64_t* off, const Fr* rnd, G2J* k, G2J* Vk) {
   const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -466,7 +472,7 @@ __global__ void __launch_bounds__(kBlock) k_pid_g2(size_t N, int n, int w, const
   k[lane] = a;
   Vk[lane] = b;
 }
-__global__ void __launch_bounds__(kBlock) k_pid_g1(size_t N, int n, int wb, const G1A* tblB, const G1J* sig1, const G1J* sig2,
+__global__ void PSB_PROTO_BOUNDS k_pid_g1(size_t N, int n, int wb, const G1A* tblB, const G1J* sig1, const G1J* sig2,
                                                     const uint8_t* blob, const uint64_t* off, const Fr* rnd, int h, int with_id,
                                                     G1J* o_sig1, G1J* o_sig2, G1J* W /*6 per lane*/) {
   const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -478,7 +484,7 @@ __global__ void __launch_bounds__(kBlock) k_pid_g1(size_t N, int n, int wb, cons
   o_sig2[lane] = s2;
   for (int i = 0; i < 6; i++) W[6 * lane + i] = w6[i];
 }
-__global__ void __launch_bounds__(kBlock) k_pid_hash(size_t N, int n, const uint8_t* hide, int h, int with_id, const uint8_t* blob,
+__global__ void PSB_PROTO_BOUNDS k_pid_hash(size_t N, int n, const uint8_t* hide, int h, int with_id, const uint8_t* blob,
                                                       const uint64_t* off, const uint8_t* ad_blob, const uint64_t* ad_off,
                                                       const Fr* rnd, G2J* k, const G2J* Vk, const G1J* W, G1J* phi, G1J* E1,
                                                       G1J* E2, Fr* c, Fr* rs) {

@@ -118,3 +118,32 @@ def test_randomize_verify_round_trip_large(gpu_pkg, ref):
     assert np.array_equal(again, exp)
     assert not r1[5].any() and not r2[5].any()
     pk.close()
+
+
+def test_full_size_2p20_properties(gpu_pkg, ref):
+    """BASELINE.json configs[1] at its full size -- 2^20 signatures, 5 attributes -- through size-independent properties
+    (the oracle needs 73 core-minutes for this batch): (i) the verdict bitmap equals the construction (honest lanes
+    accept, the 1024 tampered lanes -- swapped, sigma1 = 0, attribute changed -- reject); (ii) idempotence: a second
+    pass gives the same bitmap; (iii) verify(randomize(sigma, t)) == verify(sigma) lane by lane; (iv) a uniformly drawn
+    sample of 512 lanes + every tampered lane of the first 2^16 agrees with the reference's PSVerifier::verify."""
+    import bench
+    lanes = 1 << 20
+    key = bench.load_key(5)
+    sig1, sig2, blob, off, expected, lane_attrs = bench.make_batch(gpu_pkg, key, lanes, 0)
+    pk = gpu_pkg.PSPubKey(key["g"], key["gg"], key["XX"], key["Y"], key["YY"], window_bits=16)
+    ver = gpu_pkg.PSVerifier(pk)
+    v1 = ver.verify(sig1, sig2, (blob, off))
+    assert np.array_equal(v1, expected) and int(v1.sum()) == lanes - lanes // 1024
+    assert np.array_equal(ver.verify(sig1, sig2, (blob, off)), v1)
+    rng = np.random.default_rng(5)
+    t = np.frombuffer(rng.bytes(32 * lanes), dtype=np.uint64).reshape(lanes, 4).copy()
+    t[:, 3] &= np.uint64(0x0FFFFFFFFFFFFFFF)
+    t[:, 0] |= np.uint64(1)
+    r1, r2 = gpu_pkg.PSRequester.randomize_credential(sig1, sig2, t)
+    assert np.array_equal(ver.verify(r1, r2, (blob, off)), v1)
+    pick = np.unique(np.concatenate([rng.integers(0, lanes, 512), np.arange(1023, 1 << 16, 1024)]))
+    km = ref.KeyMaterial(5, seed_=1)             # the key of tests/golden/keys.json (bench.load_key)
+    assert np.array_equal(km.XX.reshape(-1), key["XX"].reshape(-1))
+    want = ref.ps_verify(km, sig1[pick].copy(), sig2[pick].copy(), [lane_attrs[j] for j in pick], nthreads=ref.hw_threads())
+    assert np.array_equal(v1[pick], want)
+    pk.close()
