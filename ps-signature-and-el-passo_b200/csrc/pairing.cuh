@@ -281,8 +281,9 @@ PSB_HD PSB_NOINL void pow_z_gs(Fp12& y, const Fp12& x) {
 // PSB_Z_NBITS compressed squarings (6 Fp2 squarings each instead of 9) passes through every x^(2^i); the compressed
 // values at the set bits are kept, their (g0, g1) coordinates are rebuilt with ONE shared inversion (Montgomery's trick
 // over the denominators 4 g2), and the full elements are multiplied together.  x must lie in the cyclotomic subgroup.
-// A zero denominator (x = 1, e.g. a lane whose Miller value is trivial; otherwise probability ~2^-760) falls back to
-// pow_z_gs, so the result is the same field element on every input.
+// x = 1 (the only element of the odd-order cyclotomic subgroup with a power-of-two power equal to 1) is handled in line
+// with unit denominators; a zero g2 on any other element (probability ~2^-380) falls back to pow_z_gs, so the result
+// is the same field element on every input.
 constexpr int kZSetBits = PSB_Z_SETBITS_HI;          // set bits of |z| above bit 0, including the leading one
 PSB_HD PSB_NOINL void pow_z(Fp12& y, const Fp12& x) {
 #ifdef PSB_POWZ_GS
