@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from tests import workload
-from tests.conftest import FPW
+from tests.conftest import FPW, bls_only
 
 pytestmark = pytest.mark.gpu
 
@@ -120,6 +120,7 @@ def test_randomize_verify_round_trip_large(gpu_pkg, ref):
     pk.close()
 
 
+@bls_only
 def test_full_size_2p20_properties(gpu_pkg, ref):
     """BASELINE.json configs[1] at its full size -- 2^20 signatures, 5 attributes -- through size-independent properties
     (the oracle needs 73 core-minutes for this batch): (i) the verdict bitmap equals the construction (honest lanes
