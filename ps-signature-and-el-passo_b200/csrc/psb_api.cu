@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <array>
+#include <algorithm>
 #include <atomic>
 #include <memory>
 #include <cstdio>
@@ -40,6 +41,8 @@ struct DevBuf {
 struct Dev {
   int ordinal = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy = nullptr;           // host->device staging of the NEXT chunk while the current one computes (psb_verify)
+  cudaEvent_t ev_in[8] = {};             // "inputs of chunk c are on the device"
   DevBuf in[8];   // staging for host-pointer entry points
   DevBuf ws;      // phase hand-over scratch
   DevBuf arena;   // staging + scratch of the EL PASSO entry points (carved by Arena)
@@ -258,6 +261,8 @@ int psb_init(int curve, const int* devices, int ndev) {
     d->ordinal = o;
     CK(cudaSetDevice(o));
     CK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&d->copy, cudaStreamNonBlocking));
+    for (auto& e : d->ev_in) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     // thread-local state (Fp12 temporaries, window tables of points) lives in local memory:
     // prefer L1 over shared memory, and give deep call chains enough stack
     cudaDeviceSetLimit(cudaLimitStackSize, 32 * 1024);
@@ -274,6 +279,8 @@ void psb_shutdown(void) {
     if (d->ws.p) cudaFree(d->ws.p);
     if (d->arena.p) cudaFree(d->arena.p);
     for (auto& e : d->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : d->ev_in) if (e) cudaEventDestroy(e);
+    if (d->copy) cudaStreamDestroy(d->copy);
     if (d->stream) cudaStreamDestroy(d->stream);
     delete d;
   }
@@ -374,33 +381,57 @@ int psb_verify(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* sig
     CK(cudaSetDevice(dv->ordinal));
     cudaStream_t st = dv->stream;
     int rc;
+    // Chunks of whole waves: the inputs of chunk c+1 travel on the copy stream while chunk c runs its three phase
+    // kernels on the compute stream (one event per chunk); small batches are one chunk.
+    const size_t wave = (size_t)g_sms * kPairBlock;
+    size_t chunk = 4 * wave;
+    if (L < 2 * chunk) chunk = L;
+    const size_t nchunks = (L + chunk - 1) / chunk;
+    if (nchunks > 8) chunk = (((L + 7) / 8 + wave - 1) / wave) * wave;
     if ((rc = ensure(dv->in[0], L * sizeof(G1J)))) return rc;
     if ((rc = ensure(dv->in[1], L * sizeof(G1J)))) return rc;
     if ((rc = ensure(dv->in[4], L + 16))) return rc;
-    if ((rc = ensure(dv->ws, psb_verify_ws_bytes(key, L)))) return rc;
+    if ((rc = ensure(dv->ws, psb_verify_ws_bytes(key, chunk)))) return rc;
     if (gt && (rc = ensure(dv->in[5], L * sizeof(Fp12)))) return rc;
-    CK(cudaMemcpyAsync(dv->in[0].p, sig1 + b * kG1W, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(dv->in[1].p, sig2 + b * kG1W, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
     const uint8_t* d_blob = nullptr; const uint64_t* d_off = nullptr; const Fr* d_m = nullptr;
+    uint64_t o0 = 0;
     if (attr_blob) {
-      const uint64_t o0 = attr_off[b * n], o1 = attr_off[e * n];
+      o0 = attr_off[b * n];
+      const uint64_t o1 = attr_off[e * n];
       if ((rc = ensure(dv->in[2], (size_t)(o1 - o0) + 16))) return rc;
       if ((rc = ensure(dv->in[3], (L * n + 1) * sizeof(uint64_t)))) return rc;
-      if (o1 > o0) CK(cudaMemcpyAsync(dv->in[2].p, attr_blob + o0, (size_t)(o1 - o0), cudaMemcpyHostToDevice, st));
-      CK(cudaMemcpyAsync(dv->in[3].p, attr_off + b * n, (L * n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
       d_blob = (const uint8_t*)dv->in[2].p - o0;  // offsets stay absolute
       d_off = (const uint64_t*)dv->in[3].p;
     } else if (n) {
       if ((rc = ensure(dv->in[2], L * n * sizeof(Fr)))) return rc;
-      CK(cudaMemcpyAsync(dv->in[2].p, m + b * n * 4, L * n * sizeof(Fr), cudaMemcpyHostToDevice, st));
       d_m = (const Fr*)dv->in[2].p;
     }
-    rc = verify_launch(key, di, L, (const G1J*)dv->in[0].p, (const G1J*)dv->in[1].p, d_blob, d_off, d_m,
-                       (uint8_t*)dv->in[4].p, gt ? (Fp12*)dv->in[5].p : nullptr, dv->ws.p, st);
-    if (rc) return rc;
+    G1J* dS1 = (G1J*)dv->in[0].p; G1J* dS2 = (G1J*)dv->in[1].p;
+    int c = 0;
+    for (size_t cb = 0; cb < L; cb += chunk, c++) {
+      const size_t cl = std::min(chunk, L - cb);
+      cudaStream_t cs = (c == 0) ? st : dv->copy;          // the first chunk has nothing to overlap with
+      CK(cudaMemcpyAsync(dS1 + cb, sig1 + (b + cb) * kG1W, cl * sizeof(G1J), cudaMemcpyHostToDevice, cs));
+      CK(cudaMemcpyAsync(dS2 + cb, sig2 + (b + cb) * kG1W, cl * sizeof(G1J), cudaMemcpyHostToDevice, cs));
+      if (attr_blob) {
+        const uint64_t c0 = attr_off[(b + cb) * n], c1 = attr_off[(b + cb + cl) * n];
+        if (c1 > c0) CK(cudaMemcpyAsync((uint8_t*)dv->in[2].p + (c0 - o0), attr_blob + c0, (size_t)(c1 - c0), cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpyAsync((uint64_t*)dv->in[3].p + cb * n, attr_off + (b + cb) * n, (cl * n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, cs));
+      } else if (n) {
+        CK(cudaMemcpyAsync((Fr*)dv->in[2].p + cb * n, m + (b + cb) * n * 4, cl * n * sizeof(Fr), cudaMemcpyHostToDevice, cs));
+      }
+      if (c > 0) {
+        CK(cudaEventRecord(dv->ev_in[c & 7], dv->copy));
+        CK(cudaStreamWaitEvent(st, dv->ev_in[c & 7], 0));
+      }
+      rc = verify_launch(key, di, cl, dS1 + cb, dS2 + cb, d_blob, d_off ? d_off + cb * n : nullptr, d_m ? d_m + cb * n : nullptr,
+                         (uint8_t*)dv->in[4].p + cb, gt ? (Fp12*)dv->in[5].p + cb : nullptr, dv->ws.p, st);
+      if (rc) return rc;
+    }
     CK(cudaMemcpyAsync(verdict + b, dv->in[4].p, L, cudaMemcpyDeviceToHost, st));
     if (gt) CK(cudaMemcpyAsync(gt + b * kGtW, dv->in[5].p, L * sizeof(Fp12), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    CK(cudaStreamSynchronize(dv->copy));
     return PSB_OK;
   });
 }
