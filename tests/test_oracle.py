@@ -181,3 +181,13 @@ def test_reference_own_tests_build_and_pass():
     assert out.returncode == 0, out.stderr[-2000:]
     assert "failure" not in out.stdout and "failed" not in out.stdout
     assert out.stdout.count("ends without errors") >= 2
+
+
+def test_hard_part_factorisation_identity():
+    """csrc/pairing.cuh computes the hard part of the final exponentiation through (z-1)^2 (z+p) (z^2+p^2-1) + 3
+    (Hayashida-Hayasaka-Teruya); it must be the exponent mcl's expHardPartBLS12 realises, 3 (p^4-p^2+1)/r."""
+    z = -0xD201000000010000
+    r = z ** 4 - z ** 2 + 1
+    p = (z - 1) ** 2 * r // 3 + z
+    assert (3 * (p ** 4 - p ** 2 + 1)) % r == 0
+    assert (z - 1) ** 2 * (z + p) * (z ** 2 + p ** 2 - 1) + 3 == 3 * (p ** 4 - p ** 2 + 1) // r
