@@ -278,13 +278,19 @@ PSB_HD PSB_NOINL void pow_z_gs(Fp12& y, const Fp12& x) {
 }
 
 // The same value through Karabina's compressed squarings: x^|z| = prod over the set bits i of x^(2^i).  ONE chain of
-// PSB_Z_NBITS compressed squarings (6 Fp2 squarings each instead of 9) passes through every x^(2^i); the compressed
-// values at the set bits are kept, their (g0, g1) coordinates are rebuilt with ONE shared inversion (Montgomery's trick
+// PSB_Z_PIVOT compressed squarings (6 Fp2 squarings each instead of 9) passes through every x^(2^i), i <= pivot; the
+// compressed values at the set bits are kept (the bits above the pivot are finished on the full element, see below), their (g0, g1) coordinates are rebuilt with ONE shared inversion (Montgomery's trick
 // over the denominators 4 g2), and the full elements are multiplied together.  x must lie in the cyclotomic subgroup.
 // x = 1 (the only element of the odd-order cyclotomic subgroup with a power-of-two power equal to 1) is handled in line
 // with unit denominators; a zero g2 on any other element (probability ~2^-380) falls back to pow_z_gs, so the result
 // is the same field element on every input.
-constexpr int kZSetBits = PSB_Z_SETBITS_HI;          // set bits of |z| above bit 0, including the leading one
+#ifdef PSB_Z_PIVOT_OVERRIDE   // A/B builds: -DPSB_Z_PIVOT_OVERRIDE=<bit> -DPSB_Z_SETBITS_OVERRIDE=<set bits in [1, bit]>
+#undef PSB_Z_PIVOT
+#undef PSB_Z_SETBITS_HI
+#define PSB_Z_PIVOT PSB_Z_PIVOT_OVERRIDE
+#define PSB_Z_SETBITS_HI PSB_Z_SETBITS_OVERRIDE
+#endif
+constexpr int kZSetBits = PSB_Z_SETBITS_HI;          // set bits of |z| in [1, pivot]: one kept compressed value each
 PSB_HD PSB_NOINL void pow_z(Fp12& y, const Fp12& x) {
 #ifdef PSB_POWZ_GS
   pow_z_gs(y, x);
@@ -296,9 +302,9 @@ PSB_HD PSB_NOINL void pow_z(Fp12& y, const Fp12& x) {
     c.g2 = x.b.a; c.g3 = x.a.c; c.g4 = x.a.b; c.g5 = x.b.c;
     int k = 0;
     PSB_ROLL   // (left to itself the compiler unrolls all 63 trips: 40 KB of straight-line code through the instruction caches)
-    for (int i = 1; i <= PSB_Z_NBITS; i++) {
+    for (int i = 1; i <= PSB_Z_PIVOT; i++) {
       cyclo_csqr(c, c);
-      if (i == PSB_Z_NBITS || z_bit(i)) keep[k++] = c;
+      if (i == PSB_Z_PIVOT || z_bit(i)) keep[k++] = c;
     }
   }
   // prefix products of the denominators 4 g2.  x = 1 (a lane whose Miller value lies in a proper subfield, e.g. a
@@ -343,6 +349,16 @@ PSB_HD PSB_NOINL void pow_z(Fp12& y, const Fp12& x) {
     fp2_mul(g1, num, dinv);
     if (k == kZSetBits - 1) {
       cyclo_decompress_fill(acc, keep[k], g1);
+      // the set bits above the pivot lie within three squarings of each other: x^(2^pivot) raised to |z| >> pivot by
+      // plain cyclotomic squarings costs less than a decompression per bit (BLS12-381: 105 = 1101001b; BN254: 1)
+      if ((PSB_Z_ABS >> PSB_Z_PIVOT) > 1) {
+        t = acc;
+        PSB_ROLL
+        for (int i = PSB_Z_NBITS - PSB_Z_PIVOT - 1; i >= 0; i--) {
+          fp12_cyclo_sqr(acc, acc);
+          if (z_bit(PSB_Z_PIVOT + i)) fp12_mul(acc, acc, t);
+        }
+      }
     } else {
       cyclo_decompress_fill(t, keep[k], g1);
       fp12_mul(acc, acc, t);
