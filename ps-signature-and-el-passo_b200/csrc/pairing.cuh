@@ -351,7 +351,16 @@ PSB_HD PSB_NOINL void pow_z(Fp12& y, const Fp12& x) {
       cyclo_decompress_fill(acc, keep[k], g1);
       // the set bits above the pivot lie within three squarings of each other: x^(2^pivot) raised to |z| >> pivot by
       // plain cyclotomic squarings costs less than a decompression per bit (BLS12-381: 105 = 1101001b; BN254: 1)
-      if ((PSB_Z_ABS >> PSB_Z_PIVOT) > 1) {
+      if ((PSB_Z_ABS >> PSB_Z_PIVOT) == 105) {
+        // 105 = (2^3 - 1)(2^4 - 1), and an inverse is a conjugation in the cyclotomic subgroup:
+        // 7 squarings + 2 products instead of 6 + 3 for the binary chain
+        PSB_ROLL
+        for (int r = 0; r < 2; r++) {
+          fp12_conj(t, acc);
+          for (int i = 0; i < 3 + r; i++) fp12_cyclo_sqr(acc, acc);
+          fp12_mul(acc, acc, t);                  // y^7, then (y^7)^15
+        }
+      } else if ((PSB_Z_ABS >> PSB_Z_PIVOT) > 1) {
         t = acc;
         PSB_ROLL
         for (int i = PSB_Z_NBITS - PSB_Z_PIVOT - 1; i >= 0; i--) {
