@@ -273,8 +273,9 @@ __global__ void PSB_PAIR_BOUNDS k_verify_msm(size_t N, int n, int w, const uint8
 // phase 2: f = ML(sig1, K) * ML(-sig2, gg)  (one multi-Miller loop per lane)
 __global__ void PSB_PAIR_BOUNDS k_verify_miller(size_t N, const G1J* sig1, const G1J* sig2, const G2J* K,
                                                            const FixedLine* lines, Fp12* fout) {
-  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (lane >= N) return;
+  const size_t lane0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = lane0 < N;
+  const size_t lane = live ? lane0 : N - 1;        // as in k_verify_final: no early exit, the block may re-align itself
   Fp x1, y1, x2, y2;
   {
     G1J p = sig1[lane];
@@ -285,8 +286,8 @@ __global__ void PSB_PAIR_BOUNDS k_verify_miller(size_t N, const G1J* sig1, const
   }
   G2J q = K[lane];
   Fp12 f;
-  miller_loop2(f, x1, y1, q, x2, y2, lines, true);
-  fout[lane] = f;
+  miller_loop2(f, x1, y1, q, x2, y2, lines, true, true);
+  if (live) fout[lane] = f;
 }
 
 // phase 3: final exponentiation, verdict = (sig1 != 0) && (f^e == 1), optional GT
@@ -294,10 +295,12 @@ __global__ void PSB_PAIR_BOUNDS k_verify_miller(size_t N, const G1J* sig1, const
 //          pre (optional): per-lane verdict of an earlier step (the NIZK check) that is ANDed in.
 __global__ void PSB_PAIR_BOUNDS k_verify_final(size_t N, const G1J* sig1, const Fp12* fin, uint8_t* verdict,
                                                           Fp12* gt, const uint8_t* pre, int reject_zero_sig1) {
-  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (lane >= N) return;
-  Fp12 f = fin[lane], e;
-  final_exp(e, f);
+  const size_t lane0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = lane0 < N;
+  const size_t lane = live ? lane0 : N - 1;        // surplus threads of the last block shadow the last lane: no early exit,
+  Fp12 f = fin[lane], e;                           // so the block can re-align itself inside final_exp
+  final_exp(e, f, true);
+  if (!live) return;
   const bool s1zero = reject_zero_sig1 && fp_is_zero(sig1[lane].z);
   const bool pre_ok = pre ? pre[lane] != 0 : true;
   verdict[lane] = (pre_ok && !s1zero && fp12_is_one(e)) ? 1 : 0;
@@ -318,11 +321,12 @@ __global__ void PSB_PAIR_BOUNDS k_pairing_miller(size_t N, const G1J* P, const G
   fout[lane] = f;
 }
 __global__ void PSB_PAIR_BOUNDS k_final_exp(size_t N, const Fp12* fin, Fp12* out) {
-  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (lane >= N) return;
+  const size_t lane0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = lane0 < N;
+  const size_t lane = live ? lane0 : N - 1;
   Fp12 f = fin[lane], e;
-  final_exp(e, f);
-  out[lane] = e;
+  final_exp(e, f, true);
+  if (live) out[lane] = e;
 }
 
 

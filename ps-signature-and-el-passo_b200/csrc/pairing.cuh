@@ -148,8 +148,27 @@ PSB_HD PSB_NOINL void g2h_frobenius(G2H& Q) {
 //   lines fall into Fp2 and die in the final exponentiation, like mcl: bls12_test.cpp:288-296).
 //   Q1: G2 Jacobian (any z); q1_zero => that pairing contributes 1 (bn.hpp:1666-1669).
 //   lines2: kMillerSteps precomputed lines of the fixed Q2 (per key); use2 = false skips them.
+// `block_sync` (here and in final_exp): the caller guarantees that EVERY thread of the block is inside this call (no early
+// exit); the block is then re-aligned at a few points of the straight-line schedule so that its warps keep sharing
+// instruction fetches (kernels.cuh, launch shape).  Measured on B200, 2^20 lanes (profiles/r1zb_ab_block_sync.txt).
+#ifndef PSB_FE_SYNC
+#define PSB_FE_SYNC 1
+#endif
+#ifndef PSB_ML_SYNC
+#define PSB_ML_SYNC 0
+#endif
+#if defined(__CUDA_ARCH__) && PSB_FE_SYNC
+#define PSB_FE_BARRIER(on) do { if (on) __syncthreads(); } while (0)
+#else
+#define PSB_FE_BARRIER(on) do { (void)(on); } while (0)
+#endif
+#if defined(__CUDA_ARCH__) && PSB_ML_SYNC
+#define PSB_ML_BARRIER(on) do { if (on) __syncthreads(); } while (0)
+#else
+#define PSB_ML_BARRIER(on) do { (void)(on); } while (0)
+#endif
 PSB_HD PSB_NOINL void miller_loop2(Fp12& f, const Fp& x1, const Fp& y1, const G2J& Q1, const Fp& x2, const Fp& y2,
-                                   const FixedLine* lines2, bool use2) {
+                                   const FixedLine* lines2, bool use2, bool block_sync = false) {
   const bool use1 = !pt_is_zero(Q1);
   const bool scaled2 = use2 && lines2[kMillerSteps].nl.a.v[0] != 0;
   Fp nx1, ny1;
@@ -165,6 +184,7 @@ PSB_HD PSB_NOINL void miller_loop2(Fp12& f, const Fp& x1, const Fp& y1, const G2
   int li = 0;
   PSB_ROLL
   for (int i = PSB_ML_NBITS - 1; i >= 0; i--) {
+    PSB_ML_BARRIER(block_sync);
     if (i != PSB_ML_NBITS - 1) fp12_sqr(f, f);
     if (use1) {
       ml_dbl_step(T, c0, c2, c3, x1, ny1);
@@ -379,7 +399,8 @@ PSB_HD PSB_NOINL void pow_z(Fp12& y, const Fp12& x) {
 }
 
 // y = x^((p^12-1)/r * 3), structured as mcl's finalExp (bn.hpp:1643-1659)
-PSB_HD PSB_NOINL void final_exp(Fp12& y, const Fp12& x) {
+// `block_sync`: see miller_loop2; the block is re-aligned before each pow_z
+PSB_HD PSB_NOINL void final_exp(Fp12& y, const Fp12& x, bool block_sync = false) {
   Fp12 a0, a1, a2, a3, a4, a5, a7, t;
   // easy part: t = x^((p^6-1)(p^2+1))   (mapToCyclotomic, bn.hpp:1494-1502)
   fp12_frobenius(a0, x, 2);
@@ -441,10 +462,16 @@ PSB_HD PSB_NOINL void final_exp(Fp12& y, const Fp12& x) {
   // factorisation of Hayashida, Hayasaka and Teruya (2020):  (z - 1)^2 (z + p) (z^2 + p^2 - 1) + 3   (identity checked in
   // tests/test_oracle.py) -- five pow_z like mcl, but 7 Fp12 products, 1 cyclotomic squaring and 2 Frobenius maps
   // instead of 12, 2 and 3; equal exponents give the same field element, so GT bytes are unchanged.
+  PSB_FE_BARRIER(block_sync);
   pow_z(a0, t); fp12_conj(a1, t); fp12_mul(a0, a0, a1);                 // t^(z-1)
+  PSB_FE_BARRIER(block_sync);
   pow_z(a2, a0); fp12_conj(a1, a0); fp12_mul(a2, a2, a1);               // ^(z-1)
+  PSB_FE_BARRIER(block_sync);
   pow_z(a0, a2); fp12_frobenius(a1, a2, 1); fp12_mul(a0, a0, a1);       // ^(z+p)            =: u
-  pow_z(a2, a0); pow_z(a2, a2);                                         // u^(z^2)
+  PSB_FE_BARRIER(block_sync);
+  pow_z(a2, a0);
+  PSB_FE_BARRIER(block_sync);
+  pow_z(a2, a2);                                                        // u^(z^2)
   fp12_frobenius(a1, a0, 2); fp12_mul(a2, a2, a1);                      // u^(z^2+p^2)
   fp12_conj(a1, a0); fp12_mul(a2, a2, a1);                              // u^(z^2+p^2-1)
   fp12_cyclo_sqr(a1, t); fp12_mul(a1, a1, t);                           // t^3
