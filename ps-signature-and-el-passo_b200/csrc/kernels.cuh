@@ -309,16 +309,17 @@ __global__ void PSB_PAIR_BOUNDS k_verify_final(size_t N, const G1J* sig1, const 
 
 // plain pairing e(P, Q) per lane (no fixed argument)
 __global__ void PSB_PAIR_BOUNDS k_pairing_miller(size_t N, const G1J* P, const G2J* Q, Fp12* fout) {
-  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (lane >= N) return;
+  const size_t lane0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = lane0 < N;
+  const size_t lane = live ? lane0 : N - 1;
   Fp x1, y1, zero;
   fp_set_zero(zero);
   G1J p = P[lane];
   g1_affine_for_pairing(x1, y1, p);
   G2J q = Q[lane];
   Fp12 f;
-  miller_loop2(f, x1, y1, q, zero, zero, nullptr, false);
-  fout[lane] = f;
+  miller_loop2(f, x1, y1, q, zero, zero, nullptr, false, true);
+  if (live) fout[lane] = f;
 }
 __global__ void PSB_PAIR_BOUNDS k_final_exp(size_t N, const Fp12* fin, Fp12* out) {
   const size_t lane0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

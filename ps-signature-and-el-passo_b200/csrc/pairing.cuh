@@ -155,7 +155,19 @@ PSB_HD PSB_NOINL void g2h_frobenius(G2H& Q) {
 #define PSB_FE_SYNC 1
 #endif
 #ifndef PSB_ML_SYNC
-#define PSB_ML_SYNC 0
+#define PSB_ML_SYNC 16     // barrier every PSB_ML_SYNC Miller iterations (0 = never; 1: -3 %, 16: +0.5 %, 32: 0)
+#endif
+#ifndef PSB_POWZ_SYNC
+#define PSB_POWZ_SYNC 0    // barrier every PSB_POWZ_SYNC compressed squarings inside pow_z (0 = never; 4/8/16/32 lose to MID alone)
+#endif
+#ifndef PSB_POWZ_SYNC_TAIL
+#define PSB_POWZ_SYNC_TAIL 0 // barrier before each decompression + product of pow_z
+#endif
+#ifndef PSB_FE_SYNC_EASY
+#define PSB_FE_SYNC_EASY 0   // barrier after the inversion of the easy part
+#endif
+#ifndef PSB_POWZ_SYNC_MID
+#define PSB_POWZ_SYNC_MID 1  // barrier between the squaring chain and the decompressions of pow_z
 #endif
 #if defined(__CUDA_ARCH__) && PSB_FE_SYNC
 #define PSB_FE_BARRIER(on) do { if (on) __syncthreads(); } while (0)
@@ -184,7 +196,9 @@ PSB_HD PSB_NOINL void miller_loop2(Fp12& f, const Fp& x1, const Fp& y1, const G2
   int li = 0;
   PSB_ROLL
   for (int i = PSB_ML_NBITS - 1; i >= 0; i--) {
-    PSB_ML_BARRIER(block_sync);
+#if PSB_ML_SYNC
+    if (i % PSB_ML_SYNC == 0) PSB_ML_BARRIER(block_sync);
+#endif
     if (i != PSB_ML_NBITS - 1) fp12_sqr(f, f);
     if (use1) {
       ml_dbl_step(T, c0, c2, c3, x1, ny1);
@@ -311,7 +325,7 @@ PSB_HD PSB_NOINL void pow_z_gs(Fp12& y, const Fp12& x) {
 #define PSB_Z_SETBITS_HI PSB_Z_SETBITS_OVERRIDE
 #endif
 constexpr int kZSetBits = PSB_Z_SETBITS_HI;          // set bits of |z| in [1, pivot]: one kept compressed value each
-PSB_HD PSB_NOINL void pow_z(Fp12& y, const Fp12& x) {
+PSB_HD PSB_NOINL void pow_z(Fp12& y, const Fp12& x, bool block_sync = false) {
 #ifdef PSB_POWZ_GS
   pow_z_gs(y, x);
 #else
@@ -325,8 +339,14 @@ PSB_HD PSB_NOINL void pow_z(Fp12& y, const Fp12& x) {
     for (int i = 1; i <= PSB_Z_PIVOT; i++) {
       cyclo_csqr(c, c);
       if (i == PSB_Z_PIVOT || z_bit(i)) keep[k++] = c;
+#if PSB_POWZ_SYNC
+      if (i % PSB_POWZ_SYNC == 0) PSB_FE_BARRIER(block_sync);
+#endif
     }
   }
+#if PSB_POWZ_SYNC_MID
+  PSB_FE_BARRIER(block_sync);
+#endif
   // prefix products of the denominators 4 g2.  x = 1 (a lane whose Miller value lies in a proper subfield, e.g. a
   // credential with sigma = 0) compresses to (0, 0, 0, 0): there the denominator is replaced by 1 -- the numerator is 0,
   // so g1 = 0 and g0 = 1 come out right with no other code path (a tampered lane must not slow down its warp).
@@ -355,6 +375,9 @@ PSB_HD PSB_NOINL void pow_z(Fp12& y, const Fp12& x) {
   PSB_ROLL
   for (int k = kZSetBits - 1; k >= 0; k--) {
     Fp2 dinv, num, g1;
+#if PSB_POWZ_SYNC_TAIL
+    PSB_FE_BARRIER(block_sync);
+#endif
     if (k > 0) {
       Fp2 d, one;
       fp2_mul(dinv, inv, pre[k - 1]);            // 1 / den_k
@@ -406,6 +429,9 @@ PSB_HD PSB_NOINL void final_exp(Fp12& y, const Fp12& x, bool block_sync = false)
   fp12_frobenius(a0, x, 2);
   fp12_mul(a0, a0, x);          // x^(p^2+1)
   fp12_inv(a1, a0);
+#if PSB_FE_SYNC_EASY
+  PSB_FE_BARRIER(block_sync);
+#endif
   fp12_conj(a0, a0);            // ^(p^6)
   fp12_mul(t, a1, a0);
 #if PSB_IS_BN
@@ -463,15 +489,15 @@ PSB_HD PSB_NOINL void final_exp(Fp12& y, const Fp12& x, bool block_sync = false)
   // tests/test_oracle.py) -- five pow_z like mcl, but 7 Fp12 products, 1 cyclotomic squaring and 2 Frobenius maps
   // instead of 12, 2 and 3; equal exponents give the same field element, so GT bytes are unchanged.
   PSB_FE_BARRIER(block_sync);
-  pow_z(a0, t); fp12_conj(a1, t); fp12_mul(a0, a0, a1);                 // t^(z-1)
+  pow_z(a0, t, block_sync); fp12_conj(a1, t); fp12_mul(a0, a0, a1);                 // t^(z-1)
   PSB_FE_BARRIER(block_sync);
-  pow_z(a2, a0); fp12_conj(a1, a0); fp12_mul(a2, a2, a1);               // ^(z-1)
+  pow_z(a2, a0, block_sync); fp12_conj(a1, a0); fp12_mul(a2, a2, a1);               // ^(z-1)
   PSB_FE_BARRIER(block_sync);
-  pow_z(a0, a2); fp12_frobenius(a1, a2, 1); fp12_mul(a0, a0, a1);       // ^(z+p)            =: u
+  pow_z(a0, a2, block_sync); fp12_frobenius(a1, a2, 1); fp12_mul(a0, a0, a1);       // ^(z+p)            =: u
   PSB_FE_BARRIER(block_sync);
-  pow_z(a2, a0);
+  pow_z(a2, a0, block_sync);
   PSB_FE_BARRIER(block_sync);
-  pow_z(a2, a2);                                                        // u^(z^2)
+  pow_z(a2, a2, block_sync);                                                        // u^(z^2)
   fp12_frobenius(a1, a0, 2); fp12_mul(a2, a2, a1);                      // u^(z^2+p^2)
   fp12_conj(a1, a0); fp12_mul(a2, a2, a1);                              // u^(z^2+p^2-1)
   fp12_cyclo_sqr(a1, t); fp12_mul(a1, a1, t);                           // t^3
