@@ -248,9 +248,9 @@ __global__ void k_fixed_lines(const G2J* gg /*normalised*/, FixedLine* lines) {
 // ---- PS verification pipeline -------------------------------------------------------------------------
 // phase 1: scalars m_i (SHA-256 of the attribute strings, or the caller's Fr) and
 //          K = XX + sum_i m_i YY_i from the per-key window tables.
-__global__ void PSB_PAIR_BOUNDS k_verify_msm(size_t N, int n, int w, const uint8_t* blob, const uint64_t* off,
+__global__ void PSB_PAIR_BOUNDS k_verify_msm(size_t N, size_t base, int n, int w, const uint8_t* blob, const uint64_t* off,
                                                         const Fr* m_mont, const G2J* XX, const G2A* tbl, G2J* Kout) {
-  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t lane = base + (size_t)blockIdx.x * blockDim.x + threadIdx.x;    // lanes [base, N): psb_api.cu, for_waves
   if (lane >= N) return;
   const size_t per_base = (size_t)fixed_nwin(w) << (w - 1);
   G2J acc = *XX;
@@ -271,9 +271,9 @@ __global__ void PSB_PAIR_BOUNDS k_verify_msm(size_t N, int n, int w, const uint8
 }
 
 // phase 2: f = ML(sig1, K) * ML(-sig2, gg)  (one multi-Miller loop per lane)
-__global__ void PSB_PAIR_BOUNDS k_verify_miller(size_t N, const G1J* sig1, const G1J* sig2, const G2J* K,
+__global__ void PSB_PAIR_BOUNDS k_verify_miller(size_t N, size_t base, const G1J* sig1, const G1J* sig2, const G2J* K,
                                                            const FixedLine* lines, Fp12* fout) {
-  const size_t lane0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t lane0 = base + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = lane0 < N;
   const size_t lane = live ? lane0 : N - 1;        // as in k_verify_final: no early exit, the block may re-align itself
   Fp x1, y1, x2, y2;
@@ -293,9 +293,9 @@ __global__ void PSB_PAIR_BOUNDS k_verify_miller(size_t N, const G1J* sig1, const
 // phase 3: final exponentiation, verdict = (sig1 != 0) && (f^e == 1), optional GT
 //          reject_zero_sig1: PSVerifier::verify rejects sig1 == 0 (ps-verifier.cc:16-18), el_passo_verify_id does not;
 //          pre (optional): per-lane verdict of an earlier step (the NIZK check) that is ANDed in.
-__global__ void PSB_PAIR_BOUNDS k_verify_final(size_t N, const G1J* sig1, const Fp12* fin, uint8_t* verdict,
+__global__ void PSB_PAIR_BOUNDS k_verify_final(size_t N, size_t base, const G1J* sig1, const Fp12* fin, uint8_t* verdict,
                                                           Fp12* gt, const uint8_t* pre, int reject_zero_sig1) {
-  const size_t lane0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t lane0 = base + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = lane0 < N;
   const size_t lane = live ? lane0 : N - 1;        // surplus threads of the last block shadow the last lane: no early exit,
   Fp12 f = fin[lane], e;                           // so the block can re-align itself inside final_exp
@@ -308,8 +308,8 @@ __global__ void PSB_PAIR_BOUNDS k_verify_final(size_t N, const G1J* sig1, const 
 }
 
 // plain pairing e(P, Q) per lane (no fixed argument)
-__global__ void PSB_PAIR_BOUNDS k_pairing_miller(size_t N, const G1J* P, const G2J* Q, Fp12* fout) {
-  const size_t lane0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void PSB_PAIR_BOUNDS k_pairing_miller(size_t N, size_t base, const G1J* P, const G2J* Q, Fp12* fout) {
+  const size_t lane0 = base + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = lane0 < N;
   const size_t lane = live ? lane0 : N - 1;
   Fp x1, y1, zero;
@@ -321,8 +321,8 @@ __global__ void PSB_PAIR_BOUNDS k_pairing_miller(size_t N, const G1J* P, const G
   miller_loop2(f, x1, y1, q, zero, zero, nullptr, false, true);
   if (live) fout[lane] = f;
 }
-__global__ void PSB_PAIR_BOUNDS k_final_exp(size_t N, const Fp12* fin, Fp12* out) {
-  const size_t lane0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void PSB_PAIR_BOUNDS k_final_exp(size_t N, size_t base, const Fp12* fin, Fp12* out) {
+  const size_t lane0 = base + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = lane0 < N;
   const size_t lane = live ? lane0 : N - 1;
   Fp12 f = fin[lane], e;

@@ -71,14 +71,27 @@ int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
 #define LAUNCHED() g_launches.fetch_add(1, std::memory_order_relaxed)
 
 inline unsigned nblocks(size_t n, int block = kBlock) { return (unsigned)((n + block - 1) / block); }
-// block size of the pairing-pipeline kernels: one 512-thread block per SM once the batch fills the GPU that way (shared
-// instruction fetches, kernels.cuh), smaller blocks for small batches so that they still spread over all SMs
+// Launch shape of the pairing-pipeline kernels: ONE 512-thread block per SM and wave (shared instruction fetches,
+// kernels.cuh) for the whole waves of a batch, then the ragged rest as ONE thinner block per SM in a second launch.
+// A wave lasts as long as its fullest scheduler has warps (measured: 14- and 16-warp blocks take the same time, the
+// phase kernels run alike from 2 warps per scheduler up), so a rest of full 512-thread blocks on part of the SMs costs
+// a whole wave, the same lanes spread over all SMs only their share of one: 2^18 lanes = 3.46 waves cost 3.5, not 4.
 int g_sms = 148;   // SMs of device 0 (psb_init)
-inline int pair_block(size_t n) {
-  int b = kPairBlock;
-  while (b > 128 && n < (size_t)g_sms * b) b >>= 1;
-  return b;
+template <class Launch> inline void for_waves(size_t n, Launch&& launch) {   // launch(first lane, end lane, block size)
+  const size_t wave = (size_t)g_sms * kPairBlock;
+  const size_t full = n / wave * wave;
+  if (full) launch((size_t)0, full, kPairBlock);
+  if (n > full) {
+    const size_t per_sm = (n - full + g_sms - 1) / g_sms;
+    const size_t b = std::min<size_t>(std::max<size_t>((per_sm + 31) / 32 * 32, 32), kPairBlock);
+    launch(full, n, (int)b);
+  }
 }
+#define PSB_WAVES(n, kernel, ...)                                                              \
+  for_waves((n), [&](size_t wb_, size_t we_, int blk_) {                                       \
+    kernel<<<nblocks(we_ - wb_, blk_), blk_, 0, st>>>(we_, wb_, __VA_ARGS__);                  \
+    LAUNCHED();                                                                                \
+  })
 
 int ensure(DevBuf& b, size_t bytes) {
   if (bytes <= b.cap) return PSB_OK;
@@ -201,14 +214,11 @@ int verify_launch(const psb_key* key, int di, size_t N, const G1J* d_sig1, const
     for (auto& e : dv->ev) if (!e) CK(cudaEventCreate(&e));
     CK(cudaEventRecord(dv->ev[0], st));
   }
-  k_verify_msm<<<nblocks(N, pair_block(N)), pair_block(N), 0, st>>>(N, (int)key->n, key->w, d_blob, d_off, d_m, kd.g2pts + 1, kd.tblYY, dK);
-  LAUNCHED();
+  PSB_WAVES(N, k_verify_msm, (int)key->n, key->w, d_blob, d_off, d_m, kd.g2pts + 1, kd.tblYY, dK);
   if (prof) CK(cudaEventRecord(dv->ev[1], st));
-  k_verify_miller<<<nblocks(N, pair_block(N)), pair_block(N), 0, st>>>(N, d_sig1, d_sig2, dK, kd.lines, dF);
-  LAUNCHED();
+  PSB_WAVES(N, k_verify_miller, d_sig1, d_sig2, dK, kd.lines, dF);
   if (prof) CK(cudaEventRecord(dv->ev[2], st));
-  k_verify_final<<<nblocks(N, pair_block(N)), pair_block(N), 0, st>>>(N, d_sig1, dF, d_verdict, d_gt, d_pre, 1);
-  LAUNCHED();
+  PSB_WAVES(N, k_verify_final, d_sig1, dF, d_verdict, d_gt, d_pre, 1);
   if (prof) CK(cudaEventRecord(dv->ev[3], st));
   CK(cudaGetLastError());
   return PSB_OK;
@@ -528,10 +538,8 @@ int psb_pairing(size_t N, const uint64_t* P, const uint64_t* Q, uint64_t* out) {
     if ((rc = ensure(dv->ws, L * sizeof(Fp12)))) return rc;
     CK(cudaMemcpyAsync(dv->in[0].p, P + b * kG1W, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(dv->in[1].p, Q + b * kG2W, L * sizeof(G2J), cudaMemcpyHostToDevice, st));
-    k_pairing_miller<<<nblocks(L, pair_block(L)), pair_block(L), 0, st>>>(L, (const G1J*)dv->in[0].p, (const G2J*)dv->in[1].p, (Fp12*)dv->ws.p);
-    LAUNCHED();
-    k_final_exp<<<nblocks(L, pair_block(L)), pair_block(L), 0, st>>>(L, (const Fp12*)dv->ws.p, (Fp12*)dv->in[5].p);
-    LAUNCHED();
+    PSB_WAVES(L, k_pairing_miller, (const G1J*)dv->in[0].p, (const G2J*)dv->in[1].p, (Fp12*)dv->ws.p);
+    PSB_WAVES(L, k_final_exp, (const Fp12*)dv->ws.p, (Fp12*)dv->in[5].p);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out + b * kGtW, dv->in[5].p, L * sizeof(Fp12), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -830,10 +838,8 @@ int psb_verify_id(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* 
     LAUNCHED();
     k_vid_hash<<<nblocks(L), kBlock, 0, st>>>(L, dk, dphi, dE1, dE2, dVk, dV, with_id, dc, dad - a0, dadoff, dok);
     LAUNCHED();
-    k_verify_miller<<<nblocks(L, pair_block(L)), pair_block(L), 0, st>>>(L, dS1, dS2, dK, kd.lines, dF);
-    LAUNCHED();
-    k_verify_final<<<nblocks(L, pair_block(L)), pair_block(L), 0, st>>>(L, dS1, dF, dver, nullptr, dok, 0);
-    LAUNCHED();
+    PSB_WAVES(L, k_verify_miller, dS1, dS2, dK, kd.lines, dF);
+    PSB_WAVES(L, k_verify_final, dS1, dF, dver, nullptr, dok, 0);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(verdict + b, dver, L, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
