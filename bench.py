@@ -367,7 +367,7 @@ def main():
     achieved = work[dom] * FPMUL_MAC32 * N / (phase[dom] * 1e-3)
     traffic = None
     try:  # DRAM bytes of that kernel from the committed ncu --set full capture, scaled per lane to this launch
-        with open(os.path.join(ROOT, "profiles", "r1za_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r1zb_traffic.json")) as f:
             tr = json.load(f)
         traffic = tr["dram_bytes_per_launch"][names[dom]] / tr["lanes"] * N
     except Exception:
