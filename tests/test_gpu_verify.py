@@ -148,3 +148,35 @@ def test_full_size_2p20_properties(gpu_pkg, ref):
     want = ref.ps_verify(km, sig1[pick].copy(), sig2[pick].copy(), [lane_attrs[j] for j in pick], nthreads=ref.hw_threads())
     assert np.array_equal(v1[pick], want)
     pk.close()
+
+
+@bls_only
+def test_wave_boundaries(gpu_pkg, ref):
+    """Launch shape (psb_api.cu, for_waves): whole waves of 512-thread blocks, then the ragged rest as one thinner block
+    per SM with a lane offset.  Batches of one wave -1 / +0 / +1 lanes and of two waves + 33 (a rest of a single warp on
+    33 SMs): the verdict bitmap equals the construction, the lanes either side of every launch boundary agree with the
+    reference's PSVerifier::verify, and psb_pairing returns the same GT for a tiled input on both sides of the seam."""
+    import torch
+    import bench
+    wave = torch.cuda.get_device_properties(0).multi_processor_count * 512
+    key = bench.load_key(5)
+    pk = gpu_pkg.PSPubKey(key["g"], key["gg"], key["XX"], key["Y"], key["YY"], window_bits=12)
+    ver = gpu_pkg.PSVerifier(pk)
+    km = ref.KeyMaterial(5, seed_=1)
+    for lanes in (wave - 1, wave, wave + 1, 2 * wave + 33):
+        sig1, sig2, blob, off, expected, lane_attrs = bench.make_batch(gpu_pkg, key, lanes, 0, base=2048)
+        got = ver.verify(sig1, sig2, (blob, off))
+        assert np.array_equal(got, expected), lanes
+        full = lanes // wave * wave
+        pick = np.unique(np.clip(np.array([0, full - 2, full - 1, full, full + 1, lanes - 2, lanes - 1, 1023]), 0, lanes - 1))
+        want = ref.ps_verify(km, sig1[pick].copy(), sig2[pick].copy(), [lane_attrs[j] for j in pick])
+        assert np.array_equal(got[pick], want), lanes
+    pk.close()
+    ref.seed(7)
+    k = ref.fr_rand(8)
+    P, Q = ref.g1_mul(ref.hash_to_g1(b"abc"), k), ref.g2_mul(ref.hash_to_g2(b"edf"), k)
+    lanes = wave + 40
+    gt = gpu_pkg.pairing(np.tile(P, (lanes // 8 + 1, 1))[:lanes].copy(), np.tile(Q, (lanes // 8 + 1, 1))[:lanes].copy())
+    exp = ref.pairing(P, Q)
+    assert np.array_equal(gt[:8], exp) and np.array_equal(gt[wave - 8:wave], exp) and np.array_equal(gt[wave:wave + 8], exp)
+    assert np.array_equal(gt[lanes - 8:], exp)
