@@ -50,7 +50,7 @@ uint64_t psb_launch_count(void);
  * points may have any z (they are normalised once here).  X_secret = g^x, the PSSigner secret
  * m_sk_X (src/ps-signer.h), or NULL for verify-only keys.  Builds the fixed-base window tables
  * (idea: mcl/include/mcl/window_method.hpp:68-108) in HBM on every device.
- * window_bits: 0 = default (16), else 4..20 (w = 20: 1.3 GB per G2 base -- sized for 180 GB of HBM). */
+ * window_bits: 0 = default (16), else 4..24 (w = 20: 1.3 GB per G2 base, w = 22: 4.8 GB, w = 24: 17.7 GB -- sized for 180 GB of HBM). */
 psb_key* psb_key_create(const uint64_t* g, const uint64_t* gg, const uint64_t* XX, const uint64_t* Y,
                         const uint64_t* YY, size_t n, const uint64_t* X_secret, int window_bits);
 void psb_key_destroy(psb_key* key);

@@ -206,10 +206,10 @@ __global__ void __launch_bounds__(kBlock) k_build_table(const Aff<F>* wb, int nb
   const uint32_t ch = (uint32_t)(gid % chunks_per_win);
   const uint32_t d0 = ch * kTblChunk;           // entries d0+1 .. d0+kTblChunk
   const Aff<F> B = wb[bw];
-  // S = d0 * B by double-and-add (d0 < 2^19 for w <= 20)
+  // S = d0 * B by double-and-add (d0 < 2^(w-1))
   Jac<F> S;
   pt_set_zero(S);
-  for (int bit = 19; bit >= 0; bit--) {
+  for (int bit = w - 2; bit >= 0; bit--) {
     pt_dbl(S, S);
     if ((d0 >> bit) & 1u) pt_madd(S, S, B);
   }

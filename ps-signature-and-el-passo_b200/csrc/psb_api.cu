@@ -317,7 +317,7 @@ psb_key* psb_key_create(const uint64_t* g, const uint64_t* gg, const uint64_t* X
   if (!g_init) { fail(PSB_ERR_NOT_INIT, "psb_init not called"); return nullptr; }
   if (!g || !gg || !XX || (n && (!Y || !YY))) { fail(PSB_ERR_ARG, "null key component"); return nullptr; }
   int w = window_bits == 0 ? 16 : window_bits;
-  if (w < 4 || w > 20) { fail(PSB_ERR_ARG, "window_bits must be 4..20"); return nullptr; }
+  if (w < 4 || w > 24) { fail(PSB_ERR_ARG, "window_bits must be 4..24"); return nullptr; }
   // fixed bases must be finite points: their window tables hold affine entries (z == 0 <=> infinity)
   bool inf = is_zero_words(g + 2 * kFpW, kFpW) || is_zero_words(gg + 4 * kFpW, 2 * kFpW) || is_zero_words(XX + 4 * kFpW, 2 * kFpW);
   for (size_t i = 0; i < n; i++) inf = inf || is_zero_words(Y + kG1W * i + 2 * kFpW, kFpW) || is_zero_words(YY + kG2W * i + 4 * kFpW, 2 * kFpW);

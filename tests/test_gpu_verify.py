@@ -10,7 +10,7 @@ from tests.conftest import FPW, bls_only
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("n_attrs,lanes,w", [(5, 130, 8), (5, 64, 16), (1, 33, 4), (3, 40, 11), (0, 8, 8)])
+@pytest.mark.parametrize("n_attrs,lanes,w", [(5, 130, 8), (5, 64, 16), (1, 33, 4), (3, 40, 11), (0, 8, 8), (2, 40, 22), (1, 33, 24)])
 def test_verify_matches_reference(gpu_pkg, ref, n_attrs, lanes, w):
     wl = workload.make_verify_workload(n_attrs=n_attrs, lanes=lanes, seed=11, tamper_every=5)
     pk = gpu_pkg.PSPubKey(wl.key.g, wl.key.gg, wl.key.XX, wl.key.Y, wl.key.YY, window_bits=w)
