@@ -437,14 +437,17 @@ PSB_HD PSB_NOINL void final_exp(Fp12& y, const Fp12& x, bool block_sync = false)
 #if PSB_IS_BN
   // hard part (expHardPartBN, bn.hpp:1576-1621): t^(d 2z(6z^2+3z+1)), d = (p^4 - p^2 + 1)/r  (Fuentes-Castaneda et al.)
   Fp12 a, b;
-  pow_z(b, t);                  // t^z
+  PSB_FE_BARRIER(block_sync);   // block re-alignment as in the BLS12 branch below
+  pow_z(b, t, block_sync);      // t^z
   fp12_cyclo_sqr(b, b);         // t^2z
   fp12_cyclo_sqr(a, b);         // t^4z
   fp12_mul(a, a, b);            // t^6z
-  pow_z(a2, a);                 // t^(6z^2)
+  PSB_FE_BARRIER(block_sync);
+  pow_z(a2, a, block_sync);     // t^(6z^2)
   fp12_mul(a, a, a2);
   fp12_cyclo_sqr(a3, a2);       // t^(12z^2)
-  pow_z(a3, a3);                // t^(12z^3)
+  PSB_FE_BARRIER(block_sync);
+  pow_z(a3, a3, block_sync);    // t^(12z^3)
   fp12_mul(a, a, a3);
   fp12_conj(b, b);
   fp12_mul(b, b, a);
