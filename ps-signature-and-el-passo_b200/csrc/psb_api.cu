@@ -11,6 +11,7 @@
 #include <atomic>
 #include <memory>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -276,6 +277,14 @@ int psb_init(int curve, const int* devices, int ndev) {
     // thread-local state (Fp12 temporaries, window tables of points) lives in local memory:
     // prefer L1 over shared memory, and give deep call chains enough stack
     cudaDeviceSetLimit(cudaLimitStackSize, 32 * 1024);
+    if (!getenv("PSB_NO_L1_PREF")) {   // (A/B switch; the kernels use no shared memory)
+      const int l1 = cudaSharedmemCarveoutMaxL1;
+      cudaFuncSetAttribute(k_verify_msm, cudaFuncAttributePreferredSharedMemoryCarveout, l1);
+      cudaFuncSetAttribute(k_verify_miller, cudaFuncAttributePreferredSharedMemoryCarveout, l1);
+      cudaFuncSetAttribute(k_verify_final, cudaFuncAttributePreferredSharedMemoryCarveout, l1);
+      cudaFuncSetAttribute(k_pairing_miller, cudaFuncAttributePreferredSharedMemoryCarveout, l1);
+      cudaFuncSetAttribute(k_final_exp, cudaFuncAttributePreferredSharedMemoryCarveout, l1);
+    }
     g_devs.push_back(d);
   }
   g_init = true;
