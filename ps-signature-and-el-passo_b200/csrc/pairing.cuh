@@ -62,6 +62,15 @@ PSB_HD PSB_INL void ml_mul_line(Fp12& f, const Fp2& c0, const Fp2& c2, const Fp2
 #endif
 }
 
+// f = line for f == 1 (all other coefficients of f are already 0): the same slots ml_mul_line multiplies by
+PSB_HD PSB_INL void ml_set_line(Fp12& f, const Fp2& c0, const Fp2& c2, const Fp2& c3) {
+#if PSB_TWIST_MTYPE
+  f.a.a = c0; f.a.b = c2; f.b.b = c3;      // c0 + c2 w^2 + c3 w^3  (w^2 = v)
+#else
+  f.a.a = c3; f.b.a = c2; f.b.b = c0;      // c3 + c2 w + c0 w^3
+#endif
+}
+
 // T <- 2T and the tangent line at T evaluated at P = (xP, yP); nyP = -yP:
 //   line = (E - B) + (3 X^2 xP) w^2 + (-2YZ yP) w^3     (scaled by -2YZ in Fp2)
 PSB_HD PSB_NOINL void ml_dbl_step(G2H& T, Fp2& c0, Fp2& c2, Fp2& c3, const Fp& xP, const Fp& nyP) {
@@ -208,8 +217,8 @@ PSB_HD PSB_NOINL void miller_loop2(Fp12& f, const Fp& x1, const Fp& y1, const G2
     if (i != PSB_ML_NBITS - 1) fp12_sqr(f, f);
     if (use1) {
       ml_dbl_step(T, c0, c2, c3, x1, ny1);
-#if PSB_TWIST_MTYPE && PSB_ML_FIRST_LINE
-      if (i == PSB_ML_NBITS - 1) { f.a.a = c0; f.a.b = c2; f.b.b = c3; }   // f is still 1: 1 * (c0 + c2 w^2 + c3 w^3) is the line itself
+#if PSB_ML_FIRST_LINE
+      if (i == PSB_ML_NBITS - 1) ml_set_line(f, c0, c2, c3);   // f is still 1: the product is the line itself
       else
 #endif
       ml_mul_line(f, c0, c2, c3);
