@@ -458,6 +458,19 @@ PSB_HD PSB_INL void fp_pminus_rr(Fp& r, const Fp& a) {
   for (int i = 0; i < PSB_NL; i++) { c += (int64_t)FpT::p(i) - a.v[i]; r.v[i] = (uint32_t)c; c >>= 32; }
 #endif
 }
+// 2p - a for a in [0, 2p): in (0, 2p] -- multiplier side of a product whose operands are unreduced sums (tower.cuh, engine A)
+PSB_HD PSB_INL uint32_t fp_2p_limb(int i) { return i == 0 ? (FpT::p(0) << 1) : ((FpT::p(i) << 1) | (FpT::p(i - 1) >> 31)); }
+PSB_HD PSB_INL void fp_2pminus_rr(Fp& r, const Fp& a) {
+#ifdef __CUDA_ARCH__
+  r.v[0] = ptx::sub_cc(fp_2p_limb(0), a.v[0]);
+  PSB_UNROLL
+  for (int i = 1; i < PSB_NL - 1; i++) r.v[i] = ptx::subc_cc(fp_2p_limb(i), a.v[i]);
+  r.v[PSB_NL - 1] = ptx::subc(fp_2p_limb(PSB_NL - 1), a.v[PSB_NL - 1]);
+#else
+  int64_t c = 0;
+  for (int i = 0; i < PSB_NL; i++) { c += (int64_t)fp_2p_limb(i) - a.v[i]; r.v[i] = (uint32_t)c; c >>= 32; }
+#endif
+}
 PSB_HD PSB_INL void fp_get(Fp& d, const Fp& mem) { fp_ld(d.v, mem); }
 PSB_HD PSB_INL void fp_put(Fp& mem, const Fp& s) { fp_st(mem, s.v); }
 PSB_HD PSB_INL void fp_mul_inl(Fp& r, const Fp& a, const Fp& b) { fp_mul(r, a, b); }

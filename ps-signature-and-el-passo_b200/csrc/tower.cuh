@@ -96,32 +96,37 @@ PSB_HD PSB_NOINL void fp2_mul_xi(Fp2& r, const Fp2& x) {
 PSB_HD PSB_INL Fp* fp2_comp(Fp2& x, int k) { return &x.a + k; }
 PSB_HD PSB_INL const Fp* fp2_comp(const Fp2& x, int k) { return &x.a + k; }
 
-// 2p - a for a in [0, 2p): a representative of -a in (0, 2p] (multiplicand only)
-PSB_HD PSB_INL void fp_2pminus_rr(Fp& r, const Fp& a) {
-  Fp t;
-  fp_pminus_rr(t, a);                 // p - a in (-p, p], two's complement when negative
-  Fp pp;
-  PSB_UNROLL
-  for (int i = 0; i < PSB_NL; i++) pp.v[i] = FpT::p(i);
-  add_n<PSB_NL>(r.v, t.v, pp.v);          // + p (carry out cancels the wrap)
-}
-
 #ifdef __CUDA_ARCH__
 // Two multiplier ENGINES carry every Fp2 product of the tower (instruction-cache budget: each engine is one fully
 // unrolled register-resident body; the variants differ only in a short operand-preparation prologue selected by
 // warp-uniform null-pointer tests):
 //   engine A  (re, im) = (xa ya + xb (p - yb), xa yb + xb ya)   x = x1 [+ x2],  y = y1 [+ y2]      fp2_mul, fp2_mul_sum
 //   engine B  (re, im) = (m1 n1, m2 n2)                         squares (x = x1 [+ x2]) and Fp2 * Fp  fp2_sqr, fp2_sqr_sum, fp2_mul_fp
+#ifndef PSB_LAZY_Y
+#define PSB_LAZY_Y 1
+#endif
 __device__ PSB_NOINL void fp2_engine_a(Fp2& r, const Fp2* x1, const Fp2* x2, const Fp2* y1, const Fp2* y2) {
   Fp xa, xb, ya, yb, u, nb, re;
   fp_get(xa, x1->a); fp_get(xb, x1->b); fp_get(ya, y1->a); fp_get(yb, y1->b);
   if (x2) {
     fp_get(u, x2->a); fp_addnr_rr(xa, xa, u);     // multiplicand side: unreduced (< 2p)
     fp_get(u, x2->b); fp_addnr_rr(xb, xb, u);
+#if PSB_IS_BN || !PSB_LAZY_Y
     fp_get(u, y2->a); fp_add_rr(ya, ya, u);       // multiplier side: canonical
     fp_get(u, y2->b); fp_add_rr(yb, yb, u);
   }
   fp_pminus_rr(nb, yb);
+#else
+    // 381-bit p in a 384-bit radix: with all four operands < 2p the accumulated pair of products is <= 8 p^2 and
+    // (8 p^2 + R p) / R = p (1 + 8 p / R) < 1.82 p, so the ONE conditional subtraction of the reduction still lands in
+    // [0, p) and the sums on the multiplier side need no reduction either (BN254: 8 p / R > 1, stays canonical)
+    fp_get(u, y2->a); fp_addnr_rr(ya, ya, u);
+    fp_get(u, y2->b); fp_addnr_rr(yb, yb, u);
+    fp_2pminus_rr(nb, yb);
+  } else {
+    fp_pminus_rr(nb, yb);
+  }
+#endif
   // one multiplier body, executed twice (real, imaginary): half the code of two unrolled copies -- a 20 KB
   // straight-line engine still stalled ~25 % of its samples on instruction fetch (r1g)
   PSB_ROLL

@@ -43,14 +43,28 @@ def test_fp2(gpu_pkg, ref, rng, op):
     assert np.array_equal(gpu_pkg.test_op(10 + op, a, b if op < 3 else None), ref.fp2_op(op, a, b))
 
 
+def extreme_rows(ref, a, b):
+    """worst-case magnitudes for the multiplier's unreduced operand sums (tower.cuh, engine A): every component p - 1;
+    p - 1 against (p - 1, 0) pairs (the negated imaginary part becomes 2p); p - 1 against 0 and 1"""
+    w = a.shape[1] // ref.fp_from_ints([1]).shape[1]
+    top, one = ref.fp_from_ints([FIELD_P - 1])[0], ref.fp_from_ints([1])[0]
+    fw = top.shape[0]
+    a[0] = np.tile(top, w); b[0] = np.tile(top, w)
+    a[1] = np.tile(top, w); b[1] = np.tile(np.concatenate([top, np.zeros(fw, dtype=top.dtype)]), w // 2)
+    a[2] = np.tile(np.concatenate([np.zeros(fw, dtype=top.dtype), top]), w // 2); b[2] = np.tile(top, w)
+    a[3] = np.tile(top, w); b[3] = np.tile(one, w)
+    a[4] = np.tile(top, w); b[4] = 0
+    return a, b
+
+
 def test_fp6(gpu_pkg, ref, rng):
-    a, b = rand_fp_raw(ref, rng, 65, 6), rand_fp_raw(ref, rng, 65, 6)
+    a, b = extreme_rows(ref, rand_fp_raw(ref, rng, 65, 6), rand_fp_raw(ref, rng, 65, 6))
     assert np.array_equal(gpu_pkg.test_op(20, a, b), ref.fp6_op(ref.OP_MUL, a, b))
     assert np.array_equal(gpu_pkg.test_op(21, a), ref.fp6_op(ref.OP_INV, a))
 
 
 def test_fp12(gpu_pkg, ref, rng):
-    a, b = rand_fp_raw(ref, rng, 65, 12), rand_fp_raw(ref, rng, 65, 12)
+    a, b = extreme_rows(ref, rand_fp_raw(ref, rng, 65, 12), rand_fp_raw(ref, rng, 65, 12))
     assert np.array_equal(gpu_pkg.test_op(30, a, b), ref.fp12_op(ref.OP_MUL, a, b))
     assert np.array_equal(gpu_pkg.test_op(31, a), ref.fp12_op(ref.OP_SQR, a))
     assert np.array_equal(gpu_pkg.test_op(32, a), ref.fp12_op(ref.OP_INV, a))
