@@ -129,70 +129,89 @@ __device__ PSB_INL void dot2_rr(uint32_t* r, const L12& a, const L12& b, const L
   finish_rr(r, Y, X);
 }
 
-// ---- rolled cores (EXPERIMENT, not on the product path) ------------------------------------------------
-// Rolled loops keep the multiplicands in registers and stream the multiplier limbs from memory, two rows per
-// iteration.  Measured (r1f): the per-row shift of the accumulator arrays is free register renaming in unrolled code
-// but costs ~24 IMAD.MOV per array per iteration at the loop back edge (+45 % instructions) -> kept for reference only.
-__device__ PSB_INL void zero12(L12& x) {
+// ---- split form: wide product and stand-alone reduction (lazy reduction of the Fp2 engine, tower.cuh) -------------
+// T (2N limbs) = a * b without reduction (mcl FpDbl::mulPre, fp_tower.hpp:13-178): the rows of the fused multiplier
+// with the reduction steps left out -- after each row the low limb of the window is final and is peeled off before the
+// window shifts.  Any N-limb operands (the Karatsuba middle term multiplies sums up to 4p).  N^2 wide MACs.
+__device__ PSB_INL void mulpre_rr(uint32_t* T, const L12& a, const L12& b) {
+  L12 X, Y;
+  first(X, Y, a, b[0]);
+  T[0] = X[0];
   PSB_UNROLL
-  for (int i = 0; i < PSB_NL; i++) x[i] = 0;
+  for (int i = 1; i < PSB_NL; i += 2) {
+    mac_shift(Y, X, a, b[i]);
+    T[i] = Y[0];
+    if (i + 1 < PSB_NL) {
+      mac_shift(X, Y, a, b[i + 1]);
+      T[i + 1] = X[0];
+    }
+  }
+  T[PSB_NL] = ptx::add_cc(Y[1], X[0]);                       // high half = (Y >> 32) + X
+  PSB_UNROLL
+  for (int i = 1; i < PSB_TOP; i++) T[PSB_NL + i] = ptx::addc_cc(Y[i + 1], X[i]);
+  T[PSB_NL + PSB_TOP] = ptx::addc_cc(0, X[PSB_TOP]);         // (carry out is 0 by the value bound: see chain_after)
 }
-__device__ PSB_INL uint2 ld2(const uint32_t* p) { return *reinterpret_cast<const uint2*>(p); }   // limb pairs are 8-byte aligned
+// Orders two independent products for ptxas: x picks up the (always zero) carry that the previous mulpre_rr left, so the
+// next product cannot start before the previous one has finished.  Left to itself ptxas interleaves independent
+// products for ILP the multiply pipe cannot use (one wide MAC per 4 cycles and warp) and runs out of predicate
+// registers for their carry chains: 160 LOP3 of predicate spills in one Fp2 product.
+__device__ PSB_INL void chain_after(uint32_t& x) { asm volatile("addc.u32 %0, %0, 0;" : "+r"(x)); }
+// r = T / R mod p for a 2N-limb T < pR (mcl FpDbl::mod, low_func.hpp:511-547), canonical.  The window holds the low
+// half only: r = (T_lo + M p) / R + T_hi < p + 1 + T_hi <= 2p.  The shift of the window is folded into the m p_odd
+// chain of the next row (PSB_RED_ODD_RSHIFT), as the fused multiplier folds it into its a_odd b chain: N^2 wide MACs
+// + N plain ones, like the reduction half of the fused form.
+__device__ PSB_INL void redc_rr(uint32_t* r, const uint32_t* T) {
+  L12 X, Y;
+  PSB_UNROLL
+  for (int i = 0; i < PSB_NL; i++) X[i] = T[i];
+  uint32_t m = X[0] * PSB_FP_N0;
+  PSB_X(PSB_RED_FIRST_ODD, PSB_ALL(Y), m);
+  PSB_X(PSB_RED_EVEN, PSB_ALL(X), Y[PSB_TOP], m);
+  PSB_UNROLL
+  for (int i = 1; i < PSB_NL; i += 2) {
+    PSB_X(PSB_RED_ODD_RSHIFT, m, Y[0], PSB_ALL(X));
+    PSB_X(PSB_RED_EVEN, PSB_ALL(Y), X[PSB_TOP], m);
+    if (i + 1 < PSB_NL) {
+      PSB_X(PSB_RED_ODD_RSHIFT, m, X[0], PSB_ALL(Y));
+      PSB_X(PSB_RED_EVEN, PSB_ALL(X), Y[PSB_TOP], m);
+    }
+  }
+  uint32_t t[PSB_NL];
+  t[0] = ptx::add_cc(Y[1], X[0]);                             // (Y >> 32) + X   (Y[0] == 0)
+  PSB_UNROLL
+  for (int i = 1; i < PSB_TOP; i++) t[i] = ptx::addc_cc(Y[i + 1], X[i]);
+  t[PSB_TOP] = ptx::addc(0, X[PSB_TOP]);
+  r[0] = ptx::add_cc(t[0], T[PSB_NL]);                        // + T_hi
+  PSB_UNROLL
+  for (int i = 1; i < PSB_TOP; i++) r[i] = ptx::addc_cc(t[i], T[PSB_NL + i]);
+  r[PSB_TOP] = ptx::addc(t[PSB_TOP], T[PSB_NL + PSB_TOP]);
+  cond_sub_mod<FpT>(r);
+}
 
-// two independent products side by side:  r1 = a1 * b1,  r2 = a2 * b2   (b1, b2 in memory)
-__device__ PSB_INL void mul2_loop(uint32_t* r1, uint32_t* r2, const L12& a1, const uint32_t* b1, const L12& a2, const uint32_t* b2) {
-  L12 X1, Y1, X2, Y2;
-  zero12(X1); zero12(Y1); zero12(X2); zero12(Y2);
-#pragma unroll 1
-  for (int i = 0; i < PSB_NL; i += 2) {
-    const uint2 p = ld2(b1 + i), q = ld2(b2 + i);
-    mac_shift(X1, Y1, a1, p.x); reduce(X1, Y1);
-    mac_shift(X2, Y2, a2, q.x); reduce(X2, Y2);
-    mac_shift(Y1, X1, a1, p.y); reduce(Y1, X1);
-    mac_shift(Y2, X2, a2, q.y); reduce(Y2, X2);
-  }
-  finish_rr(r1, Y1, X1);
-  finish_rr(r2, Y2, X2);
+// T (2N limbs) = a^2: the cross products once (N (N - 1) / 2 wide MACs on the EV / OD accumulator arrays, generated rows
+// PSB_SQR_CROSS), merged and doubled, plus the N diagonal products -- 78 wide MACs for N = 12 instead of 144
+// (mcl sqrPre, low_func.hpp:554-652 / fp_generator.hpp gen_sqr).  Any N-limb operand.
+__device__ PSB_INL void sqrpre_rr(uint32_t* T, const L12& a) {
+  uint32_t EV[2 * PSB_NL], OD[2 * PSB_NL];
+  PSB_UNROLL
+  for (int i = 0; i < 2 * PSB_NL; i++) { EV[i] = 0; OD[i] = 0; }
+  PSB_SQR_CROSS(a, EV, OD);
+  T[0] = EV[0];                                               // T = EV + (OD << 32)
+  T[1] = ptx::add_cc(EV[1], OD[0]);
+  PSB_UNROLL
+  for (int i = 2; i < 2 * PSB_NL - 1; i++) T[i] = ptx::addc_cc(EV[i], OD[i - 1]);
+  T[2 * PSB_NL - 1] = ptx::addc(EV[2 * PSB_NL - 1], OD[2 * PSB_NL - 2]);
+  T[0] = ptx::add_cc(T[0], T[0]);                             // T = 2 T  (cross sum < 2^(64 N - 1))
+  PSB_UNROLL
+  for (int i = 1; i < 2 * PSB_NL - 1; i++) T[i] = ptx::addc_cc(T[i], T[i]);
+  T[2 * PSB_NL - 1] = ptx::addc(T[2 * PSB_NL - 1], T[2 * PSB_NL - 1]);
+  PSB_SQR_DIAG(a, T);
 }
-// Fp2 product with multiplicands xa, xb, nxb = -xb (mod p, any representative < 2p) in registers and the
-// multiplier y = (ya, yb) in memory:  re = xa ya + nxb yb,  im = xa yb + xb ya   (four carry chains per row)
-__device__ PSB_INL void fp2mul_loop(uint32_t* re, uint32_t* im, const L12& xa, const L12& xb, const L12& nxb,
-                                    const uint32_t* ya, const uint32_t* yb) {
-  L12 X1, Y1, X2, Y2;
-  zero12(X1); zero12(Y1); zero12(X2); zero12(Y2);
-#pragma unroll 1
-  for (int i = 0; i < PSB_NL; i += 2) {
-    const uint2 p = ld2(ya + i), q = ld2(yb + i);
-    mac_shift(X1, Y1, xa, p.x); mac(X1, Y1, nxb, q.x); reduce(X1, Y1);
-    mac_shift(X2, Y2, xa, q.x); mac(X2, Y2, xb, p.x); reduce(X2, Y2);
-    mac_shift(Y1, X1, xa, p.y); mac(Y1, X1, nxb, q.y); reduce(Y1, X1);
-    mac_shift(Y2, X2, xa, q.y); mac(Y2, X2, xb, p.y); reduce(Y2, X2);
-  }
-  finish_rr(re, Y1, X1);
-  finish_rr(im, Y2, X2);
-}
-// single product / two-product dot with streamed multipliers
-__device__ PSB_INL void mul_loop(uint32_t* r, const L12& a, const uint32_t* b) {
-  L12 X, Y;
-  zero12(X); zero12(Y);
-#pragma unroll 1
-  for (int i = 0; i < PSB_NL; i += 2) {
-    const uint2 p = ld2(b + i);
-    mac_shift(X, Y, a, p.x); reduce(X, Y);
-    mac_shift(Y, X, a, p.y); reduce(Y, X);
-  }
-  finish_rr(r, Y, X);
-}
-__device__ PSB_INL void dot2_loop(uint32_t* r, const L12& a, const uint32_t* b, const L12& c, const uint32_t* d) {
-  L12 X, Y;
-  zero12(X); zero12(Y);
-#pragma unroll 1
-  for (int i = 0; i < PSB_NL; i += 2) {
-    const uint2 p = ld2(b + i), q = ld2(d + i);
-    mac_shift(X, Y, a, p.x); mac(X, Y, c, q.x); reduce(X, Y);
-    mac_shift(Y, X, a, p.y); mac(Y, X, c, q.y); reduce(Y, X);
-  }
-  finish_rr(r, Y, X);
+// r = a^2 / R mod p, canonical, for a < 2p (T < 4 p^2 < pR): N (N + 1) / 2 + N^2 + N wide MACs (234 against the product's 300)
+__device__ PSB_INL void sqr_rr(uint32_t* r, const L12& a) {
+  uint32_t T[2 * PSB_NL];
+  sqrpre_rr(T, a);
+  redc_rr(r, T);
 }
 
 __device__ PSB_INL void store12(uint32_t* r, const L12& t) {
@@ -209,6 +228,13 @@ __device__ PSB_NOINL void mul(uint32_t* r, const uint32_t* a_, const uint32_t* b
   load12(a, a_);
   load12(b, b_);
   mul_rr(t, a, b);
+  store12(r, t);
+}
+// r = a * a / R mod p  (memory operand; r may alias a): the dedicated squaring
+__device__ PSB_NOINL void sqr(uint32_t* r, const uint32_t* a_) {
+  L12 a, t;
+  load12(a, a_);
+  sqr_rr(t, a);
   store12(r, t);
 }
 // r = (a b + c d) / R mod p  (memory operands)

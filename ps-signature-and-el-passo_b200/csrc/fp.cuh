@@ -421,7 +421,14 @@ PSB_HD PSB_INL void fpw_sub_nr(FpW& r, const FpW& a, const FpW& b) { sub_n<2 * P
 namespace psb {
 #ifdef __CUDA_ARCH__
 __device__ PSB_INL void fp_mul(Fp& r, const Fp& a, const Fp& b) { cios::mul(r.v, a.v, b.v); }
+#ifndef PSB_FP_SQR_DEDICATED
+#define PSB_FP_SQR_DEDICATED 1     // 0: squares through the general product (A/B builds)
+#endif
+#if PSB_FP_SQR_DEDICATED
+__device__ PSB_INL void fp_sqr(Fp& r, const Fp& a) { cios::sqr(r.v, a.v); }
+#else
 __device__ PSB_INL void fp_sqr(Fp& r, const Fp& a) { cios::mul(r.v, a.v, a.v); }
+#endif
 __device__ PSB_INL void fp_dot2(Fp& r, const Fp& a, const Fp& b, const Fp& c, const Fp& d) { cios::dot2(r.v, a.v, b.v, c.v, d.v); }
 #else
 // host build (tests/hostsim only): same values through the generic product-scanning code

@@ -29,7 +29,10 @@ constexpr int kBlock = PSB_BLOCK;
 #define PSB_PAIR_BLOCK 512
 #endif
 constexpr int kPairBlock = PSB_PAIR_BLOCK;
-#define PSB_PAIR_BOUNDS __launch_bounds__(kPairBlock, 512 / kPairBlock)
+#ifndef PSB_PAIR_MINB
+#define PSB_PAIR_MINB (512 / PSB_PAIR_BLOCK)   // 128 registers per thread at any block size; 1 with 256-thread blocks lets ptxas use up to 255
+#endif
+#define PSB_PAIR_BOUNDS __launch_bounds__(kPairBlock, PSB_PAIR_MINB)
 // protocol kernels (EL PASSO NIZK steps, issuance, prover side): 128-thread blocks
 #ifndef PSB_PROTO_MINB
 #define PSB_PROTO_BOUNDS __launch_bounds__(kBlock)
@@ -148,6 +151,25 @@ __global__ void __launch_bounds__(256) k_bench_mad(int kind, int iters, const ui
     }
     unsigned long long s = 0;
     for (int j = 0; j < 13; j++) s ^= acc[j];
+    if (s == 0xdeadbeefull) sink[0] = (uint32_t)s;
+  } else if (kind == 10 || kind == 11) {
+    // carry-free wide MACs that ptxas cannot fold: 16 independent 64-bit accumulators, a DISTINCT multiplicand per
+    // accumulator (kind 10: shared multiplier b, the operand pattern of a multiplier row; kind 11: distinct multiplier
+    // too).  (Kind 5 shares BOTH factors across its accumulators and ptxas turns it into ONE IMAD.WIDE plus 64-bit
+    // additions per trip -- checked in SASS -- so it measures the adder, not the multiplier: not a MAC peak.)
+    unsigned long long acc[16];
+    uint32_t av[16], cv[16];
+    for (int j = 0; j < 16; j++) { acc[j] = ((unsigned long long)seed[j] << 32) | (seed[16 + j] ^ t); av[j] = seed[j + 5] * (t | 1) + j; cv[j] = seed[j + 9] ^ (t * 2654435761u) ^ j; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        if (kind == 10) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(av[j]), "r"(b));
+        else asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(av[j]), "r"(cv[j]));
+      }
+      b += (uint32_t)acc[0];
+    }
+    unsigned long long s = 0;
+    for (int j = 0; j < 16; j++) s ^= acc[j];
     if (s == 0xdeadbeefull) sink[0] = (uint32_t)s;
   } else {
     // plain 32-bit IMAD (lo only), 16 independent chains

@@ -105,8 +105,23 @@ PSB_HD PSB_INL const Fp* fp2_comp(const Fp2& x, int k) { return &x.a + k; }
 #ifndef PSB_LAZY_Y
 #define PSB_LAZY_Y 1
 #endif
+// Engine A comes in two forms (PSB_ENGINE_A_LAZY):
+//   0 (default)  the fused two-product form: one reduction per row inside the multiplier, 4 N^2 + 2 (N^2 + N) wide MACs
+//                (888 for N = 12), one multiplier body executed twice (11.5 KB of code).
+//   1            Karatsuba over i with LAZY REDUCTION (the shape of mcl's Fp2Dbl::mulPre + FpDbl::mod, fp_tower.hpp:713-757):
+//                three wide products T0 = xa ya, T1 = xb yb, T2 = (xa + xb)(ya + yb), then re = T0 - T1 (+ pR on
+//                borrow), im = T2 - T0 - T1, and two stand-alone Montgomery reductions: 3 N^2 + 2 (N^2 + N) wide MACs (744).
+//                Bit-identical results (74 GPU parity tests green) but SLOWER on B200 (r2a, profiles/r2a_ab_lazy_engine.txt):
+//                Miller loop 381.6 -> 422.6 ms per 2^20 lanes.  The 144 saved wide MACs cost ~190 extra additions and 5.5 KB
+//                more straight-line code (17 KB): instruction-fetch stalls 0.54 -> 2.40 cycles per issue, multiply-pipe
+//                active cycles 81 % -> 67 %.  Rolling the three products back into one body costs as many SEL / MOV as
+//                it saves (15.8 KB).  Kept as an A/B build only; what mcl gains on x86 (cheap adds, deep caches) does
+//                not transfer.  Bounds of this form are checked on the interpreted rows in tests/test_cios_model.py.
+#ifndef PSB_ENGINE_A_LAZY
+#define PSB_ENGINE_A_LAZY 0
+#endif
 __device__ PSB_NOINL void fp2_engine_a(Fp2& r, const Fp2* x1, const Fp2* x2, const Fp2* y1, const Fp2* y2) {
-  Fp xa, xb, ya, yb, u, nb, re;
+  Fp xa, xb, ya, yb, u;
   fp_get(xa, x1->a); fp_get(xb, x1->b); fp_get(ya, y1->a); fp_get(yb, y1->b);
   if (x2) {
     fp_get(u, x2->a); fp_addnr_rr(xa, xa, u);     // multiplicand side: unreduced (< 2p)
@@ -114,18 +129,43 @@ __device__ PSB_NOINL void fp2_engine_a(Fp2& r, const Fp2* x1, const Fp2* x2, con
 #if PSB_IS_BN || !PSB_LAZY_Y
     fp_get(u, y2->a); fp_add_rr(ya, ya, u);       // multiplier side: canonical
     fp_get(u, y2->b); fp_add_rr(yb, yb, u);
-  }
-  fp_pminus_rr(nb, yb);
 #else
-    // 381-bit p in a 384-bit radix: with all four operands < 2p the accumulated pair of products is <= 8 p^2 and
-    // (8 p^2 + R p) / R = p (1 + 8 p / R) < 1.82 p, so the ONE conditional subtraction of the reduction still lands in
-    // [0, p) and the sums on the multiplier side need no reduction either (BN254: 8 p / R > 1, stays canonical)
+    // 381-bit p in a 384-bit radix: the multiplier side may stay unreduced too.  Fused form: the accumulated pair of
+    // products is <= 8 p^2 and (8 p^2 + R p) / R = p (1 + 8 p / R) < 1.82 p, so the ONE conditional subtraction of the
+    // reduction still lands in [0, p) (BN254: 8 p / R > 1, stays canonical)
     fp_get(u, y2->a); fp_addnr_rr(ya, ya, u);
     fp_get(u, y2->b); fp_addnr_rr(yb, yb, u);
-    fp_2pminus_rr(nb, yb);
-  } else {
-    fp_pminus_rr(nb, yb);
+#endif
   }
+#if PSB_ENGINE_A_LAZY
+  uint32_t T0[2 * PSB_NL], T1[2 * PSB_NL], T2[2 * PSB_NL];
+  Fp sa, sb;
+  add_n<PSB_NL>(sa.v, xa.v, xb.v);                // Karatsuba sums, < 4p < R
+  add_n<PSB_NL>(sb.v, ya.v, yb.v);
+  cios::mulpre_rr(T0, xa.v, ya.v);
+  cios::chain_after(yb.v[0]);
+  cios::mulpre_rr(T1, xb.v, yb.v);
+  cios::chain_after(sb.v[0]);
+  cios::mulpre_rr(T2, sa.v, sb.v);
+  sub_n<2 * PSB_NL>(T2, T2, T0);
+  sub_n<2 * PSB_NL>(T2, T2, T1);                  // im = xa yb + xb ya
+  const uint32_t borrow = sub_n<2 * PSB_NL>(T0, T0, T1);   // re = xa ya - xb yb, + pR when negative
+  add_mod_masked_n<FpT>(T0 + PSB_NL, T0 + PSB_NL, 0u - borrow);
+  // one reduction body, executed twice (instruction-cache budget, and the two reductions stay one after the other)
+  PSB_ROLL
+  for (int k = 0; k < 2; k++) {
+    uint32_t T[2 * PSB_NL];
+    PSB_UNROLL
+    for (int i = 0; i < 2 * PSB_NL; i++) T[i] = k == 0 ? T0[i] : T2[i];
+    cios::redc_rr(u.v, T);
+    fp_put(*fp2_comp(r, k), u);
+  }
+#else
+  Fp nb, re;
+#if PSB_IS_BN || !PSB_LAZY_Y
+  fp_pminus_rr(nb, yb);
+#else
+  if (x2) fp_2pminus_rr(nb, yb); else fp_pminus_rr(nb, yb);
 #endif
   // one multiplier body, executed twice (real, imaginary): half the code of two unrolled copies -- a 20 KB
   // straight-line engine still stalled ~25 % of its samples on instruction fetch (r1g)
@@ -136,6 +176,7 @@ __device__ PSB_NOINL void fp2_engine_a(Fp2& r, const Fp2* x1, const Fp2* x2, con
     fp_dot2_rr(re, xa, q, xb, t);
     fp_put(*fp2_comp(r, k), re);
   }
+#endif
 }
 __device__ PSB_NOINL void fp2_engine_b(Fp2& r, const Fp2* x1, const Fp2* x2, const Fp* k) {
   Fp m1, n1, m2, n2, u, re;

@@ -15,9 +15,11 @@ pkg = ge.load_package()
 pkg.init([0])
 SM = 148
 res = {"mad": [], "field": []}
-for kind, name, per_iter in [(6, "imad32 (mul.lo+add)", 16), (4, "mad.lo.cc+madc.hi (MAC32)", 8), (5, "mad.wide.u32 (MAC32)", 8),
+for kind, name, per_iter in [(6, "imad32 (mul.lo+add)", 16), (4, "mad.lo.cc+madc.hi (MAC32)", 8), (5, "mad.wide.u32 with BOTH factors shared: ptxas folds it into 1 IMAD.WIDE + 8 64-bit adds per trip -- NOT a MAC rate", 8),
                              (7, "carry-chained IMAD.WIDE.U32.X rows (CIOS form, MAC32)", 36),
-                             (8, "fma.rz.f64 (DFMA)", 8), (9, "mad.wide.u32 rows of 13 distinct limbs (radix-2^30 form, MAC)", 13)]:
+                             (8, "fma.rz.f64 (DFMA)", 8), (9, "mad.wide.u32 rows of 13 distinct limbs (radix-2^30 form, MAC)", 13),
+                             (10, "mad.wide.u32, 16 accumulators, distinct multiplicands, shared multiplier (carry-free MAC32, not foldable)", 16),
+                             (11, "mad.wide.u32, 16 accumulators, distinct multiplicands and multipliers (carry-free MAC32)", 16)]:
     for bps, thr in [(1, 256), (2, 256), (4, 256), (8, 256), (4, 128), (1, 128)]:
         iters = 20000
         ms = pkg.microbench(kind, SM * bps, thr, iters)
