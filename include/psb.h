@@ -37,6 +37,9 @@ typedef struct psb_key psb_key;
  * devices = CUDA ordinals to shard over (NULL/0 -> device 0 only).  One host worker thread and
  * one stream per device; no inter-device communication. */
 int psb_init(int curve, const int* devices, int ndev);
+/* Releases every device resource, INCLUDING the device memory of keys that are still alive: such keys become dead
+ * handles (every call with one fails with PSB_ERR_ARG; psb_key_destroy stays valid and frees the host object).
+ * psb_init on an initialised library is psb_shutdown + init; a failed psb_init leaves the library shut down. */
 void psb_shutdown(void);
 int psb_num_devices(void);
 const char* psb_last_error(void);
@@ -116,15 +119,46 @@ int psb_provide_id(psb_key* key, size_t N, const uint64_t* A, const uint64_t* c,
                    const uint8_t* ad_blob, const uint64_t* ad_off, const uint64_t* u,
                    uint8_t* verdict, uint64_t* sig1, uint64_t* sig2, uint8_t* ser);
 
-/* Batched PSVerifier::el_passo_verify_id (src/ps-verifier.cc:37-138; with_id = 1) and
- * el_passo_verify_id_without_id_retrieval (:140-212; with_id = 0, E1/E2/y/g/h ignored).
- * service_pt = hashAndMapToG1(service_name), one value per batch computed by the host. */
+/* Batched PSSigner::sign_commitment (src/ps-signer.cc:132-146; n_attrs = 0) and PSSigner::sign_hybrid (:112-130; n_attrs =
+ * the length of the attribute list, <= the key's, "" = committed attribute; a ONE-entry list is signed as a bare
+ * commitment exactly like the reference does, :114-116):  sig = (u*g, u*(X + commitment + sum H(attr_i) Y_i)) with
+ * host-supplied u (N Fr, Montgomery), NORMALISED; ser optional (N x 2 compressed G1).  Needs a key created with X_secret. */
+int psb_sign(psb_key* key, size_t N, const uint64_t* commitment, size_t n_attrs, const uint8_t* attr_blob,
+             const uint64_t* attr_off, const uint64_t* u, uint64_t* sig1, uint64_t* sig2, uint8_t* ser);
+
+/* flags of the sign-on verification entry points */
+#define PSB_VID_WITH_ID 1            /* el_passo_verify_id; clear = el_passo_verify_id_without_id_retrieval */
+#define PSB_VID_REJECT_ZERO_SIGMA 2  /* STRICT: also reject sigma1 == 0.  The reference's el_passo_verify_id has no such
+                                      * check (unlike PSVerifier::verify, src/ps-verifier.cc:16-18): a proof with sigma1 =
+                                      * sigma2 = 0 and an honestly built k and NIZK passes there because e(0, K) = e(0, gg) = 1
+                                      * -- a sign-on without a credential.  Clear = bit-exact reference verdicts. */
+
+/* Batched PSVerifier::el_passo_verify_id (src/ps-verifier.cc:37-138; PSB_VID_WITH_ID) and
+ * el_passo_verify_id_without_id_retrieval (:140-212; E1/E2/y/g/h ignored).
+ * service_pt = hashAndMapToG1(service_name), one value per batch computed by the host.
+ * flags = PSB_VID_* bits (0 / 1 keep their round-1 meaning of with_id). */
 int psb_verify_id(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* sig2, const uint64_t* k,
                   const uint64_t* phi, const uint64_t* E1, const uint64_t* E2, const uint64_t* c,
                   const uint64_t* rs, size_t rs_per_lane, const uint8_t* attr_blob,
                   const uint64_t* attr_off, const uint8_t* ad_blob, const uint64_t* ad_off,
                   const uint64_t* service_pt, const uint64_t* y, const uint64_t* g, const uint64_t* h,
-                  int with_id, uint8_t* verdict);
+                  int flags, uint8_t* verdict);
+
+/* ---- wire-format ingest on the device.  Lane j = buf[buf_off[j] .. buf_off[j+1]): the bytes of
+ * IdProof::toBufferString() (src/ps-encoding.cc:452-468) resp. PSCredRequest::toBufferString() (:429-439), or with
+ * base64 != 0 their base64 text (PSBuffer::toBase64 / fromBase64, :111-122, decoder :56-96).  The TLV walk (:124-162,
+ * :178-256, :332-384, :441-450, :470-489), base64 decoding and the decompression of every point run on the GPU; the lanes
+ * then go through the same kernels as psb_verify_id / psb_provide_id, so a lane may carry any number of responses.
+ * parsed[j] (optional) = 1 iff the buffer is a well-formed message whose points and scalars mcl's deserialize accepts and
+ * whose attribute list has the key's length; other lanes get verdict 0 -- the reference either throws (short buffer),
+ * walks on with an uninitialised object (wrong type byte) or ignores the failed deserialize and verifies a point that
+ * is not on the curve; none of these can end in `true`.  A proof without E1/E2 fails PSB_VID_WITH_ID. ---- */
+int psb_verify_id_ser(psb_key* key, size_t N, const uint8_t* buf, const uint64_t* buf_off, int base64,
+                      const uint8_t* ad_blob, const uint64_t* ad_off, const uint64_t* service_pt, const uint64_t* y,
+                      const uint64_t* g, const uint64_t* h, int flags, uint8_t* verdict, uint8_t* parsed);
+int psb_provide_id_ser(psb_key* key, size_t N, const uint8_t* buf, const uint64_t* buf_off, int base64,
+                       const uint8_t* ad_blob, const uint64_t* ad_off, const uint64_t* u, uint8_t* verdict,
+                       uint64_t* sig1, uint64_t* sig2, uint8_t* ser, uint8_t* parsed);
 
 /* ---- prover side.  The reference draws its blinding / commitment scalars from mcl's CSPRNG;
  * the batch entries take them from the host, per lane, IN THE REFERENCE'S DRAW ORDER, so the same scalars reproduce the

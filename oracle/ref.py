@@ -490,3 +490,96 @@ def verify_id(key, proof, attrs, ads, service: bytes, y, g, h, with_id=True, nth
                         C.c_char_p(service), _p(_u64(y)), _p(_u64(g)), _p(_u64(h)),
                         C.c_int(int(with_id)), _p(verdict), C.c_int(nthreads))
     return verdict
+
+
+# ---- wire formats (src/ps-encoding.cc): IdProof / PSCredRequest through the reference's own encoder and parser ----------
+def idproof_encode(key, proof, attrs, with_e=True, base64=False):
+    """IdProof::toBufferString (or its base64 text) of every lane -> packed (blob uint8, off uint64[N+1])."""
+    N = proof["sig1"].shape[0]
+    blob, off = pack_attrs(attrs)
+    rs = _u64(proof["rs"]).reshape(N, -1, FR)
+    cap = N * (16 * G1 * 8 + rs.shape[1] * 40 + 64) * 2 + int(off[-1]) * 2 + 4 * len(off) + 1024
+    out = np.zeros(cap, dtype=np.uint8)
+    ooff = np.zeros(N + 1, dtype=np.uint64)
+    lib().ref_idproof_encode.restype = C.c_size_t
+    used = lib().ref_idproof_encode(C.c_size_t(N), C.c_size_t(key.n), _p(_u64(proof["sig1"])), _p(_u64(proof["sig2"])),
+                                    _p(_u64(proof["k"])), _p(_u64(proof["phi"])), _p(_u64(proof["E1"])), _p(_u64(proof["E2"])),
+                                    _p(_u64(proof["c"])), _p(rs), C.c_size_t(rs.shape[1]), _p(blob), _p(off),
+                                    C.c_int(int(with_e)), C.c_int(int(base64)), _p(out), _p(ooff), C.c_size_t(cap))
+    assert used and used == int(ooff[-1])
+    return out[:used + 8].copy(), ooff
+
+
+def request_encode(key, A, c, rs, attrs, base64=False):
+    """PSCredRequest::toBufferString (or base64) of every lane -> packed (blob, off)."""
+    N = A.shape[0]
+    blob, off = pack_attrs(attrs)
+    rs = _u64(rs).reshape(N, -1, FR)
+    cap = N * (4 * G1 * 8 + rs.shape[1] * 40 + 64) * 2 + int(off[-1]) * 2 + 4 * len(off) + 1024
+    out = np.zeros(cap, dtype=np.uint8)
+    ooff = np.zeros(N + 1, dtype=np.uint64)
+    lib().ref_request_encode.restype = C.c_size_t
+    used = lib().ref_request_encode(C.c_size_t(N), C.c_size_t(key.n), _p(_u64(A)), _p(_u64(c)), _p(rs), C.c_size_t(rs.shape[1]),
+                                    _p(blob), _p(off), C.c_int(int(base64)), _p(out), _p(ooff), C.c_size_t(cap))
+    assert used and used == int(ooff[-1])
+    return out[:used + 8].copy(), ooff
+
+
+def verify_id_wire(key, wire, ads, service: bytes, y, g, h, with_id=True, base64=False, nthreads=1):
+    """IdProof::fromBufferString + el_passo_verify_id on every lane -> (verdict, status); status 1 = the reference threw."""
+    blob, off = wire
+    N = off.shape[0] - 1
+    ad_blob, ad_off = pack_strings(ads)
+    verdict = np.zeros(N, dtype=np.uint8)
+    status = np.zeros(N, dtype=np.uint8)
+    lib().ref_verify_id_wire(key.handle, C.c_size_t(N), _p(blob), _p(off), C.c_int(int(base64)), _p(ad_blob), _p(ad_off),
+                             C.c_char_p(service), _p(_u64(y)), _p(_u64(g)), _p(_u64(h)), C.c_int(int(with_id)),
+                             _p(verdict), _p(status), C.c_int(nthreads))
+    return verdict, status
+
+
+def idproof_decode(key, wire, rs_cap, base64=False):
+    """the fields IdProof::fromBufferString produces (dict of arrays) + per, has_e, status per lane."""
+    blob, off = wire
+    N = off.shape[0] - 1
+    o = dict(sig1=np.zeros((N, G1), np.uint64), sig2=np.zeros((N, G1), np.uint64), k=np.zeros((N, G2), np.uint64),
+             phi=np.zeros((N, G1), np.uint64), E1=np.zeros((N, G1), np.uint64), E2=np.zeros((N, G1), np.uint64),
+             c=np.zeros((N, FR), np.uint64), rs=np.zeros((N, rs_cap, FR), np.uint64))
+    per = np.zeros(N, dtype=np.int32)
+    has_e = np.zeros(N, dtype=np.uint8)
+    status = np.zeros(N, dtype=np.uint8)
+    lib().ref_idproof_decode(C.c_size_t(N), C.c_size_t(key.n), _p(blob), _p(off), C.c_int(int(base64)), _p(o["sig1"]), _p(o["sig2"]),
+                             _p(o["k"]), _p(o["phi"]), _p(o["E1"]), _p(o["E2"]), _p(o["c"]), _p(o["rs"]), C.c_size_t(rs_cap),
+                             _p(per), _p(has_e), _p(status))
+    return o, per, has_e, status
+
+
+def provide_id_wire(key, wire, ads, u, base64=False, nthreads=1):
+    blob, off = wire
+    N = off.shape[0] - 1
+    ad_blob, ad_off = pack_strings(ads)
+    verdict = np.zeros(N, dtype=np.uint8)
+    status = np.zeros(N, dtype=np.uint8)
+    s1 = np.zeros((N, G1), dtype=np.uint64)
+    s2 = np.zeros((N, G1), dtype=np.uint64)
+    ser = np.zeros((N, SZ2), dtype=np.uint8)
+    lib().ref_provide_id_wire(key.signer(), C.c_size_t(N), _p(blob), _p(off), C.c_int(int(base64)), _p(ad_blob), _p(ad_off),
+                              _p(_u64(u)), _p(verdict), _p(s1), _p(s2), _p(ser), _p(status), C.c_int(nthreads))
+    return verdict, s1, s2, ser, status
+
+
+def sign(key, commitment, attrs, u, nthreads=1):
+    """PSSigner::sign_hybrid (attrs: per lane na strings) or sign_commitment (attrs None) with the RandGen primed to u."""
+    Cm = _u64(commitment).reshape(-1, G1)
+    N = Cm.shape[0]
+    if attrs is None:
+        blob, off, na = np.zeros(8, dtype=np.uint8), np.zeros(1, dtype=np.uint64), 0
+    else:
+        blob, off = pack_attrs(attrs)
+        na = len(attrs[0]) if N else 0
+    s1 = np.zeros((N, G1), dtype=np.uint64)
+    s2 = np.zeros((N, G1), dtype=np.uint64)
+    ser = np.zeros((N, SZ2), dtype=np.uint8)
+    lib().ref_sign(key.signer(), C.c_size_t(N), C.c_size_t(na), _p(Cm), _p(blob), _p(off), _p(_u64(u)), _p(s1), _p(s2), _p(ser),
+                   C.c_int(nthreads))
+    return s1, s2, ser

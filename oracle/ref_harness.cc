@@ -512,6 +512,132 @@ void ref_verify_id(void* key, size_t N, size_t n, const G1* sig1, const G1* sig2
   });
 }
 
+// ---- the reference's wire formats (src/ps-encoding.cc): IdProof / PSCredRequest -> toBufferString [-> toBase64] and back --
+// Encoders return the bytes used (0 = cap too small); lane j's message is out[out_off[j] .. out_off[j+1]).
+static size_t put_wire(PSBuffer& b, int base64, uint8_t* out, u64* out_off, size_t i, size_t used, size_t cap) {
+  std::string t;
+  const uint8_t* src = b.data();
+  size_t len = b.size();
+  if (base64) { t = b.toBase64(); src = (const uint8_t*)t.data(); len = t.size(); }
+  if (used + len > cap) return 0;
+  memcpy(out + used, src, len);
+  out_off[i + 1] = used + len;
+  return len;
+}
+size_t ref_idproof_encode(size_t N, size_t n, const G1* sig1, const G1* sig2, const G2* kk, const G1* phi, const G1* E1,
+                          const G1* E2, const Fr* c, const Fr* rs, size_t rs_per_lane, const uint8_t* blob, const u64* off,
+                          int with_e, int base64, uint8_t* out, u64* out_off, size_t cap) {
+  size_t used = 0;
+  out_off[0] = 0;
+  for (size_t i = 0; i < N; i++) {
+    IdProof p; p.sig1 = sig1[i]; p.sig2 = sig2[i]; p.k = kk[i]; p.phi = phi[i]; p.c = c[i];
+    if (with_e) { p.E1 = E1[i]; p.E2 = E2[i]; }
+    p.rs.assign(rs + i * rs_per_lane, rs + (i + 1) * rs_per_lane);
+    p.attributes = lane_attrs(blob, off, i, n);
+    PSBuffer b = p.toBufferString();
+    const size_t len = put_wire(b, base64, out, out_off, i, used, cap);
+    if (!len) return 0;
+    used += len;
+  }
+  return used;
+}
+size_t ref_request_encode(size_t N, size_t n, const G1* A, const Fr* c, const Fr* rs, size_t rs_per_lane, const uint8_t* blob,
+                          const u64* off, int base64, uint8_t* out, u64* out_off, size_t cap) {
+  size_t used = 0;
+  out_off[0] = 0;
+  for (size_t i = 0; i < N; i++) {
+    PSCredRequest r; r.A = A[i]; r.c = c[i];
+    r.rs.assign(rs + i * rs_per_lane, rs + (i + 1) * rs_per_lane);
+    r.attributes = lane_attrs(blob, off, i, n);
+    PSBuffer b = r.toBufferString();
+    const size_t len = put_wire(b, base64, out, out_off, i, used, cap);
+    if (!len) return 0;
+    used += len;
+  }
+  return used;
+}
+static PSBuffer take_wire(const uint8_t* buf, const u64* off, size_t i, int base64) {
+  if (base64) return PSBuffer::fromBase64(std::string((const char*)buf + off[i], (size_t)(off[i + 1] - off[i])));
+  PSBuffer b; b.assign(buf + off[i], buf + off[i + 1]);
+  return b;
+}
+// IdProof::fromBufferString + el_passo_verify_id[_without_id_retrieval] on every lane.  status: 0 = the reference ran
+// to completion, 1 = it threw (PSBuffer::at on a short buffer, std::length_error, bad optional access ...): verdict 0.
+// NOTE the reference ignores failed deserializations and wrong type bytes: on such lanes it verifies an
+// object that is partly uninitialised -- its verdict is recorded but only `false` can be relied on.
+void ref_verify_id_wire(void* key, size_t N, const uint8_t* buf, const u64* off, int base64, const uint8_t* ad_blob,
+                        const u64* ad_off, const char* service, const G1* y, const G1* g, const G1* h, int with_id,
+                        uint8_t* verdict, uint8_t* status, int nthreads) {
+  RefKey* k = (RefKey*)key;
+  PSVerifier v(k->pk);
+  std::string svc(service);
+  par_for(N, nthreads, [&](size_t i, int) {
+    verdict[i] = 0; status[i] = 0;
+    try {
+      PSBuffer b = take_wire(buf, off, i, base64);
+      IdProof p = IdProof::fromBufferString(b);
+      std::string ad((const char*)ad_blob + ad_off[i], (size_t)(ad_off[i + 1] - ad_off[i]));
+      verdict[i] = (with_id ? v.el_passo_verify_id(p, ad, svc, *y, *g, *h)
+                            : v.el_passo_verify_id_without_id_retrieval(p, ad, svc)) ? 1 : 0;
+    } catch (...) { status[i] = 1; }
+  });
+}
+// the parsed fields of well-formed IdProof buffers (checks our device parser field by field); E1/E2 zero when absent
+void ref_idproof_decode(size_t N, size_t n, const uint8_t* buf, const u64* off, int base64, G1* sig1, G1* sig2, G2* kk, G1* phi,
+                        G1* E1, G1* E2, Fr* c, Fr* rs, size_t rs_cap, int* per, uint8_t* has_e, uint8_t* status) {
+  for (size_t i = 0; i < N; i++) {
+    status[i] = 0; per[i] = 0; has_e[i] = 0;
+    E1[i].clear(); E2[i].clear();
+    try {
+      IdProof p = IdProof::fromBufferString(take_wire(buf, off, i, base64));
+      sig1[i] = p.sig1; sig2[i] = p.sig2; kk[i] = p.k; phi[i] = p.phi; c[i] = p.c;
+      per[i] = (int)p.rs.size();
+      for (size_t j = 0; j < p.rs.size() && j < rs_cap; j++) rs[i * rs_cap + j] = p.rs[j];
+      if (p.E1.has_value() && p.E2.has_value()) { has_e[i] = 1; E1[i] = *p.E1; E2[i] = *p.E2; }
+      if (p.attributes.size() != n) status[i] = 2;
+    } catch (...) { status[i] = 1; }
+  }
+}
+// PSCredRequest::fromBufferString + el_passo_provide_id with the caller's u (see ref_provide_id)
+void ref_provide_id_wire(void* signer, size_t N, const uint8_t* buf, const u64* off, int base64, const uint8_t* ad_blob,
+                         const u64* ad_off, const Fr* u, uint8_t* verdict, G1* sig1, G1* sig2, uint8_t* ser, uint8_t* status,
+                         int nthreads) {
+  RefSigner* s = (RefSigner*)signer;
+  mcl::fp::RandGen::setRandFunc(nullptr, inject_read);
+  par_for(N, nthreads, [&](size_t i, int) {
+    verdict[i] = 0; status[i] = 0;
+    PSCredential out; out.sig1.clear(); out.sig2.clear();
+    try {
+      PSCredRequest r = PSCredRequest::fromBufferString(take_wire(buf, off, i, base64));
+      std::string ad((const char*)ad_blob + ad_off[i], (size_t)(ad_off[i + 1] - ad_off[i]));
+      uint8_t ub[32]; u[i].serialize(ub, 32);
+      g_inject = ub; g_inject_left = 32;
+      verdict[i] = s->s->el_passo_provide_id(r, ad, out) ? 1 : 0;
+    } catch (...) { status[i] = 1; }
+    g_inject_left = 0;
+    sig1[i] = out.sig1; sig2[i] = out.sig2;
+    out.sig1.serialize(ser + SZ2 * i, SZ1);
+    out.sig2.serialize(ser + SZ2 * i + SZ1, SZ1);
+  });
+  mcl::fp::RandGen::setRandFunc(nullptr, det_read);
+}
+// PSSigner::sign_hybrid (na attributes per lane; na = 0: sign_commitment) with the caller's u
+void ref_sign(void* signer, size_t N, size_t na, const G1* commitment, const uint8_t* blob, const u64* off, const Fr* u,
+              G1* sig1, G1* sig2, uint8_t* ser, int nthreads) {
+  RefSigner* s = (RefSigner*)signer;
+  mcl::fp::RandGen::setRandFunc(nullptr, inject_read);
+  par_for(N, nthreads, [&](size_t i, int) {
+    uint8_t ub[32]; u[i].serialize(ub, 32);
+    g_inject = ub; g_inject_left = 32;
+    PSCredential out = na ? s->s->sign_hybrid(commitment[i], lane_attrs(blob, off, i, na)) : s->s->sign_commitment(commitment[i]);
+    g_inject_left = 0;
+    sig1[i] = out.sig1; sig2[i] = out.sig2;
+    out.sig1.serialize(ser + SZ2 * i, SZ1);
+    out.sig2.serialize(ser + SZ2 * i + SZ1, SZ1);
+  });
+  mcl::fp::RandGen::setRandFunc(nullptr, det_read);
+}
+
 // timed loop of the reference's own PSVerifier::verify for the CPU baseline: runs lanes
 // [0, N) once on nthreads threads, returns seconds.
 double ref_time_ps_verify(void* key, size_t N, size_t n, const G1* sig1, const G1* sig2,

@@ -11,6 +11,7 @@
 #include "protocol.cuh"
 #include "prover.cuh"
 #include "hash_to_curve.cuh"
+#include "wire.cuh"
 
 namespace psb {
 
@@ -409,8 +410,19 @@ __global__ void __launch_bounds__(kBlock) k_g2_deserialize(size_t N, const uint8
 }
 
 // ---- PSSigner::el_passo_provide_id (src/ps-signer.cc:63-146) -------------------------------------------
+// Lane geometry shared by the EL PASSO kernels: lane j reads its responses at rs + j * rs_stride, `per` of them
+// (per_lane[j] when the counts come from parsed wire buffers, else the batch's `per`), and its attribute offsets at
+// off + j * off_stride (n entries + the end: stride n for a packed batch whose lanes share boundaries, n + 1 for
+// parsed buffers).  pre (optional): verdict of an earlier step (the wire parser) that is ANDed in.
+struct LaneGeom {
+  int per, rs_stride, off_stride;
+  const int* per_lane;
+  const uint8_t* pre;
+  PSB_HD int count(size_t lane) const { return per_lane ? per_lane[lane] : per; }
+  PSB_HD bool pre_ok(size_t lane) const { return pre ? pre[lane] != 0 : true; }
+};
 __global__ void PSB_PROTO_BOUNDS k_provide_id(size_t N, int n, int w, const G1A* tblG1, const G1J* g1pts,
-                                                        const G1J* A, const Fr* c, const Fr* rs, int per,
+                                                        const G1J* A, const Fr* c, const Fr* rs, LaneGeom lg,
                                                         const uint8_t* blob, const uint64_t* off, const uint8_t* ad_blob,
                                                         const uint64_t* ad_off, const Fr* u, uint8_t* verdict, G1J* sig1,
                                                         G1J* sig2, uint8_t* ser) {
@@ -418,9 +430,27 @@ __global__ void PSB_PROTO_BOUNDS k_provide_id(size_t N, int n, int w, const G1A*
   if (lane >= N) return;
   G1J s1, s2;
   const TblGeom tg{w};
-  const bool ok = provide_id_lane(n, tg, tblG1, g1pts[1], A[lane], c + lane, rs + lane * per, per, blob, off + lane * n,
-                                  ad_blob + ad_off[lane], (size_t)(ad_off[lane + 1] - ad_off[lane]), u + lane, s1, s2);
+  bool ok = provide_id_lane(n, tg, tblG1, g1pts[1], A[lane], c + lane, rs + lane * lg.rs_stride, lg.count(lane), blob,
+                            off + lane * lg.off_stride, ad_blob + ad_off[lane], (size_t)(ad_off[lane + 1] - ad_off[lane]),
+                            u + lane, s1, s2);
+  if (!lg.pre_ok(lane)) { ok = false; pt_set_zero(s1); pt_set_zero(s2); }
   verdict[lane] = ok ? 1 : 0;
+  sig1[lane] = s1;
+  sig2[lane] = s2;
+  if (ser) {
+    g1_serialize_norm(ser + lane * 2 * kFpBytes, s1);
+    g1_serialize_norm(ser + lane * 2 * kFpBytes + kFpBytes, s2);
+  }
+}
+
+// ---- PSSigner::sign_commitment / sign_hybrid (src/ps-signer.cc:112-146), u host-supplied ------------------------
+__global__ void PSB_PROTO_BOUNDS k_sign(size_t N, int na, int w, const G1A* tblG1, const G1J* g1pts, const G1J* C,
+                                                  const uint8_t* blob, const uint64_t* off, const Fr* u, G1J* sig1, G1J* sig2,
+                                                  uint8_t* ser) {
+  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= N) return;
+  G1J s1, s2;
+  sign_lane(na, TblGeom{w}, tblG1, g1pts[1], C[lane], blob, off ? off + lane * na : nullptr, u + lane, s1, s2);
   sig1[lane] = s1;
   sig2[lane] = s2;
   if (ser) {
@@ -432,27 +462,27 @@ __global__ void PSB_PROTO_BOUNDS k_provide_id(size_t N, int n, int w, const G1A*
 // ---- PSVerifier::el_passo_verify_id (src/ps-verifier.cc:37-212): NIZK steps; the pairing check reuses
 //      k_verify_miller / k_verify_final with K from step 1 ------------------------------------------------
 __global__ void PSB_PROTO_BOUNDS k_vid_g2(size_t N, int n, int w, const G2A* tblYY, const G2A* tblAux, const G2J* k,
-                                                    const Fr* c, const Fr* rs, int per, int with_id, const uint8_t* blob,
+                                                    const Fr* c, const Fr* rs, LaneGeom lg, int with_id, const uint8_t* blob,
                                                     const uint64_t* off, G2J* Vk, G2J* K, uint8_t* ok) {
   const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (lane >= N) return;
   G2J vk, kk;
   const TblGeom tg{w};
-  const bool r = verify_id_g2_lane(n, tg, tblYY, tblAux, k[lane], c + lane, rs + lane * per, per, with_id, blob,
-                                   off + lane * n, vk, kk);
+  const bool r = verify_id_g2_lane(n, tg, tblYY, tblAux, k[lane], c + lane, rs + lane * lg.rs_stride, lg.count(lane), with_id,
+                                   blob, off + lane * lg.off_stride, vk, kk);
   Vk[lane] = vk;
   K[lane] = kk;
-  ok[lane] = r ? 1 : 0;
+  ok[lane] = (r && lg.pre_ok(lane)) ? 1 : 0;
 }
 __global__ void PSB_PROTO_BOUNDS k_vid_g1(size_t N, int wb, const G1A* tblB, const G1J* phi, const G1J* E1,
-                                                    const G1J* E2, const Fr* c, const Fr* rs, int per, int with_id,
+                                                    const G1J* E2, const Fr* c, const Fr* rs, LaneGeom lg, int with_id,
                                                     G1J* V /*3 per lane*/) {
   const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (lane >= N) return;
   G1J a, b, d;
   const TblGeom tb{wb};
   verify_id_g1_lane(tb, tblB, phi[lane], with_id ? E1 + lane : nullptr, with_id ? E2 + lane : nullptr, c + lane,
-                    rs + lane * per, per, with_id, a, b, d);
+                    rs + lane * lg.rs_stride, lg.count(lane), with_id, a, b, d);
   V[3 * lane] = a; V[3 * lane + 1] = b; V[3 * lane + 2] = d;
 }
 __global__ void PSB_PROTO_BOUNDS k_vid_hash(size_t N, const G2J* k, const G1J* phi, const G1J* E1, const G1J* E2,
@@ -465,6 +495,67 @@ __global__ void PSB_PROTO_BOUNDS k_vid_hash(size_t N, const G2J* k, const G1J* p
                                      Vk[lane], V[3 * lane], V[3 * lane + 1], V[3 * lane + 2], with_id, c + lane,
                                      ad_blob + ad_off[lane], (size_t)(ad_off[lane + 1] - ad_off[lane]));
   ok[lane] = r ? 1 : 0;
+}
+
+// ---- wire-format ingest (csrc/wire.cuh) ------------------------------------------------------------
+// lane j's text is in[off[j] .. off[j+1]); the decoded bytes go to out + off[j] (never longer than the text)
+__global__ void __launch_bounds__(kBlock) k_wire_base64(size_t N, const uint8_t* in, const uint64_t* off, uint8_t* out, uint32_t* out_len) {
+  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= N) return;
+  out_len[lane] = (uint32_t)base64_decode_lane(out + off[lane], in + off[lane], (size_t)(off[lane + 1] - off[lane]));
+}
+// kind 0: IdProof, 1: PSCredRequest.  len (optional) = decoded lengths after k_wire_base64.  Outputs per lane: pos[W_SLOTS],
+// c, rs[n + 2], per, the attribute strings copied to attr_blob + off[j] with attr_off[j * (n + 1) ..] absolute offsets,
+// parsed (structure ok) and has_e.
+__global__ void __launch_bounds__(kBlock) k_wire_parse(size_t N, int n, int kind, const uint8_t* buf, const uint64_t* off,
+                                                        const uint32_t* len, uint32_t* pos, Fr* c, Fr* rs, int* per,
+                                                        uint8_t* attr_blob, uint64_t* attr_off, uint8_t* parsed, uint8_t* has_e) {
+  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= N) return;
+  const size_t l = len ? len[lane] : (size_t)(off[lane + 1] - off[lane]);
+  Fr cc;
+  for (int i = 0; i < 8; i++) cc.v[i] = 0;
+  int p = 0;
+  bool he = false;
+  const bool ok = kind == 0
+      ? parse_idproof_lane(buf + off[lane], l, n, pos + lane * W_SLOTS, cc, rs + lane * (n + 2), p, attr_blob + off[lane],
+                           attr_off + lane * (n + 1), off[lane], he)
+      : parse_request_lane(buf + off[lane], l, n, pos + lane * W_SLOTS, cc, rs + lane * (n + 2), p, attr_blob + off[lane],
+                           attr_off + lane * (n + 1), off[lane]);
+  c[lane] = cc;
+  per[lane] = p;
+  parsed[lane] = ok ? 1 : 0;
+  has_e[lane] = he ? 1 : 0;
+}
+// decompression of every (lane, slot) pair, one thread each, slot-major so that a warp works on one kind of point:
+// slots 0..4 = G1 (sig1 / A, sig2, phi, E1, E2) into g1out[slot][lane], slot 5 = G2 (k).  An absent slot gives the zero point
+// and does not count as a failure; a payload mcl's deserialize would reject clears parsed[lane] (atomic AND through a byte store
+// of 0: every writer writes the same value).
+__global__ void __launch_bounds__(kBlock) k_and_flags(size_t N, uint8_t* a, const uint8_t* b) {
+  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane < N) a[lane] = (uint8_t)(a[lane] & b[lane]);
+}
+struct WireG1Out { G1J* p[5]; };
+__global__ void __launch_bounds__(kBlock) k_wire_points(size_t N, int nslots, const uint8_t* buf, const uint64_t* off, const uint32_t* pos,
+                                                         WireG1Out g1out, G2J* kout, uint8_t* parsed) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N * (size_t)nslots) return;
+  const int slot = (int)(t / N);
+  const size_t lane = t % N;
+  const uint32_t at = pos[lane * W_SLOTS + slot];
+  bool ok = true;
+  if (slot == W_K) {
+    G2J P;
+    pt_set_zero(P);
+    if (at != kWireAbsent) ok = g2_deserialize(P, buf + off[lane] + at);
+    kout[lane] = P;
+  } else {
+    G1J P;
+    pt_set_zero(P);
+    if (at != kWireAbsent) ok = g1_deserialize(P, buf + off[lane] + at);
+    g1out.p[slot][lane] = P;
+  }
+  if (!ok) parsed[lane] = 0;
 }
 
 // ---- prover side: PSRequester::el_passo_request_id / unblind_credential / el_passo_prove_id ----

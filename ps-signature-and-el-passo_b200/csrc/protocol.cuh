@@ -303,6 +303,30 @@ PSB_HD PSB_NOINL bool provide_id_lane(int n, TblGeom tg, const G1A* tblG1, const
   return ok;
 }
 
+// ---- PSSigner::sign_hybrid / sign_commitment, one lane (src/ps-signer.cc:112-146) ------------------------
+//   na = number of attribute strings of the call (0: sign_commitment; sign_hybrid signs a ONE-attribute list as a bare
+//   commitment, :114-116); "" = a committed attribute, skipped.  sig = (u g, u (X + C + sum H(attr_i) Y_i)), normalised.
+PSB_HD PSB_NOINL void sign_lane(int na, TblGeom tg, const G1A* tblG1, const G1J& X, const G1J& C, const uint8_t* blob,
+                                const uint64_t* off, const Fr* u_mont, G1J& sig1, G1J& sig2) {
+  const size_t pb = tg.per_base();
+  uint32_t k[8];
+  G1J Ap = C, T;
+  if (na != 1) {
+    for (int i = 0; i < na; i++) {
+      const uint64_t b = off[i], e = off[i + 1];
+      if (e == b) continue;
+      fr_set_hash_of(k, blob + b, (size_t)(e - b));
+      pt_fixed_mul_acc(Ap, tblG1 + (size_t)(1 + i) * pb, k, tg.w);
+    }
+  }
+  fr_load_normal(k, u_mont);
+  pt_set_zero(sig1);
+  pt_fixed_mul_acc(sig1, tblG1, k, tg.w);
+  pt_add(T, X, Ap);
+  pt_mul(sig2, T, k);
+  g1_normalize2(sig1, sig2);
+}
+
 // ---- PSVerifier::el_passo_verify_id, one lane, three steps ---------------------------------------------
 // step 1 (G2): V_k = c k + sum_hidden rs[cnt] YY_i + rs[gg_idx] gg + (1-c) XX   (ps-verifier.cc:72-88 / :166-182)
 //              K   = k + sum_plain H(attr_i) YY_i                                   (:214-229)

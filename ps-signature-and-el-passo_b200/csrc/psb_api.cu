@@ -53,6 +53,9 @@ struct Dev {
 
 std::vector<Dev*> g_devs;
 bool g_init = false;
+uint64_t g_epoch = 0;                  // bumped by every psb_init / psb_shutdown
+std::mutex g_keys_mu;
+std::vector<psb_key*> g_keys;          // live keys of the current context: psb_shutdown releases their device memory
 thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
 bool g_profile = false;
@@ -64,6 +67,7 @@ int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
   g_err = buf;
   return code;
 }
+inline bool key_dead(const psb_key* key);
 #define CK(call)                                                        \
   do {                                                                  \
     cudaError_t e_ = (call);                                            \
@@ -137,13 +141,30 @@ struct psb_key {
   int w = 16;
   bool hasX = false;
   size_t table_bytes = 0;
-  std::vector<KeyDev> d;
+  std::vector<KeyDev> d;                           // one entry per device of the context the key was created in
+  std::vector<int> ordinals;                       // CUDA ordinal of d[i] (the key does not index g_devs)
+  uint64_t epoch = 0;                              // psb_init generation; a key of an earlier context is dead
   std::mutex mu;                                   // lazy tables + batch-table cache
   bool haveG1 = false, haveAux = false;
   std::vector<std::shared_ptr<BatchTbl>> batch;    // FIFO, at most kBatchCache entries
 };
 
 namespace {
+inline bool key_dead(const psb_key* key) { return key->epoch != g_epoch || key->d.size() != g_devs.size(); }
+#define KEY_ALIVE(key) do { if (key_dead(key)) return fail(PSB_ERR_ARG, "the key belongs to a context that was shut down (psb_shutdown / psb_init)"); } while (0)
+// device memory of a key; the secret X = g^x (slot 1 of g1pts, and its window-table base) is overwritten before the free
+void key_release_device(psb_key* key) {
+  for (size_t i = 0; i < key->d.size(); i++) {
+    if (cudaSetDevice(key->ordinals[i]) != cudaSuccess) continue;
+    KeyDev& k = key->d[i];
+    if (key->hasX && k.g1pts) cudaMemset(k.g1pts + 1, 0, sizeof(G1J));
+    cudaFree(k.g1pts); cudaFree(k.g2pts); cudaFree(k.tblYY); cudaFree(k.tblAux); cudaFree(k.tblG1);
+    cudaFree(k.lines);
+    k = KeyDev();
+  }
+  key->batch.clear();
+  key->d.clear();
+}
 
 // run f(dev_index, lane_begin, lane_end) on every device over a contiguous split of [0, N)
 template <class Fn>
@@ -259,7 +280,8 @@ int psb_init(int curve, const int* devices, int ndev) {
 #else
   if (curve != PSB_MCL_CURVE) return fail(PSB_ERR_UNSUPPORTED, "this library (libpsb.so) is built for BLS12-381 (curve 5); BN254 is libpsb_bn254.so");
 #endif
-  if (g_init) psb_shutdown();
+  psb_shutdown();      // also clears a half-built device list of an earlier failed psb_init
+  struct Guard { bool ok = false; ~Guard() { if (!ok) psb_shutdown(); } } guard;
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0) return fail(PSB_ERR_CUDA, "no CUDA device (this library has no CPU path)", e);
@@ -273,6 +295,7 @@ int psb_init(int curve, const int* devices, int ndev) {
     if (g_devs.empty()) g_sms = prop.multiProcessorCount;
     Dev* d = new Dev();
     d->ordinal = o;
+    g_devs.push_back(d);                 // owned by the list from here on: the guard frees it if a later step fails
     CK(cudaSetDevice(o));
     CK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&d->copy, cudaStreamNonBlocking));
@@ -296,13 +319,21 @@ int psb_init(int curve, const int* devices, int ndev) {
       cudaFuncSetAttribute(k_pairing_miller, cudaFuncAttributePreferredSharedMemoryCarveout, l1);
       cudaFuncSetAttribute(k_final_exp, cudaFuncAttributePreferredSharedMemoryCarveout, l1);
     }
-    g_devs.push_back(d);
   }
   g_init = true;
+  guard.ok = true;
   return PSB_OK;
 }
 
 void psb_shutdown(void) {
+  {
+    // keys outlive the context only as dead handles: their device memory goes with the context, every later call with
+    // such a key fails with PSB_ERR_ARG, psb_key_destroy only frees the host object
+    std::lock_guard<std::mutex> lk(g_keys_mu);
+    for (psb_key* k : g_keys) key_release_device(k);
+    g_keys.clear();
+    g_epoch++;
+  }
   for (Dev* d : g_devs) {
     cudaSetDevice(d->ordinal);
     for (auto& b : d->in) if (b.p) cudaFree(b.p);
@@ -323,11 +354,10 @@ size_t psb_key_table_bytes(const psb_key* key) { return key ? key->table_bytes :
 
 void psb_key_destroy(psb_key* key) {
   if (!key) return;
-  for (size_t i = 0; i < key->d.size(); i++) {
-    cudaSetDevice(g_devs[i]->ordinal);
-    KeyDev& k = key->d[i];
-    cudaFree(k.g1pts); cudaFree(k.g2pts); cudaFree(k.tblYY); cudaFree(k.tblAux); cudaFree(k.tblG1);
-    cudaFree(k.lines);
+  {
+    std::lock_guard<std::mutex> lk(g_keys_mu);
+    auto it = std::find(g_keys.begin(), g_keys.end(), key);
+    if (it != g_keys.end()) { g_keys.erase(it); key_release_device(key); }   // else: psb_shutdown already released it
   }
   delete key;
 }
@@ -345,6 +375,9 @@ psb_key* psb_key_create(const uint64_t* g, const uint64_t* gg, const uint64_t* X
   psb_key* key = new psb_key();
   key->n = n; key->w = w; key->hasX = X_secret != nullptr;
   key->d.resize(g_devs.size());
+  for (Dev* dv : g_devs) key->ordinals.push_back(dv->ordinal);
+  key->epoch = g_epoch;
+  { std::lock_guard<std::mutex> lk(g_keys_mu); g_keys.push_back(key); }
   const int nwin = fixed_nwin(w);
   const size_t half = (size_t)1 << (w - 1);
   key->table_bytes = n * nwin * half * sizeof(G2A);
@@ -375,6 +408,10 @@ psb_key* psb_key_create(const uint64_t* g, const uint64_t* gg, const uint64_t* X
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { fail(PSB_ERR_CUDA, "key setup kernels", e); psb_key_destroy(key); return nullptr; }
   }
+  if (X_secret) {      // the staging copy of the secret does not linger on the host heap
+    volatile uint64_t* z = reinterpret_cast<volatile uint64_t*>(&h1[1]);
+    for (size_t i = 0; i < kG1W; i++) z[i] = 0;
+  }
   return key;
 }
 
@@ -388,6 +425,7 @@ int psb_verify_dev(psb_key* key, int dev_index, size_t N, const uint64_t* d_sig1
                    uint8_t* d_verdict, uint64_t* d_gt, void* d_ws, void* stream) {
   if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
   if (!key || dev_index < 0 || dev_index >= (int)g_devs.size()) return fail(PSB_ERR_ARG, "bad key/device");
+  KEY_ALIVE(key);
   if (!d_sig1 || !d_sig2 || !d_verdict || !d_ws || (!d_attr_blob && !d_m && key->n)) return fail(PSB_ERR_ARG, "null buffer");
   if (d_attr_blob && !d_attr_off) return fail(PSB_ERR_ARG, "attr_off missing");
   CK(cudaSetDevice(g_devs[dev_index]->ordinal));
@@ -400,6 +438,7 @@ int psb_verify(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* sig
                const uint64_t* attr_off, const uint64_t* m, uint8_t* verdict, uint64_t* gt) {
   if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
   if (!key || !sig1 || !sig2 || !verdict) return fail(PSB_ERR_ARG, "null argument");
+  KEY_ALIVE(key);
   if (key->n && !attr_blob && !m) return fail(PSB_ERR_ARG, "need attributes or scalars");
   if (attr_blob && !attr_off) return fail(PSB_ERR_ARG, "attr_off missing");
   const size_t n = key->n;
@@ -507,6 +546,7 @@ int psb_verify_ser(psb_key* key, size_t N, const uint8_t* cred, size_t stride, s
                    const uint8_t* attr_blob, const uint64_t* attr_off, uint8_t* verdict, uint8_t* decoded) {
   if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
   if (!key || !cred || !verdict || (key->n && (!attr_blob || !attr_off))) return fail(PSB_ERR_ARG, "null argument");
+  KEY_ALIVE(key);
   if (off1 + kG1Ser > stride || off2 + kG1Ser > stride) return fail(PSB_ERR_ARG, "offsets exceed the stride");
   const size_t n = key->n;
   return shard(N, [&](int di, size_t b, size_t e) -> int {
@@ -746,12 +786,37 @@ static int get_batch_tables(psb_key* key, const uint64_t* const pts[4], int nb, 
   return PSB_OK;
 }
 
+// ---- device-side cores shared by the object-array entry points and the wire-format ones --------------------------
+// sign-on verification of L lanes whose inputs are all on device `di`: NIZK steps, then the fused Miller loop and the
+// final exponentiation; dok carries an optional pre-verdict in and the NIZK verdict out; scratch from the arena.
+struct VidDev {
+  const G1J *S1, *S2, *phi, *E1, *E2; const G2J* k; const Fr *c, *rs;
+  const uint8_t* blob; const uint64_t* off; const uint8_t* ad; const uint64_t* adoff;
+  G2J *Vk, *K; G1J* V; Fp12* F; uint8_t *ok, *ver;
+};
+static int verify_id_core(psb_key* key, int di, size_t L, const VidDev& v, LaneGeom lg, int with_id, int strict,
+                          const BatchTbl& bt, cudaStream_t st) {
+  const KeyDev& kd = key->d[di];
+  k_vid_g2<<<nblocks(L), kBlock, 0, st>>>(L, (int)key->n, key->w, kd.tblYY, kd.tblAux, v.k, v.c, v.rs, lg, with_id, v.blob, v.off,
+                                          v.Vk, v.K, v.ok);
+  LAUNCHED();
+  k_vid_g1<<<nblocks(L), kBlock, 0, st>>>(L, kBatchW, bt.tbl[di], v.phi, v.E1, v.E2, v.c, v.rs, lg, with_id, v.V);
+  LAUNCHED();
+  k_vid_hash<<<nblocks(L), kBlock, 0, st>>>(L, v.k, v.phi, v.E1, v.E2, v.Vk, v.V, with_id, v.c, v.ad, v.adoff, v.ok);
+  LAUNCHED();
+  PSB_WAVES(L, k_verify_miller, v.S1, v.S2, v.K, kd.lines, v.F);
+  PSB_WAVES(L, k_verify_final, v.S1, v.F, v.ver, nullptr, v.ok, strict);
+  CK(cudaGetLastError());
+  return PSB_OK;
+}
+
 int psb_provide_id(psb_key* key, size_t N, const uint64_t* A, const uint64_t* c, const uint64_t* rs, size_t per,
                    const uint8_t* attr_blob, const uint64_t* attr_off, const uint8_t* ad_blob, const uint64_t* ad_off,
                    const uint64_t* u, uint8_t* verdict, uint64_t* sig1, uint64_t* sig2, uint8_t* ser) {
   if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
   if (!key || !A || !c || (per && !rs) || !attr_blob || !attr_off || !ad_blob || !ad_off || !u || !verdict || !sig1 || !sig2)
     return fail(PSB_ERR_ARG, "null argument");
+  KEY_ALIVE(key);
   if (!key->hasX) return fail(PSB_ERR_ARG, "key was created without the signer secret X");
   int rc = ensure_issuer_tables(key);
   if (rc) return rc;
@@ -784,7 +849,8 @@ int psb_provide_id(psb_key* key, size_t N, const uint64_t* A, const uint64_t* c,
     if (a1 > a0) CK(cudaMemcpyAsync(dad, ad_blob + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(dadoff, ad_off + b, (L + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     const KeyDev& kd = key->d[di];
-    k_provide_id<<<nblocks(L), kBlock, 0, st>>>(L, (int)n, key->w, kd.tblG1, kd.g1pts, dA, dc, drs, (int)per, dblob - o0, doff,
+    const LaneGeom lg{(int)per, (int)per, (int)n, nullptr, nullptr};
+    k_provide_id<<<nblocks(L), kBlock, 0, st>>>(L, (int)n, key->w, kd.tblG1, kd.g1pts, dA, dc, drs, lg, dblob - o0, doff,
                                                 dad - a0, dadoff, du, dver, dS1, dS2, ser ? dser : nullptr);
     LAUNCHED();
     CK(cudaGetLastError());
@@ -797,15 +863,61 @@ int psb_provide_id(psb_key* key, size_t N, const uint64_t* A, const uint64_t* c,
   });
 }
 
+int psb_sign(psb_key* key, size_t N, const uint64_t* commitment, size_t n_attrs, const uint8_t* attr_blob,
+             const uint64_t* attr_off, const uint64_t* u, uint64_t* sig1, uint64_t* sig2, uint8_t* ser) {
+  if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
+  if (!key || !commitment || !u || !sig1 || !sig2 || (n_attrs && (!attr_blob || !attr_off))) return fail(PSB_ERR_ARG, "null argument");
+  KEY_ALIVE(key);
+  if (!key->hasX) return fail(PSB_ERR_ARG, "key was created without the signer secret X");
+  if (n_attrs > key->n) return fail(PSB_ERR_ARG, "more attributes than the key has bases (undefined in the reference: m_pk.Yi[i])");
+  int rc = ensure_issuer_tables(key);
+  if (rc) return rc;
+  const size_t na = n_attrs;
+  return shard(N, [&](int di, size_t b, size_t e) -> int {
+    Dev* dv = g_devs[di];
+    std::lock_guard<std::mutex> lk(dv->mu);
+    const size_t L = e - b;
+    if (L == 0) return PSB_OK;
+    CK(cudaSetDevice(dv->ordinal));
+    cudaStream_t st = dv->stream;
+    const uint64_t o0 = na ? attr_off[b * na] : 0, o1 = na ? attr_off[e * na] : 0;
+    Arena ar;
+    G1J *dC = nullptr, *dS1 = nullptr, *dS2 = nullptr; Fr* du = nullptr;
+    uint8_t *dblob = nullptr, *dser = nullptr; uint64_t* doff = nullptr;
+    for (int pass = 0; pass < 2; pass++) {
+      ar.used = 0;
+      dC = ar.take<G1J>(L); du = ar.take<Fr>(L); dblob = ar.take<uint8_t>((size_t)(o1 - o0) + 16); doff = ar.take<uint64_t>(L * na + 1);
+      dS1 = ar.take<G1J>(L); dS2 = ar.take<G1J>(L); dser = ar.take<uint8_t>(L * kCredSer);
+      if (pass == 0) { int r = ensure(dv->arena, ar.used); if (r) return r; ar.base = (char*)dv->arena.p; }
+    }
+    CK(cudaMemcpyAsync(dC, commitment + b * kG1W, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(du, u + b * 4, L * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    if (o1 > o0) CK(cudaMemcpyAsync(dblob, attr_blob + o0, (size_t)(o1 - o0), cudaMemcpyHostToDevice, st));
+    if (na) CK(cudaMemcpyAsync(doff, attr_off + b * na, (L * na + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    const KeyDev& kd = key->d[di];
+    k_sign<<<nblocks(L), kBlock, 0, st>>>(L, (int)na, key->w, kd.tblG1, kd.g1pts, dC, dblob - o0, na ? doff : nullptr, du, dS1, dS2,
+                                          ser ? dser : nullptr);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(sig1 + b * kG1W, dS1, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(sig2 + b * kG1W, dS2, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+    if (ser) CK(cudaMemcpyAsync(ser + b * kCredSer, dser, L * kCredSer, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PSB_OK;
+  });
+}
+
 int psb_verify_id(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* sig2, const uint64_t* k,
                   const uint64_t* phi, const uint64_t* E1, const uint64_t* E2, const uint64_t* c, const uint64_t* rs,
                   size_t per, const uint8_t* attr_blob, const uint64_t* attr_off, const uint8_t* ad_blob,
                   const uint64_t* ad_off, const uint64_t* service_pt, const uint64_t* y, const uint64_t* g,
-                  const uint64_t* h, int with_id, uint8_t* verdict) {
+                  const uint64_t* h, int flags, uint8_t* verdict) {
   if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
   if (!key || !sig1 || !sig2 || !k || !phi || !c || (per && !rs) || !attr_blob || !attr_off || !ad_blob || !ad_off ||
       !service_pt || !verdict)
     return fail(PSB_ERR_ARG, "null argument");
+  KEY_ALIVE(key);
+  const int with_id = flags & PSB_VID_WITH_ID, strict = (flags & PSB_VID_REJECT_ZERO_SIGMA) ? 1 : 0;
   if (with_id && (!E1 || !E2 || !y || !g || !h)) return fail(PSB_ERR_ARG, "E1/E2/y/g/h are required with id retrieval");
   int rc = ensure_verifier_tables(key);
   if (rc) return rc;
@@ -850,18 +962,149 @@ int psb_verify_id(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* 
     CK(cudaMemcpyAsync(doff, attr_off + b * n, (L * n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     if (a1 > a0) CK(cudaMemcpyAsync(dad, ad_blob + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(dadoff, ad_off + b, (L + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    const VidDev v{dS1, dS2, dphi, dE1, dE2, dk, dc, drs, dblob - o0, doff, dad - a0, dadoff, dVk, dK, dV, dF, dok, dver};
+    const LaneGeom lg{(int)per, (int)per, (int)n, nullptr, nullptr};
+    int r = verify_id_core(key, di, L, v, lg, with_id ? 1 : 0, strict, *bt, st);
+    if (r) return r;
+    CK(cudaMemcpyAsync(verdict + b, dver, L, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PSB_OK;
+  });
+}
+
+// ---- wire-format entry points: lane j = buf[buf_off[j] .. buf_off[j+1]), the bytes of
+//      IdProof::toBufferString() / PSCredRequest::toBufferString(), or their base64 text (PSBuffer::toBase64) --------------
+struct WireDev {
+  uint8_t *raw, *attr; uint64_t *off, *aoff; uint32_t *len, *pos; Fr *c, *rs; int* per; uint8_t *parsed, *has_e;
+};
+// H2D of the buffers + base64 + TLV walk on device; carves from `ar` (called in both arena passes)
+static void wire_carve(Arena& ar, WireDev& w, size_t L, size_t bytes, size_t n, uint8_t** text) {
+  *text = ar.take<uint8_t>(bytes + 16);
+  w.raw = ar.take<uint8_t>(bytes + 16); w.attr = ar.take<uint8_t>(bytes + 16);
+  w.off = ar.take<uint64_t>(L + 1); w.aoff = ar.take<uint64_t>(L * (n + 1) + 1);
+  w.len = ar.take<uint32_t>(L); w.pos = ar.take<uint32_t>(L * W_SLOTS);
+  w.c = ar.take<Fr>(L); w.rs = ar.take<Fr>(L * (n + 2) + 1); w.per = ar.take<int>(L);
+  w.parsed = ar.take<uint8_t>(L); w.has_e = ar.take<uint8_t>(L);
+}
+static int wire_ingest(const WireDev& w, uint8_t* dtext, size_t L, size_t n, int kind, int base64, const uint8_t* buf,
+                       const uint64_t* buf_off, size_t b, cudaStream_t st) {
+  const uint64_t w0 = buf_off[b], w1 = buf_off[b + L];
+  uint8_t* dst = base64 ? dtext : w.raw;
+  if (w1 > w0) CK(cudaMemcpyAsync(dst, buf + w0, (size_t)(w1 - w0), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(w.off, buf_off + b, (L + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  // device offsets stay absolute (as the host gave them): the data pointers are biased by -w0 instead
+  if (base64) { k_wire_base64<<<nblocks(L), kBlock, 0, st>>>(L, dtext - w0, w.off, w.raw - w0, w.len); LAUNCHED(); }
+  k_wire_parse<<<nblocks(L), kBlock, 0, st>>>(L, (int)n, kind, w.raw - w0, w.off, base64 ? w.len : nullptr, w.pos, w.c, w.rs, w.per,
+                                              w.attr - w0, w.aoff, w.parsed, w.has_e);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  return PSB_OK;
+}
+
+int psb_verify_id_ser(psb_key* key, size_t N, const uint8_t* buf, const uint64_t* buf_off, int base64, const uint8_t* ad_blob,
+                      const uint64_t* ad_off, const uint64_t* service_pt, const uint64_t* y, const uint64_t* g,
+                      const uint64_t* h, int flags, uint8_t* verdict, uint8_t* parsed) {
+  if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
+  if (!key || !buf || !buf_off || !ad_blob || !ad_off || !service_pt || !verdict) return fail(PSB_ERR_ARG, "null argument");
+  KEY_ALIVE(key);
+  const int with_id = flags & PSB_VID_WITH_ID, strict = (flags & PSB_VID_REJECT_ZERO_SIGMA) ? 1 : 0;
+  if (with_id && (!y || !g || !h)) return fail(PSB_ERR_ARG, "y/g/h are required with id retrieval");
+  int rc = ensure_verifier_tables(key);
+  if (rc) return rc;
+  std::shared_ptr<BatchTbl> bt;
+  const uint64_t* const pts[4] = {service_pt, g, y, h};
+  if ((rc = get_batch_tables(key, pts, with_id ? 4 : 1, bt))) return rc;
+  const size_t n = key->n;
+  return shard(N, [&](int di, size_t b, size_t e) -> int {
+    Dev* dv = g_devs[di];
+    std::lock_guard<std::mutex> lk(dv->mu);
+    const size_t L = e - b;
+    if (L == 0) return PSB_OK;
+    CK(cudaSetDevice(dv->ordinal));
+    cudaStream_t st = dv->stream;
+    const uint64_t w0 = buf_off[b], w1 = buf_off[e], a0 = ad_off[b], a1 = ad_off[e];
+    Arena ar;
+    WireDev w{};
+    uint8_t* dtext = nullptr;
+    G1J *dS1 = nullptr, *dS2 = nullptr, *dphi = nullptr, *dE1 = nullptr, *dE2 = nullptr, *dV = nullptr;
+    G2J *dk = nullptr, *dVk = nullptr, *dK = nullptr; Fp12* dF = nullptr;
+    uint8_t *dad = nullptr, *dver = nullptr, *dok = nullptr; uint64_t* dadoff = nullptr;
+    for (int pass = 0; pass < 2; pass++) {
+      ar.used = 0;
+      wire_carve(ar, w, L, (size_t)(w1 - w0), n, &dtext);
+      dS1 = ar.take<G1J>(L); dS2 = ar.take<G1J>(L); dk = ar.take<G2J>(L); dphi = ar.take<G1J>(L); dE1 = ar.take<G1J>(L); dE2 = ar.take<G1J>(L);
+      dad = ar.take<uint8_t>((size_t)(a1 - a0) + 16); dadoff = ar.take<uint64_t>(L + 1);
+      dVk = ar.take<G2J>(L); dK = ar.take<G2J>(L); dV = ar.take<G1J>(3 * L); dF = ar.take<Fp12>(L);
+      dok = ar.take<uint8_t>(L); dver = ar.take<uint8_t>(L);
+      if (pass == 0) { int r = ensure(dv->arena, ar.used); if (r) return r; ar.base = (char*)dv->arena.p; }
+    }
+    int r = wire_ingest(w, dtext, L, n, 0, base64, buf, buf_off, b, st);
+    if (r) return r;
+    if (a1 > a0) CK(cudaMemcpyAsync(dad, ad_blob + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dadoff, ad_off + b, (L + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    const WireG1Out g1o{{dS1, dS2, dphi, dE1, dE2}};
+    k_wire_points<<<nblocks(L * W_SLOTS), kBlock, 0, st>>>(L, W_SLOTS, w.raw - w0, w.off, w.pos, g1o, dk, w.parsed);
+    LAUNCHED();
+    if (with_id) { k_and_flags<<<nblocks(L), kBlock, 0, st>>>(L, w.parsed, w.has_e); LAUNCHED(); }   // no E1 / E2: the reference returns false
+    const VidDev v{dS1, dS2, dphi, dE1, dE2, dk, w.c, w.rs, w.attr - w0, w.aoff, dad - a0, dadoff, dVk, dK, dV, dF, dok, dver};
+    const LaneGeom lg{0, (int)n + 2, (int)n + 1, w.per, w.parsed};
+    if ((r = verify_id_core(key, di, L, v, lg, with_id ? 1 : 0, strict, *bt, st))) return r;
+    CK(cudaMemcpyAsync(verdict + b, dver, L, cudaMemcpyDeviceToHost, st));
+    if (parsed) CK(cudaMemcpyAsync(parsed + b, w.parsed, L, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PSB_OK;
+  });
+}
+
+int psb_provide_id_ser(psb_key* key, size_t N, const uint8_t* buf, const uint64_t* buf_off, int base64, const uint8_t* ad_blob,
+                       const uint64_t* ad_off, const uint64_t* u, uint8_t* verdict, uint64_t* sig1, uint64_t* sig2, uint8_t* ser,
+                       uint8_t* parsed) {
+  if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
+  if (!key || !buf || !buf_off || !ad_blob || !ad_off || !u || !verdict || !sig1 || !sig2) return fail(PSB_ERR_ARG, "null argument");
+  KEY_ALIVE(key);
+  if (!key->hasX) return fail(PSB_ERR_ARG, "key was created without the signer secret X");
+  int rc = ensure_issuer_tables(key);
+  if (rc) return rc;
+  const size_t n = key->n;
+  return shard(N, [&](int di, size_t b, size_t e) -> int {
+    Dev* dv = g_devs[di];
+    std::lock_guard<std::mutex> lk(dv->mu);
+    const size_t L = e - b;
+    if (L == 0) return PSB_OK;
+    CK(cudaSetDevice(dv->ordinal));
+    cudaStream_t st = dv->stream;
+    const uint64_t w0 = buf_off[b], w1 = buf_off[e], a0 = ad_off[b], a1 = ad_off[e];
+    Arena ar;
+    WireDev w{};
+    uint8_t* dtext = nullptr;
+    G1J *dA = nullptr, *dS1 = nullptr, *dS2 = nullptr; Fr* du = nullptr;
+    uint8_t *dad = nullptr, *dver = nullptr, *dser = nullptr; uint64_t* dadoff = nullptr;
+    for (int pass = 0; pass < 2; pass++) {
+      ar.used = 0;
+      wire_carve(ar, w, L, (size_t)(w1 - w0), n, &dtext);
+      dA = ar.take<G1J>(L); du = ar.take<Fr>(L); dad = ar.take<uint8_t>((size_t)(a1 - a0) + 16); dadoff = ar.take<uint64_t>(L + 1);
+      dver = ar.take<uint8_t>(L); dS1 = ar.take<G1J>(L); dS2 = ar.take<G1J>(L); dser = ar.take<uint8_t>(L * kCredSer);
+      if (pass == 0) { int r = ensure(dv->arena, ar.used); if (r) return r; ar.base = (char*)dv->arena.p; }
+    }
+    int r = wire_ingest(w, dtext, L, n, 1, base64, buf, buf_off, b, st);
+    if (r) return r;
+    CK(cudaMemcpyAsync(du, u + b * 4, L * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    if (a1 > a0) CK(cudaMemcpyAsync(dad, ad_blob + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dadoff, ad_off + b, (L + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    const WireG1Out g1o{{dA, nullptr, nullptr, nullptr, nullptr}};
+    k_wire_points<<<nblocks(L), kBlock, 0, st>>>(L, 1, w.raw - w0, w.off, w.pos, g1o, nullptr, w.parsed);
+    LAUNCHED();
     const KeyDev& kd = key->d[di];
-    k_vid_g2<<<nblocks(L), kBlock, 0, st>>>(L, (int)n, key->w, kd.tblYY, kd.tblAux, dk, dc, drs, (int)per, with_id, dblob - o0, doff,
-                                            dVk, dK, dok);
+    const LaneGeom lg{0, (int)n + 2, (int)n + 1, w.per, w.parsed};
+    k_provide_id<<<nblocks(L), kBlock, 0, st>>>(L, (int)n, key->w, kd.tblG1, kd.g1pts, dA, w.c, w.rs, lg, w.attr - w0, w.aoff,
+                                                dad - a0, dadoff, du, dver, dS1, dS2, ser ? dser : nullptr);
     LAUNCHED();
-    k_vid_g1<<<nblocks(L), kBlock, 0, st>>>(L, kBatchW, bt->tbl[di], dphi, dE1, dE2, dc, drs, (int)per, with_id, dV);
-    LAUNCHED();
-    k_vid_hash<<<nblocks(L), kBlock, 0, st>>>(L, dk, dphi, dE1, dE2, dVk, dV, with_id, dc, dad - a0, dadoff, dok);
-    LAUNCHED();
-    PSB_WAVES(L, k_verify_miller, dS1, dS2, dK, kd.lines, dF);
-    PSB_WAVES(L, k_verify_final, dS1, dF, dver, nullptr, dok, 0);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(verdict + b, dver, L, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(sig1 + b * kG1W, dS1, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(sig2 + b * kG1W, dS2, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+    if (ser) CK(cudaMemcpyAsync(ser + b * kCredSer, dser, L * kCredSer, cudaMemcpyDeviceToHost, st));
+    if (parsed) CK(cudaMemcpyAsync(parsed + b, w.parsed, L, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return PSB_OK;
   });
@@ -880,6 +1123,7 @@ int psb_request_id(psb_key* key, size_t N, const uint8_t* attr_blob, const uint6
   if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
   if (!key || !attr_blob || !attr_off || (key->n && !hide) || !ad_blob || !ad_off || !rnd || !A || !c || !rs)
     return fail(PSB_ERR_ARG, "null argument");
+  KEY_ALIVE(key);
   int rc = ensure_issuer_tables(key);
   if (rc) return rc;
   const size_t n = key->n, h = count_hidden(hide, n);
@@ -956,6 +1200,7 @@ int psb_prove_id(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* s
   if (!key || !sig1 || !sig2 || !attr_blob || !attr_off || !hide || !ad_blob || !ad_off || !service_pt || !rnd || !o_sig1 ||
       !o_sig2 || !o_k || !o_phi || !o_c || !o_rs)
     return fail(PSB_ERR_ARG, "null argument");
+  KEY_ALIVE(key);
   if (with_id && (!y || !g || !h_pt || !o_E1 || !o_E2)) return fail(PSB_ERR_ARG, "y/g/h/E1/E2 are required with id retrieval");
   // the reference reads attributes[0] (and attributes[1] with id retrieval) unconditionally: ps-requester.cc:173,185
   if (key->n < (with_id ? 2u : 1u)) return fail(PSB_ERR_ARG, "the proof needs attribute 0 (and attribute 1 with id retrieval)");

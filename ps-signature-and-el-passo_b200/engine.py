@@ -32,6 +32,7 @@ FR, G1, G2, GT = 4, 3 * FP, 6 * FP, 12 * FP         # u64 words
 G1_SER, G2_SER = 8 * FP, 16 * FP                    # compressed point bytes (mcl serialize)
 CRED_SER = 2 * G1_SER                               # bare serialized credential (sigma1 || sigma2)
 CURVE_BLS12_381, CURVE_BN254 = 5, 0                 # mcl/include/mcl/curve_type.h
+VID_WITH_ID, VID_REJECT_ZERO_SIGMA = 1, 2           # include/psb.h PSB_VID_*
 MCL_CURVE = CURVE_BN254 if BN254 else CURVE_BLS12_381
 
 _lib = None
@@ -67,7 +68,7 @@ def lib():
 EXPORTS = ["psb_init", "psb_shutdown", "psb_num_devices", "psb_last_error", "psb_shard_range", "psb_launch_count",
            "psb_key_create", "psb_key_destroy", "psb_key_num_attributes", "psb_key_table_bytes",
            "psb_verify", "psb_verify_ser", "psb_g1_deserialize", "psb_g2_deserialize", "psb_verify_ws_bytes", "psb_verify_dev", "psb_randomize", "psb_provide_id",
-           "psb_verify_id", "psb_request_id", "psb_unblind", "psb_prove_id", "psb_hash_to_g1", "psb_pairing", "psb_g1_mul", "psb_set_profiling", "psb_last_phase_ms", "psb_test_op_shape", "psb_test_op", "psb_microbench"]
+           "psb_verify_id", "psb_sign", "psb_verify_id_ser", "psb_provide_id_ser", "psb_request_id", "psb_unblind", "psb_prove_id", "psb_hash_to_g1", "psb_pairing", "psb_g1_mul", "psb_set_profiling", "psb_last_phase_ms", "psb_test_op_shape", "psb_test_op", "psb_microbench"]
 
 
 def _check(rc: int, what: str):
@@ -229,8 +230,26 @@ class PSVerifier:
                                     C.c_size_t(off2), _p(blob), _p(off), _p(verdict), _p(decoded)), "psb_verify_ser")
         return verdict, decoded
 
+    def el_passo_verify_id_wire(self, buffers, associated_data: Sequence[bytes], service_pt, authority_pk=None, g=None,
+                                h=None, with_id: bool = True, base64: bool = False, strict: bool = False):
+        """el_passo_verify_id straight from the WIRE (psb_verify_id_ser): buffers = per lane the bytes of
+        IdProof::toBufferString() (or their base64 text), or a packed (blob, off) pair.  Returns (verdict, parsed)."""
+        blob, off = _packed(buffers, True)
+        ad_blob, ad_off = _packed(associated_data, True)
+        N = off.shape[0] - 1
+        if ad_off.shape[0] != N + 1:
+            raise ValueError("one associated_data per proof")
+        verdict = np.zeros(N, dtype=np.uint8)
+        parsed = np.zeros(N, dtype=np.uint8)
+        flags = (VID_WITH_ID if with_id else 0) | (VID_REJECT_ZERO_SIGMA if strict else 0)
+        _check(lib().psb_verify_id_ser(
+            self.m_pk.handle, C.c_size_t(N), _p(blob), _p(off), C.c_int(int(base64)), _p(ad_blob), _p(ad_off),
+            _p(_u64(service_pt, G1)), _p(_u64(authority_pk, G1)) if with_id else None, _p(_u64(g, G1)) if with_id else None,
+            _p(_u64(h, G1)) if with_id else None, C.c_int(flags), _p(verdict), _p(parsed)), "psb_verify_id_ser")
+        return verdict, parsed
+
     def el_passo_verify_id(self, proof: dict, attributes, associated_data: Sequence[bytes], service_pt,
-                           authority_pk=None, g=None, h=None, with_id: bool = True):
+                           authority_pk=None, g=None, h=None, with_id: bool = True, strict: bool = False):
         """batched el_passo_verify_id (src/ps-verifier.cc:37-138) / _without_id_retrieval (:140-212).
         proof: dict of arrays sig1, sig2, k, phi, E1, E2, c, rs (N, per, 4); attributes: per lane the
         proof's attribute list (b"" = hidden)."""
@@ -249,7 +268,8 @@ class PSVerifier:
             _p(_u64(proof["E2"], G1)) if with_id else None, _p(_u64(proof["c"], FR)), _p(rs),
             C.c_size_t(rs.shape[1]), _p(blob), _p(off), _p(ad_blob), _p(ad_off), _p(_u64(service_pt, G1)),
             _p(_u64(authority_pk, G1)) if with_id else _p(z1), _p(_u64(g, G1)) if with_id else _p(z1),
-            _p(_u64(h, G1)) if with_id else _p(z1), C.c_int(int(with_id)), _p(verdict)), "psb_verify_id")
+            _p(_u64(h, G1)) if with_id else _p(z1),
+            C.c_int((VID_WITH_ID if with_id else 0) | (VID_REJECT_ZERO_SIGMA if strict else 0)), _p(verdict)), "psb_verify_id")
         return verdict
 
 
@@ -363,6 +383,47 @@ class PSSigner:
                                     C.c_size_t(rs.shape[1]), _p(blob), _p(off), _p(ad_blob), _p(ad_off),
                                     _p(_u64(u, FR)), _p(verdict), _p(s1), _p(s2), _p(ser)), "psb_provide_id")
         return verdict, s1, s2, ser
+
+    def el_passo_provide_id_wire(self, buffers, associated_data, u, base64: bool = False):
+        """el_passo_provide_id straight from the WIRE (psb_provide_id_ser): buffers = per lane the bytes of
+        PSCredRequest::toBufferString() (or their base64 text).  Returns (verdict, sig1, sig2, ser, parsed)."""
+        blob, off = _packed(buffers, True)
+        ad_blob, ad_off = _packed(associated_data, True)
+        N = off.shape[0] - 1
+        if ad_off.shape[0] != N + 1:
+            raise ValueError("one associated_data per request")
+        verdict = np.zeros(N, dtype=np.uint8)
+        parsed = np.zeros(N, dtype=np.uint8)
+        s1 = np.zeros((N, G1), dtype=np.uint64)
+        s2 = np.zeros((N, G1), dtype=np.uint64)
+        ser = np.zeros((N, CRED_SER), dtype=np.uint8)
+        _check(lib().psb_provide_id_ser(self.m_pk.handle, C.c_size_t(N), _p(blob), _p(off), C.c_int(int(base64)), _p(ad_blob),
+                                        _p(ad_off), _p(_u64(u, FR)), _p(verdict), _p(s1), _p(s2), _p(ser), _p(parsed)),
+               "psb_provide_id_ser")
+        return verdict, s1, s2, ser, parsed
+
+    def sign_commitment(self, commitment, u):
+        """batched PSSigner::sign_commitment (src/ps-signer.cc:132-146) with host-supplied u: (sig1, sig2, ser)."""
+        return self.sign_hybrid(commitment, None, u)
+
+    def sign_hybrid(self, commitment, attributes, u):
+        """batched PSSigner::sign_hybrid (src/ps-signer.cc:112-130): attributes = per lane the same number of strings
+        (b"" = committed attribute), or None for sign_commitment."""
+        Cm = _u64(commitment, G1)
+        N = Cm.shape[0]
+        if attributes is None:
+            blob, off, na = None, None, 0
+        else:
+            blob, off = _packed(attributes, False)
+            na = (off.shape[0] - 1) // N if N else 0
+            if off.shape[0] != N * na + 1:
+                raise ValueError("attribute size does not match")
+        s1 = np.zeros((N, G1), dtype=np.uint64)
+        s2 = np.zeros((N, G1), dtype=np.uint64)
+        ser = np.zeros((N, CRED_SER), dtype=np.uint8)
+        _check(lib().psb_sign(self.m_pk.handle, C.c_size_t(N), _p(Cm), C.c_size_t(na), _p(blob), _p(off), _p(_u64(u, FR)),
+                              _p(s1), _p(s2), _p(ser)), "psb_sign")
+        return s1, s2, ser
 
 
 def pairing(P, Q):

@@ -22,6 +22,7 @@ void hostsim_set_hash_of(const uint8_t* msg, size_t len, uint32_t* k) { psb::fr_
 #include <vector>
 #include "../../ps-signature-and-el-passo_b200/csrc/prover.cuh"
 #include "../../ps-signature-and-el-passo_b200/csrc/hash_to_curve.cuh"
+#include "../../ps-signature-and-el-passo_b200/csrc/wire.cuh"
 namespace {
 using namespace psb;
 constexpr int kG1U = 3 * PSB_NL, kG2U = 6 * PSB_NL;   // u32 words of a Jacobian G1 / G2 point
@@ -174,4 +175,50 @@ void hostsim_sha512(const uint8_t* msg, size_t len, uint8_t* out64) {
 }
 int hostsim_hash_to_g1(const uint8_t* msg, size_t len, uint32_t* out) { G1J P; const bool r = hash_and_map_to_g1(P, msg, len); st(out, P); return r; }
 int hostsim_map_to_g1(const uint32_t* t, uint32_t* out) { Fp tt; ld(tt, t); G1J P, Q; const bool r = map_to_g1(P, tt); if (r) g1_clear_cofactor(Q, P); else pt_set_zero(Q); st(out, Q); return r; }
+
+// ---- wire formats (csrc/wire.cuh): base64 + TLV walk + point decompression of ONE message, as the device kernels
+//      k_wire_base64 / k_wire_parse / k_wire_points do it.  kind 0 = IdProof, 1 = PSCredRequest.  Returns `parsed`.
+int hostsim_wire_parse(int kind, int n, const uint8_t* in, size_t len, int base64, uint32_t* g1pts /*5 x G1*/, uint32_t* g2pt,
+                       uint32_t* c, uint32_t* rs /*(n + 2) x Fr*/, int* per, uint8_t* attr_out, uint64_t* attr_off /*n + 1*/,
+                       int* has_e) {
+  std::vector<uint8_t> raw(in, in + len);
+  if (base64) { raw.resize(len + 4); raw.resize(base64_decode_lane(raw.data(), in, len)); }
+  uint32_t pos[W_SLOTS];
+  Fr cc;
+  for (int i = 0; i < 8; i++) cc.v[i] = 0;
+  std::vector<Fr> r(n + 2);
+  bool he = false;
+  bool ok = kind == 0 ? parse_idproof_lane(raw.data(), raw.size(), n, pos, cc, r.data(), *per, attr_out, attr_off, 0, he)
+                      : parse_request_lane(raw.data(), raw.size(), n, pos, cc, r.data(), *per, attr_out, attr_off, 0);
+  *has_e = he;
+  for (int i = 0; i < 8; i++) c[i] = cc.v[i];
+  for (int j = 0; j < *per; j++) for (int i = 0; i < 8; i++) rs[8 * j + i] = r[j].v[i];
+  for (int slot = 0; slot < W_SLOTS; slot++) {
+    if (slot == W_K) {
+      G2J P; pt_set_zero(P);
+      if (pos[slot] != kWireAbsent && !g2_deserialize(P, raw.data() + pos[slot])) ok = false;
+      st(g2pt, P);
+    } else {
+      G1J P; pt_set_zero(P);
+      if (pos[slot] != kWireAbsent && !g1_deserialize(P, raw.data() + pos[slot])) ok = false;
+      st(g1pts + kG1U * slot, P);
+    }
+  }
+  return ok ? 1 : 0;
+}
+size_t hostsim_base64_decode(const uint8_t* in, size_t len, uint8_t* out) { return base64_decode_lane(out, in, len); }
+
+// PSSigner::sign_hybrid / sign_commitment lanes (csrc/protocol.cuh sign_lane)
+void hostsim_sign(int n, int na, int w, const uint32_t* g, const uint32_t* X, const uint32_t* Y, size_t N, const uint32_t* Cm,
+                  const uint8_t* blob, const uint64_t* off, const uint32_t* u, uint32_t* sig1, uint32_t* sig2) {
+  std::vector<G1A> tbl;
+  G1J b; ld(b, g); host_table(tbl, b, w);
+  for (int i = 0; i < n; i++) { ld(b, Y + kG1U * i); host_table(tbl, b, w); }
+  G1J Xs; ld(Xs, X);
+  for (size_t j = 0; j < N; j++) {
+    G1J cm, s1, s2; ld(cm, Cm + kG1U * j);
+    sign_lane(na, TblGeom{w}, tbl.data(), Xs, cm, blob, na ? off + j * na : nullptr, (const Fr*)(u + 8 * j), s1, s2);
+    st(sig1 + kG1U * j, s1); st(sig2 + kG1U * j, s2);
+  }
+}
 }

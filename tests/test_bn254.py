@@ -11,9 +11,9 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CPU_MODULES = ["test_hostsim.py", "test_hostsim_protocol.py", "test_hostsim_prover.py", "test_hash_to_curve.py", "test_abi.py"]
+CPU_MODULES = ["test_hostsim.py", "test_hostsim_protocol.py", "test_hostsim_prover.py", "test_hostsim_wire.py", "test_hash_to_curve.py", "test_abi.py"]
 GPU_MODULES = ["test_gpu_arith.py", "test_gpu_verify.py", "test_gpu_protocol.py", "test_gpu_elpasso.py", "test_gpu_prover.py",
-               "test_gpu_wire.py", "test_hash_to_curve.py"]
+               "test_gpu_wire.py", "test_gpu_configs.py", "test_hash_to_curve.py"]
 
 
 def _child(modules, marker, min_passed):
