@@ -70,6 +70,11 @@ int psb_verify(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* sig
                const uint8_t* attr_blob, const uint64_t* attr_off, const uint64_t* m,
                uint8_t* verdict, uint64_t* gt);
 
+/* psb_verify on an ARRAY OF CREDENTIALS: cred = N x (sigma1 || sigma2), 2 x 18 u64 per lane -- the bytes of
+ * std::vector<PSCredential> (src/ps-encoding.h:89-109: two G1 members), passed without a copy. */
+int psb_verify_aos(psb_key* key, size_t N, const uint64_t* cred, const uint8_t* attr_blob, const uint64_t* attr_off,
+                   const uint64_t* m, uint8_t* verdict, uint64_t* gt);
+
 /* Batched G1::deserialize / G2::deserialize = point decompression (mcl/include/mcl/ec.hpp:924-1057, IoSerialize,
  * mcl's default little-endian mode): element j is the 48 (G1) / 96 (G2) bytes at ser + j * stride.  out[j] = the
  * point with z = 1 (all-zero for the infinity encoding); ok[j] = 1 iff mcl's deserialize would succeed (x < p and

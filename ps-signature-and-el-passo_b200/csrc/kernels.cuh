@@ -294,16 +294,18 @@ __global__ void PSB_PAIR_BOUNDS k_verify_msm(size_t N, size_t base, int n, int w
 }
 
 // phase 2: f = ML(sig1, K) * ML(-sig2, gg)  (one multi-Miller loop per lane)
-__global__ void PSB_PAIR_BOUNDS k_verify_miller(size_t N, size_t base, const G1J* sig1, const G1J* sig2, const G2J* K,
+//          ss = stride of the credential arrays in G1J units: 1 for separate sigma1 / sigma2 arrays, 2 for an array of
+//          (sigma1, sigma2) pairs such as std::vector<PSCredential> (sig2 = sig1 + 1)
+__global__ void PSB_PAIR_BOUNDS k_verify_miller(size_t N, size_t base, const G1J* sig1, const G1J* sig2, int ss, const G2J* K,
                                                            const FixedLine* lines, Fp12* fout) {
   const size_t lane0 = base + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = lane0 < N;
   const size_t lane = live ? lane0 : N - 1;        // as in k_verify_final: no early exit, the block may re-align itself
   Fp x1, y1, x2, y2;
   {
-    G1J p = sig1[lane];
+    G1J p = sig1[lane * ss];
     g1_affine_for_pairing(x1, y1, p);
-    p = sig2[lane];
+    p = sig2[lane * ss];
     g1_affine_for_pairing(x2, y2, p);
     fp_neg(y2, y2);
   }
@@ -316,7 +318,7 @@ __global__ void PSB_PAIR_BOUNDS k_verify_miller(size_t N, size_t base, const G1J
 // phase 3: final exponentiation, verdict = (sig1 != 0) && (f^e == 1), optional GT
 //          reject_zero_sig1: PSVerifier::verify rejects sig1 == 0 (ps-verifier.cc:16-18), el_passo_verify_id does not;
 //          pre (optional): per-lane verdict of an earlier step (the NIZK check) that is ANDed in.
-__global__ void PSB_PAIR_BOUNDS k_verify_final(size_t N, size_t base, const G1J* sig1, const Fp12* fin, uint8_t* verdict,
+__global__ void PSB_PAIR_BOUNDS k_verify_final(size_t N, size_t base, const G1J* sig1, int ss, const Fp12* fin, uint8_t* verdict,
                                                           Fp12* gt, const uint8_t* pre, int reject_zero_sig1) {
   const size_t lane0 = base + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = lane0 < N;
@@ -324,7 +326,7 @@ __global__ void PSB_PAIR_BOUNDS k_verify_final(size_t N, size_t base, const G1J*
   Fp12 f = fin[lane], e;                           // so the block can re-align itself inside final_exp
   final_exp(e, f, true);
   if (!live) return;
-  const bool s1zero = reject_zero_sig1 && fp_is_zero(sig1[lane].z);
+  const bool s1zero = reject_zero_sig1 && fp_is_zero(sig1[lane * ss].z);
   const bool pre_ok = pre ? pre[lane] != 0 : true;
   verdict[lane] = (pre_ok && !s1zero && fp12_is_one(e)) ? 1 : 0;
   if (gt) gt[lane] = e;

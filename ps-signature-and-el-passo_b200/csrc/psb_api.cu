@@ -228,7 +228,7 @@ bool is_zero_words(const uint64_t* p, size_t n) {
 
 int verify_launch(const psb_key* key, int di, size_t N, const G1J* d_sig1, const G1J* d_sig2, const uint8_t* d_blob,
                   const uint64_t* d_off, const Fr* d_m, uint8_t* d_verdict, Fp12* d_gt, void* d_ws, cudaStream_t st,
-                  const uint8_t* d_pre = nullptr) {
+                  const uint8_t* d_pre = nullptr, int ss = 1) {
   if (N == 0) return PSB_OK;
   const KeyDev& kd = key->d[di];
   G2J* dK = (G2J*)d_ws;
@@ -241,9 +241,9 @@ int verify_launch(const psb_key* key, int di, size_t N, const G1J* d_sig1, const
   }
   PSB_WAVES(N, k_verify_msm, (int)key->n, key->w, d_blob, d_off, d_m, kd.g2pts + 1, kd.tblYY, dK);
   if (prof) CK(cudaEventRecord(dv->ev[1], st));
-  PSB_WAVES(N, k_verify_miller, d_sig1, d_sig2, dK, kd.lines, dF);
+  PSB_WAVES(N, k_verify_miller, d_sig1, d_sig2, ss, dK, kd.lines, dF);
   if (prof) CK(cudaEventRecord(dv->ev[2], st));
-  PSB_WAVES(N, k_verify_final, d_sig1, dF, d_verdict, d_gt, d_pre, 1);
+  PSB_WAVES(N, k_verify_final, d_sig1, ss, dF, d_verdict, d_gt, d_pre, 1);
   if (prof) CK(cudaEventRecord(dv->ev[3], st));
   CK(cudaGetLastError());
   return PSB_OK;
@@ -434,8 +434,22 @@ int psb_verify_dev(psb_key* key, int dev_index, size_t N, const uint64_t* d_sig1
                        (const Fr*)d_m, d_verdict, (Fp12*)d_gt, d_ws, st);
 }
 
+// sig2 == nullptr: sig1 is an array of (sigma1, sigma2) PAIRS (std::vector<PSCredential>::data()), copied as it lies
+static int verify_host(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* sig2, const uint8_t* attr_blob,
+                       const uint64_t* attr_off, const uint64_t* m, uint8_t* verdict, uint64_t* gt);
 int psb_verify(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* sig2, const uint8_t* attr_blob,
                const uint64_t* attr_off, const uint64_t* m, uint8_t* verdict, uint64_t* gt) {
+  if (!sig2) return fail(PSB_ERR_ARG, "null argument");
+  return verify_host(key, N, sig1, sig2, attr_blob, attr_off, m, verdict, gt);
+}
+int psb_verify_aos(psb_key* key, size_t N, const uint64_t* cred, const uint8_t* attr_blob, const uint64_t* attr_off,
+                   const uint64_t* m, uint8_t* verdict, uint64_t* gt) {
+  return verify_host(key, N, cred, nullptr, attr_blob, attr_off, m, verdict, gt);
+}
+static int verify_host(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* sig2, const uint8_t* attr_blob,
+                       const uint64_t* attr_off, const uint64_t* m, uint8_t* verdict, uint64_t* gt) {
+  const bool aos = sig2 == nullptr;
+  if (aos) sig2 = sig1;   // (only for the null check below)
   if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
   if (!key || !sig1 || !sig2 || !verdict) return fail(PSB_ERR_ARG, "null argument");
   KEY_ALIVE(key);
@@ -457,8 +471,8 @@ int psb_verify(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* sig
     if (L < 2 * chunk) chunk = L;
     const size_t nchunks = (L + chunk - 1) / chunk;
     if (nchunks > 8) chunk = (((L + 7) / 8 + wave - 1) / wave) * wave;
-    if ((rc = ensure(dv->in[0], L * sizeof(G1J)))) return rc;
-    if ((rc = ensure(dv->in[1], L * sizeof(G1J)))) return rc;
+    if ((rc = ensure(dv->in[0], L * sizeof(G1J) * (aos ? 2 : 1)))) return rc;
+    if (!aos && (rc = ensure(dv->in[1], L * sizeof(G1J)))) return rc;
     if ((rc = ensure(dv->in[4], L + 16))) return rc;
     if ((rc = ensure(dv->ws, psb_verify_ws_bytes(key, chunk)))) return rc;
     if (gt && (rc = ensure(dv->in[5], L * sizeof(Fp12)))) return rc;
@@ -475,13 +489,14 @@ int psb_verify(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* sig
       if ((rc = ensure(dv->in[2], L * n * sizeof(Fr)))) return rc;
       d_m = (const Fr*)dv->in[2].p;
     }
-    G1J* dS1 = (G1J*)dv->in[0].p; G1J* dS2 = (G1J*)dv->in[1].p;
+    const int ss = aos ? 2 : 1;
+    G1J* dS1 = (G1J*)dv->in[0].p; G1J* dS2 = aos ? dS1 + 1 : (G1J*)dv->in[1].p;
     int c = 0;
     for (size_t cb = 0; cb < L; cb += chunk, c++) {
       const size_t cl = std::min(chunk, L - cb);
       cudaStream_t cs = (c == 0) ? st : dv->copy;          // the first chunk has nothing to overlap with
-      CK(cudaMemcpyAsync(dS1 + cb, sig1 + (b + cb) * kG1W, cl * sizeof(G1J), cudaMemcpyHostToDevice, cs));
-      CK(cudaMemcpyAsync(dS2 + cb, sig2 + (b + cb) * kG1W, cl * sizeof(G1J), cudaMemcpyHostToDevice, cs));
+      CK(cudaMemcpyAsync(dS1 + cb * ss, sig1 + (b + cb) * kG1W * ss, cl * sizeof(G1J) * ss, cudaMemcpyHostToDevice, cs));
+      if (!aos) CK(cudaMemcpyAsync(dS2 + cb, sig2 + (b + cb) * kG1W, cl * sizeof(G1J), cudaMemcpyHostToDevice, cs));
       if (attr_blob) {
         const uint64_t c0 = attr_off[(b + cb) * n], c1 = attr_off[(b + cb + cl) * n];
         if (c1 > c0) CK(cudaMemcpyAsync((uint8_t*)dv->in[2].p + (c0 - o0), attr_blob + c0, (size_t)(c1 - c0), cudaMemcpyHostToDevice, cs));
@@ -493,8 +508,8 @@ int psb_verify(psb_key* key, size_t N, const uint64_t* sig1, const uint64_t* sig
         CK(cudaEventRecord(dv->ev_in[c & 7], dv->copy));
         CK(cudaStreamWaitEvent(st, dv->ev_in[c & 7], 0));
       }
-      rc = verify_launch(key, di, cl, dS1 + cb, dS2 + cb, d_blob, d_off ? d_off + cb * n : nullptr, d_m ? d_m + cb * n : nullptr,
-                         (uint8_t*)dv->in[4].p + cb, gt ? (Fp12*)dv->in[5].p + cb : nullptr, dv->ws.p, st);
+      rc = verify_launch(key, di, cl, dS1 + cb * ss, dS2 + cb * ss, d_blob, d_off ? d_off + cb * n : nullptr, d_m ? d_m + cb * n : nullptr,
+                         (uint8_t*)dv->in[4].p + cb, gt ? (Fp12*)dv->in[5].p + cb : nullptr, dv->ws.p, st, nullptr, ss);
       if (rc) return rc;
     }
     CK(cudaMemcpyAsync(verdict + b, dv->in[4].p, L, cudaMemcpyDeviceToHost, st));
@@ -804,8 +819,8 @@ static int verify_id_core(psb_key* key, int di, size_t L, const VidDev& v, LaneG
   LAUNCHED();
   k_vid_hash<<<nblocks(L), kBlock, 0, st>>>(L, v.k, v.phi, v.E1, v.E2, v.Vk, v.V, with_id, v.c, v.ad, v.adoff, v.ok);
   LAUNCHED();
-  PSB_WAVES(L, k_verify_miller, v.S1, v.S2, v.K, kd.lines, v.F);
-  PSB_WAVES(L, k_verify_final, v.S1, v.F, v.ver, nullptr, v.ok, strict);
+  PSB_WAVES(L, k_verify_miller, v.S1, v.S2, 1, v.K, kd.lines, v.F);
+  PSB_WAVES(L, k_verify_final, v.S1, 1, v.F, v.ver, nullptr, v.ok, strict);
   CK(cudaGetLastError());
   return PSB_OK;
 }

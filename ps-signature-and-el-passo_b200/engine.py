@@ -67,7 +67,7 @@ def lib():
 
 EXPORTS = ["psb_init", "psb_shutdown", "psb_num_devices", "psb_last_error", "psb_shard_range", "psb_launch_count",
            "psb_key_create", "psb_key_destroy", "psb_key_num_attributes", "psb_key_table_bytes",
-           "psb_verify", "psb_verify_ser", "psb_g1_deserialize", "psb_g2_deserialize", "psb_verify_ws_bytes", "psb_verify_dev", "psb_randomize", "psb_provide_id",
+           "psb_verify", "psb_verify_aos", "psb_verify_ser", "psb_g1_deserialize", "psb_g2_deserialize", "psb_verify_ws_bytes", "psb_verify_dev", "psb_randomize", "psb_provide_id",
            "psb_verify_id", "psb_sign", "psb_verify_id_ser", "psb_provide_id_ser", "psb_request_id", "psb_unblind", "psb_prove_id", "psb_hash_to_g1", "psb_pairing", "psb_g1_mul", "psb_set_profiling", "psb_last_phase_ms", "psb_test_op_shape", "psb_test_op", "psb_microbench"]
 
 

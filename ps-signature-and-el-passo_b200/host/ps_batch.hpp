@@ -16,6 +16,14 @@
 //   psb::PSRequester::unblind_credential(sigs, t1)                      -> psb_unblind     (t1 = rnd[j][0] of the request)
 //   psb::PSRequester::el_passo_prove_id[_without_id_retrieval](...)     -> psb_prove_id    (rnd host-supplied, draw order)
 //   psb::PSSigner::el_passo_provide_id(requests, ads, u, sigs)          -> psb_provide_id  (u host-supplied)
+//   psb::PSSigner::sign_commitment / sign_hybrid(commitments, [attrs], u) -> psb_sign       (u host-supplied)
+//   psb::PSVerifier::el_passo_verify_id[_without_id_retrieval](wire, ...) -> psb_verify_id_ser  (base64 text or PSBuffer bytes
+//   psb::PSSigner::el_passo_provide_id(wire, ads, u, sigs)               -> psb_provide_id_ser  of toBufferString(), parsed on the GPU)
+//
+// Per-lane problems are DATA, never exceptions: a lane whose attribute list has the wrong length (undefined behaviour in
+// the reference: m_pk.YYi[counter] out of range, src/ps-verifier.cc:26), a proof without E1/E2, an undecodable wire buffer
+// get verdict 0 and the rest of the batch is unaffected.  Lanes may carry different numbers of responses (they are
+// grouped by rs.size()).  Exceptions are for the CALL: mismatching vector lengths, engine failures.
 //
 // mcl objects are passed WITHOUT conversion: G1/G2/Fr in memory are Montgomery limb arrays in exactly
 // the layout psb.h takes.  One curve per build, like mcl's own bn256 / bn384 libraries: with
@@ -27,11 +35,15 @@
 #ifndef PSB_HOST_PS_BATCH_HPP_
 #define PSB_HOST_PS_BATCH_HPP_
 
+#include <algorithm>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <tuple>
+#include <type_traits>
 #include <vector>
 
 #include "ps-requester.h"
@@ -78,6 +90,66 @@ struct Strings {
   const uint8_t* data() { if (blob.empty()) blob.push_back(0); return blob.data(); }
 };
 
+// The reference keeps the signer's secret X = g^x and its public key in PRIVATE members (src/ps-signer.h:92-95) and
+// offers no accessor.  Explicit template instantiation may name private members (access checks do not apply to its
+// arguments, [temp.spec]), which gives the batch layer read / write access WITHOUT touching the reference's sources,
+// the process-wide RandGen, or any lock.  A maintainer who prefers an in-class accessor finds the two-line patch in
+// INTEGRATION.md; this header then works unchanged.
+template <class Tag, typename Tag::type Member> struct MemberAccess {
+  friend typename Tag::type member_of(Tag) { return Member; }
+};
+typedef ::PSSigner RefSigner;   // (the reference's class; psb::PSSigner below derives from it)
+struct SignerSecretX { typedef mcl::bls12::G1 RefSigner::*type; friend type member_of(SignerSecretX); };
+struct SignerPubKey { typedef PSPubKey RefSigner::*type; friend type member_of(SignerPubKey); };
+template struct MemberAccess<SignerSecretX, &RefSigner::m_sk_X>;
+template struct MemberAccess<SignerPubKey, &RefSigner::m_pk>;
+
+inline unsigned marshal_threads(size_t lanes) {
+  if (lanes < 8192) return 1;
+  const unsigned hw = std::thread::hardware_concurrency();
+  return std::max(1u, std::min(hw ? hw : 4u, 16u));
+}
+template <class F> inline void parallel_lanes(size_t lanes, F f) {   // f(begin, end) on disjoint lane ranges
+  const unsigned T = marshal_threads(lanes);
+  if (T == 1) { f((size_t)0, lanes); return; }
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < T; t++) th.emplace_back([=] { f(lanes * t / T, lanes * (t + 1) / T); });
+  for (auto& x : th) x.join();
+}
+// N lanes x n strings -> blob + off[N * n + 1], in parallel (two passes: sizes, then copies).  get(j) returns lane j's
+// list; a lane whose list is not n long is flattened as n empty strings and flagged in bad[j].
+template <class Get>
+inline void flatten_lanes(size_t N, size_t n, Get get, std::vector<uint8_t>& blob, std::vector<uint64_t>& off,
+                          std::vector<uint8_t>& bad) {
+  std::vector<uint64_t> lane_bytes(N + 1, 0);
+  bad.assign(N, 0);
+  parallel_lanes(N, [&](size_t b, size_t e) {
+    for (size_t j = b; j < e; j++) {
+      const auto& l = get(j);
+      if (l.size() != n) { bad[j] = 1; continue; }
+      uint64_t t = 0;
+      for (const auto& a : l) t += a.size();
+      lane_bytes[j + 1] = t;
+    }
+  });
+  for (size_t j = 0; j < N; j++) lane_bytes[j + 1] += lane_bytes[j];
+  blob.resize((size_t)lane_bytes[N] + 8);
+  off.resize(N * n + 1);
+  off[N * n] = lane_bytes[N];
+  parallel_lanes(N, [&](size_t b, size_t e) {
+    for (size_t j = b; j < e; j++) {
+      uint64_t at = lane_bytes[j];
+      if (bad[j]) { for (size_t i = 0; i < n; i++) off[j * n + i] = at; continue; }
+      const auto& l = get(j);
+      for (size_t i = 0; i < n; i++) {
+        off[j * n + i] = at;
+        if (!l[i].empty()) std::memcpy(&blob[(size_t)at], l[i].data(), l[i].size());
+        at += l[i].size();
+      }
+    }
+  });
+}
+
 struct KeyDeleter { void operator()(psb_key* k) const { psb_key_destroy(k); } };
 using KeyHandle = std::shared_ptr<psb_key>;
 
@@ -89,30 +161,42 @@ inline KeyHandle make_key(const PSPubKey& pk, const mcl::bls12::G1* X_secret, in
   return KeyHandle(k, KeyDeleter());
 }
 
+// PSCredential is two G1 members and nothing else (src/ps-encoding.h:89-109): std::vector<PSCredential>::data() IS the
+// array of (sigma1, sigma2) pairs psb_verify_aos takes -- no per-credential copy
+static_assert(sizeof(PSCredential) == 2 * sizeof(mcl::bls12::G1), "PSCredential must be exactly (sig1, sig2)");
 inline std::vector<uint8_t> verify_batch(psb_key* key, size_t n, const std::vector<PSCredential>& sigs,
                                          const std::vector<std::vector<std::string>>& all_attributes) {
   const size_t N = sigs.size();
   if (all_attributes.size() != N) throw std::runtime_error("attribute size does not match");
-  std::vector<mcl::bls12::G1> s1(N), s2(N);
-  Strings at;
-  for (size_t j = 0; j < N; j++) {
-    if (all_attributes[j].size() != n) throw std::runtime_error("attribute size does not match");
-    s1[j] = sigs[j].sig1; s2[j] = sigs[j].sig2;
-    for (const auto& a : all_attributes[j]) at.add(a);
-  }
   std::vector<uint8_t> verdict(N);
   if (N == 0) return verdict;
-  check(psb_verify(key, N, u64(s1.data()), u64(s2.data()), at.data(), at.off.data(), nullptr, verdict.data(), nullptr),
-        "psb_verify");
+  std::vector<uint8_t> blob, bad;
+  std::vector<uint64_t> off;
+  flatten_lanes(N, n, [&](size_t j) -> const std::vector<std::string>& { return all_attributes[j]; }, blob, off, bad);
+  check(psb_verify_aos(key, N, u64(sigs.data()), blob.data(), off.data(), nullptr, verdict.data(), nullptr), "psb_verify_aos");
+  for (size_t j = 0; j < N; j++) if (bad[j]) verdict[j] = 0;   // wrong attribute count: undefined in the reference, rejected here
   return verdict;
+}
+// wire buffers -> blob + off[N + 1]
+template <class Buf>
+inline void flatten_wire(const std::vector<Buf>& bufs, std::vector<uint8_t>& blob, std::vector<uint64_t>& off) {
+  off.assign(bufs.size() + 1, 0);
+  for (size_t j = 0; j < bufs.size(); j++) off[j + 1] = off[j] + bufs[j].size();
+  blob.resize((size_t)off.back() + 8);
+  parallel_lanes(bufs.size(), [&](size_t b, size_t e) {
+    for (size_t j = b; j < e; j++) if (bufs[j].size()) std::memcpy(&blob[(size_t)off[j]], bufs[j].data(), bufs[j].size());
+  });
 }
 }  // namespace detail
 
 // ---- PSVerifier ----------------------------------------------------------------------------------------
 class PSVerifier : public ::PSVerifier {
 public:
-  explicit PSVerifier(const PSPubKey& pk, int window_bits = 0)
-      : ::PSVerifier(pk), m_n(pk.Yi.size()), m_key(detail::make_key(pk, nullptr, window_bits)) {}
+  // strict_sigma: the batched sign-on verification ALSO rejects sigma1 == 0 (PSB_VID_REJECT_ZERO_SIGMA).  The reference's
+  // el_passo_verify_id lacks that check: a proof with sigma1 = sigma2 = 0 and an honestly built NIZK
+  // passes it without any credential.  Default ON for the batch path; pass false for bit-exact reference verdicts.
+  explicit PSVerifier(const PSPubKey& pk, int window_bits = 0, bool strict_sigma = true)
+      : ::PSVerifier(pk), m_n(pk.Yi.size()), m_strict(strict_sigma), m_key(detail::make_key(pk, nullptr, window_bits)) {}
 
   using ::PSVerifier::verify;
   using ::PSVerifier::el_passo_verify_id;
@@ -135,23 +219,25 @@ public:
     if (all_attributes.size() != N) throw std::runtime_error("attribute size does not match");
     constexpr size_t S = kG1Ser, T = 2 + kG1Ser;   // compressed G1, one TLV-framed G1
     std::vector<uint8_t> flat(N * 2 * S + 1), verdict(N);
-    detail::Strings at;
-    for (size_t j = 0; j < N; j++) {
-      if (all_attributes[j].size() != m_n) throw std::runtime_error("attribute size does not match");
-      const PSBuffer& b = credentials[j];
-      if (b.size() == kCredSer && b[0] == 1 && b[1] == S && b[T] == 1 && b[T + 1] == S) {
-        std::memcpy(&flat[2 * S * j], &b[2], S);
-        std::memcpy(&flat[2 * S * j + S], &b[T + 2], S);
-      } else {
-        PSCredential c = PSCredential::fromBufferString(b);
-        c.sig1.serialize(&flat[2 * S * j], S);
-        c.sig2.serialize(&flat[2 * S * j + S], S);
-      }
-      for (const auto& a : all_attributes[j]) at.add(a);
-    }
     if (N == 0) return verdict;
-    check(psb_verify_ser(m_key.get(), N, flat.data(), 2 * S, 0, S, at.data(), at.off.data(), verdict.data(), nullptr),
+    std::vector<uint8_t> blob, bad;
+    std::vector<uint64_t> off;
+    detail::flatten_lanes(N, m_n, [&](size_t j) -> const std::vector<std::string>& { return all_attributes[j]; }, blob, off, bad);
+    detail::parallel_lanes(N, [&](size_t b0, size_t e0) {
+      for (size_t j = b0; j < e0; j++) {
+        const PSBuffer& b = credentials[j];
+        if (b.size() == kCredSer && b[0] == 1 && b[1] == S && b[T] == 1 && b[T + 1] == S) {
+          std::memcpy(&flat[2 * S * j], &b[2], S);
+          std::memcpy(&flat[2 * S * j + S], &b[T + 2], S);
+        } else {
+          bad[j] = 1;                              // not the canonical layout: the lane is rejected (all-zero = infinity = reject)
+          std::memset(&flat[2 * S * j], 0, 2 * S);
+        }
+      }
+    });
+    check(psb_verify_ser(m_key.get(), N, flat.data(), 2 * S, 0, S, blob.data(), off.data(), verdict.data(), nullptr),
           "psb_verify_ser");
+    for (size_t j = 0; j < N; j++) if (bad[j]) verdict[j] = 0;
     return verdict;
   }
 
@@ -168,7 +254,50 @@ public:
     return verify_id_batch(proofs, associated_data, service_name, nullptr, nullptr, nullptr);
   }
 
+  // The same two calls straight from the WIRE: wire[j] = base64 text (PSBuffer::toBase64 of IdProof::toBufferString(),
+  // what a relying party receives) when Buf is std::string, the raw bytes when Buf is PSBuffer.  base64, the TLV walk
+  // and the decompression of all points run on the GPU (psb_verify_id_ser); a malformed buffer is verdict 0.
+  template <class Buf>
+  std::vector<uint8_t> el_passo_verify_id(const std::vector<Buf>& wire, const std::vector<std::string>& associated_data,
+                                          const std::string& service_name, const mcl::bls12::G1& authority_pk,
+                                          const mcl::bls12::G1& g, const mcl::bls12::G1& h,
+                                          typename std::enable_if<!std::is_same<Buf, IdProof>::value>::type* = nullptr) const {
+    return verify_id_wire(wire, associated_data, service_name, &authority_pk, &g, &h);
+  }
+  template <class Buf>
+  std::vector<uint8_t> el_passo_verify_id_without_id_retrieval(const std::vector<Buf>& wire,
+                                                               const std::vector<std::string>& associated_data,
+                                                               const std::string& service_name,
+                                                               typename std::enable_if<!std::is_same<Buf, IdProof>::value>::type* = nullptr) const {
+    return verify_id_wire(wire, associated_data, service_name, nullptr, nullptr, nullptr);
+  }
+
 private:
+  int flags(bool with_id) const { return (with_id ? PSB_VID_WITH_ID : 0) | (m_strict ? PSB_VID_REJECT_ZERO_SIGMA : 0); }
+
+  template <class Buf>
+  std::vector<uint8_t> verify_id_wire(const std::vector<Buf>& wire, const std::vector<std::string>& ads,
+                                      const std::string& service_name, const mcl::bls12::G1* y, const mcl::bls12::G1* g,
+                                      const mcl::bls12::G1* h) const {
+    using namespace mcl::bls12;
+    static_assert(std::is_same<Buf, std::string>::value || std::is_same<Buf, PSBuffer>::value,
+                  "wire buffers are std::string (base64 text) or PSBuffer (bytes)");
+    const size_t N = wire.size();
+    if (ads.size() != N) throw std::runtime_error("associated data size does not match");
+    std::vector<uint8_t> verdict(N);
+    if (N == 0) return verdict;
+    std::vector<uint8_t> blob, adb;
+    std::vector<uint64_t> off, ado;
+    detail::flatten_wire(wire, blob, off);
+    detail::flatten_wire(ads, adb, ado);
+    G1 svc;
+    hashAndMapToG1(svc, service_name);   // one value per batch, on the host
+    check(psb_verify_id_ser(m_key.get(), N, blob.data(), off.data(), std::is_same<Buf, std::string>::value ? 1 : 0, adb.data(),
+                            ado.data(), detail::u64(&svc), y ? detail::u64(y) : nullptr, y ? detail::u64(g) : nullptr,
+                            y ? detail::u64(h) : nullptr, flags(y != nullptr), verdict.data(), nullptr), "psb_verify_id_ser");
+    return verdict;
+  }
+
   std::vector<uint8_t> verify_id_batch(const std::vector<IdProof>& proofs, const std::vector<std::string>& ads,
                                        const std::string& service_name, const mcl::bls12::G1* y, const mcl::bls12::G1* g,
                                        const mcl::bls12::G1* h) const {
@@ -176,41 +305,55 @@ private:
     const size_t N = proofs.size();
     const bool with_id = y != nullptr;
     if (ads.size() != N) throw std::runtime_error("associated data size does not match");
-    std::vector<uint8_t> verdict(N);
+    std::vector<uint8_t> verdict(N, 0);
     if (N == 0) return verdict;
-    const size_t per = proofs[0].rs.size();
-    std::vector<G1> s1(N), s2(N), phi(N), E1(with_id ? N : 0), E2(with_id ? N : 0);
-    std::vector<G2> k(N);
-    std::vector<Fr> c(N), rs(N * per + 1);
-    std::vector<uint8_t> missing(N, 0);
-    detail::Strings at, ad;
+    // lanes are grouped by their number of responses (proofs may hide different numbers of attributes); a lane with a
+    // wrong attribute count or without E1 / E2 (the reference returns false, ps-verifier.cc:68-70) is verdict 0 and
+    // does not enter any group
+    std::map<size_t, std::vector<size_t>> groups;
     for (size_t j = 0; j < N; j++) {
       const IdProof& p = proofs[j];
-      if (p.attributes.size() != m_n) throw std::runtime_error("attribute size does not match");
-      if (p.rs.size() != per) throw std::runtime_error("psb: proofs of one batch must carry the same number of responses");
-      s1[j] = p.sig1; s2[j] = p.sig2; k[j] = p.k; phi[j] = p.phi; c[j] = p.c;
-      for (size_t i = 0; i < per; i++) rs[j * per + i] = p.rs[i];
-      if (with_id) {
-        if (p.E1.has_value() && p.E2.has_value()) { E1[j] = *p.E1; E2[j] = *p.E2; }
-        else { E1[j].clear(); E2[j].clear(); missing[j] = 1; }   // reference returns false (ps-verifier.cc:68-70)
-      }
-      for (const auto& a : p.attributes) at.add(a);
-      ad.add(ads[j]);
+      if (p.attributes.size() != m_n) continue;
+      if (with_id && !(p.E1.has_value() && p.E2.has_value())) continue;
+      groups[p.rs.size()].push_back(j);
     }
     G1 svc;
     hashAndMapToG1(svc, service_name);   // one value per batch, on the host
-    check(psb_verify_id(m_key.get(), N, detail::u64(s1.data()), detail::u64(s2.data()), detail::u64(k.data()),
-                                detail::u64(phi.data()), with_id ? detail::u64(E1.data()) : nullptr,
-                                with_id ? detail::u64(E2.data()) : nullptr, detail::u64(c.data()), detail::u64(rs.data()), per,
-                                at.data(), at.off.data(), ad.data(), ad.off.data(), detail::u64(&svc),
-                                with_id ? detail::u64(y) : nullptr, with_id ? detail::u64(g) : nullptr,
-                                with_id ? detail::u64(h) : nullptr, with_id ? 1 : 0, verdict.data()),
-                  "psb_verify_id");
-    for (size_t j = 0; j < N; j++) if (missing[j]) verdict[j] = 0;
+    for (const auto& grp : groups) {
+      const size_t per = grp.first, M = grp.second.size();
+      const std::vector<size_t>& idx = grp.second;
+      std::vector<G1> s1(M), s2(M), phi(M), E1(with_id ? M : 0), E2(with_id ? M : 0);
+      std::vector<G2> k(M);
+      std::vector<Fr> c(M), rs(M * per + 1);
+      std::vector<uint8_t> blob, bad, adb, v(M);
+      std::vector<uint64_t> off, ado;
+      detail::flatten_lanes(M, m_n, [&](size_t t) -> const std::vector<std::string>& { return proofs[idx[t]].attributes; }, blob, off, bad);
+      detail::parallel_lanes(M, [&](size_t b0, size_t e0) {
+        for (size_t t = b0; t < e0; t++) {
+          const IdProof& p = proofs[idx[t]];
+          s1[t] = p.sig1; s2[t] = p.sig2; k[t] = p.k; phi[t] = p.phi; c[t] = p.c;
+          for (size_t i = 0; i < per; i++) rs[t * per + i] = p.rs[i];
+          if (with_id) { E1[t] = *p.E1; E2[t] = *p.E2; }
+        }
+      });
+      ado.assign(M + 1, 0);
+      for (size_t t = 0; t < M; t++) ado[t + 1] = ado[t] + ads[idx[t]].size();
+      adb.resize((size_t)ado[M] + 8);
+      for (size_t t = 0; t < M; t++) if (!ads[idx[t]].empty()) std::memcpy(&adb[(size_t)ado[t]], ads[idx[t]].data(), ads[idx[t]].size());
+      check(psb_verify_id(m_key.get(), M, detail::u64(s1.data()), detail::u64(s2.data()), detail::u64(k.data()),
+                          detail::u64(phi.data()), with_id ? detail::u64(E1.data()) : nullptr,
+                          with_id ? detail::u64(E2.data()) : nullptr, detail::u64(c.data()), detail::u64(rs.data()), per,
+                          blob.data(), off.data(), adb.data(), ado.data(), detail::u64(&svc),
+                          with_id ? detail::u64(y) : nullptr, with_id ? detail::u64(g) : nullptr,
+                          with_id ? detail::u64(h) : nullptr, flags(with_id), v.data()),
+            "psb_verify_id");
+      for (size_t t = 0; t < M; t++) verdict[idx[t]] = v[t];
+    }
     return verdict;
   }
 
   size_t m_n;
+  bool m_strict;
   detail::KeyHandle m_key;
 };
 
@@ -374,28 +517,31 @@ private:
 };
 
 // ---- PSSigner ------------------------------------------------------------------------------------------
-// The reference keeps X = g^x private (src/ps-signer.h:92) and drops the exponents.  The
-// batch path needs X on the device; key_gen() below recovers it through the PUBLIC API only: with the
-// process RandGen momentarily yielding u = 1, sign_commitment(g) returns (g, X + g) (ps-signer.cc:132-146).
-// A maintainer applying INTEGRATION.md's in-class patch reads m_sk_X directly instead.
+// The batch path needs the signer's secret X = g^x on the device.  The reference keeps it private and drops the
+// exponents (src/ps-signer.h:92); detail::MemberAccess reads it in place -- no RandGen games, no locks,
+// nothing process-wide.  A signer whose key was LOADED rather than generated uses the (pk, X) constructor.
 class PSSigner : public ::PSSigner {
 public:
   explicit PSSigner(size_t attribute_num, int window_bits = 0) : ::PSSigner(attribute_num), m_w(window_bits) {}
   PSSigner(size_t attribute_num, const mcl::bls12::G1& g, const mcl::bls12::G2& gg, int window_bits = 0)
       : ::PSSigner(attribute_num, g, gg), m_w(window_bits) {}
+  // existing key material: the public key and the secret X = g^x (e.g. from a key store).  The scalar methods of the
+  // base class work on the same key.
+  PSSigner(const PSPubKey& pk, const mcl::bls12::G1& X, int window_bits = 0)
+      : ::PSSigner(pk.Yi.size(), pk.g, pk.gg), m_w(window_bits) {
+    this->*member_of(detail::SignerPubKey()) = pk;
+    this->*member_of(detail::SignerSecretX()) = X;
+    m_n = pk.Yi.size();
+    m_key = detail::make_key(pk, &X, m_w);
+  }
 
   using ::PSSigner::el_passo_provide_id;
+  using ::PSSigner::sign_commitment;
+  using ::PSSigner::sign_hybrid;
 
   PSPubKey key_gen() {   // hides ::PSSigner::key_gen (not virtual there); same return value
-    using namespace mcl::bls12;
     PSPubKey pk = ::PSSigner::key_gen();
-    mcl::fp::RandGen saved = mcl::fp::RandGen::get();
-    mcl::fp::RandGen::setRandFunc(nullptr, read_one);
-    PSCredential s = ::PSSigner::sign_commitment(pk.g);
-    mcl::fp::RandGen::setRandGen(saved);
-    G1 X;
-    G1::sub(X, s.sig2, pk.g);
-    if (s.sig1 != pk.g) throw std::runtime_error("psb: could not recover the signer secret through sign_commitment");
+    const mcl::bls12::G1& X = this->*member_of(detail::SignerSecretX());
     m_n = pk.Yi.size();
     m_key = detail::make_key(pk, &X, m_w);
     return pk;
@@ -408,37 +554,103 @@ public:
                                            const std::vector<std::string>& associated_data,
                                            const std::vector<mcl::bls12::Fr>& u, std::vector<PSCredential>& sigs) const {
     using namespace mcl::bls12;
-    if (!m_key) throw std::runtime_error("psb: call key_gen() first");
+    need_key();
     const size_t N = requests.size();
     if (associated_data.size() != N || u.size() != N) throw std::runtime_error("psb: one associated_data and one u per request");
-    std::vector<uint8_t> verdict(N);
+    std::vector<uint8_t> verdict(N, 0);
     sigs.resize(N);
     if (N == 0) return verdict;
-    const size_t per = requests[0].rs.size();
-    std::vector<G1> A(N), o1(N), o2(N);
-    std::vector<Fr> c(N), rs(N * per + 1);
-    detail::Strings at, ad;
-    for (size_t j = 0; j < N; j++) {
-      const PSCredRequest& r = requests[j];
-      if (r.attributes.size() != m_n) throw std::runtime_error("attribute size does not match");
-      if (r.rs.size() != per) throw std::runtime_error("psb: requests of one batch must carry the same number of responses");
-      A[j] = r.A; c[j] = r.c;
-      for (size_t i = 0; i < per; i++) rs[j * per + i] = r.rs[i];
-      for (const auto& a : r.attributes) at.add(a);
-      ad.add(associated_data[j]);
+    std::map<size_t, std::vector<size_t>> groups;   // by number of responses; wrong attribute count = verdict 0
+    for (size_t j = 0; j < N; j++) if (requests[j].attributes.size() == m_n) groups[requests[j].rs.size()].push_back(j);
+    for (const auto& grp : groups) {
+      const size_t per = grp.first, M = grp.second.size();
+      const std::vector<size_t>& idx = grp.second;
+      std::vector<G1> A(M), o1(M), o2(M);
+      std::vector<Fr> c(M), rs(M * per + 1), uu(M);
+      std::vector<uint8_t> blob, bad, adb, v(M);
+      std::vector<uint64_t> off, ado(M + 1, 0);
+      detail::flatten_lanes(M, m_n, [&](size_t t) -> const std::vector<std::string>& { return requests[idx[t]].attributes; }, blob, off, bad);
+      for (size_t t = 0; t < M; t++) {
+        const PSCredRequest& r = requests[idx[t]];
+        A[t] = r.A; c[t] = r.c; uu[t] = u[idx[t]];
+        for (size_t i = 0; i < per; i++) rs[t * per + i] = r.rs[i];
+        ado[t + 1] = ado[t] + associated_data[idx[t]].size();
+      }
+      adb.resize((size_t)ado[M] + 8);
+      for (size_t t = 0; t < M; t++)
+        if (!associated_data[idx[t]].empty()) std::memcpy(&adb[(size_t)ado[t]], associated_data[idx[t]].data(), associated_data[idx[t]].size());
+      check(psb_provide_id(m_key.get(), M, detail::u64(A.data()), detail::u64(c.data()), detail::u64(rs.data()), per,
+                           blob.data(), off.data(), adb.data(), ado.data(), detail::u64(uu.data()), v.data(),
+                           detail::u64(o1.data()), detail::u64(o2.data()), nullptr), "psb_provide_id");
+      for (size_t t = 0; t < M; t++) {
+        verdict[idx[t]] = v[t];
+        if (v[t]) { sigs[idx[t]].sig1 = o1[t]; sigs[idx[t]].sig2 = o2[t]; }
+      }
     }
-    check(psb_provide_id(m_key.get(), N, detail::u64(A.data()), detail::u64(c.data()), detail::u64(rs.data()), per,
-                                 at.data(), at.off.data(), ad.data(), ad.off.data(), detail::u64(u.data()), verdict.data(),
-                                 detail::u64(o1.data()), detail::u64(o2.data()), nullptr), "psb_provide_id");
+    return verdict;
+  }
+
+  // the same from the WIRE: wire[j] = base64 text (std::string) or bytes (PSBuffer) of PSCredRequest::toBufferString()
+  template <class Buf>
+  std::vector<uint8_t> el_passo_provide_id(const std::vector<Buf>& wire, const std::vector<std::string>& associated_data,
+                                           const std::vector<mcl::bls12::Fr>& u, std::vector<PSCredential>& sigs,
+                                           typename std::enable_if<!std::is_same<Buf, PSCredRequest>::value>::type* = nullptr) const {
+    using namespace mcl::bls12;
+    static_assert(std::is_same<Buf, std::string>::value || std::is_same<Buf, PSBuffer>::value,
+                  "wire buffers are std::string (base64 text) or PSBuffer (bytes)");
+    need_key();
+    const size_t N = wire.size();
+    if (associated_data.size() != N || u.size() != N) throw std::runtime_error("psb: one associated_data and one u per request");
+    std::vector<uint8_t> verdict(N, 0);
+    sigs.resize(N);
+    if (N == 0) return verdict;
+    std::vector<uint8_t> blob, adb;
+    std::vector<uint64_t> off, ado;
+    detail::flatten_wire(wire, blob, off);
+    detail::flatten_wire(associated_data, adb, ado);
+    std::vector<G1> o1(N), o2(N);
+    check(psb_provide_id_ser(m_key.get(), N, blob.data(), off.data(), std::is_same<Buf, std::string>::value ? 1 : 0, adb.data(),
+                             ado.data(), detail::u64(u.data()), verdict.data(), detail::u64(o1.data()), detail::u64(o2.data()),
+                             nullptr, nullptr), "psb_provide_id_ser");
     for (size_t j = 0; j < N; j++) if (verdict[j]) { sigs[j].sig1 = o1[j]; sigs[j].sig2 = o2[j]; }
     return verdict;
   }
 
+  // batched sign_commitment (src/ps-signer.cc:132-146): (u[j] g, u[j] (X + commitments[j])), u host-supplied
+  std::vector<PSCredential> sign_commitment(const std::vector<mcl::bls12::G1>& commitments,
+                                            const std::vector<mcl::bls12::Fr>& u) const {
+    return sign_batch(commitments, nullptr, u);
+  }
+  // batched sign_hybrid (src/ps-signer.cc:112-130): every lane carries the same number of attribute strings ("" = committed)
+  std::vector<PSCredential> sign_hybrid(const std::vector<mcl::bls12::G1>& commitments,
+                                        const std::vector<std::vector<std::string>>& attributes,
+                                        const std::vector<mcl::bls12::Fr>& u) const {
+    return sign_batch(commitments, &attributes, u);
+  }
+
 private:
-  static uint32_t read_one(void*, void* buf, uint32_t n) {   // little-endian integer 1
-    std::memset(buf, 0, n);
-    if (n) static_cast<uint8_t*>(buf)[0] = 1;
-    return n;
+  void need_key() const { if (!m_key) throw std::runtime_error("psb: call key_gen() first (or construct from (pk, X))"); }
+  std::vector<PSCredential> sign_batch(const std::vector<mcl::bls12::G1>& cm, const std::vector<std::vector<std::string>>* attrs,
+                                       const std::vector<mcl::bls12::Fr>& u) const {
+    using namespace mcl::bls12;
+    need_key();
+    const size_t N = cm.size();
+    if (u.size() != N || (attrs && attrs->size() != N)) throw std::runtime_error("psb: one u (and one attribute list) per commitment");
+    std::vector<PSCredential> out(N);
+    if (N == 0) return out;
+    const size_t na = attrs ? (*attrs)[0].size() : 0;
+    if (na > m_n) throw std::runtime_error("attribute size does not match");
+    std::vector<uint8_t> blob, bad;
+    std::vector<uint64_t> off;
+    if (na) {
+      detail::flatten_lanes(N, na, [&](size_t j) -> const std::vector<std::string>& { return (*attrs)[j]; }, blob, off, bad);
+      for (size_t j = 0; j < N; j++) if (bad[j]) throw std::runtime_error("psb: all lanes of a sign_hybrid batch carry the same number of attributes");
+    }
+    std::vector<G1> o1(N), o2(N);
+    check(psb_sign(m_key.get(), N, detail::u64(cm.data()), na, na ? blob.data() : nullptr, na ? off.data() : nullptr,
+                   detail::u64(u.data()), detail::u64(o1.data()), detail::u64(o2.data()), nullptr), "psb_sign");
+    for (size_t j = 0; j < N; j++) { out[j].sig1 = o1[j]; out[j].sig2 = o2[j]; }
+    return out;
   }
   int m_w;
   size_t m_n = 0;

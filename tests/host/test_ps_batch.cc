@@ -186,10 +186,105 @@ int main(int argc, char** argv) {
     }
   }
 
-  // size mismatch raises like the reference's requester (src/ps-requester.cc:31-33)
-  bool threw = false;
-  try { plain[0].pop_back(); rp.verify(vc, plain); } catch (const std::runtime_error&) { threw = true; }
-  EXPECT(threw);
+  // ---- sign-on and issuance straight from the WIRE (base64 text / PSBuffer bytes parsed on the GPU) ---------------
+  {
+    psb::PSVerifier exact(pk, 8, /*strict_sigma=*/false);      // bit-exact reference verdicts
+    std::vector<std::string> b64, b64n;
+    std::vector<PSBuffer> raw;
+    for (size_t j = 0; j < N; j++) {
+      PSBuffer b = proofs[j].toBufferString();
+      raw.push_back(b);
+      b64.push_back(b.toBase64());
+      b64n.push_back(proofs2[j].toBufferString().toBase64());
+    }
+    if (N > 8) { b64[7] = b64[7].substr(0, 37); raw[8][0] = 2; }   // a truncated text, a wrong type byte
+    std::vector<uint8_t> x1 = exact.el_passo_verify_id(b64, ads, "service", authority_pk, g, h);
+    std::vector<uint8_t> x2 = exact.el_passo_verify_id(raw, ads, "service", authority_pk, g, h);
+    std::vector<uint8_t> x3 = exact.el_passo_verify_id_without_id_retrieval(b64n, ads, "service");
+    for (size_t j = 0; j < N; j++) {
+      if (N > 8 && j == 7) { EXPECT(x1[j] == 0); EXPECT(x2[j] == w1[j]); }
+      else if (N > 8 && j == 8) { EXPECT(x2[j] == 0); EXPECT(x1[j] == w1[j]); }
+      else { EXPECT(x1[j] == w1[j]); EXPECT(x2[j] == w1[j]); }
+      EXPECT(x3[j] == w2[j]);
+    }
+    // proofs hiding DIFFERENT numbers of attributes in one batch (lanes are grouped by rs.size())
+    std::vector<IdProof> mixed = proofs;
+    std::vector<size_t> three;
+    for (size_t j = 9; j < N && j < 12; j++) {
+      auto a3 = attrs[j];
+      std::get<1>(a3[2]) = true;
+      mixed[j] = users[j].el_passo_prove_id(creds[j], a3, ads[j], "service", authority_pk, g, h);
+      three.push_back(j);
+    }
+    std::vector<uint8_t> m1 = exact.el_passo_verify_id(mixed, ads, "service", authority_pk, g, h);
+    for (size_t j = 0; j < N; j++)
+      EXPECT(static_cast<const ::PSVerifier&>(exact).el_passo_verify_id(mixed[j], ads[j], "service", authority_pk, g, h) == (m1[j] != 0));
+    for (size_t j : three) EXPECT(mixed[j].rs.size() == 5 && m1[j] == 1);
+    // strict default: sigma = (0, 0) with an honest NIZK passes the reference, the batch classes reject it unless told otherwise
+    if (N > 12) {
+      std::vector<IdProof> z = proofs;
+      z[12].sig1.clear(); z[12].sig2.clear();
+      EXPECT(static_cast<const ::PSVerifier&>(rp).el_passo_verify_id(z[12], ads[12], "service", authority_pk, g, h));
+      EXPECT(exact.el_passo_verify_id(z, ads, "service", authority_pk, g, h)[12] == 1);
+      EXPECT(rp.el_passo_verify_id(z, ads, "service", authority_pk, g, h)[12] == 0);
+    }
+    // issuance from wire requests
+    std::vector<std::string> rq64;
+    for (auto& r : requests) rq64.push_back(r.toBufferString().toBase64());
+    std::vector<PSCredential> iss3;
+    std::vector<uint8_t> ok3 = idp.el_passo_provide_id(rq64, ads, u, iss3);
+    for (size_t j = 0; j < N; j++) {
+      EXPECT(ok3[j] == ok[j]);
+      if (ok[j]) EXPECT(ser(iss3[j].sig1) == ser(issued[j].sig1) && ser(iss3[j].sig2) == ser(issued[j].sig2));
+    }
+  }
+
+  // ---- a signer built from LOADED key material (pk, X) + batched sign_commitment / sign_hybrid ------------------------
+  {
+    const G1 X = idp.*member_of(psb::detail::SignerSecretX());
+    psb::PSSigner idp2(pk, X, 8);
+    std::vector<PSCredential> iss4;
+    std::vector<uint8_t> ok4 = idp2.el_passo_provide_id(requests, ads, u, iss4);
+    for (size_t j = 0; j < N; j++) {
+      EXPECT(ok4[j] == ok[j]);
+      if (ok[j]) EXPECT(ser(iss4[j].sig2) == ser(issued[j].sig2));
+    }
+    PSCredential sc; EXPECT(static_cast<const ::PSSigner&>(idp2).el_passo_provide_id(requests[0], ads[0], sc));   // scalar methods share the key
+    std::vector<G1> cm(N);
+    for (size_t j = 0; j < N; j++) cm[j] = requests[j].A;
+    std::vector<PSCredential> s5 = idp2.sign_commitment(cm, u);
+    std::vector<std::vector<std::string>> hy(N);
+    for (size_t j = 0; j < N; j++) for (size_t i = 0; i < n; i++) hy[j].push_back(i < 2 ? std::string() : plain[j][i]);
+    std::vector<PSCredential> s6 = idp2.sign_hybrid(cm, hy, u);
+    for (size_t j = 0; j < N; j++) {
+      G1 ug, t2, full = cm[j];
+      G1::mul(ug, pk.g, u[j]);
+      G1::add(t2, X, cm[j]); G1::mul(t2, t2, u[j]);
+      EXPECT(ser(s5[j].sig1) == ser(ug) && ser(s5[j].sig2) == ser(t2));
+      for (size_t i = 2; i < n; i++) { Fr m; m.setHashOf(plain[j][i]); G1 y; G1::mul(y, pk.Yi[i], m); G1::add(full, full, y); }
+      G1::add(t2, X, full); G1::mul(t2, t2, u[j]);
+      EXPECT(ser(s6[j].sig1) == ser(ug) && ser(s6[j].sig2) == ser(t2));
+      if (ok[j]) EXPECT(ser(s6[j].sig2) == ser(issued[j].sig2));   // provide_id = NIZK check + sign_hybrid
+    }
+  }
+
+  // a lane with the wrong number of attributes is DATA (verdict 0), not an exception: the reference indexes m_pk.YYi out
+  // of range there (src/ps-verifier.cc:26), and one malformed lane must not abort the honest ones
+  {
+    std::vector<std::vector<std::string>> p2 = plain;
+    p2[0].pop_back();
+    std::vector<uint8_t> v9 = rp.verify(vc, p2);
+    EXPECT(v9[0] == 0);
+    for (size_t j = 1; j < N; j++) EXPECT(v9[j] == v1[j]);
+    std::vector<IdProof> pz = proofs;
+    pz[1].attributes.pop_back();
+    std::vector<uint8_t> w9 = rp.el_passo_verify_id(pz, ads, "service", authority_pk, g, h);
+    EXPECT(w9[1] == 0);
+    for (size_t j = 0; j < N; j++) if (j != 1) EXPECT(w9[j] == w1[j]);
+    bool threw = false;       // the CALL is still checked: one attribute list per credential
+    try { p2.pop_back(); rp.verify(vc, p2); } catch (const std::runtime_error&) { threw = true; }
+    EXPECT(threw);
+  }
 
   std::printf("test_ps_batch: %zu lanes, %llu kernel launches, %d failures\n", N, (unsigned long long)psb_launch_count(), fails);
   return fails ? 1 : 0;
