@@ -32,7 +32,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-R_ORDER = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+R_ORDERS = {"bls12_381": 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001,
+            # mcl's BN254 = the Barreto-Naehrig curve with z = -(2^62 + 2^55 + 1) (mcl/include/mcl/curve_type.h), not alt_bn128
+            "bn254": (lambda z: 36 * z ** 4 + 36 * z ** 3 + 18 * z ** 2 + 6 * z + 1)(-((1 << 62) + (1 << 55) + 1))}
+R_ORDER = R_ORDERS["bls12_381"]   # main() switches both for --curve bn254
+FPW = 6                           # u64 words of an Fp (BN254: 4)
 N_ATTRS = 5
 # algorithmic work per verification in 32x32->64 multiply-accumulates:
 FPMUL_MAC32 = 300
@@ -52,6 +56,7 @@ A_MILLER2 = 7673 - 680 - 39  # two-pairing Miller loop, FpMul-eq
 #           and raises to their value 105 = (2^3-1)(2^4-1) with 7 squarings + 2 products instead of 6 + 3: 5 * 36 = 180 fewer
 A_FINALEXP = 6100 + 480 - (476 - 8) - 1145 - 303 - 180 - 180
 A_MSM_PER_ADD = 29    # one mixed Jacobian+affine G2 addition
+TRAFFIC_FILE = "r1zb_traffic.json"   # latest committed ncu DRAM-traffic capture (profiles/)
 
 
 def a_verify_fpmul(n_attrs: int, window_bits: int) -> float:
@@ -61,9 +66,10 @@ def a_verify_fpmul(n_attrs: int, window_bits: int) -> float:
 
 def fr_hash(msg: bytes) -> int:
     """Fr::setHashOf rule (host-side scalar bookkeeping of the workload generator)."""
-    x = int.from_bytes(hashlib.sha256(msg).digest(), "little") & ((1 << 255) - 1)
+    bits = R_ORDER.bit_length()    # mcl setArrayMask: keep bitSize bits, one fewer if that is still >= r
+    x = int.from_bytes(hashlib.sha256(msg).digest(), "little") & ((1 << bits) - 1)
     if x >= R_ORDER:
-        x &= (1 << 254) - 1
+        x &= (1 << (bits - 1)) - 1
     return x
 
 
@@ -75,42 +81,100 @@ def fr_mont(vals) -> np.ndarray:
 
 
 def load_key(n: int):
-    with open(os.path.join(ROOT, "tests", "golden", "keys.json")) as f:
+    with open(os.path.join(ROOT, "tests", "golden", "keys.json" if FPW == 6 else "keys_bn254.json")) as f:
         k = json.load(f)["keys"][str(n)]
     arr = lambda h, w: np.frombuffer(bytes.fromhex(h), dtype=np.uint64).reshape(-1, w).copy()  # noqa: E731
-    return dict(g=arr(k["g"], 18), gg=arr(k["gg"], 36), XX=arr(k["XX"], 36), Y=arr(k["Y"], 18), YY=arr(k["YY"], 36),
-                X=arr(k["X"], 18), x=int(k["x"], 16), y=[int(v, 16) for v in k["y"]])
+    g1, g2 = 3 * FPW, 6 * FPW
+    return dict(g=arr(k["g"], g1), gg=arr(k["gg"], g2), XX=arr(k["XX"], g2), Y=arr(k["Y"], g1), YY=arr(k["YY"], g2),
+                X=arr(k["X"], g1), x=int(k["x"], 16), y=[int(v, 16) for v in k["y"]])
 
 
-def make_batch(pkg, key, lanes: int, rank: int, base: int = 1 << 14):
-    """(sig1, sig2, blob, off, expected verdict) for `lanes` lanes."""
+def fr_val(raw: np.ndarray) -> int:
+    """value of an Fr given as raw Montgomery limbs (4 x u64)."""
+    return int.from_bytes(raw.tobytes(), "little") * pow(1 << 256, -1, R_ORDER) % R_ORDER
+
+
+def tile_packed(blob: np.ndarray, off: np.ndarray, reps: int):
+    """(blob, off) of k strings -> the same k strings repeated `reps` times (numpy only, no Python loop)."""
+    total, k = int(off[-1]), off.shape[0] - 1
+    if reps == 1:
+        return blob, off
+    b = np.concatenate([np.tile(blob[:total], reps), np.zeros(8, dtype=np.uint8)])
+    o = np.empty(k * reps + 1, dtype=np.uint64)
+    o[:-1] = (np.tile(off[:-1], reps).reshape(reps, k) + (np.arange(reps, dtype=np.uint64) * np.uint64(total))[:, None]).reshape(-1)
+    o[-1] = total * reps
+    return b, o
+
+
+def attr_lists(n_attrs: int, lanes: int):
+    return [[b"a%d:%d" % (i, j) for i in range(n_attrs)] for j in range(lanes)]
+
+
+def honest_credentials(pkg, key, n_attrs: int, lanes: int, seed: int, base: int):
+    """`lanes` distinct honest credentials under `key`: `base` signatures built from known exponents with the engine's
+    own G1 kernels (sigma1 = u g, sigma2 = s sigma1, s = x + sum y_i m_i), expanded by per-lane randomisation
+    (psb_randomize).  Lane j carries the attribute list of base lane j % base.  Returns sig1, sig2 and k with sigma2 = k g
+    resolved lazily (the sigma2 += g tamper needs it)."""
     base = min(base, lanes)
-    rng = np.random.default_rng(1000 + rank)
-    attrs = [[b"a%d:%d" % (i, j) for i in range(N_ATTRS)] for j in range(base)]
-    s = [(key["x"] + sum(key["y"][i] * fr_hash(a[i]) for i in range(N_ATTRS))) % R_ORDER for a in attrs]
+    rng = np.random.default_rng(seed)
+    attrs = attr_lists(n_attrs, base)
+    s = [(key["x"] + sum(key["y"][i] * fr_hash(a[i]) for i in range(n_attrs))) % R_ORDER for a in attrs]
     u = [int.from_bytes(rng.bytes(32), "little") % R_ORDER for _ in range(base)]
     b1 = pkg.g1_mul(key["g"], fr_mont(u))                                  # sigma1 = u g
     b2 = pkg.g1_mul(key["g"], fr_mont([a * b % R_ORDER for a, b in zip(u, s)]))  # sigma2 = s sigma1
     reps = (lanes + base - 1) // base
-    sig1 = np.tile(b1, (reps, 1))[:lanes].copy()
-    sig2 = np.tile(b2, (reps, 1))[:lanes].copy()
-    if reps > 1:  # make every lane distinct: (t sigma1, t sigma2) with a per-lane t
+    t = None
+    if reps == 1:
+        sig1, sig2 = b1[:lanes].copy(), b2[:lanes].copy()
+    else:  # make every lane distinct: (t sigma1, t sigma2) with a per-lane t
+        sig1 = np.empty((lanes, b1.shape[1]), dtype=np.uint64)
+        sig2 = np.empty_like(sig1)
         t = np.frombuffer(rng.bytes(32 * lanes), dtype=np.uint64).reshape(lanes, 4).copy()
         t[:, 3] &= np.uint64(0x0FFFFFFFFFFFFFFF)  # < r; raw limbs are simply interpreted as Montgomery form
-        sig1, sig2 = pkg.PSRequester.randomize_credential(sig1, sig2, t)
-    lane_attrs = [attrs[j % base] for j in range(lanes)]
+        step = base * max(1, (1 << 21) // base)
+        for a in range(0, lanes, step):
+            e = min(lanes, a + step)
+            r = (e - a + base - 1) // base
+            sig1[a:e], sig2[a:e] = pkg.PSRequester.randomize_credential(np.tile(b1, (r, 1))[:e - a], np.tile(b2, (r, 1))[:e - a], t[a:e])
+
+    def sigma2_exponent(j: int) -> int:
+        k = u[j % base] * s[j % base] % R_ORDER
+        return k * fr_val(t[j]) % R_ORDER if t is not None else k
+    return sig1, sig2, attrs, sigma2_exponent
+
+
+def make_batch(pkg, key, lanes: int, rank: int, base: int = 1 << 14, n_attrs: int = N_ATTRS, tamper_every: int = 1024,
+               attr_period: int = 0):
+    """(sig1, sig2, blob, off, expected verdict) for `lanes` lanes; every `tamper_every`-th lane is tampered, cycling
+    through SURVEY 8d's four kinds: sigma1 <-> sigma2, sigma1 = 0, an attribute byte changed, sigma2 += g.
+    attr_period (a multiple of base and of 4 * tamper_every that divides lanes): blob / off describe only that many lanes --
+    lane j carries the strings of lane j % attr_period (a large batch is verified in chunks that share them)."""
+    base = min(base, lanes)
+    period = attr_period or lanes
+    assert lanes % period == 0 and (period == lanes or (period % base == 0 and period % (4 * tamper_every) == 0))
+    sig1, sig2, attrs, s2exp = honest_credentials(pkg, key, n_attrs, lanes, 1000 + rank, base)
+    bblob, boff = pkg.pack_attrs(attrs)
+    reps = (period + base - 1) // base
+    blob, off = tile_packed(bblob, boff, reps)
+    if reps * base != period:
+        off = off[:period * n_attrs + 1].copy()
+    blob = blob.copy()
     expected = np.ones(lanes, dtype=np.uint8)
-    for n_t, j in enumerate(range(1023, lanes, 1024)):
-        kind = n_t % 3
+    plus_g = []
+    for n_t, j in enumerate(range(tamper_every - 1, lanes, tamper_every)):
+        kind = n_t % 4
         if kind == 0:
             sig1[j], sig2[j] = sig2[j].copy(), sig1[j].copy()
         elif kind == 1:
             sig1[j] = 0
-        else:
-            a = list(lane_attrs[j]); a[0] = b"b" + a[0][1:]; lane_attrs[j] = a
+        elif kind == 2:
+            blob[int(off[(j % period) * n_attrs])] = ord("b")   # b"a0:j" -> b"b0:j"
+        else:                                               # sigma2 + g = (k + 1) g: a valid point, full pairing, must fail
+            plus_g.append((j, (s2exp(j) + 1) % R_ORDER))
         expected[j] = 0
-    blob, off = pkg.pack_attrs(lane_attrs)
-    return sig1, sig2, blob, off, expected, lane_attrs
+    if plus_g:
+        sig2[[j for j, _ in plus_g]] = pkg.g1_mul(key["g"], fr_mont([k for _, k in plus_g]))
+    return sig1, sig2, blob, off, expected
 
 
 class ClockSampler:
@@ -154,24 +218,30 @@ class ClockSampler:
                 "power_w_max": max(float(r[2]) for r in self.rows if len(r) >= 7), "samples": len(sm)}
 
 
-def cpu_reference_verify(key_n: int, sig1, sig2, lane_attrs, budget_s: float):
+def packed_prefix(blob, off, strings: int):
+    """(blob, off) of the first `strings` strings of a packed pair (views; the reference harness only reads)."""
+    return blob, np.ascontiguousarray(off[:strings + 1])
+
+
+def cpu_reference_verify(key_n: int, sig1, sig2, blob, off, budget_s: float, pairings: bool = True):
     """the reference's own PSVerifier::verify (mcl) on all host threads over a bounded lane sample."""
     from oracle import ref
     km = ref.KeyMaterial(key_n, seed_=1)
     threads = ref.hw_threads()
-    n = min(len(lane_attrs), 64 * threads)
-    blob, off = ref.pack_attrs(lane_attrs[:n])
-    v, t = ref.ps_verify_packed(km, sig1[:n].copy(), sig2[:n].copy(), blob, off, nthreads=threads, timed=True)
+    lanes = sig1.shape[0]
+    n = min(lanes, 64 * threads)
+    v, t = ref.ps_verify_packed(km, sig1[:n].copy(), sig2[:n].copy(), *packed_prefix(blob, off, n * key_n), nthreads=threads, timed=True)
     rate = n / t
-    n2 = int(min(len(lane_attrs), max(n, rate * budget_s)))
+    n2 = int(min(lanes, max(n, rate * budget_s)))
     if n2 > n:
-        blob, off = ref.pack_attrs(lane_attrs[:n2])
-        v, t = ref.ps_verify_packed(km, sig1[:n2].copy(), sig2[:n2].copy(), blob, off, nthreads=threads, timed=True)
+        v, t = ref.ps_verify_packed(km, sig1[:n2].copy(), sig2[:n2].copy(), *packed_prefix(blob, off, n2 * key_n), nthreads=threads, timed=True)
         n = n2
-    pair_iters = 200
-    tp = ref.time_pairing(pair_iters, threads)
-    return dict(verdict=v, lanes=n, seconds=t, threads=threads, rate=n / t, pairings_per_s=pair_iters * threads / tp,
-                jit=ref.jit_enabled())
+    out = dict(verdict=v, lanes=n, seconds=t, threads=threads, rate=n / t, jit=ref.jit_enabled())
+    if pairings:
+        pair_iters = 200
+        tp = ref.time_pairing(pair_iters, threads)
+        out["pairings_per_s"] = pair_iters * threads / tp
+    return out
 
 
 def max_over_ranks(values, world: int, device=None):
@@ -189,6 +259,348 @@ def max_over_ranks(values, world: int, device=None):
 def job_throughput(lanes_per_rank: int, world: int, steps: int, ms_max: float) -> float:
     """whole-job units per second: every rank processed lanes_per_rank * steps lanes in ms_max (weak scaling)."""
     return world * lanes_per_rank * steps / (ms_max * 1e-3)
+
+
+# ---- the other BASELINE.json configs (configs[2..4]) -- one entry each in the line's "configs" object ----------------
+# Inputs are made with the engine's OWN prover side (psb_prove_id / psb_request_id, parity-tested in tests/test_gpu_prover.py)
+# from honest credentials with known exponents; the reference (oracle/_ref) only checks a lane sample and is timed on it.
+def rand_fr(rng, shape) -> np.ndarray:
+    t = np.frombuffer(rng.bytes(32 * int(np.prod(shape))), dtype=np.uint64).reshape(*shape, 4).copy()
+    t[..., 3] &= np.uint64(0x0FFFFFFFFFFFFFFF)
+    return t
+
+
+class Ranks:
+    """what a config needs from the launch: rank, world size, a barrier and the MAX over ranks of its times.  The configs
+    synchronise over a gloo side group with a timeout, so a config that throws on one rank cannot leave the others waiting
+    forever inside an NCCL collective: they time out, every later config is reported as an error, the headline line survives."""
+
+    def __init__(self, rank, world, dev, torch=None, group=None):
+        self.rank, self.world, self.dev, self.torch, self.group, self.failed = rank, world, dev, torch, group, False
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier(group=self.group)
+        if self.torch is not None:
+            self.torch.cuda.synchronize(self.dev)
+
+    def timed(self, fn, steps):
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = fn()
+        return out, time.perf_counter() - t0
+
+    def max_ms(self, values):
+        if self.world <= 1:
+            return [float(v) for v in values]
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor(values, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return [float(v) for v in t]
+
+
+def _ref_sample_lanes(lanes: int) -> int:
+    return min(lanes, 1024)
+
+
+def cfg_signon(pkg, rk: Ranks, steps: int, window_bits: int, lanes: int, cpu: bool, wire: bool):
+    """configs[2]: EL PASSO relying-party sign-on verification -- PSVerifier::el_passo_verify_id (src/ps-verifier.cc:37-138),
+    10 attributes (2 hidden), `lanes` requests per GPU; plus the same requests arriving as IdProof::toBufferString bytes."""
+    n, nh, base = 10, 2, min(1 << 12, lanes)
+    key = load_key(n)
+    pk = pkg.PSPubKey(key["g"], key["gg"], key["XX"], key["Y"], key["YY"], window_bits=window_bits)
+    sig1, sig2, attrs, _ = honest_credentials(pkg, key, n, lanes, 3000 + rk.rank, base)
+    hidden = np.zeros(n, dtype=np.uint8)
+    hidden[:nh] = 1
+    reps = lanes // base
+    shown = [[b"" if hidden[i] else a[i] for i in range(n)] for a in attrs]
+    ads = [b"sess%d" % j for j in range(base)]
+    all_p, shown_p, ads_p = (tile_packed(*pkg.pack_attrs(attrs), reps), tile_packed(*pkg.pack_attrs(shown), reps),
+                             tile_packed(*pkg.pack_strings(ads), reps))
+    pts, ok = pkg.hash_and_map_to_g1([b"rp.example", b"ghi", b"abc", b"jkl"])
+    assert ok.all()
+    service_pt, y, g, h = pts[0:1], pts[1:2], pts[2:3], pts[3:4]
+    rng = np.random.default_rng(3100 + rk.rank)
+    rq = pkg.PSRequester(pk)
+    proof = rq.el_passo_prove_id(sig1, sig2, all_p, hidden, ads_p, service_pt, y, g, h, rnd=rand_fr(rng, (lanes, nh + 5)), with_id=True)
+    expected = np.ones(lanes, dtype=np.uint8)
+    for t, j in enumerate(range(63, lanes, 64)):      # challenge, response, sigma2 and k of every 64th proof tampered
+        kind = t % 4
+        if kind == 0:
+            proof["c"][j, 0] ^= np.uint64(1)
+        elif kind == 1:
+            proof["rs"][j, 0, 0] ^= np.uint64(1)
+        elif kind == 2:
+            proof["sig2"][j] = proof["sig2"][j - 1]
+        else:
+            proof["k"][j] = proof["k"][j - 1]
+        expected[j] = 0
+    ver = pkg.PSVerifier(pk)
+    call = lambda: ver.el_passo_verify_id(proof, shown_p, ads_p, service_pt, y, g, h, with_id=True)  # noqa: E731
+    call()                                            # tables + staging buffers
+    l0 = pkg.launch_count()
+    got, dt = rk.timed(call, steps)
+    launches = pkg.launch_count() - l0
+    ok_local = bool(np.array_equal(got, expected))
+    h2d = int(sum(v.nbytes for v in proof.values()) + shown_p[0].nbytes + shown_p[1].nbytes + ads_p[0].nbytes + ads_p[1].nbytes)
+    out = {"call": "PSVerifier::el_passo_verify_id (psb_verify_id)", "n_attrs": n, "hidden": nh, "lanes_per_gpu": lanes,
+           "metric": "signon_verifications_per_sec", "unit": "verifications/s", "steps": steps, "window_bits": window_bits,
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": lanes, "gpu_launches": int(launches), "tampered_lanes": int((expected == 0).sum()),
+           "inputs": "proofs made by psb_prove_id from honest credentials, every lane distinct"}
+    local = [dt * 1e3, 0.0 if ok_local else 1.0]
+    if wire:
+        ser = pkg.idproof_serialize(proof, shown_p, pk.n)
+        wcall = lambda: ver.el_passo_verify_id_wire(ser, ads_p, service_pt, y, g, h, with_id=True)  # noqa: E731
+        wcall()
+        (wgot, wparsed), wdt = rk.timed(wcall, steps)
+        local += [wdt * 1e3, 0.0 if (np.array_equal(wgot, expected) and wparsed.all()) else 1.0]
+        out["wire"] = {"call": "psb_verify_id_ser: IdProof::toBufferString bytes parsed and decompressed on the device",
+                       "h2d_bytes_per_step": int(ser[0].nbytes + ser[1].nbytes + ads_p[0].nbytes + ads_p[1].nbytes),
+                       "bytes_per_proof": int(ser[1][1] - ser[1][0])}
+    red = rk.max_ms(local)
+    out["e2e_value"] = rk.world * lanes * steps / (red[0] * 1e-3)
+    out["verdicts_ok"] = red[1] == 0.0
+    if wire:
+        out["wire"]["e2e_value"] = rk.world * lanes * steps / (red[2] * 1e-3)
+        out["wire"]["verdicts_ok"] = red[3] == 0.0
+    if cpu and rk.rank == 0:
+        from oracle import ref
+        km, threads, S = ref.KeyMaterial(n, seed_=1), ref.hw_threads(), _ref_sample_lanes(lanes)
+        t0 = time.perf_counter()
+        ev = ref.verify_id(km, {k: np.ascontiguousarray(v[:S]) for k, v in proof.items()}, [shown[j % base] for j in range(S)],
+                           [ads[j % base] for j in range(S)], b"rp.example", y, g, h, True, threads)
+        cpu_s = time.perf_counter() - t0
+        out["cpu_reference"] = {"value": S / cpu_s, "unit": "verifications/s", "cores": threads, "kind": "reference",
+                                "sample": f"first {S} lanes, PSVerifier::el_passo_verify_id via mcl"}
+        out["parity"] = bool(np.array_equal(ev, got[:S]))
+    pk.close()
+    return out
+
+
+def cfg_issuance(pkg, rk: Ranks, steps: int, window_bits: int, lanes: int, cpu: bool):
+    """configs[3]: EL PASSO blind issuance -- PSSigner::el_passo_provide_id (src/ps-signer.cc:63-146), 20 attributes (2 hidden)
+    -- followed by PSRequester::randomize_credential (src/ps-requester.cc:139-148) of the issued credentials."""
+    n, nh, base = 20, 2, min(1 << 12, lanes)
+    key = load_key(n)
+    pk = pkg.PSPubKey(key["g"], key["gg"], key["XX"], key["Y"], key["YY"], X_secret=key["X"], window_bits=window_bits)
+    attrs = attr_lists(n, base)
+    hidden = np.zeros(n, dtype=np.uint8)
+    hidden[:nh] = 1
+    reps = lanes // base
+    shown = [[b"" if hidden[i] else a[i] for i in range(n)] for a in attrs]
+    ads = [b"sess%d" % j for j in range(base)]
+    all_p, shown_p, ads_p = (tile_packed(*pkg.pack_attrs(attrs), reps), tile_packed(*pkg.pack_attrs(shown), reps),
+                             tile_packed(*pkg.pack_strings(ads), reps))
+    rng = np.random.default_rng(4100 + rk.rank)
+    A, c, rs = pkg.PSRequester(pk).el_passo_request_id(all_p, hidden, ads_p, rand_fr(rng, (lanes, nh + 2)))
+    expected = np.ones(lanes, dtype=np.uint8)
+    for t, j in enumerate(range(63, lanes, 64)):
+        kind = t % 3
+        if kind == 0:
+            c[j, 0] ^= np.uint64(1)
+        elif kind == 1:
+            rs[j, -1, 0] ^= np.uint64(1)
+        else:
+            A[j] = A[j - 1]
+        expected[j] = 0
+    u, t_r = rand_fr(rng, (lanes,)), rand_fr(rng, (lanes,))
+    sg = pkg.PSSigner(pk)
+    issue = lambda: sg.el_passo_provide_id(A, c, rs, shown_p, ads_p, u)  # noqa: E731
+    issue()
+    l0 = pkg.launch_count()
+    (v, s1, s2, ser), dt_issue = rk.timed(issue, steps)
+    rnd = lambda: pkg.PSRequester.randomize_credential(s1, s2, t_r, want_serialized=True)  # noqa: E731
+    rnd()
+    (o1, o2, oser), dt_rnd = rk.timed(rnd, steps)
+    launches = pkg.launch_count() - l0
+    ok_local = bool(np.array_equal(v, expected))
+    red = rk.max_ms([dt_issue * 1e3, dt_rnd * 1e3, 0.0 if ok_local else 1.0])
+    out = {"call": "PSSigner::el_passo_provide_id (psb_provide_id) then PSRequester::randomize_credential (psb_randomize)",
+           "n_attrs": n, "hidden": nh, "lanes_per_gpu": lanes, "metric": "credentials_issued_per_sec", "unit": "credentials/s",
+           "steps": steps, "window_bits": window_bits, "gpu_launches": int(launches), "tampered_lanes": int((expected == 0).sum()),
+           "e2e_value": rk.world * lanes * steps / (red[0] * 1e-3),
+           "randomize_e2e_value": rk.world * lanes * steps / (red[1] * 1e-3),
+           "issue_then_randomize_e2e_value": rk.world * lanes * steps / ((red[0] + red[1]) * 1e-3),
+           "h2d_bytes_per_step": int(A.nbytes + c.nbytes + rs.nbytes + u.nbytes + shown_p[0].nbytes + shown_p[1].nbytes + ads_p[0].nbytes + ads_p[1].nbytes),
+           "d2h_bytes_per_step": int(v.nbytes + s1.nbytes + s2.nbytes + ser.nbytes),
+           "verdicts_ok": red[2] == 0.0, "inputs": "requests made by psb_request_id, every lane distinct"}
+    if cpu and rk.rank == 0:
+        from oracle import ref
+        km, threads, S = ref.KeyMaterial(n, seed_=1), ref.hw_threads(), _ref_sample_lanes(lanes)
+        cut = lambda a: np.ascontiguousarray(a[:S])  # noqa: E731
+        t0 = time.perf_counter()
+        ev, e1, e2, eser = ref.provide_id(km, cut(A), cut(c), cut(rs), [shown[j % base] for j in range(S)],
+                                          [ads[j % base] for j in range(S)], cut(u), threads)
+        cpu_issue = time.perf_counter() - t0
+        good = ev.astype(bool)
+        t0 = time.perf_counter()
+        r1, r2, rser = ref.randomize(cut(s1), cut(s2), cut(t_r), nthreads=threads)
+        cpu_rnd = time.perf_counter() - t0
+        out["cpu_reference"] = {"value": S / cpu_issue, "randomize_value": S / cpu_rnd, "unit": "credentials/s", "cores": threads,
+                                "kind": "reference", "sample": f"first {S} lanes, PSSigner::el_passo_provide_id / t*sigma via mcl"}
+        out["parity"] = bool(np.array_equal(ev, v[:S]) and np.array_equal(eser[good], ser[:S][good])
+                             and np.array_equal(rser[good], oser[:S][good]))
+    pk.close()
+    return out
+
+
+def cfg_verify50(pkg, rk: Ranks, window_bits: int, lanes_total: int, cpu: bool, torch):
+    """configs[4]: batched PS verification, 50 attributes, `lanes_total` signatures SHARDED over the ranks (strong scaling):
+    each rank verifies lanes_total / world lanes in chunks of at most 2^21, device-resident (`value`) and from host buffers (`e2e`)."""
+    n, base = 50, 1 << 12
+    per = lanes_total // rk.world
+    chunk = min(per, 1 << 21)
+    key = load_key(n)
+    t0 = time.perf_counter()
+    pk = pkg.PSPubKey(key["g"], key["gg"], key["XX"], key["Y"], key["YY"], window_bits=window_bits)
+    sig1, sig2, blob, off, expected = make_batch(pkg, key, per, rk.rank, base=base, n_attrs=n, attr_period=chunk)
+    setup_s = time.perf_counter() - t0
+    dev = rk.dev
+    stream = torch.cuda.Stream(dev)    # kernels and timing events share this explicit stream
+    pin = lambda a: torch.from_numpy(a).pin_memory()  # noqa: E731
+    h_s1, h_s2, h_blob, h_off = pin(sig1.view(np.int64)), pin(sig2.view(np.int64)), pin(blob), pin(off.view(np.int64))
+    t_s1, t_s2, t_blob, t_off = (x.to(dev) for x in (h_s1, h_s2, h_blob, h_off))
+    t_verdict = torch.zeros(per, dtype=torch.uint8, device=dev)
+    t_ws = torch.empty(pkg.verify_ws_bytes(pk, chunk), dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize(dev)
+    G1B = sig1.shape[1] * 8
+
+    def pass_dev():
+        for a in range(0, per, chunk):
+            pkg.verify_dev(pk, 0, min(chunk, per - a), t_s1.data_ptr() + a * G1B, t_s2.data_ptr() + a * G1B, t_blob.data_ptr(),
+                           t_off.data_ptr(), 0, t_verdict.data_ptr() + a, 0, t_ws.data_ptr(), stream.cuda_stream)
+
+    pkg.verify_dev(pk, 0, chunk, t_s1.data_ptr(), t_s2.data_ptr(), t_blob.data_ptr(), t_off.data_ptr(), 0, t_verdict.data_ptr(), 0,
+                   t_ws.data_ptr(), stream.cuda_stream)          # warm-up: one chunk
+    torch.cuda.synchronize(dev)
+    l0 = pkg.launch_count()
+    rk.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    pass_dev()
+    ev1.record(stream)
+    rk.barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = pkg.launch_count() - l0
+    ok_dev = bool(np.array_equal(t_verdict.cpu().numpy(), expected))
+    ver = pkg.PSVerifier(pk)
+    n_s1, n_s2, n_blob, n_off = h_s1.numpy().view(np.uint64), h_s2.numpy().view(np.uint64), h_blob.numpy(), h_off.numpy().view(np.uint64)
+    h_verdict = torch.zeros(per, dtype=torch.uint8).pin_memory().numpy()
+    ver.verify(n_s1[:chunk], n_s2[:chunk], (n_blob, n_off), out=h_verdict[:chunk])   # staging buffers at the chunk size
+
+    def pass_host():
+        for a in range(0, per, chunk):
+            ver.verify(n_s1[a:a + chunk], n_s2[a:a + chunk], (n_blob, n_off), out=h_verdict[a:a + chunk])
+
+    _, e2e_s = rk.timed(pass_host, 1)
+    ok_e2e = bool(np.array_equal(h_verdict, expected))
+    red = rk.max_ms([dev_ms, e2e_s * 1e3, 0.0 if (ok_dev and ok_e2e) else 1.0])
+    nwin = (256 + window_bits - 1) // window_bits
+    out = {"call": "PSVerifier::verify (psb_verify_dev / psb_verify)", "n_attrs": n, "lanes_total": per * rk.world,
+           "lanes_per_gpu": per, "chunk_lanes": chunk, "scaling": "strong", "metric": "ps_verifications_per_sec",
+           "unit": "verifications/s", "steps": 1, "window_bits": window_bits, "table_bytes": pk.table_bytes,
+           "value": per * rk.world / (red[0] * 1e-3), "e2e_value": per * rk.world / (red[1] * 1e-3),
+           "ms_per_pass": red[0], "gpu_launches": int(launches), "verdicts_ok": red[2] == 0.0,
+           "tampered_lanes": int((expected == 0).sum()), "setup_seconds": setup_s,
+           "h2d_bytes_per_step": int(sig1.nbytes + sig2.nbytes + (per // chunk) * (int(off[-1]) + off.nbytes)), "d2h_bytes_per_step": per,
+           "whole_step_frac_fpmul_eq": a_verify_fpmul(n, window_bits),
+           "inputs": f"every signature distinct; the attribute strings of one chunk ({chunk} lanes) are shared by all chunks"}
+    if cpu and rk.rank == 0:
+        cb = cpu_reference_verify(n, sig1, sig2, blob, off, 3.0, pairings=False)
+        out["cpu_reference"] = {"value": cb["rate"], "unit": "verifications/s", "cores": cb["threads"], "kind": "reference",
+                                "sample": f"first {cb['lanes']} lanes, PSVerifier::verify via mcl"}
+        out["parity"] = bool(np.array_equal(cb["verdict"], h_verdict[:cb["lanes"]]))
+    del t_s1, t_s2, t_blob, t_off, t_ws, t_verdict
+    torch.cuda.empty_cache()
+    pk.close()
+    return out
+
+
+def run_configs(pkg, args, rk: Ranks, torch):
+    """configs[2..4] of BASELINE.json, each through the public batched call; a config that fails on any rank is reported
+    as an error entry instead of taking the headline line down with it."""
+    which = [c for c in args.configs.split(",") if c and c != "none"]
+    steps = max(1, min(args.steps, 3))
+    cpu = not args.no_cpu_baseline
+    res = {}
+    jobs = {"cfg3_signon": lambda: cfg_signon(pkg, rk, steps, args.config_window_bits, args.config_lanes, cpu, True),
+            "cfg4_issuance": lambda: cfg_issuance(pkg, rk, steps, args.config_window_bits, args.config_lanes, cpu),
+            "cfg5_verify50": lambda: cfg_verify50(pkg, rk, args.window_bits50, args.lanes50, cpu, torch)}
+    for name, job in jobs.items():
+        if name.split("_")[0] not in which:
+            continue
+        t0 = time.perf_counter()
+        if rk.failed:
+            res[name] = {"error": "skipped: an earlier config failed on some rank"}
+            continue
+        try:
+            res[name] = job()
+        except Exception as e:  # noqa: BLE001  (reported in the line; the side group's timeout frees the other ranks)
+            rk.failed = True
+            res[name] = {"error": f"{type(e).__name__}: {e}"[:400]}
+        res[name]["wall_seconds"] = time.perf_counter() - t0
+    return res
+
+
+def run_in_process(pkg, args, world, key, sig1, sig2, blob, off, expected, torch):
+    """SURVEY 8e's other launch model, measured after the torchrun ranks have gone: ONE process drives all `world` GPUs
+    (psb_init(devices...): one host thread + stream per device inside psb_verify, verdict bytes gathered into the caller's
+    array) on world x lanes lanes from host buffers."""
+    t_wait = time.perf_counter()
+    for d in range(1, world):       # the other ranks release their devices when they exit
+        while time.perf_counter() - t_wait < 120:
+            free, total = torch.cuda.mem_get_info(d)
+            if free > 0.9 * total:
+                break
+            time.sleep(0.5)
+    pkg.shutdown()
+    pkg.init(list(range(world)))
+    pk = pkg.PSPubKey(key["g"], key["gg"], key["XX"], key["Y"], key["YY"], window_bits=args.window_bits)
+    N = sig1.shape[0]
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()  # noqa: E731
+    b_blob, b_off = tile_packed(blob, off, world)
+    h_s1, h_s2 = pin(np.tile(sig1, (world, 1)).view(np.int64)).view(np.uint64), pin(np.tile(sig2, (world, 1)).view(np.int64)).view(np.uint64)
+    h_blob, h_off = pin(b_blob), pin(b_off.view(np.int64)).view(np.uint64)
+    h_verdict = torch.zeros(N * world, dtype=torch.uint8).pin_memory().numpy()
+    ver = pkg.PSVerifier(pk)
+    ver.verify(h_s1, h_s2, (h_blob, h_off), out=h_verdict)
+    steps = max(1, min(args.steps, 3))
+    l0 = pkg.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ver.verify(h_s1, h_s2, (h_blob, h_off), out=h_verdict)
+    dt = time.perf_counter() - t0
+    out = {"call": "psb_init(all devices) + psb_verify from host buffers in ONE process (host thread + stream per device)",
+           "devices": int(pkg.lib().psb_num_devices()), "lanes": N * world, "steps": steps, "value": N * world * steps / dt,
+           "unit": "verifications/s", "gpu_launches": int(pkg.launch_count() - l0),
+           "verdicts_ok": bool(np.array_equal(h_verdict, np.tile(expected, world)))}
+    pk.close()
+    return out
+
+
+def run_bn254_child(args, local_rank: int):
+    """the headline shape on BN254 (what initPairing() selects in the reference's shipped tests, test/ps-tests.cc:142):
+    one curve per process, so a child process runs this file with --curve bn254 on the same GPU once this one is done."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--curve", "bn254", "--gpus", "1", "--steps", str(max(1, min(args.steps, 3))),
+           "--warmup", str(min(args.warmup, 3)), "--lanes", str(args.lanes), "--window-bits", str(args.window_bits), "--cpu-budget-s", "3"]
+    if args.no_cpu_baseline:
+        cmd.append("--no-cpu-baseline")
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "PSB_LIB")}
+    env["CUDA_VISIBLE_DEVICES"] = os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[local_rank] if os.environ.get("CUDA_VISIBLE_DEVICES") else str(local_rank)
+    try:
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+        child = json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:  # noqa: BLE001
+        tail = (r.stderr or "")[-600:] if "r" in locals() else ""
+        return {"error": f"{type(e).__name__}: {e}"[:200], "child_stderr_tail": tail}
+    keep = {k: child.get(k) for k in ("metric", "value", "unit", "n_gpus", "steps", "ms_per_step", "e2e", "pairings", "gpu_launches", "cpu_baseline")}
+    keep["config"] = child.get("config")
+    keep["phase_ms"] = (child.get("roofline") or {}).get("phase_ms")
+    keep["parity"] = (child.get("cpu_baseline") or {}).get("verdicts_agree_with_gpu")
+    return keep
 
 
 def _claim_stdout():
@@ -216,12 +628,26 @@ def main():
     ap.add_argument("--window-bits", type=int, default=20, help="fixed-base window of the per-key G2 tables (20: 13 additions per base, 1.3 GB per base)")
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--configs", default="cfg3,cfg4,cfg5,inproc,bn254",
+                    help="secondary entries of the line: BASELINE configs[2..4], the in-process multi-device run (N > 1), BN254; 'none' = headline only")
+    ap.add_argument("--config-lanes", type=int, default=1 << 18, help="lanes per GPU of cfg3 / cfg4 (named: 2^18)")
+    ap.add_argument("--config-window-bits", type=int, default=16)
+    ap.add_argument("--lanes50", type=int, default=1 << 24, help="TOTAL lanes of cfg5 (named: 2^24), sharded over the ranks")
+    ap.add_argument("--window-bits50", type=int, default=20, help="fixed-base window of the 50-attribute key (20: 65 GB of tables)")
+    ap.add_argument("--curve", default="bls12_381", choices=["bls12_381", "bn254"],
+                    help="bn254: the headline shape on libpsb_bn254.so (the curve the reference's shipped tests run); no roofline figures")
     args = ap.parse_args()
+    global R_ORDER, FPW
+    bls = args.curve == "bls12_381"
+    if not bls:      # one curve per process (like mcl): select the library and the reference build before either is loaded
+        os.environ["PSB_CURVE"] = "bn254"
+        R_ORDER, FPW = R_ORDERS["bn254"], 4
+        args.configs = "none"
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = f"ps_verify n_attrs={N_ATTRS} lanes_per_gpu={args.lanes} BLS12-381"
+    workload = f"ps_verify n_attrs={N_ATTRS} lanes_per_gpu={args.lanes} " + ("BLS12-381" if bls else "BN254")
 
     if args.impl == "reference":
         if rank != 0:
@@ -261,15 +687,18 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU: the engine has no CPU path")
     torch.cuda.set_device(local_rank)
+    side = None
     if world > 1:
+        import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        side = dist.new_group(backend="gloo", timeout=datetime.timedelta(seconds=900))   # see class Ranks
     pkg.init([local_rank])
     dev = torch.device("cuda", local_rank)
 
     key = load_key(N_ATTRS)
     pk = pkg.PSPubKey(key["g"], key["gg"], key["XX"], key["Y"], key["YY"], window_bits=args.window_bits)
     N = args.lanes
-    sig1, sig2, blob, off, expected, lane_attrs = make_batch(pkg, key, N, rank)
+    sig1, sig2, blob, off, expected = make_batch(pkg, key, N, rank)
 
     # measured integer-MAC peak of this GPU (roofline denominator), a few hundred ms
     peak_ms = min(pkg.microbench(5, 148 * 8, 256, 20000) for _ in range(2))
@@ -288,7 +717,8 @@ def main():
     t_off = torch.from_numpy(off.view(np.int64)).to(dev)
     t_verdict = torch.zeros(N, dtype=torch.uint8, device=dev)
     t_ws = torch.empty(pkg.verify_ws_bytes(pk, N), dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)    # an explicit non-default stream: the kernels are launched on it, the events recorded on it
+    torch.cuda.synchronize(dev)
 
     def step_dev():
         pkg.verify_dev(pk, 0, N, t_s1.data_ptr(), t_s2.data_ptr(), t_blob.data_ptr(), t_off.data_ptr(), 0,
@@ -329,7 +759,7 @@ def main():
     h_s1, h_s2, h_blob, h_off = pin(sig1), pin(sig2), pin(blob), pin(off.view(np.int64)).view(np.uint64)
     h_verdict = torch.zeros(N, dtype=torch.uint8).pin_memory().numpy()
     ver.verify(h_s1, h_s2, (h_blob, h_off), out=h_verdict)  # one untimed full-size call: the library sizes its staging buffers
-    e2e_steps = max(1, min(args.steps, 2))
+    e2e_steps = max(1, args.steps)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -354,10 +784,26 @@ def main():
     gt_pair = pkg.pairing(Pp, Qq)
     pair_s = time.perf_counter() - t0
     ms_total, e2e_ms, pair_ms = max_over_ranks([ms_total, e2e_s * 1e3, pair_s * 1e3], world, dev)
+
+    # ---- the other configs (all ranks), then rank 0 alone: in-process multi-device run, BN254 ---------------------------
+    table_bytes, ws_bytes = pk.table_bytes, len(t_ws)
+    pk.close()
+    del t_s1, t_s2, t_blob, t_off, t_ws, t_verdict
+    torch.cuda.empty_cache()
+    configs = run_configs(pkg, args, Ranks(rank, world, dev, torch, side), torch) if bls else {}
+    if world > 1:
+        dist.destroy_process_group()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
+    which = [c for c in args.configs.split(",") if c]
+    if world > 1 and "inproc" in which:
+        try:
+            configs["in_process"] = run_in_process(pkg, args, world, key, sig1, sig2, blob, off, expected, torch)
+        except Exception as e:  # noqa: BLE001
+            configs["in_process"] = {"error": f"{type(e).__name__}: {e}"[:400]}
+    pkg.shutdown()
+    if bls and "bn254" in which:
+        configs["bn254_verify"] = run_bn254_child(args, local_rank)
 
     value = job_throughput(N, world, args.steps, ms_total)
     e2e_val = job_throughput(N, world, e2e_steps, e2e_ms)
@@ -366,11 +812,19 @@ def main():
     work = [N_ATTRS * nwin * A_MSM_PER_ADD, A_MILLER2, A_FINALEXP]
     dom = int(np.argmax(phase))
     achieved = work[dom] * FPMUL_MAC32 * N / (phase[dom] * 1e-3)
-    traffic = None
-    try:  # DRAM bytes of that kernel from the committed ncu --set full capture, scaled per lane to this launch
-        with open(os.path.join(ROOT, "profiles", "r1zb_traffic.json")) as f:
+    kernels = [{"name": names[i], "ms": float(phase[i]), "fpmul_eq_per_lane": work[i],
+                "achieved_tmac32": work[i] * FPMUL_MAC32 * N / (phase[i] * 1e-3) / 1e12,
+                "frac": work[i] * FPMUL_MAC32 * N / (phase[i] * 1e-3) / peak_mac,
+                "frac_of_carry_chain": work[i] * FPMUL_MAC32 * N / (phase[i] * 1e-3) / peak_chain} for i in range(3)]
+    traffic, traffic_source = None, None
+    try:  # DRAM bytes of that kernel: NOT measured in this run -- the committed ncu --set full capture, scaled per lane
+        with open(os.path.join(ROOT, "profiles", TRAFFIC_FILE)) as f:
             tr = json.load(f)
         traffic = tr["dram_bytes_per_launch"][names[dom]] / tr["lanes"] * N
+        traffic_source = (f"profiles/{TRAFFIC_FILE} ({tr.get('date', 'n/a')}, ncu --set full of one wave of {tr['lanes']} lanes at "
+                          f"commit {tr.get('commit', 'n/a')}), scaled per lane to this launch -- stale by construction, not from this run")
+        for k in kernels:
+            k["traffic_bytes_per_lane_ncu"] = tr["dram_bytes_per_launch"][k["name"]] / tr["lanes"]
     except Exception:
         pass
     whole = a_verify_fpmul(N_ATTRS, args.window_bits) * FPMUL_MAC32 * value / world
@@ -378,8 +832,8 @@ def main():
         "metric": "ps_verifications_per_sec", "value": value, "unit": "verifications/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32-limbs (381-bit Montgomery, int32 MAC)", "data": "synthetic",
-        "config": {"workload": workload, "window_bits": args.window_bits, "table_bytes": pk.table_bytes,
-                   "l2": "inputs + phase state (%.0f MB) exceed the 126 MB L2" % ((sig1.nbytes * 2 + len(t_ws)) / 1e6),
+        "config": {"workload": workload, "window_bits": args.window_bits, "table_bytes": table_bytes,
+                   "l2": "inputs + phase state (%.0f MB) exceed the 126 MB L2" % ((sig1.nbytes * 2 + ws_bytes) / 1e6),
                    "parallelism": f"lanes sharded over {world} GPU(s), no collective"},
         "e2e": {"value": e2e_val, "unit": "verifications/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps},
@@ -388,7 +842,8 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "roofline": {"bound": "int32-mac", "kernel": names[dom], "achieved": achieved / 1e12, "peak": peak_mac / 1e12,
-                     "unit": "TMAC32/s", "frac": achieved / peak_mac, "traffic": traffic,
+                     "unit": "TMAC32/s", "frac": achieved / peak_mac, "traffic": traffic, "traffic_source": traffic_source,
+                     "kernels": kernels,
                      "peak_source": "measured live (carry-free mad.wide.u32 probe, all SMs)",
                      "peak_carry_chain": peak_chain / 1e12, "frac_of_carry_chain_peak": achieved / peak_chain,
                      "peak_carry_chain_source": "measured live (IMAD.WIDE.U32.X carry-chain rows, the multiplier's instruction form)",
@@ -397,9 +852,13 @@ def main():
                      "hbm": {"algorithmic_bytes_per_lane": h2d / N + 1 + 864 * 2,
                              "achieved_GBps": (h2d / N + 1 + 864 * 2) * value / world / 1e9}},
     }
+    if configs:
+        line["configs"] = configs
+    if not bls:
+        line["roofline"] = {"note": "MAC32 work figures are derived for BLS12-381 only; phase_ms given", "phase_ms": line["roofline"]["phase_ms"]}
     if world == 1 and not args.no_cpu_baseline:
         try:
-            cb = cpu_reference_verify(N_ATTRS, sig1, sig2, lane_attrs, args.cpu_budget_s)
+            cb = cpu_reference_verify(N_ATTRS, sig1, sig2, blob, off, args.cpu_budget_s)
             agree = bool(np.array_equal(cb["verdict"], got[:cb["lanes"]]))
             from oracle import ref as _ref   # checker: GT bytes of a pairing sample against mcl::bn::pairing
             pair_ok = bool(np.array_equal(gt_pair[:64], _ref.pairing(Pp[:64], Qq[:64])))
@@ -417,8 +876,6 @@ def main():
             line["cpu_baseline"] = {"value": None, "unit": "verifications/s", "cores": 0, "kind": "reference",
                                     "sample": f"unavailable: {e}"}
     _emit(out_fd, line)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

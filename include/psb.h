@@ -165,6 +165,22 @@ int psb_provide_id_ser(psb_key* key, size_t N, const uint8_t* buf, const uint64_
                        const uint8_t* ad_blob, const uint64_t* ad_off, const uint64_t* u, uint8_t* verdict,
                        uint64_t* sig1, uint64_t* sig2, uint8_t* ser, uint8_t* parsed);
 
+/* ---- wire-format OUTPUT: the bytes a batched prover sends.  kind = PSB_WIRE_IDPROOF: IdProof::toBufferString()
+ * (src/ps-encoding.cc:452-468: sig1 sig2 k phi c rs attributes [E1 E2]; E1 = E2 = NULL for a proof without id retrieval),
+ * kind = PSB_WIRE_REQUEST: PSCredRequest::toBufferString() (:429-439: A c rs attributes; p0 = A, sig2 = k = phi = NULL).
+ * Points may be any Jacobian representative (they are normalised like mcl's serialize does, ec.hpp:849-896); rs holds rs_per
+ * scalars per lane; lane j's n_attrs strings are attr_blob[attr_off[j*n_attrs + i] .. attr_off[j*n_attrs + i + 1]) ("" = hidden).
+ * base64 != 0 writes PSBuffer::toBase64() text (:14-54, '=' padded) instead of the raw bytes.  out_off[N + 1] is always
+ * written (lane j's message = out[out_off[j] .. out_off[j+1])); with out == NULL nothing else happens (size query), else
+ * out_cap >= out_off[N] is required.  Lists or strings longer than 0xFFFF (which the reference's appendVar silently
+ * drops, :138-146) are PSB_ERR_ARG. ---- */
+#define PSB_WIRE_IDPROOF 0
+#define PSB_WIRE_REQUEST 1
+int psb_wire_encode(int kind, size_t N, size_t n_attrs, const uint64_t* p0, const uint64_t* sig2, const uint64_t* k,
+                    const uint64_t* phi, const uint64_t* E1, const uint64_t* E2, const uint64_t* c, const uint64_t* rs,
+                    size_t rs_per, const uint8_t* attr_blob, const uint64_t* attr_off, int base64, uint8_t* out, size_t out_cap,
+                    uint64_t* out_off);
+
 /* ---- prover side.  The reference draws its blinding / commitment scalars from mcl's CSPRNG;
  * the batch entries take them from the host, per lane, IN THE REFERENCE'S DRAW ORDER, so the same scalars reproduce the
  * reference's requests and proofs byte for byte.  hide = n flags shared by the batch (1 = attribute hidden), h = their

@@ -560,6 +560,24 @@ __global__ void __launch_bounds__(kBlock) k_wire_points(size_t N, int nslots, co
   if (!ok) parsed[lane] = 0;
 }
 
+// ---- wire-format OUTPUT (csrc/wire.cuh encode_message_lane): what a batched prover sends.  One thread per lane writes its
+// message to out + out_off[lane]; out_off comes from the host (wire_message_size).  pts.p[3] / p[4] null = no E1 / E2.
+__global__ void PSB_PROTO_BOUNDS k_wire_encode(size_t N, int kind, int n, int per, WireG1Out pts, const G2J* k, const Fr* c, const Fr* rs,
+                                               const uint8_t* attr, const uint64_t* attr_off, uint8_t* out, const uint64_t* out_off) {
+  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= N) return;
+  const G1J* p[5];
+  for (int i = 0; i < 5; i++) p[i] = pts.p[i] ? pts.p[i] + lane : nullptr;
+  encode_message_lane(out + out_off[lane], kind, n, p, k ? k + lane : nullptr, c[lane], rs + lane * (size_t)per, per, attr,
+                      attr_off + lane * (size_t)n);
+}
+__global__ void __launch_bounds__(kBlock) k_wire_base64_encode(size_t N, const uint8_t* in, const uint64_t* in_off, uint8_t* out,
+                                                                const uint64_t* out_off) {
+  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= N) return;
+  base64_encode_lane(out + out_off[lane], in + in_off[lane], (size_t)(in_off[lane + 1] - in_off[lane]));
+}
+
 // ---- prover side: PSRequester::el_passo_request_id / unblind_credential / el_passo_prove_id ----
 // hide: n flags shared by the batch; rnd: `per` host-supplied scalars per lane in the reference's draw order (prover.cuh)
 __global__ void PSB_PROTO_BOUNDS k_request_id(size_t N, int n, int w, const G1A* tblG1, const uint8_t* hide, int h,

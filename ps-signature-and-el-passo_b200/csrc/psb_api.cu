@@ -1179,6 +1179,84 @@ int psb_request_id(psb_key* key, size_t N, const uint8_t* attr_blob, const uint6
   });
 }
 
+int psb_wire_encode(int kind, size_t N, size_t n_attrs, const uint64_t* p0, const uint64_t* sig2, const uint64_t* k,
+                    const uint64_t* phi, const uint64_t* E1, const uint64_t* E2, const uint64_t* c, const uint64_t* rs,
+                    size_t rs_per, const uint8_t* attr_blob, const uint64_t* attr_off, int base64, uint8_t* out, size_t out_cap,
+                    uint64_t* out_off) {
+  if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
+  if (kind != PSB_WIRE_IDPROOF && kind != PSB_WIRE_REQUEST) return fail(PSB_ERR_ARG, "kind must be PSB_WIRE_IDPROOF or PSB_WIRE_REQUEST");
+  if (!p0 || !c || !rs || !attr_off || !out_off || (kind == PSB_WIRE_IDPROOF && (!sig2 || !k || !phi)))
+    return fail(PSB_ERR_ARG, "null argument");
+  if ((E1 == nullptr) != (E2 == nullptr)) return fail(PSB_ERR_ARG, "E1 and E2 go together");
+  if (rs_per > 0xFFFF || n_attrs > 0xFFFF) return fail(PSB_ERR_ARG, "list longer than appendVar can express");
+  const bool has_e = kind == PSB_WIRE_IDPROOF && E1;
+  const int n = (int)n_attrs, per = (int)rs_per;
+  // message sizes on the host: raw_off (binary) and, with base64, the text offsets
+  std::vector<uint64_t> raw_off(base64 ? N + 1 : 0);
+  uint64_t* ro = base64 ? raw_off.data() : out_off;
+  ro[0] = 0;
+  for (size_t j = 0; j < N; j++) {
+    const uint64_t* ao = attr_off + j * n_attrs;
+    for (size_t i = 0; i < n_attrs; i++) {
+      if (ao[i + 1] < ao[i]) return fail(PSB_ERR_ARG, "attr_off must be non-decreasing");
+      if (ao[i + 1] - ao[i] > 0xFFFF) return fail(PSB_ERR_ARG, "attribute longer than appendVar can express");
+    }
+    ro[j + 1] = ro[j] + wire_message_size(kind, n, per, ao, has_e);
+  }
+  if (base64) {
+    out_off[0] = 0;
+    for (size_t j = 0; j < N; j++) out_off[j + 1] = out_off[j] + base64_encoded_size((size_t)(ro[j + 1] - ro[j]));
+  }
+  if (!out) return PSB_OK;                       // size query
+  if (out_cap < out_off[N]) return fail(PSB_ERR_ARG, "out_cap is smaller than out_off[N]");
+  if (N && n_attrs && !attr_blob && attr_off[N * n_attrs] != attr_off[0]) return fail(PSB_ERR_ARG, "null argument");
+  return shard(N, [&](int di, size_t b, size_t e) -> int {
+    Dev* dv = g_devs[di];
+    std::lock_guard<std::mutex> lk(dv->mu);
+    const size_t L = e - b;
+    if (L == 0) return PSB_OK;
+    CK(cudaSetDevice(dv->ordinal));
+    cudaStream_t st = dv->stream;
+    const uint64_t a0 = attr_off[b * n_attrs], a1 = attr_off[e * n_attrs], r0 = ro[b], r1 = ro[e], t0 = out_off[b], t1 = out_off[e];
+    Arena ar;
+    G1J* dP[5] = {}; G2J* dk = nullptr; Fr *dc = nullptr, *drs = nullptr;
+    uint8_t *dattr = nullptr, *draw = nullptr, *dtext = nullptr; uint64_t *daoff = nullptr, *droff = nullptr, *dtoff = nullptr;
+    const int npts = kind == PSB_WIRE_IDPROOF ? (has_e ? 5 : 3) : 1;
+    for (int pass = 0; pass < 2; pass++) {
+      ar.used = 0;
+      for (int i = 0; i < npts; i++) dP[i] = ar.take<G1J>(L);
+      if (kind == PSB_WIRE_IDPROOF) dk = ar.take<G2J>(L);
+      dc = ar.take<Fr>(L); drs = ar.take<Fr>(L * rs_per + 1);
+      dattr = ar.take<uint8_t>((size_t)(a1 - a0) + 16); daoff = ar.take<uint64_t>(L * n_attrs + 1);
+      draw = ar.take<uint8_t>((size_t)(r1 - r0) + 16); droff = ar.take<uint64_t>(L + 1);
+      if (base64) { dtext = ar.take<uint8_t>((size_t)(t1 - t0) + 16); dtoff = ar.take<uint64_t>(L + 1); }
+      if (pass == 0) { int r = ensure(dv->arena, ar.used); if (r) return r; ar.base = (char*)dv->arena.p; }
+    }
+    const uint64_t* src[5] = {p0, sig2, phi, E1, E2};
+    for (int i = 0; i < npts; i++) CK(cudaMemcpyAsync(dP[i], src[i] + b * kG1W, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
+    if (dk) CK(cudaMemcpyAsync(dk, k + b * kG2W, L * sizeof(G2J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dc, c + b * 4, L * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    if (rs_per) CK(cudaMemcpyAsync(drs, rs + b * rs_per * 4, L * rs_per * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    if (a1 > a0) CK(cudaMemcpyAsync(dattr, attr_blob + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(daoff, attr_off + b * n_attrs, (L * n_attrs + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(droff, ro + b, (L + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    WireG1Out pts{};
+    for (int i = 0; i < npts; i++) pts.p[i] = dP[i];
+    // offsets on the device stay ABSOLUTE; the base pointers are shifted by the range's first byte instead
+    k_wire_encode<<<nblocks(L), kBlock, 0, st>>>(L, kind, n, per, pts, dk, dc, drs, dattr - a0, daoff, draw - r0, droff);
+    LAUNCHED();
+    if (base64) {
+      CK(cudaMemcpyAsync(dtoff, out_off + b, (L + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+      k_wire_base64_encode<<<nblocks(L), kBlock, 0, st>>>(L, draw - r0, droff, dtext - t0, dtoff);
+      LAUNCHED();
+    }
+    CK(cudaGetLastError());
+    if (t1 > t0) CK(cudaMemcpyAsync(out + t0, base64 ? dtext : draw, (size_t)(t1 - t0), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PSB_OK;
+  });
+}
+
 int psb_unblind(size_t N, const uint64_t* sig1, const uint64_t* sig2, const uint64_t* t1, uint64_t* out2) {
   if (!g_init) return fail(PSB_ERR_NOT_INIT, "psb_init not called");
   if (!sig1 || !sig2 || !t1 || !out2) return fail(PSB_ERR_ARG, "null argument");

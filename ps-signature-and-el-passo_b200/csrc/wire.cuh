@@ -159,4 +159,81 @@ PSB_HD PSB_NOINL bool parse_request_lane(const uint8_t* b, size_t len, int n, ui
   return c.ok;
 }
 
+// ---- the other direction: IdProof::toBufferString / PSCredRequest::toBufferString (src/ps-encoding.cc:429-439, :452-468) ------
+// What a batched prover (psb_prove_id, psb_request_id) puts on the wire.  appendVar (:138-146) writes one byte below 253,
+// else 253 + big-endian u16 (lengths above 0xFFFF write NOTHING in the reference: psb_wire_encode refuses them); points go
+// through mcl's serialize, i.e. they are normalised first (ec.hpp:849-896); scalars are 32 little-endian bytes.
+PSB_HD PSB_INL size_t wire_var_size(size_t v) { return v < 253 ? 1 : 3; }
+// bytes of one message: kind 0 = IdProof (has_e: E1 and E2 appended), 1 = PSCredRequest; aoff = n + 1 offsets of the lane's strings
+PSB_HD PSB_INL size_t wire_message_size(int kind, int n, int per, const uint64_t* aoff, bool has_e) {
+  size_t s = (kind == 0 ? 3 * (2 + (size_t)kFpBytes) + (2 + 2 * (size_t)kFpBytes) : 2 + (size_t)kFpBytes) + (2 + kFrBytes) + 1 +
+             wire_var_size((size_t)per) + (size_t)per * (1 + kFrBytes) + 1 + wire_var_size((size_t)n);
+  for (int i = 0; i < n; i++) { const size_t l = (size_t)(aoff[i + 1] - aoff[i]); s += wire_var_size(l) + l; }
+  if (kind == 0 && has_e) s += 2 * (2 + (size_t)kFpBytes);
+  return s;
+}
+PSB_HD PSB_INL void wire_put_var(uint8_t*& o, size_t v) {
+  if (v < 253) { *o++ = (uint8_t)v; return; }
+  *o++ = 253; *o++ = (uint8_t)(v >> 8); *o++ = (uint8_t)v;
+}
+PSB_HD PSB_NOINL void wire_put_g1(uint8_t*& o, const G1J& P) {
+  G1J Q;
+  pt_normalize(Q, P);
+  *o++ = 1; *o++ = (uint8_t)kFpBytes;
+  g1_serialize_norm(o, Q);
+  o += kFpBytes;
+}
+PSB_HD PSB_NOINL void wire_put_g2(uint8_t*& o, const G2J& P) {
+  G2J Q;
+  pt_normalize(Q, P);
+  *o++ = 2; *o++ = (uint8_t)(2 * kFpBytes);
+  g2_serialize_norm(o, Q);
+  o += 2 * kFpBytes;
+}
+PSB_HD PSB_INL void wire_put_fr(uint8_t*& o, const Fr& a, bool typed) {
+  Fr n;
+  fr_from_mont(n, a);
+  if (typed) *o++ = 3;
+  *o++ = (uint8_t)kFrBytes;
+  for (int i = 0; i < 8; i++) { *o++ = (uint8_t)n.v[i]; *o++ = (uint8_t)(n.v[i] >> 8); *o++ = (uint8_t)(n.v[i] >> 16); *o++ = (uint8_t)(n.v[i] >> 24); }
+}
+// pts: IdProof = {sig1, sig2, phi, E1, E2} (E1 / E2 null when absent), PSCredRequest = {A}; returns the bytes written
+PSB_HD PSB_NOINL size_t encode_message_lane(uint8_t* out, int kind, int n, const G1J* const* pts, const G2J* k, const Fr& cc,
+                                            const Fr* rs, int per, const uint8_t* attr, const uint64_t* aoff) {
+  uint8_t* o = out;
+  wire_put_g1(o, *pts[0]);
+  if (kind == 0) {
+    wire_put_g1(o, *pts[1]);
+    wire_put_g2(o, *k);
+    wire_put_g1(o, *pts[2]);
+  }
+  wire_put_fr(o, cc, true);
+  *o++ = 6;
+  wire_put_var(o, (size_t)per);
+  for (int i = 0; i < per; i++) wire_put_fr(o, rs[i], false);
+  *o++ = 7;
+  wire_put_var(o, (size_t)n);
+  for (int i = 0; i < n; i++) {
+    const size_t l = (size_t)(aoff[i + 1] - aoff[i]);
+    wire_put_var(o, l);
+    for (size_t t = 0; t < l; t++) *o++ = attr[aoff[i] + t];
+  }
+  if (kind == 0 && pts[3] && pts[4]) { wire_put_g1(o, *pts[3]); wire_put_g1(o, *pts[4]); }
+  return (size_t)(o - out);
+}
+// base64_encode (src/ps-encoding.cc:14-54): '=' padded; 4 * ceil(len / 3) characters
+PSB_HD PSB_INL size_t base64_encoded_size(size_t len) { return (len + 2) / 3 * 4; }
+PSB_HD PSB_NOINL void base64_encode_lane(uint8_t* out, const uint8_t* in, size_t len) {
+  const char* tab = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+  size_t o = 0;
+  for (size_t p = 0; p < len; p += 3) {
+    const int m = (int)(len - p < 3 ? len - p : 3);
+    const uint32_t v = ((uint32_t)in[p] << 16) | ((m > 1 ? (uint32_t)in[p + 1] : 0u) << 8) | (m > 2 ? (uint32_t)in[p + 2] : 0u);
+    out[o++] = (uint8_t)tab[(v >> 18) & 63];
+    out[o++] = (uint8_t)tab[(v >> 12) & 63];
+    out[o++] = m > 1 ? (uint8_t)tab[(v >> 6) & 63] : (uint8_t)'=';
+    out[o++] = m > 2 ? (uint8_t)tab[v & 63] : (uint8_t)'=';
+  }
+}
+
 }  // namespace psb

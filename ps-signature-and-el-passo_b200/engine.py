@@ -68,7 +68,7 @@ def lib():
 EXPORTS = ["psb_init", "psb_shutdown", "psb_num_devices", "psb_last_error", "psb_shard_range", "psb_launch_count",
            "psb_key_create", "psb_key_destroy", "psb_key_num_attributes", "psb_key_table_bytes",
            "psb_verify", "psb_verify_aos", "psb_verify_ser", "psb_g1_deserialize", "psb_g2_deserialize", "psb_verify_ws_bytes", "psb_verify_dev", "psb_randomize", "psb_provide_id",
-           "psb_verify_id", "psb_sign", "psb_verify_id_ser", "psb_provide_id_ser", "psb_request_id", "psb_unblind", "psb_prove_id", "psb_hash_to_g1", "psb_pairing", "psb_g1_mul", "psb_set_profiling", "psb_last_phase_ms", "psb_test_op_shape", "psb_test_op", "psb_microbench"]
+           "psb_verify_id", "psb_sign", "psb_verify_id_ser", "psb_provide_id_ser", "psb_wire_encode", "psb_request_id", "psb_unblind", "psb_prove_id", "psb_hash_to_g1", "psb_pairing", "psb_g1_mul", "psb_set_profiling", "psb_last_phase_ms", "psb_test_op_shape", "psb_test_op", "psb_microbench"]
 
 
 def _check(rc: int, what: str):
@@ -87,6 +87,13 @@ def init(devices: Optional[Sequence[int]] = None) -> None:
         rc = L.psb_init(MCL_CURVE, arr, len(devices))
     _check(rc, "psb_init")
     _inited = True
+
+
+def shutdown() -> None:
+    """psb_shutdown: frees every device context; live keys become dead handles (every later use is PSB_ERR_ARG)."""
+    global _inited
+    lib().psb_shutdown()
+    _inited = False
 
 
 def ensure_init():
@@ -424,6 +431,38 @@ class PSSigner:
         _check(lib().psb_sign(self.m_pk.handle, C.c_size_t(N), _p(Cm), C.c_size_t(na), _p(blob), _p(off), _p(_u64(u, FR)),
                               _p(s1), _p(s2), _p(ser)), "psb_sign")
         return s1, s2, ser
+
+
+WIRE_IDPROOF, WIRE_REQUEST = 0, 1                    # include/psb.h PSB_WIRE_*
+
+
+def _wire_encode(kind, n_attrs, p0, sig2, k, phi, E1, E2, c, rs, attributes, base64):
+    ensure_init()
+    p0 = _u64(p0, G1)
+    N = p0.shape[0]
+    rs = np.ascontiguousarray(rs, dtype=np.uint64).reshape(N, -1, FR)
+    blob, off = _packed(attributes, False)
+    if off.shape[0] != N * n_attrs + 1:
+        raise ValueError("attribute size does not match")
+    opt = lambda a, w: None if a is None else _p(_u64(a, w))  # noqa: E731
+    out_off = np.zeros(N + 1, dtype=np.uint64)
+    args = [C.c_int(kind), C.c_size_t(N), C.c_size_t(n_attrs), _p(p0), opt(sig2, G1), opt(k, G2), opt(phi, G1), opt(E1, G1),
+            opt(E2, G1), _p(_u64(c, FR)), _p(rs), C.c_size_t(rs.shape[1]), _p(blob), _p(off), C.c_int(int(base64))]
+    _check(lib().psb_wire_encode(*args, None, C.c_size_t(0), _p(out_off)), "psb_wire_encode")
+    out = np.zeros(int(out_off[-1]) + 8, dtype=np.uint8)
+    _check(lib().psb_wire_encode(*args, _p(out), C.c_size_t(int(out_off[-1])), _p(out_off)), "psb_wire_encode")
+    return out, out_off
+
+
+def idproof_serialize(proof: dict, attributes, n_attrs: int, with_id: bool = True, base64: bool = False):
+    """batched IdProof::toBufferString() (or its base64 text) on the device: packed (blob, off) of N messages."""
+    return _wire_encode(WIRE_IDPROOF, n_attrs, proof["sig1"], proof["sig2"], proof["k"], proof["phi"],
+                        proof["E1"] if with_id else None, proof["E2"] if with_id else None, proof["c"], proof["rs"], attributes, base64)
+
+
+def request_serialize(A, c, rs, attributes, n_attrs: int, base64: bool = False):
+    """batched PSCredRequest::toBufferString() (or its base64 text) on the device."""
+    return _wire_encode(WIRE_REQUEST, n_attrs, A, None, None, None, None, None, c, rs, attributes, base64)
 
 
 def pairing(P, Q):

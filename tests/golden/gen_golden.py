@@ -7,6 +7,7 @@ reference compiled by oracle/Makefile).  Outputs, all small JSON with hex string
                  finalExp input/output pair (:398-436)
   keys.json      synthetic PS keys (n = 5, 10, 20, 50) with known exponents, seed 1,
                  g = H1("abc"), gg = H2("edf"), all points normalized
+  keys_bn254.json  the same for BN254 (n = 5), written when run with PSB_CURVE=bn254 (only this file is written then)
   protocol.json  reference outputs of the protocol entry points on small seeded batches:
                  verify (verdict + fused GT), randomize (serialized)
   elpasso.json   reference outputs of el_passo_provide_id (serialized credentials) and
@@ -52,9 +53,9 @@ def mcl_kat():
             "final_exp_in": ["0x" + x for x in e0], "final_exp_out": ["0x" + x for x in e1]}
 
 
-def keys():
+def keys(sizes=(5, 10, 20, 50)):
     out = {}
-    for n in (5, 10, 20, 50):
+    for n in sizes:
         k = ref.KeyMaterial(n, seed_=1)
         out[str(n)] = {"g": hx(k.g), "gg": hx(k.gg), "XX": hx(k.XX), "Y": hx(k.Y), "YY": hx(k.YY), "X": hx(k.X),
                        "x": hex(ref.fr_to_ints(k.x)[0]), "y": [hex(v) for v in ref.fr_to_ints(k.y)]}
@@ -120,6 +121,11 @@ def prover():
 
 
 if __name__ == "__main__":
+    if ref.BN254:
+        with open(os.path.join(HERE, "keys_bn254.json"), "w") as f:
+            json.dump(keys((5,)), f, indent=1)
+        print("wrote keys_bn254.json")
+        sys.exit(0)
     for name, fn in (("mcl_kat.json", mcl_kat), ("keys.json", keys), ("protocol.json", protocol), ("elpasso.json", elpasso), ("prover.json", prover)):
         with open(os.path.join(HERE, name), "w") as f:
             json.dump(fn(), f, indent=1)

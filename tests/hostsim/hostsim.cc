@@ -19,6 +19,7 @@ void hostsim_set_hash_of(const uint8_t* msg, size_t len, uint32_t* k) { psb::fr_
 }
 
 // ---- protocol lane functions (csrc/protocol.cuh) on the host: table building + one lane at a time ------
+#include <cstring>
 #include <vector>
 #include "../../ps-signature-and-el-passo_b200/csrc/prover.cuh"
 #include "../../ps-signature-and-el-passo_b200/csrc/hash_to_curve.cuh"
@@ -205,6 +206,25 @@ int hostsim_wire_parse(int kind, int n, const uint8_t* in, size_t len, int base6
     }
   }
   return ok ? 1 : 0;
+}
+// the encoder of ONE message (csrc/wire.cuh encode_message_lane / base64_encode_lane, kernels k_wire_encode / k_wire_base64_encode):
+// g1pts = sig1 sig2 phi E1 E2 (kind 0) or A (kind 1); returns the bytes written to out
+size_t hostsim_wire_encode(int kind, int n, const uint32_t* g1pts, const uint32_t* g2pt, int has_e, const uint32_t* c, const uint32_t* rs,
+                           int per, const uint8_t* attr, const uint64_t* aoff, int base64, uint8_t* out) {
+  G1J P[5]; G2J K; Fr cc; std::vector<Fr> r(per + 1);
+  const int np = kind == 0 ? 5 : 1;
+  for (int i = 0; i < np; i++) ld(P[i], g1pts + kG1U * i);
+  if (kind == 0) ld(K, g2pt);
+  for (int i = 0; i < 8; i++) cc.v[i] = c[i];
+  for (int j = 0; j < per; j++) for (int i = 0; i < 8; i++) r[j].v[i] = rs[8 * j + i];
+  const G1J* pts[5] = {&P[0], &P[1], &P[2], has_e ? &P[3] : nullptr, has_e ? &P[4] : nullptr};
+  const size_t want = wire_message_size(kind, n, per, aoff, has_e != 0);
+  std::vector<uint8_t> raw(want + 8);
+  const size_t got = encode_message_lane(raw.data(), kind, n, pts, &K, cc, r.data(), per, attr, aoff);
+  if (got != want) return 0;
+  if (!base64) { memcpy(out, raw.data(), got); return got; }
+  base64_encode_lane(out, raw.data(), got);
+  return base64_encoded_size(got);
 }
 size_t hostsim_base64_decode(const uint8_t* in, size_t len, uint8_t* out) { return base64_decode_lane(out, in, len); }
 

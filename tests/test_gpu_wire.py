@@ -188,3 +188,27 @@ def test_key_outlives_context_as_dead_handle(gpu_pkg, ref):
     pk2 = gpu_pkg.PSPubKey(wl.key.g, wl.key.gg, wl.key.XX, wl.key.Y, wl.key.YY, window_bits=6)
     assert gpu_pkg.PSVerifier(pk2).verify(wl.sig1, wl.sig2, wl.attrs).all()
     pk2.close()
+
+
+@pytest.mark.parametrize("b64", [False, True])
+def test_wire_encode_matches_reference_and_round_trips(gpu_pkg, ref, b64):
+    """psb_wire_encode (the batched prover's output format) against IdProof::toBufferString / PSCredRequest::toBufferString /
+    PSBuffer::toBase64 byte for byte, then back through psb_verify_id_ser: same verdicts as the reference on the same bytes."""
+    n, lanes = 5, 300
+    wl = workload.make_signon_workload(n, lanes, 2, seed=45, with_id=True, tamper_every=7)
+    wl.proof_attrs[1][3] = b"y" * 300
+    want = ref.idproof_encode(wl.key, wl.proof, wl.proof_attrs, with_e=True, base64=b64)
+    blob, off = gpu_pkg.idproof_serialize(wl.proof, wl.proof_attrs, n, with_id=True, base64=b64)
+    assert np.array_equal(off, want[1]) and np.array_equal(blob[:int(off[-1])], want[0][:int(off[-1])])
+    nb, no = gpu_pkg.idproof_serialize(wl.proof, wl.proof_attrs, n, with_id=False, base64=b64)
+    w2 = ref.idproof_encode(wl.key, wl.proof, wl.proof_attrs, with_e=False, base64=b64)
+    assert np.array_equal(no, w2[1]) and np.array_equal(nb[:int(no[-1])], w2[0][:int(no[-1])])
+    pk = gpu_pkg.PSPubKey(wl.key.g, wl.key.gg, wl.key.XX, wl.key.Y, wl.key.YY, window_bits=8)
+    got, parsed = gpu_pkg.PSVerifier(pk).el_passo_verify_id_wire((blob, off), wl.ads, wl.service_pt, wl.y, wl.g, wl.h, base64=b64)
+    exp = workload.expected_verify_id(wl)
+    assert parsed.all() and np.array_equal(got, exp) and 0 < exp.sum() < lanes
+    iw = workload.make_issuance_workload(n, 64, 2, seed=46)
+    want = ref.request_encode(iw.key, iw.A, iw.c, iw.rs, iw.req_attrs, base64=b64)
+    blob, off = gpu_pkg.request_serialize(iw.A, iw.c, iw.rs, iw.req_attrs, n, base64=b64)
+    assert np.array_equal(off, want[1]) and np.array_equal(blob[:int(off[-1])], want[0][:int(off[-1])])
+    pk.close()

@@ -199,3 +199,33 @@ def test_sign_lanes(hostsim, ref, n_attrs, na):
     hostsim.hostsim_sign(C.c_int(n_attrs), C.c_int(na), C.c_int(4), _p(key.g), _p(key.X), _p(key.Y), C.c_size_t(lanes), _p(Cm),
                          _p(blob), _p(off), _p(u), _p(s1), _p(s2))
     assert np.array_equal(s1, ref.g1_op(ref.G_NORM, e1)) and np.array_equal(s2, ref.g1_op(ref.G_NORM, e2))
+
+
+@pytest.mark.parametrize("with_id,b64", [(True, False), (True, True), (False, False), (False, True)])
+def test_encoder_matches_reference(hostsim, ref, with_id, b64):
+    """csrc/wire.cuh encode_message_lane / base64_encode_lane against IdProof::toBufferString, PSCredRequest::toBufferString and
+    PSBuffer::toBase64 (src/ps-encoding.cc:14-54, :429-439, :452-468), byte for byte; the reference's proofs hold raw Jacobian
+    points, so the normalisation inside the encoder is exercised too."""
+    hostsim.hostsim_wire_encode.restype = C.c_size_t
+    n, lanes = 5, 4
+    wl = workload.make_signon_workload(n, lanes, 2, seed=43, with_id=with_id)
+    wl.proof_attrs[1][3] = b"y" * 300                       # 253-prefixed length
+    wl.proof_attrs[2][4] = b""
+    want = _lanes(ref.idproof_encode(wl.key, wl.proof, wl.proof_attrs, with_e=with_id, base64=b64))
+    per = wl.proof["rs"].shape[1]
+    for j in range(lanes):
+        g1 = np.stack([wl.proof[k][j] for k in ("sig1", "sig2", "phi", "E1", "E2")])
+        blob, off = ref.pack_attrs([wl.proof_attrs[j]])
+        out = np.zeros(4096, dtype=np.uint8)
+        k = hostsim.hostsim_wire_encode(C.c_int(0), C.c_int(n), _p(g1), _p(wl.proof["k"][j]), C.c_int(int(with_id)), _p(wl.proof["c"][j]),
+                                        _p(wl.proof["rs"][j]), C.c_int(per), _p(blob), _p(off), C.c_int(int(b64)), _p(out))
+        assert bytes(out[:k]) == want[j]
+    iw = workload.make_issuance_workload(n, lanes, 2, seed=44)
+    iw.req_attrs[0][2] = b"z" * 260
+    want = _lanes(ref.request_encode(iw.key, iw.A, iw.c, iw.rs, iw.req_attrs, base64=b64))
+    for j in range(lanes):
+        blob, off = ref.pack_attrs([iw.req_attrs[j]])
+        out = np.zeros(4096, dtype=np.uint8)
+        k = hostsim.hostsim_wire_encode(C.c_int(1), C.c_int(n), _p(iw.A[j]), None, C.c_int(0), _p(iw.c[j]), _p(iw.rs[j]),
+                                        C.c_int(iw.rs.shape[1]), _p(blob), _p(off), C.c_int(int(b64)), _p(out))
+        assert bytes(out[:k]) == want[j]
