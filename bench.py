@@ -700,15 +700,19 @@ def main():
     N = args.lanes
     sig1, sig2, blob, off, expected = make_batch(pkg, key, N, rank)
 
-    # measured integer-MAC peak of this GPU (roofline denominator), a few hundred ms
-    peak_ms = min(pkg.microbench(5, 148 * 8, 256, 20000) for _ in range(2))
-    peak_mac = 148 * 8 * 256 * 20000 * 8 / (peak_ms * 1e-3)
-    peak_ms2 = min(pkg.microbench(4, 148 * 8, 256, 20000) for _ in range(2))
-    peak_mac = max(peak_mac, 148 * 8 * 256 * 20000 * 8 / (peak_ms2 * 1e-3))
-    # the same probe in the multiplier's own instruction form (carry-chained IMAD.WIDE.U32.X rows): the ceiling a
-    # carry-chain Montgomery multiplier can reach on this part (reported next to the carry-free peak, not instead of it)
-    chain_ms = min(pkg.microbench(7, 148 * 8, 256, 5000) for _ in range(2))
-    peak_chain = 148 * 8 * 256 * 5000 * 36 / (chain_ms * 1e-3)
+    # measured integer-MAC rates of this GPU (roofline denominators), a few hundred ms.  A MAC32 on this part is ONE IMAD.WIDE
+    # (32 x 32 + 64 -> 64); the pipe issues one per 4 clocks and scheduler (IMAD: 2 clocks per warp on the 16-lane fma pipe, the
+    # wide form two passes), i.e. 32 MAC32 / clk / SM.  Valid probes: carry-chained rows in the multiplier's own form (kind 7),
+    # mad.lo.cc + madc.hi pairs (kind 4), carry-free rows of 13 distinct limbs (kind 9); `peak` is the best of them.
+    # Round 1's "carry-free peak" (kind 5, 44.7 / clk / SM) is NOT a MAC rate: both factors are shared by its accumulators and
+    # ptxas folds the trip into one IMAD.WIDE plus 64-bit additions (SASS checked, profiles/r2a_microbench.json); it is kept
+    # only as `peak_r1_invalid` so that round 1's fractions can be compared.
+    geom = 148 * 8 * 256
+    rate = lambda kind, iters, per: geom * iters * per / (min(pkg.microbench(kind, 148 * 8, 256, iters) for _ in range(2)) * 1e-3)  # noqa: E731
+    peak_r1 = max(rate(5, 20000, 8), rate(4, 20000, 8))
+    peak_chain = rate(7, 5000, 36)
+    peak_mac = max(peak_chain, rate(4, 20000, 8), rate(9, 5000, 13))
+    peak_issue = 32 * 148 * 1.965e9
 
     # ---- device-resident arm -------------------------------------------------------------------
     t_s1 = torch.from_numpy(sig1.view(np.int64)).to(dev)
@@ -844,7 +848,11 @@ def main():
         "roofline": {"bound": "int32-mac", "kernel": names[dom], "achieved": achieved / 1e12, "peak": peak_mac / 1e12,
                      "unit": "TMAC32/s", "frac": achieved / peak_mac, "traffic": traffic, "traffic_source": traffic_source,
                      "kernels": kernels,
-                     "peak_source": "measured live (carry-free mad.wide.u32 probe, all SMs)",
+                     "peak_source": "measured live on all SMs: best of the valid MAC32 probes (IMAD.WIDE.U32.X carry-chain rows, mad.lo.cc + madc.hi pairs, carry-free rows of 13 limbs)",
+                     "peak_pipe_issue": peak_issue / 1e12, "frac_of_pipe_issue": achieved / peak_issue,
+                     "peak_pipe_issue_source": "derived: 1 IMAD.WIDE per 4 clocks and scheduler = 32 MAC32 / clk / SM x 148 SMs x 1.965 GHz",
+                     "peak_r1_invalid": peak_r1 / 1e12, "frac_vs_r1_denominator": achieved / peak_r1,
+                     "peak_r1_invalid_note": "round 1's denominator: a probe ptxas folds into 1 IMAD.WIDE + 8 adds per trip, not a MAC rate",
                      "peak_carry_chain": peak_chain / 1e12, "frac_of_carry_chain_peak": achieved / peak_chain,
                      "peak_carry_chain_source": "measured live (IMAD.WIDE.U32.X carry-chain rows, the multiplier's instruction form)",
                      "whole_step_frac": whole / peak_mac,

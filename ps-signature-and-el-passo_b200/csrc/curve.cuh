@@ -310,9 +310,127 @@ PSB_HD PSB_NOINL void g2_mul_gls(G2J& R, const G2J& P, const uint32_t* k) {
 PSB_HD PSB_INL void pt_mul(G1J& R, const G1J& P, const uint32_t* k) { g1_mul_glv(R, P, k); }
 PSB_HD PSB_INL void pt_mul(G2J& R, const G2J& P, const uint32_t* k) { g2_mul_gls(R, P, k); }
 #else
-// BN254: plain fixed-window multiplication (the GLV / GLS lattices of BN curves are not built; same group element)
-PSB_HD PSB_INL void pt_mul(G1J& R, const G1J& P, const uint32_t* k) { pt_mul_window(R, P, k); }
-PSB_HD PSB_INL void pt_mul(G2J& R, const G2J& P, const uint32_t* k) { pt_mul_window(R, P, k); }
+// ---- BN254: GLV in G1 (2 dimensions), GLS in G2 (4 dimensions) ---------------------------------------------------------
+// Same group elements as mcl's GLV1 / GLV2 on BN curves (ec.hpp:1457-1523, bn.hpp:765-860); the lattices, the rounding and
+// the schedule are ours (tools/gen_constants.py derives and checks the constants on the integer operations used here):
+//   G1: phi(X, Y, Z) = (beta X, Y, Z) = [lambda] P, lambda = 36 z^4 - 1;  k = k1 + k2 lambda, |k1|, |k2| < 2^127 by Babai
+//       rounding on a reduced basis of {(a, b): a + b lambda = 0 mod r}.  128 doublings instead of 256.
+//   G2: psi = [mu], mu = p mod r = 6 z^2;  k = d0 + d1 mu + d2 mu^2 + d3 mu^3, |d_i| < 2^64 by Babai rounding on an
+//       LLL-reduced basis of the 4-dimensional lattice.  64 doublings instead of 256.
+// Rounded quotients are c = (k g + 2^(32 S - 1)) >> 32 S with g = |round(2^(32 S) coefficient)|, S = PSB_GLVBN_SHIFT_LIMBS;
+// only their low 128 bits are needed: the remainders are computed mod 2^128 in two's complement and are small.
+typedef unsigned __int128 u128;
+// low 128 bits of (k * g + 2^(32 S - 1)) >> 32 S;  k: 8 limbs, g: gl limbs
+PSB_HD PSB_INL u128 mul_round_shift(const uint32_t* k, const uint32_t* g, int gl) {
+  constexpr int S = PSB_GLVBN_SHIFT_LIMBS;
+  uint32_t out[4] = {0, 0, 0, 0};
+  uint64_t lo = 0, hi = 0;
+  for (int col = 0; col < S + 4; col++) {
+    if (col == S - 1) { const uint64_t nl = lo + 0x80000000ull; hi += nl < lo; lo = nl; }   // + 2^(32 S - 1)
+    for (int i = 0; i < 8; i++) {
+      const int j = col - i;
+      if (j < 0 || j >= gl) continue;
+      const uint64_t pr = (uint64_t)k[i] * g[j];
+      const uint64_t nl = lo + pr;
+      hi += nl < lo;
+      lo = nl;
+    }
+    if (col >= S) out[col - S] = (uint32_t)lo;
+    lo = (lo >> 32) | (hi << 32);
+    hi = 0;
+  }
+  return ((u128)out[3] << 96) | ((u128)out[2] << 64) | ((u128)out[1] << 32) | out[0];
+}
+PSB_HD PSB_INL u128 load_u128(const uint32_t* w) { return ((u128)w[3] << 96) | ((u128)w[2] << 64) | ((u128)w[1] << 32) | w[0]; }
+// |v| of a two's-complement 128-bit value, neg = sign
+PSB_HD PSB_INL u128 abs_s128(u128 v, bool& neg) { neg = (v >> 127) != 0; return neg ? (u128)0 - v : v; }
+PSB_HD PSB_INL uint32_t nibble_u128(u128 v, int i) { return (uint32_t)(v >> (4 * i)) & 0xFu; }
+
+PSB_HD PSB_NOINL void g1_mul_glv(G1J& R, const G1J& P, const uint32_t* k) {
+  const u128 c1 = mul_round_shift(k, PSB_K(GLVBN_G), 6), c2 = mul_round_shift(k, PSB_K(GLVBN_G) + 6, 6);
+  const u128 klo = load_u128(k);
+  bool n1, n2;
+  const u128 k1 = abs_s128(klo - c1 * load_u128(PSB_K(GLVBN_SA)) - c2 * load_u128(PSB_K(GLVBN_SA) + 4), n1);
+  const u128 k2 = abs_s128((u128)0 - c1 * load_u128(PSB_K(GLVBN_SB)) - c2 * load_u128(PSB_K(GLVBN_SB) + 4), n2);
+  G1J tbl[16];
+  pt_set_zero(tbl[0]);
+  tbl[1] = P;
+  pt_dbl(tbl[2], P);
+  for (int i = 3; i < 16; i++) pt_add(tbl[i], tbl[i - 1], P);
+  Fp beta;
+  for (int i = 0; i < PSB_NL; i++) beta.v[i] = PSB_K(GLV_BETA)[i];
+  G1J acc, T;
+  pt_set_zero(acc);
+  for (int i = 31; i >= 0; i--) {
+    pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc);
+    const uint32_t d1 = nibble_u128(k1, i), d2 = nibble_u128(k2, i);
+    if (d1) {
+      T = tbl[d1];
+      if (n1) fp_neg(T.y, T.y);
+      pt_add(acc, acc, T);
+    }
+    if (d2) {
+      T = tbl[d2];
+      fp_mul(T.x, T.x, beta);          // phi(d2 P)
+      if (n2) fp_neg(T.y, T.y);
+      pt_add(acc, acc, T);
+    }
+  }
+  R = acc;
+}
+
+// psi^j(T) for a Jacobian point, j = 1..3 (D-type twist constants from tools/gen_constants.py):
+//   psi(x, y) = (conj(x) cx, conj(y) cy), psi^2(x, y) = (x N(cx), -y), psi^3(x, y) = (conj(x) cx3, -conj(y) cy)
+PSB_HD PSB_NOINL void g2_psi_pow(G2J& T, int j) {
+  if (j == 2) {
+    Fp n;
+    for (int i = 0; i < PSB_NL; i++) n.v[i] = PSB_K(PSI_NCX)[i];
+    fp2_mul_fp(T.x, T.x, n);
+    fp2_neg(T.y, T.y);
+    return;
+  }
+  Fp2 c;
+  const uint32_t* cxp = (j == 1) ? PSB_K(PSI_CX) : PSB_K(PSI_CX3);
+  for (int i = 0; i < PSB_NL; i++) { c.a.v[i] = cxp[i]; c.b.v[i] = cxp[PSB_NL + i]; }
+  fp2_conj(T.x, T.x); fp2_conj(T.y, T.y); fp2_conj(T.z, T.z);
+  fp2_mul(T.x, T.x, c);
+  for (int i = 0; i < PSB_NL; i++) { c.a.v[i] = PSB_K(PSI_CY)[i]; c.b.v[i] = PSB_K(PSI_CY)[PSB_NL + i]; }
+  fp2_mul(T.y, T.y, c);
+  if (j == 3) fp2_neg(T.y, T.y);
+}
+
+PSB_HD PSB_NOINL void g2_mul_gls(G2J& R, const G2J& P, const uint32_t* k) {
+  u128 c[4], d[4];
+  bool neg[4];
+  for (int j = 0; j < 4; j++) c[j] = mul_round_shift(k, PSB_K(GLSBN_G) + 8 * j, 8);
+  for (int i = 0; i < 4; i++) {
+    u128 v = i == 0 ? load_u128(k) : (u128)0;
+    for (int j = 0; j < 4; j++) v -= c[j] * load_u128(PSB_K(GLSBN_SB) + 4 * (4 * j + i));
+    d[i] = abs_s128(v, neg[i]);
+  }
+  G2J tbl[16];
+  pt_set_zero(tbl[0]);
+  tbl[1] = P;
+  pt_dbl(tbl[2], P);
+  for (int i = 3; i < 16; i++) pt_add(tbl[i], tbl[i - 1], P);
+  G2J acc, T;
+  pt_set_zero(acc);
+  for (int i = PSB_GLS_BN_WINDOWS - 1; i >= 0; i--) {
+    pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc);
+    for (int j = 0; j < 4; j++) {
+      const uint32_t dj = nibble_u128(d[j], i);
+      if (!dj) continue;
+      T = tbl[dj];
+      if (j) g2_psi_pow(T, j);
+      if (neg[j]) fp2_neg(T.y, T.y);
+      pt_add(acc, acc, T);
+    }
+  }
+  R = acc;
+}
+
+PSB_HD PSB_INL void pt_mul(G1J& R, const G1J& P, const uint32_t* k) { g1_mul_glv(R, P, k); }
+PSB_HD PSB_INL void pt_mul(G2J& R, const G2J& P, const uint32_t* k) { g2_mul_gls(R, P, k); }
 #endif
 
 // ---- fixed-base windows --------------------------------------------------------------------------

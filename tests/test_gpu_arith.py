@@ -4,7 +4,7 @@ raw Montgomery limbs / serialized points."""
 import numpy as np
 import pytest
 
-from tests.conftest import CURVE_Z, FIELD_P, GROUP_R, rand_fp_raw
+from tests.conftest import BN254, CURVE_Z, FIELD_P, GROUP_R, rand_fp_raw
 
 pytestmark = pytest.mark.gpu
 
@@ -158,6 +158,10 @@ def test_glv_gls_scalar_edges(gpu_pkg, ref):
     lam = Z * Z - 1          # BLS12-381's GLV eigenvalue; on BN254 just another boundary-sized scalar
     ks = [0, 1, 2, 15, 16, lam - 1, lam, lam + 1, 2 * lam, lam * lam, lam * (lam + 1), Z - 1, Z, Z + 1, Z * Z, Z ** 3, Z ** 3 - 1,
           (1 << 64) - 1, 1 << 64, (1 << 128) - 1, 1 << 128, R - 1, R - 2]
+    if BN254:                # BN254's eigenvalues: lambda = 36 z^4 - 1 (G1), mu = 6 z^2 (G2), and the sizes of the lattice vectors
+        lb, mu = 36 * Z ** 4 - 1, 6 * Z * Z
+        ks += [lb - 1, lb, lb + 1, 2 * lb, mu - 1, mu, mu + 1, mu * mu, mu ** 3, mu ** 3 + mu, 6 * Z * Z + 2 * Z, 2 * Z + 1, (1 << 127) - 1,
+               1 << 127, (1 << 253) + 1, R // 2, R // 2 + 1, R // 3, 2 * R // 3]
     ks = [k % R for k in ks]
     rng = np.random.default_rng(5)
     ks += [int.from_bytes(rng.bytes(32), "little") % R for _ in range(105)]
