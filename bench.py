@@ -106,6 +106,11 @@ def tile_packed(blob: np.ndarray, off: np.ndarray, reps: int):
     return b, o
 
 
+def lane_strings(blob, off, j: int, n_attrs: int):
+    """the attribute strings of lane j of a packed batch (checker side: the reference takes lists)."""
+    return [bytes(blob[int(off[j * n_attrs + i]):int(off[j * n_attrs + i + 1])]) for i in range(n_attrs)]
+
+
 def attr_lists(n_attrs: int, lanes: int):
     return [[b"a%d:%d" % (i, j) for i in range(n_attrs)] for j in range(lanes)]
 

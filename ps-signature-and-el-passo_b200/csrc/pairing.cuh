@@ -484,30 +484,6 @@ PSB_HD PSB_NOINL void final_exp(Fp12& y, const Fp12& x, bool block_sync = false)
   fp12_frobenius(a4, a4, 3);
   fp12_mul(y, a4, a);
   (void)a5; (void)a7;
-#elif defined(PSB_HARD_MCL)
-  // hard part, mcl's own sequence (expHardPartBLS12, bn.hpp:1508-1555): kept for A/B builds
-  fp12_conj(a0, t);             // t^-1
-  fp12_cyclo_sqr(a1, a0);       // t^-2
-  pow_z(a2, t);                 // t^z
-  fp12_cyclo_sqr(a3, a2);       // t^2z
-  fp12_mul(a1, a1, a2);         // t^(z-2)
-  pow_z(a7, a1);                // t^(z^2-2z)
-  pow_z(a4, a7);                // t^(z^3-2z^2)
-  pow_z(a5, a4);                // t^(z^4-2z^3)
-  fp12_mul(a3, a3, a5);         // t^(z^4-2z^3+2z)
-  pow_z(a5, a3);                // t^(z^5-2z^4+2z^2)   (mcl's a6)
-  fp12_conj(a1, a1);            // t^(2-z)
-  fp12_mul(a1, a1, a5);
-  fp12_mul(a1, a1, t);          // t^c0,  c0 = z^5-2z^4+2z^2-z+3
-  fp12_mul(a3, a3, a0);         // t^c1,  c1 = z^4-2z^3+2z-1
-  fp12_frobenius(a3, a3, 1);
-  fp12_mul(a1, a1, a3);
-  fp12_mul(a4, a4, a2);         // t^c2,  c2 = z^3-2z^2+z
-  fp12_frobenius(a4, a4, 2);
-  fp12_mul(a1, a1, a4);
-  fp12_mul(a7, a7, t);          // t^c3,  c3 = z^2-2z+1
-  fp12_frobenius(a7, a7, 3);
-  fp12_mul(y, a7, a1);
 #else
   // hard part: the SAME exponent as mcl's expHardPartBLS12 (bn.hpp:1508-1555), 3 (p^4 - p^2 + 1) / r, through the
   // factorisation of Hayashida, Hayasaka and Teruya (2020):  (z - 1)^2 (z + p) (z^2 + p^2 - 1) + 3   (identity checked in

@@ -92,12 +92,9 @@ template <class Launch> inline void for_waves(size_t n, Launch&& launch) {   // 
     launch(full, n, (int)b);
   }
 }
-// A/B switch PSB_OCC_SMEM=<bytes>: dynamic shared memory requested (and not used) by the pairing-pipeline kernels, to cap
-// the resident blocks per SM below what the register file allows (e.g. 118784 with 256-thread blocks: ONE block per SM).
-size_t g_pair_smem = 0;
 #define PSB_WAVES(n, kernel, ...)                                                              \
   for_waves((n), [&](size_t wb_, size_t we_, int blk_) {                                       \
-    kernel<<<nblocks(we_ - wb_, blk_), blk_, g_pair_smem, st>>>(we_, wb_, __VA_ARGS__);        \
+    kernel<<<nblocks(we_ - wb_, blk_), blk_, 0, st>>>(we_, wb_, __VA_ARGS__);        \
     LAUNCHED();                                                                                \
   })
 
@@ -303,16 +300,8 @@ int psb_init(int curve, const int* devices, int ndev) {
     // thread-local state (Fp12 temporaries, window tables of points) lives in local memory:
     // prefer L1 over shared memory, and give deep call chains enough stack
     cudaDeviceSetLimit(cudaLimitStackSize, 32 * 1024);
-    if (const char* occ = getenv("PSB_OCC_SMEM")) {
-      g_pair_smem = (size_t)atol(occ);
-      const int b = (int)g_pair_smem;
-      cudaFuncSetAttribute(k_verify_msm, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
-      cudaFuncSetAttribute(k_verify_miller, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
-      cudaFuncSetAttribute(k_verify_final, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
-      cudaFuncSetAttribute(k_pairing_miller, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
-      cudaFuncSetAttribute(k_final_exp, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
-    } else if (!getenv("PSB_NO_L1_PREF")) {   // (A/B switch; the kernels use no shared memory)
-      const int l1 = cudaSharedmemCarveoutMaxL1;
+    {
+      const int l1 = cudaSharedmemCarveoutMaxL1;   // the kernels use no shared memory (measured: the driver picks this anyway)
       cudaFuncSetAttribute(k_verify_msm, cudaFuncAttributePreferredSharedMemoryCarveout, l1);
       cudaFuncSetAttribute(k_verify_miller, cudaFuncAttributePreferredSharedMemoryCarveout, l1);
       cudaFuncSetAttribute(k_verify_final, cudaFuncAttributePreferredSharedMemoryCarveout, l1);

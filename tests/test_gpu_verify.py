@@ -124,13 +124,13 @@ def test_randomize_verify_round_trip_large(gpu_pkg, ref):
 def test_full_size_2p20_properties(gpu_pkg, ref):
     """BASELINE.json configs[1] at its full size -- 2^20 signatures, 5 attributes -- through size-independent properties
     (the oracle needs 73 core-minutes for this batch): (i) the verdict bitmap equals the construction (honest lanes
-    accept, the 1024 tampered lanes -- swapped, sigma1 = 0, attribute changed -- reject); (ii) idempotence: a second
+    accept, the 1024 tampered lanes -- swapped, sigma1 = 0, attribute changed, sigma2 += g -- reject); (ii) idempotence: a second
     pass gives the same bitmap; (iii) verify(randomize(sigma, t)) == verify(sigma) lane by lane; (iv) a uniformly drawn
     sample of 512 lanes + every tampered lane of the first 2^16 agrees with the reference's PSVerifier::verify."""
     import bench
     lanes = 1 << 20
     key = bench.load_key(5)
-    sig1, sig2, blob, off, expected, lane_attrs = bench.make_batch(gpu_pkg, key, lanes, 0)
+    sig1, sig2, blob, off, expected = bench.make_batch(gpu_pkg, key, lanes, 0)
     pk = gpu_pkg.PSPubKey(key["g"], key["gg"], key["XX"], key["Y"], key["YY"], window_bits=16)
     ver = gpu_pkg.PSVerifier(pk)
     v1 = ver.verify(sig1, sig2, (blob, off))
@@ -145,7 +145,7 @@ def test_full_size_2p20_properties(gpu_pkg, ref):
     pick = np.unique(np.concatenate([rng.integers(0, lanes, 512), np.arange(1023, 1 << 16, 1024)]))
     km = ref.KeyMaterial(5, seed_=1)             # the key of tests/golden/keys.json (bench.load_key)
     assert np.array_equal(km.XX.reshape(-1), key["XX"].reshape(-1))
-    want = ref.ps_verify(km, sig1[pick].copy(), sig2[pick].copy(), [lane_attrs[j] for j in pick], nthreads=ref.hw_threads())
+    want = ref.ps_verify(km, sig1[pick].copy(), sig2[pick].copy(), [bench.lane_strings(blob, off, j, 5) for j in pick], nthreads=ref.hw_threads())
     assert np.array_equal(v1[pick], want)
     pk.close()
 
@@ -164,12 +164,12 @@ def test_wave_boundaries(gpu_pkg, ref):
     ver = gpu_pkg.PSVerifier(pk)
     km = ref.KeyMaterial(5, seed_=1)
     for lanes in (wave - 1, wave, wave + 1, 2 * wave + 33):
-        sig1, sig2, blob, off, expected, lane_attrs = bench.make_batch(gpu_pkg, key, lanes, 0, base=2048)
+        sig1, sig2, blob, off, expected = bench.make_batch(gpu_pkg, key, lanes, 0, base=2048)
         got = ver.verify(sig1, sig2, (blob, off))
         assert np.array_equal(got, expected), lanes
         full = lanes // wave * wave
         pick = np.unique(np.clip(np.array([0, full - 2, full - 1, full, full + 1, lanes - 2, lanes - 1, 1023]), 0, lanes - 1))
-        want = ref.ps_verify(km, sig1[pick].copy(), sig2[pick].copy(), [lane_attrs[j] for j in pick])
+        want = ref.ps_verify(km, sig1[pick].copy(), sig2[pick].copy(), [bench.lane_strings(blob, off, j, 5) for j in pick])
         assert np.array_equal(got[pick], want), lanes
     pk.close()
     ref.seed(7)

@@ -1,6 +1,8 @@
 #!/usr/bin/env python3
-"""tools/ncu_summary.py <report.ncu-rep> -- prints the per-kernel metrics we track (CPU side, no GPU)."""
-import csv, subprocess, sys, io
+"""tools/ncu_summary.py <report.ncu-rep> [--traffic OUT.json LANES COMMIT DATE] -- prints the per-kernel metrics we track
+(CPU side, no GPU).  sm__pipe_fmaheavy_cycles_active is the pipe that executes IMAD.WIDE (the multiplier's instruction);
+--traffic also writes the DRAM bytes per launch of the k_verify_* kernels (what bench.py's roofline.traffic scales per lane)."""
+import csv, json, subprocess, sys, io
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
@@ -19,3 +21,15 @@ for r in rows[2:]:
     for k in keys:
         if k in hdr:
             i = hdr.index(k); print('  %-88s %s %s' % (k, r[i], units[i]))
+
+if len(sys.argv) > 2 and sys.argv[2] == "--traffic":
+    out, lanes, commit, date = sys.argv[3], int(sys.argv[4]), sys.argv[5], sys.argv[6]
+    tr = {}
+    ir, iw, ik = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum'), hdr.index('Kernel Name')
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for r in rows[2:]:
+        name = r[ik].split("(")[0]
+        if name.startswith("k_verify_") and name not in tr:
+            tr[name] = float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
+    json.dump({"source": "ncu --set full, one full wave, " + rep, "lanes": lanes, "commit": commit, "date": date,
+               "dram_bytes_per_launch": tr}, open(out, "w"), indent=1)

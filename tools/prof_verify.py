@@ -12,7 +12,7 @@ steps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 pkg = ge.load_package(); pkg.init([0])
 key = bench.load_key(5)
 pk = pkg.PSPubKey(key["g"], key["gg"], key["XX"], key["Y"], key["YY"], window_bits=wbits)
-sig1, sig2, blob, off, expected, _ = bench.make_batch(pkg, key, lanes, 0, base=min(lanes, 4096))
+sig1, sig2, blob, off, expected = bench.make_batch(pkg, key, lanes, 0, base=min(lanes, 4096))
 ver = pkg.PSVerifier(pk)
 for _ in range(steps):
     v = ver.verify(sig1, sig2, (blob, off))
