@@ -56,7 +56,7 @@ A_MILLER2 = 7673 - 680 - 39  # two-pairing Miller loop, FpMul-eq
 #           and raises to their value 105 = (2^3-1)(2^4-1) with 7 squarings + 2 products instead of 6 + 3: 5 * 36 = 180 fewer
 A_FINALEXP = 6100 + 480 - (476 - 8) - 1145 - 303 - 180 - 180
 A_MSM_PER_ADD = 29    # one mixed Jacobian+affine G2 addition
-TRAFFIC_FILE = "r1zb_traffic.json"   # latest committed ncu DRAM-traffic capture (profiles/)
+TRAFFIC_FILE = "r2h_traffic.json"   # latest committed ncu DRAM-traffic capture (profiles/)
 
 
 def a_verify_fpmul(n_attrs: int, window_bits: int) -> float:

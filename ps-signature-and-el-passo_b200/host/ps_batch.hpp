@@ -657,5 +657,86 @@ private:
   detail::KeyHandle m_key;
 };
 
+// ---- wire-format OUTPUT on the GPU (psb_wire_encode) -------------------------------------------------------------------------
+// to_wire_base64(msgs)[j] == msgs[j].toBufferString().toBase64(), to_wire(msgs)[j] == msgs[j].toBufferString()
+// (src/ps-encoding.cc:14-54, :429-439, :452-468) for std::vector<IdProof> and std::vector<PSCredRequest>: normalisation of
+// every point (one inversion each in mcl's serialize), TLV framing and base64 run on the device -- what a batched prover
+// (el_passo_prove_id / el_passo_request_id above) sends.  All messages of one call must carry the same number of responses
+// and attributes, and either all or none of the proofs carry E1 / E2 (true for the outputs of one batched prover call).
+namespace detail {
+template <class Msg> struct WireKind;
+template <> struct WireKind<IdProof> { static constexpr int kind = PSB_WIRE_IDPROOF; };
+template <> struct WireKind<PSCredRequest> { static constexpr int kind = PSB_WIRE_REQUEST; };
+inline const mcl::bls12::G1& first_point(const IdProof& p) { return p.sig1; }
+inline const mcl::bls12::G1& first_point(const PSCredRequest& r) { return r.A; }
+
+template <class Msg>
+inline void wire_encode(const std::vector<Msg>& msgs, bool base64, std::vector<uint8_t>& out, std::vector<uint64_t>& off) {
+  using namespace mcl::bls12;
+  constexpr bool proof = std::is_same<Msg, IdProof>::value;
+  const size_t N = msgs.size();
+  off.assign(N + 1, 0);
+  out.clear();
+  if (N == 0) return;
+  const size_t per = msgs[0].rs.size(), n = msgs[0].attributes.size();
+  bool has_e = false;
+  if constexpr (proof) has_e = msgs[0].E1.has_value() && msgs[0].E2.has_value();
+  std::vector<G1> p0(N), s2(proof ? N : 0), phi(proof ? N : 0), E1(has_e ? N : 0), E2(has_e ? N : 0);
+  std::vector<G2> k(proof ? N : 0);
+  std::vector<Fr> c(N), rs(N * per + 1);
+  std::vector<uint8_t> blob, bad;
+  std::vector<uint64_t> aoff;
+  for (size_t j = 0; j < N; j++) {
+    if (msgs[j].rs.size() != per || msgs[j].attributes.size() != n) throw std::runtime_error("attribute size does not match");
+    if constexpr (proof)
+      if ((msgs[j].E1.has_value() && msgs[j].E2.has_value()) != has_e) throw std::runtime_error("proofs with and without E1 / E2 in one batch");
+  }
+  flatten_lanes(N, n, [&](size_t j) -> const std::vector<std::string>& { return msgs[j].attributes; }, blob, aoff, bad);
+  parallel_lanes(N, [&](size_t b, size_t e) {
+    for (size_t j = b; j < e; j++) {
+      p0[j] = first_point(msgs[j]);
+      c[j] = msgs[j].c;
+      for (size_t i = 0; i < per; i++) rs[j * per + i] = msgs[j].rs[i];
+      if constexpr (proof) {
+        s2[j] = msgs[j].sig2; k[j] = msgs[j].k; phi[j] = msgs[j].phi;
+        if (has_e) { E1[j] = *msgs[j].E1; E2[j] = *msgs[j].E2; }
+      }
+    }
+  });
+  auto call = [&](uint8_t* dst, size_t cap) {
+    check(psb_wire_encode(WireKind<Msg>::kind, N, n, u64(p0.data()), proof ? u64(s2.data()) : nullptr, proof ? u64(k.data()) : nullptr,
+                          proof ? u64(phi.data()) : nullptr, has_e ? u64(E1.data()) : nullptr, has_e ? u64(E2.data()) : nullptr,
+                          u64(c.data()), u64(rs.data()), per, blob.data(), aoff.data(), base64 ? 1 : 0, dst, cap, off.data()),
+          "psb_wire_encode");
+  };
+  call(nullptr, 0);                          // sizes
+  out.resize((size_t)off[N] + 8);
+  call(out.data(), (size_t)off[N]);
+}
+}  // namespace detail
+
+template <class Msg>
+inline std::vector<std::string> to_wire_base64(const std::vector<Msg>& msgs) {
+  std::vector<uint8_t> out;
+  std::vector<uint64_t> off;
+  detail::wire_encode(msgs, true, out, off);
+  std::vector<std::string> r(msgs.size());
+  detail::parallel_lanes(msgs.size(), [&](size_t b, size_t e) {
+    for (size_t j = b; j < e; j++) r[j].assign(reinterpret_cast<const char*>(out.data()) + off[j], (size_t)(off[j + 1] - off[j]));
+  });
+  return r;
+}
+template <class Msg>
+inline std::vector<PSBuffer> to_wire(const std::vector<Msg>& msgs) {
+  std::vector<uint8_t> out;
+  std::vector<uint64_t> off;
+  detail::wire_encode(msgs, false, out, off);
+  std::vector<PSBuffer> r(msgs.size());
+  detail::parallel_lanes(msgs.size(), [&](size_t b, size_t e) {
+    for (size_t j = b; j < e; j++) r[j].insert(r[j].end(), out.begin() + (size_t)off[j], out.begin() + (size_t)off[j + 1]);
+  });
+  return r;
+}
+
 }  // namespace psb
 #endif  // PSB_HOST_PS_BATCH_HPP_

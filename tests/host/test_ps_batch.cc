@@ -228,6 +228,17 @@ int main(int argc, char** argv) {
       EXPECT(exact.el_passo_verify_id(z, ads, "service", authority_pk, g, h)[12] == 1);
       EXPECT(rp.el_passo_verify_id(z, ads, "service", authority_pk, g, h)[12] == 0);
     }
+    // the other direction: the device-side encoder (psb_wire_encode) against toBufferString() / toBase64(), byte for byte
+    {
+      std::vector<std::string> e64 = psb::to_wire_base64(proofs), e64n = psb::to_wire_base64(proofs2), r64 = psb::to_wire_base64(requests);
+      std::vector<PSBuffer> eraw = psb::to_wire(proofs);
+      for (size_t j = 0; j < N; j++) {
+        EXPECT(e64[j] == proofs[j].toBufferString().toBase64());
+        EXPECT(e64n[j] == proofs2[j].toBufferString().toBase64());
+        EXPECT(r64[j] == requests[j].toBufferString().toBase64());
+        EXPECT(eraw[j] == proofs[j].toBufferString());
+      }
+    }
     // issuance from wire requests
     std::vector<std::string> rq64;
     for (auto& r : requests) rq64.push_back(r.toBufferString().toBase64());
