@@ -661,8 +661,8 @@ private:
 // to_wire_base64(msgs)[j] == msgs[j].toBufferString().toBase64(), to_wire(msgs)[j] == msgs[j].toBufferString()
 // (src/ps-encoding.cc:14-54, :429-439, :452-468) for std::vector<IdProof> and std::vector<PSCredRequest>: normalisation of
 // every point (one inversion each in mcl's serialize), TLV framing and base64 run on the device -- what a batched prover
-// (el_passo_prove_id / el_passo_request_id above) sends.  All messages of one call must carry the same number of responses
-// and attributes, and either all or none of the proofs carry E1 / E2 (true for the outputs of one batched prover call).
+// (el_passo_prove_id / el_passo_request_id above) sends.  Messages may differ in their numbers of responses / attributes and in
+// carrying E1 / E2: lanes are grouped, one device call per group.
 namespace detail {
 template <class Msg> struct WireKind;
 template <> struct WireKind<IdProof> { static constexpr int kind = PSB_WIRE_IDPROOF; };
@@ -670,36 +670,35 @@ template <> struct WireKind<PSCredRequest> { static constexpr int kind = PSB_WIR
 inline const mcl::bls12::G1& first_point(const IdProof& p) { return p.sig1; }
 inline const mcl::bls12::G1& first_point(const PSCredRequest& r) { return r.A; }
 
+// one homogeneous group of messages (same number of responses and attributes, E1 / E2 all present or all absent)
 template <class Msg>
-inline void wire_encode(const std::vector<Msg>& msgs, bool base64, std::vector<uint8_t>& out, std::vector<uint64_t>& off) {
+inline void wire_encode_group(const std::vector<Msg>& msgs, const std::vector<size_t>& idx, bool base64, std::vector<uint8_t>& out,
+                              std::vector<uint64_t>& off) {
   using namespace mcl::bls12;
   constexpr bool proof = std::is_same<Msg, IdProof>::value;
-  const size_t N = msgs.size();
+  const size_t N = idx.size();
   off.assign(N + 1, 0);
   out.clear();
   if (N == 0) return;
-  const size_t per = msgs[0].rs.size(), n = msgs[0].attributes.size();
+  const Msg& m0 = msgs[idx[0]];
+  const size_t per = m0.rs.size(), n = m0.attributes.size();
   bool has_e = false;
-  if constexpr (proof) has_e = msgs[0].E1.has_value() && msgs[0].E2.has_value();
+  if constexpr (proof) has_e = m0.E1.has_value() && m0.E2.has_value();
   std::vector<G1> p0(N), s2(proof ? N : 0), phi(proof ? N : 0), E1(has_e ? N : 0), E2(has_e ? N : 0);
   std::vector<G2> k(proof ? N : 0);
   std::vector<Fr> c(N), rs(N * per + 1);
   std::vector<uint8_t> blob, bad;
   std::vector<uint64_t> aoff;
-  for (size_t j = 0; j < N; j++) {
-    if (msgs[j].rs.size() != per || msgs[j].attributes.size() != n) throw std::runtime_error("attribute size does not match");
-    if constexpr (proof)
-      if ((msgs[j].E1.has_value() && msgs[j].E2.has_value()) != has_e) throw std::runtime_error("proofs with and without E1 / E2 in one batch");
-  }
-  flatten_lanes(N, n, [&](size_t j) -> const std::vector<std::string>& { return msgs[j].attributes; }, blob, aoff, bad);
+  flatten_lanes(N, n, [&](size_t t) -> const std::vector<std::string>& { return msgs[idx[t]].attributes; }, blob, aoff, bad);
   parallel_lanes(N, [&](size_t b, size_t e) {
-    for (size_t j = b; j < e; j++) {
-      p0[j] = first_point(msgs[j]);
-      c[j] = msgs[j].c;
-      for (size_t i = 0; i < per; i++) rs[j * per + i] = msgs[j].rs[i];
+    for (size_t t = b; t < e; t++) {
+      const Msg& m = msgs[idx[t]];
+      p0[t] = first_point(m);
+      c[t] = m.c;
+      for (size_t i = 0; i < per; i++) rs[t * per + i] = m.rs[i];
       if constexpr (proof) {
-        s2[j] = msgs[j].sig2; k[j] = msgs[j].k; phi[j] = msgs[j].phi;
-        if (has_e) { E1[j] = *msgs[j].E1; E2[j] = *msgs[j].E2; }
+        s2[t] = m.sig2; k[t] = m.k; phi[t] = m.phi;
+        if (has_e) { E1[t] = *m.E1; E2[t] = *m.E2; }
       }
     }
   });
@@ -713,28 +712,37 @@ inline void wire_encode(const std::vector<Msg>& msgs, bool base64, std::vector<u
   out.resize((size_t)off[N] + 8);
   call(out.data(), (size_t)off[N]);
 }
+// any mix of messages: lanes are grouped by (responses, attributes, E1 / E2 present), one device call per group;
+// put(j, bytes, len) receives lane j's message
+template <class Msg, class Put>
+inline void wire_encode(const std::vector<Msg>& msgs, bool base64, Put put) {
+  std::map<std::tuple<size_t, size_t, bool>, std::vector<size_t>> groups;
+  for (size_t j = 0; j < msgs.size(); j++) {
+    bool has_e = false;
+    if constexpr (std::is_same<Msg, IdProof>::value) has_e = msgs[j].E1.has_value() && msgs[j].E2.has_value();
+    groups[std::make_tuple(msgs[j].rs.size(), msgs[j].attributes.size(), has_e)].push_back(j);
+  }
+  for (const auto& g : groups) {
+    std::vector<uint8_t> out;
+    std::vector<uint64_t> off;
+    wire_encode_group(msgs, g.second, base64, out, off);
+    parallel_lanes(g.second.size(), [&](size_t b, size_t e) {
+      for (size_t t = b; t < e; t++) put(g.second[t], out.data() + off[t], (size_t)(off[t + 1] - off[t]));
+    });
+  }
+}
 }  // namespace detail
 
 template <class Msg>
 inline std::vector<std::string> to_wire_base64(const std::vector<Msg>& msgs) {
-  std::vector<uint8_t> out;
-  std::vector<uint64_t> off;
-  detail::wire_encode(msgs, true, out, off);
   std::vector<std::string> r(msgs.size());
-  detail::parallel_lanes(msgs.size(), [&](size_t b, size_t e) {
-    for (size_t j = b; j < e; j++) r[j].assign(reinterpret_cast<const char*>(out.data()) + off[j], (size_t)(off[j + 1] - off[j]));
-  });
+  detail::wire_encode(msgs, true, [&](size_t j, const uint8_t* p, size_t len) { r[j].assign(reinterpret_cast<const char*>(p), len); });
   return r;
 }
 template <class Msg>
 inline std::vector<PSBuffer> to_wire(const std::vector<Msg>& msgs) {
-  std::vector<uint8_t> out;
-  std::vector<uint64_t> off;
-  detail::wire_encode(msgs, false, out, off);
   std::vector<PSBuffer> r(msgs.size());
-  detail::parallel_lanes(msgs.size(), [&](size_t b, size_t e) {
-    for (size_t j = b; j < e; j++) r[j].insert(r[j].end(), out.begin() + (size_t)off[j], out.begin() + (size_t)off[j + 1]);
-  });
+  detail::wire_encode(msgs, false, [&](size_t j, const uint8_t* p, size_t len) { r[j].insert(r[j].end(), p, p + len); });
   return r;
 }
 
