@@ -126,6 +126,37 @@ __global__ void __launch_bounds__(256) k_bench_mad(int kind, int iters, const ui
     for (int j = 0; j < PSB_NL; j++) s ^= E1[j] ^ O1[j] ^ E2[j] ^ O2[j] ^ E3[j] ^ O3[j];
     if (s == 0xdeadbeefu) sink[0] = s;
 #endif
+  } else if (kind == 12 || kind == 13 || kind == 14) {
+#ifdef __CUDA_ARCH__
+    // kind 7's carry-chained rows (36 MAC32 per iteration) with an FP64 stream beside them: 24 (kind 12) or 72 (kind 13)
+    // independent DFMA per iteration, or the 72 DFMA alone (kind 14).  Question: does the idle FP64 pipe issue beside the
+    // saturated integer-multiply pipe?  (72 DFMA = two per MAC32: an exact 32 x 32 product takes two DFMA with 16-bit split factors.)
+    cios::L12 E1, O1, E2, O2, E3, O3, av;
+    for (int j = 0; j < PSB_NL; j++) { E1[j] = seed[j] + t; O1[j] = seed[PSB_NL + j] ^ t; E2[j] = E1[j] + 1; O2[j] = O1[j] + 2; E3[j] = E1[j] ^ 5; O3[j] = O1[j] ^ 9; av[j] = seed[j] * (t | 1); }
+    double f[12], x = 1.0 + (double)(seed[0] & 7u) * 1e-9, y = (double)(t | 1u);
+    for (int j = 0; j < 12; j++) f[j] = (double)(seed[j] ^ t);
+    const int nd = kind == 12 ? 2 : 6;
+    for (int it = 0; it < iters; it++) {
+      if (kind != 14) cios::mac(E1, O1, av, b);
+      for (int r = 0; r < nd; r++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) f[j] = __fma_rz(f[j], x, y);
+      if (kind != 14) cios::mac(E2, O2, av, a);
+      for (int r = 0; r < nd; r++)
+#pragma unroll
+        for (int j = 4; j < 8; j++) f[j] = __fma_rz(f[j], x, y);
+      if (kind != 14) cios::mac(E3, O3, av, b ^ a);
+      for (int r = 0; r < nd; r++)
+#pragma unroll
+        for (int j = 8; j < 12; j++) f[j] = __fma_rz(f[j], x, y);
+      a += E1[0];
+    }
+    uint32_t s = 0;
+    double fs = 0;
+    for (int j = 0; j < PSB_NL; j++) s ^= E1[j] ^ O1[j] ^ E2[j] ^ O2[j] ^ E3[j] ^ O3[j];
+    for (int j = 0; j < 12; j++) fs += f[j];
+    if (s == 0xdeadbeefu || fs == 12345.678) sink[0] = s;
+#endif
   } else if (kind == 8) {
     // FP64 fused multiply-add (round toward zero, the form of the double-precision big-number multipliers): 8 chains.
     // Orientation for a DFMA-based Montgomery multiplier: one DFMA carries a 52-bit x 52-bit partial product.
