@@ -105,6 +105,11 @@ PSB_HD PSB_INL const Fp* fp2_comp(const Fp2& x, int k) { return &x.a + k; }
 #ifndef PSB_LAZY_Y
 #define PSB_LAZY_Y 1
 #endif
+#if PSB_LAZY_Y && !PSB_IS_BN
+// unreduced sums on the MULTIPLIER side need (8 p^2 + R p) / R < 2p, i.e. 8 p < R = 2^(32 N): three spare bits in the limbs
+// (tests/test_cios_model.py::test_fused_dot2_with_unreduced_operands runs the generated rows at that bound)
+static_assert(PSB_FP_BITS + 3 <= 32 * PSB_NL, "PSB_LAZY_Y needs 8p < R: keep the multiplier-side sums canonical on this curve");
+#endif
 // Engine A comes in two forms (PSB_ENGINE_A_LAZY):
 //   0 (default)  the fused two-product form: one reduction per row inside the multiplier, 4 N^2 + 2 (N^2 + N) wide MACs
 //                (888 for N = 12), one multiplier body executed twice (11.5 KB of code).

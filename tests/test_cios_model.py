@@ -113,3 +113,30 @@ def test_wide_square(curve):
     for a in _operands(m, rng, 2 * m.p):          # the Montgomery square: operands below 2p give T < 4 p^2 < pR
         r = m.redc(m.sqrpre(m.limbs(a)))
         assert r < 2 * m.p and r % m.p == a * a * ri % m.p
+
+
+@pytest.mark.parametrize("curve", ["bls12_381", "bn254"])
+def test_fused_dot2_with_unreduced_operands(curve):
+    """engine A of csrc/tower.cuh: (re, im) = (xa ya + xb (2p - yb), xa yb + xb ya) through cios::dot2_rr.  The multiplicand
+    side is always an unreduced sum (< 2p); on BLS12-381 (PSB_LAZY_Y) the multiplier side is too, so the accumulated pair of
+    products reaches 8 p^2: the rows must not overflow their window and the result must stay below 2p, so that the single
+    conditional subtraction canonicalises it ((8 p^2 + R p) / R < 1.82 p needs 8 p < R: true for 381 bits in 384, false for
+    BN254, whose multiplier side therefore stays canonical)."""
+    m = gen_cios.Model(curve)
+    rng = random.Random(6)
+    ri = pow(m.R, -1, m.p)
+    lazy_y = curve == "bls12_381"
+    assert (8 * m.p < m.R) == lazy_y
+    xb, yb = 2 * m.p, (2 * m.p if lazy_y else m.p)
+    xs = [xb - 1, xb - 2, m.p, 1, 0] + [rng.randrange(xb) for _ in range(12)]
+    ys = [yb - 1, yb - 2, m.p - 1, 1, 0] + [rng.randrange(yb) for _ in range(12)]
+    worst = 0
+    for xa in xs:
+        for xbv in xs[::2]:
+            for ya in ys[::2]:
+                for ybv in ys[::3]:
+                    t = m.dot2(m.limbs(xa), m.limbs(ya), m.limbs(xbv), m.limbs(ybv))
+                    assert t < 2 * m.p, (hex(xa), hex(ya), hex(xbv), hex(ybv))
+                    assert t % m.p == (xa * ya + xbv * ybv) * ri % m.p
+                    worst = max(worst, t)
+    assert worst >= m.p          # the top of the range is exercised

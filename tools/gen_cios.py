@@ -279,6 +279,18 @@ class Model:
                 self.mac_shift(X, Y, a, b[i]); self.reduce(X, Y)
         return self.finish_nored(Y, X)
 
+    def dot2(self, a, b, c, d):
+        """cios::dot2_rr -- (a b + c d) / R, one reduction per row; returns the UNCANONICALISED sum"""
+        n = self.n
+        X, Y = [0] * n, [0] * n
+        self.first(X, Y, a, b[0]); self.mac(X, Y, c, d[0]); self.reduce(X, Y)
+        for i in range(1, n):
+            if i & 1:
+                self.mac_shift(Y, X, a, b[i]); self.mac(Y, X, c, d[i]); self.reduce(Y, X)
+            else:
+                self.mac_shift(X, Y, a, b[i]); self.mac(X, Y, c, d[i]); self.reduce(X, Y)
+        return self.finish_nored(Y, X)
+
     def mulpre(self, a, b):
         """cios::mulpre_rr -- the 2n-limb product, low limbs peeled off row by row"""
         n = self.n
