@@ -41,6 +41,33 @@ constexpr int kPairBlock = PSB_PAIR_BLOCK;
 #define PSB_PROTO_BOUNDS __launch_bounds__(kBlock, PSB_PROTO_MINB)
 #endif
 
+// ---- steering ptxas's pipe balancer ---------------------------------------------------------------------------------
+// ptxas balances the integer-add (ALU) and multiply (FMA) pipes from the STATIC instruction counts of a whole kernel: in a kernel
+// with much additive glue it rewrites carry absorptions and register moves INSIDE the multiplier rows as IMAD.X / IMAD.MOV
+// (25 + 13 per engine pass in k_verify_miller), i.e. it puts them on the one pipe that is saturated at run time -- the static
+// count cannot know that the 11 KB multiplier body executes 2 800 times per lane and the glue once.  A block of plain IMADs
+// that never executes (its condition is a lane count no batch can have) tips the static balance: with it the same rows come
+// out with IADD3.X / MOV only (checked with cuobjdump: tools/sass_regions.py; the engine compiled on its own gets the same
+// code).  Cold code at the end of the kernel: no instruction-cache footprint on the hot path.
+#ifndef PSB_FMA_BALLAST
+#define PSB_FMA_BALLAST 3000
+#endif
+template <int COUNT>
+__device__ __forceinline__ void ptxas_fma_ballast(bool never, void* sink) {
+#if PSB_FMA_BALLAST > 0
+  if (never) {
+    uint32_t u = threadIdx.x;
+    const uint32_t v = blockIdx.x;
+#pragma unroll
+    for (int i = 0; i < COUNT; i++) asm volatile("mad.lo.u32 %0, %0, %1, %1;" : "+r"(u) : "r"(v));
+    *reinterpret_cast<volatile uint32_t*>(sink) = u;
+  }
+#else
+  (void)never; (void)sink;
+#endif
+}
+#define PSB_BALLAST(N, sink) ptxas_fma_ballast<PSB_FMA_BALLAST>((N) == ~(size_t)0, (void*)(sink))
+
 // ---- parity probe ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_test_op(int op, size_t n, int s0, int s1, int s2, int s3,
                                                     const uint32_t* a, const uint32_t* b, const uint32_t* c,
@@ -322,6 +349,7 @@ __global__ void PSB_PAIR_BOUNDS k_verify_msm(size_t N, size_t base, int n, int w
     pt_fixed_mul_acc(acc, tbl + (size_t)i * per_base, k, w);
   }
   Kout[lane] = acc;
+  PSB_BALLAST(N, Kout);
 }
 
 // phase 2: f = ML(sig1, K) * ML(-sig2, gg)  (one multi-Miller loop per lane)
@@ -344,6 +372,7 @@ __global__ void PSB_PAIR_BOUNDS k_verify_miller(size_t N, size_t base, const G1J
   Fp12 f;
   miller_loop2(f, x1, y1, q, x2, y2, lines, true, true);
   if (live) fout[lane] = f;
+  PSB_BALLAST(N, fout);
 }
 
 // phase 3: final exponentiation, verdict = (sig1 != 0) && (f^e == 1), optional GT
@@ -361,6 +390,7 @@ __global__ void PSB_PAIR_BOUNDS k_verify_final(size_t N, size_t base, const G1J*
   const bool pre_ok = pre ? pre[lane] != 0 : true;
   verdict[lane] = (pre_ok && !s1zero && fp12_is_one(e)) ? 1 : 0;
   if (gt) gt[lane] = e;
+  PSB_BALLAST(N, verdict);
 }
 
 // plain pairing e(P, Q) per lane (no fixed argument)
@@ -376,6 +406,7 @@ __global__ void PSB_PAIR_BOUNDS k_pairing_miller(size_t N, size_t base, const G1
   Fp12 f;
   miller_loop2(f, x1, y1, q, zero, zero, nullptr, false, true);
   if (live) fout[lane] = f;
+  PSB_BALLAST(N, fout);
 }
 __global__ void PSB_PAIR_BOUNDS k_final_exp(size_t N, size_t base, const Fp12* fin, Fp12* out) {
   const size_t lane0 = base + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -384,6 +415,7 @@ __global__ void PSB_PAIR_BOUNDS k_final_exp(size_t N, size_t base, const Fp12* f
   Fp12 f = fin[lane], e;
   final_exp(e, f, true);
   if (live) out[lane] = e;
+  PSB_BALLAST(N, out);
 }
 
 
@@ -406,6 +438,7 @@ __global__ void PSB_PROTO_BOUNDS k_randomize(size_t N, const G1J* sig1, const G1
     g1_serialize_norm(ser + lane * 2 * kFpBytes, ra);
     g1_serialize_norm(ser + lane * 2 * kFpBytes + kFpBytes, rb);
   }
+  PSB_BALLAST(N, ser);
 }
 
 // out[j] = k[j] * P[j or 0], normalised (generic batched G1::mul, used to synthesise workloads)
@@ -419,6 +452,7 @@ __global__ void PSB_PROTO_BOUNDS k_g1_mul(size_t N, const G1J* P, int p_stride, 
   pt_mul(r, a, kn.v);
   pt_normalize(n, r);
   out[lane] = n;
+  PSB_BALLAST(N, out);
 }
 
 // ---- batched G1::deserialize / G2::deserialize (point decompression) ----------------------
@@ -474,6 +508,7 @@ __global__ void PSB_PROTO_BOUNDS k_provide_id(size_t N, int n, int w, const G1A*
     g1_serialize_norm(ser + lane * 2 * kFpBytes, s1);
     g1_serialize_norm(ser + lane * 2 * kFpBytes + kFpBytes, s2);
   }
+  PSB_BALLAST(N, ser);
 }
 
 // ---- PSSigner::sign_commitment / sign_hybrid (src/ps-signer.cc:112-146), u host-supplied ------------------------
@@ -490,6 +525,7 @@ __global__ void PSB_PROTO_BOUNDS k_sign(size_t N, int na, int w, const G1A* tblG
     g1_serialize_norm(ser + lane * 2 * kFpBytes, s1);
     g1_serialize_norm(ser + lane * 2 * kFpBytes + kFpBytes, s2);
   }
+  PSB_BALLAST(N, ser);
 }
 
 // ---- PSVerifier::el_passo_verify_id (src/ps-verifier.cc:37-212): NIZK steps; the pairing check reuses
@@ -506,6 +542,7 @@ __global__ void PSB_PROTO_BOUNDS k_vid_g2(size_t N, int n, int w, const G2A* tbl
   Vk[lane] = vk;
   K[lane] = kk;
   ok[lane] = (r && lg.pre_ok(lane)) ? 1 : 0;
+  PSB_BALLAST(N, ok);
 }
 __global__ void PSB_PROTO_BOUNDS k_vid_g1(size_t N, int wb, const G1A* tblB, const G1J* phi, const G1J* E1,
                                                     const G1J* E2, const Fr* c, const Fr* rs, LaneGeom lg, int with_id,
@@ -517,6 +554,7 @@ __global__ void PSB_PROTO_BOUNDS k_vid_g1(size_t N, int wb, const G1A* tblB, con
   verify_id_g1_lane(tb, tblB, phi[lane], with_id ? E1 + lane : nullptr, with_id ? E2 + lane : nullptr, c + lane,
                     rs + lane * lg.rs_stride, lg.count(lane), with_id, a, b, d);
   V[3 * lane] = a; V[3 * lane + 1] = b; V[3 * lane + 2] = d;
+  PSB_BALLAST(N, V);
 }
 __global__ void PSB_PROTO_BOUNDS k_vid_hash(size_t N, const G2J* k, const G1J* phi, const G1J* E1, const G1J* E2,
                                                       const G2J* Vk, const G1J* V, int with_id, const Fr* c,
@@ -622,6 +660,7 @@ __global__ void PSB_PROTO_BOUNDS k_request_id(size_t N, int n, int w, const G1A*
                   (size_t)(ad_off[lane + 1] - ad_off[lane]), rnd + lane * (h + 2), a, cc, rs + lane * (h + 1));
   A[lane] = a;
   c[lane] = cc;
+  PSB_BALLAST(N, rs);
 }
 __global__ void PSB_PROTO_BOUNDS k_unblind(size_t N, const G1J* sig1, const G1J* sig2, const Fr* t1, G1J* out2) {
   const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -629,6 +668,7 @@ __global__ void PSB_PROTO_BOUNDS k_unblind(size_t N, const G1J* sig1, const G1J*
   G1J r;
   unblind_lane(r, sig1[lane], sig2[lane], t1 + lane);
   out2[lane] = r;
+  PSB_BALLAST(N, out2);
 }
 __global__ void PSB_PROTO_BOUNDS k_pid_g2(size_t N, int n, int w, const G2A* tblYY, const G2A* tblAux, const G2J* XX,
                                                     const uint8_t* hide, int h, int with_id, const uint8_t* blob,
@@ -640,6 +680,7 @@ __global__ void PSB_PROTO_BOUNDS k_pid_g2(size_t N, int n, int w, const G2A* tbl
                    with_id, a, b);
   k[lane] = a;
   Vk[lane] = b;
+  PSB_BALLAST(N, Vk);
 }
 __global__ void PSB_PROTO_BOUNDS k_pid_g1(size_t N, int n, int wb, const G1A* tblB, const G1J* sig1, const G1J* sig2,
                                                     const uint8_t* blob, const uint64_t* off, const Fr* rnd, int h, int with_id,
@@ -652,6 +693,7 @@ __global__ void PSB_PROTO_BOUNDS k_pid_g1(size_t N, int n, int wb, const G1A* tb
   o_sig1[lane] = s1;
   o_sig2[lane] = s2;
   for (int i = 0; i < 6; i++) W[6 * lane + i] = w6[i];
+  PSB_BALLAST(N, W);
 }
 __global__ void PSB_PROTO_BOUNDS k_pid_hash(size_t N, int n, const uint8_t* hide, int h, int with_id, const uint8_t* blob,
                                                       const uint64_t* off, const uint8_t* ad_blob, const uint64_t* ad_off,
