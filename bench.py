@@ -678,7 +678,8 @@ def main():
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u64-limbs (mcl, Xbyak JIT=%d)" % int(ref.jit_enabled()), "data": "synthetic",
-                "config": {"workload": workload, "reference": "PSVerifier::verify via mcl (oracle/_ref/libpsref.so)"},
+                "config": {"workload": workload},
+                "reference_path": "PSVerifier::verify via mcl (oracle/_ref/libpsref.so), the unmodified reference compiled by oracle/Makefile",
                 "cpu_baseline": {"value": val, "unit": "verifications/s", "cores": threads, "kind": "reference",
                                  "sample": f"{sample} lanes per step"},
                 "e2e": {"value": val, "unit": "verifications/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
