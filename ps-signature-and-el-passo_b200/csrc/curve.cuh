@@ -465,4 +465,102 @@ PSB_HD PSB_INL void pt_fixed_mul_acc(Jac<F>& acc, const Aff<F>* tbl, const uint3
   }
 }
 
+// ---- fixed-base sums with batched affine additions ----------------------------------------------------------
+// A multi-scalar fixed-base sum is a sum of TABLE ENTRIES (affine points), n * nwin of them per lane.  Adding two affine
+// points costs 1 inversion + 2M + 1S; with Montgomery's trick the inversions of a whole batch of independent pairs become ONE
+// inversion plus 3M per pair, so a pair sum is 5M + 1S against 7M + 4S for pushing one of the two entries through the mixed
+// Jacobian addition.  AffBatch pairs the entries as they come (slot 2i with slot 2i+1), forms the pair sums in affine
+// coordinates and feeds those to the Jacobian accumulator: per two entries 5M + 1S + (7M + 4S) + 1/G of an inversion instead
+// of 2 (7M + 4S).  Every lane pushes the same number of slots (a zero digit pushes kAffNone), so the flushes are warp-uniform.
+// Pairs the affine formula cannot take (an absent entry, P = +-Q) go through pt_madd entry by entry: same group element.
+// Per-lane state: 2G slot descriptors (table index | sign << 31) and G prefix products.
+constexpr int kAffG = 64;                     // pairs per inversion at most (the exception mask is one 64-bit word)
+constexpr uint32_t kAffNone = 0xFFFFFFFFu;
+constexpr uint32_t kAffIdx = 0x7FFFFFFFu;
+template <class F>
+struct AffBatch {
+  uint32_t desc[2 * kAffG];
+  F pre[kAffG];
+  int cnt, cap;                               // slots filled / slots per flush (even, <= 2 kAffG)
+};
+// slots per flush for `total` slots: as few flushes as kAffG allows, of equal size
+PSB_HD PSB_INL int aff_batch_cap(int total) {
+  const int pairs = total / 2;
+  if (pairs <= 0) return 2;
+  const int nb = (pairs + kAffG - 1) / kAffG;
+  return 2 * ((pairs + nb - 1) / nb);
+}
+template <class F> PSB_HD PSB_INL void aff_init(AffBatch<F>& b, int total_slots) { b.cnt = 0; b.cap = aff_batch_cap(total_slots); }
+template <class F> PSB_HD PSB_INL void aff_fetch(Aff<F>& e, const Aff<F>* tbl, uint32_t d) {
+  e = tbl[d & kAffIdx];
+  if (d >> 31) f_neg(e.y, e.y);
+}
+// below this many pairs one inversion (~110 Fp products of time) is not repaid by 4 Fp2 products + 3 squarings per pair
+constexpr int kAffMinPairs = 10;
+
+template <class F>
+PSB_HD PSB_NOINL void aff_flush(Jac<F>& acc, AffBatch<F>& b, const Aff<F>* tbl) {
+  const int np = b.cnt >> 1;
+  Aff<F> P, Q, S;
+  if (np >= kAffMinPairs) {
+    uint64_t exc = 0;
+    F run, d;
+    for (int i = 0; i < np; i++) {
+      const uint32_t da = b.desc[2 * i], db = b.desc[2 * i + 1];
+      bool bad = da == kAffNone || db == kAffNone;
+      if (!bad) {
+        f_sub(d, tbl[db & kAffIdx].x, tbl[da & kAffIdx].x);
+        bad = f_is_zero(d);
+      }
+      if (bad) { f_set_one(d); exc |= 1ull << i; }
+      if (i == 0) run = d; else f_mul(run, run, d);
+      b.pre[i] = run;
+    }
+    f_inv(run, run);                          // 1 / (d_0 ... d_{np-1})
+    for (int i = np - 1; i >= 0; i--) {
+      const uint32_t da = b.desc[2 * i], db = b.desc[2 * i + 1];
+      if ((exc >> i) & 1ull) {                // d_i = 1: `run` is already 1 / (d_0 ... d_{i-1})
+        if (da != kAffNone) { aff_fetch(P, tbl, da); pt_madd(acc, acc, P); }
+        if (db != kAffNone) { aff_fetch(Q, tbl, db); pt_madd(acc, acc, Q); }
+        continue;
+      }
+      aff_fetch(P, tbl, da);
+      aff_fetch(Q, tbl, db);
+      F li, lam, t;
+      f_sub(d, Q.x, P.x);
+      if (i) f_mul(li, run, b.pre[i - 1]); else li = run;     // 1 / d_i
+      f_mul(run, run, d);
+      f_sub(t, Q.y, P.y); f_mul(lam, t, li);
+      f_sqr(t, lam); f_sub(t, t, P.x); f_sub(S.x, t, Q.x);
+      f_sub(t, P.x, S.x); f_mul(t, lam, t); f_sub(S.y, t, P.y);
+      pt_madd(acc, acc, S);
+    }
+  } else {
+    for (int i = 0; i < 2 * np; i++)
+      if (b.desc[i] != kAffNone) { aff_fetch(P, tbl, b.desc[i]); pt_madd(acc, acc, P); }
+  }
+  if (b.cnt & 1) {
+    const uint32_t dl = b.desc[b.cnt - 1];
+    if (dl != kAffNone) { aff_fetch(P, tbl, dl); pt_madd(acc, acc, P); }
+  }
+  b.cnt = 0;
+}
+
+// push the nwin table entries of k * B (the entries pt_fixed_mul_acc would add): tbl_first = index of the first entry of
+// this base in the table the batch is flushed against
+template <class F>
+PSB_HD PSB_INL void aff_push_fixed_mul(Jac<F>& acc, AffBatch<F>& b, const Aff<F>* tbl, size_t tbl_first, const uint32_t* k, int w) {
+  const int nwin = fixed_nwin(w);
+  const uint32_t half = 1u << (w - 1);
+  uint32_t carry = 0;
+  for (int j = 0; j < nwin; j++) {
+    uint32_t d = scalar_bits(k, j * w, w) + carry;
+    carry = 0;
+    uint32_t neg = 0;
+    if (d > half) { d = (1u << w) - d; neg = 1u << 31; carry = 1; }
+    b.desc[b.cnt++] = d ? ((uint32_t)(tbl_first + (size_t)j * half + (d - 1)) | neg) : kAffNone;
+    if (b.cnt == b.cap) aff_flush(acc, b, tbl);
+  }
+}
+
 }  // namespace psb

@@ -330,11 +330,13 @@ __global__ void k_fixed_lines(const G2J* gg /*normalised*/, FixedLine* lines) {
 // phase 1: scalars m_i (SHA-256 of the attribute strings, or the caller's Fr) and
 //          K = XX + sum_i m_i YY_i from the per-key window tables.
 __global__ void PSB_PAIR_BOUNDS k_verify_msm(size_t N, size_t base, int n, int w, const uint8_t* blob, const uint64_t* off,
-                                                        const Fr* m_mont, const G2J* XX, const G2A* tbl, G2J* Kout) {
+                                                        const Fr* m_mont, const G2J* XX, const G2A* tbl, G2J* Kout, int affine) {
   const size_t lane = base + (size_t)blockIdx.x * blockDim.x + threadIdx.x;    // lanes [base, N): psb_api.cu, for_waves
   if (lane >= N) return;
   const size_t per_base = (size_t)fixed_nwin(w) << (w - 1);
   G2J acc = *XX;
+  AffBatch<Fp2> batch;
+  if (affine) aff_init(batch, n * fixed_nwin(w));
   for (int i = 0; i < n; i++) {
     uint32_t k[8];
     if (blob) {
@@ -346,8 +348,10 @@ __global__ void PSB_PAIR_BOUNDS k_verify_msm(size_t N, size_t base, int n, int w
       fr_from_mont(tn, t);
       for (int j = 0; j < 8; j++) k[j] = tn.v[j];
     }
-    pt_fixed_mul_acc(acc, tbl + (size_t)i * per_base, k, w);
+    if (affine) aff_push_fixed_mul(acc, batch, tbl, (size_t)i * per_base, k, w);   // pair sums in affine coordinates (curve.cuh)
+    else pt_fixed_mul_acc(acc, tbl + (size_t)i * per_base, k, w);
   }
+  if (affine) aff_flush(acc, batch, tbl);
   Kout[lane] = acc;
   PSB_BALLAST(N, Kout);
 }

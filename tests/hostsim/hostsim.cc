@@ -45,6 +45,28 @@ void host_table(std::vector<Aff<F>>& out, const Jac<F>& base, int w) {
     for (int t = 0; t < w; t++) pt_dbl(cur, cur);
   }
 }
+// fixed-base sum probe: acc0 + sum_i k_i B_i over host-built tables, once through the plain mixed-addition chain
+// (pt_fixed_mul_acc) and once through the batched affine pair additions (AffBatch, curve.cuh) -- both normalised
+template <class F>
+static void fixed_msm(int w, int nbases, const uint32_t* bases, const uint32_t* k_mont, const uint32_t* acc0, uint32_t* out_plain,
+                      uint32_t* out_aff) {
+  constexpr int U = sizeof(Jac<F>) / 4;
+  std::vector<Aff<F>> t;
+  for (int i = 0; i < nbases; i++) { Jac<F> b; ld(b, bases + U * i); host_table(t, b, w); }
+  const size_t pb = (size_t)fixed_nwin(w) << (w - 1);
+  Jac<F> a, c, n;
+  ld(a, acc0); c = a;
+  AffBatch<F> batch;
+  aff_init(batch, nbases * fixed_nwin(w));
+  for (int i = 0; i < nbases; i++) {
+    uint32_t k[8]; Fr km; ld(km, k_mont + 8 * i); fr_load_normal(k, &km);
+    pt_fixed_mul_acc(a, t.data() + i * pb, k, w);
+    aff_push_fixed_mul(c, batch, t.data(), i * pb, k, w);
+  }
+  aff_flush(c, batch, t.data());
+  pt_normalize(n, a); st(out_plain, n);
+  pt_normalize(n, c); st(out_aff, n);
+}
 }  // namespace
 
 extern "C" {
@@ -56,6 +78,12 @@ void hostsim_fixed_mul_g1(int w, const uint32_t* B, const uint32_t* k_mont, uint
   G1J acc; pt_set_zero(acc);
   pt_fixed_mul_acc(acc, t.data(), k, w);
   G1J n; pt_normalize(n, acc); st(out, n);
+}
+
+void hostsim_fixed_msm(int is_g2, int w, int nbases, const uint32_t* bases, const uint32_t* k_mont, const uint32_t* acc0,
+                       uint32_t* out_plain, uint32_t* out_aff) {
+  if (is_g2) fixed_msm<Fp2>(w, nbases, bases, k_mont, acc0, out_plain, out_aff);
+  else fixed_msm<Fp>(w, nbases, bases, k_mont, acc0, out_plain, out_aff);
 }
 
 void hostsim_provide_id(int n, int w, const uint32_t* g, const uint32_t* X, const uint32_t* Y, size_t N,

@@ -77,3 +77,47 @@ def test_point_decompression_lanes(hostsim, ref, g2):
         assert r == okv[j], j
         if okv[j]:
             assert np.array_equal(out, want[j]), j
+
+
+@pytest.mark.parametrize("is_g2", [0, 1])
+def test_fixed_base_sum_batched_affine(hostsim, ref, is_g2):
+    """Fixed-base sums through the batched affine pair additions (AffBatch in csrc/curve.cuh, the path k_verify_msm runs)
+    against the plain mixed-addition chain AND against the reference's G::mul / add: random scalars, absent entries (zero
+    digits), a single small batch (below the inversion's break-even), and the two pairs the affine formula cannot take --
+    P = Q and P = -Q -- built by giving base 1 = 2^252 base 0 (w = 7: 37 windows, so the top window of base 0 pairs with
+    window 0 of base 1) and base 3 = -2^252 base 2."""
+    from tests.conftest import GROUP_R
+    W = G2W if is_g2 else G1W
+    mul, op = (ref.g2_mul, ref.g2_op) if is_g2 else (ref.g1_mul, ref.g1_op)
+    rng = np.random.default_rng(5 + is_g2)
+    B0 = ref.hash_to_g2(b"base-0") if is_g2 else ref.hash_to_g1(b"base-0")
+    B2 = ref.hash_to_g2(b"base-2") if is_g2 else ref.hash_to_g1(b"base-2")
+    shift = ref.fr_from_ints([(1 << 252) % GROUP_R])
+    B1 = mul(B0, shift)[0]
+    B3 = op(ref.G_NEG, mul(B2, shift))[0]
+    acc0 = mul(B2, ref.fr_from_ints([12345]))[0]
+
+    def run(w, bases, ks):
+        bases = op(ref.G_NORM, np.stack(bases))
+        km = ref.fr_from_ints(ks)
+        o1 = np.zeros(W, dtype=np.uint64)
+        o2 = np.zeros(W, dtype=np.uint64)
+        hostsim.hostsim_fixed_msm(C.c_int(is_g2), C.c_int(w), C.c_int(len(ks)), _p(bases), _p(km), _p(acc0), _p(o1), _p(o2))
+        exp = acc0.reshape(1, -1)
+        for b, k in zip(bases, km):
+            exp = op(ref.G_ADD, exp, mul(b, k.reshape(1, -1)))
+        exp = op(ref.G_NORM, exp)[0]
+        assert np.array_equal(o1, exp), ("plain", w)
+        assert np.array_equal(o2, exp), ("batched affine", w)
+
+    low = lambda: int.from_bytes(rng.bytes(12), "little")  # noqa: E731
+    top = 2 << 252
+    # P = Q at the seam of bases 0/1, P = -Q at the seam of bases 2/3 (sum = infinity), random scalars elsewhere
+    run(7, [B0, B1, B2, B3], [top + (low() << 7), 2 + (low() << 7), top + (low() << 7), 2 + (low() << 7)])
+    # zero digits: small scalars leave most windows empty; k = 0 leaves a whole base empty
+    run(5, [B0, B2, B1], [5, 0, (1 << 200) + 77])
+    # random full-size scalars, two flushes (3 x 64 slots = 96 pairs -> 2 batches of 48)
+    run(4, [B0, B2, B3], [int.from_bytes(rng.bytes(40), "little") % GROUP_R for _ in range(3)])
+    # one short batch (8 pairs: plain additions), and an even slot count in one flush (w = 5: 52 windows)
+    run(16, [B0], [int.from_bytes(rng.bytes(40), "little") % GROUP_R])
+    run(5, [B2], [int.from_bytes(rng.bytes(40), "little") % GROUP_R])
