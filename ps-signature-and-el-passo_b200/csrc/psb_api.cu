@@ -294,7 +294,12 @@ int psb_init(int curve, const int* devices, int ndev) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, o));
     if (prop.major < 10) return fail(PSB_ERR_UNSUPPORTED, "kernels are built for sm_100a only");
-    if (g_devs.empty()) g_sms = prop.multiProcessorCount;
+    if (g_devs.empty()) {
+      g_sms = prop.multiProcessorCount;
+      // probe only (tools/probe_l2_fit.py): shape the launches as if the device had fewer SMs, so that a batch of
+      // PSB_SMS x 512 lanes runs one full block on that many SMs and its thread-local state fits the L2
+      if (const char* e = getenv("PSB_SMS")) { const int v = atoi(e); if (v > 0 && v <= g_sms) g_sms = v; }
+    }
     Dev* d = new Dev();
     d->ordinal = o;
     g_devs.push_back(d);                 // owned by the list from here on: the guard frees it if a later step fails
