@@ -473,14 +473,18 @@ PSB_HD PSB_INL void pt_fixed_mul_acc(Jac<F>& acc, const Aff<F>* tbl, const uint3
 // coordinates and feeds those to the Jacobian accumulator: per two entries 5M + 1S + (7M + 4S) + 1/G of an inversion instead
 // of 2 (7M + 4S).  Every lane pushes the same number of slots (a zero digit pushes kAffNone), so the flushes are warp-uniform.
 // Pairs the affine formula cannot take (an absent entry, P = +-Q) go through pt_madd entry by entry: same group element.
-// Per-lane state: 2G slot descriptors (table index | sign << 31) and G prefix products.
+// Per-lane state: 2G slot descriptors (29-bit table index | table id << 29 | sign << 31) and G prefix products; a batch
+// draws its entries from up to three tables (the per-key and per-batch tables of the EL PASSO kernels).
+// Measured on B200 (profiles/r2s_ab_msm_batched_affine.txt): k_verify_msm 76.4 -> 64.6 ms per 2^20 lanes at 5 attributes.
 constexpr int kAffG = 64;                     // pairs per inversion at most (the exception mask is one 64-bit word)
-constexpr uint32_t kAffNone = 0xFFFFFFFFu;
-constexpr uint32_t kAffIdx = 0x7FFFFFFFu;
+constexpr uint32_t kAffNone = 0xFFFFFFFFu;    // table id 3 is never used, so this is no entry
+constexpr uint32_t kAffIdx = 0x1FFFFFFFu;
+constexpr size_t kAffMaxEntries = (size_t)1 << 29;
 template <class F>
 struct AffBatch {
   uint32_t desc[2 * kAffG];
   F pre[kAffG];
+  const Aff<F>* tbl[3];
   int cnt, cap;                               // slots filled / slots per flush (even, <= 2 kAffG)
 };
 // slots per flush for `total` slots: as few flushes as kAffG allows, of equal size
@@ -490,16 +494,21 @@ PSB_HD PSB_INL int aff_batch_cap(int total) {
   const int nb = (pairs + kAffG - 1) / kAffG;
   return 2 * ((pairs + nb - 1) / nb);
 }
-template <class F> PSB_HD PSB_INL void aff_init(AffBatch<F>& b, int total_slots) { b.cnt = 0; b.cap = aff_batch_cap(total_slots); }
-template <class F> PSB_HD PSB_INL void aff_fetch(Aff<F>& e, const Aff<F>* tbl, uint32_t d) {
-  e = tbl[d & kAffIdx];
+template <class F>
+PSB_HD PSB_INL void aff_init(AffBatch<F>& b, int total_slots, const Aff<F>* t0, const Aff<F>* t1 = nullptr, const Aff<F>* t2 = nullptr) {
+  b.cnt = 0; b.cap = aff_batch_cap(total_slots);
+  b.tbl[0] = t0; b.tbl[1] = t1; b.tbl[2] = t2;
+}
+template <class F> PSB_HD PSB_INL const Aff<F>* aff_entry(const AffBatch<F>& b, uint32_t d) { return b.tbl[(d >> 29) & 3u] + (d & kAffIdx); }
+template <class F> PSB_HD PSB_INL void aff_fetch(Aff<F>& e, const AffBatch<F>& b, uint32_t d) {
+  e = *aff_entry(b, d);
   if (d >> 31) f_neg(e.y, e.y);
 }
 // below this many pairs one inversion (~110 Fp products of time) is not repaid by 4 Fp2 products + 3 squarings per pair
 constexpr int kAffMinPairs = 10;
 
 template <class F>
-PSB_HD PSB_NOINL void aff_flush(Jac<F>& acc, AffBatch<F>& b, const Aff<F>* tbl) {
+PSB_HD PSB_NOINL void aff_flush(Jac<F>& acc, AffBatch<F>& b) {
   const int np = b.cnt >> 1;
   Aff<F> P, Q, S;
   if (np >= kAffMinPairs) {
@@ -509,7 +518,7 @@ PSB_HD PSB_NOINL void aff_flush(Jac<F>& acc, AffBatch<F>& b, const Aff<F>* tbl) 
       const uint32_t da = b.desc[2 * i], db = b.desc[2 * i + 1];
       bool bad = da == kAffNone || db == kAffNone;
       if (!bad) {
-        f_sub(d, tbl[db & kAffIdx].x, tbl[da & kAffIdx].x);
+        f_sub(d, aff_entry(b, db)->x, aff_entry(b, da)->x);
         bad = f_is_zero(d);
       }
       if (bad) { f_set_one(d); exc |= 1ull << i; }
@@ -520,12 +529,12 @@ PSB_HD PSB_NOINL void aff_flush(Jac<F>& acc, AffBatch<F>& b, const Aff<F>* tbl) 
     for (int i = np - 1; i >= 0; i--) {
       const uint32_t da = b.desc[2 * i], db = b.desc[2 * i + 1];
       if ((exc >> i) & 1ull) {                // d_i = 1: `run` is already 1 / (d_0 ... d_{i-1})
-        if (da != kAffNone) { aff_fetch(P, tbl, da); pt_madd(acc, acc, P); }
-        if (db != kAffNone) { aff_fetch(Q, tbl, db); pt_madd(acc, acc, Q); }
+        if (da != kAffNone) { aff_fetch(P, b, da); pt_madd(acc, acc, P); }
+        if (db != kAffNone) { aff_fetch(Q, b, db); pt_madd(acc, acc, Q); }
         continue;
       }
-      aff_fetch(P, tbl, da);
-      aff_fetch(Q, tbl, db);
+      aff_fetch(P, b, da);
+      aff_fetch(Q, b, db);
       F li, lam, t;
       f_sub(d, Q.x, P.x);
       if (i) f_mul(li, run, b.pre[i - 1]); else li = run;     // 1 / d_i
@@ -537,29 +546,30 @@ PSB_HD PSB_NOINL void aff_flush(Jac<F>& acc, AffBatch<F>& b, const Aff<F>* tbl) 
     }
   } else {
     for (int i = 0; i < 2 * np; i++)
-      if (b.desc[i] != kAffNone) { aff_fetch(P, tbl, b.desc[i]); pt_madd(acc, acc, P); }
+      if (b.desc[i] != kAffNone) { aff_fetch(P, b, b.desc[i]); pt_madd(acc, acc, P); }
   }
   if (b.cnt & 1) {
     const uint32_t dl = b.desc[b.cnt - 1];
-    if (dl != kAffNone) { aff_fetch(P, tbl, dl); pt_madd(acc, acc, P); }
+    if (dl != kAffNone) { aff_fetch(P, b, dl); pt_madd(acc, acc, P); }
   }
   b.cnt = 0;
 }
 
-// push the nwin table entries of k * B (the entries pt_fixed_mul_acc would add): tbl_first = index of the first entry of
-// this base in the table the batch is flushed against
+// push the nwin table entries of k * B (the entries pt_fixed_mul_acc would add): `first` = index of the first entry of
+// this base in table `tid` of the batch
 template <class F>
-PSB_HD PSB_INL void aff_push_fixed_mul(Jac<F>& acc, AffBatch<F>& b, const Aff<F>* tbl, size_t tbl_first, const uint32_t* k, int w) {
+PSB_HD PSB_INL void aff_push_fixed_mul(Jac<F>& acc, AffBatch<F>& b, int tid, size_t first, const uint32_t* k, int w) {
   const int nwin = fixed_nwin(w);
   const uint32_t half = 1u << (w - 1);
+  const uint32_t tag = (uint32_t)tid << 29;
   uint32_t carry = 0;
   for (int j = 0; j < nwin; j++) {
     uint32_t d = scalar_bits(k, j * w, w) + carry;
     carry = 0;
     uint32_t neg = 0;
     if (d > half) { d = (1u << w) - d; neg = 1u << 31; carry = 1; }
-    b.desc[b.cnt++] = d ? ((uint32_t)(tbl_first + (size_t)j * half + (d - 1)) | neg) : kAffNone;
-    if (b.cnt == b.cap) aff_flush(acc, b, tbl);
+    b.desc[b.cnt++] = d ? ((uint32_t)(first + (size_t)j * half + (d - 1)) | tag | neg) : kAffNone;
+    if (b.cnt == b.cap) aff_flush(acc, b);
   }
 }
 

@@ -336,7 +336,7 @@ __global__ void PSB_PAIR_BOUNDS k_verify_msm(size_t N, size_t base, int n, int w
   const size_t per_base = (size_t)fixed_nwin(w) << (w - 1);
   G2J acc = *XX;
   AffBatch<Fp2> batch;
-  if (affine) aff_init(batch, n * fixed_nwin(w));
+  if (affine) aff_init(batch, n * fixed_nwin(w), tbl);
   for (int i = 0; i < n; i++) {
     uint32_t k[8];
     if (blob) {
@@ -348,10 +348,10 @@ __global__ void PSB_PAIR_BOUNDS k_verify_msm(size_t N, size_t base, int n, int w
       fr_from_mont(tn, t);
       for (int j = 0; j < 8; j++) k[j] = tn.v[j];
     }
-    if (affine) aff_push_fixed_mul(acc, batch, tbl, (size_t)i * per_base, k, w);   // pair sums in affine coordinates (curve.cuh)
+    if (affine) aff_push_fixed_mul(acc, batch, 0, (size_t)i * per_base, k, w);   // pair sums in affine coordinates (curve.cuh)
     else pt_fixed_mul_acc(acc, tbl + (size_t)i * per_base, k, w);
   }
-  if (affine) aff_flush(acc, batch, tbl);
+  if (affine) aff_flush(acc, batch);
   Kout[lane] = acc;
   PSB_BALLAST(N, Kout);
 }

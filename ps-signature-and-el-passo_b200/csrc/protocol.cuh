@@ -267,6 +267,8 @@ PSB_HD PSB_NOINL bool provide_id_lane(int n, TblGeom tg, const G1A* tblG1, const
   G1J V, Ap = A_in, A = A_in;
   fr_load_normal(cn, c_mont);
   pt_mul(V, A, cn);
+  // (G1 sums stay on the plain mixed-addition chain: batched affine pair additions, which pay in G2, measured 2.4 % SLOWER
+  // here -- an Fp product is too cheap against the inversion and the second table fetch, profiles/r2u_ab_affine_protocol.txt)
   if (ok) { fr_load_normal(k, rs); pt_fixed_mul_acc(V, tblG1, k, tg.w); }
   int j = 1;
   for (int i = 0; i < n; i++) {
@@ -341,27 +343,37 @@ PSB_HD PSB_NOINL bool verify_id_g2_lane(int n, TblGeom tg, const G2A* tblYY, con
   G2J kk = k_in;
   pt_mul(Vk, kk, k);
   K = kk;
+  // the table entries of V_k and of K are summed pairwise in affine coordinates (AffBatch, curve.cuh)
+  AffBatch<Fp2> bV, bK;
+  {
+    int hid = 0;
+    for (int i = 0; i < n; i++) hid += off[i + 1] == off[i];
+    aff_init(bV, (hid + 2) * fixed_nwin(tg.w), tblYY, tblAux);
+    aff_init(bK, (n - hid) * fixed_nwin(tg.w), tblYY);
+  }
   int cnt = 0;
   for (int i = 0; i < n; i++) {
     const uint64_t b = off[i], e = off[i + 1];
     if (e == b) {
-      if (cnt < per) { fr_load_normal(k, rs + cnt); pt_fixed_mul_acc(Vk, tblYY + (size_t)i * pb, k, tg.w); }
+      if (cnt < per) { fr_load_normal(k, rs + cnt); aff_push_fixed_mul(Vk, bV, 0, (size_t)i * pb, k, tg.w); }
       else ok = false;
       cnt++;
     } else {
       fr_set_hash_of(k, blob + b, (size_t)(e - b));
-      pt_fixed_mul_acc(K, tblYY + (size_t)i * pb, k, tg.w);
+      aff_push_fixed_mul(K, bK, 0, (size_t)i * pb, k, tg.w);
     }
   }
   if (ok) {
     fr_load_normal(k, rs + (with_id ? per - 2 : per - 1));
-    pt_fixed_mul_acc(Vk, tblAux, k, tg.w);
+    aff_push_fixed_mul(Vk, bV, 1, 0, k, tg.w);
   }
   Fr one, omc, cm = *c_mont;
   for (int i = 0; i < 8; i++) one.v[i] = PSB_K(FR_ONE)[i];
   fr_sub(omc, one, cm);
   fr_load_normal(k, &omc);
-  pt_fixed_mul_acc(Vk, tblAux + pb, k, tg.w);
+  aff_push_fixed_mul(Vk, bV, 1, pb, k, tg.w);
+  aff_flush(Vk, bV);
+  aff_flush(K, bK);
   return ok;
 }
 

@@ -99,19 +99,25 @@ PSB_HD PSB_NOINL void prove_id_g2_lane(int n, TblGeom tg, const G2A* tblYY, cons
   const Fr* rr = rnd + (with_id ? 3 : 2);
   uint32_t s[8];
   G2J K = XX, V = XX;
+  // the table entries of k and of V_k are summed pairwise in affine coordinates (AffBatch, curve.cuh)
+  AffBatch<Fp2> bK, bV;
+  aff_init(bK, (h + 1) * fixed_nwin(tg.w), tblYY, tblAux);
+  aff_init(bV, (h + 1) * fixed_nwin(tg.w), tblYY, tblAux);
   int j = 0;
   for (int i = 0; i < n; i++) {
     if (!hide[i]) continue;
     fr_set_hash_of(s, blob + off[i], (size_t)(off[i + 1] - off[i]));
-    pt_fixed_mul_acc(K, tblYY + (size_t)i * pb, s, tg.w);
+    aff_push_fixed_mul(K, bK, 0, (size_t)i * pb, s, tg.w);
     fr_load_normal(s, rr + j);
-    pt_fixed_mul_acc(V, tblYY + (size_t)i * pb, s, tg.w);
+    aff_push_fixed_mul(V, bV, 0, (size_t)i * pb, s, tg.w);
     j++;
   }
   fr_load_normal(s, rnd);          // t
-  pt_fixed_mul_acc(K, tblAux, s, tg.w);
+  aff_push_fixed_mul(K, bK, 1, 0, s, tg.w);
   fr_load_normal(s, rr + h);       // random2
-  pt_fixed_mul_acc(V, tblAux, s, tg.w);
+  aff_push_fixed_mul(V, bV, 1, 0, s, tg.w);
+  aff_flush(K, bK);
+  aff_flush(V, bV);
   k_out = K;
   Vk_out = V;
 }

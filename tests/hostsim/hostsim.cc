@@ -57,13 +57,13 @@ static void fixed_msm(int w, int nbases, const uint32_t* bases, const uint32_t* 
   Jac<F> a, c, n;
   ld(a, acc0); c = a;
   AffBatch<F> batch;
-  aff_init(batch, nbases * fixed_nwin(w));
+  aff_init(batch, nbases * fixed_nwin(w), t.data());
   for (int i = 0; i < nbases; i++) {
     uint32_t k[8]; Fr km; ld(km, k_mont + 8 * i); fr_load_normal(k, &km);
     pt_fixed_mul_acc(a, t.data() + i * pb, k, w);
-    aff_push_fixed_mul(c, batch, t.data(), i * pb, k, w);
+    aff_push_fixed_mul(c, batch, 0, i * pb, k, w);
   }
-  aff_flush(c, batch, t.data());
+  aff_flush(c, batch);
   pt_normalize(n, a); st(out_plain, n);
   pt_normalize(n, c); st(out_aff, n);
 }
