@@ -55,13 +55,91 @@ A_MILLER2 = 7673 - 680 - 39  # two-pairing Miller loop, FpMul-eq
 #           +36) instead of three more decompressions (-72): 5 * 36 = 180 fewer
 #           and raises to their value 105 = (2^3-1)(2^4-1) with 7 squarings + 2 products instead of 6 + 3: 5 * 36 = 180 fewer
 A_FINALEXP = 6100 + 480 - (476 - 8) - 1145 - 303 - 180 - 180
-A_MSM_PER_ADD = 29    # one mixed Jacobian+affine G2 addition
+A_MSM_PER_ADD = 29    # one mixed Jacobian+affine G2 addition (7 Fp2 products + 4 Fp2 squarings)
+A_MSM_PER_PAIR = 17   # one affine pair sum inside a batch: 5 Fp2 products + 1 Fp2 squaring (csrc/curve.cuh, AffBatch)
+A_MSM_PER_INV = 14    # the Fp2 inversion a batch shares: norm (2) + Bernstein-Yang divsteps (8) + R^3 product (1) + 2 products (+1)
+# EXECUTED wide MACs per lane, counted (not derived): tests/hostsim builds the engine's own headers for the host with call
+# counters on fp_mul / fp_sqr / fp_dot2 / fp_inv, and on the device each of those calls is exactly one cios::mul (2 N^2 + N
+# = 300 wide MACs), cios::sqr (234), cios::dot2 (3 N^2 + N = 444) or one divstep inversion (30 batches x 78).  Pinned by
+# tests/test_hostsim.py::test_executed_mac_counts.  (mul, sqr, dot2, inv) per lane, BLS12-381:
+EXEC_MAC32 = (300, 234, 444, 2340)
+EXEC_OPS_MILLER = (1322, 0, 4996, 0)
+EXEC_OPS_FINAL = (4182, 0, 1296, 6)
+MSM_AFFINE_LEVELS = 2   # psb_api.cu default (PSB_MSM_AFFINE): table entries summed pairwise in affine coordinates, twice
+K_AFF_G, K_AFF_L2, K_AFF_MIN_PAIRS = 64, 64, 10   # csrc/curve.cuh
+
+
+def msm_ops(n_attrs: int, window_bits: int, levels: int = MSM_AFFINE_LEVELS):
+    """Work of K = XX + sum m_i YY_i for one lane with no zero digit, mirroring aff_push_fixed_mul / aff_flush / aff_flush_l2
+    (csrc/curve.cuh): returns (FpMul-eq in SURVEY 8d's accounting, (mul, sqr, dot2, inv) executed Fp-level calls)."""
+    nwin = (256 + window_bits - 1) // window_bits
+    E = n_attrs * nwin
+    st = {"pairs": 0, "edge": 0, "inv": 0, "madd": 0}
+
+    def batch(np_):            # one batch of np_ pairs: prefix products, one inversion, np_ pair sums
+        st["pairs"] += np_
+        st["edge"] += 1        # the first pair of a batch has no prefix product and no 1/d product
+        st["inv"] += 1
+
+    l2 = {"cnt": 0}
+
+    def flush_l2():
+        np_ = l2["cnt"] // 2
+        if np_ >= K_AFF_MIN_PAIRS:
+            batch(np_)
+            st["madd"] += np_
+        else:
+            st["madd"] += 2 * np_
+        st["madd"] += l2["cnt"] & 1
+        l2["cnt"] = 0
+
+    def flush_l1(cnt, use_l2):
+        np_ = cnt // 2
+        if np_ >= K_AFF_MIN_PAIRS:
+            batch(np_)
+            if use_l2:
+                for _ in range(np_):
+                    l2["cnt"] += 1
+                    if l2["cnt"] == K_AFF_L2:
+                        flush_l2()
+            else:
+                st["madd"] += np_
+        else:
+            st["madd"] += 2 * np_
+        st["madd"] += cnt & 1
+
+    if levels == 0:
+        st["madd"] = E
+    else:
+        pairs = E // 2
+        nb = max(1, -(-pairs // K_AFF_G))
+        cap = 2 * (-(-pairs // nb)) if pairs else 2
+        use_l2 = levels > 1 and E >= 4 * K_AFF_MIN_PAIRS
+        cnt = 0
+        for _ in range(E):
+            cnt += 1
+            if cnt == cap:
+                flush_l1(cnt, use_l2)
+                cnt = 0
+        flush_l1(cnt, use_l2)
+        if use_l2:
+            flush_l2()
+    fpmul = st["madd"] * A_MSM_PER_ADD + st["pairs"] * A_MSM_PER_PAIR + st["inv"] * A_MSM_PER_INV
+    # executed calls: madd = 7 Fp2 products (2 dot2 each) + 4 Fp2 squarings (2 mul each); a pair = 5 Fp2 products + 1 squaring,
+    # less the 2 products the first pair of a batch skips; the shared Fp2 inversion = 1 dot2 + 1 inv (+ its R^3 product) + 2 mul
+    mul = st["madd"] * 8 + st["pairs"] * 2 + st["inv"] * 3
+    dot2 = st["madd"] * 14 + st["pairs"] * 10 - st["edge"] * 4 + st["inv"]
+    return fpmul, (mul, 0, dot2, st["inv"])
+
+
+def exec_mac32(ops) -> int:
+    return int(sum(c * m for c, m in zip(ops, EXEC_MAC32)))
 TRAFFIC_FILE = "r2h_traffic.json"   # latest committed ncu DRAM-traffic capture (profiles/)
 
 
 def a_verify_fpmul(n_attrs: int, window_bits: int) -> float:
     nwin = (256 + window_bits - 1) // window_bits
-    return A_MILLER2 + A_FINALEXP + n_attrs * nwin * A_MSM_PER_ADD
+    return A_MILLER2 + A_FINALEXP + msm_ops(n_attrs, window_bits)[0]
 
 
 def fr_hash(msg: bytes) -> int:
@@ -819,13 +897,20 @@ def main():
     e2e_val = job_throughput(N, world, e2e_steps, e2e_ms)
     names = ["k_verify_msm", "k_verify_miller", "k_verify_final"]
     nwin = (256 + args.window_bits - 1) // args.window_bits
-    work = [N_ATTRS * nwin * A_MSM_PER_ADD, A_MILLER2, A_FINALEXP]
+    msm_fpmul, msm_exec = msm_ops(N_ATTRS, args.window_bits)
+    work = [msm_fpmul, A_MILLER2, A_FINALEXP]
+    executed = [exec_mac32(msm_exec), exec_mac32(EXEC_OPS_MILLER), exec_mac32(EXEC_OPS_FINAL)]
     dom = int(np.argmax(phase))
     achieved = work[dom] * FPMUL_MAC32 * N / (phase[dom] * 1e-3)
     kernels = [{"name": names[i], "ms": float(phase[i]), "fpmul_eq_per_lane": work[i],
                 "achieved_tmac32": work[i] * FPMUL_MAC32 * N / (phase[i] * 1e-3) / 1e12,
                 "frac": work[i] * FPMUL_MAC32 * N / (phase[i] * 1e-3) / peak_mac,
-                "frac_of_carry_chain": work[i] * FPMUL_MAC32 * N / (phase[i] * 1e-3) / peak_chain} for i in range(3)]
+                "frac_of_carry_chain": work[i] * FPMUL_MAC32 * N / (phase[i] * 1e-3) / peak_chain,
+                # what the lane really executes (counted on the instrumented host build, see EXEC_OPS_*): the numerator above
+                # credits a lazily reduced Karatsuba tower (744 wide MACs per Fp2 product), the engine runs 888
+                "executed_mac32_per_lane": executed[i],
+                "executed_tmac32": executed[i] * N / (phase[i] * 1e-3) / 1e12,
+                "executed_frac": executed[i] * N / (phase[i] * 1e-3) / peak_mac} for i in range(3)]
     traffic, traffic_source = None, None
     try:  # DRAM bytes of that kernel: NOT measured in this run -- the committed ncu --set full capture, scaled per lane
         with open(os.path.join(ROOT, "profiles", TRAFFIC_FILE)) as f:

@@ -480,11 +480,24 @@ constexpr int kAffG = 64;                     // pairs per inversion at most (th
 constexpr uint32_t kAffNone = 0xFFFFFFFFu;    // table id 3 is never used, so this is no entry
 constexpr uint32_t kAffIdx = 0x1FFFFFFFu;
 constexpr size_t kAffMaxEntries = (size_t)1 << 29;
+// below this many pairs one inversion (~110 Fp products of time) is not repaid by 4 Fp2 products + 3 squarings per pair
+constexpr int kAffMinPairs = 10;
+// optional second level: the pair sums of a batch are themselves paired up (explicit points) before they reach the Jacobian
+// accumulator -- per FOUR entries 3 (5M + 1S) + (7M + 4S) instead of 2 (5M + 1S) + 2 (7M + 4S).  12 KB of lane state in G2.
+constexpr int kAffL2 = 64;                    // points per second-level flush
+template <class F>
+struct AffPts {
+  Aff<F> pts[kAffL2];
+  F pre[kAffL2 / 2];
+  uint64_t absent;                            // bit i: slot i holds no point
+  int cnt;
+};
 template <class F>
 struct AffBatch {
   uint32_t desc[2 * kAffG];
   F pre[kAffG];
   const Aff<F>* tbl[3];
+  AffPts<F>* l2;                              // nullptr: pair sums go straight to the accumulator
   int cnt, cap;                               // slots filled / slots per flush (even, <= 2 kAffG)
 };
 // slots per flush for `total` slots: as few flushes as kAffG allows, of equal size
@@ -495,20 +508,79 @@ PSB_HD PSB_INL int aff_batch_cap(int total) {
   return 2 * ((pairs + nb - 1) / nb);
 }
 template <class F>
-PSB_HD PSB_INL void aff_init(AffBatch<F>& b, int total_slots, const Aff<F>* t0, const Aff<F>* t1 = nullptr, const Aff<F>* t2 = nullptr) {
+PSB_HD PSB_INL void aff_init(AffBatch<F>& b, int total_slots, const Aff<F>* t0, const Aff<F>* t1 = nullptr, const Aff<F>* t2 = nullptr,
+                             AffPts<F>* l2 = nullptr) {
   b.cnt = 0; b.cap = aff_batch_cap(total_slots);
   b.tbl[0] = t0; b.tbl[1] = t1; b.tbl[2] = t2;
+  b.l2 = total_slots >= 4 * kAffMinPairs ? l2 : nullptr;     // fewer than kAffMinPairs second-level pairs: not worth it
+  if (b.l2) { b.l2->cnt = 0; b.l2->absent = 0; }
 }
 template <class F> PSB_HD PSB_INL const Aff<F>* aff_entry(const AffBatch<F>& b, uint32_t d) { return b.tbl[(d >> 29) & 3u] + (d & kAffIdx); }
 template <class F> PSB_HD PSB_INL void aff_fetch(Aff<F>& e, const AffBatch<F>& b, uint32_t d) {
   e = *aff_entry(b, d);
   if (d >> 31) f_neg(e.y, e.y);
 }
-// below this many pairs one inversion (~110 Fp products of time) is not repaid by 4 Fp2 products + 3 squarings per pair
-constexpr int kAffMinPairs = 10;
 
+// S = P + Q for affine P != +-Q, given li = 1 / (Q.x - P.x): 2M + 1S
 template <class F>
-PSB_HD PSB_NOINL void aff_flush(Jac<F>& acc, AffBatch<F>& b) {
+PSB_HD PSB_INL void aff_pair_sum(Aff<F>& S, const Aff<F>& P, const Aff<F>& Q, const F& li) {
+  F lam, t;
+  f_sub(t, Q.y, P.y); f_mul(lam, t, li);
+  f_sqr(t, lam); f_sub(t, t, P.x); f_sub(S.x, t, Q.x);
+  f_sub(t, P.x, S.x); f_mul(t, lam, t); f_sub(S.y, t, P.y);
+}
+
+// second level: flush the explicit points (pairs 2i / 2i+1) into the accumulator
+template <class F>
+PSB_HD PSB_NOINL void aff_flush_l2(Jac<F>& acc, AffPts<F>& l) {
+  const int np = l.cnt >> 1;
+  Aff<F> S;
+  if (np >= kAffMinPairs) {
+    uint64_t exc = 0;
+    F run, d;
+    for (int i = 0; i < np; i++) {
+      bool bad = ((l.absent >> (2 * i)) & 3ull) != 0;
+      if (!bad) {
+        f_sub(d, l.pts[2 * i + 1].x, l.pts[2 * i].x);
+        bad = f_is_zero(d);
+      }
+      if (bad) { f_set_one(d); exc |= 1ull << i; }
+      if (i == 0) run = d; else f_mul(run, run, d);
+      l.pre[i] = run;
+    }
+    f_inv(run, run);
+    for (int i = np - 1; i >= 0; i--) {
+      if ((exc >> i) & 1ull) {
+        if (!((l.absent >> (2 * i)) & 1ull)) pt_madd(acc, acc, l.pts[2 * i]);
+        if (!((l.absent >> (2 * i + 1)) & 1ull)) pt_madd(acc, acc, l.pts[2 * i + 1]);
+        continue;
+      }
+      F li;
+      f_sub(d, l.pts[2 * i + 1].x, l.pts[2 * i].x);
+      if (i) f_mul(li, run, l.pre[i - 1]); else li = run;
+      f_mul(run, run, d);
+      aff_pair_sum(S, l.pts[2 * i], l.pts[2 * i + 1], li);
+      pt_madd(acc, acc, S);
+    }
+  } else {
+    for (int i = 0; i < 2 * np; i++)
+      if (!((l.absent >> i) & 1ull)) pt_madd(acc, acc, l.pts[i]);
+  }
+  if ((l.cnt & 1) && !((l.absent >> (l.cnt - 1)) & 1ull)) pt_madd(acc, acc, l.pts[l.cnt - 1]);
+  l.cnt = 0;
+  l.absent = 0;
+}
+// hand one first-level result (or "nothing") to the second level; every lane hands over the same number of slots
+template <class F>
+PSB_HD PSB_INL void aff_l2_push(Jac<F>& acc, AffPts<F>& l, const Aff<F>* S) {
+  if (S) l.pts[l.cnt] = *S; else l.absent |= 1ull << l.cnt;
+  l.cnt++;
+  if (l.cnt == kAffL2) aff_flush_l2(acc, l);
+}
+
+// first level: flush the table entries named by the slot descriptors.  `last`: nothing follows, drain the second level too.
+template <class F>
+PSB_HD PSB_NOINL void aff_flush(Jac<F>& acc, AffBatch<F>& b, bool last = true) {
   const int np = b.cnt >> 1;
   Aff<F> P, Q, S;
   if (np >= kAffMinPairs) {
@@ -528,21 +600,30 @@ PSB_HD PSB_NOINL void aff_flush(Jac<F>& acc, AffBatch<F>& b) {
     f_inv(run, run);                          // 1 / (d_0 ... d_{np-1})
     for (int i = np - 1; i >= 0; i--) {
       const uint32_t da = b.desc[2 * i], db = b.desc[2 * i + 1];
+      bool have = true;                       // S holds the pair sum
       if ((exc >> i) & 1ull) {                // d_i = 1: `run` is already 1 / (d_0 ... d_{i-1})
-        if (da != kAffNone) { aff_fetch(P, b, da); pt_madd(acc, acc, P); }
-        if (db != kAffNone) { aff_fetch(Q, b, db); pt_madd(acc, acc, Q); }
-        continue;
+        const bool ha = da != kAffNone, hb = db != kAffNone;
+        if (ha && hb) {                       // P = +-Q: through the Jacobian formulas
+          aff_fetch(P, b, da); pt_madd(acc, acc, P);
+          aff_fetch(Q, b, db); pt_madd(acc, acc, Q);
+          have = false;
+        } else if (ha || hb) {                // one entry: it IS the pair sum
+          aff_fetch(S, b, ha ? da : db);
+        } else {
+          have = false;
+        }
+      } else {
+        aff_fetch(P, b, da);
+        aff_fetch(Q, b, db);
+        F li;
+        f_sub(d, Q.x, P.x);
+        if (i) f_mul(li, run, b.pre[i - 1]); else li = run;     // 1 / d_i
+        f_mul(run, run, d);
+        aff_pair_sum(S, P, Q, li);
       }
-      aff_fetch(P, b, da);
-      aff_fetch(Q, b, db);
-      F li, lam, t;
-      f_sub(d, Q.x, P.x);
-      if (i) f_mul(li, run, b.pre[i - 1]); else li = run;     // 1 / d_i
-      f_mul(run, run, d);
-      f_sub(t, Q.y, P.y); f_mul(lam, t, li);
-      f_sqr(t, lam); f_sub(t, t, P.x); f_sub(S.x, t, Q.x);
-      f_sub(t, P.x, S.x); f_mul(t, lam, t); f_sub(S.y, t, P.y);
-      pt_madd(acc, acc, S);
+      // (the hand-over sits after the branches: every lane reaches a second-level flush at the same point)
+      if (b.l2) aff_l2_push(acc, *b.l2, have ? &S : (const Aff<F>*)nullptr);
+      else if (have) pt_madd(acc, acc, S);
     }
   } else {
     for (int i = 0; i < 2 * np; i++)
@@ -553,6 +634,7 @@ PSB_HD PSB_NOINL void aff_flush(Jac<F>& acc, AffBatch<F>& b) {
     if (dl != kAffNone) { aff_fetch(P, b, dl); pt_madd(acc, acc, P); }
   }
   b.cnt = 0;
+  if (last && b.l2) aff_flush_l2(acc, *b.l2);
 }
 
 // push the nwin table entries of k * B (the entries pt_fixed_mul_acc would add): `first` = index of the first entry of
@@ -569,7 +651,7 @@ PSB_HD PSB_INL void aff_push_fixed_mul(Jac<F>& acc, AffBatch<F>& b, int tid, siz
     uint32_t neg = 0;
     if (d > half) { d = (1u << w) - d; neg = 1u << 31; carry = 1; }
     b.desc[b.cnt++] = d ? ((uint32_t)(first + (size_t)j * half + (d - 1)) | tag | neg) : kAffNone;
-    if (b.cnt == b.cap) aff_flush(acc, b);
+    if (b.cnt == b.cap) aff_flush(acc, b, false);
   }
 }
 

@@ -431,12 +431,25 @@ __device__ PSB_INL void fp_sqr(Fp& r, const Fp& a) { cios::mul(r.v, a.v, a.v); }
 #endif
 __device__ PSB_INL void fp_dot2(Fp& r, const Fp& a, const Fp& b, const Fp& c, const Fp& d) { cios::dot2(r.v, a.v, b.v, c.v, d.v); }
 #else
-// host build (tests/hostsim only): same values through the generic product-scanning code
-PSB_HD inline void fp_mul(Fp& r, const Fp& a, const Fp& b) { FpW t; fp_mulw(t, a, b); fp_redc(r, t); }
-PSB_HD inline void fp_sqr(Fp& r, const Fp& a) { FpW t; fp_sqrw(t, a); fp_redc(r, t); }
+// host build (tests/hostsim only): same values through the generic product-scanning code.
+// PSB_COUNT_OPS (tests/hostsim): count the calls -- on the device the same calls are one cios::mul (2 N^2 + N wide MACs),
+// cios::sqr (N (N + 1) / 2 + N^2 + N) and cios::dot2 (3 N^2 + N) each, so the counts of a host run are the MACs a lane executes
+// (bench.py `executed_mac32_per_lane`, pinned by tests/test_hostsim.py::test_executed_mac_counts)
+#ifdef PSB_COUNT_OPS
+namespace opcount { enum { MUL, SQR, DOT2, INV, N_ }; inline unsigned long long c[N_]; }
+#define PSB_OPCOUNT(k) (++::psb::opcount::c[::psb::opcount::k])
+#else
+#define PSB_OPCOUNT(k) ((void)0)
+#endif
+PSB_HD inline void fp_mul(Fp& r, const Fp& a, const Fp& b) { PSB_OPCOUNT(MUL); FpW t; fp_mulw(t, a, b); fp_redc(r, t); }
+PSB_HD inline void fp_sqr(Fp& r, const Fp& a) { PSB_OPCOUNT(SQR); FpW t; fp_sqrw(t, a); fp_redc(r, t); }
 PSB_HD inline void fp_dot2(Fp& r, const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+  PSB_OPCOUNT(DOT2);
   FpW t, u; fp_mulw(t, a, b); fp_mulw(u, c, d); fpw_add_nr(t, t, u); fp_redc(r, t);
 }
+#endif
+#ifndef PSB_OPCOUNT
+#define PSB_OPCOUNT(k) ((void)0)
 #endif
 // register-resident variants for the fused tower functions: operands are LOCAL Fp values that never touch memory
 // (loaded once with fp_ld, stored once with fp_st); everything inlines.
@@ -444,8 +457,9 @@ PSB_HD inline void fp_dot2(Fp& r, const Fp& a, const Fp& b, const Fp& c, const F
 __device__ PSB_INL void fp_mul_rr(Fp& r, const Fp& a, const Fp& b) { cios::mul_rr(r.v, a.v, b.v); }
 __device__ PSB_INL void fp_dot2_rr(Fp& r, const Fp& a, const Fp& b, const Fp& c, const Fp& d) { cios::dot2_rr(r.v, a.v, b.v, c.v, d.v); }
 #else
-PSB_HD PSB_INL void fp_mul_rr(Fp& r, const Fp& a, const Fp& b) { FpW t; mulw_n<PSB_NL>(t.v, a.v, b.v); redc_n<FpT>(r.v, t.v); }
+PSB_HD PSB_INL void fp_mul_rr(Fp& r, const Fp& a, const Fp& b) { PSB_OPCOUNT(MUL); FpW t; mulw_n<PSB_NL>(t.v, a.v, b.v); redc_n<FpT>(r.v, t.v); }
 PSB_HD PSB_INL void fp_dot2_rr(Fp& r, const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+  PSB_OPCOUNT(DOT2);
   FpW t, u; mulw_n<PSB_NL>(t.v, a.v, b.v); mulw_n<PSB_NL>(u.v, c.v, d.v); add_n<2 * PSB_NL>(t.v, t.v, u.v); redc_n<FpT>(r.v, t.v);
 }
 #endif

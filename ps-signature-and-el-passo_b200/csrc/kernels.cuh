@@ -336,7 +336,8 @@ __global__ void PSB_PAIR_BOUNDS k_verify_msm(size_t N, size_t base, int n, int w
   const size_t per_base = (size_t)fixed_nwin(w) << (w - 1);
   G2J acc = *XX;
   AffBatch<Fp2> batch;
-  if (affine) aff_init(batch, n * fixed_nwin(w), tbl);
+  AffPts<Fp2> level2;
+  if (affine) aff_init(batch, n * fixed_nwin(w), tbl, (const G2A*)nullptr, (const G2A*)nullptr, affine > 1 ? &level2 : nullptr);
   for (int i = 0; i < n; i++) {
     uint32_t k[8];
     if (blob) {

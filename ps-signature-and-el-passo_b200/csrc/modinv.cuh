@@ -153,6 +153,7 @@ PSB_HD PSB_NOINL void inv_plain(uint32_t* out, const uint32_t* x) {
 // a^-1 in Montgomery form: (aR)^-1 = a^-1 R^-1 as a plain integer, times R^3 through one Montgomery product
 PSB_HD PSB_INL void fp_inv_by(Fp& r, const Fp& a) {
   Fp t, r3;
+  PSB_OPCOUNT(INV);
   modinv::inv_plain(t.v, a.v);
   PSB_UNROLL
   for (int i = 0; i < PSB_NL; i++) r3.v[i] = PSB_K(FP_R3)[i];

@@ -61,7 +61,8 @@ std::atomic<uint64_t> g_launches{0};
 bool g_profile = false;
 // fixed-base sums of psb_verify with batched affine pair additions (curve.cuh, AffBatch); PSB_MSM_AFFINE=0 keeps the plain
 // mixed-addition chain (A/B switch, read once per process)
-bool g_msm_affine = [] { const char* e = getenv("PSB_MSM_AFFINE"); return !(e && e[0] == '0'); }();
+// (2, default: the pair sums are paired up once more before they reach the Jacobian accumulator; 1: one level)
+int g_msm_affine = [] { const char* e = getenv("PSB_MSM_AFFINE"); return e && e[0] >= '0' && e[0] <= '2' ? e[0] - '0' : 2; }();
 
 int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
   char buf[512];
@@ -240,7 +241,7 @@ int verify_launch(const psb_key* key, int di, size_t N, const G1J* d_sig1, const
     CK(cudaEventRecord(dv->ev[0], st));
   }
   // slot descriptors of the batched affine path are 29-bit table indices
-  const int affine = g_msm_affine && ((size_t)key->n * fixed_nwin(key->w)) << (key->w - 1) < kAffMaxEntries;
+  const int affine = ((size_t)key->n * fixed_nwin(key->w)) << (key->w - 1) < kAffMaxEntries ? g_msm_affine : 0;
   PSB_WAVES(N, k_verify_msm, (int)key->n, key->w, d_blob, d_off, d_m, kd.g2pts + 1, kd.tblYY, dK, affine);
   if (prof) CK(cudaEventRecord(dv->ev[1], st));
   PSB_WAVES(N, k_verify_miller, d_sig1, d_sig2, ss, dK, kd.lines, dF);

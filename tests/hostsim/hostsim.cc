@@ -4,6 +4,7 @@
 // can check the tower / curve / pairing LOGIC against the oracle without a GPU.  This library is
 // never linked into, loaded by, or used as a fallback for libpsb.so.
 #include <stddef.h>
+#define PSB_COUNT_OPS 1   // host-side call counters of fp_mul / fp_sqr / fp_dot2 / fp_inv (csrc/fp.cuh): the MACs a lane executes
 #include "../../ps-signature-and-el-passo_b200/csrc/testops.cuh"
 
 extern "C" {
@@ -49,7 +50,7 @@ void host_table(std::vector<Aff<F>>& out, const Jac<F>& base, int w) {
 // (pt_fixed_mul_acc) and once through the batched affine pair additions (AffBatch, curve.cuh) -- both normalised
 template <class F>
 static void fixed_msm(int w, int nbases, const uint32_t* bases, const uint32_t* k_mont, const uint32_t* acc0, uint32_t* out_plain,
-                      uint32_t* out_aff) {
+                      uint32_t* out_aff, int two_levels) {
   constexpr int U = sizeof(Jac<F>) / 4;
   std::vector<Aff<F>> t;
   for (int i = 0; i < nbases; i++) { Jac<F> b; ld(b, bases + U * i); host_table(t, b, w); }
@@ -57,7 +58,8 @@ static void fixed_msm(int w, int nbases, const uint32_t* bases, const uint32_t* 
   Jac<F> a, c, n;
   ld(a, acc0); c = a;
   AffBatch<F> batch;
-  aff_init(batch, nbases * fixed_nwin(w), t.data());
+  AffPts<F> level2;
+  aff_init(batch, nbases * fixed_nwin(w), t.data(), (const Aff<F>*)nullptr, (const Aff<F>*)nullptr, two_levels ? &level2 : nullptr);
   for (int i = 0; i < nbases; i++) {
     uint32_t k[8]; Fr km; ld(km, k_mont + 8 * i); fr_load_normal(k, &km);
     pt_fixed_mul_acc(a, t.data() + i * pb, k, w);
@@ -66,6 +68,22 @@ static void fixed_msm(int w, int nbases, const uint32_t* bases, const uint32_t* 
   aff_flush(c, batch);
   pt_normalize(n, a); st(out_plain, n);
   pt_normalize(n, c); st(out_aff, n);
+}
+// second level of the batched affine sums on its own: acc0 + sum of the given normalised points (present[i] = 0: an empty slot)
+template <class F>
+static void aff_l2_probe(int npts, const uint32_t* pts, const uint8_t* present, const uint32_t* acc0, uint32_t* out) {
+  constexpr int U = sizeof(Jac<F>) / 4;
+  Jac<F> a, n;
+  ld(a, acc0);
+  AffPts<F> l;
+  l.cnt = 0; l.absent = 0;
+  for (int i = 0; i < npts; i++) {
+    Jac<F> p; ld(p, pts + U * i);
+    Aff<F> e; e.x = p.x; e.y = p.y;
+    aff_l2_push(a, l, present[i] ? &e : (const Aff<F>*)nullptr);
+  }
+  aff_flush_l2(a, l);
+  pt_normalize(n, a); st(out, n);
 }
 }  // namespace
 
@@ -80,10 +98,49 @@ void hostsim_fixed_mul_g1(int w, const uint32_t* B, const uint32_t* k_mont, uint
   G1J n; pt_normalize(n, acc); st(out, n);
 }
 
+void hostsim_aff_l2(int is_g2, int npts, const uint32_t* pts, const uint8_t* present, const uint32_t* acc0, uint32_t* out) {
+  if (is_g2) aff_l2_probe<Fp2>(npts, pts, present, acc0, out); else aff_l2_probe<Fp>(npts, pts, present, acc0, out);
+}
+// executed Fp-level operations of one psb_verify lane, phase by phase (k_verify_msm / k_verify_miller / k_verify_final run the
+// same functions): out[phase * 4 + {mul, sqr, dot2, inv}].  The MSM phase is counted on host-built tables of window w (the
+// count depends on n and nwin only); `levels` as PSB_MSM_AFFINE (0 plain chain, 1 / 2 batched affine levels).
+void hostsim_count_verify_ops(int n, int w, int levels, const uint32_t* gg, const uint32_t* XX, const uint32_t* YY, const uint32_t* k_mont,
+                              const uint32_t* sig1, const uint32_t* sig2, unsigned long long* out) {
+  std::vector<G2A> t;
+  G2J b2, ggj;
+  for (int i = 0; i < n; i++) { ld(b2, YY + kG2U * i); host_table(t, b2, w); }
+  ld(ggj, gg);
+  std::vector<FixedLine> lines(kFixedLineSlots);
+  G2A q; q.x = ggj.x; q.y = ggj.y;
+  precompute_fixed_lines(lines.data(), q);
+  const size_t pb = (size_t)fixed_nwin(w) << (w - 1);
+  auto snap = [&](int phase) { for (int j = 0; j < 4; j++) { out[phase * 4 + j] = opcount::c[j]; opcount::c[j] = 0; } };
+  for (int j = 0; j < 4; j++) opcount::c[j] = 0;
+  G2J K; ld(K, XX);
+  AffBatch<Fp2> batch;
+  AffPts<Fp2> level2;
+  if (levels) aff_init(batch, n * fixed_nwin(w), t.data(), (const G2A*)nullptr, (const G2A*)nullptr, levels > 1 ? &level2 : nullptr);
+  for (int i = 0; i < n; i++) {
+    uint32_t k[8]; Fr km; ld(km, k_mont + 8 * i); fr_load_normal(k, &km);
+    if (levels) aff_push_fixed_mul(K, batch, 0, i * pb, k, w); else pt_fixed_mul_acc(K, t.data() + i * pb, k, w);
+  }
+  if (levels) aff_flush(K, batch);
+  snap(0);
+  G1J s1, s2; ld(s1, sig1); ld(s2, sig2);
+  Fp x1, y1, x2, y2;
+  g1_affine_for_pairing(x1, y1, s1);
+  g1_affine_for_pairing(x2, y2, s2);
+  fp_neg(y2, y2);
+  Fp12 f, e;
+  miller_loop2(f, x1, y1, K, x2, y2, lines.data(), true);
+  snap(1);
+  final_exp(e, f);
+  snap(2);
+}
 void hostsim_fixed_msm(int is_g2, int w, int nbases, const uint32_t* bases, const uint32_t* k_mont, const uint32_t* acc0,
-                       uint32_t* out_plain, uint32_t* out_aff) {
-  if (is_g2) fixed_msm<Fp2>(w, nbases, bases, k_mont, acc0, out_plain, out_aff);
-  else fixed_msm<Fp>(w, nbases, bases, k_mont, acc0, out_plain, out_aff);
+                       uint32_t* out_plain, uint32_t* out_aff, int two_levels) {
+  if (is_g2) fixed_msm<Fp2>(w, nbases, bases, k_mont, acc0, out_plain, out_aff, two_levels);
+  else fixed_msm<Fp>(w, nbases, bases, k_mont, acc0, out_plain, out_aff, two_levels);
 }
 
 void hostsim_provide_id(int n, int w, const uint32_t* g, const uint32_t* X, const uint32_t* Y, size_t N,

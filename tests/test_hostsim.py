@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from tests.conftest import BN254, CURVE_Z, FIELD_P, FP_BYTES, GROUP_R, rand_fp_raw
+from tests.conftest import BN254, CURVE_Z, FIELD_P, FP_BYTES, GROUP_R, bls_only, rand_fp_raw
 
 
 def hop(hs, op, a, b=None, c=None):
@@ -134,3 +134,35 @@ def test_glv_gls_scalar_edges(hostsim, ref):
     Q2 = ref.g2_op(ref.G_DBL, Q)
     assert np.array_equal(norm1(hop(hostsim, 43, P2, k)), ref.g1_op(ref.G_NORM, ref.g1_mul(P2, k)))
     assert np.array_equal(norm2(hop(hostsim, 53, Q2, k)), ref.g2_op(ref.G_NORM, ref.g2_mul(Q2, k)))
+
+
+@bls_only
+def test_executed_mac_counts(hostsim, ref):
+    """bench.py's `executed_mac32_per_lane`: the Fp-level calls one psb_verify lane makes in each phase, counted by the
+    instrumented host build of the engine's own headers (PSB_COUNT_OPS in tests/hostsim), equal the constants bench.py
+    reports and its mirror of the batched affine sums (msm_ops) at every level setting."""
+    import bench
+    from tests import workload
+    p = lambda a: np.ascontiguousarray(a).ctypes.data_as(C.c_void_p)  # noqa: E731
+    rng = np.random.default_rng(3)
+    for n, w in ((5, 8), (5, 4), (2, 8)):
+        wl = workload.make_verify_workload(n_attrs=n, lanes=1, seed=3)
+        # scalars without a zero digit and without recoding carries: every w-bit digit in [1, 2^(w-1) - 1], top digit small (< r)
+        ks = []
+        for _ in range(n):
+            digs = [int(rng.integers(1, 1 << (w - 1))) for _ in range(256 // w)]
+            digs[-1] = 1 + digs[-1] % 2 if w == 4 else 1 + digs[-1] % 0x2f
+            ks.append(sum(d << (w * j) for j, d in enumerate(digs)))
+        km = ref.fr_from_ints(ks)
+        for levels in (0, 1, 2):
+            out = np.zeros(12, dtype=np.uint64)
+            hostsim.hostsim_count_verify_ops(C.c_int(n), C.c_int(w), C.c_int(levels), p(wl.key.gg), p(wl.key.XX), p(wl.key.YY),
+                                             p(km), p(wl.sig1[0]), p(wl.sig2[0]), p(out))
+            got = out.reshape(3, 4)
+            assert tuple(int(x) for x in got[0]) == bench.msm_ops(n, w, levels)[1], (n, w, levels)
+            assert tuple(int(x) for x in got[1]) == bench.EXEC_OPS_MILLER
+            assert tuple(int(x) for x in got[2]) == bench.EXEC_OPS_FINAL
+    # the headline shape: fewer executed MACs with every level, and the FpMul-eq numerator follows
+    f0, f1, f2 = (bench.msm_ops(5, 20, lv) for lv in (0, 1, 2))
+    assert f0[0] == 5 * 13 * 29 and f0[0] > f1[0] > f2[0]
+    assert bench.exec_mac32(f0[1]) > bench.exec_mac32(f1[1]) > bench.exec_mac32(f2[1])

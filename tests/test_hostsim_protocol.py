@@ -100,15 +100,17 @@ def test_fixed_base_sum_batched_affine(hostsim, ref, is_g2):
     def run(w, bases, ks):
         bases = op(ref.G_NORM, np.stack(bases))
         km = ref.fr_from_ints(ks)
-        o1 = np.zeros(W, dtype=np.uint64)
-        o2 = np.zeros(W, dtype=np.uint64)
-        hostsim.hostsim_fixed_msm(C.c_int(is_g2), C.c_int(w), C.c_int(len(ks)), _p(bases), _p(km), _p(acc0), _p(o1), _p(o2))
         exp = acc0.reshape(1, -1)
         for b, k in zip(bases, km):
             exp = op(ref.G_ADD, exp, mul(b, k.reshape(1, -1)))
         exp = op(ref.G_NORM, exp)[0]
-        assert np.array_equal(o1, exp), ("plain", w)
-        assert np.array_equal(o2, exp), ("batched affine", w)
+        for levels in (0, 1):     # pair sums straight into the accumulator / paired up once more (AffPts)
+            o1 = np.zeros(W, dtype=np.uint64)
+            o2 = np.zeros(W, dtype=np.uint64)
+            hostsim.hostsim_fixed_msm(C.c_int(is_g2), C.c_int(w), C.c_int(len(ks)), _p(bases), _p(km), _p(acc0), _p(o1), _p(o2),
+                                      C.c_int(levels))
+            assert np.array_equal(o1, exp), ("plain", w)
+            assert np.array_equal(o2, exp), ("batched affine", w, levels)
 
     low = lambda: int.from_bytes(rng.bytes(12), "little")  # noqa: E731
     top = 2 << 252
@@ -118,6 +120,38 @@ def test_fixed_base_sum_batched_affine(hostsim, ref, is_g2):
     run(5, [B0, B2, B1], [5, 0, (1 << 200) + 77])
     # random full-size scalars, two flushes (3 x 64 slots = 96 pairs -> 2 batches of 48)
     run(4, [B0, B2, B3], [int.from_bytes(rng.bytes(40), "little") % GROUP_R for _ in range(3)])
+    run(3, [B0, B2, B1, B3], [int.from_bytes(rng.bytes(40), "little") % GROUP_R for _ in range(4)])   # 344 slots: 3 + 3 flushes
     # one short batch (8 pairs: plain additions), and an even slot count in one flush (w = 5: 52 windows)
     run(16, [B0], [int.from_bytes(rng.bytes(40), "little") % GROUP_R])
     run(5, [B2], [int.from_bytes(rng.bytes(40), "little") % GROUP_R])
+
+
+@pytest.mark.parametrize("is_g2", [0, 1])
+def test_batched_affine_second_level(hostsim, ref, is_g2):
+    """AffPts (the second level of the batched affine sums) on explicit points: pairs P + P, P + (-P), a point beside an empty
+    slot, two empty slots, a flush that fills up in the middle (70 points: 64 + 6) and a short one (plain additions)."""
+    from tests.conftest import GROUP_R
+    W = G2W if is_g2 else G1W
+    mul, op = (ref.g2_mul, ref.g2_op) if is_g2 else (ref.g1_mul, ref.g1_op)
+    rng = np.random.default_rng(11 + is_g2)
+    B = ref.hash_to_g2(b"l2") if is_g2 else ref.hash_to_g1(b"l2")
+    acc0 = mul(B, ref.fr_from_ints([777]))[0]
+
+    def rand_pts(n):
+        return op(ref.G_NORM, mul(B, ref.fr_from_ints([int.from_bytes(rng.bytes(40), "little") % GROUP_R for _ in range(n)])))
+
+    for total in (70, 24, 7):
+        pts = rand_pts(total)
+        present = np.ones(total, dtype=np.uint8)
+        pts[1] = pts[0]                                   # P + P
+        pts[3] = op(ref.G_NEG, pts[2:3])[0]               # P + (-P)
+        present[5] = 0                                    # a point beside an empty slot
+        if total > 8:
+            present[6] = present[7] = 0                   # two empty slots
+        out = np.zeros(W, dtype=np.uint64)
+        hostsim.hostsim_aff_l2(C.c_int(is_g2), C.c_int(total), _p(pts), _p(present), _p(acc0), _p(out))
+        exp = acc0.reshape(1, -1)
+        for i in range(total):
+            if present[i]:
+                exp = op(ref.G_ADD, exp, pts[i:i + 1])
+        assert np.array_equal(out, op(ref.G_NORM, exp)[0]), total
