@@ -134,7 +134,7 @@ def msm_ops(n_attrs: int, window_bits: int, levels: int = MSM_AFFINE_LEVELS):
 
 def exec_mac32(ops) -> int:
     return int(sum(c * m for c, m in zip(ops, EXEC_MAC32)))
-TRAFFIC_FILE = "r2h_traffic.json"   # latest committed ncu DRAM-traffic capture (profiles/)
+TRAFFIC_FILE = "r2w_traffic.json"   # latest committed ncu DRAM-traffic capture (profiles/)
 
 
 def a_verify_fpmul(n_attrs: int, window_bits: int) -> float:

@@ -180,3 +180,54 @@ def test_wave_boundaries(gpu_pkg, ref):
     exp = ref.pairing(P, Q)
     assert np.array_equal(gt[:8], exp) and np.array_equal(gt[wave - 8:wave], exp) and np.array_equal(gt[wave:wave + 8], exp)
     assert np.array_equal(gt[lanes - 8:], exp)
+
+
+def test_batched_affine_sum_exceptional_pairs(gpu_pkg, ref):
+    """The fixed-base sum of k_verify_msm adds table entries pairwise in AFFINE coordinates (AffBatch, csrc/curve.cuh); pairs the
+    affine formula cannot take -- P = Q, P = -Q, an absent entry (zero digit) -- must come out as the same group element.
+    Key with YY_1 = 2^252 YY_0 and YY_3 = -2^252 YY_2 and w = 7 (37 windows: the top window of one base pairs with window 0
+    of the next), host-supplied scalars whose digits meet at those seams; lanes with small scalars (mostly absent entries)
+    and ordinary random lanes share the warps.  Expected: K from the reference's G2 arithmetic, GT from its pairings,
+    verdict 1 exactly on the lanes signed under the equivalent exponents."""
+    from tests.conftest import GROUP_R
+    rng = np.random.default_rng(21)
+    km = ref.KeyMaterial(2, seed_=5)
+    shift = (1 << 252) % GROUP_R
+    sh = ref.fr_from_ints([shift])
+    YY = np.stack([km.YY[0], ref.g2_mul(km.YY[0], sh)[0], km.YY[1], ref.g2_op(ref.G_NEG, ref.g2_mul(km.YY[1], sh))[0]])
+    YY = ref.g2_op(ref.G_NORM, YY)
+    Y = np.stack([km.Y[0], km.Y[0], km.Y[1], km.Y[1]])          # G1 side of the key: unused by verify
+    y0, y1 = ref.fr_to_ints(km.y)
+    x = ref.fr_to_ints(km.x.reshape(1, -1))[0]
+    ya = [y0, shift * y0 % GROUP_R, y1, (GROUP_R - shift) * y1 % GROUP_R]
+    lanes = 96
+    low = lambda: int.from_bytes(rng.bytes(12), "little") << 7  # noqa: E731
+    ms = []
+    for j in range(lanes):
+        kind = j % 4
+        if kind == 0:      # P = Q at the 0/1 seam, P = -Q at the 2/3 seam
+            ms.append([(2 << 252) + low(), 2 + low(), (2 << 252) + low(), 2 + low()])
+        elif kind == 1:    # mostly absent entries
+            ms.append([5, 0, 1 << 200, 77])
+        else:              # ordinary scalars
+            ms.append([int.from_bytes(rng.bytes(40), "little") % GROUP_R for _ in range(4)])
+    m = ref.fr_from_ints([v for lane in ms for v in lane])
+    ref.seed(9)
+    h = ref.g1_mul(km.g, ref.fr_rand(lanes))
+    e = [(x + sum(a * b for a, b in zip(lane, ya))) % GROUP_R for lane in ms]
+    sig2 = ref.g1_mul(h, ref.fr_from_ints(e))
+    bad = np.arange(lanes) % 5 == 4
+    sig2[bad] = ref.g1_op(ref.G_ADD, sig2[bad], np.broadcast_to(km.g, (int(bad.sum()), km.g.size)).copy())
+    sig1 = ref.g1_op(ref.G_NORM, h)
+    sig2 = ref.g1_op(ref.G_NORM, sig2)
+    K = np.broadcast_to(km.XX, (lanes, km.XX.size)).copy()
+    mm = m.reshape(lanes, 4, -1)
+    for i in range(4):
+        K = ref.g2_op(ref.G_ADD, K, ref.g2_mul(np.broadcast_to(YY[i], (lanes, YY[i].size)).copy(), mm[:, i]))
+    exp_gt = ref.pairing_ratio(sig1, K, sig2, np.broadcast_to(km.gg, (lanes, km.gg.size)).copy())
+    for w in (7, 8):       # w = 8: 32 windows per base, no seam pairs -- the same lanes through ordinary pairs
+        pk = gpu_pkg.PSPubKey(km.g, km.gg, km.XX, Y, YY, window_bits=w)
+        got_v, got_gt = gpu_pkg.PSVerifier(pk).verify(sig1, sig2, scalars=m, want_gt=True)
+        assert np.array_equal(got_gt, exp_gt), w
+        assert np.array_equal(got_v.astype(bool), ~bad), w
+        pk.close()
