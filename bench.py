@@ -714,7 +714,7 @@ def main():
     ap.add_argument("--configs", default="cfg3,cfg4,cfg5,inproc,bn254",
                     help="secondary entries of the line: BASELINE configs[2..4], the in-process multi-device run (N > 1), BN254; 'none' = headline only")
     ap.add_argument("--config-lanes", type=int, default=1 << 18, help="lanes per GPU of cfg3 / cfg4 (named: 2^18)")
-    ap.add_argument("--config-window-bits", type=int, default=16)
+    ap.add_argument("--config-window-bits", type=int, default=20, help="window of the per-key tables of cfg3 / cfg4 (20: +2.8 % sign-on, +6.5 % issuance over 16, profiles/r2z_ab_config_windows.txt)")
     ap.add_argument("--lanes50", type=int, default=1 << 24, help="TOTAL lanes of cfg5 (named: 2^24), sharded over the ranks")
     ap.add_argument("--window-bits50", type=int, default=20, help="fixed-base window of the 50-attribute key (20: 65 GB of tables)")
     ap.add_argument("--curve", default="bls12_381", choices=["bls12_381", "bn254"],

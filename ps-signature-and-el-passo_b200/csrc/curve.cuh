@@ -499,6 +499,7 @@ struct AffBatch {
   const Aff<F>* tbl[3];
   AffPts<F>* l2;                              // nullptr: pair sums go straight to the accumulator
   int cnt, cap;                               // slots filled / slots per flush (even, <= 2 kAffG)
+  bool plain;                                 // a table too large for the 29-bit slot index: plain mixed-addition chain
 };
 // slots per flush for `total` slots: as few flushes as kAffG allows, of equal size
 PSB_HD PSB_INL int aff_batch_cap(int total) {
@@ -507,10 +508,13 @@ PSB_HD PSB_INL int aff_batch_cap(int total) {
   const int nb = (pairs + kAffG - 1) / kAffG;
   return 2 * ((pairs + nb - 1) / nb);
 }
+// `max_entries`: size of the largest table the batch draws from (entries); kept 32-bit on purpose -- 64-bit descriptors cost
+// k_vid_g2 78 registers and the whole gain (profiles/r2z_ab_config_windows.txt)
 template <class F>
-PSB_HD PSB_INL void aff_init(AffBatch<F>& b, int total_slots, const Aff<F>* t0, const Aff<F>* t1 = nullptr, const Aff<F>* t2 = nullptr,
-                             AffPts<F>* l2 = nullptr) {
+PSB_HD PSB_INL void aff_init(AffBatch<F>& b, int total_slots, size_t max_entries, const Aff<F>* t0, const Aff<F>* t1 = nullptr,
+                             const Aff<F>* t2 = nullptr, AffPts<F>* l2 = nullptr) {
   b.cnt = 0; b.cap = aff_batch_cap(total_slots);
+  b.plain = max_entries >= kAffMaxEntries;
   b.tbl[0] = t0; b.tbl[1] = t1; b.tbl[2] = t2;
   b.l2 = total_slots >= 4 * kAffMinPairs ? l2 : nullptr;     // fewer than kAffMinPairs second-level pairs: not worth it
   if (b.l2) { b.l2->cnt = 0; b.l2->absent = 0; }
@@ -641,6 +645,7 @@ PSB_HD PSB_NOINL void aff_flush(Jac<F>& acc, AffBatch<F>& b, bool last = true) {
 // this base in table `tid` of the batch
 template <class F>
 PSB_HD PSB_INL void aff_push_fixed_mul(Jac<F>& acc, AffBatch<F>& b, int tid, size_t first, const uint32_t* k, int w) {
+  if (b.plain) { pt_fixed_mul_acc(acc, b.tbl[tid] + first, k, w); return; }
   const int nwin = fixed_nwin(w);
   const uint32_t half = 1u << (w - 1);
   const uint32_t tag = (uint32_t)tid << 29;

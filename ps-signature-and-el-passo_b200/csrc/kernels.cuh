@@ -40,6 +40,10 @@ constexpr int kPairBlock = PSB_PAIR_BLOCK;
 #else
 #define PSB_PROTO_BOUNDS __launch_bounds__(kBlock, PSB_PROTO_MINB)
 #endif
+// the two G2 NIZK kernels hold their register count at 168 (three blocks = 12 warps per SM): left to itself ptxas settles on
+// 168 or ~248 registers depending on small changes elsewhere in the lane function, and at 248 (8 warps per SM) sign-on
+// verification loses the whole gain of the batched affine sums (profiles/r2z_ab_config_windows.txt)
+#define PSB_PROTO_G2_BOUNDS __launch_bounds__(kBlock, 3)
 
 // ---- steering ptxas's pipe balancer ---------------------------------------------------------------------------------
 // ptxas balances the integer-add (ALU) and multiply (FMA) pipes from the STATIC instruction counts of a whole kernel: in a kernel
@@ -337,7 +341,7 @@ __global__ void PSB_PAIR_BOUNDS k_verify_msm(size_t N, size_t base, int n, int w
   G2J acc = *XX;
   AffBatch<Fp2> batch;
   AffPts<Fp2> level2;
-  if (affine) aff_init(batch, n * fixed_nwin(w), tbl, (const G2A*)nullptr, (const G2A*)nullptr, affine > 1 ? &level2 : nullptr);
+  if (affine) aff_init(batch, n * fixed_nwin(w), (size_t)n * per_base, tbl, (const G2A*)nullptr, (const G2A*)nullptr, affine > 1 ? &level2 : nullptr);
   for (int i = 0; i < n; i++) {
     uint32_t k[8];
     if (blob) {
@@ -535,7 +539,7 @@ __global__ void PSB_PROTO_BOUNDS k_sign(size_t N, int na, int w, const G1A* tblG
 
 // ---- PSVerifier::el_passo_verify_id (src/ps-verifier.cc:37-212): NIZK steps; the pairing check reuses
 //      k_verify_miller / k_verify_final with K from step 1 ------------------------------------------------
-__global__ void PSB_PROTO_BOUNDS k_vid_g2(size_t N, int n, int w, const G2A* tblYY, const G2A* tblAux, const G2J* k,
+__global__ void PSB_PROTO_G2_BOUNDS k_vid_g2(size_t N, int n, int w, const G2A* tblYY, const G2A* tblAux, const G2J* k,
                                                     const Fr* c, const Fr* rs, LaneGeom lg, int with_id, const uint8_t* blob,
                                                     const uint64_t* off, G2J* Vk, G2J* K, uint8_t* ok) {
   const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -675,7 +679,7 @@ __global__ void PSB_PROTO_BOUNDS k_unblind(size_t N, const G1J* sig1, const G1J*
   out2[lane] = r;
   PSB_BALLAST(N, out2);
 }
-__global__ void PSB_PROTO_BOUNDS k_pid_g2(size_t N, int n, int w, const G2A* tblYY, const G2A* tblAux, const G2J* XX,
+__global__ void PSB_PROTO_G2_BOUNDS k_pid_g2(size_t N, int n, int w, const G2A* tblYY, const G2A* tblAux, const G2J* XX,
                                                     const uint8_t* hide, int h, int with_id, const uint8_t* blob,
                                                     const uint64_t* off, const Fr* rnd, G2J* k, G2J* Vk) {
   const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -348,8 +348,8 @@ PSB_HD PSB_NOINL bool verify_id_g2_lane(int n, TblGeom tg, const G2A* tblYY, con
   {
     int hid = 0;
     for (int i = 0; i < n; i++) hid += off[i + 1] == off[i];
-    aff_init(bV, (hid + 2) * fixed_nwin(tg.w), tblYY, tblAux);
-    aff_init(bK, (n - hid) * fixed_nwin(tg.w), tblYY);
+    aff_init(bV, (hid + 2) * fixed_nwin(tg.w), (size_t)(n > 2 ? n : 2) * pb, tblYY, tblAux);
+    aff_init(bK, (n - hid) * fixed_nwin(tg.w), (size_t)n * pb, tblYY);
   }
   int cnt = 0;
   for (int i = 0; i < n; i++) {

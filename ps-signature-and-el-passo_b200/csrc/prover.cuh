@@ -101,8 +101,8 @@ PSB_HD PSB_NOINL void prove_id_g2_lane(int n, TblGeom tg, const G2A* tblYY, cons
   G2J K = XX, V = XX;
   // the table entries of k and of V_k are summed pairwise in affine coordinates (AffBatch, curve.cuh)
   AffBatch<Fp2> bK, bV;
-  aff_init(bK, (h + 1) * fixed_nwin(tg.w), tblYY, tblAux);
-  aff_init(bV, (h + 1) * fixed_nwin(tg.w), tblYY, tblAux);
+  aff_init(bK, (h + 1) * fixed_nwin(tg.w), (size_t)(n > 2 ? n : 2) * pb, tblYY, tblAux);
+  aff_init(bV, (h + 1) * fixed_nwin(tg.w), (size_t)(n > 2 ? n : 2) * pb, tblYY, tblAux);
   int j = 0;
   for (int i = 0; i < n; i++) {
     if (!hide[i]) continue;

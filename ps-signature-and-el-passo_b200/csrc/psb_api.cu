@@ -240,8 +240,7 @@ int verify_launch(const psb_key* key, int di, size_t N, const G1J* d_sig1, const
     for (auto& e : dv->ev) if (!e) CK(cudaEventCreate(&e));
     CK(cudaEventRecord(dv->ev[0], st));
   }
-  // slot descriptors of the batched affine path are 29-bit table indices
-  const int affine = ((size_t)key->n * fixed_nwin(key->w)) << (key->w - 1) < kAffMaxEntries ? g_msm_affine : 0;
+  const int affine = g_msm_affine;   // (tables beyond 2^29 entries take the plain chain inside the kernel: AffBatch::plain)
   PSB_WAVES(N, k_verify_msm, (int)key->n, key->w, d_blob, d_off, d_m, kd.g2pts + 1, kd.tblYY, dK, affine);
   if (prof) CK(cudaEventRecord(dv->ev[1], st));
   PSB_WAVES(N, k_verify_miller, d_sig1, d_sig2, ss, dK, kd.lines, dF);

@@ -59,7 +59,8 @@ static void fixed_msm(int w, int nbases, const uint32_t* bases, const uint32_t* 
   ld(a, acc0); c = a;
   AffBatch<F> batch;
   AffPts<F> level2;
-  aff_init(batch, nbases * fixed_nwin(w), t.data(), (const Aff<F>*)nullptr, (const Aff<F>*)nullptr, two_levels ? &level2 : nullptr);
+  aff_init(batch, nbases * fixed_nwin(w), two_levels == 2 ? kAffMaxEntries : t.size(), t.data(), (const Aff<F>*)nullptr, (const Aff<F>*)nullptr,
+           two_levels == 1 ? &level2 : nullptr);   // two_levels == 2: pretend the table is too large (plain chain)
   for (int i = 0; i < nbases; i++) {
     uint32_t k[8]; Fr km; ld(km, k_mont + 8 * i); fr_load_normal(k, &km);
     pt_fixed_mul_acc(a, t.data() + i * pb, k, w);
@@ -119,7 +120,7 @@ void hostsim_count_verify_ops(int n, int w, int levels, const uint32_t* gg, cons
   G2J K; ld(K, XX);
   AffBatch<Fp2> batch;
   AffPts<Fp2> level2;
-  if (levels) aff_init(batch, n * fixed_nwin(w), t.data(), (const G2A*)nullptr, (const G2A*)nullptr, levels > 1 ? &level2 : nullptr);
+  if (levels) aff_init(batch, n * fixed_nwin(w), t.size(), t.data(), (const G2A*)nullptr, (const G2A*)nullptr, levels > 1 ? &level2 : nullptr);
   for (int i = 0; i < n; i++) {
     uint32_t k[8]; Fr km; ld(km, k_mont + 8 * i); fr_load_normal(k, &km);
     if (levels) aff_push_fixed_mul(K, batch, 0, i * pb, k, w); else pt_fixed_mul_acc(K, t.data() + i * pb, k, w);

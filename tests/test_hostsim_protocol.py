@@ -104,7 +104,7 @@ def test_fixed_base_sum_batched_affine(hostsim, ref, is_g2):
         for b, k in zip(bases, km):
             exp = op(ref.G_ADD, exp, mul(b, k.reshape(1, -1)))
         exp = op(ref.G_NORM, exp)[0]
-        for levels in (0, 1):     # pair sums straight into the accumulator / paired up once more (AffPts)
+        for levels in (0, 1, 2):  # pair sums straight into the accumulator / paired up once more (AffPts) / table declared too large for the slot index: plain chain
             o1 = np.zeros(W, dtype=np.uint64)
             o2 = np.zeros(W, dtype=np.uint64)
             hostsim.hostsim_fixed_msm(C.c_int(is_g2), C.c_int(w), C.c_int(len(ks)), _p(bases), _p(km), _p(acc0), _p(o1), _p(o2),
