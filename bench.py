@@ -422,7 +422,11 @@ def cfg_signon(pkg, rk: Ranks, steps: int, window_bits: int, lanes: int, cpu: bo
             proof["k"][j] = proof["k"][j - 1]
         expected[j] = 0
     ver = pkg.PSVerifier(pk)
-    call = lambda: ver.el_passo_verify_id(proof, shown_p, ads_p, service_pt, y, g, h, with_id=True)  # noqa: E731
+    # host side of the timed calls: page-locked input arrays and a page-locked, reused verdict buffer (psb_host_alloc)
+    proof = {k: pkg.pinned_copy(v) for k, v in proof.items()}
+    shown_p, ads_p = tuple(pkg.pinned_copy(a) for a in shown_p), tuple(pkg.pinned_copy(a) for a in ads_p)
+    h_verdict = pkg.pinned_empty((lanes,), np.uint8)
+    call = lambda: ver.el_passo_verify_id(proof, shown_p, ads_p, service_pt, y, g, h, with_id=True, out=h_verdict)  # noqa: E731
     call()                                            # tables + staging buffers
     l0 = pkg.launch_count()
     got, dt = rk.timed(call, steps)
@@ -432,11 +436,12 @@ def cfg_signon(pkg, rk: Ranks, steps: int, window_bits: int, lanes: int, cpu: bo
     out = {"call": "PSVerifier::el_passo_verify_id (psb_verify_id)", "n_attrs": n, "hidden": nh, "lanes_per_gpu": lanes,
            "metric": "signon_verifications_per_sec", "unit": "verifications/s", "steps": steps, "window_bits": window_bits,
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": lanes, "gpu_launches": int(launches), "tampered_lanes": int((expected == 0).sum()),
-           "inputs": "proofs made by psb_prove_id from honest credentials, every lane distinct"}
+           "inputs": "proofs made by psb_prove_id from honest credentials, every lane distinct; page-locked host buffers"}
     local = [dt * 1e3, 0.0 if ok_local else 1.0]
     if wire:
-        ser = pkg.idproof_serialize(proof, shown_p, pk.n)
-        wcall = lambda: ver.el_passo_verify_id_wire(ser, ads_p, service_pt, y, g, h, with_id=True)  # noqa: E731
+        ser = tuple(pkg.pinned_copy(a) for a in pkg.idproof_serialize(proof, shown_p, pk.n))
+        w_out = (pkg.pinned_empty((lanes,), np.uint8), pkg.pinned_empty((lanes,), np.uint8))
+        wcall = lambda: ver.el_passo_verify_id_wire(ser, ads_p, service_pt, y, g, h, with_id=True, out=w_out)  # noqa: E731
         wcall()
         (wgot, wparsed), wdt = rk.timed(wcall, steps)
         local += [wdt * 1e3, 0.0 if (np.array_equal(wgot, expected) and wparsed.all()) else 1.0]
@@ -491,11 +496,18 @@ def cfg_issuance(pkg, rk: Ranks, steps: int, window_bits: int, lanes: int, cpu: 
         expected[j] = 0
     u, t_r = rand_fr(rng, (lanes,)), rand_fr(rng, (lanes,))
     sg = pkg.PSSigner(pk)
-    issue = lambda: sg.el_passo_provide_id(A, c, rs, shown_p, ads_p, u)  # noqa: E731
+    # host side of the timed calls: page-locked input arrays and page-locked, reused output buffers (psb_host_alloc)
+    A, c, rs, u, t_r = (pkg.pinned_copy(a) for a in (A, c, rs, u, t_r))
+    shown_p, ads_p = tuple(pkg.pinned_copy(a) for a in shown_p), tuple(pkg.pinned_copy(a) for a in ads_p)
+    G1W = A.shape[1]
+    SER = 16 * G1W // 3          # sigma1 || sigma2 compressed: 2 x 8 x (u64 words of an Fp)
+    o_issue = (pkg.pinned_empty((lanes,), np.uint8), pkg.pinned_empty((lanes, G1W), np.uint64), pkg.pinned_empty((lanes, G1W), np.uint64), pkg.pinned_empty((lanes, SER), np.uint8))
+    o_rnd = (pkg.pinned_empty((lanes, G1W), np.uint64), pkg.pinned_empty((lanes, G1W), np.uint64), pkg.pinned_empty((lanes, SER), np.uint8))
+    issue = lambda: sg.el_passo_provide_id(A, c, rs, shown_p, ads_p, u, out=o_issue)  # noqa: E731
     issue()
     l0 = pkg.launch_count()
     (v, s1, s2, ser), dt_issue = rk.timed(issue, steps)
-    rnd = lambda: pkg.PSRequester.randomize_credential(s1, s2, t_r, want_serialized=True)  # noqa: E731
+    rnd = lambda: pkg.PSRequester.randomize_credential(s1, s2, t_r, want_serialized=True, out=o_rnd)  # noqa: E731
     rnd()
     (o1, o2, oser), dt_rnd = rk.timed(rnd, steps)
     launches = pkg.launch_count() - l0
@@ -509,7 +521,7 @@ def cfg_issuance(pkg, rk: Ranks, steps: int, window_bits: int, lanes: int, cpu: 
            "issue_then_randomize_e2e_value": rk.world * lanes * steps / ((red[0] + red[1]) * 1e-3),
            "h2d_bytes_per_step": int(A.nbytes + c.nbytes + rs.nbytes + u.nbytes + shown_p[0].nbytes + shown_p[1].nbytes + ads_p[0].nbytes + ads_p[1].nbytes),
            "d2h_bytes_per_step": int(v.nbytes + s1.nbytes + s2.nbytes + ser.nbytes),
-           "verdicts_ok": red[2] == 0.0, "inputs": "requests made by psb_request_id, every lane distinct"}
+           "verdicts_ok": red[2] == 0.0, "inputs": "requests made by psb_request_id, every lane distinct; page-locked host buffers"}
     if cpu and rk.rank == 0:
         from oracle import ref
         km, threads, S = ref.KeyMaterial(n, seed_=1), ref.hw_threads(), _ref_sample_lanes(lanes)

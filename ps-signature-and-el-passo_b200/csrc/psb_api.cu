@@ -265,6 +265,14 @@ int psb_shard_range(size_t N, int ndev, int k, size_t* begin, size_t* end) {
   *end = (size_t)((unsigned __int128)N * (unsigned)(k + 1) / (unsigned)ndev);
   return PSB_OK;
 }
+void* psb_host_alloc(size_t bytes) {
+  if (!g_init) { fail(PSB_ERR_NOT_INIT, "psb_init not called"); return nullptr; }
+  void* p = nullptr;
+  const cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable);
+  if (e != cudaSuccess) { fail(PSB_ERR_NOMEM, "cudaHostAlloc", e); return nullptr; }
+  return p;
+}
+void psb_host_free(void* p) { if (p) cudaFreeHost(p); }
 int psb_set_profiling(int on) { g_profile = on != 0; return PSB_OK; }
 int psb_last_phase_ms(int dev_index, float* ms) {
   if (!g_init || dev_index < 0 || dev_index >= (int)g_devs.size() || !ms) return fail(PSB_ERR_ARG, "bad argument");

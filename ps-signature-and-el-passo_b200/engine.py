@@ -58,6 +58,9 @@ def lib():
         L.psb_key_table_bytes.restype = C.c_size_t
         L.psb_verify_ws_bytes.restype = C.c_size_t
         L.psb_microbench.restype = C.c_double
+        L.psb_host_alloc.restype = C.c_void_p
+        L.psb_host_alloc.argtypes = [C.c_size_t]
+        L.psb_host_free.argtypes = [C.c_void_p]
         L.psb_key_destroy.argtypes = [C.c_void_p]
         L.psb_key_num_attributes.argtypes = [C.c_void_p]
         L.psb_key_table_bytes.argtypes = [C.c_void_p]
@@ -68,7 +71,7 @@ def lib():
 EXPORTS = ["psb_init", "psb_shutdown", "psb_num_devices", "psb_last_error", "psb_shard_range", "psb_launch_count",
            "psb_key_create", "psb_key_destroy", "psb_key_num_attributes", "psb_key_table_bytes",
            "psb_verify", "psb_verify_aos", "psb_verify_ser", "psb_g1_deserialize", "psb_g2_deserialize", "psb_verify_ws_bytes", "psb_verify_dev", "psb_randomize", "psb_provide_id",
-           "psb_verify_id", "psb_sign", "psb_verify_id_ser", "psb_provide_id_ser", "psb_wire_encode", "psb_request_id", "psb_unblind", "psb_prove_id", "psb_hash_to_g1", "psb_pairing", "psb_g1_mul", "psb_set_profiling", "psb_last_phase_ms", "psb_test_op_shape", "psb_test_op", "psb_microbench"]
+           "psb_verify_id", "psb_sign", "psb_verify_id_ser", "psb_provide_id_ser", "psb_wire_encode", "psb_request_id", "psb_unblind", "psb_prove_id", "psb_hash_to_g1", "psb_pairing", "psb_g1_mul", "psb_host_alloc", "psb_host_free", "psb_set_profiling", "psb_last_phase_ms", "psb_test_op_shape", "psb_test_op", "psb_microbench"]
 
 
 def _check(rc: int, what: str):
@@ -135,6 +138,16 @@ def pack_strings(strs: Sequence[bytes]):
 
 def pack_attrs(attrs: Sequence[Sequence[bytes]]):
     return pack_strings([a for lane in attrs for a in lane])
+
+
+def _out(out, i, shape, dtype):
+    """the i-th caller-supplied output buffer (e.g. page-locked, reused across calls) or a fresh array"""
+    if out is None or out[i] is None:
+        return np.zeros(shape, dtype=dtype)
+    a = out[i]
+    if a.shape != tuple(shape) or a.dtype != dtype or not a.flags["C_CONTIGUOUS"]:
+        raise ValueError(f"out[{i}] must be a C-contiguous {np.dtype(dtype).name}{tuple(shape)} array")
+    return a
 
 
 def _packed(x, flat: bool):
@@ -238,7 +251,7 @@ class PSVerifier:
         return verdict, decoded
 
     def el_passo_verify_id_wire(self, buffers, associated_data: Sequence[bytes], service_pt, authority_pk=None, g=None,
-                                h=None, with_id: bool = True, base64: bool = False, strict: bool = False):
+                                h=None, with_id: bool = True, base64: bool = False, strict: bool = False, out=None):
         """el_passo_verify_id straight from the WIRE (psb_verify_id_ser): buffers = per lane the bytes of
         IdProof::toBufferString() (or their base64 text), or a packed (blob, off) pair.  Returns (verdict, parsed)."""
         blob, off = _packed(buffers, True)
@@ -246,8 +259,8 @@ class PSVerifier:
         N = off.shape[0] - 1
         if ad_off.shape[0] != N + 1:
             raise ValueError("one associated_data per proof")
-        verdict = np.zeros(N, dtype=np.uint8)
-        parsed = np.zeros(N, dtype=np.uint8)
+        verdict = _out(out, 0, (N,), np.uint8)    # out = (verdict, parsed)
+        parsed = _out(out, 1, (N,), np.uint8)
         flags = (VID_WITH_ID if with_id else 0) | (VID_REJECT_ZERO_SIGMA if strict else 0)
         _check(lib().psb_verify_id_ser(
             self.m_pk.handle, C.c_size_t(N), _p(blob), _p(off), C.c_int(int(base64)), _p(ad_blob), _p(ad_off),
@@ -256,7 +269,7 @@ class PSVerifier:
         return verdict, parsed
 
     def el_passo_verify_id(self, proof: dict, attributes, associated_data: Sequence[bytes], service_pt,
-                           authority_pk=None, g=None, h=None, with_id: bool = True, strict: bool = False):
+                           authority_pk=None, g=None, h=None, with_id: bool = True, strict: bool = False, out=None):
         """batched el_passo_verify_id (src/ps-verifier.cc:37-138) / _without_id_retrieval (:140-212).
         proof: dict of arrays sig1, sig2, k, phi, E1, E2, c, rs (N, per, 4); attributes: per lane the
         proof's attribute list (b"" = hidden)."""
@@ -267,7 +280,7 @@ class PSVerifier:
         ad_blob, ad_off = _packed(associated_data, True)
         if off.shape[0] != N * self.m_pk.n + 1 or ad_off.shape[0] != N + 1:
             raise ValueError("attribute size does not match")
-        verdict = np.zeros(N, dtype=np.uint8)
+        verdict = np.zeros(N, dtype=np.uint8) if out is None else _out((out,), 0, (N,), np.uint8)
         z1 = np.zeros((1, G1), dtype=np.uint64)
         _check(lib().psb_verify_id(
             self.m_pk.handle, C.c_size_t(N), _p(s1), _p(_u64(proof["sig2"], G1)), _p(_u64(proof["k"], G2)),
@@ -291,16 +304,17 @@ class PSRequester:
         return PSVerifier(self.m_pk).verify(sig1, sig2, all_attributes, scalars, want_gt)
 
     @staticmethod
-    def randomize_credential(sig1, sig2, t, want_serialized: bool = False):
-        """batched randomize_credential (src/ps-requester.cc:139-148) with host-supplied t (N,4)."""
+    def randomize_credential(sig1, sig2, t, want_serialized: bool = False, out=None):
+        """batched randomize_credential (src/ps-requester.cc:139-148) with host-supplied t (N,4).
+        out = (sig1', sig2', ser): optional caller-owned output buffers (e.g. page-locked, reused across calls)."""
         ensure_init()
         s1 = _u64(sig1, G1)
         s2 = _u64(sig2, G1)
         tt = _u64(t, FR)
         N = s1.shape[0]
-        o1 = np.zeros((N, G1), dtype=np.uint64)
-        o2 = np.zeros((N, G1), dtype=np.uint64)
-        ser = np.zeros((N, CRED_SER), dtype=np.uint8) if want_serialized else None
+        o1 = _out(out, 0, (N, G1), np.uint64)
+        o2 = _out(out, 1, (N, G1), np.uint64)
+        ser = _out(out, 2, (N, CRED_SER), np.uint8) if want_serialized else None
         _check(lib().psb_randomize(C.c_size_t(N), _p(s1), _p(s2), _p(tt), _p(o1), _p(o2), _p(ser)),
                "psb_randomize")
         return (o1, o2, ser) if want_serialized else (o1, o2)
@@ -374,7 +388,8 @@ class PSSigner:
             raise ValueError("signer key needs X_secret")
         self.m_pk = pk
 
-    def el_passo_provide_id(self, A, c, rs, attributes, associated_data, u):
+    def el_passo_provide_id(self, A, c, rs, attributes, associated_data, u, out=None):
+        """out = (verdict, sig1, sig2, ser): optional caller-owned output buffers (e.g. page-locked, reused across calls)"""
         A = _u64(A, G1)
         N = A.shape[0]
         rs = np.ascontiguousarray(rs, dtype=np.uint64).reshape(N, -1, FR)
@@ -382,10 +397,10 @@ class PSSigner:
         ad_blob, ad_off = _packed(associated_data, True)
         if off.shape[0] != N * self.m_pk.n + 1 or ad_off.shape[0] != N + 1:
             raise ValueError("attribute size does not match")
-        verdict = np.zeros(N, dtype=np.uint8)
-        s1 = np.zeros((N, G1), dtype=np.uint64)
-        s2 = np.zeros((N, G1), dtype=np.uint64)
-        ser = np.zeros((N, CRED_SER), dtype=np.uint8)
+        verdict = _out(out, 0, (N,), np.uint8)
+        s1 = _out(out, 1, (N, G1), np.uint64)
+        s2 = _out(out, 2, (N, G1), np.uint64)
+        ser = _out(out, 3, (N, CRED_SER), np.uint8)
         _check(lib().psb_provide_id(self.m_pk.handle, C.c_size_t(N), _p(A), _p(_u64(c, FR)), _p(rs),
                                     C.c_size_t(rs.shape[1]), _p(blob), _p(off), _p(ad_blob), _p(ad_off),
                                     _p(_u64(u, FR)), _p(verdict), _p(s1), _p(s2), _p(ser)), "psb_provide_id")
@@ -552,6 +567,43 @@ def verify_dev(pk: PSPubKey, dev_index: int, N: int, d_sig1: int, d_sig2: int, d
     _check(lib().psb_verify_dev(pk.handle, C.c_int(dev_index), C.c_size_t(N), vp(d_sig1), vp(d_sig2), vp(d_blob),
                                 vp(d_off), vp(d_m), vp(d_verdict), vp(d_gt), vp(d_ws), vp(stream)),
            "psb_verify_dev")
+
+
+class _Pinned:
+    """owner of one psb_host_alloc block, exported through the buffer protocol (PEP 688): the arrays made from it keep
+    it alive as their base, and the block is freed with the last of them"""
+
+    def __init__(self, nbytes: int):
+        self.ptr = lib().psb_host_alloc(C.c_size_t(nbytes))
+        if not self.ptr:
+            raise PsbError("psb_host_alloc failed: " + lib().psb_last_error().decode())
+        self.buf = (C.c_uint8 * max(nbytes, 1)).from_address(self.ptr)
+
+    def __buffer__(self, flags):
+        return memoryview(self.buf)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().psb_host_free(C.c_void_p(self.ptr))
+        except Exception:  # interpreter shutdown
+            pass
+
+
+def pinned_empty(shape, dtype=np.uint8) -> np.ndarray:
+    """a page-locked host array (psb_host_alloc) for the inputs and `out=` buffers of the batched calls"""
+    ensure_init()
+    dt = np.dtype(dtype)
+    shape = (shape,) if isinstance(shape, int) else tuple(shape)
+    n = int(np.prod(shape, dtype=np.int64)) * dt.itemsize
+    return np.frombuffer(_Pinned(n), dtype=np.uint8, count=n).view(dt).reshape(shape)
+
+
+def pinned_copy(a) -> np.ndarray:
+    a = np.ascontiguousarray(a)
+    out = pinned_empty(a.shape, a.dtype)
+    out[...] = a
+    return out
 
 
 def set_profiling(on: bool) -> None:

@@ -39,6 +39,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <new>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -80,6 +81,22 @@ inline const uint64_t* u64(const void* p) { return reinterpret_cast<const uint64
 inline uint64_t* u64(void* p) { return reinterpret_cast<uint64_t*>(p); }
 
 // flat string arrays: blob + offsets[count + 1]
+// std::allocator drop-in over psb_host_alloc: std::vector<T, psb::pinned_allocator<T>> keeps a batch array in page-locked
+// memory, which the psb_* calls copy at the full PCIe rate (include/psb.h).  Needs psb::init() first.
+template <class T> struct pinned_allocator {
+  typedef T value_type;
+  pinned_allocator() = default;
+  template <class U> pinned_allocator(const pinned_allocator<U>&) {}
+  T* allocate(size_t n) {
+    void* p = psb_host_alloc(n * sizeof(T));
+    if (!p) throw std::bad_alloc();
+    return static_cast<T*>(p);
+  }
+  void deallocate(T* p, size_t) { psb_host_free(p); }
+  template <class U> bool operator==(const pinned_allocator<U>&) const { return true; }
+  template <class U> bool operator!=(const pinned_allocator<U>&) const { return false; }
+};
+
 struct Strings {
   std::vector<uint8_t> blob;
   std::vector<uint64_t> off{0};

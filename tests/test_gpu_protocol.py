@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from tests import workload
-from tests.conftest import G1_SER, bls_only
+from tests.conftest import G1_SER, G1W, bls_only
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -26,6 +26,32 @@ def test_randomize_matches_reference(gpu_pkg, ref):
     assert not o1[3].any()
     # randomized credentials still verify (reference check of GPU output)
     assert ref.ps_verify(wl.key, o1[4:], o2[4:], wl.attrs[4:]).all()
+
+
+def test_pinned_buffers_and_out_arguments(gpu_pkg, ref):
+    """psb_host_alloc / psb_host_free through the mirror (pinned_empty / pinned_copy): page-locked inputs and caller-owned,
+    reused `out=` buffers give the same bytes as fresh pageable arrays; views keep the block alive; wrong shapes are refused."""
+    wl = workload.make_verify_workload(n_attrs=2, lanes=70, seed=5)
+    ref.seed(8)
+    t = ref.fr_rand(70)
+    exp = gpu_pkg.PSRequester.randomize_credential(wl.sig1, wl.sig2, t, want_serialized=True)
+    s1, s2, tp = (gpu_pkg.pinned_copy(a) for a in (wl.sig1, wl.sig2, t))
+    out = (gpu_pkg.pinned_empty((70, G1W), np.uint64), gpu_pkg.pinned_empty((70, G1W), np.uint64), gpu_pkg.pinned_empty((70, 2 * G1_SER), np.uint8))
+    for _ in range(2):                                    # reused across calls
+        got = gpu_pkg.PSRequester.randomize_credential(s1, s2, tp, want_serialized=True, out=out)
+        assert all(g is o for g, o in zip(got, out))
+        assert all(np.array_equal(g, e) for g, e in zip(got, exp))
+    row = out[2][5]                                       # a view outlives the arrays it came from
+    del out, got
+    import gc
+    gc.collect()
+    assert np.array_equal(row, exp[2][5])
+    with pytest.raises(ValueError):
+        gpu_pkg.PSRequester.randomize_credential(s1, s2, tp, want_serialized=True, out=(np.zeros((3, G1W), np.uint64), None, None))
+    v = gpu_pkg.pinned_empty(70, np.uint8)
+    pk = gpu_pkg.PSPubKey(wl.key.g, wl.key.gg, wl.key.XX, wl.key.Y, wl.key.YY, window_bits=8)
+    assert gpu_pkg.PSVerifier(pk).verify(s1, s2, wl.attrs, out=v) is v and v.all()
+    pk.close()
 
 
 def test_randomize_seeded_reference_method(gpu_pkg, ref):
