@@ -102,6 +102,13 @@ template <class Launch> inline void for_waves(size_t n, Launch&& launch) {   // 
     LAUNCHED();                                                                                \
   })
 
+// Single-kernel entry points (randomisation, issuance) as a two-stream pipeline: the lanes of a device are cut into a few
+// chunks, chunk c runs copy-in -> kernel -> copy-out in order on stream c & 1, so the copies of one chunk overlap the kernel
+// of the other and the kernels themselves overlap at their ragged ends (no wave is lost at a chunk boundary).  The device
+// buffers hold all lanes; the chunks are disjoint slices.  Small batches stay one chunk.
+constexpr size_t kPipeMinLanes = 1 << 15;
+inline size_t pipe_chunk(size_t L) { return L < 2 * kPipeMinLanes ? L : (L + 3) / 4; }
+
 int ensure(DevBuf& b, size_t bytes) {
   if (bytes <= b.cap) return PSB_OK;
   if (b.p) cudaFree(b.p);
@@ -701,17 +708,26 @@ int psb_randomize(size_t N, const uint64_t* sig1, const uint64_t* sig2, const ui
     if ((rc = ensure(dv->in[2], L * sizeof(Fr)))) return rc;
     for (int i = 3; i < 5; i++) if ((rc = ensure(dv->in[i], L * sizeof(G1J)))) return rc;
     if (ser && (rc = ensure(dv->in[5], L * kCredSer))) return rc;
-    CK(cudaMemcpyAsync(dv->in[0].p, sig1 + b * kG1W, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(dv->in[1].p, sig2 + b * kG1W, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(dv->in[2].p, t + b * 4, L * sizeof(Fr), cudaMemcpyHostToDevice, st));
-    k_randomize<<<nblocks(L), kBlock, 0, st>>>(L, (const G1J*)dv->in[0].p, (const G1J*)dv->in[1].p, (const Fr*)dv->in[2].p,
-                                               (G1J*)dv->in[3].p, (G1J*)dv->in[4].p, ser ? (uint8_t*)dv->in[5].p : nullptr);
-    LAUNCHED();
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(out1 + b * kG1W, dv->in[3].p, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(out2 + b * kG1W, dv->in[4].p, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
-    if (ser) CK(cudaMemcpyAsync(ser + b * kCredSer, dv->in[5].p, L * kCredSer, cudaMemcpyDeviceToHost, st));
+    G1J *d1 = (G1J*)dv->in[0].p, *d2 = (G1J*)dv->in[1].p, *o1 = (G1J*)dv->in[3].p, *o2 = (G1J*)dv->in[4].p;
+    Fr* dt = (Fr*)dv->in[2].p;
+    uint8_t* dser = ser ? (uint8_t*)dv->in[5].p : nullptr;
+    const size_t chunk = pipe_chunk(L);
+    int c = 0;
+    for (size_t cb = 0; cb < L; cb += chunk, c++) {
+      const size_t cl = std::min(chunk, L - cb);
+      cudaStream_t cs = (c & 1) ? dv->copy : st;
+      CK(cudaMemcpyAsync(d1 + cb, sig1 + (b + cb) * kG1W, cl * sizeof(G1J), cudaMemcpyHostToDevice, cs));
+      CK(cudaMemcpyAsync(d2 + cb, sig2 + (b + cb) * kG1W, cl * sizeof(G1J), cudaMemcpyHostToDevice, cs));
+      CK(cudaMemcpyAsync(dt + cb, t + (b + cb) * 4, cl * sizeof(Fr), cudaMemcpyHostToDevice, cs));
+      k_randomize<<<nblocks(cl), kBlock, 0, cs>>>(cl, d1 + cb, d2 + cb, dt + cb, o1 + cb, o2 + cb, dser ? dser + cb * kCredSer : nullptr);
+      LAUNCHED();
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(out1 + (b + cb) * kG1W, o1 + cb, cl * sizeof(G1J), cudaMemcpyDeviceToHost, cs));
+      CK(cudaMemcpyAsync(out2 + (b + cb) * kG1W, o2 + cb, cl * sizeof(G1J), cudaMemcpyDeviceToHost, cs));
+      if (ser) CK(cudaMemcpyAsync(ser + (b + cb) * kCredSer, dser + cb * kCredSer, cl * kCredSer, cudaMemcpyDeviceToHost, cs));
+    }
     CK(cudaStreamSynchronize(st));
+    if (c > 1) CK(cudaStreamSynchronize(dv->copy));
     return PSB_OK;
   });
 }
@@ -862,25 +878,35 @@ int psb_provide_id(psb_key* key, size_t N, const uint64_t* A, const uint64_t* c,
       dver = ar.take<uint8_t>(L); dS1 = ar.take<G1J>(L); dS2 = ar.take<G1J>(L); dser = ar.take<uint8_t>(L * kCredSer);
       if (pass == 0) { int r = ensure(dv->arena, ar.used); if (r) return r; ar.base = (char*)dv->arena.p; }
     }
-    CK(cudaMemcpyAsync(dA, A + b * kG1W, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(dc, c + b * 4, L * sizeof(Fr), cudaMemcpyHostToDevice, st));
-    if (per) CK(cudaMemcpyAsync(drs, rs + b * per * 4, L * per * sizeof(Fr), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(du, u + b * 4, L * sizeof(Fr), cudaMemcpyHostToDevice, st));
-    if (o1 > o0) CK(cudaMemcpyAsync(dblob, attr_blob + o0, (size_t)(o1 - o0), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(doff, attr_off + b * n, (L * n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-    if (a1 > a0) CK(cudaMemcpyAsync(dad, ad_blob + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(dadoff, ad_off + b, (L + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     const KeyDev& kd = key->d[di];
     const LaneGeom lg{(int)per, (int)per, (int)n, nullptr, nullptr};
-    k_provide_id<<<nblocks(L), kBlock, 0, st>>>(L, (int)n, key->w, kd.tblG1, kd.g1pts, dA, dc, drs, lg, dblob - o0, doff,
-                                                dad - a0, dadoff, du, dver, dS1, dS2, ser ? dser : nullptr);
-    LAUNCHED();
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(verdict + b, dver, L, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(sig1 + b * kG1W, dS1, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(sig2 + b * kG1W, dS2, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
-    if (ser) CK(cudaMemcpyAsync(ser + b * kCredSer, dser, L * kCredSer, cudaMemcpyDeviceToHost, st));
+    const size_t chunk = pipe_chunk(L);     // two-stream pipeline over chunks of lanes (see pipe_chunk)
+    int ci = 0;
+    for (size_t cb = 0; cb < L; cb += chunk, ci++) {
+      const size_t cl = std::min(chunk, L - cb), g = b + cb;
+      cudaStream_t cs = (ci & 1) ? dv->copy : st;
+      const uint64_t c0 = attr_off[g * n], c1 = attr_off[(g + cl) * n], d0 = ad_off[g], d1 = ad_off[g + cl];
+      CK(cudaMemcpyAsync(dA + cb, A + g * kG1W, cl * sizeof(G1J), cudaMemcpyHostToDevice, cs));
+      CK(cudaMemcpyAsync(dc + cb, c + g * 4, cl * sizeof(Fr), cudaMemcpyHostToDevice, cs));
+      if (per) CK(cudaMemcpyAsync(drs + cb * per, rs + g * per * 4, cl * per * sizeof(Fr), cudaMemcpyHostToDevice, cs));
+      CK(cudaMemcpyAsync(du + cb, u + g * 4, cl * sizeof(Fr), cudaMemcpyHostToDevice, cs));
+      if (c1 > c0) CK(cudaMemcpyAsync(dblob + (c0 - o0), attr_blob + c0, (size_t)(c1 - c0), cudaMemcpyHostToDevice, cs));
+      // (offsets stay absolute; consecutive chunks write the shared boundary entry with the same value)
+      CK(cudaMemcpyAsync(doff + cb * n, attr_off + g * n, (cl * n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, cs));
+      if (d1 > d0) CK(cudaMemcpyAsync(dad + (d0 - a0), ad_blob + d0, (size_t)(d1 - d0), cudaMemcpyHostToDevice, cs));
+      CK(cudaMemcpyAsync(dadoff + cb, ad_off + g, (cl + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, cs));
+      k_provide_id<<<nblocks(cl), kBlock, 0, cs>>>(cl, (int)n, key->w, kd.tblG1, kd.g1pts, dA + cb, dc + cb, drs + cb * per, lg, dblob - o0,
+                                                   doff + cb * n, dad - a0, dadoff + cb, du + cb, dver + cb, dS1 + cb, dS2 + cb,
+                                                   ser ? dser + cb * kCredSer : nullptr);
+      LAUNCHED();
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(verdict + g, dver + cb, cl, cudaMemcpyDeviceToHost, cs));
+      CK(cudaMemcpyAsync(sig1 + g * kG1W, dS1 + cb, cl * sizeof(G1J), cudaMemcpyDeviceToHost, cs));
+      CK(cudaMemcpyAsync(sig2 + g * kG1W, dS2 + cb, cl * sizeof(G1J), cudaMemcpyDeviceToHost, cs));
+      if (ser) CK(cudaMemcpyAsync(ser + g * kCredSer, dser + cb * kCredSer, cl * kCredSer, cudaMemcpyDeviceToHost, cs));
+    }
     CK(cudaStreamSynchronize(st));
+    if (ci > 1) CK(cudaStreamSynchronize(dv->copy));
     return PSB_OK;
   });
 }
