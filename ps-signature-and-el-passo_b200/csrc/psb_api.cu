@@ -1193,21 +1193,32 @@ int psb_request_id(psb_key* key, size_t N, const uint8_t* attr_blob, const uint6
       dad = ar.take<uint8_t>((size_t)(a1 - a0) + 16); dadoff = ar.take<uint64_t>(L + 1); dhide = ar.take<uint8_t>(n + 16);
       if (pass == 0) { int r = ensure(dv->arena, ar.used); if (r) return r; ar.base = (char*)dv->arena.p; }
     }
-    CK(cudaMemcpyAsync(drnd, rnd + b * (h + 2) * 4, L * (h + 2) * sizeof(Fr), cudaMemcpyHostToDevice, st));
-    if (o1 > o0) CK(cudaMemcpyAsync(dblob, attr_blob + o0, (size_t)(o1 - o0), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(doff, attr_off + b * n, (L * n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-    if (a1 > a0) CK(cudaMemcpyAsync(dad, ad_blob + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(dadoff, ad_off + b, (L + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-    if (n) CK(cudaMemcpyAsync(dhide, hide, n, cudaMemcpyHostToDevice, st));
+    if (n) {   // shared by every chunk: on the device before either stream starts
+      CK(cudaMemcpyAsync(dhide, hide, n, cudaMemcpyHostToDevice, st));
+      CK(cudaStreamSynchronize(st));
+    }
     const KeyDev& kd = key->d[di];
-    k_request_id<<<nblocks(L), kBlock, 0, st>>>(L, (int)n, key->w, kd.tblG1, dhide, (int)h, dblob - o0, doff, dad - a0, dadoff,
-                                                drnd, dA, dc, drs);
-    LAUNCHED();
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(A + b * kG1W, dA, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(c + b * 4, dc, L * sizeof(Fr), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(rs + b * (h + 1) * 4, drs, L * (h + 1) * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+    const size_t chunk = pipe_chunk(L);     // two-stream pipeline over chunks of lanes (see pipe_chunk)
+    int ci = 0;
+    for (size_t cb = 0; cb < L; cb += chunk, ci++) {
+      const size_t cl = std::min(chunk, L - cb), g = b + cb;
+      cudaStream_t cs = (ci & 1) ? dv->copy : st;
+      const uint64_t c0 = attr_off[g * n], c1 = attr_off[(g + cl) * n], d0 = ad_off[g], d1 = ad_off[g + cl];
+      CK(cudaMemcpyAsync(drnd + cb * (h + 2), rnd + g * (h + 2) * 4, cl * (h + 2) * sizeof(Fr), cudaMemcpyHostToDevice, cs));
+      if (c1 > c0) CK(cudaMemcpyAsync(dblob + (c0 - o0), attr_blob + c0, (size_t)(c1 - c0), cudaMemcpyHostToDevice, cs));
+      CK(cudaMemcpyAsync(doff + cb * n, attr_off + g * n, (cl * n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, cs));
+      if (d1 > d0) CK(cudaMemcpyAsync(dad + (d0 - a0), ad_blob + d0, (size_t)(d1 - d0), cudaMemcpyHostToDevice, cs));
+      CK(cudaMemcpyAsync(dadoff + cb, ad_off + g, (cl + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, cs));
+      k_request_id<<<nblocks(cl), kBlock, 0, cs>>>(cl, (int)n, key->w, kd.tblG1, dhide, (int)h, dblob - o0, doff + cb * n, dad - a0,
+                                                   dadoff + cb, drnd + cb * (h + 2), dA + cb, dc + cb, drs + cb * (h + 1));
+      LAUNCHED();
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(A + g * kG1W, dA + cb, cl * sizeof(G1J), cudaMemcpyDeviceToHost, cs));
+      CK(cudaMemcpyAsync(c + g * 4, dc + cb, cl * sizeof(Fr), cudaMemcpyDeviceToHost, cs));
+      CK(cudaMemcpyAsync(rs + g * (h + 1) * 4, drs + cb * (h + 1), cl * (h + 1) * sizeof(Fr), cudaMemcpyDeviceToHost, cs));
+    }
     CK(cudaStreamSynchronize(st));
+    if (ci > 1) CK(cudaStreamSynchronize(dv->copy));
     return PSB_OK;
   });
 }
@@ -1304,15 +1315,23 @@ int psb_unblind(size_t N, const uint64_t* sig1, const uint64_t* sig2, const uint
     for (int i = 0; i < 2; i++) if ((rc = ensure(dv->in[i], L * sizeof(G1J)))) return rc;
     if ((rc = ensure(dv->in[2], L * sizeof(Fr)))) return rc;
     if ((rc = ensure(dv->in[3], L * sizeof(G1J)))) return rc;
-    CK(cudaMemcpyAsync(dv->in[0].p, sig1 + b * kG1W, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(dv->in[1].p, sig2 + b * kG1W, L * sizeof(G1J), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(dv->in[2].p, t1 + b * 4, L * sizeof(Fr), cudaMemcpyHostToDevice, st));
-    k_unblind<<<nblocks(L), kBlock, 0, st>>>(L, (const G1J*)dv->in[0].p, (const G1J*)dv->in[1].p, (const Fr*)dv->in[2].p,
-                                             (G1J*)dv->in[3].p);
-    LAUNCHED();
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(out2 + b * kG1W, dv->in[3].p, L * sizeof(G1J), cudaMemcpyDeviceToHost, st));
+    G1J *d1 = (G1J*)dv->in[0].p, *d2 = (G1J*)dv->in[1].p, *o2 = (G1J*)dv->in[3].p;
+    Fr* dt = (Fr*)dv->in[2].p;
+    const size_t chunk = pipe_chunk(L);     // two-stream pipeline over chunks of lanes (see pipe_chunk)
+    int ci = 0;
+    for (size_t cb = 0; cb < L; cb += chunk, ci++) {
+      const size_t cl = std::min(chunk, L - cb);
+      cudaStream_t cs = (ci & 1) ? dv->copy : st;
+      CK(cudaMemcpyAsync(d1 + cb, sig1 + (b + cb) * kG1W, cl * sizeof(G1J), cudaMemcpyHostToDevice, cs));
+      CK(cudaMemcpyAsync(d2 + cb, sig2 + (b + cb) * kG1W, cl * sizeof(G1J), cudaMemcpyHostToDevice, cs));
+      CK(cudaMemcpyAsync(dt + cb, t1 + (b + cb) * 4, cl * sizeof(Fr), cudaMemcpyHostToDevice, cs));
+      k_unblind<<<nblocks(cl), kBlock, 0, cs>>>(cl, d1 + cb, d2 + cb, dt + cb, o2 + cb);
+      LAUNCHED();
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(out2 + (b + cb) * kG1W, o2 + cb, cl * sizeof(G1J), cudaMemcpyDeviceToHost, cs));
+    }
     CK(cudaStreamSynchronize(st));
+    if (ci > 1) CK(cudaStreamSynchronize(dv->copy));
     return PSB_OK;
   });
 }

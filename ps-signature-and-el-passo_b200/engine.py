@@ -319,7 +319,7 @@ class PSRequester:
                "psb_randomize")
         return (o1, o2, ser) if want_serialized else (o1, o2)
 
-    def el_passo_request_id(self, attributes, hidden, associated_data, rnd):
+    def el_passo_request_id(self, attributes, hidden, associated_data, rnd, out=None):
         """batched el_passo_request_id (src/ps-requester.cc:19-97).  attributes: per lane ALL n values; hidden: n flags
         shared by the batch; rnd (N, h+2, 4) = t1, r0, one per hidden attribute (the reference's draw order).
         Returns A (N,18) normalised, c (N,4), rs (N,h+1,4)."""
@@ -334,21 +334,22 @@ class PSRequester:
         if off.shape[0] != N * pk.n + 1:
             raise ValueError("attribute size does not match")
         rnd = np.ascontiguousarray(rnd, dtype=np.uint64).reshape(N, h + 2, FR)
-        A = np.zeros((N, G1), dtype=np.uint64)
-        c = np.zeros((N, FR), dtype=np.uint64)
-        rs = np.zeros((N, h + 1, FR), dtype=np.uint64)
+        A = _out(out, 0, (N, G1), np.uint64)       # out = (A, c, rs)
+        c = _out(out, 1, (N, FR), np.uint64)
+        rs = _out(out, 2, (N, h + 1, FR), np.uint64)
         _check(lib().psb_request_id(pk.handle, C.c_size_t(N), _p(blob), _p(off), _p(hidden), _p(ad_blob), _p(ad_off),
                                     _p(rnd), _p(A), _p(c), _p(rs)), "psb_request_id")
         return A, c, rs
 
     @staticmethod
-    def unblind_credential(sig1, sig2, t1):
-        """batched unblind_credential (src/ps-requester.cc:99-113): (sig1, sig2 - t1 sig1); sig2 normalised."""
+    def unblind_credential(sig1, sig2, t1, out=None):
+        """batched unblind_credential (src/ps-requester.cc:99-113): (sig1, sig2 - t1 sig1); sig2 normalised.
+        out: optional caller-owned (N, G1) buffer for sig2'."""
         ensure_init()
         s1 = _u64(sig1, G1)
         s2 = _u64(sig2, G1)
         N = s1.shape[0]
-        o2 = np.zeros((N, G1), dtype=np.uint64)
+        o2 = _out((out,), 0, (N, G1), np.uint64)
         _check(lib().psb_unblind(C.c_size_t(N), _p(s1), _p(s2), _p(_u64(t1, FR)), _p(o2)), "psb_unblind")
         return s1, o2
 

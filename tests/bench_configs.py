@@ -155,6 +155,7 @@ def main():
 
     if "p" in cfgs:   # prover side: what generates cfg3 / cfg4 inputs at scale
         pw = workload.make_prover_request_workload(20, D, 2, seed=6, nthreads=threads)
+        A_W = pw.exp_A.shape[1]
         t0 = time.perf_counter()
         ref.request_id(pw.key, pw.attrs, pw.hidden, pw.ads, 6 * 1000003, threads)
         cpu_s = time.perf_counter() - t0
@@ -162,8 +163,11 @@ def main():
         rq = pkg.PSRequester(pk)
         attrs, ads, rnd = pkg.pack_attrs(pw.attrs * reps_tile), pkg.pack_strings(pw.ads * reps_tile), tile(pw.rnd, reps_tile)
         rq.el_passo_request_id(pw.attrs, pw.hidden, pw.ads, pw.rnd)
+        # page-locked inputs and caller-owned outputs (psb_host_alloc), like bench.py's EL PASSO configs
+        attrs, ads, rnd = tuple(pkg.pinned_copy(a) for a in attrs), tuple(pkg.pinned_copy(a) for a in ads), pkg.pinned_copy(rnd)
+        o_req = (pkg.pinned_empty((N, A_W), np.uint64), pkg.pinned_empty((N, 4), np.uint64), pkg.pinned_empty((N, 3, 4), np.uint64))
         l0 = pkg.launch_count()
-        (A, c, rs), dt = timed(lambda: rq.el_passo_request_id(attrs, pw.hidden, ads, rnd), args.reps)
+        (A, c, rs), dt = timed(lambda: rq.el_passo_request_id(attrs, pw.hidden, ads, rnd, out=o_req), args.reps)
         assert np.array_equal(A[-D:], ref.g1_op(ref.G_NORM, pw.exp_A)) and np.array_equal(c[:D], pw.exp_c) and \
             np.array_equal(rs[-D:], pw.exp_rs), "request_id mismatch vs reference"
         emit({"config": "prover el_passo_request_id", "n_attrs": 20, "hidden": 2, "lanes": N, "distinct": D,
@@ -175,8 +179,10 @@ def main():
         ref.unblind(pw.key, pw.attrs, pw.hidden, pw.ads, 6 * 1000003, pw.blind_sig1, pw.blind_sig2, threads)
         cpu_s = time.perf_counter() - t0
         rq.unblind_credential(b1[:D], b2[:D], t1[:D])
+        b1, b2, t1 = (pkg.pinned_copy(a) for a in (b1, b2, t1))
+        o_un = pkg.pinned_empty((N, A_W), np.uint64)
         l0 = pkg.launch_count()
-        (_, un2), dt = timed(lambda: rq.unblind_credential(b1, b2, t1), args.reps)
+        (_, un2), dt = timed(lambda: rq.unblind_credential(b1, b2, t1, out=o_un), args.reps)
         assert np.array_equal(un2[-D:], ref.g1_op(ref.G_NORM, pw.exp_unblind2)), "unblind mismatch vs reference"
         emit({"config": "prover unblind_credential", "lanes": N, "distinct": D, "metric": "credentials_unblinded_per_sec",
               "e2e_value": N / dt, "seconds": dt, "gpu_launches": pkg.launch_count() - l0,
