@@ -156,6 +156,53 @@ PSB_HD PSB_NOINL void pt_mul_window(Jac<F>& R, const Jac<F>& P, const uint32_t* 
   R = acc;
 }
 
+// ---- helpers of the variable-base multiplications: signed 4-bit windows over a table of AFFINE multiples -------------------
+// Signed radix-16 digits of a magnitude v < 2^(4 nd) (nibbles through get(i)): d_i in [-8, 8], sum d_i 16^i = v, nd + 1 digits
+// (the last one is the final carry, 0 or 1).  Halves the table (multiples 1..8) against unsigned nibbles.
+template <class Get>
+PSB_HD PSB_INL void signed_nibbles(int8_t* dig, int nd, Get get) {
+  int carry = 0;
+  for (int i = 0; i < nd; i++) {
+    int d = (int)get(i) + carry;
+    carry = d > 8;
+    dig[i] = (int8_t)(carry ? d - 16 : d);
+  }
+  dig[nd] = (int8_t)carry;
+}
+// tbl[i] = i P in affine coordinates for i = 1..8 with ONE inversion (Montgomery's trick over the z coordinates), so that the
+// 64 window additions of a multiplication are mixed additions (7M + 4S instead of 11M + 5S).  Returns a mask: bit i set <=> i P
+// is the point at infinity (P of small order -- adversarial input only -- or P itself infinite): those entries are skipped.
+template <class F>
+PSB_HD PSB_NOINL uint32_t pt_affine_multiples8(Aff<F>* tbl /*[9], [0] unused*/, const Jac<F>& P) {
+  Jac<F> J[9];
+  F pre[9];
+  J[1] = P;
+  pt_dbl(J[2], P);
+  for (int i = 3; i <= 8; i++) pt_add(J[i], J[i - 1], P);
+  uint32_t inf = 0;
+  F inv, one;
+  f_set_one(one);
+  // prefix products of the z coordinates (an infinite multiple contributes 1), written IN PLACE as in k_build_table.  (A first
+  // version kept the running product in a local, `f_mul(run, run, z); pre[i] = run;`: correct on the host build and for Fp2,
+  // but the sm_100a build for Fp copied a stale `run` into pre[i] for i >= 2 -- entries 2..8 of the table were wrong on the
+  // device only.  Found by the parity test of test op T_G1_AFFMUL; every prefix chain in this file now writes its array directly.)
+  for (int i = 1; i <= 8; i++) {
+    if (f_is_zero(J[i].z)) { inf |= 1u << i; J[i].z = one; }
+    if (i == 1) pre[1] = J[1].z; else f_mul(pre[i], pre[i - 1], J[i].z);
+  }
+  f_inv(inv, pre[8]);
+  for (int i = 8; i >= 1; i--) {
+    F zi, zi2;
+    if (i > 1) f_mul(zi, inv, pre[i - 1]); else zi = inv;
+    f_mul(inv, inv, J[i].z);
+    f_sqr(zi2, zi);
+    f_mul(tbl[i].x, J[i].x, zi2);
+    f_mul(zi2, zi2, zi);
+    f_mul(tbl[i].y, J[i].y, zi2);
+  }
+  return inf;
+}
+
 // ---- GLV (G1) and GLS (G2) variable-base multiplication -----------------------------------------------------
 // Same group element as mcl's G1::mul / G2::mul (which use the same endomorphisms with w-NAF: ec.hpp:1457-1523
 // GLV1, bn.hpp:765-860 GLV2); only the schedule is ours: fixed 4-bit joint windows, one shared table of multiples
@@ -225,23 +272,29 @@ PSB_HD PSB_INL void glv1_split(uint32_t k1[4], uint32_t k2[4], const uint32_t* k
 PSB_HD PSB_NOINL void g1_mul_glv(G1J& R, const G1J& P, const uint32_t* k) {
   uint32_t k1[4], k2[4];
   glv1_split(k1, k2, k);
-  G1J tbl[16];
-  pt_set_zero(tbl[0]);
-  tbl[1] = P;
-  pt_dbl(tbl[2], P);
-  for (int i = 3; i < 16; i++) pt_add(tbl[i], tbl[i - 1], P);
+  int8_t e1[33], e2[33];
+  signed_nibbles(e1, 32, [&](int i) { return (k1[i >> 3] >> ((i & 7) * 4)) & 0xFu; });
+  signed_nibbles(e2, 32, [&](int i) { return (k2[i >> 3] >> ((i & 7) * 4)) & 0xFu; });
+  G1A tbl[9], T;
+  const uint32_t inf = pt_affine_multiples8(tbl, P);
   Fp beta;
   for (int i = 0; i < 12; i++) beta.v[i] = PSB_K(GLV_BETA)[i];
-  G1J acc, T;
+  G1J acc;
   pt_set_zero(acc);
-  for (int i = 31; i >= 0; i--) {
-    pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc);
-    const uint32_t d1 = (k1[i >> 3] >> ((i & 7) * 4)) & 0xF, d2 = (k2[i >> 3] >> ((i & 7) * 4)) & 0xF;
-    if (d1) pt_add(acc, acc, tbl[d1]);
-    if (d2) {
-      T = tbl[d2];
+  for (int i = 32; i >= 0; i--) {
+    if (i < 32) { pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc); }
+    const int d1 = e1[i], d2 = e2[i];
+    const int a1 = d1 < 0 ? -d1 : d1, a2 = d2 < 0 ? -d2 : d2;
+    if (a1 && !((inf >> a1) & 1u)) {
+      T = tbl[a1];
+      if (d1 < 0) fp_neg(T.y, T.y);
+      pt_madd(acc, acc, T);
+    }
+    if (a2 && !((inf >> a2) & 1u)) {
+      T = tbl[a2];
       fp_mul(T.x, T.x, beta);          // phi(d2 P)
-      pt_add(acc, acc, T);
+      if (d2 < 0) fp_neg(T.y, T.y);
+      pt_madd(acc, acc, T);
     }
   }
   R = acc;
@@ -263,8 +316,8 @@ PSB_HD PSB_INL void gls_split(uint64_t d[4], const uint32_t* k) {
   d[3] = ((uint64_t)q[1] << 32) | q[0];
 }
 
-// (-1)^j psi^j(T) for a Jacobian point, j = 1..3 (constants from tools/gen_constants.py)
-PSB_HD PSB_NOINL void g2_psi_signed(G2J& T, int j) {
+// (-1)^j psi^j(T) for an AFFINE point, j = 1..3 (constants from tools/gen_constants.py)
+PSB_HD PSB_NOINL void g2_psi_signed(G2A& T, int j) {
   if (j == 2) {
     Fp n;
     for (int i = 0; i < 12; i++) n.v[i] = PSB_K(PSI_NCX)[i];
@@ -275,7 +328,7 @@ PSB_HD PSB_NOINL void g2_psi_signed(G2J& T, int j) {
   Fp2 c;
   const uint32_t* cxp = (j == 1) ? PSB_K(PSI_CX) : PSB_K(PSI_CX3);
   for (int i = 0; i < 12; i++) { c.a.v[i] = cxp[i]; c.b.v[i] = cxp[12 + i]; }
-  fp2_conj(T.x, T.x); fp2_conj(T.y, T.y); fp2_conj(T.z, T.z);
+  fp2_conj(T.x, T.x); fp2_conj(T.y, T.y);
   fp2_mul(T.x, T.x, c);
   for (int i = 0; i < 12; i++) { c.a.v[i] = PSB_K(PSI_CY)[i]; c.b.v[i] = PSB_K(PSI_CY)[12 + i]; }
   fp2_mul(T.y, T.y, c);
@@ -285,22 +338,21 @@ PSB_HD PSB_NOINL void g2_psi_signed(G2J& T, int j) {
 PSB_HD PSB_NOINL void g2_mul_gls(G2J& R, const G2J& P, const uint32_t* k) {
   uint64_t d[4];
   gls_split(d, k);
-  G2J tbl[16];
-  pt_set_zero(tbl[0]);
-  tbl[1] = P;
-  pt_dbl(tbl[2], P);
-  for (int i = 3; i < 16; i++) pt_add(tbl[i], tbl[i - 1], P);
-  G2J acc, T;
+  int8_t e[4][17];
+  for (int j = 0; j < 4; j++) signed_nibbles(e[j], 16, [&](int i) { return (uint32_t)(d[j] >> (4 * i)) & 0xFu; });
+  G2A tbl[9], T;
+  const uint32_t inf = pt_affine_multiples8(tbl, P);
+  G2J acc;
   pt_set_zero(acc);
-  for (int i = 15; i >= 0; i--) {
-    pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc);
+  for (int i = 16; i >= 0; i--) {
+    if (i < 16) { pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc); }
     for (int j = 0; j < 4; j++) {
-      const uint32_t dj = (uint32_t)(d[j] >> (4 * i)) & 0xF;
-      if (!dj) continue;
-      if (j == 0) { pt_add(acc, acc, tbl[dj]); continue; }
-      T = tbl[dj];
-      g2_psi_signed(T, j);
-      pt_add(acc, acc, T);
+      const int dj = e[j][i], aj = dj < 0 ? -dj : dj;
+      if (!aj || ((inf >> aj) & 1u)) continue;
+      T = tbl[aj];
+      if (j) g2_psi_signed(T, j);
+      if (dj < 0) fp2_neg(T.y, T.y);
+      pt_madd(acc, acc, T);
     }
   }
   R = acc;
@@ -352,36 +404,37 @@ PSB_HD PSB_NOINL void g1_mul_glv(G1J& R, const G1J& P, const uint32_t* k) {
   bool n1, n2;
   const u128 k1 = abs_s128(klo - c1 * load_u128(PSB_K(GLVBN_SA)) - c2 * load_u128(PSB_K(GLVBN_SA) + 4), n1);
   const u128 k2 = abs_s128((u128)0 - c1 * load_u128(PSB_K(GLVBN_SB)) - c2 * load_u128(PSB_K(GLVBN_SB) + 4), n2);
-  G1J tbl[16];
-  pt_set_zero(tbl[0]);
-  tbl[1] = P;
-  pt_dbl(tbl[2], P);
-  for (int i = 3; i < 16; i++) pt_add(tbl[i], tbl[i - 1], P);
+  int8_t e1[33], e2[33];
+  signed_nibbles(e1, 32, [&](int i) { return nibble_u128(k1, i); });
+  signed_nibbles(e2, 32, [&](int i) { return nibble_u128(k2, i); });
+  G1A tbl[9], T;
+  const uint32_t inf = pt_affine_multiples8(tbl, P);
   Fp beta;
   for (int i = 0; i < PSB_NL; i++) beta.v[i] = PSB_K(GLV_BETA)[i];
-  G1J acc, T;
+  G1J acc;
   pt_set_zero(acc);
-  for (int i = 31; i >= 0; i--) {
-    pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc);
-    const uint32_t d1 = nibble_u128(k1, i), d2 = nibble_u128(k2, i);
-    if (d1) {
-      T = tbl[d1];
-      if (n1) fp_neg(T.y, T.y);
-      pt_add(acc, acc, T);
+  for (int i = 32; i >= 0; i--) {
+    if (i < 32) { pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc); }
+    const int d1 = e1[i], d2 = e2[i];
+    const int a1 = d1 < 0 ? -d1 : d1, a2 = d2 < 0 ? -d2 : d2;
+    if (a1 && !((inf >> a1) & 1u)) {
+      T = tbl[a1];
+      if ((d1 < 0) != n1) fp_neg(T.y, T.y);
+      pt_madd(acc, acc, T);
     }
-    if (d2) {
-      T = tbl[d2];
+    if (a2 && !((inf >> a2) & 1u)) {
+      T = tbl[a2];
       fp_mul(T.x, T.x, beta);          // phi(d2 P)
-      if (n2) fp_neg(T.y, T.y);
-      pt_add(acc, acc, T);
+      if ((d2 < 0) != n2) fp_neg(T.y, T.y);
+      pt_madd(acc, acc, T);
     }
   }
   R = acc;
 }
 
-// psi^j(T) for a Jacobian point, j = 1..3 (D-type twist constants from tools/gen_constants.py):
+// psi^j(T) for an AFFINE point, j = 1..3 (D-type twist constants from tools/gen_constants.py):
 //   psi(x, y) = (conj(x) cx, conj(y) cy), psi^2(x, y) = (x N(cx), -y), psi^3(x, y) = (conj(x) cx3, -conj(y) cy)
-PSB_HD PSB_NOINL void g2_psi_pow(G2J& T, int j) {
+PSB_HD PSB_NOINL void g2_psi_pow(G2A& T, int j) {
   if (j == 2) {
     Fp n;
     for (int i = 0; i < PSB_NL; i++) n.v[i] = PSB_K(PSI_NCX)[i];
@@ -392,7 +445,7 @@ PSB_HD PSB_NOINL void g2_psi_pow(G2J& T, int j) {
   Fp2 c;
   const uint32_t* cxp = (j == 1) ? PSB_K(PSI_CX) : PSB_K(PSI_CX3);
   for (int i = 0; i < PSB_NL; i++) { c.a.v[i] = cxp[i]; c.b.v[i] = cxp[PSB_NL + i]; }
-  fp2_conj(T.x, T.x); fp2_conj(T.y, T.y); fp2_conj(T.z, T.z);
+  fp2_conj(T.x, T.x); fp2_conj(T.y, T.y);
   fp2_mul(T.x, T.x, c);
   for (int i = 0; i < PSB_NL; i++) { c.a.v[i] = PSB_K(PSI_CY)[i]; c.b.v[i] = PSB_K(PSI_CY)[PSB_NL + i]; }
   fp2_mul(T.y, T.y, c);
@@ -408,22 +461,21 @@ PSB_HD PSB_NOINL void g2_mul_gls(G2J& R, const G2J& P, const uint32_t* k) {
     for (int j = 0; j < 4; j++) v -= c[j] * load_u128(PSB_K(GLSBN_SB) + 4 * (4 * j + i));
     d[i] = abs_s128(v, neg[i]);
   }
-  G2J tbl[16];
-  pt_set_zero(tbl[0]);
-  tbl[1] = P;
-  pt_dbl(tbl[2], P);
-  for (int i = 3; i < 16; i++) pt_add(tbl[i], tbl[i - 1], P);
-  G2J acc, T;
+  int8_t e[4][PSB_GLS_BN_WINDOWS + 1];
+  for (int j = 0; j < 4; j++) signed_nibbles(e[j], PSB_GLS_BN_WINDOWS, [&](int i) { return nibble_u128(d[j], i); });
+  G2A tbl[9], T;
+  const uint32_t inf = pt_affine_multiples8(tbl, P);
+  G2J acc;
   pt_set_zero(acc);
-  for (int i = PSB_GLS_BN_WINDOWS - 1; i >= 0; i--) {
-    pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc);
+  for (int i = PSB_GLS_BN_WINDOWS; i >= 0; i--) {
+    if (i < PSB_GLS_BN_WINDOWS) { pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc); }
     for (int j = 0; j < 4; j++) {
-      const uint32_t dj = nibble_u128(d[j], i);
-      if (!dj) continue;
-      T = tbl[dj];
+      const int dj = e[j][i], aj = dj < 0 ? -dj : dj;
+      if (!aj || ((inf >> aj) & 1u)) continue;
+      T = tbl[aj];
       if (j) g2_psi_pow(T, j);
-      if (neg[j]) fp2_neg(T.y, T.y);
-      pt_add(acc, acc, T);
+      if ((dj < 0) != neg[j]) fp2_neg(T.y, T.y);
+      pt_madd(acc, acc, T);
     }
   }
   R = acc;
@@ -549,10 +601,9 @@ PSB_HD PSB_NOINL void aff_flush_l2(Jac<F>& acc, AffPts<F>& l) {
         bad = f_is_zero(d);
       }
       if (bad) { f_set_one(d); exc |= 1ull << i; }
-      if (i == 0) run = d; else f_mul(run, run, d);
-      l.pre[i] = run;
+      if (i == 0) l.pre[0] = d; else f_mul(l.pre[i], l.pre[i - 1], d);     // (written in place: see pt_affine_multiples8)
     }
-    f_inv(run, run);
+    f_inv(run, l.pre[np - 1]);
     for (int i = np - 1; i >= 0; i--) {
       if ((exc >> i) & 1ull) {
         if (!((l.absent >> (2 * i)) & 1ull)) pt_madd(acc, acc, l.pts[2 * i]);
@@ -598,10 +649,9 @@ PSB_HD PSB_NOINL void aff_flush(Jac<F>& acc, AffBatch<F>& b, bool last = true) {
         bad = f_is_zero(d);
       }
       if (bad) { f_set_one(d); exc |= 1ull << i; }
-      if (i == 0) run = d; else f_mul(run, run, d);
-      b.pre[i] = run;
+      if (i == 0) b.pre[0] = d; else f_mul(b.pre[i], b.pre[i - 1], d);     // (written in place: see pt_affine_multiples8)
     }
-    f_inv(run, run);                          // 1 / (d_0 ... d_{np-1})
+    f_inv(run, b.pre[np - 1]);                // 1 / (d_0 ... d_{np-1})
     for (int i = np - 1; i >= 0; i--) {
       const uint32_t da = b.desc[2 * i], db = b.desc[2 * i + 1];
       bool have = true;                       // S holds the pair sum

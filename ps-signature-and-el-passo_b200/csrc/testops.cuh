@@ -13,8 +13,8 @@ enum TestOp {
   T_FP6_MUL = 20, T_FP6_INV,
   T_FP12_MUL = 30, T_FP12_SQR, T_FP12_INV, T_FP12_FROB1, T_FP12_FROB2, T_FP12_FROB3, T_FP12_CYCLO_SQR,
   T_FP12_MUL_LINE,  // a = Fp12, b = 3 Fp2: M-type twist c0 + c2 w^2 + c3 w^3, D-type twist c0 + c1 w + c3 w^3
-  T_G1_ADD = 40, T_G1_DBL, T_G1_NORM, T_G1_MUL /* b = Fr Montgomery */, T_G1_MADD /* b = normalised G1 */,
-  T_G2_ADD = 50, T_G2_DBL, T_G2_NORM, T_G2_MUL, T_G2_MADD,
+  T_G1_ADD = 40, T_G1_DBL, T_G1_NORM, T_G1_MUL /* b = Fr Montgomery */, T_G1_MADD /* b = normalised G1 */, T_G1_AFFMUL /* b = Fr m in 1..8: entry m of pt_affine_multiples8 */,
+  T_G2_ADD = 50, T_G2_DBL, T_G2_NORM, T_G2_MUL, T_G2_MADD, T_G2_AFFMUL,
   T_PAIRING = 60,      // a = G1, b = G2 -> GT = finalExp(millerLoop(a, b))
   T_MILLER_FE_ONLY,    // a = Fp12 -> finalExp(a)
   T_PAIRING_RATIO,     // a = G1 P1, b = G2 Q1, c = G1 P2 | G2 Q2 (normalised) -> e(P1,Q1) e(P2,Q2)^-1
@@ -38,10 +38,10 @@ PSB_HD inline bool test_op_shape(int op, int s[4]) {
     case T_FP12_MUL_LINE: s[0] = s[3] = FP12; s[1] = 3 * FP2; return true;
     case T_G1_ADD: case T_G1_MADD: s[0] = s[1] = s[3] = G1; return true;
     case T_G1_DBL: case T_G1_NORM: s[0] = s[3] = G1; return true;
-    case T_G1_MUL: s[0] = s[3] = G1; s[1] = FR; return true;
+    case T_G1_MUL: case T_G1_AFFMUL: s[0] = s[3] = G1; s[1] = FR; return true;
     case T_G2_ADD: case T_G2_MADD: s[0] = s[1] = s[3] = G2; return true;
     case T_G2_DBL: case T_G2_NORM: s[0] = s[3] = G2; return true;
-    case T_G2_MUL: s[0] = s[3] = G2; s[1] = FR; return true;
+    case T_G2_MUL: case T_G2_AFFMUL: s[0] = s[3] = G2; s[1] = FR; return true;
     case T_PAIRING: s[0] = G1; s[1] = G2; s[3] = FP12; return true;
     case T_MILLER_FE_ONLY: s[0] = s[3] = FP12; return true;
     case T_PAIRING_RATIO: s[0] = G1; s[1] = G2; s[2] = G1 + G2; s[3] = FP12; return true;
@@ -112,17 +112,31 @@ PSB_HD inline void test_op_run(int op, const uint32_t* a, const uint32_t* b, con
 #endif
       }
       st(out, r); break; }
-    case T_G1_ADD: case T_G1_DBL: case T_G1_NORM: case T_G1_MUL: case T_G1_MADD: {
+    case T_G1_ADD: case T_G1_DBL: case T_G1_NORM: case T_G1_MUL: case T_G1_MADD: case T_G1_AFFMUL: {
       G1J x, y, r; ld(x, a);
-      if (op == T_G1_ADD) { ld(y, b); pt_add(r, x, y); }
+      if (op == T_G1_AFFMUL) {
+        Fr k, kn; ld(k, b); fr_from_mont(kn, k);
+        G1A t[9];
+        const uint32_t inf = pt_affine_multiples8(t, x);
+        const uint32_t m = kn.v[0] & 15u;
+        if (m < 1 || m > 8 || ((inf >> m) & 1u)) pt_set_zero(r); else pt_from_aff(r, t[m]);
+      }
+      else if (op == T_G1_ADD) { ld(y, b); pt_add(r, x, y); }
       else if (op == T_G1_DBL) pt_dbl(r, x);
       else if (op == T_G1_NORM) pt_normalize(r, x);
       else if (op == T_G1_MADD) { ld(y, b); G1A q; q.x = y.x; q.y = y.y; pt_madd(r, x, q); }
       else { Fr k, kn; ld(k, b); fr_from_mont(kn, k); pt_mul(r, x, kn.v); }
       st(out, r); break; }
-    case T_G2_ADD: case T_G2_DBL: case T_G2_NORM: case T_G2_MUL: case T_G2_MADD: {
+    case T_G2_ADD: case T_G2_DBL: case T_G2_NORM: case T_G2_MUL: case T_G2_MADD: case T_G2_AFFMUL: {
       G2J x, y, r; ld(x, a);
-      if (op == T_G2_ADD) { ld(y, b); pt_add(r, x, y); }
+      if (op == T_G2_AFFMUL) {
+        Fr k, kn; ld(k, b); fr_from_mont(kn, k);
+        G2A t[9];
+        const uint32_t inf = pt_affine_multiples8(t, x);
+        const uint32_t m = kn.v[0] & 15u;
+        if (m < 1 || m > 8 || ((inf >> m) & 1u)) pt_set_zero(r); else pt_from_aff(r, t[m]);
+      }
+      else if (op == T_G2_ADD) { ld(y, b); pt_add(r, x, y); }
       else if (op == T_G2_DBL) pt_dbl(r, x);
       else if (op == T_G2_NORM) pt_normalize(r, x);
       else if (op == T_G2_MADD) { ld(y, b); G2A q; q.x = y.x; q.y = y.y; pt_madd(r, x, q); }

@@ -95,6 +95,9 @@ def test_g1(gpu_pkg, ref, points):
     assert np.array_equal(s(gpu_pkg.test_op(40, zero, P2)), s(P2))
     assert np.array_equal(s(gpu_pkg.test_op(43, P, k)), s(ref.g1_mul(P, k)))
     assert np.array_equal(s(gpu_pkg.test_op(44, P, ref.g1_op(ref.G_NORM, P2))), s(ref.g1_op(ref.G_ADD, P, P2)))
+    # the table of affine multiples 1..8 behind G1::mul (one shared inversion), every entry, lanes with different entries per warp
+    ms = ref.fr_from_ints([1 + (i % 8) for i in range(P.shape[0])])
+    assert np.array_equal(gpu_pkg.test_op(45, P, ms), ref.g1_op(ref.G_NORM, ref.g1_mul(P, ms)))
 
 
 def test_g2(gpu_pkg, ref, points):
@@ -106,6 +109,8 @@ def test_g2(gpu_pkg, ref, points):
     assert np.array_equal(s(gpu_pkg.test_op(50, Q, Q)), s(ref.g2_op(ref.G_DBL, Q)))
     assert np.array_equal(s(gpu_pkg.test_op(53, Q, k)), s(ref.g2_mul(Q, k)))
     assert np.array_equal(s(gpu_pkg.test_op(54, Q, ref.g2_op(ref.G_NORM, Q2))), s(ref.g2_op(ref.G_ADD, Q, Q2)))
+    ms = ref.fr_from_ints([1 + (i % 8) for i in range(Q.shape[0])])
+    assert np.array_equal(gpu_pkg.test_op(55, Q, ms), ref.g2_op(ref.G_NORM, ref.g2_mul(Q, ms)))
 
 
 def test_scalar_edge_cases(gpu_pkg, ref, points):

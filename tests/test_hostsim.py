@@ -134,6 +134,19 @@ def test_glv_gls_scalar_edges(hostsim, ref):
     Q2 = ref.g2_op(ref.G_DBL, Q)
     assert np.array_equal(norm1(hop(hostsim, 43, P2, k)), ref.g1_op(ref.G_NORM, ref.g1_mul(P2, k)))
     assert np.array_equal(norm2(hop(hostsim, 53, Q2, k)), ref.g2_op(ref.G_NORM, ref.g2_mul(Q2, k)))
+    # the point at infinity (every entry of the affine table of multiples is masked out) and scalars made of the extreme signed
+    # digits: 0x8 (digit 8), 0x9 (digit -7 with a carry), 0xf (carries rippling to the extra top window)
+    zero1, zero2 = np.zeros_like(P[:3]), np.zeros_like(Q[:3])
+    assert not hop(hostsim, 43, zero1, k[-3:]).any() and not hop(hostsim, 53, zero2, k[-3:]).any()
+    # the table of affine multiples behind both multiplications (test ops 45 / 55: entry m of pt_affine_multiples8), z = 1 and z != 1
+    ms = ref.fr_from_ints(list(range(1, 9)))
+    for PP, QQ in ((P[:8], Q[:8]), (P2[:8], Q2[:8])):
+        assert np.array_equal(hop(hostsim, 45, PP, ms), ref.g1_op(ref.G_NORM, ref.g1_mul(PP, ms)))
+        assert np.array_equal(hop(hostsim, 55, QQ, ms), ref.g2_op(ref.G_NORM, ref.g2_mul(QQ, ms)))
+    pat = [int(h * 64, 16) % R for h in "89f7"] + [int("f" * 31, 16), int("8" * 32, 16), int("9" * 48, 16) % R]
+    kp = ref.fr_from_ints(pat)
+    assert np.array_equal(norm1(hop(hostsim, 43, P[:len(pat)], kp)), ref.g1_op(ref.G_NORM, ref.g1_mul(g, kp)))
+    assert np.array_equal(norm2(hop(hostsim, 53, Q[:len(pat)], kp)), ref.g2_op(ref.G_NORM, ref.g2_mul(gg, kp)))
 
 
 @bls_only
