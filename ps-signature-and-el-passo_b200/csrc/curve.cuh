@@ -172,13 +172,31 @@ PSB_HD PSB_INL void signed_nibbles(int8_t* dig, int nd, Get get) {
 // tbl[i] = i P in affine coordinates for i = 1..8 with ONE inversion (Montgomery's trick over the z coordinates), so that the
 // 64 window additions of a multiplication are mixed additions (7M + 4S instead of 11M + 5S).  Returns a mask: bit i set <=> i P
 // is the point at infinity (P of small order -- adversarial input only -- or P itself infinite): those entries are skipped.
+// A lane whose P is at infinity (a malformed wire message, a zero commitment) builds the table from a fixed finite stand-in
+// point instead and reports every multiple as infinite: otherwise it would leave pt_add early while its warp carries on, and
+// on sm_100a the lanes of such a warp read garbage stack addresses in the NEXT call (compute-sanitizer "Invalid __local__
+// read" in pt_add, psb_verify_id_ser with malformed lanes; ptxas keeps stack addresses in uniform registers across a call
+// that only part of the warp enters -- the same hazard pow_z guards against with its warp-uniform fallback).
+PSB_HD PSB_INL void pt_load_standin(Jac<Fp>& S) {
+  for (int i = 0; i < PSB_NL; i++) { S.x.v[i] = PSB_K(G1_STANDIN)[i]; S.y.v[i] = PSB_K(G1_STANDIN)[PSB_NL + i]; }
+  fp_set_one(S.z);
+}
+PSB_HD PSB_INL void pt_load_standin(Jac<Fp2>& S) {
+  for (int i = 0; i < PSB_NL; i++) {
+    S.x.a.v[i] = PSB_K(G2_STANDIN)[i]; S.x.b.v[i] = PSB_K(G2_STANDIN)[PSB_NL + i];
+    S.y.a.v[i] = PSB_K(G2_STANDIN)[2 * PSB_NL + i]; S.y.b.v[i] = PSB_K(G2_STANDIN)[3 * PSB_NL + i];
+  }
+  fp2_set_one(S.z);
+}
 template <class F>
 PSB_HD PSB_NOINL uint32_t pt_affine_multiples8(Aff<F>* tbl /*[9], [0] unused*/, const Jac<F>& P) {
   Jac<F> J[9];
   F pre[9];
+  const bool pinf = pt_is_zero(P);
   J[1] = P;
-  pt_dbl(J[2], P);
-  for (int i = 3; i <= 8; i++) pt_add(J[i], J[i - 1], P);
+  if (pinf) pt_load_standin(J[1]);            // (element-wise stores, no call under this branch)
+  pt_dbl(J[2], J[1]);
+  for (int i = 3; i <= 8; i++) pt_add(J[i], J[i - 1], J[1]);
   uint32_t inf = 0;
   F inv, one;
   f_set_one(one);
@@ -200,7 +218,7 @@ PSB_HD PSB_NOINL uint32_t pt_affine_multiples8(Aff<F>* tbl /*[9], [0] unused*/, 
     f_mul(zi2, zi2, zi);
     f_mul(tbl[i].y, J[i].y, zi2);
   }
-  return inf;
+  return pinf ? 0x1FEu : inf;
 }
 
 // ---- GLV (G1) and GLS (G2) variable-base multiplication -----------------------------------------------------
