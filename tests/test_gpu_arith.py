@@ -176,6 +176,16 @@ def test_glv_gls_scalar_edges(gpu_pkg, ref):
     Q = ref.g2_op(ref.G_DBL, np.repeat(gg.reshape(1, -1), len(ks), axis=0))
     assert np.array_equal(ref.g1_serialize(gpu_pkg.test_op(43, P, k)), ref.g1_serialize(ref.g1_mul(P, k)))
     assert np.array_equal(ref.g2_serialize(gpu_pkg.test_op(53, Q, k)), ref.g2_serialize(ref.g2_mul(Q, k)))
+    # lanes holding the point at infinity MIXED with ordinary lanes in the same warps (they build their table of multiples from a
+    # stand-in point and must not disturb their neighbours), and scalars made of the extreme signed digits
+    pat = [int(h * 64, 16) % GROUP_R for h in "89f7"] + [int("f" * 31, 16), int("8" * 32, 16), int("9" * 48, 16) % GROUP_R]
+    kp = ref.fr_from_ints((pat * 10)[:64])
+    P, Q = P[:1].repeat(64, axis=0).copy(), Q[:1].repeat(64, axis=0).copy()
+    P[::3] = 0
+    Q[1::4] = 0
+    got1, got2 = gpu_pkg.test_op(42, gpu_pkg.test_op(43, P, kp)), gpu_pkg.test_op(52, gpu_pkg.test_op(53, Q, kp))
+    assert np.array_equal(got1, ref.g1_op(ref.G_NORM, ref.g1_mul(P, kp))) and not got1[::3].any()
+    assert np.array_equal(got2, ref.g2_op(ref.G_NORM, ref.g2_mul(Q, kp))) and not got2[1::4].any()
 
 
 def test_fp_inv_divsteps_edges_gpu(gpu_pkg, ref):
