@@ -148,8 +148,10 @@ PSB_HD PSB_NOINL void pt_mul_window(Jac<F>& R, const Jac<F>& P, const uint32_t* 
   for (int i = 3; i < 16; i++) pt_add(tbl[i], tbl[i - 1], P);
   Jac<F> acc;
   pt_set_zero(acc);
-  for (int i = 63; i >= 0; i--) {
-    pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc);
+  int top = 63;                                 // leading zero windows are skipped (the one caller passes a constant: the
+  while (top > 0 && ((k[top >> 3] >> ((top & 7) * 4)) & 0xF) == 0) top--;   // 126-bit G1 cofactor -- half the doublings)
+  for (int i = top; i >= 0; i--) {
+    if (i != top) { pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc); }
     const uint32_t d = (k[i >> 3] >> ((i & 7) * 4)) & 0xF;
     if (d) pt_add(acc, acc, tbl[d]);
   }
