@@ -88,3 +88,44 @@ def test_cfg4_issuance_20_attributes_2p14_then_randomize(gpu_pkg, ref):
     assert np.array_equal(rser[j], exp_ser)
     assert np.array_equal(o1[j], ref.g1_op(ref.G_NORM, r1)) and np.array_equal(o2[j], ref.g1_op(ref.G_NORM, r2))
     pk.close()
+
+
+def test_pipelined_entry_points_across_chunk_boundaries(gpu_pkg, ref):
+    """psb_provide_id / psb_randomize / psb_request_id / psb_unblind cut a batch of >= 2^16 lanes into four chunks that run as a
+    two-stream copy / compute pipeline (csrc/psb_api.cu, pipe_chunk).  A reference-checked workload of 1 024 distinct lanes is
+    tiled 80 times (81 920 lanes: chunks of 20 480 lanes, so every chunk boundary falls INSIDE a tile) with page-locked buffers and
+    caller-owned outputs: tile 0 must equal the reference and every other tile must equal tile 0, byte for byte."""
+    D, reps, n, nh = 1024, 80, 6, 2
+    N = D * reps
+    tile = lambda a: np.ascontiguousarray(np.tile(a, (reps,) + (1,) * (a.ndim - 1)))  # noqa: E731
+    same = lambda a: np.array_equal(a.reshape(reps, D, -1), np.broadcast_to(a[:D].reshape(1, D, -1), (reps, D, a[:D].size // D)))  # noqa: E731
+    wl = workload.make_issuance_workload(n, D, nh, seed=71, tamper_every=37)
+    pk = gpu_pkg.PSPubKey(wl.key.g, wl.key.gg, wl.key.XX, wl.key.Y, wl.key.YY, X_secret=wl.key.X, window_bits=12)
+    ev, e1, e2, eser = workload.expected_provide_id(wl)
+    A, c, rs, u = (gpu_pkg.pinned_copy(tile(a)) for a in (wl.A, wl.c, wl.rs, wl.u))
+    attrs, ads = gpu_pkg.pack_attrs(wl.req_attrs * reps), gpu_pkg.pack_strings(wl.ads * reps)
+    G1W = wl.A.shape[1]
+    out = (gpu_pkg.pinned_empty(N, np.uint8), gpu_pkg.pinned_empty((N, G1W), np.uint64), gpu_pkg.pinned_empty((N, G1W), np.uint64),
+           gpu_pkg.pinned_empty((N, eser.shape[1]), np.uint8))
+    v, s1, s2, ser = gpu_pkg.PSSigner(pk).el_passo_provide_id(A, c, rs, attrs, ads, u, out=out)
+    ok = ev.astype(bool)
+    assert np.array_equal(v[:D], ev) and np.array_equal(ser[:D][ok], eser[ok]) and 0 < ok.sum() < D
+    assert same(v) and same(s1) and same(s2) and same(ser)
+    # randomisation of the issued credentials
+    ref.seed(72)
+    t = ref.fr_rand(D)
+    o1, o2, rser = gpu_pkg.PSRequester.randomize_credential(s1, s2, gpu_pkg.pinned_copy(tile(t)), want_serialized=True)
+    _, _, exp_ser = ref.randomize(np.ascontiguousarray(s1[:D][ok]), np.ascontiguousarray(s2[:D][ok]), np.ascontiguousarray(t[ok]))
+    assert np.array_equal(rser[:D][ok], exp_ser) and same(o1) and same(o2) and same(rser)
+    pk.close()
+    # prover side: request_id and unblind
+    pw = workload.make_prover_request_workload(n, D, nh, seed=73)
+    pk = gpu_pkg.PSPubKey(pw.key.g, pw.key.gg, pw.key.XX, pw.key.Y, pw.key.YY, window_bits=12)
+    rq = gpu_pkg.PSRequester(pk)
+    A2, c2, rs2 = rq.el_passo_request_id(gpu_pkg.pack_attrs(pw.attrs * reps), pw.hidden, gpu_pkg.pack_strings(pw.ads * reps),
+                                         gpu_pkg.pinned_copy(tile(pw.rnd)))
+    assert np.array_equal(A2[:D], ref.g1_op(ref.G_NORM, pw.exp_A)) and np.array_equal(c2[:D], pw.exp_c) and np.array_equal(rs2[:D], pw.exp_rs)
+    assert same(A2) and same(c2) and same(rs2)
+    _, un2 = rq.unblind_credential(tile(pw.blind_sig1), tile(pw.blind_sig2), tile(pw.rnd[:, 0].copy()))
+    assert np.array_equal(un2[:D], ref.g1_op(ref.G_NORM, pw.exp_unblind2)) and same(un2)
+    pk.close()
