@@ -76,11 +76,6 @@ inline void init(const std::vector<int>& devices = {}) {
                  (int)devices.size()), "psb_init");
 }
 
-namespace detail {
-inline const uint64_t* u64(const void* p) { return reinterpret_cast<const uint64_t*>(p); }
-inline uint64_t* u64(void* p) { return reinterpret_cast<uint64_t*>(p); }
-
-// flat string arrays: blob + offsets[count + 1]
 // std::allocator drop-in over psb_host_alloc: std::vector<T, psb::pinned_allocator<T>> keeps a batch array in page-locked
 // memory, which the psb_* calls copy at the full PCIe rate (include/psb.h).  Needs psb::init() first.
 template <class T> struct pinned_allocator {
@@ -97,6 +92,11 @@ template <class T> struct pinned_allocator {
   template <class U> bool operator!=(const pinned_allocator<U>&) const { return false; }
 };
 
+namespace detail {
+inline const uint64_t* u64(const void* p) { return reinterpret_cast<const uint64_t*>(p); }
+inline uint64_t* u64(void* p) { return reinterpret_cast<uint64_t*>(p); }
+
+// flat string arrays: blob + offsets[count + 1]
 struct Strings {
   std::vector<uint8_t> blob;
   std::vector<uint64_t> off{0};

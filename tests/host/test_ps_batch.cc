@@ -33,6 +33,11 @@ int main(int argc, char** argv) {
     std::printf("psb::init failed (no CPU fallback): %s\n", e.what());
     return 3;
   }
+  {  // page-locked batch arrays through the std::allocator drop-in (psb_host_alloc / psb_host_free)
+    std::vector<uint64_t, psb::pinned_allocator<uint64_t>> pinned(1 << 16, 7);
+    pinned.resize(1 << 17);
+    EXPECT(pinned[0] == 7 && pinned[(1 << 16) - 1] == 7 && pinned[(1 << 17) - 1] == 0);
+  }
   G1 g, authority_pk, h;
   G2 gg;
   hashAndMapToG1(g, "abc");
