@@ -132,6 +132,23 @@ def msm_ops(n_attrs: int, window_bits: int, levels: int = MSM_AFFINE_LEVELS):
     return fpmul, (mul, 0, dot2, st["inv"])
 
 
+def hbm_line(alg_bytes_per_lane: float, lanes_per_s: float, dom_traffic, dom_ms: float) -> dict:
+    """the HBM side of the roofline: algorithmic bytes against the driver-measured copy bandwidth (MEASURED_PEAKS.json, else
+    the profiling recipe's fallback), and the DRAM rate of the dominant kernel from the committed ncu capture"""
+    peak, src = 6457.0, "B200_PROFILING.md fallback (measured copy bandwidth of this pool)"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak, src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        pass
+    out = {"algorithmic_bytes_per_lane": alg_bytes_per_lane, "achieved_GBps": alg_bytes_per_lane * lanes_per_s / 1e9,
+           "peak_GBps": peak, "peak_source": src, "frac": alg_bytes_per_lane * lanes_per_s / 1e9 / peak}
+    if dom_traffic:
+        out["dominant_kernel_dram_GBps_ncu"] = dom_traffic / (dom_ms * 1e-3) / 1e9   # thread-local spill traffic, not algorithmic
+        out["dominant_kernel_dram_frac_of_peak"] = out["dominant_kernel_dram_GBps_ncu"] / peak
+    return out
+
+
 def exec_mac32(ops) -> int:
     return int(sum(c * m for c, m in zip(ops, EXEC_MAC32)))
 TRAFFIC_FILE = "r2w_traffic.json"   # latest committed ncu DRAM-traffic capture (profiles/)
@@ -960,8 +977,7 @@ def main():
                      "peak_carry_chain_source": "measured live (IMAD.WIDE.U32.X carry-chain rows, the multiplier's instruction form)",
                      "whole_step_frac": whole / peak_mac,
                      "phase_ms": dict(zip(names, [float(x) for x in phase])),
-                     "hbm": {"algorithmic_bytes_per_lane": h2d / N + 1 + 864 * 2,
-                             "achieved_GBps": (h2d / N + 1 + 864 * 2) * value / world / 1e9}},
+                     "hbm": hbm_line(h2d / N + 1 + 864 * 2, value / world, traffic, phase[dom])},
     }
     if configs:
         line["configs"] = configs
